@@ -1,0 +1,193 @@
+"""ctypes binding of oracle/_ref/libmercury_ref.so -- TEST INFRASTRUCTURE ONLY.
+
+The .so is the UNMODIFIED reference physical layer (compiled by oracle/Makefile from
+/root/reference) plus oracle/ref_driver.cc.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py may import this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libmercury_ref.so")
+
+GEOM_FIELDS = [
+    "Nsymb", "Nc", "Nfft", "Ngi", "Nofdm", "nData", "nPilots", "nBits", "N", "K", "P", "M",
+    "preamble_nSymb", "frame_bytes", "estimator", "amp_restore", "bit_il_block", "tf_il_block",
+    "interp_rate", "buffer_Nsymb", "total_frame_size", "Cwidth", "Vwidth", "dwidth", "ldpc_iters",
+    "outer_reserved", "ls_win_h", "ls_win_w",
+]
+
+RATE_OF_CONFIG = {0: 1, 1: 2, 2: 3, 3: 4, 4: 5, 5: 6, 6: 8, 7: 5, 8: 6, 9: 8, 10: 6, 11: 8, 12: 14, 13: 8, 14: 14, 15: 14, 16: 14}
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+class _RxOut(C.Structure):
+    _fields_ = [
+        ("Y", C.c_void_p), ("H", C.c_void_p), ("Z", C.c_void_p), ("llr_demod", C.c_void_p),
+        ("llr_cw", C.c_void_p), ("bits", C.c_void_p), ("bytes", C.c_void_p), ("payload", C.c_void_p),
+        ("stats", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/libmercury_ref.so not built (make -C oracle ref; needs /root/reference)")
+        L = C.CDLL(_SO)
+        L.mref_create.restype = C.c_void_p
+        L.mref_create.argtypes = [C.c_int, C.c_int]
+        L.mref_destroy.argtypes = [C.c_void_p]
+        L.mref_geometry.argtypes = [C.c_void_p, C.c_void_p]
+        L.mref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.mref_ldpc_tables.argtypes = [C.c_int] + [C.c_void_p] * 5
+        L.mref_ldpc_tables.restype = C.c_int
+        L.mref_random.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+        L.mref_crc16.argtypes = [C.c_void_p, C.c_int]
+        L.mref_crc16.restype = C.c_int
+        L.mref_tx_baseband.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.mref_rx_tail.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mref_rx_tail_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mref_rx_tail_timed.restype = C.c_double
+        L.mref_ldpc_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mref_ldpc_decode.restype = C.c_int
+        L.mref_transmit_byte.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mref_transmit_byte.restype = C.c_int
+        L.mref_receive_byte.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def ref_random(seed, n):
+    out = np.zeros(n, np.int32)
+    lib().mref_random(seed, n, _p(out))
+    return out
+
+
+def ref_crc16(data):
+    a = np.asarray(list(data), np.int32)
+    return lib().mref_crc16(_p(a), len(a))
+
+
+def ldpc_tables(rate_num):
+    """-> dict(C[P,Cw], V[N,Vw], d[dw], Enc[P,Cw-1]) as held by the reference."""
+    dims = np.zeros(3, np.int32)
+    assert lib().mref_ldpc_tables(rate_num, _p(dims), None, None, None, None) == 0
+    Cw, Vw, dw = (int(x) for x in dims)
+    N, K = 1600, 100 * rate_num
+    P = N - K
+    Cm = np.zeros((P, Cw), np.int32)
+    Vm = np.zeros((N, Vw), np.int32)
+    d = np.zeros(dw, np.int32)
+    E = np.zeros((P, Cw - 1), np.int32)
+    lib().mref_ldpc_tables(rate_num, _p(dims), _p(Cm), _p(Vm), _p(d), _p(E))
+    return dict(C=Cm, V=Vm, d=d, Enc=E, N=N, K=K, P=P)
+
+
+class Ref:
+    """One reference cl_telecom_system loaded with CONFIG_<config> and -I <ldpc_iters>."""
+
+    def __init__(self, config, ldpc_iters=50):
+        self.h = lib().mref_create(config, ldpc_iters)
+        self.config = config
+        g = np.zeros(64, np.int32)
+        lib().mref_geometry(self.h, _p(g))
+        self.geom = {k: int(g[i]) for i, k in enumerate(GEOM_FIELDS)}
+        self.__dict__.update(self.geom)
+        self.nReal = self.nBits - self.P
+        self.nVirtual = self.N - self.nBits
+
+    def close(self):
+        if self.h:
+            lib().mref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tables(self):
+        ct = np.zeros(self.Nsymb * self.Nc, np.int32)
+        ps = np.zeros(self.nPilots, np.float64)
+        sc = np.zeros(self.N, np.int32)
+        co = np.zeros(2 * self.M, np.float64)
+        boost = np.zeros(1, np.float64)
+        lib().mref_tables(self.h, _p(ct), _p(ps), _p(sc), _p(co), _p(boost))
+        return dict(carrier_type=ct.reshape(self.Nsymb, self.Nc), pilot_seq=ps, scrambler=sc,
+                    constellation=co.view(np.complex128), pilot_boost=float(boost[0]))
+
+    def tx_baseband(self, payload, want_aux=False):
+        pl = np.asarray(list(payload), np.int32)
+        out = np.zeros(self.Nsymb * self.Nofdm, np.complex128)
+        info = np.zeros(self.nReal, np.int32)
+        cw = np.zeros(self.N, np.int32)
+        framed = np.zeros(self.Nsymb * self.Nc, np.complex128)
+        lib().mref_tx_baseband(self.h, _p(pl), len(pl), _p(out), _p(info), _p(cw), _p(framed))
+        if want_aux:
+            return out, dict(info_bits=info, codeword=cw, framed=framed.reshape(self.Nsymb, self.Nc))
+        return out
+
+    def rx_tail(self, baseband):
+        bb = np.ascontiguousarray(baseband, np.complex128).reshape(-1)
+        assert bb.size == self.Nsymb * self.Nofdm
+        cells = self.Nsymb * self.Nc
+        r = dict(
+            Y=np.zeros(cells, np.complex128), H=np.zeros(cells, np.complex128), Z=np.zeros(cells, np.complex128),
+            llr_demod=np.zeros(self.nBits, np.float32), llr_cw=np.zeros(self.N, np.float32),
+            bits=np.zeros(self.K, np.int32), bytes=np.zeros(self.nReal // 8, np.int32),
+            payload=np.zeros(self.frame_bytes, np.int32), stats=np.zeros(8, np.float64),
+        )
+        o = _RxOut(*[_p(r[k]) for k in ("Y", "H", "Z", "llr_demod", "llr_cw", "bits", "bytes", "payload", "stats")])
+        lib().mref_rx_tail(self.h, _p(bb), C.byref(o))
+        st = r.pop("stats")
+        r.update(iterations=int(st[0]), crc=int(st[1]), all_zeros=int(st[2]), decoded=int(st[3]), snr=float(st[4]),
+                 variance=np.float32(st[5]), mean_H=float(st[7]))
+        for k in ("Y", "H", "Z"):
+            r[k] = r[k].reshape(self.Nsymb, self.Nc)
+        return r
+
+    def rx_tail_timed(self, baseband_batch):
+        bb = np.ascontiguousarray(baseband_batch, np.complex128)
+        n = bb.size // (self.Nsymb * self.Nofdm)
+        pay = np.zeros((n, self.frame_bytes), np.int32)
+        dec = np.zeros(n, np.int32)
+        its = np.zeros(n, np.int32)
+        secs = lib().mref_rx_tail_timed(self.h, _p(bb), n, _p(pay), _p(dec), _p(its))
+        return secs, pay, dec, its
+
+    def ldpc_decode(self, llr_cw):
+        l = np.ascontiguousarray(llr_cw, np.float32)
+        bits = np.zeros(self.K, np.int32)
+        it = lib().mref_ldpc_decode(self.h, _p(l), _p(bits))
+        return it, bits
+
+    def transmit_byte(self, payload):
+        pl = np.asarray(list(payload), np.int32)
+        out = np.zeros(self.total_frame_size + 16, np.float64)
+        n = lib().mref_transmit_byte(self.h, _p(pl), len(pl), _p(out))
+        return out[:n]
+
+    def receive_byte(self, passband):
+        n = self.Nofdm * self.buffer_Nsymb * self.interp_rate
+        pb = np.ascontiguousarray(passband, np.float64)
+        assert pb.size == n, (pb.size, n)
+        out = np.zeros(self.frame_bytes, np.int32)
+        st = np.zeros(8, np.float64)
+        bb = np.zeros((self.Nsymb + self.preamble_nSymb) * self.Nofdm, np.complex128)
+        lib().mref_receive_byte(self.h, _p(pb), _p(out), _p(st), _p(bb))
+        return dict(payload=out, iterations=int(st[0]), crc=int(st[1]), all_zeros=int(st[2]), decoded=int(st[3]),
+                    snr=float(st[4]), delay=int(st[5]), sync_trials=int(st[6]), freq_offset=float(st[7]), baseband=bb)
