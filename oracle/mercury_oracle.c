@@ -1,0 +1,823 @@
+/*
+ * oracle/mercury_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked into, or called by, the product).
+ *
+ * Plain-C (C11 + C99 complex), double-precision CPU restatement of the Mercury physical-layer RX hot
+ * path and of the TX chain that synthesises its inputs.  All paths below are relative to
+ * /root/reference/ (Rhizomatica/mercury @ c91aa4b).  Operation order follows the reference so that,
+ * compiled by the same gcc without FMA contraction, results are bit-identical to oracle/_ref
+ * (tests/test_oracle_vs_ref.py); complex products / quotients use C99 `double complex`, which gcc
+ * lowers to the same libgcc helpers as std::complex<double>.
+ *
+ * Parity status: PINNED -- against the unmodified reference (oracle/_ref, this container) and against
+ * the committed fixtures in tests/golden/ that were generated from it (tests/golden/make_golden.py).
+ */
+#define _GNU_SOURCE
+#include "mercury_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * PRNG: glibc random() TYPE_3, as vendored in source/common/os_interop.cc:100-283 (__srandom/__random).
+ * Restated in its textbook form: additive lagged Fibonacci r[i] = r[i-3] + r[i-31] (mod 2^32), seeded by
+ * the Park-Miller LCG (16807, Schrage's method), first 310 outputs discarded, output = r >> 1.
+ * seed 0 is replaced by 1 (os_interop.cc:252-253).
+ * ---------------------------------------------------------------------------------------------- */
+static uint32_t g_rng[34];
+static int g_rng_i;
+
+void mo_srandom(unsigned seed)
+{
+	int32_t r[34];
+	if (seed == 0) seed = 1;
+	r[0] = (int32_t)seed;
+	for (int i = 1; i < 31; i++) {
+		long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+		long w = 16807 * lo - 2836 * hi;
+		if (w < 0) w += 2147483647;
+		r[i] = (int32_t)w;
+	}
+	for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+	for (int i = 0; i < 34; i++) g_rng[i] = (uint32_t)r[i];
+	g_rng_i = 0;
+	for (int i = 34; i < 344; i++) (void)mo_random();
+}
+
+int mo_random(void)
+{
+	/* ring of 34: slot i holds r[n], r[n-31] is slot (i+3)%34, r[n-3] is slot (i+31)%34 */
+	uint32_t v = g_rng[(g_rng_i + 3) % 34] + g_rng[(g_rng_i + 31) % 34];
+	g_rng[g_rng_i] = v;
+	g_rng_i = (g_rng_i + 1) % 34;
+	return (int)(v >> 1);
+}
+
+void mo_random_seq(unsigned seed, int n, int *out)
+{
+	mo_srandom(seed);
+	for (int i = 0; i < n; i++) out[i] = mo_random();
+}
+
+/* CRC-16/MODBUS: source/physical_layer/crc16_modbus_rtu.cc:25-45 (init 0xFFFF, reflected poly 0xA001). */
+int mo_crc16(const int *bytes, int n)
+{
+	uint16_t crc = 0xffff;
+	for (int j = 0; j < n; j++) {
+		crc ^= (uint16_t)(bytes[j] & 0xFF);
+		for (int i = 0; i < 8; i++) crc = (crc & 1) ? (uint16_t)((crc >> 1) ^ 0xA001) : (uint16_t)(crc >> 1);
+	}
+	return crc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Mode table: source/physical_layer/telecom_system.cc:2506-2624 (CONFIG_0..16), Nsymb by modulation
+ * :1818-1826 (HIGH_DENSITY, the compiled default physical_config.cc:48), phase-only flag :2647-2654.
+ * ---------------------------------------------------------------------------------------------- */
+static const struct { int M, rate, pre, est; } k_modes[17] = {
+	{2, 1, 4, 1},  {2, 2, 4, 1},  {2, 3, 4, 1},  {2, 4, 4, 1},  {2, 5, 4, 1},  {2, 6, 4, 1},
+	{2, 8, 4, 1},  {4, 5, 4, 1},  {4, 6, 4, 1},  {4, 8, 4, 1},  {8, 6, 3, 1},  {8, 8, 3, 1},
+	{4, 14, 3, 1}, {16, 8, 2, 1}, {8, 14, 2, 1}, {16, 14, 2, 0}, {32, 14, 1, 0},
+};
+
+static int nsymb_of(int M)
+{
+	switch (M) {
+	case 2: return 48;
+	case 4: return 24;
+	case 8: return 16;
+	case 16: return 12;
+	case 32: return 9;
+	case 64: return 8;
+	}
+	return 0;
+}
+
+/* Constellations: source/physical_layer/psk.cc:65-226, unit mean power normalisation :229-256
+ * (the normaliser is accumulated and kept in *float*, :231,245-248). */
+static void build_constellation(mo_mode *m)
+{
+	static const signed char q16[16][2] = {{-3, 3}, {-3, 1}, {-3, -3}, {-3, -1}, {-1, 3}, {-1, 1}, {-1, -3}, {-1, -1},
+					       {3, 3},	{3, 1},	 {3, -3},  {3, -1},  {1, 3},  {1, 1},  {1, -3},	 {1, -1}};
+	static const signed char q32[32][2] = {{-3, 5}, {-1, 5}, {-3, -5}, {-1, -5}, {-5, 3}, {-5, 1}, {-5, -3}, {-5, -1},
+					       {-1, 3}, {-1, 1}, {-1, -3}, {-1, -1}, {-3, 3}, {-3, 1}, {-3, -3}, {-3, -1},
+					       {3, 5},	{1, 5},	 {3, -5},  {1, -5},  {5, 3},  {5, 1},  {5, -3},	 {5, -1},
+					       {1, 3},	{1, 1},	 {1, -3},  {1, -1},  {3, 3},  {3, 1},  {3, -3},	 {3, -1}};
+	double complex *c = m->constellation;
+	double h = sqrt(2.0) / 2.0;
+	if (m->M == 2) {
+		c[0] = 1;
+		c[1] = -1;
+	} else if (m->M == 4) {
+		c[0] = -1 + 1 * I;
+		c[1] = -1 - 1 * I;
+		c[2] = 1 + 1 * I;
+		c[3] = 1 - 1 * I;
+	} else if (m->M == 8) {
+		c[0] = (-1 - 1 * I) * h;
+		c[1] = -1;
+		c[2] = 1 * I;
+		c[3] = (-1 + 1 * I) * h;
+		c[4] = -1 * I;
+		c[5] = (1 - 1 * I) * h;
+		c[6] = (1 + 1 * I) * h;
+		c[7] = 1;
+	} else if (m->M == 16) {
+		for (int i = 0; i < 16; i++) c[i] = q16[i][0] + q16[i][1] * I;
+	} else if (m->M == 32) {
+		for (int i = 0; i < 32; i++) c[i] = q32[i][0] + q32[i][1] * I;
+	}
+	float pn = 0;
+	for (int i = 0; i < m->M; i++) pn += creal(c[i]) * creal(c[i]) + cimag(c[i]) * cimag(c[i]);
+	pn = 1 / (sqrt(pn / m->M));
+	for (int i = 0; i < m->M; i++) c[i] *= pn;
+}
+
+/* Pilot lattice: cl_pilot_configurator::configure, source/physical_layer/ofdm.cc:976-1064 with the
+ * defaults Dx=1 (telecom_system.cc:1838-1846), Dy=3 (:1848-1858), all edge options DATA, last_col AUTO
+ * (physical_config.cc:40-46).  Pilot DBPSK sequence: ofdm.cc:940-951, seed 0 (physical_config.cc:47). */
+static void build_pilots(mo_mode *m)
+{
+	enum { DATA = 0, PILOT = 1 };
+	int Dx = 1, Dy = 3;
+	int ncm = m->Nc > m->Nsymb ? m->Nc : m->Nsymb;
+	unsigned char *v = calloc((size_t)ncm * ncm, 1);
+	int x = 0, y = 0;
+	while (x < ncm && y < ncm) {
+		for (int j = y; j < ncm; j += Dy) v[j * ncm + x] = PILOT;
+		for (int j = y; j >= 0; j -= Dy) v[j * ncm + x] = PILOT;
+		y++;
+		x += Dx;
+	}
+	int cnt = 0;
+	for (int j = 0; j < m->Nsymb; j++) cnt += v[j * ncm + m->Nc - 1] == PILOT;
+	if (cnt < 2) /* last_col AUTO_SELLECT -> COPY_FIRST_COL (ofdm.cc:1004-1007,1031-1034) */
+		for (int j = 0; j < ncm; j++) v[j * ncm + m->Nc - 1] = v[j * ncm + 0];
+	m->nPilots = 0;
+	m->nData = m->Nc * m->Nsymb;
+	for (int j = 0; j < m->Nsymb; j++)
+		for (int i = 0; i < m->Nc; i++) {
+			m->is_pilot[j * m->Nc + i] = v[j * ncm + i] == PILOT;
+			if (v[j * ncm + i] == PILOT) {
+				m->nPilots++;
+				m->nData--;
+			}
+		}
+	free(v);
+	mo_srandom(0);
+	int last = 0, k = 0;
+	for (int c = 0; c < m->Nsymb * m->Nc; c++) {
+		m->pilot_val[c] = 0;
+		if (!m->is_pilot[c]) continue;
+		int pv = (mo_random() % 2) ^ last;
+		m->pilot_val[c] = (double)(2 * pv - 1) * m->boost;
+		last = pv;
+		k++;
+	}
+}
+
+/* FFT tables: cl_ofdm::init_fft_tables, source/physical_layer/ofdm.cc:256-290. */
+static void build_fft_tables(mo_mode *m)
+{
+	int n = MO_NFFT;
+	for (int k = 0; k < n / 2; k++) {
+		double angle = -2.0 * M_PI * k / n;
+		m->twiddle[k] = cos(angle) + sin(angle) * I;
+	}
+	for (int i = 0; i < n; i++) {
+		int rev = 0;
+		for (int j = 0; j < 8; j++)
+			if (i & (1 << j)) rev |= 1 << (7 - j);
+		m->bitrev[i] = rev;
+	}
+}
+
+/* LDPC tables from mercury_b200/data/ldpc_tables.bin (format: tools/extract_ldpc_tables.py), rebuilt into
+ * the reference's QCmatrixC / QCmatrixV layout (mercury_normal_*_16.cc) and V_pos (ldpc_decoder_SPA.cc:81-104). */
+static int load_ldpc(mo_mode *m, const char *path)
+{
+	FILE *f = fopen(path, "rb");
+	if (!f) return -1;
+	unsigned char hdr[12];
+	if (fread(hdr, 1, 12, f) != 12 || memcmp(hdr, "MLDP", 4) != 0) {
+		fclose(f);
+		return -2;
+	}
+	uint32_t nrates;
+	memcpy(&nrates, hdr + 8, 4);
+	int rc = -3;
+	for (uint32_t r = 0; r < nrates; r++) {
+		uint16_t h[6];
+		uint32_t ne;
+		if (fread(h, 2, 6, f) != 6 || fread(&ne, 4, 1, f) != 1) break;
+		int N = h[1], P = h[3], Cw = h[4], Vw = h[5];
+		uint16_t *cdeg = malloc(2 * P), *ev = malloc(2 * ne), *vdeg = malloc(2 * N), *vc = malloc(2 * ne);
+		int ok = fread(cdeg, 2, P, f) == (size_t)P && fread(ev, 2, ne, f) == ne && fread(vdeg, 2, N, f) == (size_t)N &&
+			 fread(vc, 2, ne, f) == ne;
+		if (ok && h[0] == m->rate_num) {
+			m->Cwidth = Cw;
+			m->Vwidth = Vw;
+			m->n_edges = (int)ne;
+			m->C = malloc(sizeof(int) * P * Cw);
+			m->V = malloc(sizeof(int) * N * Vw);
+			m->Vpos = malloc(sizeof(int) * P * Cw);
+			m->vdeg = malloc(sizeof(int) * N);
+			for (int i = 0; i < P * Cw; i++) m->C[i] = -1;
+			for (int i = 0; i < N * Vw; i++) m->V[i] = -1;
+			int e = 0;
+			for (int c = 0; c < P; c++)
+				for (int j = 0; j < cdeg[c]; j++) m->C[c * Cw + j] = ev[e++];
+			e = 0;
+			for (int v = 0; v < N; v++) {
+				m->vdeg[v] = vdeg[v];
+				for (int j = 0; j < vdeg[v]; j++) m->V[v * Vw + j] = vc[e++];
+			}
+			for (int c = 0; c < P; c++)
+				for (int j = 0; j < Cw; j++) {
+					int v = m->C[c * Cw + j], pos = -1;
+					if (v != -1)
+						for (int k = 0; k < Vw; k++)
+							if (m->V[v * Vw + k] == c) {
+								pos = k;
+								break;
+							}
+					m->Vpos[c * Cw + j] = pos;
+				}
+			rc = 0;
+		}
+		free(cdeg);
+		free(ev);
+		free(vdeg);
+		free(vc);
+		if (!ok || rc == 0) break;
+	}
+	fclose(f);
+	return rc;
+}
+
+/* cl_telecom_system::load_configuration(int) + init(): source/physical_layer/telecom_system.cc:2487-3025, 1804-1982. */
+int mo_mode_init(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_path)
+{
+	if (config < 0 || config > 16) return -1;
+	memset(m, 0, sizeof(*m));
+	m->config = config;
+	m->M = k_modes[config].M;
+	m->rate_num = k_modes[config].rate;
+	m->preamble_nSymb = k_modes[config].pre;
+	m->estimator = k_modes[config].est;
+	m->phase_only = (m->M == 2 || m->M == 4 || m->M == 8);
+	m->bits_per_symbol = (int)log2(m->M);
+	m->Nsymb = nsymb_of(m->M);
+	m->Nc = MO_NC;
+	m->Nfft = MO_NFFT;
+	m->Ngi = MO_NGI;
+	m->Nofdm = MO_NOFDM;
+	m->boost = (double)1.33f;	       /* physical_config.cc:46; stored in a float (ofdm.h) */
+	m->ls_window = 21;		       /* 20 -> odd 21, telecom_system.cc:2799-2809 */
+	m->ldpc_iters = ldpc_iters;	       /* physical_config.cc:74 / main.cc:547-575 */
+	m->N = MO_N;
+	m->K = (int)((float)m->N * ((float)m->rate_num / 16.0f)); /* ldpc.cc:66 */
+	m->P = m->N - m->K;
+	build_pilots(m);
+	m->nBits = m->nData * m->bits_per_symbol;  /* data_container.cc:90-172 */
+	m->nReal = m->nBits - m->P;
+	m->nVirtual = m->N - m->nBits;
+	m->frame_bytes = (m->nReal - 16) / 8;	   /* telecom_system.cc:332-335 (outer_code_reserved_bits = 16) */
+	m->bit_il_block = m->nBits / 10;	   /* telecom_system.cc:2910 */
+	m->tf_il_block = m->nData / 10;		   /* telecom_system.cc:2911 */
+	build_constellation(m);
+	build_fft_tables(m);
+	mo_srandom(0);				   /* telecom_system.cc:1961-1966 */
+	for (int i = 0; i < m->N; i++) m->scrambler[i] = mo_random() % 2;
+	return load_ldpc(m, ldpc_blob_path);
+}
+
+void mo_mode_free(mo_mode *m)
+{
+	free(m->C);
+	free(m->V);
+	free(m->Vpos);
+	free(m->vdeg);
+	m->C = m->V = m->Vpos = m->vdeg = NULL;
+}
+
+mo_mode *mo_mode_new(int config, int ldpc_iters, const char *ldpc_blob_path)
+{
+	mo_mode *m = malloc(sizeof(mo_mode));
+	if (mo_mode_init(m, config, ldpc_iters, ldpc_blob_path) != 0) {
+		free(m);
+		return NULL;
+	}
+	return m;
+}
+
+void mo_mode_delete(mo_mode *m)
+{
+	if (m) {
+		mo_mode_free(m);
+		free(m);
+	}
+}
+
+void mo_geometry(const mo_mode *m, int *g)
+{
+	int v[28] = {m->Nsymb, m->Nc, m->Nfft, m->Ngi, m->Nofdm, m->nData, m->nPilots, m->nBits, m->N, m->K, m->P, m->M,
+		     m->preamble_nSymb, m->frame_bytes, m->estimator, m->phase_only, m->bit_il_block, m->tf_il_block,
+		     4, 0, 0, m->Cwidth, m->Vwidth, 0, m->ldpc_iters, 16, m->ls_window, m->ls_window};
+	memcpy(g, v, sizeof(v));
+}
+
+void mo_tables(const mo_mode *m, int *carrier_type, double *pilot_seq, int *scrambler, double *constellation, double *boost)
+{
+	int k = 0;
+	for (int c = 0; c < m->Nsymb * m->Nc; c++) {
+		if (carrier_type) carrier_type[c] = m->is_pilot[c] ? 1 /*PILOT*/ : 0 /*DATA*/;
+		if (m->is_pilot[c]) {
+			if (pilot_seq) pilot_seq[k] = m->pilot_val[c];
+			k++;
+		}
+	}
+	if (scrambler) memcpy(scrambler, m->scrambler, sizeof(int) * m->N);
+	if (constellation)
+		for (int i = 0; i < m->M; i++) {
+			constellation[2 * i] = creal(m->constellation[i]);
+			constellation[2 * i + 1] = cimag(m->constellation[i]);
+		}
+	if (boost) *boost = m->boost;
+}
+
+void mo_ldpc_tables(const mo_mode *m, int *dims, int *C, int *V, int *d, int *Enc)
+{
+	dims[0] = m->Cwidth;
+	dims[1] = m->Vwidth;
+	if (C) memcpy(C, m->C, sizeof(int) * m->P * m->Cwidth);
+	if (V) memcpy(V, m->V, sizeof(int) * m->N * m->Vwidth);
+	int nd = 0;
+	for (int i = 0; i < m->N;) { /* QCmatrixd = run-length of variable degrees */
+		int j = i;
+		while (j < m->N && m->vdeg[j] == m->vdeg[i]) j++;
+		if (d) {
+			d[nd] = j - i;
+			d[nd + 1] = m->vdeg[i];
+		}
+		nd += 2;
+		i = j;
+	}
+	dims[2] = nd;
+	if (Enc) /* QCmatrixEnc[i] = QCmatrixC[i] without the check's own parity bit K+i */
+		for (int c = 0; c < m->P; c++) {
+			int k = 0;
+			for (int j = 0; j < m->Cwidth - 1; j++) Enc[c * (m->Cwidth - 1) + j] = -1;
+			for (int j = 0; j < m->Cwidth; j++) {
+				int v = m->C[c * m->Cwidth + j];
+				if (v != -1 && v != m->K + c) Enc[c * (m->Cwidth - 1) + k++] = v;
+			}
+		}
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FFT: cl_ofdm::_fft_fast / _ifft_fast, source/physical_layer/ofdm.cc:310-377 (iterative radix-2 DIT,
+ * bit-reversal table, twiddle table); fft() scales by 1/N (:431-444), ifft() does not (:489-496).
+ * ---------------------------------------------------------------------------------------------- */
+static void fft_core(const mo_mode *m, double complex *v, int inverse)
+{
+	int n = MO_NFFT;
+	for (int i = 0; i < n; i++)
+		if (i < m->bitrev[i]) {
+			double complex t = v[i];
+			v[i] = v[m->bitrev[i]];
+			v[m->bitrev[i]] = t;
+		}
+	for (int size = 2; size <= n; size *= 2) {
+		int half = size / 2, step = n / size;
+		for (int i = 0; i < n; i += size)
+			for (int j = 0; j < half; j++) {
+				double complex w = inverse ? conj(m->twiddle[j * step]) : m->twiddle[j * step];
+				double complex t = w * v[i + j + half];
+				v[i + j + half] = v[i + j] - t;
+				v[i + j] = v[i + j] + t;
+			}
+	}
+}
+
+/* cl_ofdm::symbol_demod = gi_remover + fft + zero_depadder: ofdm.cc:862-867, 423-429, 431-444, 401-411 (start_shift=1). */
+static void symbol_demod(const mo_mode *m, const double complex *in, double complex *out)
+{
+	double complex v[MO_NFFT];
+	for (int j = 0; j < MO_NFFT; j++) v[j] = in[j + MO_NGI];
+	fft_core(m, v, 0);
+	for (int i = 0; i < MO_NFFT; i++) v[i] = v[i] / (double)MO_NFFT;
+	for (int j = 0; j < MO_NC / 2; j++) out[j] = v[j + MO_NFFT - MO_NC / 2];
+	for (int j = MO_NC / 2; j < MO_NC; j++) out[j] = v[j - MO_NC / 2 + 1];
+}
+
+/* cl_ofdm::symbol_mod = zero_padder + ifft + gi_adder: ofdm.cc:855-860, 379-400, 489-496, 412-422. */
+static void symbol_mod(const mo_mode *m, const double complex *in, double complex *out)
+{
+	double complex v[MO_NFFT];
+	for (int j = 0; j < MO_NFFT; j++) v[j] = 0;
+	for (int j = 0; j < MO_NC / 2; j++) v[j + MO_NFFT - MO_NC / 2] = in[j];
+	for (int j = MO_NC / 2; j < MO_NC; j++) v[j - MO_NC / 2 + 1] = in[j];
+	fft_core(m, v, 1);
+	for (int j = 0; j < MO_NFFT; j++) out[j + MO_NGI] = v[j];
+	for (int j = 0; j < MO_NGI; j++) out[j] = v[j + MO_NFFT - MO_NGI];
+}
+
+/* interleaver / deinterleaver: source/physical_layer/interleaver.cc:26-109. Index maps only. */
+static int il_src(int i, int n, int bs) /* interleaver: out[dst] = in[i]  -> returns dst */
+{
+	int nb = n / bs;
+	if (i >= nb * bs) return i;
+	return (i % bs) * nb + i / bs;
+}
+
+/* cl_ldpc::encode: source/physical_layer/ldpc.cc:111-132 (IRA accumulate through QCmatrixEnc). */
+void mo_ldpc_encode(const mo_mode *m, const int *data, int *enc)
+{
+	for (int i = 0; i < m->K; i++) enc[i] = data[i];
+	for (int i = 0; i < m->P; i++) {
+		int b = 0;
+		for (int j = 0; j < m->Cwidth; j++) {
+			int v = m->C[i * m->Cwidth + j];
+			if (v != -1 && v != m->K + i) b ^= enc[v];
+		}
+		enc[i + m->K] = b;
+	}
+}
+
+/* TX: transmit_byte/transmit_bit bit chain (telecom_system.cc:342-416) + baseband modulation chain of
+ * baseband_test_EsN0 (telecom_system.cc:129-137); psk.mod psk.cc:259-272; framer ofdm.cc:814-835. */
+void mo_tx_baseband(const mo_mode *m, const int *payload, int nBytes, double complex *out, int *info_bits, int *codeword,
+		    double complex *framed_out)
+{
+	int bytes[MO_N / 8 + 8], bit[MO_N], scr[MO_N], enc[MO_N], il[MO_N];
+	double complex mod[MO_N], tf[MO_N], framed[MO_MAX_CELLS];
+	int fs = m->frame_bytes;
+	for (int i = 0; i < fs; i++) bytes[i] = i < nBytes ? (payload[i] & 0xFF) : 0;
+	for (int i = 0; i < fs; i++) /* byte_to_bit, misc.cc:93-105: LSB first */
+		for (int j = 0; j < 8; j++) bit[i * 8 + j] = (bytes[i] >> j) & 1;
+	int crc = mo_crc16(bytes, fs);
+	for (int j = 0; j < 8; j++) bit[fs * 8 + j] = ((crc & 0xff) >> j) & 1;
+	for (int j = 0; j < 8; j++) bit[(fs + 1) * 8 + j] = ((crc >> 8) >> j) & 1;
+	for (int i = fs * 8 + 16; i < m->nReal; i++) bit[i] = 0;
+	if (info_bits) memcpy(info_bits, bit, sizeof(int) * m->nReal);
+	for (int i = 0; i < m->nReal; i++) scr[i] = bit[i] ^ m->scrambler[i]; /* interleaver.cc:111-117 */
+	for (int i = 0; i < m->nVirtual; i++) scr[m->nReal + i] = scr[i];
+	mo_ldpc_encode(m, scr, enc);
+	if (codeword) memcpy(codeword, enc, sizeof(int) * m->N);
+	for (int i = 0; i < m->P; i++) enc[m->nReal + i] = enc[i + m->K];
+	for (int i = 0; i < m->nBits; i++) il[il_src(i, m->nBits, m->bit_il_block)] = enc[i];
+	int b = m->bits_per_symbol;
+	for (int i = 0; i < m->nBits; i += b) {
+		unsigned loc = 0;
+		for (int j = 0; j < b; j++) loc = (loc << 1) | (unsigned)il[i + j];
+		mod[i / b] = m->constellation[loc];
+	}
+	for (int i = 0; i < m->nData; i++) tf[il_src(i, m->nData, m->tf_il_block)] = mod[i];
+	int di = 0;
+	for (int c = 0; c < m->Nsymb * m->Nc; c++) framed[c] = m->is_pilot[c] ? m->pilot_val[c] : tf[di++];
+	if (framed_out) memcpy(framed_out, framed, sizeof(double complex) * m->Nsymb * m->Nc);
+	for (int s = 0; s < m->Nsymb; s++) symbol_mod(m, framed + s * m->Nc, out + s * m->Nofdm);
+}
+
+/* interpolate_linear(complex): source/physical_layer/interpolator.cc:34-41. */
+static double complex lerp(double complex a, double ax, double complex b, double bx, double x)
+{
+	return a + (b - a) * (x - ax) / (bx - ax);
+}
+
+/* interpolate_linear_col(st_channel_complex*): source/physical_layer/interpolator.cc:163-254. */
+static void interp_col(double complex *H, unsigned char *st, int ncol, int nrow, int col)
+{
+	int ls = 0, le = nrow - 1, nloc = nrow - 1;
+	while (nloc > 0) {
+		for (int i = ls; i < nrow; i++)
+			if (st[i * ncol + col] == 1) {
+				ls = i;
+				break;
+			}
+		for (int i = ls + 1; i < nrow; i++)
+			if (st[i * ncol + col] == 1) {
+				le = i;
+				break;
+			}
+		nloc = le - ls;
+		for (int i = ls + 1; i < le; i++) {
+			H[i * ncol + col] = lerp(H[ls * ncol + col], ls, H[le * ncol + col], le, i);
+			st[i * ncol + col] = 2;
+		}
+		ls = le;
+	}
+	ls = 0;
+	le = nrow - 1;
+	for (int i = 0; i < nrow; i++)
+		if (st[i * ncol + col] == 1) {
+			ls = i;
+			break;
+		}
+	for (int i = ls + 1; i < nrow; i++)
+		if (st[i * ncol + col] == 1) {
+			le = i;
+			break;
+		}
+	if (ls != 0)
+		for (int i = 0; i < ls; i++) {
+			H[i * ncol + col] = lerp(H[ls * ncol + col], ls, H[le * ncol + col], le, i);
+			st[i * ncol + col] = 2;
+		}
+	le = 0;
+	ls = nrow - 1;
+	for (int i = nrow - 1; i >= 0; i--)
+		if (st[i * ncol + col] == 1) {
+			le = i;
+			break;
+		}
+	for (int i = le - 1; i >= 0; i--)
+		if (st[i * ncol + col] == 1) {
+			ls = i;
+			break;
+		}
+	if (le != nrow - 1)
+		for (int i = nrow - 1; i > le; i--) {
+			H[i * ncol + col] = lerp(H[ls * ncol + col], ls, H[le * ncol + col], le, i);
+			st[i * ncol + col] = 2;
+		}
+}
+
+/* get_angle: source/physical_layer/misc.cc:34-56 (pi/2 whenever the real part is exactly 0). */
+static double get_angle(double complex v)
+{
+	double re = creal(v), im = cimag(v);
+	if (re == 0) return M_PI / 2;
+	if (re > 0) return atan(im / re);
+	if (im >= 0) return atan(im / re) + M_PI;
+	return atan(im / re) - M_PI;
+}
+
+/* decode_SPA: source/physical_layer/ldpc_decoder_SPA.cc:25-218 (flooding tanh/atanh BP in double). */
+int mo_ldpc_decode(const mo_mode *m, const float *LLRi, int *LLRo)
+{
+	int N = m->N, P = m->P, K = m->K, Cw = m->Cwidth, Vw = m->Vwidth;
+	static _Thread_local double R[MO_N * 16], Q[MO_N * 16], LLRtmp[MO_N];
+	static _Thread_local int LLRbin[MO_N];
+	int iteration = 0, nOnes = 0;
+	for (int i = 0; i < N; i++) {
+		for (int j = 0; j < Vw; j++) R[i * Vw + j] = Q[i * Vw + j] = 0;
+		LLRbin[i] = LLRi[i] < 0;
+		LLRtmp[i] = LLRi[i];
+	}
+	for (int i = 0; i < P; i++) { /* :62-76 initial syndrome */
+		int c = LLRbin[m->C[i * Cw]];
+		for (int j = 1; j < Cw; j++)
+			if (m->C[i * Cw + j] != -1) c ^= LLRbin[m->C[i * Cw + j]];
+		nOnes += c;
+	}
+	if (nOnes != 0) {
+		for (int i = 0; i < N; i++) /* :106-122 Q init over the first deg(v) slots */
+			for (int j = 0; j < m->vdeg[i]; j++) Q[i * Vw + j] = LLRi[i];
+		for (iteration = 1; iteration <= m->ldpc_iters; iteration++) {
+			for (int ci = 0; ci < P; ci++) /* :129-160 check update */
+				for (int cj = 0; cj < Cw; cj++) {
+					int j = m->C[ci * Cw + cj];
+					if (j == -1) continue;
+					double temp = 1;
+					for (int k = 0; k < Cw; k++) {
+						int i1 = m->C[ci * Cw + k];
+						if (i1 != j && i1 != -1) temp *= tanh(0.5 * Q[i1 * Vw + m->Vpos[ci * Cw + k]]);
+					}
+					if (temp == 1) temp = 0.9999999;
+					if (temp == -1) temp = -0.9999999;
+					R[j * Vw + m->Vpos[ci * Cw + cj]] = 2 * atanh(temp);
+				}
+			for (int i = 0; i < N; i++) { /* :162-170 posterior */
+				LLRtmp[i] = LLRi[i];
+				for (int j = 0; j < Vw; j++) LLRtmp[i] += R[i * Vw + j];
+				LLRbin[i] = LLRtmp[i] < 0;
+			}
+			nOnes = 0; /* :173-190 syndrome + early exit */
+			for (int i = 0; i < P; i++) {
+				int c = LLRbin[m->C[i * Cw]];
+				for (int j = 1; j < Cw; j++)
+					if (m->C[i * Cw + j] != -1) c ^= LLRbin[m->C[i * Cw + j]];
+				nOnes += c;
+			}
+			if (nOnes == 0) break;
+			for (int i = 0; i < N; i++) /* :193-209 */
+				for (int j = 0; j < m->vdeg[i]; j++) Q[i * Vw + j] = LLRtmp[i] - R[i * Vw + j];
+		}
+	}
+	for (int i = 0; i < K; i++) LLRo[i] = LLRtmp[i] < 0;
+	return iteration;
+}
+
+/* The RX tail: source/physical_layer/telecom_system.cc:1132-1341 (+ success bookkeeping :1343-1375). */
+void mo_rx_tail(const mo_mode *m, const double complex *bb, mo_rx_out *o)
+{
+	int S = m->Nsymb, C = m->Nc, cells = S * C;
+	double complex Y[MO_MAX_CELLS], H[MO_MAX_CELLS], Hna[MO_MAX_CELLS], Z[MO_MAX_CELLS], Zna[MO_MAX_CELLS];
+	unsigned char st[MO_MAX_CELLS];
+	double complex defr[MO_N], tfd[MO_N];
+	float llr[MO_N], llr_cw[MO_N + 8];
+	int bits[MO_N], bytes[MO_N / 8 + 1];
+
+	for (int s = 0; s < S; s++) symbol_demod(m, bb + (size_t)s * m->Nofdm, Y + s * C); /* :1135-1138 */
+
+	/* automatic_gain_control: ofdm.cc:1467-1498; get_amplitude misc.cc:58-63 */
+	double amp = 0;
+	int np = 0;
+	for (int c = 0; c < cells; c++)
+		if (m->is_pilot[c]) {
+			amp += sqrt(creal(Y[c]) * creal(Y[c]) + cimag(Y[c]) * cimag(Y[c]));
+			np++;
+		}
+	amp /= np;
+	double agc = m->boost / amp;
+	for (int c = 0; c < cells; c++) Y[c] *= agc;
+	if (o->Y) memcpy(o->Y, Y, sizeof(double complex) * cells);
+
+	for (int c = 0; c < cells; c++) {
+		H[c] = 0;
+		st[c] = 0;
+	}
+	if (m->estimator == 0) { /* ZF_channel_estimator: ofdm.cc:1266-1285 */
+		for (int c = 0; c < cells; c++)
+			if (m->is_pilot[c]) {
+				H[c] = Y[c] / (double complex)(m->pilot_val[c] + 0.0 * I);
+				st[c] = 1;
+			}
+	} else { /* LS_channel_estimator: ofdm.cc:1315-1422; matrix_multiplication misc.cc:73-91 */
+		int hw = m->ls_window / 2;
+		for (int j = 0; j < C; j++)
+			for (int i = 0; i < S; i++) {
+				if (!m->is_pilot[i * C + j]) continue;
+				double complex x[512], y[512];
+				int n = 0;
+				for (int k = i - hw; k <= i + hw; k++) {
+					if (k < 0 || k >= S) continue;
+					for (int l = j - hw; l <= j + hw; l++) {
+						if (l < 0 || l >= C) continue;
+						if (m->is_pilot[k * C + l]) {
+							x[n] = m->pilot_val[k * C + l];
+							y[n] = Y[k * C + l];
+							n++;
+						}
+					}
+				}
+				double complex ch = 0;
+				for (int k = 0; k < n; k++) ch += x[k] * x[k];
+				ch = 1.0 / ch;
+				for (int k = 0; k < n; k++) x[k] *= ch;
+				double complex acc = 0;
+				for (int k = 0; k < n; k++) acc += x[k] * y[k];
+				H[i * C + j] = acc;
+				st[i * C + j] = 1;
+			}
+	}
+	for (int j = 0; j < C; j++) interp_col(H, st, C, S, j); /* Dx = 1: every column (ofdm.cc:1287-1297,1425-1435) */
+
+	double hsum = 0;
+	int hm = 0; /* mean |H| at pilots, telecom_system.cc:1225-1244 */
+	for (int c = 0; c < cells; c++)
+		if (st[c] == 1) {
+			hsum += cabs(H[c]);
+			hm++;
+		}
+	double mean_H = hm ? hsum / hm : -1.0;
+
+	if (m->phase_only) { /* restore_channel_amplitude: ofdm.cc:1453-1466; set_complex misc.cc:65-71 */
+		for (int c = 0; c < cells; c++) {
+			Hna[c] = H[c];
+			double th = get_angle(H[c]);
+			H[c] = 1 * cos(th) + (1 * sin(th)) * I;
+		}
+		for (int c = 0; c < cells; c++) Zna[c] = Y[c] / Hna[c]; /* ofdm.cc:1648-1657 */
+	}
+	if (o->H) memcpy(o->H, H, sizeof(double complex) * cells);
+	for (int c = 0; c < cells; c++) Z[c] = Y[c] / H[c]; /* channel_equalizer: ofdm.cc:1637-1647 */
+	if (o->Z) memcpy(o->Z, Z, sizeof(double complex) * cells);
+
+	/* measure_variance: ofdm.cc:1500-1521 -> float (telecom_system.cc:649,1291) */
+	double var = 0;
+	np = 0;
+	for (int c = 0; c < cells; c++)
+		if (m->is_pilot[c]) {
+			double complex d = Z[c] - m->pilot_val[c];
+			var += creal(d) * creal(d) + cimag(d) * cimag(d);
+			np++;
+		}
+	var /= (double)np;
+	float variance = (float)var;
+
+	int di = 0; /* deframer: ofdm.cc:837-852 */
+	for (int c = 0; c < cells; c++)
+		if (!m->is_pilot[c]) defr[di++] = Z[c];
+	{ /* deinterleaver(complex): interleaver.cc:94-109 */
+		int bs = m->tf_il_block, nb = m->nData / bs;
+		for (int i = 0; i < nb; i++)
+			for (int j = 0; j < bs; j++) tfd[i * bs + j] = defr[j * nb + i];
+		for (int i = nb * bs; i < m->nData; i++) tfd[i] = defr[i];
+	}
+	{ /* cl_psk::demod: psk.cc:278-326 */
+		int b = m->bits_per_symbol;
+		float D[64], L[8];
+		for (int i = 0; i < m->nBits; i += b) {
+			double complex z = tfd[i / b];
+			for (int j = 0; j < m->M; j++) {
+				double dr = creal(z) - creal(m->constellation[j]), dq = cimag(z) - cimag(m->constellation[j]);
+				D[j] = dr * dr + dq * dq;
+			}
+			unsigned mask = 1;
+			for (int k = 0; k < b; k++) {
+				float d0 = D[0], d1 = D[mask];
+				for (int j = 0; j < m->M; j++) {
+					if ((j & mask) == 0) {
+						if (D[j] < d0) d0 = D[j];
+					} else if (D[j] < d1)
+						d1 = D[j];
+				}
+				L[k] = ((1 / variance) * (d1 - d0));
+				mask <<= 1;
+			}
+			for (int j = 0; j < b; j++) llr[i + j] = L[b - j - 1];
+		}
+	}
+	if (o->llr_demod) memcpy(o->llr_demod, llr, sizeof(float) * m->nBits);
+	{ /* deinterleaver(float): interleaver.cc:77-92, then LLR expand telecom_system.cc:1300-1308 */
+		int bs = m->bit_il_block, nb = m->nBits / bs;
+		for (int i = 0; i < nb; i++)
+			for (int j = 0; j < bs; j++) llr_cw[i * bs + j] = llr[j * nb + i];
+		for (int i = nb * bs; i < m->nBits; i++) llr_cw[i] = llr[i];
+		for (int i = m->P - 1; i >= 0; i--) llr_cw[i + m->nReal + m->nVirtual] = llr_cw[i + m->nReal];
+		for (int i = 0; i < m->nVirtual; i++) llr_cw[m->nReal + i] = llr_cw[i];
+	}
+	if (o->llr_cw) memcpy(o->llr_cw, llr_cw, sizeof(float) * m->N);
+
+	int iterations = mo_ldpc_decode(m, llr_cw, bits); /* :1310 */
+	if (o->bits) memcpy(o->bits, bits, sizeof(int) * m->K);
+	for (int i = 0; i < m->nReal; i++) bits[i] ^= m->scrambler[i]; /* :1313 */
+	for (int i = 0; i < m->nReal / 8; i++) {		       /* bit_to_byte misc.cc:107-130 */
+		bytes[i] = 0;
+		for (int j = 0; j < 8; j++) bytes[i] |= bits[i * 8 + j] << j;
+	}
+	int all_zeros = 1; /* :1319-1327 */
+	for (int i = 0; i < m->nReal / 8; i++)
+		if (bytes[i] != 0) {
+			all_zeros = 0;
+			break;
+		}
+	if (o->bytes) memcpy(o->bytes, bytes, sizeof(int) * (m->nReal / 8));
+	if (o->payload) memcpy(o->payload, bytes, sizeof(int) * m->frame_bytes);
+	int crc = 0;
+	if (!all_zeros) crc = mo_crc16(bytes, m->nReal / 8); /* :1337-1341 */
+	int decoded = !(all_zeros || crc != 0);		     /* :1343-1349 */
+	double snr = -99.9;
+	if (decoded) {
+		if (m->estimator == 1) { /* :1368-1375 */
+			float v = variance;
+			if (m->phase_only) {
+				double vv = 0;
+				int n2 = 0;
+				for (int c = 0; c < cells; c++)
+					if (m->is_pilot[c]) {
+						double complex d = Zna[c] - m->pilot_val[c];
+						vv += creal(d) * creal(d) + cimag(d) * cimag(d);
+						n2++;
+					}
+				v = (float)(vv / (double)n2);
+			}
+			snr = 10.0 * log10(1.0 / v);
+		} else
+			snr = 0.0; /* ZF SNR (re-encode path, :1376-1400) is outside the exported record */
+	}
+	if (o->stats) {
+		o->stats[0] = iterations;
+		o->stats[1] = crc;
+		o->stats[2] = all_zeros;
+		o->stats[3] = decoded;
+		o->stats[4] = snr;
+		o->stats[5] = variance;
+		o->stats[6] = 0;
+		o->stats[7] = mean_H;
+	}
+}
+
+double mo_rx_tail_timed(const mo_mode *m, const double complex *bb, int n_frames, int *payloads, int *decoded, int *iterations)
+{
+	struct timespec t0, t1;
+	double st[8];
+	size_t stride = (size_t)m->Nsymb * m->Nofdm;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int f = 0; f < n_frames; f++) {
+		mo_rx_out o;
+		memset(&o, 0, sizeof(o));
+		o.stats = st;
+		o.payload = payloads ? payloads + (size_t)f * m->frame_bytes : NULL;
+		mo_rx_tail(m, bb + f * stride, &o);
+		if (decoded) decoded[f] = (int)st[3];
+		if (iterations) iterations[f] = (int)st[0];
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -1,0 +1,81 @@
+/*
+ * oracle/mercury_oracle.h -- TEST INFRASTRUCTURE ONLY (never linked into, or called by, the product).
+ *
+ * Plain-C, double-precision CPU restatement of the Mercury physical-layer RX hot path
+ * (reference: source/physical_layer/telecom_system.cc:1132-1341 and its callees) plus the TX bit /
+ * modulation chain needed to synthesise inputs.  Every function in mercury_oracle.c cites the
+ * reference file:line it follows.  Pinned against the unmodified reference (oracle/_ref) and the
+ * golden fixtures in tests/golden/ by tests/test_oracle_*.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py may use it.
+ */
+#ifndef MERCURY_ORACLE_H
+#define MERCURY_ORACLE_H
+
+#include <complex.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#error "plain C only"
+#endif
+
+#define MO_N 1600
+#define MO_NC 50
+#define MO_NFFT 256
+#define MO_NGI 16
+#define MO_NOFDM 272
+#define MO_MAX_CELLS (48 * MO_NC)
+
+typedef struct mo_mode {
+	int config, M, bits_per_symbol, rate_num;
+	int Nsymb, Nc, Nfft, Ngi, Nofdm, nData, nPilots, nBits;
+	int N, K, P, nReal, nVirtual, preamble_nSymb, frame_bytes;
+	int estimator;	 /* 0 = ZERO_FORCE, 1 = LEAST_SQUARE */
+	int phase_only;	 /* channel_estimator_amplitude_restoration == YES */
+	int ldpc_iters, bit_il_block, tf_il_block, ls_window;
+	double boost;
+	unsigned char is_pilot[MO_MAX_CELLS];
+	double pilot_val[MO_MAX_CELLS];
+	double complex constellation[64];
+	int scrambler[MO_N];
+	int Cwidth, Vwidth, n_edges;
+	int *C;	   /* [P][Cwidth], -1 padded   (QCmatrixC)   */
+	int *V;	   /* [N][Vwidth], -1 padded   (QCmatrixV)   */
+	int *Vpos; /* [P][Cwidth]              (V_pos)       */
+	int *vdeg; /* [N]                      (from QCmatrixd) */
+	double complex twiddle[MO_NFFT / 2];
+	int bitrev[MO_NFFT];
+} mo_mode;
+
+typedef struct mo_rx_out {
+	double complex *Y;     /* [Nsymb*Nc] after FFT + AGC       */
+	double complex *H;     /* [Nsymb*Nc] channel used by the equaliser */
+	double complex *Z;     /* [Nsymb*Nc] equalised grid        */
+	float *llr_demod;      /* [nBits]                          */
+	float *llr_cw;	       /* [N]  codeword order              */
+	int *bits;	       /* [K]  hard decisions (scrambled)  */
+	int *bytes;	       /* [nReal/8] incl. CRC              */
+	int *payload;	       /* [frame_bytes]                    */
+	double *stats;	       /* [8] iterations, crc, all_zeros, decoded, SNR, variance, 0, mean_H */
+} mo_rx_out;
+
+int mo_mode_init(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_path);
+void mo_mode_free(mo_mode *m);
+mo_mode *mo_mode_new(int config, int ldpc_iters, const char *ldpc_blob_path);
+void mo_mode_delete(mo_mode *m);
+void mo_geometry(const mo_mode *m, int *g /*[28], same order as ref_driver.cc*/);
+void mo_tables(const mo_mode *m, int *carrier_type, double *pilot_seq, int *scrambler, double *constellation, double *boost);
+void mo_ldpc_tables(const mo_mode *m, int *dims, int *C, int *V, int *d, int *Enc);
+
+void mo_srandom(unsigned seed);
+int mo_random(void);
+void mo_random_seq(unsigned seed, int n, int *out);
+int mo_crc16(const int *bytes, int n);
+
+void mo_tx_baseband(const mo_mode *m, const int *payload, int nBytes, double complex *out, int *info_bits, int *codeword, double complex *framed);
+void mo_rx_tail(const mo_mode *m, const double complex *baseband, mo_rx_out *o);
+double mo_rx_tail_timed(const mo_mode *m, const double complex *baseband, int n_frames, int *payloads, int *decoded, int *iterations);
+int mo_ldpc_decode(const mo_mode *m, const float *llr_cw, int *bits_out);
+void mo_ldpc_encode(const mo_mode *m, const int *data, int *encoded);
+
+#endif
