@@ -1,0 +1,161 @@
+/*
+ * mercury_b200.h -- C ABI of the B200-native Mercury physical-layer RX hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI layer: the boundary is the C++ member API of
+ * one long-lived object, cl_telecom_system (reference include/physical_layer/telecom_system.h:85-199).  The
+ * entry points below are what a binding for THAT path needs; each cites the reference interface it replaces
+ * (paths relative to the reference repository, Rhizomatica/mercury @ c91aa4b):
+ *
+ *   mercury_b200_create / destroy        cl_telecom_system::cl_telecom_system / ~  (telecom_system.cc:38-94)
+ *   mercury_b200_load_tables             the table-building half of cl_telecom_system::init()
+ *                                        (telecom_system.cc:1804-1982: ofdm.init, ldpc.init, scrambler)
+ *   mercury_b200_export/import_tables    (new) the blob rank 0 broadcasts over NCCL (north_star)
+ *   mercury_b200_load_configuration      void load_configuration(int)          (telecom_system.h:176, .cc:2487)
+ *                                        + "-I n" = ldpc_nIteration_max        (main.cc:303-311,547-575)
+ *   mercury_b200_get_frame_size_bytes    int get_frame_size_bytes()            (telecom_system.h:180, .cc:332)
+ *   mercury_b200_get_frame_size_bits     int get_frame_size_bits()             (telecom_system.h:181, .cc:337)
+ *   mercury_b200_get_geometry            public members data_container.{Nsymb,Nofdm,nBits,...}, ldpc.{N,K,P}
+ *   mercury_b200_receive_baseband        the tail of st_receive_stats receive_byte(double*,int*)
+ *                                        (telecom_system.h:142, .cc:1132-1429) on its post-synchronisation
+ *                                        data_container.baseband_data
+ *   mercury_b200_demod_decode_batch      the same tail, batched over independent frames (host buffers)
+ *   mercury_b200_demod_decode_batch_device   "  (device-resident buffers, caller's stream)
+ *   mercury_b200_demod_batch_device      symbol_demod .. psk.demod .. LLR expand   (telecom_system.cc:1135-1308)
+ *   mercury_b200_ldpc_decode_batch_device    ldpc.decode .. CRC16                  (telecom_system.cc:1310-1349)
+ *   mercury_b200_rx_stats                st_receive_stats (telecom_system.h:63-82), the fields the tail writes
+ *   mercury_b200_synth_frames            (test/bench input synthesis) transmit_byte bit chain + the baseband
+ *                                        modulation chain of baseband_test_EsN0 (telecom_system.cc:342-416,129-153)
+ *
+ * Conventions: every function returns 0 on success or a negative MERCURY_B200_E* code, never exits, never
+ * throws.  No CUDA or torch types appear in the signatures: device buffers and streams are passed as void*
+ * (a cudaStream_t is a pointer; NULL = the legacy default stream).  There is NO CPU fallback: compute entry
+ * points fail with MERCURY_B200_ENODEV when no sm_100 device is usable.
+ */
+#ifndef MERCURY_B200_H
+#define MERCURY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MERCURY_B200_OK 0
+#define MERCURY_B200_EINVAL (-1)   /* bad argument / unknown configuration */
+#define MERCURY_B200_ENODEV (-2)   /* no usable CUDA device (this library never falls back to the CPU) */
+#define MERCURY_B200_ECUDA (-3)    /* a CUDA runtime call or kernel failed; see mercury_b200_last_error() */
+#define MERCURY_B200_ESTATE (-4)   /* tables not loaded / configuration not selected */
+#define MERCURY_B200_EIO (-5)      /* LDPC table file missing or malformed */
+#define MERCURY_B200_ENOMEM (-6)
+
+#define MERCURY_B200_DECODER_SPA 0     /* sum-product, the reference's default (physical_config.cc:72) */
+#define MERCURY_B200_DECODER_MINSUM 1  /* normalised min-sum (north_star fast path) */
+
+#define MERCURY_B200_NUM_CONFIGS 17    /* CONFIG_0 .. CONFIG_16 */
+#define MERCURY_B200_N 1600            /* LDPC block length, one codeword per OFDM frame */
+#define MERCURY_B200_NOFDM 272         /* samples per OFDM symbol at the decimated rate (Nfft 256 + GI 16) */
+
+typedef struct mercury_b200 mercury_b200_t;
+
+/* Frame geometry of the selected configuration (reference: members of data_container / ofdm / ldpc). */
+typedef struct mercury_b200_geometry {
+	int32_t config, M, bits_per_symbol, ldpc_rate_num /* rate = n/16 */;
+	int32_t Nsymb, Nc, Nfft, Ngi, Nofdm;
+	int32_t nData, nPilots, nBits;
+	int32_t N, K, P, nReal /* nBits-P */, nVirtual /* N-nBits */;
+	int32_t preamble_nSymb, frame_bytes;
+	int32_t estimator /* 0 ZERO_FORCE, 1 LEAST_SQUARE */, phase_only /* amplitude restoration */;
+	int32_t ldpc_iters, ldpc_edges, decoder;
+} mercury_b200_geometry;
+
+/* Per-frame result record: the st_receive_stats fields written by telecom_system.cc:1310-1375. */
+typedef struct mercury_b200_rx_stats {
+	int32_t iterations_done; /* 0..I, I+1 = not converged (ldpc_decoder_SPA.cc:217), -1 = decode skipped (mean|H| gate, :1271) */
+	int32_t crc;             /* CRC16 over payload+crc bytes, 0 = good (telecom_system.cc:1337-1341) */
+	int32_t all_zeros;       /* telecom_system.cc:1319-1327 */
+	int32_t message_decoded; /* 1 = YES */
+	float SNR;               /* dB, -99.9 when not decoded (:1347,1368-1375); 0 for ZF modes (re-encode path not built) */
+	float variance;          /* pilot noise variance used for the LLRs (:1291) */
+	float mean_H;            /* mean |H| over pilots after AGC (:1225-1244) */
+	int32_t reserved;
+} mercury_b200_rx_stats;
+
+const char *mercury_b200_version(void);
+const char *mercury_b200_strerror(int code);
+
+int mercury_b200_create(int device, mercury_b200_t **out);
+void mercury_b200_destroy(mercury_b200_t *h);
+const char *mercury_b200_last_error(const mercury_b200_t *h);
+
+/* Build all 17 mode tables + 8 LDPC graphs from the LDPC table file and upload them (one copy to HBM). */
+int mercury_b200_load_tables(mercury_b200_t *h, const char *ldpc_table_path);
+/* Table blob exchange for multi-GPU start-up: rank 0 exports, broadcasts (NCCL), the others import. */
+int mercury_b200_export_tables(const mercury_b200_t *h, void *buf, size_t *size /* in: capacity, out: bytes */);
+int mercury_b200_import_tables(mercury_b200_t *h, const void *buf, size_t size);
+/* Host-only table construction (no device needed): same blob as export_tables(). buf may be NULL to query size. */
+int mercury_b200_build_tables_host(const char *ldpc_table_path, void *buf, size_t *size);
+
+/* O(1): all configurations stay resident. config 0..16, ldpc_iters clamped to 5..50 like the CLI's -I. */
+int mercury_b200_load_configuration(mercury_b200_t *h, int config, int ldpc_iters);
+int mercury_b200_set_decoder(mercury_b200_t *h, int decoder);
+int mercury_b200_get_geometry(const mercury_b200_t *h, mercury_b200_geometry *out);
+int mercury_b200_get_frame_size_bytes(const mercury_b200_t *h);
+int mercury_b200_get_frame_size_bits(const mercury_b200_t *h);
+
+/*
+ * Batched RX tail on frames that are already time/frequency synchronised (what receive_byte() holds in
+ * data_container.baseband_data after telecom_system.cc:1131), preamble stripped:
+ *   baseband : n_frames x Nsymb x 272 complex samples, interleaved (re,im) float32
+ *   payload  : n_frames x frame_bytes bytes (CRC bytes stripped, telecom_system.cc:1329-1332)
+ *   stats    : n_frames records
+ *   llr_cw   : optional n_frames x 1600 float32, LLRs in codeword order (the input of ldpc.decode), or NULL
+ * Host variant: pointers are host memory (pinned memory from mercury_b200_host_alloc gives full PCIe rate);
+ * copies are pipelined with the kernels in chunks.  Device variant: pointers are device memory on h's device;
+ * work is enqueued on `stream` and NOT synchronised.
+ */
+int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *baseband, size_t n_frames, uint8_t *payload,
+				    mercury_b200_rx_stats *stats, float *llr_cw);
+int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_payload,
+					   void *d_stats, void *d_llr_cw, void *stream);
+/* The two stages separately (device buffers). d_llr is n_frames x 1600 float32 in the decoder's internal order. */
+int mercury_b200_demod_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_llr, void *d_stats,
+				    void *d_llr_cw, void *stream);
+int mercury_b200_ldpc_decode_batch_device(mercury_b200_t *h, const void *d_llr, size_t n_frames, void *d_payload, void *d_stats,
+					  void *stream);
+/* Optional per-stage capture for parity tests (device, n_frames x Nsymb x 50 complex64 each; any may be NULL). */
+int mercury_b200_set_debug_capture(mercury_b200_t *h, void *d_Y, void *d_H, void *d_Z);
+/* Bytes of scratch (internal-order LLRs) demod_decode_batch_device needs per frame; owned by the handle and grown on demand. */
+
+/*
+ * One frame, the reference's own types: baseband = Nsymb*272 std::complex<double> (re,im doubles), out = one int
+ * per payload byte like receive_byte()'s `int* out`.  Returns the stats record by pointer.
+ */
+int mercury_b200_receive_baseband(mercury_b200_t *h, const double *baseband, int *out, mercury_b200_rx_stats *stats);
+
+/* Pinned host memory and plain device memory helpers for callers that do not link the CUDA runtime. */
+void *mercury_b200_host_alloc(size_t bytes);
+void mercury_b200_host_free(void *p);
+void *mercury_b200_device_alloc(mercury_b200_t *h, size_t bytes);
+void mercury_b200_device_free(mercury_b200_t *h, void *p);
+int mercury_b200_memcpy_h2d(mercury_b200_t *h, void *dst, const void *src, size_t bytes);
+int mercury_b200_memcpy_d2h(mercury_b200_t *h, void *dst, const void *src, size_t bytes);
+int mercury_b200_synchronize(mercury_b200_t *h);
+
+/* Number of kernels this library has launched through this handle (bench.py's gpu_launches). */
+uint64_t mercury_b200_kernel_launches(const mercury_b200_t *h);
+
+/*
+ * Input synthesis on the host (tests / bench only; not part of the RX path): n_frames frames of configuration
+ * `config`, payload bytes from splitmix64(seed, frame index) (or `payload_in` if non-NULL), through the TX bit
+ * chain and baseband OFDM modulator, plus complex AWGN at Es/N0 = esn0_db (baseband_test_EsN0 normalisation,
+ * telecom_system.cc:141-153; pass esn0_db >= 200 for no noise).  Needs the LDPC table file, not a device.
+ *   baseband_out : n_frames x Nsymb x 272 x 2 float32      payload_out : n_frames x frame_bytes (may be NULL)
+ */
+int mercury_b200_synth_frames(const char *ldpc_table_path, int config, size_t n_frames, uint64_t seed, double esn0_db,
+			      const uint8_t *payload_in, float *baseband_out, uint8_t *payload_out, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERCURY_B200_H */

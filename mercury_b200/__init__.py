@@ -1,0 +1,8 @@
+"""mercury_b200 -- B200-native (sm_100a) receive hot path of the Mercury HF modem's physical layer.
+
+Product = mercury_b200/libmercury_b200.so (C ABI in include/mercury_b200.h). This package is the host-side
+mirror of the reference's interface for that path; see DESIGN.md.
+"""
+from .modes import MODES, THRESH_DB  # noqa: F401
+from .telecom_system import (DECODER_MINSUM, DECODER_SPA, NO, STATS_DTYPE, YES, MercuryB200Error,  # noqa: F401
+                             TelecomSystemB200, build_tables_host, synth_frames)

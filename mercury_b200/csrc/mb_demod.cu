@@ -1,0 +1,400 @@
+// mb_demod.cu -- K_demod: fused OFDM demodulator for sm_100a, one CTA per frame.
+//
+//   FFT-256 per symbol  ->  AGC  ->  LS / ZF channel estimate  ->  column interpolation  ->  (phase-only)
+//   equalise  ->  pilot noise variance  ->  deframe + T/F de-interleave  ->  max-log soft de-map  ->
+//   bit de-interleave + LLR expand  ->  LLR[1600]
+//
+// Reference (what is computed; paths relative to /root/reference/source/physical_layer):
+//   symbol_demod            ofdm.cc:862-867 (gi_remover 423-429, fft 431-444, zero_depadder 401-411)
+//   automatic_gain_control  ofdm.cc:1467-1498
+//   LS_channel_estimator    ofdm.cc:1315-1451     ZF_channel_estimator ofdm.cc:1266-1313
+//   interpolate_linear_col  interpolator.cc:163-254
+//   restore_channel_amplitude ofdm.cc:1453-1466 (get_angle misc.cc:34-56)
+//   channel_equalizer       ofdm.cc:1637-1657     measure_variance ofdm.cc:1500-1521
+//   deframer ofdm.cc:837-852, deinterleaver interleaver.cc:77-109, cl_psk::demod psk.cc:278-326,
+//   LLR expand telecom_system.cc:1300-1308
+//
+// How (B200-first, not the reference's loops):
+//   * HBM-bound stage: every sample is read exactly once with 8-byte streaming loads (16 independent loads in
+//     flight per thread, guard interval never fetched); the only other HBM traffic is the 6.4 KB LLR vector.
+//   * FFT-256 = 16 x 16: 16 threads per OFDM symbol, two radix-4x4 16-point DFTs in registers around one
+//     conflict-free (stride-17) shared-memory transpose that needs only __syncwarp (a symbol lives in half a warp).
+//     Twiddles (with the reference's 1/N folded in) come from a 2 KB shared table laid out for broadcast reads.
+//     The second DFT is pruned to the 4 of 16 outputs that land on the 50 active carriers.
+//   * The LS estimator's O(pilots x window) double loop is restated as the windowed mean it is:
+//     a separable clipped 21x21 box sum over the pilot lattice, row pass then column pass, in shared memory.
+//   * deframe, both de-interleavers and the LLR expand are composed on the host into two gather/scatter index
+//     tables (mb_tables.cpp), so no intermediate vector is ever materialised.
+#include "mb_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
+__device__ __forceinline__ float2 cdiv(float2 a, float2 b)
+{
+	float inv = 1.0f / (b.x * b.x + b.y * b.y);
+	return make_float2((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
+}
+
+// forward 4-point DFT (W4 = -i)
+__device__ __forceinline__ void dft4(float2 a, float2 b, float2 c, float2 d, float2 &y0, float2 &y1, float2 &y2, float2 &y3)
+{
+	float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+	y0 = cadd(t0, t2);
+	y2 = csub(t0, t2);
+	y1 = cadd(t1, mul_mi(t3));
+	y3 = cadd(t1, mul_pi(t3));
+}
+
+#define MB_C1 0.92387953251128674f
+#define MB_S1 0.38268343236508977f
+#define MB_R2 0.70710678118654752f
+
+// Stage 1+2 of the radix-4x4 16-point forward DFT: A[n2][k1] = W16^(n2 k1) * sum_n1 x[4 n1 + n2] (-i)^(n1 k1)
+__device__ __forceinline__ void fft16_front(const float2 (&x)[16], float2 (&A)[4][4])
+{
+#pragma unroll
+	for (int n2 = 0; n2 < 4; n2++) dft4(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], A[n2][0], A[n2][1], A[n2][2], A[n2][3]);
+	A[1][1] = cmul(A[1][1], make_float2(MB_C1, -MB_S1));   // W16^1
+	A[1][2] = cmul(A[1][2], make_float2(MB_R2, -MB_R2));   // W16^2
+	A[1][3] = cmul(A[1][3], make_float2(MB_S1, -MB_C1));   // W16^3
+	A[2][1] = cmul(A[2][1], make_float2(MB_R2, -MB_R2));   // W16^2
+	A[2][2] = mul_mi(A[2][2]);                             // W16^4
+	A[2][3] = cmul(A[2][3], make_float2(-MB_R2, -MB_R2));  // W16^6
+	A[3][1] = cmul(A[3][1], make_float2(MB_S1, -MB_C1));   // W16^3
+	A[3][2] = cmul(A[3][2], make_float2(-MB_R2, -MB_R2));  // W16^6
+	A[3][3] = cmul(A[3][3], make_float2(-MB_C1, MB_S1));   // W16^9
+}
+
+// full 16-point forward DFT, natural order out: X[k1 + 4 k2]
+__device__ __forceinline__ void fft16(const float2 (&x)[16], float2 (&X)[16])
+{
+	float2 A[4][4];
+	fft16_front(x, A);
+#pragma unroll
+	for (int k1 = 0; k1 < 4; k1++) dft4(A[0][k1], A[1][k1], A[2][k1], A[3][k1], X[k1], X[k1 + 4], X[k1 + 8], X[k1 + 12]);
+}
+
+// 16-point forward DFT pruned to outputs 0, 1, 14, 15 (the only ones that reach the 50 active carriers)
+__device__ __forceinline__ void fft16_pruned(const float2 (&x)[16], float2 &X0, float2 &X1, float2 &X14, float2 &X15)
+{
+	float2 A[4][4];
+	fft16_front(x, A);
+	X0 = cadd(cadd(A[0][0], A[2][0]), cadd(A[1][0], A[3][0]));                   // k1=0, k2=0
+	X1 = cadd(cadd(A[0][1], A[2][1]), cadd(A[1][1], A[3][1]));                   // k1=1, k2=0
+	X14 = cadd(csub(A[0][2], A[2][2]), mul_pi(csub(A[1][2], A[3][2])));          // k1=2, k2=3
+	X15 = cadd(csub(A[0][3], A[2][3]), mul_pi(csub(A[1][3], A[3][3])));          // k1=3, k2=3
+}
+
+// Sum three values over the CTA; result valid in every thread. s_red: >= 3*32+3 floats.
+__device__ __forceinline__ void block_sum3(float &a, float &b, float &c, float *s_red)
+{
+	__syncthreads();
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		a += __shfl_xor_sync(0xffffffffu, a, o);
+		b += __shfl_xor_sync(0xffffffffu, b, o);
+		c += __shfl_xor_sync(0xffffffffu, c, o);
+	}
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	if (lane == 0) {
+		s_red[w * 3 + 0] = a;
+		s_red[w * 3 + 1] = b;
+		s_red[w * 3 + 2] = c;
+	}
+	__syncthreads();
+	if (w == 0) {
+		a = lane < nw ? s_red[lane * 3 + 0] : 0.f;
+		b = lane < nw ? s_red[lane * 3 + 1] : 0.f;
+		c = lane < nw ? s_red[lane * 3 + 2] : 0.f;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			a += __shfl_xor_sync(0xffffffffu, a, o);
+			b += __shfl_xor_sync(0xffffffffu, b, o);
+			c += __shfl_xor_sync(0xffffffffu, c, o);
+		}
+		if (lane == 0) {
+			s_red[96] = a;
+			s_red[97] = b;
+			s_red[98] = c;
+		}
+	}
+	__syncthreads();
+	a = s_red[96];
+	b = s_red[97];
+	c = s_red[98];
+}
+
+// restore_channel_amplitude (ofdm.cc:1453-1466): exp(j*arg H); get_angle returns pi/2 whenever Re == 0 (misc.cc:38-41)
+__device__ __forceinline__ float2 unit_phase(float2 h)
+{
+	if (h.x == 0.f) return make_float2(0.f, 1.f);
+	float inv = rsqrtf(h.x * h.x + h.y * h.y);
+	return make_float2(h.x * inv, h.y * inv);
+}
+
+// Channel at a data cell: linear interpolation between the pilot rows of its column, linear extrapolation
+// beyond the first / last pilot row (interpolator.cc:163-254 on the s%3==c%3 lattice).
+__device__ __forceinline__ float2 interp_channel(const float2 *s_H, int s, int c, int S)
+{
+	const int f = c % 3;
+	const int last = f + 3 * ((S - 1 - f) / 3);
+	int r0;
+	if (s < f)
+		r0 = f;
+	else if (s > last)
+		r0 = last - 3;
+	else
+		r0 = s - ((s - f) % 3);
+	const float2 a = s_H[r0 * MB_NC + c], b = s_H[(r0 + 3) * MB_NC + c];
+	const float t = (float)(s - r0);
+	return make_float2(a.x + (b.x - a.x) * t / 3.0f, a.y + (b.y - a.y) * t / 3.0f);
+}
+
+constexpr int kSmemHeadFloats = 2 * 256 + 2 * 32 + 128;  // twiddles, constellation, reduction scratch
+
+template <bool kDebug>
+__global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const MbMode &m = a.mode;
+	const int T = blockDim.x, tid = threadIdx.x;
+	const int S = m.Nsymb, cells = S * MB_NC;
+	float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
+	float2 *s_cons = s_tw + 256;
+	float *s_red = reinterpret_cast<float *>(s_cons + 32);
+	float2 *s_Y = reinterpret_cast<float2 *>(s_red + 128);
+	float2 *s_buf = s_Y + cells;  // FFT transpose scratch, then reused for T / H / L
+	float2 *s_T = s_buf;
+	float2 *s_H = s_buf + cells;
+	float *s_L = reinterpret_cast<float *>(s_buf + 2 * cells);
+
+	const size_t frame = blockIdx.x;
+	const float2 *__restrict__ xf = a.x + frame * (size_t)S * MB_NOFDM;
+	const float *__restrict__ g_pinv = reinterpret_cast<const float *>(a.blob + m.off_pinv);
+	const float *__restrict__ g_pval = reinterpret_cast<const float *>(a.blob + m.off_pval);
+	const float *__restrict__ g_invn = reinterpret_cast<const float *>(a.blob + m.off_invn);
+	const uint16_t *__restrict__ g_pilot_cell = reinterpret_cast<const uint16_t *>(a.blob + m.off_pilot_cell);
+	const uint16_t *__restrict__ g_sym_cell = reinterpret_cast<const uint16_t *>(a.blob + m.off_sym_cell);
+	const uint16_t *__restrict__ g_dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
+	const uint16_t *__restrict__ g_dst2 = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst2);
+
+	{
+		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);
+		const float2 *__restrict__ g_cons = reinterpret_cast<const float2 *>(a.blob + m.off_const);
+		for (int i = tid; i < 256; i += T) s_tw[i] = g_tw[i];
+		if (tid < m.M) s_cons[tid] = g_cons[tid];
+	}
+	__syncthreads();
+
+	// ---------------- FFT-256 per symbol (a2, a3) ------------------------------------------------------------
+	{
+		const int grp = tid >> 4, t = tid & 15, spr = T >> 4;
+		float2 *buf = s_buf + grp * (16 * 17);
+		for (int s0 = 0; s0 < S; s0 += spr) {
+			const int s = s0 + grp;
+			const bool active = s < S;
+			if (active) {
+				const float2 *__restrict__ xs = xf + (size_t)s * MB_NOFDM + MB_NGI + t;
+				float2 v[16], A[16];
+#pragma unroll
+				for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldcs(xs + 16 * n1);  // x[16 n1 + t], GI skipped
+				fft16(v, A);
+#pragma unroll
+				for (int k1 = 0; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], s_tw[k1 * 16 + t]);
+			}
+			__syncwarp();
+			if (active) {
+				float2 w[16], X0, X1, X14, X15;
+#pragma unroll
+				for (int n2 = 0; n2 < 16; n2++) w[n2] = buf[n2 * 17 + t];
+				fft16_pruned(w, X0, X1, X14, X15);  // bins t, 16+t, 224+t, 240+t
+				float2 *row = s_Y + s * MB_NC;
+				// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49
+				if (t >= 1) row[24 + t] = X0;
+				if (t <= 9) row[40 + t] = X1;
+				if (t >= 7) row[t - 7] = X14;
+				row[9 + t] = X15;
+			}
+			__syncwarp();
+		}
+	}
+
+	// ---------------- AGC (a4): g = boost / mean |Y_pilot| ---------------------------------------------------
+	float g;
+	{
+		float acc = 0.f, z0 = 0.f, z1 = 0.f;
+		__syncthreads();
+		for (int p = tid; p < m.nPilots; p += T) {
+			const float2 y = s_Y[g_pilot_cell[p]];
+			acc += sqrtf(y.x * y.x + y.y * y.y);
+		}
+		block_sum3(acc, z0, z1, s_red);
+		g = m.boost / (acc / (float)m.nPilots);
+	}
+
+	// ---------------- LS estimate (a5): separable clipped 21x21 box mean of Y/p over the pilot lattice --------
+	if (m.estimator == 1) {
+		for (int idx = tid; idx < cells; idx += T) {
+			const int k = idx / MB_NC, c = idx - k * MB_NC;
+			const int lo = max(0, c - MB_LS_HALF), hi = min(MB_NC - 1, c + MB_LS_HALF);
+			int l = lo + ((k % 3) - (lo % 3) + 3) % 3;
+			float sx = 0.f, sy = 0.f;
+			for (; l <= hi; l += 3) {
+				const float2 y = s_Y[k * MB_NC + l];
+				const float w = g_pinv[k * MB_NC + l];
+				sx += y.x * w;
+				sy += y.y * w;
+			}
+			s_T[idx] = make_float2(sx * g, sy * g);
+		}
+	}
+	__syncthreads();
+
+	// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) -----------------------------
+	float accH = 0.f, accV = 0.f, accVn = 0.f;
+	for (int p = tid; p < m.nPilots; p += T) {
+		const int cell = g_pilot_cell[p];
+		const int s = cell / MB_NC, c = cell - s * MB_NC;
+		const float2 yg = cscale(s_Y[cell], g);
+		float2 h;
+		if (m.estimator == 1) {
+			const int k0 = max(0, s - MB_LS_HALF), k1 = min(S - 1, s + MB_LS_HALF);
+			float sx = 0.f, sy = 0.f;
+			for (int k = k0; k <= k1; k++) {
+				const float2 tv = s_T[k * MB_NC + c];
+				sx += tv.x;
+				sy += tv.y;
+			}
+			const float w = g_invn[cell];
+			h = make_float2(sx * w, sy * w);
+		} else {
+			h = cscale(yg, g_pinv[cell]);  // ZF: H = Y / p
+		}
+		s_H[cell] = h;
+		accH += sqrtf(h.x * h.x + h.y * h.y);
+		const float pv = g_pval[cell];
+		float2 heq = h;
+		if (m.phase_only) {
+			heq = unit_phase(h);
+			const float2 zn = cdiv(yg, h);  // equalised without amplitude restoration: SNR report only
+			accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
+		}
+		const float2 z = cdiv(yg, heq);
+		accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
+		if (kDebug) {
+			const size_t o = frame * (size_t)cells + cell;
+			if (a.dbg_Y) a.dbg_Y[o] = yg;
+			if (a.dbg_H) a.dbg_H[o] = heq;
+			if (a.dbg_Z) a.dbg_Z[o] = z;
+		}
+	}
+	block_sum3(accH, accV, accVn, s_red);  // also orders s_H writes before the reads below
+	const float inv_np = 1.0f / (float)m.nPilots;
+	// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
+	const float variance = fmaxf(accV * inv_np, 1e-30f);
+	const float inv_var = 1.0f / variance;
+
+	// ---------------- data cells: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------------
+	for (int q = tid; q < m.nData; q += T) {
+		const int cell = g_sym_cell[q];
+		const int s = cell / MB_NC, c = cell - s * MB_NC;
+		float2 h = interp_channel(s_H, s, c, S);
+		if (m.phase_only) h = unit_phase(h);
+		const float2 yg = cscale(s_Y[cell], g);
+		const float2 z = cdiv(yg, h);
+		if (kDebug) {
+			const size_t o = frame * (size_t)cells + cell;
+			if (a.dbg_Y) a.dbg_Y[o] = yg;
+			if (a.dbg_H) a.dbg_H[o] = h;
+			if (a.dbg_Z) a.dbg_Z[o] = z;
+		}
+		// max-log LLR per bit (psk.cc:278-326): (min_{bit=1} D - min_{bit=0} D) / variance, MSB first
+		float d0[5], d1[5];
+#pragma unroll
+		for (int k = 0; k < 5; k++) d0[k] = d1[k] = 3.0e38f;
+		for (int j = 0; j < m.M; j++) {
+			const float2 cj = s_cons[j];
+			const float dx = z.x - cj.x, dy = z.y - cj.y;
+			const float D = dx * dx + dy * dy;
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				const bool one = (j >> k) & 1;
+				d0[k] = one ? d0[k] : fminf(d0[k], D);
+				d1[k] = one ? fminf(d1[k], D) : d1[k];
+			}
+		}
+		const int base = q * m.bps;
+#pragma unroll
+		for (int k = 0; k < 5; k++) {
+			if (k < m.bps) {
+				const float llr = inv_var * (d1[k] - d0[k]);
+				const int i = base + (m.bps - 1 - k);
+				s_L[g_dst[i]] = llr;
+				const unsigned d2 = g_dst2[i];
+				if (d2 != MB_NO_DST) s_L[d2] = llr;
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---------------- write LLRs (decoder order, coalesced) and the demod half of the stats record -----------
+	{
+		float4 *__restrict__ out = reinterpret_cast<float4 *>(a.llr + frame * (size_t)MB_N);
+		const float4 *src = reinterpret_cast<const float4 *>(s_L);
+		for (int i = tid; i < MB_N / 4; i += T) out[i] = src[i];
+		if (a.llr_cw) {
+			const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
+			float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
+			for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
+		}
+		if (tid == 0) {
+			MbRxStats st;
+			st.iterations_done = -1;
+			st.crc = 0;
+			st.all_zeros = 0;
+			st.message_decoded = 0;
+			const float v_rep = m.phase_only ? accVn * inv_np : variance;
+			st.SNR = m.estimator == 1 ? 10.0f * log10f(1.0f / v_rep) : 0.0f;  // candidate; finalised by the decoder
+			st.variance = variance;
+			st.mean_H = accH * inv_np;
+			st.reserved = 0;
+			a.stats[frame] = st;
+		}
+	}
+}
+
+}  // namespace
+
+size_t mb_demod_smem_bytes(int Nsymb)
+{
+	const int T = mb_demod_threads(Nsymb), cells = Nsymb * MB_NC;
+	size_t fftbuf = (size_t)(T / 16) * 16 * 17 * sizeof(float2);
+	size_t reuse = (size_t)2 * cells * sizeof(float2) + MB_N * sizeof(float);
+	return kSmemHeadFloats * sizeof(float) + (size_t)cells * sizeof(float2) + (fftbuf > reuse ? fftbuf : reuse);
+}
+
+cudaError_t mb_demod_init()
+{
+	cudaError_t e = cudaFuncSetAttribute(mb_demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(mb_demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+}
+
+cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream)
+{
+	if (n_frames == 0) return cudaSuccess;
+	const int T = mb_demod_threads(a.mode.Nsymb);
+	const size_t smem = mb_demod_smem_bytes(a.mode.Nsymb);
+	const bool dbg = a.dbg_Y || a.dbg_H || a.dbg_Z;
+	if (dbg)
+		mb_demod_kernel<true><<<(unsigned)n_frames, T, smem, stream>>>(a);
+	else
+		mb_demod_kernel<false><<<(unsigned)n_frames, T, smem, stream>>>(a);
+	return cudaGetLastError();
+}

@@ -1,0 +1,51 @@
+// mb_kernels.cuh -- launch interfaces of the two sm_100a kernels of the RX path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "mb_tables.h"
+
+// Mirrors mercury_b200_rx_stats (include/mercury_b200.h); 32 bytes.
+struct MbRxStats {
+	int32_t iterations_done, crc, all_zeros, message_decoded;
+	float SNR, variance, mean_H;
+	int32_t reserved;
+};
+
+struct MbDemodArgs {
+	const float2 *x;       // [B][Nsymb][272] complex64 baseband, preamble stripped
+	float *llr;            // [B][1600] LLRs in the decoder's internal variable order
+	float *llr_cw;         // optional [B][1600] LLRs in codeword order (parity output)
+	MbRxStats *stats;      // [B]
+	float2 *dbg_Y, *dbg_H, *dbg_Z;  // optional [B][Nsymb*50] stage captures
+	const uint8_t *blob;   // device copy of the table blob
+	uint32_t off_twiddle;
+	uint32_t off_var_of_cw;
+	MbMode mode;
+};
+
+struct MbLdpcArgs {
+	const float *llr;      // [B][1600] internal order
+	uint8_t *payload;      // [B][frame_bytes]
+	MbRxStats *stats;      // [B]  (SNR/variance/mean_H already filled by the demod kernel)
+	const uint8_t *blob;
+	MbMode mode;
+	MbRate rate;
+	int32_t max_iters;
+	int32_t check_gate;    // 1: honour the mean|H| < 0.3 gate recorded by the demod kernel
+};
+
+// Threads per CTA of the demod kernel for a frame of Nsymb symbols (16 threads per symbol, <= 384, warp multiple).
+static inline int mb_demod_threads(int Nsymb)
+{
+	int t = Nsymb * 16;
+	if (t > 384) t = 384;
+	return (t + 31) / 32 * 32;
+}
+size_t mb_demod_smem_bytes(int Nsymb);
+size_t mb_ldpc_smem_bytes(int n_edges);
+
+cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream);
+cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream);
+cudaError_t mb_demod_init();  // opt-in shared memory attributes
+cudaError_t mb_ldpc_init();

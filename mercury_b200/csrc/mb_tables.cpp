@@ -1,0 +1,454 @@
+// mb_tables.cpp -- host-side construction of the table blob (see mb_tables.h).
+//
+// Init-time work only ("deterministic tables, per mode"): nothing here runs per frame.
+// The tables are re-derived from first principles (PRNG, lattice rule, interleaver index algebra) rather than
+// dumped from the reference, and cross-checked against the oracle in tests/test_tables.py.
+#include "mb_tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace {
+
+// ---- glibc random() TYPE_3 (reference: source/common/os_interop.cc:192-283) -------------------------------
+// r[i] = r[i-3] + r[i-31] mod 2^32, Park-Miller seeding, 310 warm-up draws, output >> 1; seed 0 -> 1.
+}  // namespace
+
+void mb_srandom(uint32_t st[35], unsigned seed)
+{
+	if (seed == 0) seed = 1;
+	int32_t r = (int32_t)seed;
+	st[0] = (uint32_t)r;
+	for (int i = 1; i < 31; i++) {
+		int64_t w = 16807LL * (r % 127773) - 2836LL * (r / 127773);
+		if (w < 0) w += 2147483647;
+		r = (int32_t)w;
+		st[i] = (uint32_t)r;
+	}
+	for (int i = 31; i < 34; i++) st[i] = st[i - 31];
+	st[34] = 0;  // ring cursor
+	for (int i = 0; i < 310; i++) (void)mb_random(st);
+}
+
+int mb_random(uint32_t st[35])
+{
+	uint32_t i = st[34];
+	uint32_t v = st[(i + 3) % 34] + st[(i + 31) % 34];
+	st[i] = v;
+	st[34] = (i + 1) % 34;
+	return (int)(v >> 1);
+}
+
+int mb_rate_index(int rate_num)
+{
+	static const int rates[MB_NRATES] = {1, 2, 3, 4, 5, 6, 8, 14};
+	for (int i = 0; i < MB_NRATES; i++)
+		if (rates[i] == rate_num) return i;
+	return -1;
+}
+
+namespace {
+
+struct ModeDef {
+	int M, rate, pre, est;
+};
+// CONFIG_0..16: telecom_system.cc:2506-2624
+const ModeDef kModes[MB_NMODES] = {
+	{2, 1, 4, 1},  {2, 2, 4, 1},  {2, 3, 4, 1},  {2, 4, 4, 1},  {2, 5, 4, 1},  {2, 6, 4, 1},
+	{2, 8, 4, 1},  {4, 5, 4, 1},  {4, 6, 4, 1},  {4, 8, 4, 1},  {8, 6, 3, 1},  {8, 8, 3, 1},
+	{4, 14, 3, 1}, {16, 8, 2, 1}, {8, 14, 2, 1}, {16, 14, 2, 0}, {32, 14, 1, 0},
+};
+
+int nsymb_of(int M)  // telecom_system.cc:1818-1826 (HIGH_DENSITY pilots, the compiled default)
+{
+	switch (M) {
+	case 2: return 48;
+	case 4: return 24;
+	case 8: return 16;
+	case 16: return 12;
+	case 32: return 9;
+	}
+	return 0;
+}
+
+struct Blob {
+	std::vector<uint8_t> b;
+	uint32_t reserve(size_t bytes, size_t align = 16)
+	{
+		size_t off = (b.size() + align - 1) / align * align;
+		b.resize(off + bytes, 0);
+		return (uint32_t)off;
+	}
+	template <typename T>
+	uint32_t put(const std::vector<T> &v)
+	{
+		uint32_t off = reserve(v.size() * sizeof(T));
+		if (!v.empty()) memcpy(b.data() + off, v.data(), v.size() * sizeof(T));
+		return off;
+	}
+};
+
+struct RateTables {
+	int rate_num = 0, N = 0, K = 0, P = 0, n_edges = 0;
+	std::vector<std::vector<int>> crow;  // check -> variables, reference order (ascending)
+	std::vector<std::vector<int>> vrow;  // variable -> checks, reference V-row order
+};
+
+bool load_ldpc_file(const char *path, std::vector<RateTables> &rates, std::string &err)
+{
+	FILE *f = fopen(path, "rb");
+	if (!f) {
+		err = std::string("cannot open LDPC table file ") + path;
+		return false;
+	}
+	uint8_t hdr[12];
+	if (fread(hdr, 1, 12, f) != 12 || memcmp(hdr, "MLDP", 4) != 0) {
+		fclose(f);
+		err = "bad LDPC table file header";
+		return false;
+	}
+	uint32_t n;
+	memcpy(&n, hdr + 8, 4);
+	for (uint32_t r = 0; r < n; r++) {
+		uint16_t h[6];
+		uint32_t ne;
+		if (fread(h, 2, 6, f) != 6 || fread(&ne, 4, 1, f) != 1) break;
+		RateTables t;
+		t.rate_num = h[0], t.N = h[1], t.K = h[2], t.P = h[3], t.n_edges = (int)ne;
+		std::vector<uint16_t> cdeg(t.P), ev(ne), vdeg(t.N), vc(ne);
+		if (fread(cdeg.data(), 2, t.P, f) != (size_t)t.P || fread(ev.data(), 2, ne, f) != ne ||
+		    fread(vdeg.data(), 2, t.N, f) != (size_t)t.N || fread(vc.data(), 2, ne, f) != ne)
+			break;
+		size_t e = 0;
+		t.crow.resize(t.P);
+		for (int c = 0; c < t.P; c++)
+			for (int j = 0; j < cdeg[c]; j++) t.crow[c].push_back(ev[e++]);
+		e = 0;
+		t.vrow.resize(t.N);
+		for (int v = 0; v < t.N; v++)
+			for (int j = 0; j < vdeg[v]; j++) t.vrow[v].push_back(vc[e++]);
+		rates.push_back(std::move(t));
+	}
+	fclose(f);
+	if (rates.size() != MB_NRATES) {
+		err = "LDPC table file truncated";
+		return false;
+	}
+	return true;
+}
+
+std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<uint16_t> &var_of_cw)
+{
+	const int N = t.N, P = t.P;
+	if (N != MB_N) return "unexpected LDPC block length";
+	// checks sorted by degree, descending (stable)
+	std::vector<int> csorted(P);
+	std::iota(csorted.begin(), csorted.end(), 0);
+	std::stable_sort(csorted.begin(), csorted.end(), [&](int a, int b) { return t.crow[a].size() > t.crow[b].size(); });
+	std::vector<int> cpos(P);
+	for (int i = 0; i < P; i++) cpos[csorted[i]] = i;
+	// variables renumbered by degree, descending (stable)
+	std::vector<int> vsorted(N);
+	std::iota(vsorted.begin(), vsorted.end(), 0);
+	std::stable_sort(vsorted.begin(), vsorted.end(), [&](int a, int b) { return t.vrow[a].size() > t.vrow[b].size(); });
+	var_of_cw.assign(N, 0);
+	for (int i = 0; i < N; i++) var_of_cw[vsorted[i]] = (uint16_t)i;
+
+	int max_cdeg = (int)t.crow[csorted[0]].size(), max_vdeg = (int)t.vrow[vsorted[0]].size();
+	if (max_cdeg > MB_MAX_CDEG || max_vdeg > MB_MAX_VDEG) return "LDPC degree exceeds compiled limits";
+	std::vector<uint32_t> coff(MB_MAX_CDEG + 1, 0), voff(MB_MAX_VDEG + 1, 0);
+	for (int k = 0; k < MB_MAX_CDEG; k++) {
+		int cnt = 0;
+		for (int c = 0; c < P; c++) cnt += (int)t.crow[c].size() > k;
+		coff[k + 1] = coff[k] + cnt;
+	}
+	for (int k = 0; k < MB_MAX_VDEG; k++) {
+		int cnt = 0;
+		for (int v = 0; v < N; v++) cnt += (int)t.vrow[v].size() > k;
+		voff[k + 1] = voff[k] + cnt;
+	}
+	if ((int)coff[MB_MAX_CDEG] != t.n_edges || (int)voff[MB_MAX_VDEG] != t.n_edges) return "LDPC edge count mismatch";
+
+	std::vector<uint8_t> cdeg(P), vdeg(N);
+	std::vector<uint16_t> edge_var(t.n_edges), vedge(t.n_edges), check_of_sorted(P);
+	for (int i = 0; i < P; i++) {
+		int c = csorted[i];
+		cdeg[i] = (uint8_t)t.crow[c].size();
+		check_of_sorted[i] = (uint16_t)c;
+		for (size_t k = 0; k < t.crow[c].size(); k++) edge_var[coff[k] + i] = var_of_cw[t.crow[c][k]];
+	}
+	for (int i = 0; i < N; i++) {
+		int v = vsorted[i];
+		vdeg[i] = (uint8_t)t.vrow[v].size();
+		for (size_t k = 0; k < t.vrow[v].size(); k++) {
+			int c = t.vrow[v][k];
+			const std::vector<int> &row = t.crow[c];
+			auto it = std::find(row.begin(), row.end(), v);
+			if (it == row.end()) return "LDPC V/C tables inconsistent";
+			int kc = (int)(it - row.begin());
+			vedge[voff[k] + i] = (uint16_t)(coff[kc] + cpos[c]);
+		}
+	}
+	out.rate_num = t.rate_num, out.N = N, out.K = t.K, out.P = P, out.n_edges = t.n_edges;
+	out.max_cdeg = max_cdeg, out.max_vdeg = max_vdeg, out.c_slots = t.n_edges;
+	out.off_cdeg = bl.put(cdeg);
+	out.off_coff = bl.put(coff);
+	out.off_edge_var = bl.put(edge_var);
+	out.off_vdeg = bl.put(vdeg);
+	out.off_voff = bl.put(voff);
+	out.off_vedge = bl.put(vedge);
+	out.off_var_of_cw = bl.put(var_of_cw);
+	out.off_check_of_sorted = bl.put(check_of_sorted);
+	return "";
+}
+
+// constellations: psk.cc:65-226; unit mean power with a *float* normaliser: psk.cc:229-256
+void build_constellation(int M, std::vector<float> &out)
+{
+	static const signed char q16[16][2] = {{-3, 3}, {-3, 1}, {-3, -3}, {-3, -1}, {-1, 3}, {-1, 1}, {-1, -3}, {-1, -1},
+					       {3, 3},	{3, 1},	 {3, -3},  {3, -1},  {1, 3},  {1, 1},  {1, -3},	 {1, -1}};
+	static const signed char q32[32][2] = {{-3, 5}, {-1, 5}, {-3, -5}, {-1, -5}, {-5, 3}, {-5, 1}, {-5, -3}, {-5, -1},
+					       {-1, 3}, {-1, 1}, {-1, -3}, {-1, -1}, {-3, 3}, {-3, 1}, {-3, -3}, {-3, -1},
+					       {3, 5},	{1, 5},	 {3, -5},  {1, -5},  {5, 3},  {5, 1},  {5, -3},	 {5, -1},
+					       {1, 3},	{1, 1},	 {1, -3},  {1, -1},  {3, 3},  {3, 1},  {3, -3},	 {3, -1}};
+	std::vector<double> re(M), im(M);
+	const double h = std::sqrt(2.0) / 2.0;
+	if (M == 2) {
+		re = {1, -1}, im = {0, 0};
+	} else if (M == 4) {
+		re = {-1, -1, 1, 1}, im = {1, -1, 1, -1};
+	} else if (M == 8) {
+		re = {-h, -1, 0, -h, 0, h, h, 1}, im = {-h, 0, 1, h, -1, -h, h, 0};
+	} else if (M == 16) {
+		for (int i = 0; i < 16; i++) re[i] = q16[i][0], im[i] = q16[i][1];
+	} else {
+		for (int i = 0; i < 32; i++) re[i] = q32[i][0], im[i] = q32[i][1];
+	}
+	float pn = 0;
+	for (int i = 0; i < M; i++) pn = (float)((double)pn + re[i] * re[i] + im[i] * im[i]);
+	pn = (float)(1.0 / std::sqrt((double)(pn / M)));
+	out.resize(2 * M);
+	for (int i = 0; i < M; i++) {
+		out[2 * i] = (float)(re[i] * (double)pn);
+		out[2 * i + 1] = (float)(im[i] * (double)pn);
+	}
+}
+
+uint16_t crc_zero_byte(uint16_t s)  // advance the reflected CRC-16/MODBUS register over one zero byte
+{
+	for (int i = 0; i < 8; i++) s = (s & 1) ? (uint16_t)((s >> 1) ^ 0xA001) : (uint16_t)(s >> 1);
+	return s;
+}
+
+std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<uint16_t> &var_of_cw, MbMode &m)
+{
+	const ModeDef &d = kModes[cfg];
+	memset(&m, 0, sizeof(m));
+	m.config = cfg, m.M = d.M, m.rate_num = d.rate, m.rate_idx = mb_rate_index(d.rate);
+	m.bps = 0;
+	while ((1 << m.bps) < d.M) m.bps++;
+	m.Nsymb = nsymb_of(d.M), m.estimator = d.est, m.preamble_nSymb = d.pre;
+	m.phase_only = (d.M == 2 || d.M == 4 || d.M == 8);  // telecom_system.cc:2647-2654
+	m.boost = 1.33f;				    // physical_config.cc:46
+	m.K = rate.K, m.P = rate.P;
+	const int S = m.Nsymb, C = MB_NC, cells = S * C;
+
+	// pilot lattice (ofdm.cc:976-1064 with Dx=1, Dy=3, edges DATA): pilot iff s%3 == c%3.  The kernels rely on
+	// this closed form (row sums step by 3), so it is built by the reference's walk and then verified.
+	std::vector<uint8_t> is_pilot(cells, 0);
+	{
+		const int ncm = std::max(C, S), Dx = 1, Dy = 3;
+		std::vector<uint8_t> v((size_t)ncm * ncm, 0);
+		for (int x = 0, y = 0; x < ncm && y < ncm; y++, x += Dx) {
+			for (int j = y; j < ncm; j += Dy) v[j * ncm + x] = 1;
+			for (int j = y; j >= 0; j -= Dy) v[j * ncm + x] = 1;
+		}
+		int cnt = 0;
+		for (int j = 0; j < S; j++) cnt += v[j * ncm + C - 1];
+		if (cnt < 2)
+			for (int j = 0; j < ncm; j++) v[j * ncm + C - 1] = v[j * ncm];
+		for (int s = 0; s < S; s++)
+			for (int c = 0; c < C; c++) {
+				is_pilot[s * C + c] = v[s * ncm + c];
+				if ((v[s * ncm + c] != 0) != ((s % 3) == (c % 3))) return "pilot lattice is not s%3==c%3";
+			}
+	}
+	std::vector<float> pval(cells, 0.f), pinv(cells, 0.f), invn(cells, 0.f);
+	std::vector<uint16_t> pilot_cell, data_cell;
+	{
+		uint32_t st[35];
+		mb_srandom(st, 0);  // ofdm.cc:940-951, seed physical_config.cc:47
+		int last = 0;
+		for (int i = 0; i < cells; i++) {
+			if (!is_pilot[i]) {
+				data_cell.push_back((uint16_t)i);
+				continue;
+			}
+			int pv = (mb_random(st) % 2) ^ last;
+			last = pv;
+			double p = (double)(2 * pv - 1) * (double)m.boost;
+			pval[i] = (float)p;
+			pinv[i] = (float)(1.0 / p);
+			pilot_cell.push_back((uint16_t)i);
+		}
+	}
+	m.nPilots = (int)pilot_cell.size();
+	m.nData = (int)data_cell.size();
+	for (int s = 0; s < S; s++)  // pilots inside the clipped 21x21 window (ofdm.cc:1364-1390)
+		for (int c = 0; c < C; c++) {
+			if (!is_pilot[s * C + c]) continue;
+			int n = 0;
+			for (int k = std::max(0, s - MB_LS_HALF); k <= std::min(S - 1, s + MB_LS_HALF); k++)
+				for (int l = std::max(0, c - MB_LS_HALF); l <= std::min(C - 1, c + MB_LS_HALF); l++) n += is_pilot[k * C + l];
+			invn[s * C + c] = (float)(1.0 / n);
+		}
+	m.nBits = m.nData * m.bps;  // data_container.cc:90-172
+	m.nReal = m.nBits - m.P;
+	m.nVirtual = MB_N - m.nBits;
+	m.frame_bytes = (m.nReal - 16) / 8;  // telecom_system.cc:332-335
+	if (m.nReal <= 16 || m.nVirtual < 0 || m.nReal + m.nVirtual != m.K) return "inconsistent frame geometry";
+
+	// symbol q of the demapper input <- grid cell: deframer (ofdm.cc:837-852) then complex de-interleaver
+	// (interleaver.cc:94-109, block nData/10, telecom_system.cc:2911)
+	std::vector<uint16_t> sym_cell(m.nData);
+	{
+		int bs = m.nData / 10, nb = m.nData / bs;
+		for (int q = 0; q < m.nData; q++) {
+			int src = q;
+			if (q < nb * bs) src = (q % bs) * nb + q / bs;
+			sym_cell[q] = data_cell[src];
+		}
+	}
+	// LLR i of the demapper -> float de-interleaver (interleaver.cc:77-92, block nBits/10, :2910) -> expand
+	// (telecom_system.cc:1300-1308) -> internal variable numbering of the decoder
+	std::vector<uint16_t> dst(m.nBits), dst2(m.nBits, MB_NO_DST);
+	{
+		int bs = m.nBits / 10, nb = m.nBits / bs;
+		for (int i = 0; i < m.nBits; i++) {
+			int j = i;
+			if (i < nb * bs) j = (i % nb) * bs + i / nb;
+			int cw = j < m.nReal ? j : j + m.nVirtual;
+			dst[i] = var_of_cw[cw];
+			if (j < m.nVirtual) dst2[i] = var_of_cw[m.nReal + j];
+		}
+	}
+	std::vector<float> cons;
+	build_constellation(m.M, cons);
+
+	m.crc_bytes = m.nReal / 8;
+	std::vector<uint16_t> bit_var(8 * m.crc_bytes);
+	std::vector<uint8_t> scr(MB_N);
+	{
+		uint32_t st[35];
+		mb_srandom(st, 0);  // telecom_system.cc:1961-1966 (bit_energy_dispersal_seed = 0), N draws
+		for (int i = 0; i < MB_N; i++) scr[i] = (uint8_t)(mb_random(st) % 2);
+		for (int i = 0; i < 8 * m.crc_bytes; i++) bit_var[i] = var_of_cw[i];
+	}
+	// warp-parallel CRC: lane l owns bytes [l*chunk, (l+1)*chunk); its partial CRC (preset 0) is advanced over the
+	// bytes that follow by a 16x16 GF(2) matrix; the 0xFFFF preset contributes a constant.
+	m.crc_chunk = (m.crc_bytes + 31) / 32;
+	std::vector<uint16_t> crcmat(32 * 16, 0);
+	for (int l = 0; l < 32; l++) {
+		int end = std::min(m.crc_bytes, (l + 1) * m.crc_chunk);
+		int follow = std::max(0, m.crc_bytes - end);
+		for (int b = 0; b < 16; b++) {
+			uint16_t s = (uint16_t)(1u << b);
+			for (int i = 0; i < follow; i++) s = crc_zero_byte(s);
+			crcmat[l * 16 + b] = s;
+		}
+	}
+	{
+		uint16_t s = 0xFFFF;
+		for (int i = 0; i < m.crc_bytes; i++) s = crc_zero_byte(s);
+		m.crc_init = s;
+	}
+	m.off_pinv = bl.put(pinv);
+	m.off_pval = bl.put(pval);
+	m.off_invn = bl.put(invn);
+	m.off_pilot_cell = bl.put(pilot_cell);
+	m.off_sym_cell = bl.put(sym_cell);
+	m.off_llr_dst = bl.put(dst);
+	m.off_llr_dst2 = bl.put(dst2);
+	m.off_const = bl.put(cons);
+	m.off_bit_var = bl.put(bit_var);
+	m.off_scr = bl.put(scr);
+	m.off_crcmat = bl.put(crcmat);
+	return "";
+}
+
+}  // namespace
+
+std::string mb_build_blob(const char *ldpc_blob_path, std::vector<uint8_t> &out)
+{
+	std::vector<RateTables> rt;
+	std::string err;
+	if (!load_ldpc_file(ldpc_blob_path, rt, err)) return err;
+	Blob bl;
+	bl.reserve(sizeof(MbBlobHeader));
+	MbBlobHeader hdr;
+	memset(&hdr, 0, sizeof(hdr));
+	hdr.magic = MB_BLOB_MAGIC, hdr.version = MB_BLOB_VERSION;
+	{
+		// FFT-256 as 16x16: tw[k1*16+n2] = exp(-2 pi i n2 k1 / 256) / 256 (the 1/N of ofdm.cc:439-442 folded in)
+		std::vector<float> tw(2 * 256);
+		for (int k1 = 0; k1 < 16; k1++)
+			for (int n2 = 0; n2 < 16; n2++) {
+				double a = -2.0 * M_PI * (double)(n2 * k1) / 256.0;
+				tw[2 * (k1 * 16 + n2)] = (float)(std::cos(a) / 256.0);
+				tw[2 * (k1 * 16 + n2) + 1] = (float)(std::sin(a) / 256.0);
+			}
+		hdr.off_twiddle = bl.put(tw);
+	}
+	std::vector<std::vector<uint16_t>> var_of_cw(MB_NRATES);
+	for (int r = 0; r < MB_NRATES; r++) {
+		int idx = mb_rate_index(rt[r].rate_num);
+		if (idx < 0) return "unknown LDPC rate in table file";
+		err = build_rate(bl, rt[r], hdr.rates[idx], var_of_cw[idx]);
+		if (!err.empty()) return err;
+	}
+	for (int c = 0; c < MB_NMODES; c++) {
+		int idx = mb_rate_index(kModes[c].rate);
+		err = build_mode(bl, c, hdr.rates[idx], var_of_cw[idx], hdr.modes[c]);
+		if (!err.empty()) return "mode " + std::to_string(c) + ": " + err;
+	}
+	bl.reserve(0, 256);
+	hdr.total_bytes = (uint32_t)bl.b.size();
+	memcpy(bl.b.data(), &hdr, sizeof(hdr));
+	out.swap(bl.b);
+	return "";
+}
+
+std::string mb_validate_blob(const uint8_t *blob, size_t size)
+{
+	if (size < sizeof(MbBlobHeader)) return "table blob too small";
+	MbBlobHeader h;
+	memcpy(&h, blob, sizeof(h));
+	if (h.magic != MB_BLOB_MAGIC) return "table blob: bad magic";
+	if (h.version != MB_BLOB_VERSION) return "table blob: version mismatch";
+	if (h.total_bytes != size) return "table blob: size mismatch";
+	auto in = [&](uint32_t off, size_t bytes) { return (size_t)off + bytes <= size; };
+	if (!in(h.off_twiddle, 2 * 256 * 4)) return "table blob: twiddle out of range";
+	for (int r = 0; r < MB_NRATES; r++) {
+		const MbRate &t = h.rates[r];
+		if (t.N != MB_N || t.n_edges <= 0 || t.n_edges > 8192 || t.P <= 0 || t.P >= MB_N) return "table blob: bad rate record";
+		if (!in(t.off_cdeg, t.P) || !in(t.off_coff, 4 * (MB_MAX_CDEG + 1)) || !in(t.off_edge_var, 2 * (size_t)t.n_edges) ||
+		    !in(t.off_vdeg, t.N) || !in(t.off_voff, 4 * (MB_MAX_VDEG + 1)) || !in(t.off_vedge, 2 * (size_t)t.n_edges) ||
+		    !in(t.off_var_of_cw, 2 * (size_t)t.N))
+			return "table blob: rate table out of range";
+	}
+	for (int c = 0; c < MB_NMODES; c++) {
+		const MbMode &m = h.modes[c];
+		size_t cells = (size_t)m.Nsymb * MB_NC;
+		if (m.config != c || m.Nsymb <= 0 || m.Nsymb > MB_MAX_SYMB || m.rate_idx < 0 || m.rate_idx >= MB_NRATES || m.nBits > MB_N)
+			return "table blob: bad mode record";
+		if (!in(m.off_pinv, 4 * cells) || !in(m.off_pval, 4 * cells) || !in(m.off_invn, 4 * cells) ||
+		    !in(m.off_pilot_cell, 2 * (size_t)m.nPilots) || !in(m.off_sym_cell, 2 * (size_t)m.nData) ||
+		    !in(m.off_llr_dst, 2 * (size_t)m.nBits) || !in(m.off_llr_dst2, 2 * (size_t)m.nBits) || !in(m.off_const, 8 * (size_t)m.M) ||
+		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16))
+			return "table blob: mode table out of range";
+	}
+	return "";
+}

@@ -1,0 +1,91 @@
+// mb_tables.h -- mode / code tables of the B200 RX path, as one relocatable blob.
+//
+// Everything the kernels need besides the samples lives in ONE contiguous byte blob built on the host at
+// mercury_b200_load_tables() time: the per-mode (CONFIG_0..16) demodulator tables and the per-rate LDPC
+// graphs.  The blob is position independent (tables are addressed by byte offsets from its start), so it is
+// (a) uploaded to HBM with a single copy, (b) kept resident for ALL 17 modes so that load_configuration()
+// is O(1) (ARQ flips between data and ack configurations every batch), and (c) the thing rank 0
+// broadcasts over NCCL to the other GPUs (north_star: "NCCL broadcast of the codeword tables").
+//
+// Reference anchors (paths relative to /root/reference):
+//   mode table            source/physical_layer/telecom_system.cc:2506-2654
+//   pilot lattice/sequence source/physical_layer/ofdm.cc:904-1064
+//   constellations        source/physical_layer/psk.cc:65-256
+//   (de)interleavers      source/physical_layer/interleaver.cc:26-117
+//   LLR expand            source/physical_layer/telecom_system.cc:1300-1308
+//   scrambler             source/physical_layer/telecom_system.cc:1961-1966
+//   LDPC tables           source/physical_layer/mercury_normal_*_16.cc via mercury_b200/data/ldpc_tables.bin
+#pragma once
+#include <cstdint>
+
+#define MB_N 1600
+#define MB_NC 50
+#define MB_NFFT 256
+#define MB_NGI 16
+#define MB_NOFDM 272
+#define MB_NMODES 17
+#define MB_NRATES 8
+#define MB_MAX_SYMB 48
+#define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
+#define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
+#define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
+#define MB_BLOB_VERSION 3u
+#define MB_NO_DST 0xFFFFu
+#define MB_MAX_CDEG 48
+#define MB_MAX_VDEG 16
+
+struct MbRate {
+	int32_t rate_num, N, K, P, n_edges;
+	int32_t max_cdeg, max_vdeg;
+	int32_t c_slots;  // check-side JDS slots (== n_edges, no padding needed: slices are dense)
+	// check side, checks sorted by degree (descending): slot(k, c') = coff[k] + c'
+	uint32_t off_cdeg;      // u8 [P]            degree of sorted check c'
+	uint32_t off_coff;      // u32[MB_MAX_CDEG+1] slice offsets
+	uint32_t off_edge_var;  // u16[n_edges]      internal variable index of each check-side slot
+	// variable side, variables renumbered by degree (descending): vslot(k, v') = voff[k] + v'
+	uint32_t off_vdeg;      // u8 [N]
+	uint32_t off_voff;      // u32[MB_MAX_VDEG+1]
+	uint32_t off_vedge;     // u16[n_edges]      check-side slot id held by each variable-side slot
+	uint32_t off_var_of_cw; // u16[N]            codeword position -> internal variable index
+	uint32_t off_check_of_sorted; // u16[P]      sorted check c' -> reference check index (diagnostics)
+};
+
+struct MbMode {
+	int32_t config, M, bps, rate_idx, rate_num;
+	int32_t Nsymb, nData, nPilots, nBits, nReal, nVirtual, K, P;
+	int32_t frame_bytes, estimator /*0 ZF, 1 LS*/, phase_only, preamble_nSymb;
+	int32_t crc_bytes;      // nReal/8: bytes covered by the CRC self check
+	int32_t crc_chunk;      // bytes per lane in the warp-parallel CRC
+	uint32_t crc_init;      // contribution of the 0xFFFF preset after crc_bytes bytes
+	float boost;
+	uint32_t off_pinv;       // f32[cells]  1/p at pilot cells, 0 at data cells
+	uint32_t off_pval;       // f32[cells]  p at pilot cells, 0 at data cells
+	uint32_t off_invn;       // f32[cells]  1/(pilots inside the clipped LS window) at pilot cells
+	uint32_t off_pilot_cell; // u16[nPilots] row-major pilot cell indices
+	uint32_t off_sym_cell;   // u16[nData]  grid cell feeding demapped symbol q (deframe o T/F de-interleave)
+	uint32_t off_llr_dst;    // u16[nBits]  internal variable receiving LLR i (bit de-interleave o expand o renumber)
+	uint32_t off_llr_dst2;   // u16[nBits]  second destination for the virtual-bit copies, MB_NO_DST if none
+	uint32_t off_const;      // f32[2*M]    constellation (re,im), unit mean power
+	uint32_t off_bit_var;    // u16[8*crc_bytes] internal variable of info bit i
+	uint32_t off_scr;        // u8 [N]      scrambler bit i (bit_energy_dispersal sequence)
+	uint32_t off_crcmat;     // u16[32*16]  per-lane "advance CRC by the bytes that follow my chunk" matrices
+};
+
+struct MbBlobHeader {
+	uint32_t magic, version, total_bytes, reserved;
+	uint32_t off_twiddle;    // f32[2*256]  tw[k1*16+n2] = exp(-2 pi i n2 k1/256)/256
+	uint32_t pad[3];
+	MbMode modes[MB_NMODES];
+	MbRate rates[MB_NRATES];
+};
+
+#include <string>
+#include <vector>
+// Builds the blob from the LDPC table file. Returns an empty string on success, else an error message.
+std::string mb_build_blob(const char *ldpc_blob_path, std::vector<uint8_t> &out);
+// Sanity-check an imported blob (magic / version / size / offset bounds).
+std::string mb_validate_blob(const uint8_t *blob, size_t size);
+// glibc TYPE_3 random() as vendored by the reference (os_interop.cc:100-283); state[34] is the ring cursor.
+void mb_srandom(uint32_t state[35], unsigned seed);
+int mb_random(uint32_t state[35]);
+int mb_rate_index(int rate_num);

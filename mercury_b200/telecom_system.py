@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference's physical-layer RX interface over the C ABI.
+
+Reference: class cl_telecom_system (include/physical_layer/telecom_system.h:85-199) -- the three calls the
+datalink layer makes into the physical layer are load_configuration(int), receive_byte(double*, int*) and
+get_frame_size_bytes()/bits() (INTERNALS:11, source/datalink_layer/arq_common.cc:627,2668).  TelecomSystemB200
+keeps those names, argument meaning and error behaviour (no exceptions from the receive call: a frame that
+does not decode comes back with message_decoded == NO and SNR == -99.9), for the part of receive_byte() that
+north_star moves to the GPU: everything after time/frequency synchronisation (telecom_system.cc:1132-1429).
+
+All arithmetic happens in mercury_b200/libmercury_b200.so (CUDA, sm_100a).  numpy / torch are used only to
+hold buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Geometry, RxStats
+
+YES, NO = 1, 0
+DECODER_SPA, DECODER_MINSUM = 0, 1
+
+STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("message_decoded", "<i4"),
+                        ("SNR", "<f4"), ("variance", "<f4"), ("mean_H", "<f4"), ("reserved", "<i4")])
+assert STATS_DTYPE.itemsize == C.sizeof(RxStats) == 32
+
+
+class MercuryB200Error(RuntimeError):
+    pass
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor (host or device)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class TelecomSystemB200:
+    """One long-lived RX object per GPU, like the reference's cl_telecom_system."""
+
+    def __init__(self, device=0, ldpc_table_path=None, tables_blob=None):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.mercury_b200_create(int(device), C.byref(h))
+        if rc != 0:
+            raise MercuryB200Error(f"mercury_b200_create(device={device}): {self._L.mercury_b200_strerror(rc).decode()}")
+        self._h = h
+        self.device = int(device)
+        if tables_blob is not None:
+            buf = np.frombuffer(bytes(tables_blob), np.uint8) if not isinstance(tables_blob, np.ndarray) else tables_blob
+            self._check(self._L.mercury_b200_import_tables(self._h, _vp(buf), buf.size))
+        else:
+            path = ldpc_table_path or _lib.LDPC_TABLES
+            self._check(self._L.mercury_b200_load_tables(self._h, path.encode()))
+        self.current_configuration = -1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mercury_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.mercury_b200_last_error(self._h).decode()
+            raise MercuryB200Error(f"{self._L.mercury_b200_strerror(rc).decode()}: {msg}")
+
+    # ---- reference surface -------------------------------------------------------------------------------
+    def load_configuration(self, configuration, ldpc_nIteration_max=50):
+        """cl_telecom_system::load_configuration(int) (+ the CLI's -I). O(1): all 17 modes stay resident."""
+        self._check(self._L.mercury_b200_load_configuration(self._h, int(configuration), int(ldpc_nIteration_max)))
+        self.current_configuration = int(configuration)
+        g = Geometry()
+        self._check(self._L.mercury_b200_get_geometry(self._h, C.byref(g)))
+        self.geometry = {n: getattr(g, n) for n, _ in Geometry._fields_}
+        return self.geometry
+
+    def set_decoder(self, decoder):
+        self._check(self._L.mercury_b200_set_decoder(self._h, int(decoder)))
+        if self.current_configuration >= 0:
+            self.geometry["decoder"] = int(decoder)
+
+    def get_frame_size_bytes(self):
+        return self._L.mercury_b200_get_frame_size_bytes(self._h)
+
+    def get_frame_size_bits(self):
+        return self._L.mercury_b200_get_frame_size_bits(self._h)
+
+    def receive_baseband(self, baseband):
+        """The tail of receive_byte() on one synchronised frame: baseband = Nsymb*272 complex128 samples.
+        Returns (out, stats): out = one int per payload byte (like `int* out`), stats = dict of st_receive_stats fields."""
+        g = self.geometry
+        bb = np.ascontiguousarray(baseband, np.complex128).reshape(-1)
+        if bb.size != g["Nsymb"] * g["Nofdm"]:
+            raise ValueError("baseband must hold Nsymb*Nofdm complex samples")
+        out = np.zeros(g["frame_bytes"], np.int32)
+        st = RxStats()
+        self._check(self._L.mercury_b200_receive_baseband(self._h, _vp(bb), _vp(out), C.byref(st)))
+        return out, {n: getattr(st, n) for n, _ in RxStats._fields_ if n != "reserved"}
+
+    # ---- batched entry points ----------------------------------------------------------------------------
+    def demod_decode_batch(self, baseband, want_llr=False, out=None):
+        """Host buffers: baseband [B, Nsymb, 272] complex64 (or float32 [..., 2]). Returns (payload[B,frame_bytes] u8, stats[B], llr_cw|None)."""
+        g = self.geometry
+        bb = np.ascontiguousarray(baseband)
+        if bb.dtype == np.complex64:
+            bb = bb.view(np.float32)
+        if bb.dtype != np.float32:
+            raise TypeError("baseband must be complex64 / float32")
+        per = g["Nsymb"] * g["Nofdm"] * 2
+        if bb.size % per:
+            raise ValueError("baseband size is not a whole number of frames")
+        n = bb.size // per
+        if out is None:
+            payload = np.zeros((n, g["frame_bytes"]), np.uint8)
+            stats = np.zeros(n, STATS_DTYPE)
+        else:
+            payload, stats = out
+        llr = np.zeros((n, g["N"]), np.float32) if want_llr else None
+        self._check(self._L.mercury_b200_demod_decode_batch(self._h, _vp(bb), n, _vp(payload), _vp(stats), _vp(llr)))
+        return payload, stats, llr
+
+    def demod_decode_batch_device(self, d_baseband, n_frames, d_payload, d_stats, d_llr_cw=None, stream=0):
+        self._check(self._L.mercury_b200_demod_decode_batch_device(self._h, _vp(d_baseband), int(n_frames), _vp(d_payload),
+                                                                   _vp(d_stats), _vp(d_llr_cw), C.c_void_p(stream)))
+
+    def demod_batch_device(self, d_baseband, n_frames, d_llr, d_stats, d_llr_cw=None, stream=0):
+        self._check(self._L.mercury_b200_demod_batch_device(self._h, _vp(d_baseband), int(n_frames), _vp(d_llr), _vp(d_stats),
+                                                            _vp(d_llr_cw), C.c_void_p(stream)))
+
+    def ldpc_decode_batch_device(self, d_llr, n_frames, d_payload, d_stats, stream=0):
+        self._check(self._L.mercury_b200_ldpc_decode_batch_device(self._h, _vp(d_llr), int(n_frames), _vp(d_payload), _vp(d_stats),
+                                                                  C.c_void_p(stream)))
+
+    def set_debug_capture(self, d_Y=None, d_H=None, d_Z=None):
+        self._check(self._L.mercury_b200_set_debug_capture(self._h, _vp(d_Y), _vp(d_H), _vp(d_Z)))
+
+    def export_tables(self):
+        n = C.c_size_t(0)
+        self._check(self._L.mercury_b200_export_tables(self._h, None, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        self._check(self._L.mercury_b200_export_tables(self._h, _vp(buf), C.byref(n)))
+        return buf
+
+    def synchronize(self):
+        self._check(self._L.mercury_b200_synchronize(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.mercury_b200_kernel_launches(self._h))
+
+
+def build_tables_host(ldpc_table_path=None):
+    """The table blob, built on the host (no device needed)."""
+    L = _lib.lib()
+    path = (ldpc_table_path or _lib.LDPC_TABLES).encode()
+    n = C.c_size_t(0)
+    rc = L.mercury_b200_build_tables_host(path, None, C.byref(n))
+    if rc != 0:
+        raise MercuryB200Error(L.mercury_b200_strerror(rc).decode())
+    buf = np.zeros(n.value, np.uint8)
+    rc = L.mercury_b200_build_tables_host(path, _vp(buf), C.byref(n))
+    if rc != 0:
+        raise MercuryB200Error(L.mercury_b200_strerror(rc).decode())
+    return buf
+
+
+def synth_frames(config, n_frames, seed=0, esn0_db=300.0, payload=None, n_threads=0, out=None, ldpc_table_path=None):
+    """Synthetic baseband frames (host TX chain + AWGN). Returns (baseband[B,Nsymb,272] complex64, payload[B,frame_bytes] u8)."""
+    import os
+    L = _lib.lib()
+    from .modes import MODES
+    m = MODES[config]
+    fb = m["frame_bytes"]
+    if out is None:
+        out = np.zeros((n_frames, m["Nsymb"], 272), np.complex64)
+    pl_out = np.zeros((n_frames, fb), np.uint8)
+    pin = None
+    if payload is not None:
+        pin = np.ascontiguousarray(payload, np.uint8).reshape(n_frames, fb)
+    if n_threads <= 0:
+        n_threads = max(1, (os.cpu_count() or 1))
+    rc = L.mercury_b200_synth_frames((ldpc_table_path or _lib.LDPC_TABLES).encode(), int(config), int(n_frames), int(seed),
+                                     float(esn0_db), _vp(pin), _vp(out), _vp(pl_out), int(n_threads))
+    if rc != 0:
+        raise MercuryB200Error(L.mercury_b200_strerror(rc).decode())
+    return out, pl_out

@@ -1,0 +1,192 @@
+"""numpy walk-through of the table blob, mirroring the index logic of the CUDA kernels (csrc/mb_demod.cu,
+csrc/mb_ldpc.cu) step by step.  It exists to pin the HOST-built tables (gather/scatter indices, JDS graph,
+CRC matrices) against the oracle on a machine without a GPU; it is test code, not a fallback."""
+import numpy as np
+
+MB_NC, MB_N, MAX_CDEG, MAX_VDEG = 50, 1600, 48, 16
+
+RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "max_cdeg", "max_vdeg", "c_slots")] +
+                   [(n, "<u4") for n in ("off_cdeg", "off_coff", "off_edge_var", "off_vdeg", "off_voff", "off_vedge",
+                                         "off_var_of_cw", "off_check_of_sorted")])
+MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate_num", "Nsymb", "nData", "nPilots", "nBits",
+                                         "nReal", "nVirtual", "K", "P", "frame_bytes", "estimator", "phase_only",
+                                         "preamble_nSymb", "crc_bytes", "crc_chunk")] +
+                   [("crc_init", "<u4"), ("boost", "<f4")] +
+                   [(n, "<u4") for n in ("off_pinv", "off_pval", "off_invn", "off_pilot_cell", "off_sym_cell", "off_llr_dst",
+                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat")])
+HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("reserved", "<u4"), ("off_twiddle", "<u4"),
+                   ("pad", "<u4", (3,)), ("modes", MODE_DT, (17,)), ("rates", RATE_DT, (8,))])
+
+
+class Blob:
+    def __init__(self, buf):
+        self.b = np.ascontiguousarray(buf, np.uint8)
+        self.hdr = np.frombuffer(self.b[:HDR_DT.itemsize].tobytes(), HDR_DT)[0]
+        assert self.hdr["magic"] == 0x42324D42 and self.hdr["total_bytes"] == self.b.size
+
+    def arr(self, off, dtype, n):
+        dt = np.dtype(dtype)
+        return np.frombuffer(self.b[int(off):int(off) + dt.itemsize * int(n)].tobytes(), dt)
+
+    def mode(self, cfg):
+        m = self.hdr["modes"][cfg]
+        cells = int(m["Nsymb"]) * MB_NC
+        d = {k: (int(m[k]) if k != "boost" else float(m[k])) for k in MODE_DT.names if not k.startswith("off_")}
+        d.update(pinv=self.arr(m["off_pinv"], "<f4", cells), pval=self.arr(m["off_pval"], "<f4", cells),
+                 invn=self.arr(m["off_invn"], "<f4", cells), pilot_cell=self.arr(m["off_pilot_cell"], "<u2", m["nPilots"]),
+                 sym_cell=self.arr(m["off_sym_cell"], "<u2", m["nData"]), llr_dst=self.arr(m["off_llr_dst"], "<u2", m["nBits"]),
+                 llr_dst2=self.arr(m["off_llr_dst2"], "<u2", m["nBits"]),
+                 cons=self.arr(m["off_const"], "<f4", 2 * m["M"]).view(np.complex64),
+                 bit_var=self.arr(m["off_bit_var"], "<u2", 8 * m["crc_bytes"]), scr=self.arr(m["off_scr"], "u1", MB_N),
+                 crcmat=self.arr(m["off_crcmat"], "<u2", 512).reshape(32, 16))
+        return d
+
+    def rate(self, idx):
+        r = self.hdr["rates"][idx]
+        d = {k: int(r[k]) for k in RATE_DT.names if not k.startswith("off_")}
+        d.update(cdeg=self.arr(r["off_cdeg"], "u1", r["P"]), coff=self.arr(r["off_coff"], "<u4", MAX_CDEG + 1),
+                 edge_var=self.arr(r["off_edge_var"], "<u2", r["n_edges"]), vdeg=self.arr(r["off_vdeg"], "u1", r["N"]),
+                 voff=self.arr(r["off_voff"], "<u4", MAX_VDEG + 1), vedge=self.arr(r["off_vedge"], "<u2", r["n_edges"]),
+                 var_of_cw=self.arr(r["off_var_of_cw"], "<u2", r["N"]),
+                 check_of_sorted=self.arr(r["off_check_of_sorted"], "<u2", r["P"]))
+        return d
+
+    def twiddle(self):
+        return self.arr(self.hdr["off_twiddle"], "<f4", 512).view(np.complex64).reshape(16, 16)
+
+
+def demod(blob, cfg, x):
+    """x: [Nsymb,272] complex64 -> dict(Y,H,Z grids, llr_internal, llr_cw, variance, mean_H, snr) in float32 arithmetic."""
+    m = blob.mode(cfg)
+    r = blob.rate(m["rate_idx"])
+    S = m["Nsymb"]
+    f32, c64 = np.float32, np.complex64
+    # FFT-256 as 16x16 with the blob's twiddle table (1/256 folded in): X[k1+16k2] = sum_n2 W16^(n2 k2) tw[k1,n2] A[n2,k1]
+    tw = blob.twiddle()
+    xs = np.asarray(x).reshape(S, 272)[:, 16:].astype(c64).reshape(S, 16, 16)  # [s, n1, n2]
+    A = np.fft.fft(xs.astype(np.complex128), axis=1).astype(c64)  # over n1 -> [s, k1, n2]
+    B = (A * tw[None, :, :]).astype(c64)
+    X = np.fft.fft(B.astype(np.complex128), axis=2).astype(c64)   # over n2 -> [s, k1, k2]
+    bins = np.zeros((S, 256), c64)
+    for k1 in range(16):
+        for k2 in range(16):
+            bins[:, k1 + 16 * k2] = X[:, k1, k2]
+    Y = np.concatenate([bins[:, 231:256], bins[:, 1:26]], axis=1).reshape(-1)
+    pc = m["pilot_cell"].astype(np.int64)
+    g = f32(m["boost"]) / f32(np.abs(Y[pc]).astype(f32).sum(dtype=f32) / f32(m["nPilots"]))
+    H = np.zeros(S * MB_NC, c64)
+    if m["estimator"] == 1:
+        zf = (Y * m["pinv"]).astype(c64).reshape(S, MB_NC)
+        T = np.zeros((S, MB_NC), c64)
+        for c in range(MB_NC):
+            lo, hi = max(0, c - 10), min(MB_NC - 1, c + 10)
+            T[:, c] = zf[:, lo:hi + 1].sum(axis=1) * g
+        for cell in pc:
+            s, c = divmod(int(cell), MB_NC)
+            k0, k1 = max(0, s - 10), min(S - 1, s + 10)
+            H[cell] = T[k0:k1 + 1, c].sum() * m["invn"][cell]
+    else:
+        H[pc] = (Y[pc] * g) * m["pinv"][pc]
+    Hg = H.reshape(S, MB_NC).copy()
+    is_p = np.zeros(S * MB_NC, bool)
+    is_p[pc] = True
+    for cell in range(S * MB_NC):
+        if is_p[cell]:
+            continue
+        s, c = divmod(cell, MB_NC)
+        f = c % 3
+        last = f + 3 * ((S - 1 - f) // 3)
+        r0 = f if s < f else (last - 3 if s > last else s - ((s - f) % 3))
+        a, b = Hg[r0, c], Hg[r0 + 3, c]
+        H[cell] = a + (b - a) * f32(s - r0) / f32(3)
+    mean_H = f32(np.abs(H[pc]).mean())
+    Hraw = H.copy()
+    if m["phase_only"]:
+        H = np.where(H.real == 0, c64(1j), H / np.abs(H)).astype(c64)
+    Yg = (Y * g).astype(c64)
+    Z = (Yg / H).astype(c64)
+    variance = f32(max((np.abs(Z[pc] - m["pval"][pc]) ** 2).mean(), 1e-30))
+    v_rep = f32((np.abs(Yg[pc] / Hraw[pc] - m["pval"][pc]) ** 2).mean()) if m["phase_only"] else variance
+    w = Z[m["sym_cell"].astype(np.int64)]
+    D = (np.abs(w[:, None] - m["cons"][None, :]) ** 2).astype(f32)  # [nData, M]
+    bps = m["bps"]
+    L = np.zeros(MB_N, f32)
+    lam = np.zeros(m["nBits"], f32)
+    idx = np.arange(m["M"])
+    for k in range(bps):
+        one = ((idx >> k) & 1) == 1
+        lam[np.arange(m["nData"]) * bps + (bps - 1 - k)] = (f32(1) / variance) * (D[:, one].min(axis=1) - D[:, ~one].min(axis=1))
+    L[m["llr_dst"].astype(np.int64)] = lam
+    has2 = m["llr_dst2"] != 0xFFFF
+    L[m["llr_dst2"][has2].astype(np.int64)] = lam[has2]
+    snr = float(10 * np.log10(1.0 / v_rep)) if m["estimator"] == 1 else 0.0
+    return dict(Y=Yg.reshape(S, MB_NC), H=H.reshape(S, MB_NC), Z=Z.reshape(S, MB_NC), llr_demod=lam, llr_internal=L,
+                llr_cw=L[r["var_of_cw"].astype(np.int64)], variance=variance, mean_H=mean_H, snr=snr)
+
+
+def ldpc_decode(blob, cfg, llr_internal, max_iters):
+    """Flooding SPA on the JDS graph exactly as scheduled by mb_ldpc.cu (double precision tanh rule). -> (iterations, posterior)."""
+    m = blob.mode(cfg)
+    r = blob.rate(m["rate_idx"])
+    P, N, E = r["P"], r["N"], r["n_edges"]
+    cdeg, coff, ev = r["cdeg"].astype(int), r["coff"].astype(int), r["edge_var"].astype(int)
+    vdeg, voff, ve = r["vdeg"].astype(int), r["voff"].astype(int), r["vedge"].astype(int)
+    lch = llr_internal.astype(np.float64)
+    lam = lch.copy()
+    R = np.zeros(E)
+    rows = [[coff[k] + c for k in range(cdeg[c])] for c in range(P)]
+    vrows = [[ve[voff[k] + v] for k in range(vdeg[v])] for v in range(N)]
+    p = 0
+    while True:
+        unsat = False
+        newR = R.copy()
+        for c in range(P):
+            e = rows[c]
+            v = ev[e]
+            if (lam[v] < 0).sum() & 1:
+                unsat = True
+            q = lam[v] - R[e]
+            t = np.tanh(0.5 * q)
+            for i in range(len(e)):
+                prod = np.prod(np.delete(t, i))
+                if prod == 1:
+                    prod = 0.9999999
+                if prod == -1:
+                    prod = -0.9999999
+                newR[e[i]] = 2 * np.arctanh(prod)
+        if not unsat:
+            return p, lam
+        if p == max_iters:
+            return max_iters + 1, lam
+        R = newR
+        for v in range(N):
+            acc = lch[v]
+            for e in vrows[v]:
+                acc += R[e]
+            lam[v] = acc
+        p += 1
+
+
+def finish(blob, cfg, posterior):
+    """hard decision -> de-scramble -> pack -> warp-parallel CRC exactly as mb_ldpc.cu. -> (bytes[crc_bytes], crc, all_zeros)."""
+    m = blob.mode(cfg)
+    nb = m["crc_bytes"]
+    bits = (posterior[m["bit_var"].astype(int)] < 0).astype(np.uint8) ^ m["scr"][: 8 * nb]
+    by = np.zeros(nb, np.uint8)
+    for b in range(8):
+        by |= (bits[b::8] << b).astype(np.uint8)
+    adv = 0
+    for lane in range(32):
+        part = 0
+        for i in range(m["crc_chunk"]):
+            j = lane * m["crc_chunk"] + i
+            if j < nb:
+                part ^= int(by[j])
+                for _ in range(8):
+                    part = ((part >> 1) ^ 0xA001) if part & 1 else part >> 1
+        for b in range(16):
+            if (part >> b) & 1:
+                adv ^= int(m["crcmat"][lane, b])
+    all_zeros = int(not by.any())
+    crc = 0 if all_zeros else (adv ^ m["crc_init"]) & 0xFFFF
+    return by, crc, all_zeros

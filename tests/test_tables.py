@@ -1,0 +1,95 @@
+"""Host-built table blob (csrc/mb_tables.cpp) pinned against the oracle on CPU: geometry of all 17 modes, the
+composed gather/scatter indices, the JDS Tanner graphs and the CRC matrices, by walking the blob with the same
+index logic as the kernels (tests/blob_emulator.py)."""
+import numpy as np
+import pytest
+
+import mercury_b200 as mb
+from oracle import port
+from tests import blob_emulator as be
+
+THRESH = mb.THRESH_DB
+
+
+@pytest.fixture(scope="module")
+def blob():
+    return be.Blob(mb.build_tables_host())
+
+
+@pytest.mark.parametrize("cfg", range(17))
+def test_geometry_matches_oracle_and_static_mode_list(blob, cfg):
+    m, p, s = blob.mode(cfg), port.Port(cfg), mb.MODES[cfg]
+    for k_blob, k_port in (("M", "M"), ("Nsymb", "Nsymb"), ("nData", "nData"), ("nPilots", "nPilots"), ("nBits", "nBits"),
+                           ("K", "K"), ("P", "P"), ("frame_bytes", "frame_bytes"), ("estimator", "estimator"),
+                           ("phase_only", "amp_restore"), ("preamble_nSymb", "preamble_nSymb")):
+        assert m[k_blob] == p.geom[k_port], k_blob
+    for k in ("M", "Nsymb", "nData", "nPilots", "nBits", "K", "P", "frame_bytes", "nReal", "nVirtual", "estimator", "phase_only", "bps"):
+        assert m[k] == s[k], k
+    t = p.tables()
+    mask = np.zeros(m["Nsymb"] * 50, bool)
+    mask[m["pilot_cell"].astype(int)] = True
+    assert np.array_equal(mask.reshape(m["Nsymb"], 50), t["carrier_type"] == 1)
+    assert np.array_equal(m["pval"][mask].astype(np.float64), t["pilot_seq"].astype(np.float32).astype(np.float64))
+    assert np.allclose(m["pinv"][mask] * m["pval"][mask], 1.0, rtol=1e-6) and not m["pinv"][~mask].any()
+    assert np.array_equal(m["cons"], t["constellation"].astype(np.complex64))
+    assert np.array_equal(m["scr"], t["scrambler"].astype(np.uint8))
+
+
+@pytest.mark.parametrize("rate_idx", range(8))
+def test_jds_graph_is_the_reference_graph(blob, rate_idx):
+    r = blob.rate(rate_idx)
+    cfg = {1: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5, 8: 6, 14: 12}[r["rate_num"]]
+    lt = port.Port(cfg).ldpc_tables()
+    cw_of_var = np.zeros(1600, int)
+    cw_of_var[r["var_of_cw"].astype(int)] = np.arange(1600)
+    assert sorted(r["var_of_cw"].tolist()) == list(range(1600))
+    assert (np.diff(r["cdeg"].astype(int)) <= 0).all() and (np.diff(r["vdeg"].astype(int)) <= 0).all()
+    slot_of = {}
+    for cs in range(r["P"]):
+        c = int(r["check_of_sorted"][cs])
+        ref_row = [int(v) for v in lt["C"][c] if v != -1]
+        row = [int(cw_of_var[r["edge_var"][r["coff"][k] + cs]]) for k in range(int(r["cdeg"][cs]))]
+        assert row == ref_row
+        for k, v in enumerate(row):
+            slot_of[(c, v)] = int(r["coff"][k]) + cs
+    assert len(slot_of) == r["n_edges"] and sorted(slot_of.values()) == list(range(r["n_edges"]))
+    for vi in range(1600):
+        v = int(cw_of_var[vi])
+        ref_row = [int(c) for c in lt["V"][v] if c != -1]
+        assert int(r["vdeg"][vi]) == len(ref_row)
+        assert [int(r["vedge"][r["voff"][k] + vi]) for k in range(len(ref_row))] == [slot_of[(c, v)] for c in ref_row]
+
+
+@pytest.mark.parametrize("cfg", range(17))
+def test_demod_index_tables_reproduce_oracle_llrs(blob, cfg, golden_dir):
+    g = np.load(f"{golden_dir}/rx_mode{cfg:02d}.npz")
+    e = be.demod(blob, cfg, g["x"])
+    for k in ("Y", "H", "Z"):
+        ref = g[k]
+        assert np.abs(e[k] - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), k
+    if cfg < 15:
+        ref = g["llr_cw"]
+        tol = 1e-4 * np.maximum(np.abs(ref), np.median(np.abs(ref)))
+        assert (np.abs(e["llr_cw"] - ref) <= tol).all()
+        assert abs(e["snr"] - float(g["snr"])) < 1e-3 and abs(e["mean_H"] - float(g["mean_H"])) < 1e-4
+    else:  # ZF: the variance is rounding residue, compare what the decoder can see: the signs
+        nz = np.abs(g["llr_cw"]) > 0
+        assert np.array_equal(np.signbit(e["llr_cw"][nz]), np.signbit(g["llr_cw"][nz]))
+
+
+@pytest.mark.parametrize("cfg", [0, 5, 8, 10, 13, 14, 16])
+def test_decoder_schedule_and_crc_tables(blob, cfg, golden_dir):
+    g = np.load(f"{golden_dir}/rx_mode{cfg:02d}.npz")
+    r = blob.rate(blob.mode(cfg)["rate_idx"])
+    L = np.zeros(1600, np.float32)
+    L[r["var_of_cw"].astype(int)] = g["llr_cw"]
+    its, post = be.ldpc_decode(blob, cfg, L, int(g["ldpc_iters"]))
+    assert its == int(g["iterations"])
+    by, crc, az = be.finish(blob, cfg, post)
+    assert np.array_equal(by, g["bytes"]) and crc == int(g["crc"]) == 0 and az == int(g["all_zeros"])
+    # a corrupted byte must produce the reference's CRC value through the warp-parallel matrices too
+    m = blob.mode(cfg)
+    post2 = post.copy()
+    post2[m["bit_var"][13]] *= -1
+    by2, crc2, _ = be.finish(blob, cfg, post2)
+    assert crc2 == port.port_crc16(by2.tolist()) != 0
