@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""bench.py -- OFDM frames/s through the B200 RX hot path (demod + LDPC decode), BASELINE.json's metric.
+
+  python bench.py [--gpus N --steps K --warmup W]                 own arm (CUDA path through the C ABI)
+  python bench.py --impl reference [--gpus N --steps K --warmup W] the reference's own CPU implementation of the path
+  torchrun ... bench.py --gpus N ...                               one rank per GPU, frames sharded, no data-path collective
+
+A step = one pass of the hot path over one batch of synthetic frames.  Workload at every N: BASELINE config #2,
+mode 8 (CONFIG_8 = QPSK, LDPC 6/16), -I 50, 65,536 frames per GPU (weak scaling), Es/N0 = threshold + 2 dB = 2.5 dB,
+every frame with its own payload-tile and its own noise realisation.  Inputs (3.4 GB per GPU) are far larger than
+the 126 MB L2, so no flush is needed between timed steps.
+
+  value : frames/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e   : the same through the host-buffer C-ABI call (pinned host memory; H2D + kernels + D2H inside the timed region)
+  roofline : the demod kernel (FFT / estimate / equalise / de-map), algorithmic bytes per frame from SURVEY.md 8d
+  ldpc  : edge-updates/s of the decoder kernel = edges(rate) x iterations actually run / kernel time
+  cpu_baseline : the reference CPU path (oracle/_ref when built, else the C port) on a bounded sample, 1 core
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ofdm_frames_per_s_demod_ldpc_decode"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=65536, help="frames per GPU")
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--esn0", type=float, default=None, help="Es/N0 in dB (default: mode threshold + 2 dB)")
+    ap.add_argument("--decoder", default="spa", choices=["spa", "minsum"])
+    ap.add_argument("--unique", type=int, default=4096, help="distinct clean frames synthesised on the host")
+    ap.add_argument("--cpu-frames", type=int, default=1024, help="frames in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(m, a, esn0):
+    mod = {2: "BPSK", 4: "QPSK", 8: "8PSK", 16: "16QAM", 32: "32QAM"}[m["M"]]
+    return (f"mode {m['config']} ({mod}, LDPC {m['rate_num']}/16, Nsymb {m['Nsymb']}), -I {a.iters}, "
+            f"batch {a.batch} frames/GPU, AWGN Es/N0 {esn0:g} dB")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed regions
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None and self._t is None:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference CPU path (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_oracle(cfg, iters):
+    from oracle import port, ref
+    if ref.available():
+        return ref.Ref(cfg, iters), "reference"
+    return port.Port(cfg, iters), "port"
+
+
+def _cpu_worker(args):
+    cfg, iters, x = args
+    o, _ = _cpu_oracle(cfg, iters)
+    secs, pay, dec, its = o.rx_tail_timed(x.astype(np.complex128))
+    return secs, int(dec.sum()), x.shape[0]
+
+
+def cpu_baseline_sample(cfg, iters, x_sample, pl_sample):
+    """Single core, frames x_sample (complex64 [n,S,272]) -> dict for the JSON line."""
+    o, kind = _cpu_oracle(cfg, iters)
+    secs, pay, dec, its = o.rx_tail_timed(x_sample.astype(np.complex128))
+    ok = int(sum(int(np.array_equal(pay[i].astype(np.uint8), pl_sample[i])) for i in range(len(dec)) if dec[i]))
+    n = x_sample.shape[0]
+    return {"value": n / secs, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"first {n} frames of the same batch, one pass, {secs:.1f} s, {int(dec.sum())} decoded, {ok} payloads exact",
+            "mean_iterations": float(np.minimum(its, iters).mean())}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    import mercury_b200 as mb
+    m = mb.MODES[a.config]
+    esn0 = a.esn0 if a.esn0 is not None else m["thresh_db"] + 2.0
+    cores = os.cpu_count() or 1
+    per_core = 48 if m["Nsymb"] >= 24 else 96  # bounded sample: a few seconds of CPU work per step
+    n = cores * per_core
+    x, pl = mb.synth_frames(a.config, n, seed=1234, esn0_db=esn0)
+    _, kind = _cpu_oracle(a.config, a.iters)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        jobs = [(a.config, a.iters, x[i * per_core:(i + 1) * per_core]) for i in range(cores)]
+        for step in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, jobs)
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                times.append(dt)
+    total = float(np.sum(times))
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(m, a, esn0), "sample_frames_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n} frames per step ({per_core} per core, one forked worker per core), same generator and Es/N0 as the GPU arm"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------
+def run_own(a):
+    import torch
+    import torch.distributed as dist
+
+    import mercury_b200 as mb
+    from mercury_b200.dist import broadcast_tables
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the RX path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        blob = broadcast_tables(mb.build_tables_host() if rank == 0 else None, src=0, device=dev)  # NCCL broadcast of the tables
+        ts = mb.TelecomSystemB200(local, tables_blob=blob)
+    else:
+        ts = mb.TelecomSystemB200(local)
+    geom = ts.load_configuration(a.config, a.iters)
+    ts.set_decoder(mb.DECODER_SPA if a.decoder == "spa" else mb.DECODER_MINSUM)
+    m = mb.MODES[a.config]
+    esn0 = a.esn0 if a.esn0 is not None else m["thresh_db"] + 2.0
+    B, S, fb = a.batch, geom["Nsymb"], geom["frame_bytes"]
+    U = min(a.unique, B)
+
+    # ---- synthetic input: U distinct clean frames from the host TX chain, tiled to B, independent AWGN per frame ----
+    clean, pl_u = mb.synth_frames(a.config, U, seed=0x4D455243 + rank, esn0_db=300.0)
+    d_clean = torch.from_numpy(clean).to(dev)
+    d_x = torch.empty((B, S, 272), dtype=torch.complex64, device=dev)
+    sigma = 10.0 ** (-esn0 / 20.0) * 16.0  # telecom_system.cc:98,139-153
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(977 + rank)
+    for i in range(0, B, U):
+        k = min(U, B - i)
+        noise = torch.randn((k, S, 272, 2), device=dev, generator=gen) * (sigma / np.sqrt(2.0))
+        d_x[i:i + k] = d_clean[:k] + torch.view_as_complex(noise)
+    del noise, d_clean
+    pl_all = np.tile(pl_u, ((B + U - 1) // U, 1))[:B]
+    d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
+    d_llr = torch.empty((B, 1600), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ts.demod_decode_batch_device(d_x, B, d_pay, d_st, None, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    # ---- timed region: device-resident whole-path throughput -------------------------------------------------
+    l0 = ts.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.start()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks.stop()
+    launches = ts.kernel_launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * a.steps / (ms_total * 1e-3)
+
+    # ---- integrity of what was just timed ----------------------------------------------------------------------
+    st = d_st.cpu().numpy().view(mb.STATS_DTYPE).reshape(-1)
+    pay = d_pay.cpu().numpy()
+    dec = st["message_decoded"] == 1
+    mism = int((pay[dec] != pl_all[dec]).any(axis=1).sum())
+    its_run = np.clip(st["iterations_done"], 0, a.iters).astype(np.float64)
+
+    # ---- per-kernel timing (same stream, same inputs): roofline of the demod stage, edge rate of the decoder ----
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_demod = t_ldpc = 0.0
+    clocks.start()
+    for _ in range(a.steps):
+        ev[0].record()
+        ts.demod_batch_device(d_x, B, d_llr, d_st, None, stream=stream)
+        ev[1].record()
+        ts.ldpc_decode_batch_device(d_llr, B, d_pay, d_st, stream=stream)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_demod += ev[0].elapsed_time(ev[1])
+        t_ldpc += ev[1].elapsed_time(ev[2])
+    clocks.stop()
+    t_demod_s, t_ldpc_s = 1e-3 * t_demod / a.steps, 1e-3 * t_ldpc / a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    algo_bytes = m["demod_bytes"] * B
+    achieved = algo_bytes / t_demod_s / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"demod_mode{a.config}_bytes_per_frame")
+        traffic = None if traffic is None else traffic * B
+    except Exception:
+        pass
+    roofline = {"kernel": "mb_demod_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_frame": m["demod_bytes"], "peak_source": peak_src,
+                "kernel_ms": 1e3 * t_demod_s, "share_of_step": t_demod_s / (t_demod_s + t_ldpc_s)}
+    edge_updates = float(its_run.sum()) * m["edges"]
+    ldpc = {"kernel": "mb_ldpc_kernel", "decoder": a.decoder, "edge_updates_per_s": edge_updates / t_ldpc_s, "kernel_ms": 1e3 * t_ldpc_s,
+            "edges": m["edges"], "mean_iterations": float(its_run.mean()), "frames_per_s": B / t_ldpc_s,
+            "hbm_gbs": B * (1600 * 4 + fb + 32 + 32) / t_ldpc_s / 1e9, "share_of_step": t_ldpc_s / (t_demod_s + t_ldpc_s)}
+
+    # ---- e2e: host buffers through the C-ABI batch call (pinned memory; H2D + kernels + D2H timed) --------------
+    e2e = None
+    if not a.no_e2e:
+        h_x = torch.empty((B, S, 272), dtype=torch.complex64, pin_memory=True)
+        h_x.copy_(d_x)
+        h_pay = torch.zeros((B, fb), dtype=torch.uint8, pin_memory=True)
+        h_st = torch.zeros((B, 32), dtype=torch.uint8, pin_memory=True)
+        hx, hp, hs = h_x.numpy(), h_pay.numpy(), h_st.numpy().view(mb.STATS_DTYPE).reshape(-1)
+        for _ in range(min(2, a.warmup)):
+            ts.demod_decode_batch(hx, out=(hp, hs))
+        barrier()
+        clocks.start()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ts.demod_decode_batch(hx, out=(hp, hs))  # returns after its streams are synchronised
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        clocks.stop()
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_mism = int((hp[hs["message_decoded"] == 1] != pl_all[hs["message_decoded"] == 1]).any(axis=1).sum())
+        e2e = {"value": world * B * a.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(B * S * 272 * 8),
+               "d2h_bytes_per_step": int(B * (fb + 32)), "payload_mismatches": e2e_mism,
+               "api": "mercury_b200_demod_decode_batch (pinned host buffers, 3-slot chunk pipeline)"}
+        del h_x
+
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_frames > 0:
+        n = min(a.cpu_frames, B)
+        cpu = cpu_baseline_sample(a.config, a.iters, d_x[:n].cpu().numpy(), pl_all[:n])
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(m, a, esn0), "frames_total": world * B, "decoder": a.decoder,
+                       "l2_policy": f"inputs {B * S * 272 * 8 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
+                       "input": f"{U} distinct host-synthesised frames tiled to {B}, independent AWGN per frame (torch.randn on device)",
+                       "parallelism": f"frame shards x{world}, tables broadcast once ({'NCCL' if world > 1 else 'local'}), no data-path collective"},
+            "roofline": roofline, "ldpc": ldpc, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "integrity": {"frames_decoded": int(dec.sum()), "frames": int(B), "payload_mismatches_among_decoded": mism,
+                          "fer": float(1.0 - dec.mean())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    return run_reference(a) if a.impl == "reference" else run_own(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
