@@ -43,7 +43,7 @@ static inline int mb_demod_threads(int Nsymb)
 	return (t + 31) / 32 * 32;
 }
 size_t mb_demod_smem_bytes(int Nsymb);
-size_t mb_ldpc_smem_bytes(int n_edges);
+size_t mb_ldpc_smem_bytes(int c_slots);
 
 cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream);
 cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream);

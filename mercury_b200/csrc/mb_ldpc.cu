@@ -13,49 +13,63 @@
 //     are resident per SM); HBM is touched once for the 6.4 KB of LLRs in and <=175 bytes + 32 bytes out.
 //   * Only posterior and check->variable messages are stored: the variable->check message of the reference
 //     (its Q array) is recomputed as posterior - R, which is exactly the reference's Q update.
-//   * The Tanner graph is laid out on the host in jagged-diagonal (JDS) form on BOTH sides, checks and
-//     variables renumbered by descending degree: thread-per-check (and thread-per-variable) loops then touch the
-//     per-edge array with consecutive lanes on consecutive words (conflict free, no padding, near-uniform trip
-//     count inside a warp).  Index tables are read through the read-only path and stay in L1 (shared by all CTAs).
+//   * The Tanner graph is laid out on the host as a warp-blocked ELL on BOTH sides: checks (variables) sorted by
+//     descending degree, cut into groups of 32, each group padded to its largest degree.  A warp owns a group, so
+//     thread-per-check (thread-per-variable) loops walk the per-edge array with a constant +32-word stride, 32
+//     consecutive words per step (conflict free, <12 % padding, uniform trip count inside a warp).  Index tables
+//     are read through the read-only path and stay in L1 (shared by all CTAs of the SM).
 //   * The syndrome of iteration i is evaluated inside the check pass of iteration i+1 (it gathers the same
 //     posteriors anyway) and combined with a single __syncthreads_or: one barrier per half-iteration.
-//   * SPA mode evaluates the check node in the log-magnitude domain, s = -ln tanh(|q|/2) = 2 atanh(e^-|q|),
-//     R = phi(sum of the other s) (phi is its own inverse).  This keeps fp32 accurate where the product of
-//     tanh saturates, and reproduces the reference's double-precision clamp rule exactly: a factor whose tanh
-//     rounds to 1.0 in double (s < 2^-54) contributes 0, and an all-saturated product gives 2 atanh(0.9999999).
-//     The leave-one-out sum is total - self with the total kept in fp64 (B200 runs fp64 adds at half fp32 rate).
-//   * MINSUM mode (north_star): normalised min-sum, alpha = 0.75, same schedule / exit / clamp.
+//   * SPA mode evaluates the check node in the log-magnitude domain, s = -log2 tanh(|q|/2), R = phi(sum of the
+//     other s) (phi is its own inverse).  This keeps fp32 accurate where the product of tanh saturates, and
+//     reproduces the reference's double-precision clamp rule: a factor whose tanh rounds to 1.0 in double
+//     (s < 2^-54 nats) contributes 0, and an all-saturated product gives 2 atanh(0.9999999).
+//     The leave-one-out sum never cancels: the largest term is kept apart (rest = sum of all others), so the edge
+//     that owns it reads `rest` and every other edge reads (rest - self) + largest.  No fp64, no conversions: the
+//     kernel is bound by instruction issue and by the XU pipe (3 MUFU per phi), not by memory.
+//   * MINSUM mode (north_star): normalised min-sum (alpha 1 for degree<=2 where min-sum is exact, 0.85 for 3,
+//     0.75 above), same schedule / exit / clamp.
 #include "mb_kernels.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr float kClampR = 16.811242831518264f;   // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
-constexpr float kTanhOne = 5.5511151231257827e-17f;  // 2^-54: tanh(|q|/2) rounds to exactly 1.0 in double below this s
-constexpr float kSMax = 80.0f;                   // s of |q| -> 0 (keeps total - self finite)
-constexpr float kAlpha = 0.75f;                  // normalised min-sum scaling
+constexpr float kLn2 = 0.69314718055994531f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
+constexpr float kTanhOne2 = 5.5511151231257827e-17f * kLog2e; // s (base-2 units) below which tanh(|q|/2) == 1.0 in double
+constexpr float kSMax2 = 115.0f;                             // s of |q| -> 0 (base-2 units; ~80 nats)
+constexpr float kTiny2 = 0.015625f * kLog2e;                 // below this S, 1 - 2^-S would cancel: use log2(2/(S ln2))
 
-// phi(x) = 2 atanh(exp(-x)) = ln((1+e)/(1-e)) = -ln tanh(x/2), x >= 0; phi(phi(x)) = x.
-// Three regimes so that fp32 keeps ~1e-6 relative accuracy from x = 2^-54 up to x = 80:
-//   x <  1/64 : ln(2/x) + x^2/12                (1 - e would cancel)
-//   e <  1/4  : odd series of 2 atanh(e)        (the logarithm's argument would round to 1)
-//   otherwise : ln((1+e)/(1-e))
-__device__ __forceinline__ float phi(float x)
+// Forward map, x = |q| (nats) -> s = -log2 tanh(x/2) = log2((1+e)/(1-e)), e = exp(-x).
+//   e < 0.1 : odd series (2/ln2) e (1 + e^2/3 + e^4/5), rel. error < 2e-7  (the logarithm's argument would round to 1)
+//   else    : log2((1+e)/(1-e)).  As x -> 0 the result saturates near 24 instead of growing without bound, which only
+//             says "this edge carries no information" slightly less emphatically (see kSMax2).
+__device__ __forceinline__ float phi_fwd(float x)
 {
-	const float e = __expf(-x);
+	const float e = exp2f(-x * kLog2e);  // ex2.approx.ftz under -ftz=true
 	const float e2 = e * e;
-	float p = fmaf(e2, 1.0f / 11.0f, 1.0f / 9.0f);
-	p = fmaf(e2, p, 1.0f / 7.0f);
-	p = fmaf(e2, p, 1.0f / 5.0f);
-	p = fmaf(e2, p, 1.0f / 3.0f);
-	p = fmaf(e2, p, 1.0f);
-	const float series = 2.0f * e * p;
-	const bool tiny = x < 0.015625f;
-	const float num = tiny ? 2.0f : 1.0f + e;
-	const float den = tiny ? x : 1.0f - e;
-	const float lg = __logf(__fdividef(num, den)) + (tiny ? x * x * (1.0f / 12.0f) : 0.0f);
-	return e < 0.25f ? series : lg;
+	const float t = fmaf(e2, 0.2f, 1.0f / 3.0f);
+	const float e_s = e * (2.0f * kLog2e);
+	const float series = fmaf(e_s, e2 * t, e_s);
+	const float lg = __log2f(__fdividef(1.0f + e, 1.0f - e));
+	return e < 0.1f ? series : lg;
 }
+
+// Backward map, S (base-2 units) -> R = phi(S) in nats = ln((1+e)/(1-e)), e = 2^-S.
+//   S < kTiny2 : ln(2 / (S ln2))   (1 - e would cancel; error < 2e-5 absolute on a value > 4.8)
+//   else       : ln2 * log2((1+e)/(1-e)); for large S the result is tiny and only its absolute error (1e-7) matters.
+__device__ __forceinline__ float phi_bwd(float S)
+{
+	const float e = exp2f(-S);
+	const bool tiny = S < kTiny2;
+	const float num = tiny ? 2.0f * kLog2e : 1.0f + e;
+	const float den = tiny ? S : 1.0f - e;
+	return kLn2 * __log2f(__fdividef(num, den));
+}
+
+// parity of the hard decisions accumulated as XOR of raw sign bits -> 0/1
+__device__ __forceinline__ unsigned lam_sign_fix(unsigned x) { return x >> 31; }
 
 __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 {
@@ -66,19 +80,19 @@ __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(kThreads, 4) mb_ldpc_kernel(const MbLdpcArgs a)
+__global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const MbMode &m = a.mode;
 	const MbRate &rt = a.rate;
-	const int tid = threadIdx.x;
-	const int N = MB_N, P = rt.P, E = rt.n_edges;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int N = MB_N, P = rt.P, CS = rt.c_slots;
 	float *s_lam = reinterpret_cast<float *>(smem_raw);  // posterior
 	float *s_lch = s_lam + MB_N;                         // channel LLR
-	float *s_R = s_lch + MB_N;                           // check -> variable message per edge (check-side JDS slot)
-	uint32_t *s_coff = reinterpret_cast<uint32_t *>(s_R + ((E + 3) & ~3));
-	uint32_t *s_voff = s_coff + (MB_MAX_CDEG + 1);
-	unsigned char *s_bytes = reinterpret_cast<unsigned char *>(s_voff + (MB_MAX_VDEG + 1));
+	float *s_R = s_lch + MB_N;                           // check -> variable message per check-side slot
+	uint32_t *s_cgbase = reinterpret_cast<uint32_t *>(s_R + ((CS + 3) & ~3));
+	uint32_t *s_vgbase = s_cgbase + MB_MAX_GROUPS;
+	unsigned char *s_bytes = reinterpret_cast<unsigned char *>(s_vgbase + MB_MAX_GROUPS);
 
 	const size_t frame = blockIdx.x;
 	const uint8_t *__restrict__ g_cdeg = a.blob + rt.off_cdeg;
@@ -108,72 +122,80 @@ __global__ void __launch_bounds__(kThreads, 4) mb_ldpc_kernel(const MbLdpcArgs a
 			reinterpret_cast<float4 *>(s_lam)[i] = v;
 			reinterpret_cast<float4 *>(s_lch)[i] = v;
 		}
-		for (int i = tid; i < E; i += kThreads) s_R[i] = 0.f;
-		const uint32_t *__restrict__ g_coff = reinterpret_cast<const uint32_t *>(a.blob + rt.off_coff);
-		const uint32_t *__restrict__ g_voff = reinterpret_cast<const uint32_t *>(a.blob + rt.off_voff);
-		if (tid <= MB_MAX_CDEG) s_coff[tid] = g_coff[tid];
-		if (tid <= MB_MAX_VDEG) s_voff[tid] = g_voff[tid];
+		for (int i = tid; i < CS; i += kThreads) s_R[i] = 0.f;
+		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);
+		const uint32_t *__restrict__ g_vgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vgbase);
+		if (tid < MB_MAX_GROUPS) {
+			s_cgbase[tid] = g_cgbase[tid];
+			s_vgbase[tid] = g_vgbase[tid];
+		}
 	}
 	__syncthreads();
 
+	const int n_cgroups = (P + 31) >> 5, n_vgroups = (N + 31) >> 5;
 	int iterations = 0;
 	for (int pass = 0;; pass++) {
 		// ---- check pass: syndrome of the current posterior + new check->variable messages ----------------
-		int unsat = 0;
-		for (int c = tid; c < P; c += kThreads) {
-			const int d = g_cdeg[c];
+		unsigned unsat = 0;
+		for (int g = warp; g < n_cgroups; g += kThreads / 32) {
+			const int c = (g << 5) + lane;
+			const int d = c < P ? (int)g_cdeg[c] : 0;
+			const int e0 = (int)s_cgbase[g] + lane;
+			float *__restrict__ Re = s_R + e0;
+			const uint16_t *__restrict__ ve = g_edge_var + e0;
 			unsigned hard = 0, par = 0;
 			if (ALGO == 0) {
-				double tot = 0.0;
+				float big = 0.f, rest = 0.f;  // largest term kept apart: rest = sum of all the others
+				int arg = -1;
 				for (int k = 0; k < d; k++) {
-					const int e = s_coff[k] + c;
-					const float lam = s_lam[g_edge_var[e]];
-					const float q = lam - s_R[e];
-					hard ^= lam < 0.f ? 1u : 0u;
-					par ^= __float_as_uint(q) >> 31;
-					float s = fminf(phi(fabsf(q)), kSMax);
-					s = s < kTanhOne ? 0.f : s;
-					tot += (double)s;
-					s_R[e] = copysignf(s, q);  // park the signed magnitude in the edge slot
+					const float lam = s_lam[ve[k * 32]];
+					const float q = lam - Re[k * 32];
+					hard ^= __float_as_uint(lam);  // sign bit only is used
+					par ^= __float_as_uint(q);
+					float s = fminf(phi_fwd(fabsf(q)), kSMax2);
+					s = s < kTanhOne2 ? 0.f : s;
+					const bool bigger = s > big;
+					rest += bigger ? big : s;
+					arg = bigger ? k : arg;
+					big = bigger ? s : big;
+					Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
 				}
+				hard = (lam_sign_fix(hard));
+				const unsigned pneg = par & 0x80000000u;
 				for (int k = 0; k < d; k++) {
-					const int e = s_coff[k] + c;
-					const float t = s_R[e];
-					const float so = (float)(tot - (double)fabsf(t));
-					const float mag = so > 0.f ? phi(so) : kClampR;
-					const unsigned neg = par ^ (__float_as_uint(t) >> 31);
-					s_R[e] = neg ? -mag : mag;
+					const unsigned tb = __float_as_uint(Re[k * 32]);
+					const float so = k == arg ? rest : (rest - __uint_as_float(tb & 0x7fffffffu)) + big;
+					const float mag = so > 0.f ? phi_bwd(so) : kClampR;
+					Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
 				}
 			} else {
 				float m1 = 3.0e38f, m2 = 3.0e38f;
 				int arg = -1;
 				unsigned long long signs = 0ull;
 				for (int k = 0; k < d; k++) {
-					const int e = s_coff[k] + c;
-					const float lam = s_lam[g_edge_var[e]];
-					const float q = lam - s_R[e];
-					hard ^= lam < 0.f ? 1u : 0u;
-					const unsigned ng = q < 0.f ? 1u : 0u;
-					par ^= ng;
-					signs |= (unsigned long long)ng << k;
+					const float lam = s_lam[ve[k * 32]];
+					const float q = lam - Re[k * 32];
+					hard ^= __float_as_uint(lam);
+					par ^= __float_as_uint(q);
+					signs |= (unsigned long long)(__float_as_uint(q) >> 31) << k;
 					const float aq = fabsf(q);
-					if (aq < m1) {
-						m2 = m1;
-						m1 = aq;
-						arg = k;
-					} else if (aq < m2)
-						m2 = aq;
+					const bool lt1 = aq < m1;
+					m2 = lt1 ? m1 : fminf(m2, aq);
+					arg = lt1 ? k : arg;
+					m1 = lt1 ? aq : m1;
 				}
+				hard = (lam_sign_fix(hard));
+				const float alpha = d <= 2 ? 1.0f : (d == 3 ? 0.85f : 0.75f);
+				const unsigned pneg = par >> 31;
 				for (int k = 0; k < d; k++) {
-					const int e = s_coff[k] + c;
-					const float mag = fminf(kAlpha * (k == arg ? m2 : m1), kClampR);
-					const unsigned neg = par ^ (unsigned)((signs >> k) & 1ull);
-					s_R[e] = neg ? -mag : mag;
+					const float mag = fminf(alpha * (k == arg ? m2 : m1), kClampR);
+					const unsigned neg = pneg ^ (unsigned)((signs >> k) & 1ull);
+					Re[k * 32] = neg ? -mag : mag;
 				}
 			}
-			unsat |= (int)hard;
+			unsat |= hard;
 		}
-		const int any_unsat = __syncthreads_or(unsat);
+		const int any_unsat = __syncthreads_or((int)unsat);
 		if (!any_unsat) {
 			iterations = pass;  // converged after `pass` iterations (0 = clean on arrival, ldpc_decoder_SPA.cc:62-77)
 			break;
@@ -183,11 +205,13 @@ __global__ void __launch_bounds__(kThreads, 4) mb_ldpc_kernel(const MbLdpcArgs a
 			break;
 		}
 		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order) ----------
-		for (int v = tid; v < N; v += kThreads) {
-			const int d = g_vdeg[v];
-			float acc = s_lch[v];
-			for (int k = 0; k < d; k++) acc += s_R[g_vedge[s_voff[k] + v]];
-			s_lam[v] = acc;
+		for (int g = warp; g < n_vgroups; g += kThreads / 32) {
+			const int v = (g << 5) + lane;
+			const int d = v < N ? (int)g_vdeg[v] : 0;
+			const uint16_t *__restrict__ se = g_vedge + s_vgbase[g] + lane;
+			float acc = v < N ? s_lch[v] : 0.f;
+			for (int k = 0; k < d; k++) acc += s_R[se[k * 32]];
+			if (v < N) s_lam[v] = acc;
 		}
 		__syncthreads();
 	}
@@ -200,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 4) mb_ldpc_kernel(const MbLdpcArgs a
 #pragma unroll
 		for (int b = 0; b < 8; b++) {
 			const int i = tid * 8 + b;
-			const unsigned bit = (s_lam[g_bit_var[i]] < 0.f ? 1u : 0u) ^ (unsigned)g_scr[i];
+			const unsigned bit = (__float_as_uint(s_lam[g_bit_var[i]]) >> 31) ^ (unsigned)g_scr[i];  // hard decision = sign bit (LLR < 0)
 			byte |= bit << b;
 		}
 		s_bytes[tid] = (unsigned char)byte;
@@ -235,9 +259,9 @@ __global__ void __launch_bounds__(kThreads, 4) mb_ldpc_kernel(const MbLdpcArgs a
 
 }  // namespace
 
-size_t mb_ldpc_smem_bytes(int n_edges)
+size_t mb_ldpc_smem_bytes(int c_slots)
 {
-	return (size_t)(2 * MB_N + ((n_edges + 3) & ~3)) * sizeof(float) + (MB_MAX_CDEG + 1 + MB_MAX_VDEG + 1) * sizeof(uint32_t) + 256;
+	return (size_t)(2 * MB_N + ((c_slots + 3) & ~3)) * sizeof(float) + 2 * MB_MAX_GROUPS * sizeof(uint32_t) + 256;
 }
 
 cudaError_t mb_ldpc_init()
@@ -250,7 +274,7 @@ cudaError_t mb_ldpc_init()
 cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream)
 {
 	if (n_frames == 0) return cudaSuccess;
-	const size_t smem = mb_ldpc_smem_bytes(a.rate.n_edges);
+	const size_t smem = mb_ldpc_smem_bytes(a.rate.c_slots);
 	if (algo == 0)
 		mb_ldpc_kernel<0><<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
 	else

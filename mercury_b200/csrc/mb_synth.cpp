@@ -141,12 +141,12 @@ std::string mb_synth_frames(const std::vector<uint8_t> &blob, int config, size_t
 	T.scr.assign(b + m.off_scr, b + m.off_scr + MB_N);
 	{
 		const uint8_t *cdeg = b + T.r.off_cdeg;
-		const uint32_t *coff = (const uint32_t *)(b + T.r.off_coff);
+		const uint32_t *cgbase = (const uint32_t *)(b + T.r.off_cgbase);
 		const uint16_t *ev = (const uint16_t *)(b + T.r.off_edge_var);
 		const uint16_t *cos_ = (const uint16_t *)(b + T.r.off_check_of_sorted);
 		T.check_rows.resize(T.r.P);
 		for (int cs = 0; cs < T.r.P; cs++)
-			for (int k = 0; k < cdeg[cs]; k++) T.check_rows[cos_[cs]].push_back(T.cw_of_var[ev[coff[k] + cs]]);
+			for (int k = 0; k < cdeg[cs]; k++) T.check_rows[cos_[cs]].push_back(T.cw_of_var[ev[cgbase[cs >> 5] + 32 * k + (cs & 31)]]);
 	}
 	T.tw.resize(128);
 	for (int k = 0; k < 128; k++) T.tw[k] = std::polar(1.0, 2.0 * M_PI * k / 256.0);

@@ -159,27 +159,32 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 
 	int max_cdeg = (int)t.crow[csorted[0]].size(), max_vdeg = (int)t.vrow[vsorted[0]].size();
 	if (max_cdeg > MB_MAX_CDEG || max_vdeg > MB_MAX_VDEG) return "LDPC degree exceeds compiled limits";
-	std::vector<uint32_t> coff(MB_MAX_CDEG + 1, 0), voff(MB_MAX_VDEG + 1, 0);
-	for (int k = 0; k < MB_MAX_CDEG; k++) {
-		int cnt = 0;
-		for (int c = 0; c < P; c++) cnt += (int)t.crow[c].size() > k;
-		coff[k + 1] = coff[k] + cnt;
+	// warp-blocked ELL: groups of 32 sorted checks / variables, each padded to the degree of its first member
+	std::vector<uint32_t> cgbase(MB_MAX_GROUPS, 0), vgbase(MB_MAX_GROUPS, 0);
+	uint32_t c_slots = 0, v_slots = 0;
+	for (int g = 0; g * 32 < P; g++) {
+		cgbase[g] = c_slots;
+		c_slots += 32u * (uint32_t)t.crow[csorted[g * 32]].size();
 	}
-	for (int k = 0; k < MB_MAX_VDEG; k++) {
-		int cnt = 0;
-		for (int v = 0; v < N; v++) cnt += (int)t.vrow[v].size() > k;
-		voff[k + 1] = voff[k] + cnt;
+	for (int g = 0; g * 32 < N; g++) {
+		vgbase[g] = v_slots;
+		v_slots += 32u * (uint32_t)t.vrow[vsorted[g * 32]].size();
 	}
-	if ((int)coff[MB_MAX_CDEG] != t.n_edges || (int)voff[MB_MAX_VDEG] != t.n_edges) return "LDPC edge count mismatch";
+	if (c_slots >= 0xFFFFu || v_slots >= 0xFFFFu) return "LDPC slot count exceeds 16-bit slot ids";
+	auto cslot = [&](int k, int cs) { return cgbase[cs >> 5] + 32u * (uint32_t)k + (uint32_t)(cs & 31); };
+	auto vslot = [&](int k, int vs) { return vgbase[vs >> 5] + 32u * (uint32_t)k + (uint32_t)(vs & 31); };
 
 	std::vector<uint8_t> cdeg(P), vdeg(N);
-	std::vector<uint16_t> edge_var(t.n_edges), vedge(t.n_edges), check_of_sorted(P);
+	std::vector<uint16_t> edge_var(c_slots, 0xFFFF), vedge(v_slots, 0xFFFF), check_of_sorted(P);
+	int placed = 0;
 	for (int i = 0; i < P; i++) {
 		int c = csorted[i];
 		cdeg[i] = (uint8_t)t.crow[c].size();
 		check_of_sorted[i] = (uint16_t)c;
-		for (size_t k = 0; k < t.crow[c].size(); k++) edge_var[coff[k] + i] = var_of_cw[t.crow[c][k]];
+		for (size_t k = 0; k < t.crow[c].size(); k++) edge_var[cslot((int)k, i)] = var_of_cw[t.crow[c][k]], placed++;
 	}
+	if (placed != t.n_edges) return "LDPC edge count mismatch";
+	placed = 0;
 	for (int i = 0; i < N; i++) {
 		int v = vsorted[i];
 		vdeg[i] = (uint8_t)t.vrow[v].size();
@@ -189,16 +194,19 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 			auto it = std::find(row.begin(), row.end(), v);
 			if (it == row.end()) return "LDPC V/C tables inconsistent";
 			int kc = (int)(it - row.begin());
-			vedge[voff[k] + i] = (uint16_t)(coff[kc] + cpos[c]);
+			vedge[vslot((int)k, i)] = (uint16_t)cslot(kc, cpos[c]);
+			placed++;
 		}
 	}
+	if (placed != t.n_edges) return "LDPC edge count mismatch (variable side)";
 	out.rate_num = t.rate_num, out.N = N, out.K = t.K, out.P = P, out.n_edges = t.n_edges;
-	out.max_cdeg = max_cdeg, out.max_vdeg = max_vdeg, out.c_slots = t.n_edges;
+	out.max_cdeg = max_cdeg, out.max_vdeg = max_vdeg, out.c_slots = (int32_t)c_slots, out.v_slots = (int32_t)v_slots;
+	out.reserved = 0;
 	out.off_cdeg = bl.put(cdeg);
-	out.off_coff = bl.put(coff);
+	out.off_cgbase = bl.put(cgbase);
 	out.off_edge_var = bl.put(edge_var);
 	out.off_vdeg = bl.put(vdeg);
-	out.off_voff = bl.put(voff);
+	out.off_vgbase = bl.put(vgbase);
 	out.off_vedge = bl.put(vedge);
 	out.off_var_of_cw = bl.put(var_of_cw);
 	out.off_check_of_sorted = bl.put(check_of_sorted);
@@ -434,8 +442,9 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 	for (int r = 0; r < MB_NRATES; r++) {
 		const MbRate &t = h.rates[r];
 		if (t.N != MB_N || t.n_edges <= 0 || t.n_edges > 8192 || t.P <= 0 || t.P >= MB_N) return "table blob: bad rate record";
-		if (!in(t.off_cdeg, t.P) || !in(t.off_coff, 4 * (MB_MAX_CDEG + 1)) || !in(t.off_edge_var, 2 * (size_t)t.n_edges) ||
-		    !in(t.off_vdeg, t.N) || !in(t.off_voff, 4 * (MB_MAX_VDEG + 1)) || !in(t.off_vedge, 2 * (size_t)t.n_edges) ||
+		if (t.c_slots < t.n_edges || t.c_slots > 12288 || t.v_slots < t.n_edges || t.v_slots > 12288) return "table blob: bad slot counts";
+		if (!in(t.off_cdeg, t.P) || !in(t.off_cgbase, 4 * MB_MAX_GROUPS) || !in(t.off_edge_var, 2 * (size_t)t.c_slots) ||
+		    !in(t.off_vdeg, t.N) || !in(t.off_vgbase, 4 * MB_MAX_GROUPS) || !in(t.off_vedge, 2 * (size_t)t.v_slots) ||
 		    !in(t.off_var_of_cw, 2 * (size_t)t.N))
 			return "table blob: rate table out of range";
 	}

@@ -29,25 +29,29 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 3u
+#define MB_BLOB_VERSION 4u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
+#define MB_MAX_GROUPS 64  // warp-sized groups of checks / variables (<= 50 used)
 
 struct MbRate {
 	int32_t rate_num, N, K, P, n_edges;
 	int32_t max_cdeg, max_vdeg;
-	int32_t c_slots;  // check-side JDS slots (== n_edges, no padding needed: slices are dense)
-	// check side, checks sorted by degree (descending): slot(k, c') = coff[k] + c'
-	uint32_t off_cdeg;      // u8 [P]            degree of sorted check c'
-	uint32_t off_coff;      // u32[MB_MAX_CDEG+1] slice offsets
-	uint32_t off_edge_var;  // u16[n_edges]      internal variable index of each check-side slot
-	// variable side, variables renumbered by degree (descending): vslot(k, v') = voff[k] + v'
+	int32_t c_slots, v_slots;  // padded slot counts of the two warp-blocked ELL layouts below
+	int32_t reserved;
+	// Check side. Checks are sorted by degree (descending) and cut into groups of 32 (one warp); group g is padded to
+	// the degree of its first (= largest) check: slot(k, c') = cgbase[c' >> 5] + 32 k + (c' & 31).  A warp that owns a
+	// group therefore walks its edges with a constant +32 stride and touches 32 consecutive words per step.
+	uint32_t off_cdeg;      // u8 [P]             degree of sorted check c'
+	uint32_t off_cgbase;    // u32[MB_MAX_GROUPS] first slot of each group of 32 checks
+	uint32_t off_edge_var;  // u16[c_slots]       internal variable index of each check-side slot (0xFFFF = padding)
+	// Variable side, same layout over variables renumbered by degree (descending): vslot(k, v') = vgbase[v' >> 5] + 32 k + (v' & 31)
 	uint32_t off_vdeg;      // u8 [N]
-	uint32_t off_voff;      // u32[MB_MAX_VDEG+1]
-	uint32_t off_vedge;     // u16[n_edges]      check-side slot id held by each variable-side slot
-	uint32_t off_var_of_cw; // u16[N]            codeword position -> internal variable index
-	uint32_t off_check_of_sorted; // u16[P]      sorted check c' -> reference check index (diagnostics)
+	uint32_t off_vgbase;    // u32[MB_MAX_GROUPS]
+	uint32_t off_vedge;     // u16[v_slots]       check-side slot id held by each variable-side slot (0xFFFF = padding)
+	uint32_t off_var_of_cw; // u16[N]             codeword position -> internal variable index
+	uint32_t off_check_of_sorted; // u16[P]       sorted check c' -> reference check index (diagnostics, TX encoder)
 };
 
 struct MbMode {

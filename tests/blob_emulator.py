@@ -5,8 +5,8 @@ import numpy as np
 
 MB_NC, MB_N, MAX_CDEG, MAX_VDEG = 50, 1600, 48, 16
 
-RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "max_cdeg", "max_vdeg", "c_slots")] +
-                   [(n, "<u4") for n in ("off_cdeg", "off_coff", "off_edge_var", "off_vdeg", "off_voff", "off_vedge",
+RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "max_cdeg", "max_vdeg", "c_slots", "v_slots", "reserved")] +
+                   [(n, "<u4") for n in ("off_cdeg", "off_cgbase", "off_edge_var", "off_vdeg", "off_vgbase", "off_vedge",
                                          "off_var_of_cw", "off_check_of_sorted")])
 MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate_num", "Nsymb", "nData", "nPilots", "nBits",
                                          "nReal", "nVirtual", "K", "P", "frame_bytes", "estimator", "phase_only",
@@ -44,15 +44,24 @@ class Blob:
     def rate(self, idx):
         r = self.hdr["rates"][idx]
         d = {k: int(r[k]) for k in RATE_DT.names if not k.startswith("off_")}
-        d.update(cdeg=self.arr(r["off_cdeg"], "u1", r["P"]), coff=self.arr(r["off_coff"], "<u4", MAX_CDEG + 1),
-                 edge_var=self.arr(r["off_edge_var"], "<u2", r["n_edges"]), vdeg=self.arr(r["off_vdeg"], "u1", r["N"]),
-                 voff=self.arr(r["off_voff"], "<u4", MAX_VDEG + 1), vedge=self.arr(r["off_vedge"], "<u2", r["n_edges"]),
+        d.update(cdeg=self.arr(r["off_cdeg"], "u1", r["P"]), cgbase=self.arr(r["off_cgbase"], "<u4", 64),
+                 edge_var=self.arr(r["off_edge_var"], "<u2", r["c_slots"]), vdeg=self.arr(r["off_vdeg"], "u1", r["N"]),
+                 vgbase=self.arr(r["off_vgbase"], "<u4", 64), vedge=self.arr(r["off_vedge"], "<u2", r["v_slots"]),
                  var_of_cw=self.arr(r["off_var_of_cw"], "<u2", r["N"]),
                  check_of_sorted=self.arr(r["off_check_of_sorted"], "<u2", r["P"]))
         return d
 
     def twiddle(self):
         return self.arr(self.hdr["off_twiddle"], "<f4", 512).view(np.complex64).reshape(16, 16)
+
+
+def cslot(r, k, cs):
+    """check-side slot of edge k of sorted check cs (warp-blocked ELL, see mb_tables.h)"""
+    return int(r["cgbase"][cs >> 5]) + 32 * k + (cs & 31)
+
+
+def vslot(r, k, vs):
+    return int(r["vgbase"][vs >> 5]) + 32 * k + (vs & 31)
 
 
 def demod(blob, cfg, x):
@@ -128,14 +137,14 @@ def ldpc_decode(blob, cfg, llr_internal, max_iters):
     """Flooding SPA on the JDS graph exactly as scheduled by mb_ldpc.cu (double precision tanh rule). -> (iterations, posterior)."""
     m = blob.mode(cfg)
     r = blob.rate(m["rate_idx"])
-    P, N, E = r["P"], r["N"], r["n_edges"]
-    cdeg, coff, ev = r["cdeg"].astype(int), r["coff"].astype(int), r["edge_var"].astype(int)
-    vdeg, voff, ve = r["vdeg"].astype(int), r["voff"].astype(int), r["vedge"].astype(int)
+    P, N, E = r["P"], r["N"], r["c_slots"]
+    cdeg, ev = r["cdeg"].astype(int), r["edge_var"].astype(int)
+    vdeg, ve = r["vdeg"].astype(int), r["vedge"].astype(int)
     lch = llr_internal.astype(np.float64)
     lam = lch.copy()
     R = np.zeros(E)
-    rows = [[coff[k] + c for k in range(cdeg[c])] for c in range(P)]
-    vrows = [[ve[voff[k] + v] for k in range(vdeg[v])] for v in range(N)]
+    rows = [[cslot(r, k, c) for k in range(cdeg[c])] for c in range(P)]
+    vrows = [[ve[vslot(r, k, v)] for k in range(vdeg[v])] for v in range(N)]
     p = 0
     while True:
         unsat = False

@@ -48,16 +48,18 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
     for cs in range(r["P"]):
         c = int(r["check_of_sorted"][cs])
         ref_row = [int(v) for v in lt["C"][c] if v != -1]
-        row = [int(cw_of_var[r["edge_var"][r["coff"][k] + cs]]) for k in range(int(r["cdeg"][cs]))]
+        row = [int(cw_of_var[r["edge_var"][be.cslot(r, k, cs)]]) for k in range(int(r["cdeg"][cs]))]
         assert row == ref_row
         for k, v in enumerate(row):
-            slot_of[(c, v)] = int(r["coff"][k]) + cs
-    assert len(slot_of) == r["n_edges"] and sorted(slot_of.values()) == list(range(r["n_edges"]))
+            slot_of[(c, v)] = be.cslot(r, k, cs)
+    assert len(slot_of) == r["n_edges"] == len(set(slot_of.values())) and max(slot_of.values()) < r["c_slots"]
+    assert (r["edge_var"] != 0xFFFF).sum() == r["n_edges"] == (r["vedge"] != 0xFFFF).sum()
+    assert r["c_slots"] <= 1.15 * r["n_edges"] and r["v_slots"] <= 1.05 * r["n_edges"]  # padding stays small
     for vi in range(1600):
         v = int(cw_of_var[vi])
         ref_row = [int(c) for c in lt["V"][v] if c != -1]
         assert int(r["vdeg"][vi]) == len(ref_row)
-        assert [int(r["vedge"][r["voff"][k] + vi]) for k in range(len(ref_row))] == [slot_of[(c, v)] for c in ref_row]
+        assert [int(r["vedge"][be.vslot(r, k, vi)]) for k in range(len(ref_row))] == [slot_of[(c, v)] for c in ref_row]
 
 
 @pytest.mark.parametrize("cfg", range(17))
