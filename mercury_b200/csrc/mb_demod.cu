@@ -130,33 +130,40 @@ __device__ __forceinline__ void block_sum3(float &a, float &b, float &c, float *
 	c = s_red[98];
 }
 
-// restore_channel_amplitude (ofdm.cc:1453-1466): exp(j*arg H); get_angle returns pi/2 whenever Re == 0 (misc.cc:38-41)
-__device__ __forceinline__ float2 unit_phase(float2 h)
+// Max-log LLRs of one equalised symbol (psk.cc:278-326): for bit k (mask 1<<k) (min_{bit=1} D - min_{bit=0} D) / variance,
+// emitted MSB first.  M is a compile-time constant so every (j >> k) & 1 test folds away.
+template <int M, int BPS>
+__device__ __forceinline__ void demap_scatter(const float2 z, const float inv_var, const float2 *s_cons, const int base,
+					      const uint16_t *__restrict__ g_dst, const uint16_t *__restrict__ g_dst2, float *s_L)
 {
-	if (h.x == 0.f) return make_float2(0.f, 1.f);
-	float inv = rsqrtf(h.x * h.x + h.y * h.y);
-	return make_float2(h.x * inv, h.y * inv);
-}
-
-// Channel at a data cell: linear interpolation between the pilot rows of its column, linear extrapolation
-// beyond the first / last pilot row (interpolator.cc:163-254 on the s%3==c%3 lattice).
-__device__ __forceinline__ float2 interp_channel(const float2 *s_H, int s, int c, int S)
-{
-	const int f = c % 3;
-	const int last = f + 3 * ((S - 1 - f) / 3);
-	int r0;
-	if (s < f)
-		r0 = f;
-	else if (s > last)
-		r0 = last - 3;
-	else
-		r0 = s - ((s - f) % 3);
-	const float2 a = s_H[r0 * MB_NC + c], b = s_H[(r0 + 3) * MB_NC + c];
-	const float t = (float)(s - r0);
-	return make_float2(a.x + (b.x - a.x) * t / 3.0f, a.y + (b.y - a.y) * t / 3.0f);
+	float d0[BPS], d1[BPS];
+#pragma unroll
+	for (int k = 0; k < BPS; k++) d0[k] = d1[k] = 3.0e38f;
+#pragma unroll
+	for (int j = 0; j < M; j++) {
+		const float2 cj = s_cons[j];
+		const float dx = z.x - cj.x, dy = z.y - cj.y;
+		const float D = dx * dx + dy * dy;
+#pragma unroll
+		for (int k = 0; k < BPS; k++) {
+			if ((j >> k) & 1)
+				d1[k] = fminf(d1[k], D);
+			else
+				d0[k] = fminf(d0[k], D);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < BPS; k++) {
+		const float llr = inv_var * (d1[k] - d0[k]);
+		const int i = base + (BPS - 1 - k);
+		s_L[g_dst[i]] = llr;
+		const unsigned d2 = g_dst2[i];
+		if (d2 != MB_NO_DST) s_L[d2] = llr;
+	}
 }
 
 constexpr int kSmemHeadFloats = 2 * 256 + 2 * 32 + 128;  // twiddles, constellation, reduction scratch
+constexpr int kZfStride = 27;                            // compact pilot row: 4 zeros | <=17 pilots | zeros, as exclusive prefix
 
 template <bool kDebug>
 __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
@@ -169,18 +176,20 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 	float2 *s_cons = s_tw + 256;
 	float *s_red = reinterpret_cast<float *>(s_cons + 32);
 	float2 *s_Y = reinterpret_cast<float2 *>(s_red + 128);
-	float2 *s_buf = s_Y + cells;  // FFT transpose scratch, then reused for T / H / L
-	float2 *s_T = s_buf;
-	float2 *s_H = s_buf + cells;
-	float *s_L = reinterpret_cast<float *>(s_buf + 2 * cells);
+	float2 *s_buf = s_Y + cells;               // FFT transpose scratch, then reused:
+	float2 *s_zf = s_buf;                      //   [S][27] compact pilot rows of Y/p, turned into exclusive row prefixes;
+	float2 *s_Hc = s_buf;                      //   later the channel at pilots in the same compact slots [S][4 + col/3]
+	const int zf_elems = (S * kZfStride + 1) & ~1;  // keep everything behind it 16-byte aligned (float4 reads of s_L)
+	float2 *s_CT = s_buf + zf_elems;           //   [S+1][50] column prefix of the row-window sums
+	float *s_L = reinterpret_cast<float *>(s_CT + (S + 1) * MB_NC);  // [1600] LLRs, decoder order
 
 	const size_t frame = blockIdx.x;
 	const float2 *__restrict__ xf = a.x + frame * (size_t)S * MB_NOFDM;
 	const float *__restrict__ g_pinv = reinterpret_cast<const float *>(a.blob + m.off_pinv);
 	const float *__restrict__ g_pval = reinterpret_cast<const float *>(a.blob + m.off_pval);
 	const float *__restrict__ g_invn = reinterpret_cast<const float *>(a.blob + m.off_invn);
-	const uint16_t *__restrict__ g_pilot_cell = reinterpret_cast<const uint16_t *>(a.blob + m.off_pilot_cell);
-	const uint16_t *__restrict__ g_sym_cell = reinterpret_cast<const uint16_t *>(a.blob + m.off_sym_cell);
+	const uint32_t *__restrict__ g_pilot_info = reinterpret_cast<const uint32_t *>(a.blob + m.off_pilot_info);
+	const uint32_t *__restrict__ g_sym_info = reinterpret_cast<const uint32_t *>(a.blob + m.off_sym_info);
 	const uint16_t *__restrict__ g_dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
 	const uint16_t *__restrict__ g_dst2 = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst2);
 
@@ -224,68 +233,108 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 			__syncwarp();
 		}
 	}
+	__syncthreads();
 
-	// ---------------- AGC (a4): g = boost / mean |Y_pilot| ---------------------------------------------------
+	// ---------------- AGC (a4) + zero-forced pilots into compact, zero-padded rows -------------------------------
+	// Row s holds its pilots (columns s%3 + 3j) at [4 + j]; everything else in the 27-wide row is zero, so that every
+	// clipped 21-column window is exactly 7 consecutive entries (21 consecutive integers hold 7 of each residue mod 3).
+	for (int i = tid; i < S * kZfStride; i += T) {
+		const int j = i % kZfStride;
+		if (j < 4 || j > 19) s_zf[i] = make_float2(0.f, 0.f);  // [20] is rewritten below where a 17th pilot exists
+	}
+	__syncthreads();
 	float g;
 	{
 		float acc = 0.f, z0 = 0.f, z1 = 0.f;
-		__syncthreads();
 		for (int p = tid; p < m.nPilots; p += T) {
-			const float2 y = s_Y[g_pilot_cell[p]];
+			const unsigned info = g_pilot_info[p];
+			const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
+			const float2 y = s_Y[cell];
 			acc += sqrtf(y.x * y.x + y.y * y.y);
+			const float w = g_pinv[cell];
+			s_zf[s * kZfStride + 4 + j] = make_float2(y.x * w, y.y * w);  // ZF estimate Y/p (AGC gain applied later: all linear)
 		}
 		block_sum3(acc, z0, z1, s_red);
-		g = m.boost / (acc / (float)m.nPilots);
+		g = m.boost / (acc / (float)m.nPilots);  // automatic_gain_control, ofdm.cc:1467-1498
 	}
 
-	// ---------------- LS estimate (a5): separable clipped 21x21 box mean of Y/p over the pilot lattice --------
 	if (m.estimator == 1) {
-		for (int idx = tid; idx < cells; idx += T) {
-			const int k = idx / MB_NC, c = idx - k * MB_NC;
-			const int lo = max(0, c - MB_LS_HALF), hi = min(MB_NC - 1, c + MB_LS_HALF);
-			int l = lo + ((k % 3) - (lo % 3) + 3) % 3;
+		// ---------------- LS estimate (a5) = clipped 21x21 box mean over the pilot lattice, via two 1-D prefix sums -------
+		if (tid < S) {  // exclusive prefix along each compact row (27 loads in flight, then a register chain)
+			float2 *row = s_zf + tid * kZfStride;
+			float2 v[kZfStride];
+#pragma unroll
+			for (int j = 0; j < kZfStride; j++) v[j] = row[j];
 			float sx = 0.f, sy = 0.f;
-			for (; l <= hi; l += 3) {
-				const float2 y = s_Y[k * MB_NC + l];
-				const float w = g_pinv[k * MB_NC + l];
-				sx += y.x * w;
-				sy += y.y * w;
+#pragma unroll
+			for (int j = 0; j < kZfStride; j++) {
+				row[j] = make_float2(sx, sy);
+				sx += v[j].x;
+				sy += v[j].y;
 			}
-			s_T[idx] = make_float2(sx * g, sy * g);
 		}
+		__syncthreads();
+		if (tid < MB_NC) {  // per column: window sum of row k = prefix difference; running sum over rows -> column prefix
+			const int c = tid;
+			int lo[3];
+#pragma unroll
+			for (int r = 0; r < 3; r++) lo[r] = (c + 4 - r) / 3;  // compact index of the first pilot column >= c-10 in a row with s%3 == r
+			float sx = 0.f, sy = 0.f;
+			s_CT[c] = make_float2(0.f, 0.f);
+			int r = 0;
+			for (int k = 0; k < S; k++) {
+				const int l = r == 0 ? lo[0] : (r == 1 ? lo[1] : lo[2]);
+				const float2 pa = s_zf[k * kZfStride + l], pb = s_zf[k * kZfStride + l + 7];
+				sx += pb.x - pa.x;
+				sy += pb.y - pa.y;
+				s_CT[(k + 1) * MB_NC + c] = make_float2(sx, sy);
+				r = r == 2 ? 0 : r + 1;
+			}
+		}
+		__syncthreads();
 	}
-	__syncthreads();
 
 	// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) -----------------------------
 	float accH = 0.f, accV = 0.f, accVn = 0.f;
 	for (int p = tid; p < m.nPilots; p += T) {
-		const int cell = g_pilot_cell[p];
-		const int s = cell / MB_NC, c = cell - s * MB_NC;
+		const unsigned info = g_pilot_info[p];
+		const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
 		const float2 yg = cscale(s_Y[cell], g);
 		float2 h;
 		if (m.estimator == 1) {
-			const int k0 = max(0, s - MB_LS_HALF), k1 = min(S - 1, s + MB_LS_HALF);
-			float sx = 0.f, sy = 0.f;
-			for (int k = k0; k <= k1; k++) {
-				const float2 tv = s_T[k * MB_NC + c];
-				sx += tv.x;
-				sy += tv.y;
-			}
-			const float w = g_invn[cell];
-			h = make_float2(sx * w, sy * w);
+			const int c = cell - s * MB_NC;
+			const int k0 = max(0, s - MB_LS_HALF), k1 = min(S, s + MB_LS_HALF + 1);
+			const float2 ca = s_CT[k0 * MB_NC + c], cb = s_CT[k1 * MB_NC + c];
+			const float w = g_invn[cell] * g;
+			h = make_float2((cb.x - ca.x) * w, (cb.y - ca.y) * w);
 		} else {
-			h = cscale(yg, g_pinv[cell]);  // ZF: H = Y / p
+			h = cscale(s_zf[s * kZfStride + 4 + j], g);  // ZF: H = Y / p
 		}
-		s_H[cell] = h;
-		accH += sqrtf(h.x * h.x + h.y * h.y);
+		// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the row prefixes
+		// there are dead (the column pass consumed them before the barrier), in ZF mode this thread is the slot's only user.
+		s_Hc[s * kZfStride + 4 + j] = h;
+		const float h2 = h.x * h.x + h.y * h.y;
+		accH += sqrtf(h2);
 		const float pv = g_pval[cell];
-		float2 heq = h;
+		const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);  // yg * conj(h)
+		float2 z, heq = h;
 		if (m.phase_only) {
-			heq = unit_phase(h);
-			const float2 zn = cdiv(yg, h);  // equalised without amplitude restoration: SNR report only
+			// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
+			// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
+			const float inv = rsqrtf(h2), inv2 = 1.0f / h2;
+			if (h.x == 0.f) {
+				heq = make_float2(0.f, 1.f);
+				z = make_float2(yg.y, -yg.x);
+			} else {
+				heq = make_float2(h.x * inv, h.y * inv);
+				z = make_float2(yc.x * inv, yc.y * inv);
+			}
+			const float2 zn = make_float2(yc.x * inv2, yc.y * inv2);  // without amplitude restoration: SNR report only
 			accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
+		} else {
+			const float inv2 = 1.0f / h2;
+			z = make_float2(yc.x * inv2, yc.y * inv2);
 		}
-		const float2 z = cdiv(yg, heq);
 		accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
 		if (kDebug) {
 			const size_t o = frame * (size_t)cells + cell;
@@ -294,7 +343,7 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 			if (a.dbg_Z) a.dbg_Z[o] = z;
 		}
 	}
-	block_sum3(accH, accV, accVn, s_red);  // also orders s_H writes before the reads below
+	block_sum3(accH, accV, accVn, s_red);  // its barriers also order the s_Hc writes above before the reads below
 	const float inv_np = 1.0f / (float)m.nPilots;
 	// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
 	const float variance = fmaxf(accV * inv_np, 1e-30f);
@@ -302,43 +351,41 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 
 	// ---------------- data cells: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------------
 	for (int q = tid; q < m.nData; q += T) {
-		const int cell = g_sym_cell[q];
-		const int s = cell / MB_NC, c = cell - s * MB_NC;
-		float2 h = interp_channel(s_H, s, c, S);
-		if (m.phase_only) h = unit_phase(h);
+		const unsigned info = g_sym_info[q];
+		const int cell = info & 0xFFF, r0 = (info >> 12) & 0x3F, j = info >> 21;
+		const float t3 = (float)((int)((info >> 18) & 7) - 2) * (1.0f / 3.0f);
+		// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
+		const float2 ha = s_Hc[r0 * kZfStride + 4 + j], hb = s_Hc[(r0 + 3) * kZfStride + 4 + j];
+		const float2 h = make_float2(fmaf(hb.x - ha.x, t3, ha.x), fmaf(hb.y - ha.y, t3, ha.y));
 		const float2 yg = cscale(s_Y[cell], g);
-		const float2 z = cdiv(yg, h);
+		const float h2 = h.x * h.x + h.y * h.y;
+		const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);
+		float2 z, heq = h;
+		if (m.phase_only) {
+			const float inv = rsqrtf(h2);
+			if (h.x == 0.f) {
+				heq = make_float2(0.f, 1.f);
+				z = make_float2(yg.y, -yg.x);
+			} else {
+				heq = make_float2(h.x * inv, h.y * inv);
+				z = make_float2(yc.x * inv, yc.y * inv);
+			}
+		} else {
+			const float inv2 = 1.0f / h2;
+			z = make_float2(yc.x * inv2, yc.y * inv2);
+		}
 		if (kDebug) {
 			const size_t o = frame * (size_t)cells + cell;
 			if (a.dbg_Y) a.dbg_Y[o] = yg;
-			if (a.dbg_H) a.dbg_H[o] = h;
+			if (a.dbg_H) a.dbg_H[o] = heq;
 			if (a.dbg_Z) a.dbg_Z[o] = z;
 		}
-		// max-log LLR per bit (psk.cc:278-326): (min_{bit=1} D - min_{bit=0} D) / variance, MSB first
-		float d0[5], d1[5];
-#pragma unroll
-		for (int k = 0; k < 5; k++) d0[k] = d1[k] = 3.0e38f;
-		for (int j = 0; j < m.M; j++) {
-			const float2 cj = s_cons[j];
-			const float dx = z.x - cj.x, dy = z.y - cj.y;
-			const float D = dx * dx + dy * dy;
-#pragma unroll
-			for (int k = 0; k < 5; k++) {
-				const bool one = (j >> k) & 1;
-				d0[k] = one ? d0[k] : fminf(d0[k], D);
-				d1[k] = one ? fminf(d1[k], D) : d1[k];
-			}
-		}
-		const int base = q * m.bps;
-#pragma unroll
-		for (int k = 0; k < 5; k++) {
-			if (k < m.bps) {
-				const float llr = inv_var * (d1[k] - d0[k]);
-				const int i = base + (m.bps - 1 - k);
-				s_L[g_dst[i]] = llr;
-				const unsigned d2 = g_dst2[i];
-				if (d2 != MB_NO_DST) s_L[d2] = llr;
-			}
+		switch (m.M) {
+		case 2: demap_scatter<2, 1>(z, inv_var, s_cons, q, g_dst, g_dst2, s_L); break;
+		case 4: demap_scatter<4, 2>(z, inv_var, s_cons, q * 2, g_dst, g_dst2, s_L); break;
+		case 8: demap_scatter<8, 3>(z, inv_var, s_cons, q * 3, g_dst, g_dst2, s_L); break;
+		case 16: demap_scatter<16, 4>(z, inv_var, s_cons, q * 4, g_dst, g_dst2, s_L); break;
+		default: demap_scatter<32, 5>(z, inv_var, s_cons, q * 5, g_dst, g_dst2, s_L); break;
 		}
 	}
 	__syncthreads();
@@ -375,7 +422,7 @@ size_t mb_demod_smem_bytes(int Nsymb)
 {
 	const int T = mb_demod_threads(Nsymb), cells = Nsymb * MB_NC;
 	size_t fftbuf = (size_t)(T / 16) * 16 * 17 * sizeof(float2);
-	size_t reuse = (size_t)2 * cells * sizeof(float2) + MB_N * sizeof(float);
+	size_t reuse = ((size_t)((Nsymb * kZfStride + 1) & ~1) + (size_t)(Nsymb + 1) * MB_NC) * sizeof(float2) + MB_N * sizeof(float);
 	return kSmemHeadFloats * sizeof(float) + (size_t)cells * sizeof(float2) + (fftbuf > reuse ? fftbuf : reuse);
 }
 

@@ -373,6 +373,23 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 		for (int i = 0; i < m.crc_bytes; i++) s = crc_zero_byte(s);
 		m.crc_init = s;
 	}
+	// pilot and data-cell descriptors with the lattice arithmetic resolved here instead of per frame on the device
+	std::vector<uint32_t> pilot_info(m.nPilots), sym_info(m.nData);
+	for (int p = 0; p < m.nPilots; p++) {
+		const int cell = pilot_cell[p], s = cell / C, c = cell % C;
+		pilot_info[p] = (uint32_t)cell | ((uint32_t)s << 12) | ((uint32_t)(c / 3) << 18);
+	}
+	for (int q = 0; q < m.nData; q++) {
+		const int cell = sym_cell[q], s = cell / C, c = cell % C;
+		const int f = c % 3, last = f + 3 * ((S - 1 - f) / 3);
+		const int r0 = s < f ? f : (s > last ? last - 3 : s - ((s - f) % 3));  // interpolator.cc:163-254
+		if (r0 < 0 || r0 + 3 > S - 1) return "interpolation rows out of range";
+		const int t = s - r0;
+		if (t < -2 || t > 5 || !is_pilot[r0 * C + c] || !is_pilot[(r0 + 3) * C + c]) return "interpolation descriptor out of range";
+		sym_info[q] = (uint32_t)cell | ((uint32_t)r0 << 12) | ((uint32_t)(t + 2) << 18) | ((uint32_t)(c / 3) << 21);
+	}
+	m.off_pilot_info = bl.put(pilot_info);
+	m.off_sym_info = bl.put(sym_info);
 	m.off_pinv = bl.put(pinv);
 	m.off_pval = bl.put(pval);
 	m.off_invn = bl.put(invn);
@@ -456,7 +473,8 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		if (!in(m.off_pinv, 4 * cells) || !in(m.off_pval, 4 * cells) || !in(m.off_invn, 4 * cells) ||
 		    !in(m.off_pilot_cell, 2 * (size_t)m.nPilots) || !in(m.off_sym_cell, 2 * (size_t)m.nData) ||
 		    !in(m.off_llr_dst, 2 * (size_t)m.nBits) || !in(m.off_llr_dst2, 2 * (size_t)m.nBits) || !in(m.off_const, 8 * (size_t)m.M) ||
-		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16))
+		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16) ||
+		    !in(m.off_pilot_info, 4 * (size_t)m.nPilots) || !in(m.off_sym_info, 4 * (size_t)m.nData))
 			return "table blob: mode table out of range";
 	}
 	return "";

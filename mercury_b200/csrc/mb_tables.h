@@ -29,7 +29,7 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 4u
+#define MB_BLOB_VERSION 5u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
@@ -73,6 +73,9 @@ struct MbMode {
 	uint32_t off_bit_var;    // u16[8*crc_bytes] internal variable of info bit i
 	uint32_t off_scr;        // u8 [N]      scrambler bit i (bit_energy_dispersal sequence)
 	uint32_t off_crcmat;     // u16[32*16]  per-lane "advance CRC by the bytes that follow my chunk" matrices
+	uint32_t off_pilot_info; // u32[nPilots] cell | row << 12 | (col / 3) << 18   (no integer divisions in the kernel)
+	uint32_t off_sym_info;   // u32[nData]  cell | r0 << 12 | (t + 2) << 18 | (col / 3) << 21: channel = H[r0] + (H[r0+3] - H[r0]) * t / 3
+	                         //             (interpolator.cc:163-254 resolved on the host: r0 = bracketing / extrapolation pilot row)
 };
 
 struct MbBlobHeader {

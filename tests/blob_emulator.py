@@ -13,7 +13,7 @@ MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate
                                          "preamble_nSymb", "crc_bytes", "crc_chunk")] +
                    [("crc_init", "<u4"), ("boost", "<f4")] +
                    [(n, "<u4") for n in ("off_pinv", "off_pval", "off_invn", "off_pilot_cell", "off_sym_cell", "off_llr_dst",
-                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat")])
+                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat", "off_pilot_info", "off_sym_info")])
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("reserved", "<u4"), ("off_twiddle", "<u4"),
                    ("pad", "<u4", (3,)), ("modes", MODE_DT, (17,)), ("rates", RATE_DT, (8,))])
 
@@ -38,7 +38,8 @@ class Blob:
                  llr_dst2=self.arr(m["off_llr_dst2"], "<u2", m["nBits"]),
                  cons=self.arr(m["off_const"], "<f4", 2 * m["M"]).view(np.complex64),
                  bit_var=self.arr(m["off_bit_var"], "<u2", 8 * m["crc_bytes"]), scr=self.arr(m["off_scr"], "u1", MB_N),
-                 crcmat=self.arr(m["off_crcmat"], "<u2", 512).reshape(32, 16))
+                 crcmat=self.arr(m["off_crcmat"], "<u2", 512).reshape(32, 16),
+                 pilot_info=self.arr(m["off_pilot_info"], "<u4", m["nPilots"]), sym_info=self.arr(m["off_sym_info"], "<u4", m["nData"]))
         return d
 
     def rate(self, idx):
@@ -99,15 +100,16 @@ def demod(blob, cfg, x):
     Hg = H.reshape(S, MB_NC).copy()
     is_p = np.zeros(S * MB_NC, bool)
     is_p[pc] = True
-    for cell in range(S * MB_NC):
-        if is_p[cell]:
-            continue
+    for info in m["sym_info"]:  # the kernel's descriptor: cell | r0 << 12 | (t + 2) << 18
+        cell, r0, t = int(info) & 0xFFF, (int(info) >> 12) & 0x3F, ((int(info) >> 18) & 7) - 2
         s, c = divmod(cell, MB_NC)
-        f = c % 3
-        last = f + 3 * ((S - 1 - f) // 3)
-        r0 = f if s < f else (last - 3 if s > last else s - ((s - f) % 3))
+        assert t == s - r0 and not is_p[cell] and (int(info) >> 21) == c // 3
         a, b = Hg[r0, c], Hg[r0 + 3, c]
-        H[cell] = a + (b - a) * f32(s - r0) / f32(3)
+        H[cell] = a + (b - a) * f32(t) / f32(3)
+    assert sorted(int(i) & 0xFFF for i in m["sym_info"]) == sorted(np.flatnonzero(~is_p).tolist())
+    for p, info in enumerate(m["pilot_info"]):
+        cell = int(info) & 0xFFF
+        assert cell == pc[p] and (int(info) >> 12) & 0x3F == cell // MB_NC and (int(info) >> 18) == (cell % MB_NC) // 3
     mean_H = f32(np.abs(H[pc]).mean())
     Hraw = H.copy()
     if m["phase_only"]:
