@@ -91,43 +91,22 @@ __device__ __forceinline__ void fft16_pruned(const float2 (&x)[16], float2 &X0, 
 	X15 = cadd(csub(A[0][3], A[2][3]), mul_pi(csub(A[1][3], A[3][3])));          // k1=3, k2=3
 }
 
-// Sum three values over the CTA; result valid in every thread. s_red: >= 3*32+3 floats.
-__device__ __forceinline__ void block_sum3(float &a, float &b, float &c, float *s_red)
+// Warp-level sum of three values; lane 0 of every warp parks its partial sums in s_part[warp*3 .. +2].  The CTA-wide
+// totals are formed by every thread after the next barrier the algorithm needs anyway (no reduction-only barriers).
+__device__ __forceinline__ void warp_partials3(float a, float b, float c, float *s_part)
 {
-	__syncthreads();
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
 		a += __shfl_xor_sync(0xffffffffu, a, o);
 		b += __shfl_xor_sync(0xffffffffu, b, o);
 		c += __shfl_xor_sync(0xffffffffu, c, o);
 	}
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-	if (lane == 0) {
-		s_red[w * 3 + 0] = a;
-		s_red[w * 3 + 1] = b;
-		s_red[w * 3 + 2] = c;
+	if ((threadIdx.x & 31) == 0) {
+		const int w = threadIdx.x >> 5;
+		s_part[w * 3 + 0] = a;
+		s_part[w * 3 + 1] = b;
+		s_part[w * 3 + 2] = c;
 	}
-	__syncthreads();
-	if (w == 0) {
-		a = lane < nw ? s_red[lane * 3 + 0] : 0.f;
-		b = lane < nw ? s_red[lane * 3 + 1] : 0.f;
-		c = lane < nw ? s_red[lane * 3 + 2] : 0.f;
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			a += __shfl_xor_sync(0xffffffffu, a, o);
-			b += __shfl_xor_sync(0xffffffffu, b, o);
-			c += __shfl_xor_sync(0xffffffffu, c, o);
-		}
-		if (lane == 0) {
-			s_red[96] = a;
-			s_red[97] = b;
-			s_red[98] = c;
-		}
-	}
-	__syncthreads();
-	a = s_red[96];
-	b = s_red[97];
-	c = s_red[98];
 }
 
 // Max-log LLRs of one equalised symbol (psk.cc:278-326): for bit k (mask 1<<k) (min_{bit=1} D - min_{bit=0} D) / variance,
@@ -162,26 +141,26 @@ __device__ __forceinline__ void demap_scatter(const float2 z, const float inv_va
 	}
 }
 
-constexpr int kSmemHeadFloats = 2 * 256 + 2 * 32 + 128;  // twiddles, constellation, reduction scratch
-constexpr int kZfStride = 27;                            // compact pilot row: 4 zeros | <=17 pilots | zeros, as exclusive prefix
+constexpr int kSmemHeadFloats = 2 * 32 + 2 * 32;  // constellation, two sets of per-warp partial sums
+constexpr int kZfStride = 27;                     // compact pilot row: 4 zeros | <=17 pilots | zeros
+constexpr int kMaxThreads = 192;
 
 template <bool kDebug>
-__global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
+__global__ void __launch_bounds__(kMaxThreads, 5) mb_demod_kernel(const MbDemodArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const MbMode &m = a.mode;
-	const int T = blockDim.x, tid = threadIdx.x;
+	const int T = blockDim.x, tid = threadIdx.x, nwarps = T >> 5;
 	const int S = m.Nsymb, cells = S * MB_NC;
-	float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
-	float2 *s_cons = s_tw + 256;
-	float *s_red = reinterpret_cast<float *>(s_cons + 32);
-	float2 *s_Y = reinterpret_cast<float2 *>(s_red + 128);
+	float2 *s_cons = reinterpret_cast<float2 *>(smem_raw);
+	float *s_part1 = reinterpret_cast<float *>(s_cons + 32);  // AGC partials
+	float *s_part2 = s_part1 + 32;                             // pilot-statistics partials
+	float2 *s_Y = reinterpret_cast<float2 *>(s_part2 + 32);
 	float2 *s_buf = s_Y + cells;               // FFT transpose scratch, then reused:
-	float2 *s_zf = s_buf;                      //   [S][27] compact pilot rows of Y/p, turned into exclusive row prefixes;
-	float2 *s_Hc = s_buf;                      //   later the channel at pilots in the same compact slots [S][4 + col/3]
+	float2 *s_zf = s_buf;                      //   [S][27] compact zero-padded pilot rows of Y/p, later the channel at pilots
 	const int zf_elems = (S * kZfStride + 1) & ~1;  // keep everything behind it 16-byte aligned (float4 reads of s_L)
-	float2 *s_CT = s_buf + zf_elems;           //   [S+1][50] column prefix of the row-window sums
-	float *s_L = reinterpret_cast<float *>(s_CT + (S + 1) * MB_NC);  // [1600] LLRs, decoder order
+	float2 *s_T = s_buf + zf_elems;            //   [S][50] clipped 21-column window sums of each row
+	float *s_L = reinterpret_cast<float *>(s_T + cells);  // [1600] LLRs, decoder order
 
 	const size_t frame = blockIdx.x;
 	const float2 *__restrict__ xf = a.x + frame * (size_t)S * MB_NOFDM;
@@ -193,18 +172,17 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 	const uint16_t *__restrict__ g_dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
 	const uint16_t *__restrict__ g_dst2 = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst2);
 
-	{
-		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);
-		const float2 *__restrict__ g_cons = reinterpret_cast<const float2 *>(a.blob + m.off_const);
-		for (int i = tid; i < 256; i += T) s_tw[i] = g_tw[i];
-		if (tid < m.M) s_cons[tid] = g_cons[tid];
-	}
-	__syncthreads();
+	if (tid < m.M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];  // published by the barrier after the FFT
 
 	// ---------------- FFT-256 per symbol (a2, a3) ------------------------------------------------------------
 	{
+		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);  // 2 KB, L1 resident
 		const int grp = tid >> 4, t = tid & 15, spr = T >> 4;
 		float2 *buf = s_buf + grp * (16 * 17);
+		float2 tw[16];
+#pragma unroll
+		for (int k1 = 1; k1 < 16; k1++) tw[k1] = __ldg(g_tw + k1 * 16 + t);  // W256^(t k1)/256, kept across rounds
+		tw[0] = make_float2(1.0f / 256.0f, 0.f);
 		for (int s0 = 0; s0 < S; s0 += spr) {
 			const int s = s0 + grp;
 			const bool active = s < S;
@@ -214,8 +192,9 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 #pragma unroll
 				for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldcs(xs + 16 * n1);  // x[16 n1 + t], GI skipped
 				fft16(v, A);
+				buf[t * 17] = cscale(A[0], 1.0f / 256.0f);
 #pragma unroll
-				for (int k1 = 0; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], s_tw[k1 * 16 + t]);
+				for (int k1 = 1; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], tw[k1]);
 			}
 			__syncwarp();
 			if (active) {
@@ -235,17 +214,15 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 	}
 	__syncthreads();
 
-	// ---------------- AGC (a4) + zero-forced pilots into compact, zero-padded rows -------------------------------
+	// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
 	// Row s holds its pilots (columns s%3 + 3j) at [4 + j]; everything else in the 27-wide row is zero, so that every
 	// clipped 21-column window is exactly 7 consecutive entries (21 consecutive integers hold 7 of each residue mod 3).
 	for (int i = tid; i < S * kZfStride; i += T) {
-		const int j = i % kZfStride;
-		if (j < 4 || j > 19) s_zf[i] = make_float2(0.f, 0.f);  // [20] is rewritten below where a 17th pilot exists
+		const int s = i / kZfStride, j = i - s * kZfStride;
+		if (j < 4 || j > 20 || (j == 20 && s % 3 == 2)) s_zf[i] = make_float2(0.f, 0.f);  // rows with s%3==2 hold 16 pilots only
 	}
-	__syncthreads();
-	float g;
 	{
-		float acc = 0.f, z0 = 0.f, z1 = 0.f;
+		float acc = 0.f;
 		for (int p = tid; p < m.nPilots; p += T) {
 			const unsigned info = g_pilot_info[p];
 			const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
@@ -254,96 +231,101 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 			const float w = g_pinv[cell];
 			s_zf[s * kZfStride + 4 + j] = make_float2(y.x * w, y.y * w);  // ZF estimate Y/p (AGC gain applied later: all linear)
 		}
-		block_sum3(acc, z0, z1, s_red);
+		warp_partials3(acc, 0.f, 0.f, s_part1);
+	}
+	__syncthreads();
+
+	// ---------------- LS estimate (a5), row pass: clipped 21-column window sums over the pilot lattice -----------------
+	if (m.estimator == 1 && tid < 3 * MB_NC) {
+		const int r = tid / MB_NC, c = tid - r * MB_NC;  // this thread: column c of the rows with s%3 == r
+		const int lo = (c + 4 - r) / 3;                  // compact index of the first pilot column >= c-10 in such a row
+		for (int k = r; k < S; k += 3) {
+			const float2 *row = s_zf + k * kZfStride + lo;
+			float sx = 0.f, sy = 0.f;
+#pragma unroll
+			for (int j = 0; j < 7; j++) {
+				sx += row[j].x;
+				sy += row[j].y;
+			}
+			s_T[k * MB_NC + c] = make_float2(sx, sy);
+		}
+	}
+	float g;
+	{
+		float acc = 0.f;
+		for (int w = 0; w < nwarps; w++) acc += s_part1[w * 3];
 		g = m.boost / (acc / (float)m.nPilots);  // automatic_gain_control, ofdm.cc:1467-1498
 	}
+	__syncthreads();
 
-	if (m.estimator == 1) {
-		// ---------------- LS estimate (a5) = clipped 21x21 box mean over the pilot lattice, via two 1-D prefix sums -------
-		if (tid < S) {  // exclusive prefix along each compact row (27 loads in flight, then a register chain)
-			float2 *row = s_zf + tid * kZfStride;
-			float2 v[kZfStride];
-#pragma unroll
-			for (int j = 0; j < kZfStride; j++) v[j] = row[j];
-			float sx = 0.f, sy = 0.f;
-#pragma unroll
-			for (int j = 0; j < kZfStride; j++) {
-				row[j] = make_float2(sx, sy);
-				sx += v[j].x;
-				sy += v[j].y;
-			}
-		}
-		__syncthreads();
-		if (tid < MB_NC) {  // per column: window sum of row k = prefix difference; running sum over rows -> column prefix
-			const int c = tid;
-			int lo[3];
-#pragma unroll
-			for (int r = 0; r < 3; r++) lo[r] = (c + 4 - r) / 3;  // compact index of the first pilot column >= c-10 in a row with s%3 == r
-			float sx = 0.f, sy = 0.f;
-			s_CT[c] = make_float2(0.f, 0.f);
-			int r = 0;
-			for (int k = 0; k < S; k++) {
-				const int l = r == 0 ? lo[0] : (r == 1 ? lo[1] : lo[2]);
-				const float2 pa = s_zf[k * kZfStride + l], pb = s_zf[k * kZfStride + l + 7];
-				sx += pb.x - pa.x;
-				sy += pb.y - pa.y;
-				s_CT[(k + 1) * MB_NC + c] = make_float2(sx, sy);
-				r = r == 2 ? 0 : r + 1;
-			}
-		}
-		__syncthreads();
-	}
-
-	// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) -----------------------------
-	float accH = 0.f, accV = 0.f, accVn = 0.f;
-	for (int p = tid; p < m.nPilots; p += T) {
-		const unsigned info = g_pilot_info[p];
-		const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
-		const float2 yg = cscale(s_Y[cell], g);
-		float2 h;
-		if (m.estimator == 1) {
-			const int c = cell - s * MB_NC;
-			const int k0 = max(0, s - MB_LS_HALF), k1 = min(S, s + MB_LS_HALF + 1);
-			const float2 ca = s_CT[k0 * MB_NC + c], cb = s_CT[k1 * MB_NC + c];
-			const float w = g_invn[cell] * g;
-			h = make_float2((cb.x - ca.x) * w, (cb.y - ca.y) * w);
-		} else {
-			h = cscale(s_zf[s * kZfStride + 4 + j], g);  // ZF: H = Y / p
-		}
-		// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the row prefixes
-		// there are dead (the column pass consumed them before the barrier), in ZF mode this thread is the slot's only user.
-		s_Hc[s * kZfStride + 4 + j] = h;
-		const float h2 = h.x * h.x + h.y * h.y;
-		accH += sqrtf(h2);
-		const float pv = g_pval[cell];
-		const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);  // yg * conj(h)
-		float2 z, heq = h;
-		if (m.phase_only) {
-			// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
-			// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
-			const float inv = rsqrtf(h2), inv2 = 1.0f / h2;
-			if (h.x == 0.f) {
-				heq = make_float2(0.f, 1.f);
-				z = make_float2(yg.y, -yg.x);
+	// ---------------- channel at pilots (column pass), pilot-domain statistics (a5/a6, a8-a10) ------------------------
+	{
+		float accH = 0.f, accV = 0.f, accVn = 0.f;
+		for (int p = tid; p < m.nPilots; p += T) {
+			const unsigned info = g_pilot_info[p];
+			const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
+			const float2 yg = cscale(s_Y[cell], g);
+			float2 h;
+			if (m.estimator == 1) {
+				const int c = cell - s * MB_NC;
+				const int k0 = max(0, s - MB_LS_HALF), k1 = min(S - 1, s + MB_LS_HALF);
+				float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
+				int k = k0;
+				for (; k + 1 <= k1; k += 2) {
+					const float2 ta = s_T[k * MB_NC + c], tb = s_T[(k + 1) * MB_NC + c];
+					sx0 += ta.x, sy0 += ta.y, sx1 += tb.x, sy1 += tb.y;
+				}
+				if (k <= k1) {
+					const float2 ta = s_T[k * MB_NC + c];
+					sx0 += ta.x, sy0 += ta.y;
+				}
+				const float w = g_invn[cell] * g;
+				h = make_float2((sx0 + sx1) * w, (sy0 + sy1) * w);
 			} else {
-				heq = make_float2(h.x * inv, h.y * inv);
-				z = make_float2(yc.x * inv, yc.y * inv);
+				h = cscale(s_zf[s * kZfStride + 4 + j], g);  // ZF: H = Y / p
 			}
-			const float2 zn = make_float2(yc.x * inv2, yc.y * inv2);  // without amplitude restoration: SNR report only
-			accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
-		} else {
-			const float inv2 = 1.0f / h2;
-			z = make_float2(yc.x * inv2, yc.y * inv2);
+			// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the rows are dead
+			// (the row pass consumed them before the barrier), in ZF mode this thread is the slot's only user.
+			s_zf[s * kZfStride + 4 + j] = h;
+			const float h2 = h.x * h.x + h.y * h.y;
+			accH += sqrtf(h2);
+			const float pv = g_pval[cell];
+			const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);  // yg * conj(h)
+			float2 z, heq = h;
+			if (m.phase_only) {
+				// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
+				// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
+				const float inv = rsqrtf(h2), inv2 = 1.0f / h2;
+				if (h.x == 0.f) {
+					heq = make_float2(0.f, 1.f);
+					z = make_float2(yg.y, -yg.x);
+				} else {
+					heq = make_float2(h.x * inv, h.y * inv);
+					z = make_float2(yc.x * inv, yc.y * inv);
+				}
+				const float2 zn = make_float2(yc.x * inv2, yc.y * inv2);  // without amplitude restoration: SNR report only
+				accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
+			} else {
+				const float inv2 = 1.0f / h2;
+				z = make_float2(yc.x * inv2, yc.y * inv2);
+			}
+			accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
+			if (kDebug) {
+				const size_t o = frame * (size_t)cells + cell;
+				if (a.dbg_Y) a.dbg_Y[o] = yg;
+				if (a.dbg_H) a.dbg_H[o] = heq;
+				if (a.dbg_Z) a.dbg_Z[o] = z;
+			}
 		}
-		accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
-		if (kDebug) {
-			const size_t o = frame * (size_t)cells + cell;
-			if (a.dbg_Y) a.dbg_Y[o] = yg;
-			if (a.dbg_H) a.dbg_H[o] = heq;
-			if (a.dbg_Z) a.dbg_Z[o] = z;
-		}
+		warp_partials3(accH, accV, accVn, s_part2);
 	}
-	block_sum3(accH, accV, accVn, s_red);  // its barriers also order the s_Hc writes above before the reads below
+	__syncthreads();
+	float accH = 0.f, accV = 0.f, accVn = 0.f;
+	for (int w = 0; w < nwarps; w++) {
+		accH += s_part2[w * 3 + 0];
+		accV += s_part2[w * 3 + 1];
+		accVn += s_part2[w * 3 + 2];
+	}
 	const float inv_np = 1.0f / (float)m.nPilots;
 	// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
 	const float variance = fmaxf(accV * inv_np, 1e-30f);
@@ -355,7 +337,7 @@ __global__ void __launch_bounds__(384, 2) mb_demod_kernel(const MbDemodArgs a)
 		const int cell = info & 0xFFF, r0 = (info >> 12) & 0x3F, j = info >> 21;
 		const float t3 = (float)((int)((info >> 18) & 7) - 2) * (1.0f / 3.0f);
 		// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
-		const float2 ha = s_Hc[r0 * kZfStride + 4 + j], hb = s_Hc[(r0 + 3) * kZfStride + 4 + j];
+		const float2 ha = s_zf[r0 * kZfStride + 4 + j], hb = s_zf[(r0 + 3) * kZfStride + 4 + j];
 		const float2 h = make_float2(fmaf(hb.x - ha.x, t3, ha.x), fmaf(hb.y - ha.y, t3, ha.y));
 		const float2 yg = cscale(s_Y[cell], g);
 		const float h2 = h.x * h.x + h.y * h.y;
@@ -422,7 +404,7 @@ size_t mb_demod_smem_bytes(int Nsymb)
 {
 	const int T = mb_demod_threads(Nsymb), cells = Nsymb * MB_NC;
 	size_t fftbuf = (size_t)(T / 16) * 16 * 17 * sizeof(float2);
-	size_t reuse = ((size_t)((Nsymb * kZfStride + 1) & ~1) + (size_t)(Nsymb + 1) * MB_NC) * sizeof(float2) + MB_N * sizeof(float);
+	size_t reuse = ((size_t)((Nsymb * kZfStride + 1) & ~1) + (size_t)cells) * sizeof(float2) + MB_N * sizeof(float);
 	return kSmemHeadFloats * sizeof(float) + (size_t)cells * sizeof(float2) + (fftbuf > reuse ? fftbuf : reuse);
 }
 

@@ -35,11 +35,13 @@ struct MbLdpcArgs {
 	int32_t check_gate;    // 1: honour the mean|H| < 0.3 gate recorded by the demod kernel
 };
 
-// Threads per CTA of the demod kernel for a frame of Nsymb symbols (16 threads per symbol, <= 384, warp multiple).
+// Threads per CTA of the demod kernel for a frame of Nsymb symbols (16 threads per symbol, 160..192, warp multiple;
+// frames with more than 12 symbols are transformed in several rounds).
 static inline int mb_demod_threads(int Nsymb)
 {
 	int t = Nsymb * 16;
-	if (t > 384) t = 384;
+	if (t > 192) t = 192;
+	if (t < 160) t = 160;  // the row pass of the LS estimator wants 3 x 50 threads
 	return (t + 31) / 32 * 32;
 }
 size_t mb_demod_smem_bytes(int Nsymb);
