@@ -148,7 +148,7 @@ def run_reference(a):
     m = mb.MODES[a.config]
     esn0 = a.esn0 if a.esn0 is not None else m["thresh_db"] + 2.0
     cores = os.cpu_count() or 1
-    per_core = 48 if m["Nsymb"] >= 24 else 96  # bounded sample: a few seconds of CPU work per step
+    per_core = 128 if m["Nsymb"] >= 24 else 256  # bounded sample: a few seconds of CPU work per step
     n = cores * per_core
     x, pl = mb.synth_frames(a.config, n, seed=1234, esn0_db=esn0)
     _, kind = _cpu_oracle(a.config, a.iters)
