@@ -34,6 +34,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kCheapTestThreads = 64;  // run the syndrome-only test after an iteration that started with <= this many unhappy threads
 constexpr float kLn2 = 0.69314718055994531f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
@@ -89,10 +90,11 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 	const int N = MB_N, P = rt.P, CS = rt.c_slots;
 	float *s_lam = reinterpret_cast<float *>(smem_raw);  // posterior
 	float *s_lch = s_lam + MB_N;                         // channel LLR
-	float *s_R = s_lch + MB_N;                           // check -> variable message per check-side slot
-	uint32_t *s_cgbase = reinterpret_cast<uint32_t *>(s_R + ((CS + 3) & ~3));
+	float *s_R = s_lch + MB_N;                           // check -> variable message per check-side slot; s_R[CS] == 0 always
+	uint32_t *s_cgbase = reinterpret_cast<uint32_t *>(s_R + ((CS + 4) & ~3));
 	uint32_t *s_vgbase = s_cgbase + MB_MAX_GROUPS;
-	unsigned char *s_bytes = reinterpret_cast<unsigned char *>(s_vgbase + MB_MAX_GROUPS);
+	unsigned char *s_vgdeg = reinterpret_cast<unsigned char *>(s_vgbase + MB_MAX_GROUPS);
+	unsigned char *s_bytes = s_vgdeg + MB_MAX_GROUPS;
 
 	const size_t frame = blockIdx.x;
 	const uint8_t *__restrict__ g_cdeg = a.blob + rt.off_cdeg;
@@ -122,17 +124,18 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			reinterpret_cast<float4 *>(s_lam)[i] = v;
 			reinterpret_cast<float4 *>(s_lch)[i] = v;
 		}
-		for (int i = tid; i < CS; i += kThreads) s_R[i] = 0.f;
+		for (int i = tid; i <= CS; i += kThreads) s_R[i] = 0.f;
 		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);
 		const uint32_t *__restrict__ g_vgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vgbase);
 		if (tid < MB_MAX_GROUPS) {
 			s_cgbase[tid] = g_cgbase[tid];
 			s_vgbase[tid] = g_vgbase[tid];
+			s_vgdeg[tid] = (a.blob + rt.off_vgdeg)[tid];
 		}
 	}
 	__syncthreads();
 
-	const int n_cgroups = (P + 31) >> 5, n_vgroups = (N + 31) >> 5;
+	const int n_cgroups = (P + 31) >> 5;
 	int iterations = 0;
 	for (int pass = 0;; pass++) {
 		// ---- check pass: syndrome of the current posterior + new check->variable messages ----------------
@@ -195,8 +198,9 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			}
 			unsat |= hard;
 		}
-		const int any_unsat = __syncthreads_or((int)unsat);
-		if (!any_unsat) {
+		// number of threads that saw an unsatisfied check: 0 = converged; a small count = "probably one iteration to go"
+		const int n_unsat = __syncthreads_count((int)unsat);
+		if (n_unsat == 0) {
 			iterations = pass;  // converged after `pass` iterations (0 = clean on arrival, ldpc_decoder_SPA.cc:62-77)
 			break;
 		}
@@ -205,15 +209,33 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			break;
 		}
 		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order) ----------
-		for (int g = warp; g < n_vgroups; g += kThreads / 32) {
+		// N = 50 full groups; a group runs to its largest degree, shorter rows read the always-zero slot CS.
+		for (int g = warp; g < MB_N / 32; g += kThreads / 32) {
 			const int v = (g << 5) + lane;
-			const int d = v < N ? (int)g_vdeg[v] : 0;
+			const int d = s_vgdeg[g];
 			const uint16_t *__restrict__ se = g_vedge + s_vgbase[g] + lane;
-			float acc = v < N ? s_lch[v] : 0.f;
+			float acc = s_lch[v];
+#pragma unroll 3
 			for (int k = 0; k < d; k++) acc += s_R[se[k * 32]];
-			if (v < N) s_lam[v] = acc;
+			s_lam[v] = acc;
 		}
 		__syncthreads();
+		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
+		if (n_unsat <= kCheapTestThreads) {
+			unsigned bad = 0;
+			for (int g = warp; g < n_cgroups; g += kThreads / 32) {
+				const int c = (g << 5) + lane;
+				const int d = c < P ? (int)g_cdeg[c] : 0;
+				const uint16_t *__restrict__ ve = g_edge_var + s_cgbase[g] + lane;
+				unsigned hard = 0;
+				for (int k = 0; k < d; k++) hard ^= __float_as_uint(s_lam[ve[k * 32]]);
+				bad |= hard >> 31;
+			}
+			if (__syncthreads_or((int)bad) == 0) {
+				iterations = pass + 1;  // exactly what the next check pass would have reported
+				break;
+			}
+		}
 	}
 
 	// ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record --------------------------
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 
 size_t mb_ldpc_smem_bytes(int c_slots)
 {
-	return (size_t)(2 * MB_N + ((c_slots + 3) & ~3)) * sizeof(float) + 2 * MB_MAX_GROUPS * sizeof(uint32_t) + 256;
+	return (size_t)(2 * MB_N + ((c_slots + 4) & ~3)) * sizeof(float) + 2 * MB_MAX_GROUPS * sizeof(uint32_t) + MB_MAX_GROUPS + 256;
 }
 
 cudaError_t mb_ldpc_init()

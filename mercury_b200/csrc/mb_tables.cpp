@@ -175,7 +175,8 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	auto vslot = [&](int k, int vs) { return vgbase[vs >> 5] + 32u * (uint32_t)k + (uint32_t)(vs & 31); };
 
 	std::vector<uint8_t> cdeg(P), vdeg(N);
-	std::vector<uint16_t> edge_var(c_slots, 0xFFFF), vedge(v_slots, 0xFFFF), check_of_sorted(P);
+	std::vector<uint16_t> edge_var(c_slots, 0xFFFF), vedge(v_slots, (uint16_t)c_slots), check_of_sorted(P);
+	// variable-side padding points at slot c_slots: one extra always-zero message, so a whole group can run to its largest degree
 	int placed = 0;
 	for (int i = 0; i < P; i++) {
 		int c = csorted[i];
@@ -207,6 +208,11 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	out.off_edge_var = bl.put(edge_var);
 	out.off_vdeg = bl.put(vdeg);
 	out.off_vgbase = bl.put(vgbase);
+	{
+		std::vector<uint8_t> vgdeg(MB_MAX_GROUPS, 0);
+		for (int g = 0; g * 32 < N; g++) vgdeg[g] = (uint8_t)t.vrow[vsorted[g * 32]].size();
+		out.off_vgdeg = bl.put(vgdeg);
+	}
 	out.off_vedge = bl.put(vedge);
 	out.off_var_of_cw = bl.put(var_of_cw);
 	out.off_check_of_sorted = bl.put(check_of_sorted);
@@ -461,7 +467,7 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		if (t.N != MB_N || t.n_edges <= 0 || t.n_edges > 8192 || t.P <= 0 || t.P >= MB_N) return "table blob: bad rate record";
 		if (t.c_slots < t.n_edges || t.c_slots > 12288 || t.v_slots < t.n_edges || t.v_slots > 12288) return "table blob: bad slot counts";
 		if (!in(t.off_cdeg, t.P) || !in(t.off_cgbase, 4 * MB_MAX_GROUPS) || !in(t.off_edge_var, 2 * (size_t)t.c_slots) ||
-		    !in(t.off_vdeg, t.N) || !in(t.off_vgbase, 4 * MB_MAX_GROUPS) || !in(t.off_vedge, 2 * (size_t)t.v_slots) ||
+		    !in(t.off_vdeg, t.N) || !in(t.off_vgbase, 4 * MB_MAX_GROUPS) || !in(t.off_vgdeg, MB_MAX_GROUPS) || !in(t.off_vedge, 2 * (size_t)t.v_slots) ||
 		    !in(t.off_var_of_cw, 2 * (size_t)t.N))
 			return "table blob: rate table out of range";
 	}
