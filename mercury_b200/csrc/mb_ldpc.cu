@@ -212,11 +212,16 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 		// N = 50 full groups; a group runs to its largest degree, shorter rows read the always-zero slot CS.
 		for (int g = warp; g < MB_N / 32; g += kThreads / 32) {
 			const int v = (g << 5) + lane;
-			const int d = s_vgdeg[g];
-			const uint16_t *__restrict__ se = g_vedge + s_vgbase[g] + lane;
+			const int d = s_vgdeg[g];  // even, warp-uniform
+			const uint16_t *__restrict__ se = g_vedge + (s_vgbase[g] + lane);
 			float acc = s_lch[v];
-#pragma unroll 3
-			for (int k = 0; k < d; k++) acc += s_R[se[k * 32]];
+#pragma unroll 1
+			for (int k = 0; k < d; k += 2) {
+				const unsigned i0 = se[0], i1 = se[32];
+				se += 64;
+				acc += s_R[i0];
+				acc += s_R[i1];
+			}
 			s_lam[v] = acc;
 		}
 		__syncthreads();

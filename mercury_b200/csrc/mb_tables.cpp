@@ -166,9 +166,9 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 		cgbase[g] = c_slots;
 		c_slots += 32u * (uint32_t)t.crow[csorted[g * 32]].size();
 	}
-	for (int g = 0; g * 32 < N; g++) {
+	for (int g = 0; g * 32 < N; g++) {  // variable groups are padded to an EVEN degree: the kernel's loop takes two edges per trip
 		vgbase[g] = v_slots;
-		v_slots += 32u * (uint32_t)t.vrow[vsorted[g * 32]].size();
+		v_slots += 32u * (uint32_t)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1);
 	}
 	if (c_slots >= 0xFFFFu || v_slots >= 0xFFFFu) return "LDPC slot count exceeds 16-bit slot ids";
 	auto cslot = [&](int k, int cs) { return cgbase[cs >> 5] + 32u * (uint32_t)k + (uint32_t)(cs & 31); };
@@ -210,7 +210,7 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	out.off_vgbase = bl.put(vgbase);
 	{
 		std::vector<uint8_t> vgdeg(MB_MAX_GROUPS, 0);
-		for (int g = 0; g * 32 < N; g++) vgdeg[g] = (uint8_t)t.vrow[vsorted[g * 32]].size();
+		for (int g = 0; g * 32 < N; g++) vgdeg[g] = (uint8_t)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1);
 		out.off_vgdeg = bl.put(vgdeg);
 	}
 	out.off_vedge = bl.put(vedge);

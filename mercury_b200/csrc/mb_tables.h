@@ -29,7 +29,7 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 6u
+#define MB_BLOB_VERSION 7u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
@@ -52,7 +52,7 @@ struct MbRate {
 	uint32_t off_vedge;     // u16[v_slots]       check-side slot id held by each variable-side slot (padding = c_slots: an always-zero message)
 	uint32_t off_var_of_cw; // u16[N]             codeword position -> internal variable index
 	uint32_t off_check_of_sorted; // u16[P]       sorted check c' -> reference check index (diagnostics, TX encoder)
-	uint32_t off_vgdeg;     // u8 [MB_MAX_GROUPS] padded (= largest) degree of each group of 32 variables
+	uint32_t off_vgdeg;     // u8 [MB_MAX_GROUPS] padded degree (largest in the group, rounded up to even) of each group of 32 variables
 };
 
 struct MbMode {

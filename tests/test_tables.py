@@ -54,8 +54,8 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
             slot_of[(c, v)] = be.cslot(r, k, cs)
     assert len(slot_of) == r["n_edges"] == len(set(slot_of.values())) and max(slot_of.values()) < r["c_slots"]
     assert (r["edge_var"] != 0xFFFF).sum() == r["n_edges"] == (r["vedge"] != r["c_slots"]).sum()
-    assert all(int(r["vgdeg"][g]) == int(r["vdeg"][32 * g]) for g in range(50))
-    assert r["c_slots"] <= 1.15 * r["n_edges"] and r["v_slots"] <= 1.05 * r["n_edges"]  # padding stays small
+    assert all(int(r["vgdeg"][g]) == (int(r["vdeg"][32 * g]) + 1) // 2 * 2 for g in range(50))
+    assert r["c_slots"] <= 1.15 * r["n_edges"] and r["v_slots"] <= 1.25 * r["n_edges"]  # padding stays small
     for vi in range(1600):
         v = int(cw_of_var[vi])
         ref_row = [int(c) for c in lt["V"][v] if c != -1]
