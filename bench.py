@@ -180,6 +180,30 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------------------
+def synth_batch_on_device(config, B, esn0_db, dev, seed, unique=4096):
+    """U distinct clean frames from the host TX chain (mercury_b200.synth_frames), tiled to B on the device, with an
+    independent AWGN realisation per frame (baseband_test_EsN0 normalisation, telecom_system.cc:98,139-153).
+    Returns (d_x [B,S,272] complex64 on dev, payloads [B,frame_bytes] uint8 on host)."""
+    import torch
+
+    import mercury_b200 as mb
+    U = min(unique, B)
+    S = mb.MODES[config]["Nsymb"]
+    clean, pl_u = mb.synth_frames(config, U, seed=seed, esn0_db=300.0)
+    d_clean = torch.from_numpy(clean).to(dev)
+    d_x = torch.empty((B, S, 272), dtype=torch.complex64, device=dev)
+    sigma = 10.0 ** (-esn0_db / 20.0) * 16.0
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(977 + seed % 1000003)
+    for i in range(0, B, U):
+        k = min(U, B - i)
+        noise = torch.randn((k, S, 272, 2), device=dev, generator=gen) * (sigma / np.sqrt(2.0))
+        d_x[i:i + k] = d_clean[:k] + torch.view_as_complex(noise)
+    del d_clean
+    pl_all = np.tile(pl_u, ((B + U - 1) // U, 1))[:B]
+    return d_x, pl_all
+
+
 def run_own(a):
     import torch
     import torch.distributed as dist
@@ -208,19 +232,7 @@ def run_own(a):
     B, S, fb = a.batch, geom["Nsymb"], geom["frame_bytes"]
     U = min(a.unique, B)
 
-    # ---- synthetic input: U distinct clean frames from the host TX chain, tiled to B, independent AWGN per frame ----
-    clean, pl_u = mb.synth_frames(a.config, U, seed=0x4D455243 + rank, esn0_db=300.0)
-    d_clean = torch.from_numpy(clean).to(dev)
-    d_x = torch.empty((B, S, 272), dtype=torch.complex64, device=dev)
-    sigma = 10.0 ** (-esn0 / 20.0) * 16.0  # telecom_system.cc:98,139-153
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(977 + rank)
-    for i in range(0, B, U):
-        k = min(U, B - i)
-        noise = torch.randn((k, S, 272, 2), device=dev, generator=gen) * (sigma / np.sqrt(2.0))
-        d_x[i:i + k] = d_clean[:k] + torch.view_as_complex(noise)
-    del noise, d_clean
-    pl_all = np.tile(pl_u, ((B + U - 1) // U, 1))[:B]
+    d_x, pl_all = synth_batch_on_device(a.config, B, esn0, dev, seed=0x4D455243 + rank, unique=U)
     d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
     d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
     d_llr = torch.empty((B, 1600), dtype=torch.float32, device=dev)

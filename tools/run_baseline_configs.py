@@ -1,0 +1,114 @@
+#!/usr/bin/env python3
+"""Run BASELINE.json's parity-test configurations on one GPU and write profiles/<name>.json.
+
+  #2  mode 8 (and mode 9), -I 50, 65,536 frames
+  #3  mode 16, -I 20, 262,144 frames, AWGN sweep, FER/BER next to the reference on a sample of the same frames
+  #4  LDPC rate sweep 1..14/16 at fixed symbol count (BPSK geometry CONFIG_0..6 + mode 12 for 14/16), 131,072 frames
+  all 17 modes at threshold + 2 dB, 32,768 frames (frames/s of both stages, FER, payload integrity)
+
+Per line: device-resident frames/s (CUDA events), per-kernel times, demod GB/s on the algorithmic bytes of SURVEY.md 8d,
+decoder edge-updates/s, FER, payload mismatches among decoded frames, and -- on a bounded sample -- agreement with the
+reference CPU path (oracle/_ref if present, else the C port).  Not a bench line; bench.py keeps the driver's contract.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import mercury_b200 as mb  # noqa: E402
+
+
+def run_one(ts, cfg, B, iters, esn0, steps, sample, decoder="spa"):
+    import torch
+    from oracle import port, ref
+    dev = torch.device("cuda", 0)
+    geom = ts.load_configuration(cfg, iters)
+    ts.set_decoder(mb.DECODER_SPA if decoder == "spa" else mb.DECODER_MINSUM)
+    m = mb.MODES[cfg]
+    fb = geom["frame_bytes"]
+    d_x, pl = bench.synth_batch_on_device(cfg, B, esn0, dev, seed=1000 + cfg)
+    d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
+    d_llr = torch.empty((B, 1600), dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    td = tl = 0.0
+    for i in range(steps + 2):
+        ev[0].record()
+        ts.demod_batch_device(d_x, B, d_llr, d_st, None, stream=s)
+        ev[1].record()
+        ts.ldpc_decode_batch_device(d_llr, B, d_pay, d_st, stream=s)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            td += ev[0].elapsed_time(ev[1]) * 1e-3
+            tl += ev[1].elapsed_time(ev[2]) * 1e-3
+    td, tl = td / steps, tl / steps
+    st = d_st.cpu().numpy().view(mb.STATS_DTYPE).reshape(-1)
+    pay = d_pay.cpu().numpy()
+    dec = st["message_decoded"] == 1
+    its = np.clip(st["iterations_done"], 0, iters)
+    bit_err = int(np.unpackbits(pay ^ pl, axis=1).sum())
+    out = {
+        "config": cfg, "decoder": decoder, "frames": B, "ldpc_iters": iters, "esn0_db": esn0,
+        "frames_per_s": B / (td + tl), "demod_ms": td * 1e3, "ldpc_ms": tl * 1e3,
+        "demod_gbs_algorithmic": m["demod_bytes"] * B / td / 1e9, "demod_frames_per_s": B / td,
+        "ldpc_edge_updates_per_s": float(its.sum()) * m["edges"] / tl, "ldpc_frames_per_s": B / tl,
+        "mean_iterations": float(its.mean()), "fer": float(1 - dec.mean()), "ber_payload": bit_err / (pay.size * 8.0),
+        "payload_mismatches_among_decoded": int((pay[dec] != pl[dec]).any(axis=1).sum()),
+    }
+    if sample:
+        o = ref.Ref(cfg, iters) if ref.available() else port.Port(cfg, iters)
+        xs = d_x[:sample].cpu().numpy()
+        agree_dec = agree_pay = agree_it = ref_dec = 0
+        for f in range(sample):
+            r = o.rx_tail(xs[f].reshape(-1).astype(np.complex128))
+            agree_dec += int(r["decoded"] == st["message_decoded"][f])
+            agree_it += int(r["iterations"] == st["iterations_done"][f])
+            if r["decoded"]:
+                ref_dec += 1
+                agree_pay += int(np.array_equal(r["payload"].astype(np.uint8), pay[f]))
+        out["reference_sample"] = {"kind": "reference" if ref.available() else "port", "frames": sample, "reference_decoded": ref_dec,
+                                   "decoded_flag_agrees": agree_dec, "payload_bit_exact_where_reference_decodes": agree_pay,
+                                   "iteration_count_agrees": agree_it, "reference_fer": 1 - ref_dec / sample}
+    del d_x, d_llr
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_baseline_configs.json"))
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    ts = mb.TelecomSystemB200(0)
+    q = 8 if a.quick else 1
+    res = {"config2": [], "config3": [], "config4": [], "all_modes": []}
+    for cfg in (8, 9):
+        res["config2"].append(run_one(ts, cfg, 65536 // q, 50, mb.THRESH_DB[cfg] + 2.0, 5, 256))
+        res["config2"].append(run_one(ts, cfg, 65536 // q, 50, mb.THRESH_DB[cfg] + 2.0, 5, 0, decoder="minsum"))
+    for esn0 in (18.0, 20.0, 22.0, 25.0, 30.0):
+        res["config3"].append(run_one(ts, 16, 262144 // q, 20, esn0, 3, 128))
+    for cfg in (0, 1, 2, 3, 4, 5, 6, 12):
+        res["config4"].append(run_one(ts, cfg, 131072 // q, 50, mb.THRESH_DB[cfg] + 2.0, 3, 64))
+    for cfg in range(17):
+        esn0 = mb.THRESH_DB[cfg] + (2.0 if cfg < 15 else 14.0)
+        res["all_modes"].append(run_one(ts, cfg, 32768 // q, 20 if cfg == 16 else 50, esn0, 3, 32))
+    json.dump(res, open(a.out, "w"), indent=1)
+    for k, v in res.items():
+        print(k)
+        for r in v:
+            rs = r.get("reference_sample", {})
+            print(f"  mode {r['config']:2d} {r['decoder']:6s} B={r['frames']:6d} EsN0={r['esn0_db']:5.1f} {r['frames_per_s'] / 1e6:6.2f} Mf/s "
+                  f"demod {r['demod_gbs_algorithmic']:6.0f} GB/s ldpc {r['ldpc_edge_updates_per_s'] / 1e9:6.1f} Ge/s it {r['mean_iterations']:5.2f} "
+                  f"FER {r['fer']:.4f} mism {r['payload_mismatches_among_decoded']} "
+                  f"ref[{rs.get('frames', 0)}]: dec= {rs.get('decoded_flag_agrees', '-')} pay= {rs.get('payload_bit_exact_where_reference_decodes', '-')}/{rs.get('reference_decoded', '-')} it= {rs.get('iteration_count_agrees', '-')}")
+
+
+if __name__ == "__main__":
+    main()
