@@ -1,4 +1,4 @@
-// mb_demod.cu -- K_demod: fused OFDM demodulator for sm_100a, one CTA per frame.
+// mb_demod.cu -- K_demod: fused OFDM demodulator for sm_100a; persistent CTAs fed by the bulk-copy (TMA) engine.
 //
 //   FFT-256 per symbol  ->  AGC  ->  LS / ZF channel estimate  ->  column interpolation  ->  (phase-only)
 //   equalise  ->  pilot noise variance  ->  deframe + T/F de-interleave  ->  max-log soft de-map  ->
@@ -15,60 +15,89 @@
 //   LLR expand telecom_system.cc:1300-1308
 //
 // How (B200-first, not the reference's loops):
-//   * HBM-bound stage: every sample is read exactly once with 8-byte streaming loads (16 independent loads in
-//     flight per thread, guard interval never fetched); the only other HBM traffic is the 6.4 KB LLR vector.
-//   * FFT-256 = 16 x 16: 16 threads per OFDM symbol, two radix-4x4 16-point DFTs in registers around one
-//     conflict-free (stride-17) shared-memory transpose that needs only __syncwarp (a symbol lives in half a warp).
-//     Twiddles (with the reference's 1/N folded in) come from a 2 KB shared table laid out for broadcast reads.
-//     The second DFT is pruned to the 4 of 16 outputs that land on the 50 active carriers.
-//   * The LS estimator's O(pilots x window) double loop is restated as the windowed mean it is:
-//     a separable clipped 21x21 box sum over the pilot lattice, row pass then column pass, in shared memory.
-//   * deframe, both de-interleavers and the LLR expand are composed on the host into two gather/scatter index
-//     tables (mb_tables.cpp), so no intermediate vector is ever materialised.
+//   * HBM-bound stage, so the memory system is driven by the copy engine, not by the math warps: each CTA is persistent
+//     (grid = SMs x resident CTAs), walks its frames round-robin, and one thread keeps a two-slot shared-memory ring
+//     filled with cp.async.bulk copies (2 KB per OFDM symbol, guard interval never fetched) that complete on mbarriers.
+//     The next frame streams in while the current one is being estimated / equalised / de-mapped.  The 6.4 KB LLR vector
+//     leaves through one bulk store.  Every sample is read from HBM exactly once.
+//   * FFT-256 = 16 x 16: 16 threads per OFDM symbol, two radix-4x4 16-point DFTs in registers around an in-place,
+//     XOR-swizzled (conflict-free) transpose inside the ring slot that needs only __syncwarp (a symbol lives in half a
+//     warp).  All complex arithmetic uses the sm_100 packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one instruction per complex
+//     add, two per complex multiply, +-i rotations folded into operand swizzles).  The second DFT is pruned to the 4 of
+//     16 outputs that land on the 50 active carriers.
+//   * The LS estimator's O(pilots x window) double loop is restated as the clipped 21x21 box mean it is:
+//     compact pilot rows -> 7-entry window sums (18 distinct windows per row) -> running sums over the rows of each
+//     lattice residue -> every pilot reads 3 x (upper - lower) entries through host-resolved byte offsets.
+//   * deframe, both de-interleavers and the LLR expand are composed on the host into per-cell records (mb_tables.cpp), so
+//     no intermediate vector is ever materialised; the kernel is instantiated per (Nsymb, M, estimator, phase-only).
 #include "mb_kernels.cuh"
 
 namespace {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
-__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
-__device__ __forceinline__ float2 cdiv(float2 a, float2 b)
+// ------------------------------------------------------------------------------------------------------------------
+// packed complex arithmetic (float2 = re, im)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }  // a + (-i) b
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }  // a + (+i) b
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
 {
-	float inv = 1.0f / (b.x * b.x + b.y * b.y);
-	return make_float2((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
+	return __ffma2_rn(make_float2(a.x, a.x), w, __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x)));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 h)  // a * conj(h)
+{
+	return __ffma2_rn(make_float2(a.x, a.x), make_float2(h.x, -h.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(h.y, h.x)));
+}
+__device__ __forceinline__ float cnorm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+__device__ __forceinline__ float fast_rcp(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+	float r;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
 }
 
 // forward 4-point DFT (W4 = -i)
 __device__ __forceinline__ void dft4(float2 a, float2 b, float2 c, float2 d, float2 &y0, float2 &y1, float2 &y2, float2 &y3)
 {
-	float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+	const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
 	y0 = cadd(t0, t2);
 	y2 = csub(t0, t2);
-	y1 = cadd(t1, mul_mi(t3));
-	y3 = cadd(t1, mul_pi(t3));
+	y1 = cadd_mi(t1, t3);
+	y3 = cadd_pi(t1, t3);
 }
 
 #define MB_C1 0.92387953251128674f
 #define MB_S1 0.38268343236508977f
 #define MB_R2 0.70710678118654752f
 
-// Stage 1+2 of the radix-4x4 16-point forward DFT: A[n2][k1] = W16^(n2 k1) * sum_n1 x[4 n1 + n2] (-i)^(n1 k1)
+// Stage 1 of the radix-4x4 16-point forward DFT with the W16 twiddles applied, EXCEPT the -i of A[2][2] (W16^4), which
+// the second stage folds into its additions:  A[n2][k1] = W16^(n2 k1) * sum_n1 x[4 n1 + n2] (-i)^(n1 k1)
 __device__ __forceinline__ void fft16_front(const float2 (&x)[16], float2 (&A)[4][4])
 {
 #pragma unroll
 	for (int n2 = 0; n2 < 4; n2++) dft4(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], A[n2][0], A[n2][1], A[n2][2], A[n2][3]);
-	A[1][1] = cmul(A[1][1], make_float2(MB_C1, -MB_S1));   // W16^1
-	A[1][2] = cmul(A[1][2], make_float2(MB_R2, -MB_R2));   // W16^2
-	A[1][3] = cmul(A[1][3], make_float2(MB_S1, -MB_C1));   // W16^3
-	A[2][1] = cmul(A[2][1], make_float2(MB_R2, -MB_R2));   // W16^2
-	A[2][2] = mul_mi(A[2][2]);                             // W16^4
-	A[2][3] = cmul(A[2][3], make_float2(-MB_R2, -MB_R2));  // W16^6
-	A[3][1] = cmul(A[3][1], make_float2(MB_S1, -MB_C1));   // W16^3
-	A[3][2] = cmul(A[3][2], make_float2(-MB_R2, -MB_R2));  // W16^6
-	A[3][3] = cmul(A[3][3], make_float2(-MB_C1, MB_S1));   // W16^9
+	A[1][1] = cmul(A[1][1], make_float2(MB_C1, -MB_S1));    // W16^1
+	A[1][2] = cscale(cadd_mi(A[1][2], A[1][2]), MB_R2);     // W16^2 = (1 - i)/sqrt2
+	A[1][3] = cmul(A[1][3], make_float2(MB_S1, -MB_C1));    // W16^3
+	A[2][1] = cscale(cadd_mi(A[2][1], A[2][1]), MB_R2);     // W16^2
+	A[2][3] = cscale(cadd_pi(A[2][3], A[2][3]), -MB_R2);    // W16^6 = -(1 + i)/sqrt2
+	A[3][1] = cmul(A[3][1], make_float2(MB_S1, -MB_C1));    // W16^3
+	A[3][2] = cscale(cadd_pi(A[3][2], A[3][2]), -MB_R2);    // W16^6
+	A[3][3] = cmul(A[3][3], make_float2(-MB_C1, MB_S1));    // W16^9
 }
 
 // full 16-point forward DFT, natural order out: X[k1 + 4 k2]
@@ -77,7 +106,18 @@ __device__ __forceinline__ void fft16(const float2 (&x)[16], float2 (&X)[16])
 	float2 A[4][4];
 	fft16_front(x, A);
 #pragma unroll
-	for (int k1 = 0; k1 < 4; k1++) dft4(A[0][k1], A[1][k1], A[2][k1], A[3][k1], X[k1], X[k1 + 4], X[k1 + 8], X[k1 + 12]);
+	for (int k1 = 0; k1 < 4; k1++) {
+		if (k1 != 2) {
+			dft4(A[0][k1], A[1][k1], A[2][k1], A[3][k1], X[k1], X[k1 + 4], X[k1 + 8], X[k1 + 12]);
+		} else {  // the third input still lacks its -i
+			const float2 t0 = cadd_mi(A[0][2], A[2][2]), t1 = cadd_pi(A[0][2], A[2][2]);
+			const float2 t2 = cadd(A[1][2], A[3][2]), t3 = csub(A[1][2], A[3][2]);
+			X[2] = cadd(t0, t2);
+			X[10] = csub(t0, t2);
+			X[6] = cadd_mi(t1, t3);
+			X[14] = cadd_pi(t1, t3);
+		}
+	}
 }
 
 // 16-point forward DFT pruned to outputs 0, 1, 14, 15 (the only ones that reach the 50 active carriers)
@@ -85,11 +125,54 @@ __device__ __forceinline__ void fft16_pruned(const float2 (&x)[16], float2 &X0, 
 {
 	float2 A[4][4];
 	fft16_front(x, A);
-	X0 = cadd(cadd(A[0][0], A[2][0]), cadd(A[1][0], A[3][0]));                   // k1=0, k2=0
-	X1 = cadd(cadd(A[0][1], A[2][1]), cadd(A[1][1], A[3][1]));                   // k1=1, k2=0
-	X14 = cadd(csub(A[0][2], A[2][2]), mul_pi(csub(A[1][2], A[3][2])));          // k1=2, k2=3
-	X15 = cadd(csub(A[0][3], A[2][3]), mul_pi(csub(A[1][3], A[3][3])));          // k1=3, k2=3
+	X0 = cadd(cadd(A[0][0], A[2][0]), cadd(A[1][0], A[3][0]));          // k1=0, k2=0
+	X1 = cadd(cadd(A[0][1], A[2][1]), cadd(A[1][1], A[3][1]));          // k1=1, k2=0
+	X14 = cadd_pi(cadd_pi(A[0][2], A[2][2]), csub(A[1][2], A[3][2]));   // k1=2, k2=3: (a0 - (-i a2)) + i (a1 - a3)
+	X15 = cadd_pi(csub(A[0][3], A[2][3]), csub(A[1][3], A[3][3]));      // k1=3, k2=3
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX; SASS: SYNCS / UBLKCP)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile(
+		"{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(ok)
+		: "r"(bar), "r"(parity)
+		: "memory");
+	return ok != 0;
+}
+// Bounded wait: a byte-count mismatch must surface as a launch failure, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
+		if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+		     "r"(bar)
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Warp-level sum of three values; lane 0 of every warp parks its partial sums in s_part[warp*3 .. +2].  The CTA-wide
 // totals are formed by every thread after the next barrier the algorithm needs anyway (no reduction-only barriers).
@@ -108,21 +191,26 @@ __device__ __forceinline__ void warp_partials3(float a, float b, float c, float 
 		s_part[w * 3 + 2] = c;
 	}
 }
+__device__ __forceinline__ void warp_partial1(float a, float *s_part)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+	if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = a;
+}
 
 // Max-log LLRs of one equalised symbol (psk.cc:278-326): for bit k (mask 1<<k) (min_{bit=1} D - min_{bit=0} D) / variance,
-// emitted MSB first.  M is a compile-time constant so every (j >> k) & 1 test folds away.
+// emitted MSB first; dw[] holds the byte offsets of the emitted LLRs in the internal-order vector, two per word.
 template <int M, int BPS>
-__device__ __forceinline__ void demap_scatter(const float2 z, const float inv_var, const float2 *s_cons, const int base,
-					      const uint16_t *__restrict__ g_dst, const uint16_t *__restrict__ g_dst2, float *s_L)
+__device__ __forceinline__ void demap_scatter(const float2 z, const float inv_var, const float2 *s_cons, const uint32_t (&dw)[3],
+					      unsigned char *s_L)
 {
 	float d0[BPS], d1[BPS];
 #pragma unroll
 	for (int k = 0; k < BPS; k++) d0[k] = d1[k] = 3.0e38f;
 #pragma unroll
 	for (int j = 0; j < M; j++) {
-		const float2 cj = s_cons[j];
-		const float dx = z.x - cj.x, dy = z.y - cj.y;
-		const float D = dx * dx + dy * dy;
+		const float2 d = csub(z, s_cons[j]);
+		const float D = cnorm2(d);
 #pragma unroll
 		for (int k = 0; k < BPS; k++) {
 			if ((j >> k) & 1)
@@ -132,298 +220,422 @@ __device__ __forceinline__ void demap_scatter(const float2 z, const float inv_va
 		}
 	}
 #pragma unroll
-	for (int k = 0; k < BPS; k++) {
+	for (int e = 0; e < BPS; e++) {
+		const int k = BPS - 1 - e;
 		const float llr = inv_var * (d1[k] - d0[k]);
-		const int i = base + (BPS - 1 - k);
-		s_L[g_dst[i]] = llr;
-		const unsigned d2 = g_dst2[i];
-		if (d2 != MB_NO_DST) s_L[d2] = llr;
+		const uint32_t off = (e & 1) ? (dw[e >> 1] >> 16) : (dw[e >> 1] & 0xFFFFu);
+		*reinterpret_cast<float *>(s_L + off) = llr;
 	}
 }
 
-constexpr int kSmemHeadFloats = 2 * 32 + 2 * 32;  // constellation, two sets of per-warp partial sums
-constexpr int kZfStride = 27;                     // compact pilot row: 4 zeros | <=17 pilots | zeros
-constexpr int kMaxThreads = 192;
+// ------------------------------------------------------------------------------------------------------------------
+// compile-time geometry of one instantiation
+// ------------------------------------------------------------------------------------------------------------------
+template <int S>
+struct Geo {
+	static constexpr int SC = S == 48 ? 12 : (S == 24 ? 12 : (S == 16 ? 8 : S));  // symbols per ring slot
+	static constexpr int NCH = S / SC;                                                // slots (chunks) per frame
+	static constexpr int T = (SC * 16 + 31) / 32 * 32;                                // threads per CTA
+	static constexpr int NW = T / 32;
+	static constexpr int MINB = S == 48 ? 2 : (S == 24 || S == 12 ? 3 : 4);                // resident CTAs per SM the layout below allows
+	static constexpr int MAXREG = (65536 / (MINB * T)) / 8 * 8 > 128 ? 128 : (65536 / (MINB * T)) / 8 * 8;
+	static constexpr int CELLS = S * MB_NC;
+	static constexpr int NPIL = (S * MB_NC + 2) / 3;   // pilots: cells with s%3 == c%3
+	static constexpr int NDATA = CELLS - NPIL;
+	static constexpr int ZF = S * MB_ZF_STRIDE;
+	static constexpr int PM = (S + 1) * MB_LS_COLS;
+	// shared memory layout (bytes)
+	static constexpr int OFF_BAR = 0;                        // 2 x u64 mbarriers
+	static constexpr int OFF_PART = 16;                      // 64 floats of per-warp partial sums
+	static constexpr int OFF_CONS = OFF_PART + 256;          // 32 float2 constellation
+	static constexpr int OFF_Y = OFF_CONS + 256;             // [S][50] float2 carriers
+	static constexpr int OFF_ZF = OFF_Y + CELLS * 8;         // [S][27] float2 compact pilot rows, later the channel at pilots
+	static constexpr int OFF_PM = OFF_ZF + ((ZF * 8 + 15) & ~15);  // [S+1][18] float2 window sums / running sums
+	static constexpr int OFF_L = OFF_PM + PM * 8;            // [1600] float LLRs, decoder order
+	static constexpr int OFF_RING = (OFF_L + MB_N * 4 + 127) & ~127;
+	static constexpr int SLOT_BYTES = SC * MB_NFFT * 8;
+	static constexpr int SMEM = OFF_RING + 2 * SLOT_BYTES;
+	static_assert(S % SC == 0, "chunks must tile the frame");
+	static_assert(OFF_L % 16 == 0 && OFF_Y % 16 == 0 && OFF_ZF % 16 == 0 && OFF_PM % 16 == 0, "alignment");
+};
 
-template <bool kDebug>
-__global__ void __launch_bounds__(kMaxThreads, 5) mb_demod_kernel(const MbDemodArgs a)
+template <int S, int M, bool LS, bool PHASE>
+__global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	using G = Geo<S>;
+	constexpr int T = G::T, NW = G::NW, SC = G::SC, NCH = G::NCH;
+	constexpr int BPS = M == 2 ? 1 : (M == 4 ? 2 : (M == 8 ? 3 : (M == 16 ? 4 : 5)));
+	constexpr int RECW = BPS <= 2 ? 2 : 4;
+	extern __shared__ __align__(128) unsigned char smem[];
 	const MbMode &m = a.mode;
-	const int T = blockDim.x, tid = threadIdx.x, nwarps = T >> 5;
-	const int S = m.Nsymb, cells = S * MB_NC;
-	float2 *s_cons = reinterpret_cast<float2 *>(smem_raw);
-	float *s_part1 = reinterpret_cast<float *>(s_cons + 32);  // AGC partials
-	float *s_part2 = s_part1 + 32;                             // pilot-statistics partials
-	float2 *s_Y = reinterpret_cast<float2 *>(s_part2 + 32);
-	float2 *s_buf = s_Y + cells;               // FFT transpose scratch, then reused:
-	float2 *s_zf = s_buf;                      //   [S][27] compact zero-padded pilot rows of Y/p, later the channel at pilots
-	const int zf_elems = (S * kZfStride + 1) & ~1;  // keep everything behind it 16-byte aligned (float4 reads of s_L)
-	float2 *s_T = s_buf + zf_elems;            //   [S][50] clipped 21-column window sums of each row
-	float *s_L = reinterpret_cast<float *>(s_T + cells);  // [1600] LLRs, decoder order
+	const int tid = threadIdx.x;
+	float *s_part = reinterpret_cast<float *>(smem + G::OFF_PART);
+	float2 *s_cons = reinterpret_cast<float2 *>(smem + G::OFF_CONS);
+	float2 *s_Y = reinterpret_cast<float2 *>(smem + G::OFF_Y);
+	unsigned char *s_Yb = smem + G::OFF_Y;
+	float2 *s_zf = reinterpret_cast<float2 *>(smem + G::OFF_ZF);
+	unsigned char *s_zfb = smem + G::OFF_ZF;
+	float2 *s_pm = reinterpret_cast<float2 *>(smem + G::OFF_PM);
+	unsigned char *s_pmb = smem + G::OFF_PM;
+	unsigned char *s_Lb = smem + G::OFF_L;
+	float *s_L = reinterpret_cast<float *>(s_Lb);
+	float2 *s_ring = reinterpret_cast<float2 *>(smem + G::OFF_RING);
+	const uint32_t bar0 = smem_u32(smem + G::OFF_BAR);
 
-	const size_t frame = blockIdx.x;
-	const float2 *__restrict__ xf = a.x + frame * (size_t)S * MB_NOFDM;
-	const float *__restrict__ g_pinv = reinterpret_cast<const float *>(a.blob + m.off_pinv);
-	const float *__restrict__ g_pval = reinterpret_cast<const float *>(a.blob + m.off_pval);
-	const float *__restrict__ g_invn = reinterpret_cast<const float *>(a.blob + m.off_invn);
-	const uint32_t *__restrict__ g_pilot_info = reinterpret_cast<const uint32_t *>(a.blob + m.off_pilot_info);
-	const uint32_t *__restrict__ g_sym_info = reinterpret_cast<const uint32_t *>(a.blob + m.off_sym_info);
-	const uint16_t *__restrict__ g_dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
-	const uint16_t *__restrict__ g_dst2 = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst2);
+	const uint32_t *__restrict__ g_zf_src = reinterpret_cast<const uint32_t *>(a.blob + m.off_zf_src);
+	const uint4 *__restrict__ g_prec = reinterpret_cast<const uint4 *>(a.blob + m.off_pilot_rec);
+	const float2 *__restrict__ g_pf = reinterpret_cast<const float2 *>(a.blob + m.off_pilot_f);
+	const uint32_t *__restrict__ g_drec = reinterpret_cast<const uint32_t *>(a.blob + m.off_data_rec);
 
-	if (tid < m.M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];  // published by the barrier after the FFT
+	// frames of this CTA: blockIdx.x, + gridDim.x, ...; ring chunk q = frame slot q / NCH, symbols (q % NCH) * SC ..
+	const long long n_mine = ((long long)a.n_frames - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
+	const long long n_chunks = n_mine * NCH;
+	auto issue_chunk = [&](long long q) {  // one thread: arm the slot's mbarrier, then one 2 KB bulk copy per symbol (GI skipped)
+		const uint32_t slot = (uint32_t)(q & 1);
+		const uint32_t bar = bar0 + 8u * slot;
+		const size_t frame = (size_t)blockIdx.x + (size_t)(q / NCH) * gridDim.x;
+		const float2 *src = a.x + (frame * S + (size_t)(q % NCH) * SC) * MB_NOFDM + MB_NGI;
+		const uint32_t dst = smem_u32(s_ring) + slot * (uint32_t)G::SLOT_BYTES;
+		mbar_expect_tx(bar, (uint32_t)G::SLOT_BYTES);
+#pragma unroll 1
+		for (int s = 0; s < SC; s++) bulk_g2s(dst + (uint32_t)s * (MB_NFFT * 8), src + (size_t)s * MB_NOFDM, MB_NFFT * 8, bar);
+	};
 
-	// ---------------- FFT-256 per symbol (a2, a3) ------------------------------------------------------------
+	if (tid == 0) {
+		mbar_init(bar0, 1);
+		mbar_init(bar0 + 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		fence_proxy_async();
+	}
+	if (tid < M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];
+	if (LS)
+		for (int i = tid; i < MB_LS_COLS; i += T) s_pm[S * MB_LS_COLS + i] = make_float2(0.f, 0.f);  // the "no lower bound" row
+	__syncthreads();
+	if (tid == 0) {
+		if (n_chunks > 0) issue_chunk(0);
+		if (n_chunks > 1) issue_chunk(1);
+	}
+
+	// frame-invariant per-thread constants
+	const int grp = tid >> 4, t = tid & 15;
+	float2 tw[16];
 	{
-		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);  // 2 KB, L1 resident
-		const int grp = tid >> 4, t = tid & 15, spr = T >> 4;
-		float2 *buf = s_buf + grp * (16 * 17);
-		float2 tw[16];
+		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);
 #pragma unroll
-		for (int k1 = 1; k1 < 16; k1++) tw[k1] = __ldg(g_tw + k1 * 16 + t);  // W256^(t k1)/256, kept across rounds
+		for (int k1 = 1; k1 < 16; k1++) tw[k1] = __ldg(g_tw + k1 * 16 + t);  // W256^(t k1)/256
 		tw[0] = make_float2(1.0f / 256.0f, 0.f);
-		for (int s0 = 0; s0 < S; s0 += spr) {
-			const int s = s0 + grp;
-			const bool active = s < S;
+	}
+	uint32_t xhi[4], xlo[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		xhi[i] = (uint32_t)(i * 32) ^ (uint32_t)((t * 8) & 96);
+		xlo[i] = (uint32_t)(i * 8) ^ (uint32_t)((t * 8) & 24);
+	}
+	constexpr int ZF_PER = (G::ZF + T - 1) / T;
+	uint32_t zsrc[ZF_PER];
+#pragma unroll
+	for (int i = 0; i < ZF_PER; i++) zsrc[i] = (tid + i * T < G::ZF) ? __ldg(g_zf_src + tid + i * T) : 0u;
+	const uint32_t pinv_bits = __float_as_uint(m.pinv_mag);
+	const float inv_np = 1.0f / (float)G::NPIL;
+	const bool dbg = a.dbg_Y || a.dbg_H || a.dbg_Z;
+
+	long long q = 0;
+	for (long long fi = 0; fi < n_mine; fi++) {
+		const size_t frame = (size_t)blockIdx.x + (size_t)fi * gridDim.x;
+		// ---------------- FFT-256 per symbol (a2, a3), one ring slot (SC symbols) at a time ------------------------------
+#pragma unroll 1
+		for (int ch = 0; ch < NCH; ch++, q++) {
+			const uint32_t slot = (uint32_t)(q & 1);
+			mbar_wait(bar0 + 8u * slot, (uint32_t)((q >> 1) & 1));
+			const bool active = grp < SC;  // Nsymb = 9: the last half warp has no symbol, but still takes part in the warp syncs
+			unsigned char *symb = reinterpret_cast<unsigned char *>(s_ring) + slot * (uint32_t)G::SLOT_BYTES + (active ? grp : 0) * (MB_NFFT * 8);
+			float2 v[16];
 			if (active) {
-				const float2 *__restrict__ xs = xf + (size_t)s * MB_NOFDM + MB_NGI + t;
-				float2 v[16], A[16];
 #pragma unroll
-				for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldcs(xs + 16 * n1);  // x[16 n1 + t], GI skipped
+				for (int n1 = 0; n1 < 16; n1++) v[n1] = *reinterpret_cast<const float2 *>(symb + t * 8 + n1 * 128);  // x[16 n1 + t]
+			}
+			__syncwarp();
+			// In-place transpose: element (row r, column c) lives at byte r*128 + ((c ^ r) * 8).  (c ^ r) * 8 splits into two
+			// disjoint 2-bit fields, so every address is base[c >> 2] + xlo[c & 3]: one add per access, eight registers.
+			if (active) {
+				float2 A[16];
 				fft16(v, A);
-				buf[t * 17] = cscale(A[0], 1.0f / 256.0f);
+				unsigned char *wb[4] = {symb + t * 128 + xhi[0], symb + t * 128 + xhi[1], symb + t * 128 + xhi[2], symb + t * 128 + xhi[3]};
+				*reinterpret_cast<float2 *>(wb[0] + xlo[0]) = cscale(A[0], 1.0f / 256.0f);
 #pragma unroll
-				for (int k1 = 1; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], tw[k1]);
+				for (int k1 = 1; k1 < 16; k1++) *reinterpret_cast<float2 *>(wb[k1 >> 2] + xlo[k1 & 3]) = cmul(A[k1], tw[k1]);
 			}
 			__syncwarp();
 			if (active) {
-				float2 w[16], X0, X1, X14, X15;
+				float2 X0, X1, X14, X15;
+				const unsigned char *rb[4] = {symb + xhi[0], symb + xhi[1], symb + xhi[2], symb + xhi[3]};
 #pragma unroll
-				for (int n2 = 0; n2 < 16; n2++) w[n2] = buf[n2 * 17 + t];
-				fft16_pruned(w, X0, X1, X14, X15);  // bins t, 16+t, 224+t, 240+t
-				float2 *row = s_Y + s * MB_NC;
+				for (int n2 = 0; n2 < 16; n2++) v[n2] = *reinterpret_cast<const float2 *>(rb[n2 >> 2] + xlo[n2 & 3] + n2 * 128);
+				fft16_pruned(v, X0, X1, X14, X15);  // bins t, 16+t, 224+t, 240+t
+				float2 *row = s_Y + (ch * SC + grp) * MB_NC;
 				// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49
 				if (t >= 1) row[24 + t] = X0;
 				if (t <= 9) row[40 + t] = X1;
 				if (t >= 7) row[t - 7] = X14;
 				row[9 + t] = X15;
 			}
-			__syncwarp();
+			fence_proxy_async();  // this thread's generic-proxy accesses to the slot precede the next bulk copy into it
+			__syncthreads();
+			if (tid == 0 && q + 2 < n_chunks) issue_chunk(q + 2);
 		}
-	}
-	__syncthreads();
 
-	// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
-	// Row s holds its pilots (columns s%3 + 3j) at [4 + j]; everything else in the 27-wide row is zero, so that every
-	// clipped 21-column window is exactly 7 consecutive entries (21 consecutive integers hold 7 of each residue mod 3).
-	for (int i = tid; i < S * kZfStride; i += T) {
-		const int s = i / kZfStride, j = i - s * kZfStride;
-		if (j < 4 || j > 20 || (j == 20 && s % 3 == 2)) s_zf[i] = make_float2(0.f, 0.f);  // rows with s%3==2 hold 16 pilots only
-	}
-	{
-		float acc = 0.f;
-		for (int p = tid; p < m.nPilots; p += T) {
-			const unsigned info = g_pilot_info[p];
-			const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
-			const float2 y = s_Y[cell];
-			acc += sqrtf(y.x * y.x + y.y * y.y);
-			const float w = g_pinv[cell];
-			s_zf[s * kZfStride + 4 + j] = make_float2(y.x * w, y.y * w);  // ZF estimate Y/p (AGC gain applied later: all linear)
-		}
-		warp_partials3(acc, 0.f, 0.f, s_part1);
-	}
-	__syncthreads();
-
-	// ---------------- LS estimate (a5), row pass: clipped 21-column window sums over the pilot lattice -----------------
-	if (m.estimator == 1 && tid < 3 * MB_NC) {
-		const int r = tid / MB_NC, c = tid - r * MB_NC;  // this thread: column c of the rows with s%3 == r
-		const int lo = (c + 4 - r) / 3;                  // compact index of the first pilot column >= c-10 in such a row
-		for (int k = r; k < S; k += 3) {
-			const float2 *row = s_zf + k * kZfStride + lo;
-			float sx = 0.f, sy = 0.f;
+		// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
+		{
+			float acc = 0.f;
 #pragma unroll
-			for (int j = 0; j < 7; j++) {
-				sx += row[j].x;
-				sy += row[j].y;
+			for (int i = 0; i < ZF_PER; i++) {
+				const int idx = tid + i * T;
+				if (idx < G::ZF) {
+					const uint32_t w = zsrc[i];
+					const float2 y = *reinterpret_cast<const float2 *>(s_Yb + (w & 0x7FFFu));
+					const bool valid = (w >> 30) & 1u;
+					const float pinv = __uint_as_float(pinv_bits | (w & 0x80000000u));
+					acc += valid ? fast_sqrt(cnorm2(y)) : 0.f;
+					s_zf[idx] = valid ? cscale(y, pinv) : make_float2(0.f, 0.f);  // ZF estimate Y/p (AGC gain applied later: all linear)
+				}
 			}
-			s_T[k * MB_NC + c] = make_float2(sx, sy);
+			warp_partial1(acc, s_part);
 		}
-	}
-	float g;
-	{
-		float acc = 0.f;
-		for (int w = 0; w < nwarps; w++) acc += s_part1[w * 3];
-		g = m.boost / (acc / (float)m.nPilots);  // automatic_gain_control, ofdm.cc:1467-1498
-	}
-	__syncthreads();
-
-	// ---------------- channel at pilots (column pass), pilot-domain statistics (a5/a6, a8-a10) ------------------------
-	{
-		float accH = 0.f, accV = 0.f, accVn = 0.f;
-		for (int p = tid; p < m.nPilots; p += T) {
-			const unsigned info = g_pilot_info[p];
-			const int cell = info & 0xFFF, s = (info >> 12) & 0x3F, j = info >> 18;
-			const float2 yg = cscale(s_Y[cell], g);
-			float2 h;
-			if (m.estimator == 1) {
-				const int c = cell - s * MB_NC;
-				const int k0 = max(0, s - MB_LS_HALF), k1 = min(S - 1, s + MB_LS_HALF);
-				float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
-				int k = k0;
-				for (; k + 1 <= k1; k += 2) {
-					const float2 ta = s_T[k * MB_NC + c], tb = s_T[(k + 1) * MB_NC + c];
-					sx0 += ta.x, sy0 += ta.y, sx1 += tb.x, sy1 += tb.y;
+		__syncthreads();
+		float g;
+		{
+			float acc = 0.f;
+#pragma unroll
+			for (int w = 0; w < NW; w++) acc += s_part[w];
+			g = m.boost * fast_rcp(acc * inv_np);  // automatic_gain_control, ofdm.cc:1467-1498
+		}
+		// ---------------- LS estimate (a5): window sums + running sums over the rows of each lattice residue --------------
+		if (LS) {
+			if (tid < 3 * MB_LS_COLS) {
+				const int r = tid / MB_LS_COLS, jj = tid - r * MB_LS_COLS;
+				float2 run = make_float2(0.f, 0.f);
+#pragma unroll
+				for (int k3 = 0; k3 < (S + 2) / 3; k3++) {
+					const int k = r + 3 * k3;
+					if (k < S) {
+						const float2 *row = s_zf + k * MB_ZF_STRIDE + jj;
+						const float2 s01 = cadd(row[0], row[1]), s23 = cadd(row[2], row[3]), s45 = cadd(row[4], row[5]);
+						run = cadd(run, cadd(cadd(s01, s23), cadd(s45, row[6])));
+						s_pm[k * MB_LS_COLS + jj] = run;
+					}
 				}
-				if (k <= k1) {
-					const float2 ta = s_T[k * MB_NC + c];
-					sx0 += ta.x, sy0 += ta.y;
-				}
-				const float w = g_invn[cell] * g;
-				h = make_float2((sx0 + sx1) * w, (sy0 + sy1) * w);
-			} else {
-				h = cscale(s_zf[s * kZfStride + 4 + j], g);  // ZF: H = Y / p
 			}
-			// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the rows are dead
-			// (the row pass consumed them before the barrier), in ZF mode this thread is the slot's only user.
-			s_zf[s * kZfStride + 4 + j] = h;
-			const float h2 = h.x * h.x + h.y * h.y;
-			accH += sqrtf(h2);
-			const float pv = g_pval[cell];
-			const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);  // yg * conj(h)
+			__syncthreads();
+		}
+
+		// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) ------------------------------------
+		{
+			float accH = 0.f, accV = 0.f, accVn = 0.f;
+#pragma unroll 1
+			for (int p = tid; p < G::NPIL; p += T) {
+				const uint4 rec = __ldg(g_prec + p);
+				const float2 pf = __ldg(g_pf + p);
+				const uint32_t cellb = rec.w & 0xFFFFu, zslotb = rec.w >> 16;
+				const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
+				float2 h;
+				if (LS) {
+					const float2 u0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x & 0xFFFFu)), l0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x >> 16));
+					const float2 u1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y & 0xFFFFu)), l1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y >> 16));
+					const float2 u2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z & 0xFFFFu)), l2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z >> 16));
+					const float2 sum = cadd(cadd(csub(u0, l0), csub(u1, l1)), csub(u2, l2));
+					h = cscale(sum, pf.x * g);
+				} else {
+					h = cscale(*reinterpret_cast<const float2 *>(s_zfb + zslotb), g);  // ZF: H = Y / p
+				}
+				const float h2 = cnorm2(h);
+				accH += fast_sqrt(h2);
+				const float pv = pf.y;
+				const float2 yc = cmul_conj(yg, h);
+				float2 z, heq = h;
+				if (PHASE) {
+					// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
+					// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
+					const float inv = fast_rsqrt(h2), inv2 = fast_rcp(h2);
+					if (h.x == 0.f) {
+						heq = make_float2(0.f, 1.f);
+						z = make_float2(yg.y, -yg.x);
+					} else {
+						heq = cscale(h, inv);
+						z = cscale(yc, inv);
+					}
+					const float2 zn = cscale(yc, inv2);  // without amplitude restoration: SNR report only
+					accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
+				} else {
+					z = cscale(yc, fast_rcp(h2));
+				}
+				accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
+				// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the rows are dead
+				// (consumed by the window sums before the barrier), in ZF mode this thread is the slot's only user.
+				*reinterpret_cast<float2 *>(s_zfb + zslotb) = h;
+				if (dbg) {
+					const size_t o = frame * (size_t)G::CELLS + (cellb >> 3);
+					if (a.dbg_Y) a.dbg_Y[o] = yg;
+					if (a.dbg_H) a.dbg_H[o] = heq;
+					if (a.dbg_Z) a.dbg_Z[o] = z;
+				}
+			}
+			warp_partials3(accH, accV, accVn, s_part + 8);
+			if (tid == 0) bulk_wait_read();  // the previous frame's LLR store has finished reading s_L
+		}
+		__syncthreads();
+		float accH = 0.f, accV = 0.f, accVn = 0.f;
+#pragma unroll
+		for (int w = 0; w < NW; w++) {
+			accH += s_part[8 + w * 3 + 0];
+			accV += s_part[8 + w * 3 + 1];
+			accVn += s_part[8 + w * 3 + 2];
+		}
+		// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
+		const float variance = fmaxf(accV * inv_np, 1e-30f);
+		const float inv_var = fast_rcp(variance);
+
+		// ---------------- data cells in grid order: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------
+#pragma unroll 2
+		for (int d = tid; d < G::NDATA; d += T) {
+			uint32_t w0, dw[3] = {0u, 0u, 0u};
+			if (RECW == 2) {
+				const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + d);
+				w0 = r.x, dw[0] = r.y;
+			} else {
+				const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + d);
+				w0 = r.x, dw[0] = r.y, dw[1] = r.z, dw[2] = r.w;
+			}
+			const uint32_t cellb = w0 & 0x7FFFu, zs = (w0 >> 15) & 0x3FFFu;
+			const float t3 = (float)((int)(w0 >> 29) - 2) * (1.0f / 3.0f);
+			// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
+			const float2 ha = *reinterpret_cast<const float2 *>(s_zfb + zs), hb = *reinterpret_cast<const float2 *>(s_zfb + zs + 3 * MB_ZF_STRIDE * 8);
+			const float2 h = __ffma2_rn(csub(hb, ha), make_float2(t3, t3), ha);
+			const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
+			const float h2 = cnorm2(h);
+			const float2 yc = cmul_conj(yg, h);
 			float2 z, heq = h;
-			if (m.phase_only) {
-				// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
-				// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
-				const float inv = rsqrtf(h2), inv2 = 1.0f / h2;
+			if (PHASE) {
+				const float inv = fast_rsqrt(h2);
 				if (h.x == 0.f) {
 					heq = make_float2(0.f, 1.f);
 					z = make_float2(yg.y, -yg.x);
 				} else {
-					heq = make_float2(h.x * inv, h.y * inv);
-					z = make_float2(yc.x * inv, yc.y * inv);
+					heq = cscale(h, inv);
+					z = cscale(yc, inv);
 				}
-				const float2 zn = make_float2(yc.x * inv2, yc.y * inv2);  // without amplitude restoration: SNR report only
-				accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
 			} else {
-				const float inv2 = 1.0f / h2;
-				z = make_float2(yc.x * inv2, yc.y * inv2);
+				z = cscale(yc, fast_rcp(h2));
 			}
-			accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
-			if (kDebug) {
-				const size_t o = frame * (size_t)cells + cell;
+			if (dbg) {
+				const size_t o = frame * (size_t)G::CELLS + (cellb >> 3);
 				if (a.dbg_Y) a.dbg_Y[o] = yg;
 				if (a.dbg_H) a.dbg_H[o] = heq;
 				if (a.dbg_Z) a.dbg_Z[o] = z;
 			}
+			demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
 		}
-		warp_partials3(accH, accV, accVn, s_part2);
-	}
-	__syncthreads();
-	float accH = 0.f, accV = 0.f, accVn = 0.f;
-	for (int w = 0; w < nwarps; w++) {
-		accH += s_part2[w * 3 + 0];
-		accV += s_part2[w * 3 + 1];
-		accVn += s_part2[w * 3 + 2];
-	}
-	const float inv_np = 1.0f / (float)m.nPilots;
-	// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
-	const float variance = fmaxf(accV * inv_np, 1e-30f);
-	const float inv_var = 1.0f / variance;
-
-	// ---------------- data cells: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------------
-	for (int q = tid; q < m.nData; q += T) {
-		const unsigned info = g_sym_info[q];
-		const int cell = info & 0xFFF, r0 = (info >> 12) & 0x3F, j = info >> 21;
-		const float t3 = (float)((int)((info >> 18) & 7) - 2) * (1.0f / 3.0f);
-		// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
-		const float2 ha = s_zf[r0 * kZfStride + 4 + j], hb = s_zf[(r0 + 3) * kZfStride + 4 + j];
-		const float2 h = make_float2(fmaf(hb.x - ha.x, t3, ha.x), fmaf(hb.y - ha.y, t3, ha.y));
-		const float2 yg = cscale(s_Y[cell], g);
-		const float h2 = h.x * h.x + h.y * h.y;
-		const float2 yc = make_float2(yg.x * h.x + yg.y * h.y, yg.y * h.x - yg.x * h.y);
-		float2 z, heq = h;
-		if (m.phase_only) {
-			const float inv = rsqrtf(h2);
-			if (h.x == 0.f) {
-				heq = make_float2(0.f, 1.f);
-				z = make_float2(yg.y, -yg.x);
-			} else {
-				heq = make_float2(h.x * inv, h.y * inv);
-				z = make_float2(yc.x * inv, yc.y * inv);
+		if (m.nVirtual > 0) {  // virtual bits are copies of the first LLRs (telecom_system.cc:1303-1306)
+			__syncthreads();
+			const uint32_t *__restrict__ g_virt = reinterpret_cast<const uint32_t *>(a.blob + m.off_virt);
+			for (int i = tid; i < m.nVirtual; i += T) {
+				const uint32_t w = __ldg(g_virt + i);
+				*reinterpret_cast<float *>(s_Lb + (w >> 16)) = *reinterpret_cast<const float *>(s_Lb + (w & 0xFFFFu));
 			}
-		} else {
-			const float inv2 = 1.0f / h2;
-			z = make_float2(yc.x * inv2, yc.y * inv2);
 		}
-		if (kDebug) {
-			const size_t o = frame * (size_t)cells + cell;
-			if (a.dbg_Y) a.dbg_Y[o] = yg;
-			if (a.dbg_H) a.dbg_H[o] = heq;
-			if (a.dbg_Z) a.dbg_Z[o] = z;
-		}
-		switch (m.M) {
-		case 2: demap_scatter<2, 1>(z, inv_var, s_cons, q, g_dst, g_dst2, s_L); break;
-		case 4: demap_scatter<4, 2>(z, inv_var, s_cons, q * 2, g_dst, g_dst2, s_L); break;
-		case 8: demap_scatter<8, 3>(z, inv_var, s_cons, q * 3, g_dst, g_dst2, s_L); break;
-		case 16: demap_scatter<16, 4>(z, inv_var, s_cons, q * 4, g_dst, g_dst2, s_L); break;
-		default: demap_scatter<32, 5>(z, inv_var, s_cons, q * 5, g_dst, g_dst2, s_L); break;
-		}
-	}
-	__syncthreads();
+		fence_proxy_async();  // s_L was written through the generic proxy; the bulk store reads it through the async proxy
+		__syncthreads();
 
-	// ---------------- write LLRs (decoder order, coalesced) and the demod half of the stats record -----------
-	{
-		float4 *__restrict__ out = reinterpret_cast<float4 *>(a.llr + frame * (size_t)MB_N);
-		const float4 *src = reinterpret_cast<const float4 *>(s_L);
-		for (int i = tid; i < MB_N / 4; i += T) out[i] = src[i];
-		if (a.llr_cw) {
-			const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
-			float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
-			for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
-		}
+		// ---------------- LLRs out (one bulk store, decoder order) and the demod half of the stats record ----------------
 		if (tid == 0) {
+			bulk_s2g(a.llr + frame * (size_t)MB_N, smem_u32(s_L), MB_N * 4);
 			MbRxStats st;
 			st.iterations_done = -1;
 			st.crc = 0;
 			st.all_zeros = 0;
 			st.message_decoded = 0;
-			const float v_rep = m.phase_only ? accVn * inv_np : variance;
-			st.SNR = m.estimator == 1 ? 10.0f * log10f(1.0f / v_rep) : 0.0f;  // candidate; finalised by the decoder
+			const float v_rep = PHASE ? accVn * inv_np : variance;
+			st.SNR = LS ? 10.0f * log10f(1.0f / v_rep) : 0.0f;  // candidate; finalised by the decoder
 			st.variance = variance;
 			st.mean_H = accH * inv_np;
 			st.reserved = 0;
 			a.stats[frame] = st;
 		}
+		if (a.llr_cw) {
+			const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
+			float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
+			for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
+		}
 	}
+	if (tid == 0) bulk_wait_all();  // shared memory must outlive the last bulk store
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch plumbing: one instantiation per (Nsymb, M, estimator, phase-only) combination of the 17 modes
+// ------------------------------------------------------------------------------------------------------------------
+struct Variant {
+	int S, M, ls, phase;
+	const void *fn;
+	int threads, smem, ctas_per_sm;
+};
+
+#define MB_VARIANT(S, M, LS, PH) {S, M, LS, PH, (const void *)mb_demod_kernel<S, M, LS, PH>, Geo<S>::T, Geo<S>::SMEM, 0}
+Variant g_variants[] = {
+	MB_VARIANT(48, 2, true, true),    // CONFIG_0..6   BPSK
+	MB_VARIANT(24, 4, true, true),    // CONFIG_7..9,12 QPSK
+	MB_VARIANT(16, 8, true, true),    // CONFIG_10,11,14 8PSK
+	MB_VARIANT(12, 16, true, false),  // CONFIG_13     16QAM, LS
+	MB_VARIANT(12, 16, false, false), // CONFIG_15     16QAM, ZF
+	MB_VARIANT(9, 32, false, false),  // CONFIG_16     32QAM, ZF
+};
+int g_num_sms = 0;
+
+Variant *find_variant(const MbMode &m)
+{
+	for (Variant &v : g_variants)
+		if (v.S == m.Nsymb && v.M == m.M && v.ls == (m.estimator == 1) && v.phase == (m.phase_only != 0)) return &v;
+	return nullptr;
 }
 
 }  // namespace
 
-size_t mb_demod_smem_bytes(int Nsymb)
-{
-	const int T = mb_demod_threads(Nsymb), cells = Nsymb * MB_NC;
-	size_t fftbuf = (size_t)(T / 16) * 16 * 17 * sizeof(float2);
-	size_t reuse = ((size_t)((Nsymb * kZfStride + 1) & ~1) + (size_t)cells) * sizeof(float2) + MB_N * sizeof(float);
-	return kSmemHeadFloats * sizeof(float) + (size_t)cells * sizeof(float2) + (fftbuf > reuse ? fftbuf : reuse);
-}
-
 cudaError_t mb_demod_init()
 {
-	cudaError_t e = cudaFuncSetAttribute(mb_demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(mb_demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+	if (e != cudaSuccess) return e;
+	for (Variant &v : g_variants) {
+		e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(v.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess) return e;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.ctas_per_sm, v.fn, v.threads, (size_t)v.smem);
+		if (e != cudaSuccess) return e;
+		if (v.ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+	}
+	return cudaSuccess;
+}
+
+int mb_demod_ctas_per_sm(int Nsymb, int M, int estimator, int phase_only)
+{
+	MbMode m;
+	m.Nsymb = Nsymb, m.M = M, m.estimator = estimator, m.phase_only = phase_only;
+	const Variant *v = find_variant(m);
+	return v ? v->ctas_per_sm : 0;
 }
 
 cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream)
 {
 	if (n_frames == 0) return cudaSuccess;
-	const int T = mb_demod_threads(a.mode.Nsymb);
-	const size_t smem = mb_demod_smem_bytes(a.mode.Nsymb);
-	const bool dbg = a.dbg_Y || a.dbg_H || a.dbg_Z;
-	if (dbg)
-		mb_demod_kernel<true><<<(unsigned)n_frames, T, smem, stream>>>(a);
-	else
-		mb_demod_kernel<false><<<(unsigned)n_frames, T, smem, stream>>>(a);
-	return cudaGetLastError();
+	const Variant *v = find_variant(a.mode);
+	if (!v || g_num_sms <= 0) return cudaErrorInvalidDeviceFunction;
+	// bulk copies need 16-byte aligned global addresses; frames are multiples of 16 bytes, so only the bases matter
+	if ((reinterpret_cast<uintptr_t>(a.x) & 15u) || (reinterpret_cast<uintptr_t>(a.llr) & 15u)) return cudaErrorMisalignedAddress;
+	MbDemodArgs args = a;
+	args.n_frames = (unsigned long long)n_frames;
+	const size_t resident = (size_t)g_num_sms * (size_t)v->ctas_per_sm;
+	const unsigned grid = (unsigned)(n_frames < resident ? n_frames : resident);
+	void *params[] = {&args};
+	return cudaLaunchKernel(v->fn, dim3(grid), dim3((unsigned)v->threads), params, (size_t)v->smem, stream);
 }

@@ -21,6 +21,7 @@ struct MbDemodArgs {
 	const uint8_t *blob;   // device copy of the table blob
 	uint32_t off_twiddle;
 	uint32_t off_var_of_cw;
+	unsigned long long n_frames;  // filled by mb_launch_demod (the kernel is persistent: grid < frames)
 	MbMode mode;
 };
 
@@ -35,19 +36,10 @@ struct MbLdpcArgs {
 	int32_t check_gate;    // 1: honour the mean|H| < 0.3 gate recorded by the demod kernel
 };
 
-// Threads per CTA of the demod kernel for a frame of Nsymb symbols (16 threads per symbol, 160..192, warp multiple;
-// frames with more than 12 symbols are transformed in several rounds).
-static inline int mb_demod_threads(int Nsymb)
-{
-	int t = Nsymb * 16;
-	if (t > 192) t = 192;
-	if (t < 160) t = 160;  // the row pass of the LS estimator wants 3 x 50 threads
-	return (t + 31) / 32 * 32;
-}
-size_t mb_demod_smem_bytes(int Nsymb);
 size_t mb_ldpc_smem_bytes(int c_slots);
 
 cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream);
 cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream);
-cudaError_t mb_demod_init();  // opt-in shared memory attributes
+cudaError_t mb_demod_init();  // opt-in shared memory attributes, occupancy of every instantiation
+int mb_demod_ctas_per_sm(int Nsymb, int M, int estimator, int phase_only);  // resident CTAs per SM (0 = no such instantiation)
 cudaError_t mb_ldpc_init();

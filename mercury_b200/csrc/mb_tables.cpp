@@ -379,23 +379,75 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 		for (int i = 0; i < m.crc_bytes; i++) s = crc_zero_byte(s);
 		m.crc_init = s;
 	}
-	// pilot and data-cell descriptors with the lattice arithmetic resolved here instead of per frame on the device
-	std::vector<uint32_t> pilot_info(m.nPilots), sym_info(m.nData);
+	// ---- descriptors of the persistent demodulator kernel: lattice / window / interleaver arithmetic resolved here -------
+	// compact pilot rows: row s holds its pilots (columns s%3 + 3j) at [4 + j]; the rest of the 27-wide row is zero, so that
+	// every clipped 21-column window is exactly 7 consecutive entries starting at (c + 4 - s%3) / 3.
+	m.pinv_mag = std::fabs(pinv[pilot_cell[0]]);
+	std::vector<uint32_t> zf_src((size_t)S * MB_ZF_STRIDE, 0);
+	for (int s = 0; s < S; s++)
+		for (int j = 0; s % 3 + 3 * j < C; j++) {
+			const int cell = s * C + s % 3 + 3 * j;
+			if (!is_pilot[cell]) return "compact pilot row hits a data cell";
+			if (std::fabs(pinv[cell]) != m.pinv_mag) return "pilot magnitudes differ";
+			zf_src[(size_t)s * MB_ZF_STRIDE + 4 + j] = (uint32_t)(cell * 8) | (1u << 30) | (pinv[cell] < 0 ? 1u << 31 : 0u);
+		}
+	std::vector<uint32_t> pilot_rec(4 * (size_t)m.nPilots, 0);
+	std::vector<float> pilot_f(2 * (size_t)m.nPilots);
 	for (int p = 0; p < m.nPilots; p++) {
-		const int cell = pilot_cell[p], s = cell / C, c = cell % C;
-		pilot_info[p] = (uint32_t)cell | ((uint32_t)s << 12) | ((uint32_t)(c / 3) << 18);
+		const int cell = pilot_cell[p], s = cell / C, c = cell % C, j = c / 3;
+		if (c % 3 != s % 3) return "pilot off the lattice";
+		const int zslot = s * MB_ZF_STRIDE + 4 + j;
+		const int k0 = std::max(0, s - MB_LS_HALF), k1 = std::min(S - 1, s + MB_LS_HALF);
+		for (int r = 0; r < 3; r++) {
+			int first = k0 + ((r - k0) % 3 + 3) % 3, last = k1 - ((k1 - r) % 3 + 3) % 3;
+			if (first > last || first % 3 != r || last % 3 != r) return "LS window misses a row residue";
+			const int col = (c + 4 - r) / 3;  // first compact entry of the clipped 21-column window in a row of residue r
+			if (col < 0 || col >= MB_LS_COLS) return "LS window column out of range";
+			const uint32_t hi = (uint32_t)(last * MB_LS_COLS + col) * 8u;
+			const uint32_t lo = (uint32_t)((first >= 3 ? first - 3 : S) * MB_LS_COLS + (first >= 3 ? col : 0)) * 8u;
+			if (hi > 0xFFFFu || lo > 0xFFFFu) return "LS offsets exceed 16 bits";
+			pilot_rec[4 * (size_t)p + r] = hi | (lo << 16);
+		}
+		if (zslot * 8 > 0xFFFF) return "compact slot offset exceeds 16 bits";
+		pilot_rec[4 * (size_t)p + 3] = (uint32_t)(cell * 8) | ((uint32_t)(zslot * 8) << 16);
+		pilot_f[2 * (size_t)p] = invn[cell];
+		pilot_f[2 * (size_t)p + 1] = pval[cell];
 	}
-	for (int q = 0; q < m.nData; q++) {
-		const int cell = sym_cell[q], s = cell / C, c = cell % C;
-		const int f = c % 3, last = f + 3 * ((S - 1 - f) / 3);
-		const int r0 = s < f ? f : (s > last ? last - 3 : s - ((s - f) % 3));  // interpolator.cc:163-254
-		if (r0 < 0 || r0 + 3 > S - 1) return "interpolation rows out of range";
-		const int t = s - r0;
-		if (t < -2 || t > 5 || !is_pilot[r0 * C + c] || !is_pilot[(r0 + 3) * C + c]) return "interpolation descriptor out of range";
-		sym_info[q] = (uint32_t)cell | ((uint32_t)r0 << 12) | ((uint32_t)(t + 2) << 18) | ((uint32_t)(c / 3) << 21);
+	m.data_rec_words = m.bps <= 2 ? 2 : 4;
+	std::vector<uint32_t> data_rec((size_t)m.data_rec_words * m.nData, 0);
+	{
+		std::vector<int> q_of_cell(cells, -1);
+		for (int q = 0; q < m.nData; q++) q_of_cell[sym_cell[q]] = q;
+		for (int D = 0; D < m.nData; D++) {
+			const int cell = data_cell[D], s = cell / C, c = cell % C, q = q_of_cell[cell];
+			if (q < 0) return "data cell without a demapper slot";
+			const int f = c % 3, last = f + 3 * ((S - 1 - f) / 3);
+			const int r0 = s < f ? f : (s > last ? last - 3 : s - ((s - f) % 3));  // interpolator.cc:163-254
+			if (r0 < 0 || r0 + 3 > S - 1) return "interpolation rows out of range";
+			const int t = s - r0;
+			if (t < -2 || t > 5 || !is_pilot[r0 * C + c] || !is_pilot[(r0 + 3) * C + c]) return "interpolation descriptor out of range";
+			const uint32_t zs = (uint32_t)(r0 * MB_ZF_STRIDE + 4 + c / 3) * 8u;
+			if (cell * 8 >= (1 << 15) || zs >= (1u << 14)) return "data descriptor field overflow";
+			uint32_t *rec = &data_rec[(size_t)D * m.data_rec_words];
+			rec[0] = (uint32_t)(cell * 8) | (zs << 15) | ((uint32_t)(t + 2) << 29);
+			for (int e = 0; e < m.bps; e++) {
+				const uint32_t d = (uint32_t)dst[(size_t)q * m.bps + e] * 4u;
+				rec[1 + e / 2] |= d << (16 * (e & 1));
+			}
+		}
 	}
-	m.off_pilot_info = bl.put(pilot_info);
-	m.off_sym_info = bl.put(sym_info);
+	std::vector<uint16_t> virt;
+	for (int i = 0; i < m.nBits; i++)
+		if (dst2[i] != MB_NO_DST) {
+			virt.push_back((uint16_t)(dst[i] * 4));
+			virt.push_back((uint16_t)(dst2[i] * 4));
+		}
+	if ((int)virt.size() != 2 * m.nVirtual) return "virtual-bit copy list does not match nVirtual";
+	m.off_zf_src = bl.put(zf_src);
+	m.off_pilot_rec = bl.put(pilot_rec);
+	m.off_pilot_f = bl.put(pilot_f);
+	m.off_data_rec = bl.put(data_rec);
+	m.off_virt = bl.put(virt);
 	m.off_pinv = bl.put(pinv);
 	m.off_pval = bl.put(pval);
 	m.off_invn = bl.put(invn);
@@ -480,7 +532,9 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		    !in(m.off_pilot_cell, 2 * (size_t)m.nPilots) || !in(m.off_sym_cell, 2 * (size_t)m.nData) ||
 		    !in(m.off_llr_dst, 2 * (size_t)m.nBits) || !in(m.off_llr_dst2, 2 * (size_t)m.nBits) || !in(m.off_const, 8 * (size_t)m.M) ||
 		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16) ||
-		    !in(m.off_pilot_info, 4 * (size_t)m.nPilots) || !in(m.off_sym_info, 4 * (size_t)m.nData))
+		    !in(m.off_zf_src, 4 * (size_t)m.Nsymb * MB_ZF_STRIDE) || !in(m.off_pilot_rec, 16 * (size_t)m.nPilots) ||
+		    !in(m.off_pilot_f, 8 * (size_t)m.nPilots) || (m.data_rec_words != 2 && m.data_rec_words != 4) ||
+		    !in(m.off_data_rec, 4 * (size_t)m.data_rec_words * m.nData) || !in(m.off_virt, 4 * (size_t)m.nVirtual))
 			return "table blob: mode table out of range";
 	}
 	return "";

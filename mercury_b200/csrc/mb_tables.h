@@ -29,11 +29,13 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 7u
+#define MB_BLOB_VERSION 8u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
 #define MB_MAX_GROUPS 64  // warp-sized groups of checks / variables (<= 50 used)
+#define MB_ZF_STRIDE 27   // compact pilot row: 4 zeros | <= 17 pilots (columns s%3 + 3j at [4 + j]) | zeros
+#define MB_LS_COLS 18     // distinct clipped 21-column windows per row: start index (c + 4 - s%3) / 3 = 0..17
 
 struct MbRate {
 	int32_t rate_num, N, K, P, n_edges;
@@ -74,9 +76,20 @@ struct MbMode {
 	uint32_t off_bit_var;    // u16[8*crc_bytes] internal variable of info bit i
 	uint32_t off_scr;        // u8 [N]      scrambler bit i (bit_energy_dispersal sequence)
 	uint32_t off_crcmat;     // u16[32*16]  per-lane "advance CRC by the bytes that follow my chunk" matrices
-	uint32_t off_pilot_info; // u32[nPilots] cell | row << 12 | (col / 3) << 18   (no integer divisions in the kernel)
-	uint32_t off_sym_info;   // u32[nData]  cell | r0 << 12 | (t + 2) << 18 | (col / 3) << 21: channel = H[r0] + (H[r0+3] - H[r0]) * t / 3
-	                         //             (interpolator.cc:163-254 resolved on the host: r0 = bracketing / extrapolation pilot row)
+	// ---- descriptors of the persistent demodulator kernel (mb_demod.cu): all lattice / window / interleaver arithmetic is
+	// resolved here, offsets are BYTE offsets into the kernel's shared-memory arrays so that no scaling is left per frame.
+	uint32_t off_zf_src;     // u32[Nsymb*27] compact pilot-row slot -> (cell*8) | valid << 30 | (pilot negative) << 31
+	uint32_t off_pilot_rec;  // u32[4*nPilots] row-major pilots: {hi0 | lo0 << 16, hi1 | lo1 << 16, hi2 | lo2 << 16, cell*8 | zslot*8 << 16}
+	                         //   LS estimate = sum over row residues r of (PM[hi_r] - PM[lo_r]); PM = per-residue running sums over rows of
+	                         //   the clipped 21-column window sums, [Nsymb+1][18] float2 (row Nsymb is all zero = "no lower bound")
+	uint32_t off_pilot_f;    // f32[2*nPilots] {1 / (pilots inside the clipped 21x21 window), pilot value}
+	uint32_t off_data_rec;   // u32[data_rec_words*nData] data cells in GRID (deframer) order: word 0 = cell*8 | zslot(r0)*8 << 15 | (t+2) << 29
+	                         //   with channel = H[r0] + (H[r0+3] - H[r0]) * t / 3 (interpolator.cc:163-254 resolved on the host), then
+	                         //   one u16 per emitted LLR (MSB first): byte offset of its destination in the internal-order LLR vector
+	uint32_t off_virt;       // u16[2*nVirtual] (source byte offset, destination byte offset) of the virtual-bit copies (telecom_system.cc:1303-1306)
+	int32_t data_rec_words;  // 2 for bps <= 2, 4 above
+	float pinv_mag;          // |1/p| as float (pilot boost 1.33)
+	int32_t reserved2;
 };
 
 struct MbBlobHeader {

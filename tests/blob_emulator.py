@@ -4,6 +4,7 @@ CRC matrices) against the oracle on a machine without a GPU; it is test code, no
 import numpy as np
 
 MB_NC, MB_N, MAX_CDEG, MAX_VDEG = 50, 1600, 48, 16
+ZF_STRIDE, LS_COLS = 27, 18
 
 RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "max_cdeg", "max_vdeg", "c_slots", "v_slots", "reserved")] +
                    [(n, "<u4") for n in ("off_cdeg", "off_cgbase", "off_edge_var", "off_vdeg", "off_vgbase", "off_vedge",
@@ -13,7 +14,9 @@ MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate
                                          "preamble_nSymb", "crc_bytes", "crc_chunk")] +
                    [("crc_init", "<u4"), ("boost", "<f4")] +
                    [(n, "<u4") for n in ("off_pinv", "off_pval", "off_invn", "off_pilot_cell", "off_sym_cell", "off_llr_dst",
-                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat", "off_pilot_info", "off_sym_info")])
+                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat", "off_zf_src", "off_pilot_rec",
+                                         "off_pilot_f", "off_data_rec", "off_virt")] +
+                   [("data_rec_words", "<i4"), ("pinv_mag", "<f4"), ("reserved2", "<i4")])
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("reserved", "<u4"), ("off_twiddle", "<u4"),
                    ("pad", "<u4", (3,)), ("modes", MODE_DT, (17,)), ("rates", RATE_DT, (8,))])
 
@@ -31,7 +34,7 @@ class Blob:
     def mode(self, cfg):
         m = self.hdr["modes"][cfg]
         cells = int(m["Nsymb"]) * MB_NC
-        d = {k: (int(m[k]) if k != "boost" else float(m[k])) for k in MODE_DT.names if not k.startswith("off_")}
+        d = {k: (int(m[k]) if k not in ("boost", "pinv_mag") else float(m[k])) for k in MODE_DT.names if not k.startswith("off_")}
         d.update(pinv=self.arr(m["off_pinv"], "<f4", cells), pval=self.arr(m["off_pval"], "<f4", cells),
                  invn=self.arr(m["off_invn"], "<f4", cells), pilot_cell=self.arr(m["off_pilot_cell"], "<u2", m["nPilots"]),
                  sym_cell=self.arr(m["off_sym_cell"], "<u2", m["nData"]), llr_dst=self.arr(m["off_llr_dst"], "<u2", m["nBits"]),
@@ -39,7 +42,11 @@ class Blob:
                  cons=self.arr(m["off_const"], "<f4", 2 * m["M"]).view(np.complex64),
                  bit_var=self.arr(m["off_bit_var"], "<u2", 8 * m["crc_bytes"]), scr=self.arr(m["off_scr"], "u1", MB_N),
                  crcmat=self.arr(m["off_crcmat"], "<u2", 512).reshape(32, 16),
-                 pilot_info=self.arr(m["off_pilot_info"], "<u4", m["nPilots"]), sym_info=self.arr(m["off_sym_info"], "<u4", m["nData"]))
+                 zf_src=self.arr(m["off_zf_src"], "<u4", int(m["Nsymb"]) * ZF_STRIDE),
+                 pilot_rec=self.arr(m["off_pilot_rec"], "<u4", 4 * int(m["nPilots"])).reshape(-1, 4),
+                 pilot_f=self.arr(m["off_pilot_f"], "<f4", 2 * int(m["nPilots"])).reshape(-1, 2),
+                 data_rec=self.arr(m["off_data_rec"], "<u4", int(m["data_rec_words"]) * int(m["nData"])).reshape(int(m["nData"]), -1),
+                 virt=self.arr(m["off_virt"], "<u2", 2 * int(m["nVirtual"])).reshape(-1, 2))
         return d
 
     def rate(self, idx):
@@ -84,32 +91,50 @@ def demod(blob, cfg, x):
     Y = np.concatenate([bins[:, 231:256], bins[:, 1:26]], axis=1).reshape(-1)
     pc = m["pilot_cell"].astype(np.int64)
     g = f32(m["boost"]) / f32(np.abs(Y[pc]).astype(f32).sum(dtype=f32) / f32(m["nPilots"]))
-    H = np.zeros(S * MB_NC, c64)
+    # compact zero-padded pilot rows of Y/p, exactly as the kernel gathers them through zf_src
+    zs = m["zf_src"].astype(np.int64)
+    valid = ((zs >> 30) & 1).astype(bool)
+    pinv = np.where((zs >> 31) & 1, -f32(m["pinv_mag"]), f32(m["pinv_mag"])).astype(f32)
+    assert np.array_equal(np.sort((zs[valid] & 0x7FFF) // 8), np.sort(pc)) and valid.sum() == m["nPilots"]
+    assert np.array_equal(pinv[valid], m["pinv"][(zs[valid] & 0x7FFF) // 8])
+    zf = np.where(valid, Y[(zs & 0x7FFF) // 8] * pinv, 0).astype(c64)
+    prec, pf = m["pilot_rec"].astype(np.int64), m["pilot_f"]
+    cellb, zslotb = prec[:, 3] & 0xFFFF, prec[:, 3] >> 16
+    assert np.array_equal(cellb // 8, pc) and not (cellb % 8).any() and not (zslotb % 8).any()
+    assert np.array_equal(pf[:, 0], m["invn"][pc]) and np.array_equal(pf[:, 1], m["pval"][pc])
+    hpil = np.zeros(m["nPilots"], c64)
     if m["estimator"] == 1:
-        zf = (Y * m["pinv"]).astype(c64).reshape(S, MB_NC)
-        T = np.zeros((S, MB_NC), c64)
-        for c in range(MB_NC):
-            lo, hi = max(0, c - 10), min(MB_NC - 1, c + 10)
-            T[:, c] = zf[:, lo:hi + 1].sum(axis=1) * g
-        for cell in pc:
-            s, c = divmod(int(cell), MB_NC)
-            k0, k1 = max(0, s - 10), min(S - 1, s + 10)
-            H[cell] = T[k0:k1 + 1, c].sum() * m["invn"][cell]
+        # window sums (7 consecutive compact entries, 18 windows per row) -> running sums over the rows of each residue
+        pm = np.zeros(((S + 1) * LS_COLS,), c64)
+        for res in range(3):
+            run = np.zeros(LS_COLS, c64)
+            for k in range(res, S, 3):
+                row = zf[k * ZF_STRIDE:(k + 1) * ZF_STRIDE]
+                run = (run + np.array([row[jj:jj + 7].sum() for jj in range(LS_COLS)], c64)).astype(c64)
+                pm[k * LS_COLS:(k + 1) * LS_COLS] = run
+        acc = np.zeros(m["nPilots"], c64)
+        for res in range(3):
+            hi, lo = prec[:, res] & 0xFFFF, prec[:, res] >> 16
+            assert not (hi % 8).any() and not (lo % 8).any() and hi.max() // 8 < S * LS_COLS and lo.max() // 8 <= S * LS_COLS
+            acc = (acc + (pm[hi // 8] - pm[lo // 8])).astype(c64)
+        hpil = (acc * (pf[:, 0] * g)).astype(c64)
     else:
-        H[pc] = (Y[pc] * g) * m["pinv"][pc]
-    Hg = H.reshape(S, MB_NC).copy()
+        hpil = (zf[zslotb // 8] * g).astype(c64)
+    hc = zf.copy()  # the kernel stores the channel at pilots back into the compact rows
+    hc[zslotb // 8] = hpil
+    H = np.zeros(S * MB_NC, c64)
+    H[pc] = hpil
     is_p = np.zeros(S * MB_NC, bool)
     is_p[pc] = True
-    for info in m["sym_info"]:  # the kernel's descriptor: cell | r0 << 12 | (t + 2) << 18
-        cell, r0, t = int(info) & 0xFFF, (int(info) >> 12) & 0x3F, ((int(info) >> 18) & 7) - 2
-        s, c = divmod(cell, MB_NC)
-        assert t == s - r0 and not is_p[cell] and (int(info) >> 21) == c // 3
-        a, b = Hg[r0, c], Hg[r0 + 3, c]
+    drec = m["data_rec"].astype(np.int64)
+    dcell, dzs, dt = (drec[:, 0] & 0x7FFF) // 8, ((drec[:, 0] >> 15) & 0x3FFF) // 8, (drec[:, 0] >> 29) - 2
+    assert np.array_equal(dcell, np.flatnonzero(~is_p))  # grid (deframer) order
+    for cell, z0, t in zip(dcell, dzs, dt):
+        s, c = divmod(int(cell), MB_NC)
+        r0 = (int(z0) - 4 - c // 3) // ZF_STRIDE
+        assert int(z0) == r0 * ZF_STRIDE + 4 + c // 3 and t == s - r0 and is_p[r0 * MB_NC + c] and is_p[(r0 + 3) * MB_NC + c]
+        a, b = hc[z0], hc[z0 + 3 * ZF_STRIDE]
         H[cell] = a + (b - a) * f32(t) / f32(3)
-    assert sorted(int(i) & 0xFFF for i in m["sym_info"]) == sorted(np.flatnonzero(~is_p).tolist())
-    for p, info in enumerate(m["pilot_info"]):
-        cell = int(info) & 0xFFF
-        assert cell == pc[p] and (int(info) >> 12) & 0x3F == cell // MB_NC and (int(info) >> 18) == (cell % MB_NC) // 3
     mean_H = f32(np.abs(H[pc]).mean())
     Hraw = H.copy()
     if m["phase_only"]:
@@ -118,18 +143,30 @@ def demod(blob, cfg, x):
     Z = (Yg / H).astype(c64)
     variance = f32(max((np.abs(Z[pc] - m["pval"][pc]) ** 2).mean(), 1e-30))
     v_rep = f32((np.abs(Yg[pc] / Hraw[pc] - m["pval"][pc]) ** 2).mean()) if m["phase_only"] else variance
-    w = Z[m["sym_cell"].astype(np.int64)]
+    w = Z[dcell]
     D = (np.abs(w[:, None] - m["cons"][None, :]) ** 2).astype(f32)  # [nData, M]
     bps = m["bps"]
-    L = np.zeros(MB_N, f32)
-    lam = np.zeros(m["nBits"], f32)
+    L = np.full(MB_N, np.nan, f32)
     idx = np.arange(m["M"])
-    for k in range(bps):
+    for e in range(bps):  # emitted MSB first: bit mask 1 << (bps-1-e)
+        k = bps - 1 - e
         one = ((idx >> k) & 1) == 1
-        lam[np.arange(m["nData"]) * bps + (bps - 1 - k)] = (f32(1) / variance) * (D[:, one].min(axis=1) - D[:, ~one].min(axis=1))
-    L[m["llr_dst"].astype(np.int64)] = lam
-    has2 = m["llr_dst2"] != 0xFFFF
-    L[m["llr_dst2"][has2].astype(np.int64)] = lam[has2]
+        off = (drec[:, 1 + e // 2] >> (16 * (e & 1))) & 0xFFFF
+        assert not (off % 4).any()
+        L[off // 4] = (f32(1) / variance) * (D[:, one].min(axis=1) - D[:, ~one].min(axis=1))
+    for src, dst in m["virt"].astype(np.int64):
+        assert np.isnan(L[dst // 4]) and not np.isnan(L[src // 4])
+        L[dst // 4] = L[src // 4]
+    assert not np.isnan(L).any()  # every position of the internal-order vector is written exactly once
+    # the grid-order records must describe the same scatter as the reference-order tables (used by the TX synthesiser)
+    lam = np.zeros(m["nBits"], f32)
+    q_of_cell = {int(cc): q for q, cc in enumerate(m["sym_cell"])}
+    for D_i, cell in enumerate(dcell):
+        q = q_of_cell[int(cell)]
+        for e in range(bps):
+            off = (int(drec[D_i, 1 + e // 2]) >> (16 * (e & 1))) & 0xFFFF
+            assert off // 4 == int(m["llr_dst"][q * bps + e])
+            lam[q * bps + e] = L[off // 4]
     snr = float(10 * np.log10(1.0 / v_rep)) if m["estimator"] == 1 else 0.0
     return dict(Y=Yg.reshape(S, MB_NC), H=H.reshape(S, MB_NC), Z=Z.reshape(S, MB_NC), llr_demod=lam, llr_internal=L,
                 llr_cw=L[r["var_of_cw"].astype(np.int64)], variance=variance, mean_H=mean_H, snr=snr)
