@@ -15,21 +15,22 @@
 //   LLR expand telecom_system.cc:1300-1308
 //
 // How (B200-first, not the reference's loops):
-//   * HBM-bound stage, so the memory system is driven by the copy engine, not by the math warps: each CTA is persistent
-//     (grid = SMs x resident CTAs), walks its frames round-robin, and one thread keeps a two-slot shared-memory ring
-//     filled with cp.async.bulk copies (2 KB per OFDM symbol, guard interval never fetched) that complete on mbarriers.
-//     The next frame streams in while the current one is being estimated / equalised / de-mapped.  The 6.4 KB LLR vector
-//     leaves through one bulk store.  Every sample is read from HBM exactly once.
-//   * FFT-256 = 16 x 16: 16 threads per OFDM symbol, two radix-4x4 16-point DFTs in registers around an in-place,
-//     XOR-swizzled (conflict-free) transpose inside the ring slot that needs only __syncwarp (a symbol lives in half a
-//     warp).  All complex arithmetic uses the sm_100 packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one instruction per complex
-//     add, two per complex multiply, +-i rotations folded into operand swizzles).  The second DFT is pruned to the 4 of
-//     16 outputs that land on the 50 active carriers.
+//   * HBM-bound stage: one CTA per frame, every sample is read exactly once with 8-byte streaming loads (16 independent
+//     loads in flight per thread, guard interval never fetched); the only other HBM traffic is the 6.4 KB LLR vector,
+//     which leaves through one bulk (TMA engine) store from shared memory.
+//   * FFT-256 = 16 x 16: 16 threads per OFDM symbol, two radix-4x4 16-point DFTs in registers around a padded (stride 17,
+//     conflict-free) shared-memory transpose that needs only __syncwarp (a symbol lives in half a warp).  All complex
+//     arithmetic uses the sm_100 packed fp32 instructions (FADD2 / FMUL2 / FFMA2: one instruction per complex add, two per
+//     complex multiply, +-i rotations folded into operand swizzles); they issue at half the scalar rate, so this halves
+//     issue slots, not pipe time (profiles/r1e_f32x2_issue_rates.txt).  The second DFT is pruned to the 4 of 16 outputs
+//     that land on the 50 active carriers.
 //   * The LS estimator's O(pilots x window) double loop is restated as the clipped 21x21 box mean it is:
 //     compact pilot rows -> 7-entry window sums (18 distinct windows per row) -> running sums over the rows of each
 //     lattice residue -> every pilot reads 3 x (upper - lower) entries through host-resolved byte offsets.
 //   * deframe, both de-interleavers and the LLR expand are composed on the host into per-cell records (mb_tables.cpp), so
 //     no intermediate vector is ever materialised; the kernel is instantiated per (Nsymb, M, estimator, phase-only).
+//   (A persistent variant fed by a cp.async.bulk ring was measured first: 74 KB of shared memory per CTA left 2 CTAs per
+//    SM and 29 % of the HBM roofline, profiles/r1e_ncu_full_demod_tma_persistent.txt; occupancy wins on this kernel.)
 #include "mb_kernels.cuh"
 
 namespace {
@@ -132,46 +133,15 @@ __device__ __forceinline__ void fft16_pruned(const float2 (&x)[16], float2 &X0, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// mbarrier / bulk-copy primitives (PTX; SASS: SYNCS / UBLKCP)
+// bulk (TMA engine) store of the LLR vector: shared -> global (SASS: UBLKCP)
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-	uint32_t ok;
-	asm volatile(
-		"{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		: "=r"(ok)
-		: "r"(bar), "r"(parity)
-		: "memory");
-	return ok != 0;
-}
-// Bounded wait: a byte-count mismatch must surface as a launch failure, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-	for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
-		if (spin > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-		     "r"(bar)
-		     : "memory");
-}
 __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src, uint32_t bytes)
 {
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Warp-level sum of three values; lane 0 of every warp parks its partial sums in s_part[warp*3 .. +2].  The CTA-wide
@@ -233,34 +203,34 @@ __device__ __forceinline__ void demap_scatter(const float2 z, const float inv_va
 // ------------------------------------------------------------------------------------------------------------------
 template <int S>
 struct Geo {
-	static constexpr int SC = S == 48 ? 12 : (S == 24 ? 12 : (S == 16 ? 8 : S));  // symbols per ring slot
-	static constexpr int NCH = S / SC;                                                // slots (chunks) per frame
+	static constexpr int SC = S == 48 ? 12 : (S == 24 ? 12 : (S == 16 ? 8 : S));  // symbols transformed per round
+	static constexpr int NCH = S / SC;                                                // rounds per frame
 	static constexpr int T = (SC * 16 + 31) / 32 * 32;                                // threads per CTA
 	static constexpr int NW = T / 32;
-	static constexpr int MINB = S == 48 ? 2 : (S == 24 || S == 12 ? 3 : 4);                // resident CTAs per SM the layout below allows
-	static constexpr int MAXREG = (65536 / (MINB * T)) / 8 * 8 > 128 ? 128 : (65536 / (MINB * T)) / 8 * 8;
+	static constexpr int MINB = T <= 128 ? 6 : 5;      // resident CTAs per SM the register file is budgeted for (64 / 80 registers)
 	static constexpr int CELLS = S * MB_NC;
 	static constexpr int NPIL = (S * MB_NC + 2) / 3;   // pilots: cells with s%3 == c%3
 	static constexpr int NDATA = CELLS - NPIL;
 	static constexpr int ZF = S * MB_ZF_STRIDE;
 	static constexpr int PM = (S + 1) * MB_LS_COLS;
-	// shared memory layout (bytes)
-	static constexpr int OFF_BAR = 0;                        // 2 x u64 mbarriers
-	static constexpr int OFF_PART = 16;                      // 64 floats of per-warp partial sums
+	// shared memory layout (bytes); the FFT transpose scratch is dead before the estimator's arrays are first written
+	static constexpr int OFF_PART = 0;                       // 64 floats of per-warp partial sums
 	static constexpr int OFF_CONS = OFF_PART + 256;          // 32 float2 constellation
-	static constexpr int OFF_Y = OFF_CONS + 256;             // [S][50] float2 carriers
-	static constexpr int OFF_ZF = OFF_Y + CELLS * 8;         // [S][27] float2 compact pilot rows, later the channel at pilots
-	static constexpr int OFF_PM = OFF_ZF + ((ZF * 8 + 15) & ~15);  // [S+1][18] float2 window sums / running sums
-	static constexpr int OFF_L = OFF_PM + PM * 8;            // [1600] float LLRs, decoder order
-	static constexpr int OFF_RING = (OFF_L + MB_N * 4 + 127) & ~127;
-	static constexpr int SLOT_BYTES = SC * MB_NFFT * 8;
-	static constexpr int SMEM = OFF_RING + 2 * SLOT_BYTES;
-	static_assert(S % SC == 0, "chunks must tile the frame");
+	static constexpr int OFF_TW = OFF_CONS + 256;            // 256 float2 twiddles of the 16 x 16 split
+	static constexpr int OFF_Y = OFF_TW + 2048;              // [S][50] float2 carriers
+	static constexpr int OFF_SCR = OFF_Y + CELLS * 8;        // [SC][16][17] float2 transpose scratch, aliased with:
+	static constexpr int OFF_ZF = OFF_SCR;                   //   [S][27] float2 compact pilot rows, later the channel at pilots
+	static constexpr int OFF_PM = OFF_ZF + ((ZF * 8 + 15) & ~15);  //   [S+1][18] float2 window sums / running sums
+	static constexpr int OFF_L = OFF_PM + PM * 8;            //   [1600] float LLRs, decoder order
+	static constexpr int SCR_BYTES = SC * 16 * 17 * 8;
+	static constexpr int EST_BYTES = OFF_L + MB_N * 4 - OFF_SCR;
+	static constexpr int SMEM = OFF_SCR + (SCR_BYTES > EST_BYTES ? SCR_BYTES : EST_BYTES);
+	static_assert(S % SC == 0, "rounds must tile the frame");
 	static_assert(OFF_L % 16 == 0 && OFF_Y % 16 == 0 && OFF_ZF % 16 == 0 && OFF_PM % 16 == 0, "alignment");
 };
 
 template <int S, int M, bool LS, bool PHASE>
-__global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
+__global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const MbDemodArgs a)
 {
 	using G = Geo<S>;
 	constexpr int T = G::T, NW = G::NW, SC = G::SC, NCH = G::NCH;
@@ -271,6 +241,7 @@ __global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
 	const int tid = threadIdx.x;
 	float *s_part = reinterpret_cast<float *>(smem + G::OFF_PART);
 	float2 *s_cons = reinterpret_cast<float2 *>(smem + G::OFF_CONS);
+	float2 *s_tw = reinterpret_cast<float2 *>(smem + G::OFF_TW);
 	float2 *s_Y = reinterpret_cast<float2 *>(smem + G::OFF_Y);
 	unsigned char *s_Yb = smem + G::OFF_Y;
 	float2 *s_zf = reinterpret_cast<float2 *>(smem + G::OFF_ZF);
@@ -279,98 +250,50 @@ __global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
 	unsigned char *s_pmb = smem + G::OFF_PM;
 	unsigned char *s_Lb = smem + G::OFF_L;
 	float *s_L = reinterpret_cast<float *>(s_Lb);
-	float2 *s_ring = reinterpret_cast<float2 *>(smem + G::OFF_RING);
-	const uint32_t bar0 = smem_u32(smem + G::OFF_BAR);
 
+	const size_t frame = blockIdx.x;
 	const uint32_t *__restrict__ g_zf_src = reinterpret_cast<const uint32_t *>(a.blob + m.off_zf_src);
 	const uint4 *__restrict__ g_prec = reinterpret_cast<const uint4 *>(a.blob + m.off_pilot_rec);
 	const float2 *__restrict__ g_pf = reinterpret_cast<const float2 *>(a.blob + m.off_pilot_f);
 	const uint32_t *__restrict__ g_drec = reinterpret_cast<const uint32_t *>(a.blob + m.off_data_rec);
-
-	// frames of this CTA: blockIdx.x, + gridDim.x, ...; ring chunk q = frame slot q / NCH, symbols (q % NCH) * SC ..
-	const long long n_mine = ((long long)a.n_frames - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
-	const long long n_chunks = n_mine * NCH;
-	auto issue_chunk = [&](long long q) {  // one thread: arm the slot's mbarrier, then one 2 KB bulk copy per symbol (GI skipped)
-		const uint32_t slot = (uint32_t)(q & 1);
-		const uint32_t bar = bar0 + 8u * slot;
-		const size_t frame = (size_t)blockIdx.x + (size_t)(q / NCH) * gridDim.x;
-		const float2 *src = a.x + (frame * S + (size_t)(q % NCH) * SC) * MB_NOFDM + MB_NGI;
-		const uint32_t dst = smem_u32(s_ring) + slot * (uint32_t)G::SLOT_BYTES;
-		mbar_expect_tx(bar, (uint32_t)G::SLOT_BYTES);
-#pragma unroll 1
-		for (int s = 0; s < SC; s++) bulk_g2s(dst + (uint32_t)s * (MB_NFFT * 8), src + (size_t)s * MB_NOFDM, MB_NFFT * 8, bar);
-	};
-
-	if (tid == 0) {
-		mbar_init(bar0, 1);
-		mbar_init(bar0 + 8, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		fence_proxy_async();
-	}
-	if (tid < M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];
-	if (LS)
-		for (int i = tid; i < MB_LS_COLS; i += T) s_pm[S * MB_LS_COLS + i] = make_float2(0.f, 0.f);  // the "no lower bound" row
-	__syncthreads();
-	if (tid == 0) {
-		if (n_chunks > 0) issue_chunk(0);
-		if (n_chunks > 1) issue_chunk(1);
-	}
-
-	// frame-invariant per-thread constants
-	const int grp = tid >> 4, t = tid & 15;
-	float2 tw[16];
-	{
-		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);
-#pragma unroll
-		for (int k1 = 1; k1 < 16; k1++) tw[k1] = __ldg(g_tw + k1 * 16 + t);  // W256^(t k1)/256
-		tw[0] = make_float2(1.0f / 256.0f, 0.f);
-	}
-	uint32_t xhi[4], xlo[4];
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		xhi[i] = (uint32_t)(i * 32) ^ (uint32_t)((t * 8) & 96);
-		xlo[i] = (uint32_t)(i * 8) ^ (uint32_t)((t * 8) & 24);
-	}
-	constexpr int ZF_PER = (G::ZF + T - 1) / T;
-	uint32_t zsrc[ZF_PER];
-#pragma unroll
-	for (int i = 0; i < ZF_PER; i++) zsrc[i] = (tid + i * T < G::ZF) ? __ldg(g_zf_src + tid + i * T) : 0u;
-	const uint32_t pinv_bits = __float_as_uint(m.pinv_mag);
-	const float inv_np = 1.0f / (float)G::NPIL;
 	const bool dbg = a.dbg_Y || a.dbg_H || a.dbg_Z;
 
-	long long q = 0;
-	for (long long fi = 0; fi < n_mine; fi++) {
-		const size_t frame = (size_t)blockIdx.x + (size_t)fi * gridDim.x;
-		// ---------------- FFT-256 per symbol (a2, a3), one ring slot (SC symbols) at a time ------------------------------
+	if (tid < M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];  // published by the barrier after the FFT
+	{
+		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);  // tw[k1*16 + n2] = W256^(n2 k1)/256
+		for (int i = tid; i < 256; i += T) s_tw[i] = __ldg(g_tw + i);
+	}
+
+	// ---------------- FFT-256 per symbol (a2, a3), SC symbols per round ---------------------------------------------------
+	{
+		const int grp = tid >> 4, t = tid & 15;
+		const bool active = grp < SC;  // Nsymb = 9: the last half warp has no symbol, but still takes part in the warp syncs
+		// Transpose scratch of one symbol: 16 rows of 17 float2 (the pad makes both the row writes and the column reads
+		// conflict free, and every access is base + immediate).  Twiddles sit in shared memory for the same reason: one base
+		// register instead of 30 loop-invariant values that would not survive the 64-register budget.
+		float2 *buf = reinterpret_cast<float2 *>(smem + G::OFF_SCR) + (active ? grp : 0) * (16 * 17);
+		const float2 *tw = s_tw + t;  // tw[k1 * 16] = W256^(t k1) / 256
+		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * MB_NOFDM + MB_NGI + t;
 #pragma unroll 1
-		for (int ch = 0; ch < NCH; ch++, q++) {
-			const uint32_t slot = (uint32_t)(q & 1);
-			mbar_wait(bar0 + 8u * slot, (uint32_t)((q >> 1) & 1));
-			const bool active = grp < SC;  // Nsymb = 9: the last half warp has no symbol, but still takes part in the warp syncs
-			unsigned char *symb = reinterpret_cast<unsigned char *>(s_ring) + slot * (uint32_t)G::SLOT_BYTES + (active ? grp : 0) * (MB_NFFT * 8);
+		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * MB_NOFDM) {
 			float2 v[16];
 			if (active) {
 #pragma unroll
-				for (int n1 = 0; n1 < 16; n1++) v[n1] = *reinterpret_cast<const float2 *>(symb + t * 8 + n1 * 128);  // x[16 n1 + t]
+				for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldcs(xs + 16 * n1);  // x[16 n1 + t], GI skipped
 			}
-			__syncwarp();
-			// In-place transpose: element (row r, column c) lives at byte r*128 + ((c ^ r) * 8).  (c ^ r) * 8 splits into two
-			// disjoint 2-bit fields, so every address is base[c >> 2] + xlo[c & 3]: one add per access, eight registers.
+			if (ch == 0) __syncthreads();  // twiddle table published (the loads above are already in flight)
 			if (active) {
 				float2 A[16];
 				fft16(v, A);
-				unsigned char *wb[4] = {symb + t * 128 + xhi[0], symb + t * 128 + xhi[1], symb + t * 128 + xhi[2], symb + t * 128 + xhi[3]};
-				*reinterpret_cast<float2 *>(wb[0] + xlo[0]) = cscale(A[0], 1.0f / 256.0f);
+				buf[t * 17] = cscale(A[0], 1.0f / 256.0f);
 #pragma unroll
-				for (int k1 = 1; k1 < 16; k1++) *reinterpret_cast<float2 *>(wb[k1 >> 2] + xlo[k1 & 3]) = cmul(A[k1], tw[k1]);
+				for (int k1 = 1; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], tw[k1 * 16]);
 			}
 			__syncwarp();
 			if (active) {
 				float2 X0, X1, X14, X15;
-				const unsigned char *rb[4] = {symb + xhi[0], symb + xhi[1], symb + xhi[2], symb + xhi[3]};
 #pragma unroll
-				for (int n2 = 0; n2 < 16; n2++) v[n2] = *reinterpret_cast<const float2 *>(rb[n2 >> 2] + xlo[n2 & 3] + n2 * 128);
+				for (int n2 = 0; n2 < 16; n2++) v[n2] = buf[n2 * 17 + t];
 				fft16_pruned(v, X0, X1, X14, X15);  // bins t, 16+t, 224+t, 240+t
 				float2 *row = s_Y + (ch * SC + grp) * MB_NC;
 				// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49
@@ -379,143 +302,84 @@ __global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
 				if (t >= 7) row[t - 7] = X14;
 				row[9 + t] = X15;
 			}
-			fence_proxy_async();  // this thread's generic-proxy accesses to the slot precede the next bulk copy into it
-			__syncthreads();
-			if (tid == 0 && q + 2 < n_chunks) issue_chunk(q + 2);
+			__syncwarp();
 		}
+	}
+	__syncthreads();
 
-		// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
-		{
-			float acc = 0.f;
-#pragma unroll
-			for (int i = 0; i < ZF_PER; i++) {
-				const int idx = tid + i * T;
-				if (idx < G::ZF) {
-					const uint32_t w = zsrc[i];
-					const float2 y = *reinterpret_cast<const float2 *>(s_Yb + (w & 0x7FFFu));
-					const bool valid = (w >> 30) & 1u;
-					const float pinv = __uint_as_float(pinv_bits | (w & 0x80000000u));
-					acc += valid ? fast_sqrt(cnorm2(y)) : 0.f;
-					s_zf[idx] = valid ? cscale(y, pinv) : make_float2(0.f, 0.f);  // ZF estimate Y/p (AGC gain applied later: all linear)
-				}
-			}
-			warp_partial1(acc, s_part);
-		}
-		__syncthreads();
-		float g;
-		{
-			float acc = 0.f;
-#pragma unroll
-			for (int w = 0; w < NW; w++) acc += s_part[w];
-			g = m.boost * fast_rcp(acc * inv_np);  // automatic_gain_control, ofdm.cc:1467-1498
-		}
-		// ---------------- LS estimate (a5): window sums + running sums over the rows of each lattice residue --------------
-		if (LS) {
-			if (tid < 3 * MB_LS_COLS) {
-				const int r = tid / MB_LS_COLS, jj = tid - r * MB_LS_COLS;
-				float2 run = make_float2(0.f, 0.f);
-#pragma unroll
-				for (int k3 = 0; k3 < (S + 2) / 3; k3++) {
-					const int k = r + 3 * k3;
-					if (k < S) {
-						const float2 *row = s_zf + k * MB_ZF_STRIDE + jj;
-						const float2 s01 = cadd(row[0], row[1]), s23 = cadd(row[2], row[3]), s45 = cadd(row[4], row[5]);
-						run = cadd(run, cadd(cadd(s01, s23), cadd(s45, row[6])));
-						s_pm[k * MB_LS_COLS + jj] = run;
-					}
-				}
-			}
-			__syncthreads();
-		}
-
-		// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) ------------------------------------
-		{
-			float accH = 0.f, accV = 0.f, accVn = 0.f;
-#pragma unroll 1
-			for (int p = tid; p < G::NPIL; p += T) {
-				const uint4 rec = __ldg(g_prec + p);
-				const float2 pf = __ldg(g_pf + p);
-				const uint32_t cellb = rec.w & 0xFFFFu, zslotb = rec.w >> 16;
-				const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
-				float2 h;
-				if (LS) {
-					const float2 u0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x & 0xFFFFu)), l0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x >> 16));
-					const float2 u1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y & 0xFFFFu)), l1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y >> 16));
-					const float2 u2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z & 0xFFFFu)), l2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z >> 16));
-					const float2 sum = cadd(cadd(csub(u0, l0), csub(u1, l1)), csub(u2, l2));
-					h = cscale(sum, pf.x * g);
-				} else {
-					h = cscale(*reinterpret_cast<const float2 *>(s_zfb + zslotb), g);  // ZF: H = Y / p
-				}
-				const float h2 = cnorm2(h);
-				accH += fast_sqrt(h2);
-				const float pv = pf.y;
-				const float2 yc = cmul_conj(yg, h);
-				float2 z, heq = h;
-				if (PHASE) {
-					// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
-					// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
-					const float inv = fast_rsqrt(h2), inv2 = fast_rcp(h2);
-					if (h.x == 0.f) {
-						heq = make_float2(0.f, 1.f);
-						z = make_float2(yg.y, -yg.x);
-					} else {
-						heq = cscale(h, inv);
-						z = cscale(yc, inv);
-					}
-					const float2 zn = cscale(yc, inv2);  // without amplitude restoration: SNR report only
-					accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
-				} else {
-					z = cscale(yc, fast_rcp(h2));
-				}
-				accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
-				// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the rows are dead
-				// (consumed by the window sums before the barrier), in ZF mode this thread is the slot's only user.
-				*reinterpret_cast<float2 *>(s_zfb + zslotb) = h;
-				if (dbg) {
-					const size_t o = frame * (size_t)G::CELLS + (cellb >> 3);
-					if (a.dbg_Y) a.dbg_Y[o] = yg;
-					if (a.dbg_H) a.dbg_H[o] = heq;
-					if (a.dbg_Z) a.dbg_Z[o] = z;
-				}
-			}
-			warp_partials3(accH, accV, accVn, s_part + 8);
-			if (tid == 0) bulk_wait_read();  // the previous frame's LLR store has finished reading s_L
-		}
-		__syncthreads();
-		float accH = 0.f, accV = 0.f, accVn = 0.f;
-#pragma unroll
-		for (int w = 0; w < NW; w++) {
-			accH += s_part[8 + w * 3 + 0];
-			accV += s_part[8 + w * 3 + 1];
-			accVn += s_part[8 + w * 3 + 2];
-		}
-		// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
-		const float variance = fmaxf(accV * inv_np, 1e-30f);
-		const float inv_var = fast_rcp(variance);
-
-		// ---------------- data cells in grid order: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------
+	// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
+	const uint32_t pinv_bits = __float_as_uint(m.pinv_mag);
+	const float inv_np = 1.0f / (float)G::NPIL;
+	{
+		float acc = 0.f;
 #pragma unroll 2
-		for (int d = tid; d < G::NDATA; d += T) {
-			uint32_t w0, dw[3] = {0u, 0u, 0u};
-			if (RECW == 2) {
-				const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + d);
-				w0 = r.x, dw[0] = r.y;
-			} else {
-				const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + d);
-				w0 = r.x, dw[0] = r.y, dw[1] = r.z, dw[2] = r.w;
+		for (int idx = tid; idx < G::ZF; idx += T) {
+			const uint32_t w = __ldg(g_zf_src + idx);
+			const float2 y = *reinterpret_cast<const float2 *>(s_Yb + (w & 0x7FFFu));
+			const bool valid = (w >> 30) & 1u;
+			const float pinv = __uint_as_float(pinv_bits | (w & 0x80000000u));
+			acc += valid ? fast_sqrt(cnorm2(y)) : 0.f;
+			s_zf[idx] = valid ? cscale(y, pinv) : make_float2(0.f, 0.f);  // ZF estimate Y/p (AGC gain applied later: all linear)
+		}
+		warp_partial1(acc, s_part);
+		if (LS)
+			for (int i = tid; i < MB_LS_COLS; i += T) s_pm[S * MB_LS_COLS + i] = make_float2(0.f, 0.f);  // the "no lower bound" row
+	}
+	__syncthreads();
+	float g;
+	{
+		float acc = 0.f;
+#pragma unroll
+		for (int w = 0; w < NW; w++) acc += s_part[w];
+		g = m.boost * fast_rcp(acc * inv_np);  // automatic_gain_control, ofdm.cc:1467-1498
+	}
+	// ---------------- LS estimate (a5): window sums + running sums over the rows of each lattice residue --------------
+	if (LS) {
+		if (tid < 3 * MB_LS_COLS) {
+			const int r = tid / MB_LS_COLS, jj = tid - r * MB_LS_COLS;
+			float2 run = make_float2(0.f, 0.f);
+#pragma unroll
+			for (int k3 = 0; k3 < (S + 2) / 3; k3++) {
+				const int k = r + 3 * k3;
+				if (k < S) {
+					const float2 *row = s_zf + k * MB_ZF_STRIDE + jj;
+					const float2 s01 = cadd(row[0], row[1]), s23 = cadd(row[2], row[3]), s45 = cadd(row[4], row[5]);
+					run = cadd(run, cadd(cadd(s01, s23), cadd(s45, row[6])));
+					s_pm[k * MB_LS_COLS + jj] = run;
+				}
 			}
-			const uint32_t cellb = w0 & 0x7FFFu, zs = (w0 >> 15) & 0x3FFFu;
-			const float t3 = (float)((int)(w0 >> 29) - 2) * (1.0f / 3.0f);
-			// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
-			const float2 ha = *reinterpret_cast<const float2 *>(s_zfb + zs), hb = *reinterpret_cast<const float2 *>(s_zfb + zs + 3 * MB_ZF_STRIDE * 8);
-			const float2 h = __ffma2_rn(csub(hb, ha), make_float2(t3, t3), ha);
+		}
+		__syncthreads();
+	}
+
+	// ---------------- channel at pilots, pilot-domain statistics (a5/a6, a8-a10) ------------------------------------
+	{
+		float accH = 0.f, accV = 0.f, accVn = 0.f;
+#pragma unroll 1
+		for (int p = tid; p < G::NPIL; p += T) {
+			const uint4 rec = __ldg(g_prec + p);
+			const float2 pf = __ldg(g_pf + p);
+			const uint32_t cellb = rec.w & 0xFFFFu, zslotb = rec.w >> 16;
 			const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
+			float2 h;
+			if (LS) {
+				const float2 u0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x & 0xFFFFu)), l0 = *reinterpret_cast<const float2 *>(s_pmb + (rec.x >> 16));
+				const float2 u1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y & 0xFFFFu)), l1 = *reinterpret_cast<const float2 *>(s_pmb + (rec.y >> 16));
+				const float2 u2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z & 0xFFFFu)), l2 = *reinterpret_cast<const float2 *>(s_pmb + (rec.z >> 16));
+				const float2 sum = cadd(cadd(csub(u0, l0), csub(u1, l1)), csub(u2, l2));
+				h = cscale(sum, pf.x * g);
+			} else {
+				h = cscale(*reinterpret_cast<const float2 *>(s_zfb + zslotb), g);  // ZF: H = Y / p
+			}
 			const float h2 = cnorm2(h);
+			accH += fast_sqrt(h2);
+			const float pv = pf.y;
 			const float2 yc = cmul_conj(yg, h);
 			float2 z, heq = h;
 			if (PHASE) {
-				const float inv = fast_rsqrt(h2);
+				// restore_channel_amplitude (ofdm.cc:1453-1466): H <- exp(j arg H); dividing by a unit-modulus number is
+				// multiplying by its conjugate.  get_angle() returns pi/2 whenever Re H == 0 (misc.cc:38-41).
+				const float inv = fast_rsqrt(h2), inv2 = fast_rcp(h2);
 				if (h.x == 0.f) {
 					heq = make_float2(0.f, 1.f);
 					z = make_float2(yg.y, -yg.x);
@@ -523,50 +387,108 @@ __global__ void __maxnreg__(Geo<S>::MAXREG) mb_demod_kernel(const MbDemodArgs a)
 					heq = cscale(h, inv);
 					z = cscale(yc, inv);
 				}
+				const float2 zn = cscale(yc, inv2);  // without amplitude restoration: SNR report only
+				accVn += (zn.x - pv) * (zn.x - pv) + zn.y * zn.y;
 			} else {
 				z = cscale(yc, fast_rcp(h2));
 			}
+			accV += (z.x - pv) * (z.x - pv) + z.y * z.y;
+			// The channel at pilots goes back into the compact rows at the pilot's own slot: in LS mode the rows are dead
+			// (consumed by the window sums before the barrier), in ZF mode this thread is the slot's only user.
+			*reinterpret_cast<float2 *>(s_zfb + zslotb) = h;
 			if (dbg) {
 				const size_t o = frame * (size_t)G::CELLS + (cellb >> 3);
 				if (a.dbg_Y) a.dbg_Y[o] = yg;
 				if (a.dbg_H) a.dbg_H[o] = heq;
 				if (a.dbg_Z) a.dbg_Z[o] = z;
 			}
-			demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
 		}
-		if (m.nVirtual > 0) {  // virtual bits are copies of the first LLRs (telecom_system.cc:1303-1306)
-			__syncthreads();
-			const uint32_t *__restrict__ g_virt = reinterpret_cast<const uint32_t *>(a.blob + m.off_virt);
-			for (int i = tid; i < m.nVirtual; i += T) {
-				const uint32_t w = __ldg(g_virt + i);
-				*reinterpret_cast<float *>(s_Lb + (w >> 16)) = *reinterpret_cast<const float *>(s_Lb + (w & 0xFFFFu));
-			}
-		}
-		fence_proxy_async();  // s_L was written through the generic proxy; the bulk store reads it through the async proxy
-		__syncthreads();
+		warp_partials3(accH, accV, accVn, s_part + 8);
+	}
+	__syncthreads();
+	float accH = 0.f, accV = 0.f, accVn = 0.f;
+#pragma unroll
+	for (int w = 0; w < NW; w++) {
+		accH += s_part[8 + w * 3 + 0];
+		accV += s_part[8 + w * 3 + 1];
+		accVn += s_part[8 + w * 3 + 2];
+	}
+	// The reference has no floor here; 1e-30 only matters where it would produce inf/NaN LLRs (ZF modes)
+	const float variance = fmaxf(accV * inv_np, 1e-30f);
+	const float inv_var = fast_rcp(variance);
 
-		// ---------------- LLRs out (one bulk store, decoder order) and the demod half of the stats record ----------------
-		if (tid == 0) {
-			bulk_s2g(a.llr + frame * (size_t)MB_N, smem_u32(s_L), MB_N * 4);
-			MbRxStats st;
-			st.iterations_done = -1;
-			st.crc = 0;
-			st.all_zeros = 0;
-			st.message_decoded = 0;
-			const float v_rep = PHASE ? accVn * inv_np : variance;
-			st.SNR = LS ? 10.0f * log10f(1.0f / v_rep) : 0.0f;  // candidate; finalised by the decoder
-			st.variance = variance;
-			st.mean_H = accH * inv_np;
-			st.reserved = 0;
-			a.stats[frame] = st;
+	// ---------------- data cells in grid order: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------
+#pragma unroll 2
+	for (int d = tid; d < G::NDATA; d += T) {
+		uint32_t w0, dw[3] = {0u, 0u, 0u};
+		if (RECW == 2) {
+			const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + d);
+			w0 = r.x, dw[0] = r.y;
+		} else {
+			const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + d);
+			w0 = r.x, dw[0] = r.y, dw[1] = r.z, dw[2] = r.w;
 		}
-		if (a.llr_cw) {
-			const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
-			float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
-			for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
+		const uint32_t cellb = w0 & 0x7FFFu, zs = (w0 >> 15) & 0x3FFFu;
+		const float t3 = (float)((int)(w0 >> 29) - 2) * (1.0f / 3.0f);
+		// interpolate_linear_col (interpolator.cc:163-254): a + (b - a) * (x - xa) / (xb - xa), pilot rows 3 apart
+		const float2 ha = *reinterpret_cast<const float2 *>(s_zfb + zs), hb = *reinterpret_cast<const float2 *>(s_zfb + zs + 3 * MB_ZF_STRIDE * 8);
+		const float2 h = __ffma2_rn(csub(hb, ha), make_float2(t3, t3), ha);
+		const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
+		const float h2 = cnorm2(h);
+		const float2 yc = cmul_conj(yg, h);
+		float2 z, heq = h;
+		if (PHASE) {
+			const float inv = fast_rsqrt(h2);
+			if (h.x == 0.f) {
+				heq = make_float2(0.f, 1.f);
+				z = make_float2(yg.y, -yg.x);
+			} else {
+				heq = cscale(h, inv);
+				z = cscale(yc, inv);
+			}
+		} else {
+			z = cscale(yc, fast_rcp(h2));
+		}
+		if (dbg) {
+			const size_t o = frame * (size_t)G::CELLS + (cellb >> 3);
+			if (a.dbg_Y) a.dbg_Y[o] = yg;
+			if (a.dbg_H) a.dbg_H[o] = heq;
+			if (a.dbg_Z) a.dbg_Z[o] = z;
+		}
+		demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
+	}
+	if (m.nVirtual > 0) {  // virtual bits are copies of the first LLRs (telecom_system.cc:1303-1306)
+		__syncthreads();
+		const uint32_t *__restrict__ g_virt = reinterpret_cast<const uint32_t *>(a.blob + m.off_virt);
+		for (int i = tid; i < m.nVirtual; i += T) {
+			const uint32_t w = __ldg(g_virt + i);
+			*reinterpret_cast<float *>(s_Lb + (w >> 16)) = *reinterpret_cast<const float *>(s_Lb + (w & 0xFFFFu));
 		}
 	}
-	if (tid == 0) bulk_wait_all();  // shared memory must outlive the last bulk store
+	fence_proxy_async();  // s_L was written through the generic proxy; the bulk store reads it through the async proxy
+	__syncthreads();
+
+	// ---------------- LLRs out (one bulk store, decoder order) and the demod half of the stats record ----------------
+	if (tid == 0) {
+		bulk_s2g(a.llr + frame * (size_t)MB_N, smem_u32(s_L), MB_N * 4);
+		MbRxStats st;
+		st.iterations_done = -1;
+		st.crc = 0;
+		st.all_zeros = 0;
+		st.message_decoded = 0;
+		const float v_rep = PHASE ? accVn * inv_np : variance;
+		st.SNR = LS ? 10.0f * log10f(1.0f / v_rep) : 0.0f;  // candidate; finalised by the decoder
+		st.variance = variance;
+		st.mean_H = accH * inv_np;
+		st.reserved = 0;
+		a.stats[frame] = st;
+	}
+	if (a.llr_cw) {
+		const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
+		float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
+		for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
+	}
+	if (tid == 0) bulk_wait_read();  // shared memory must outlive the bulk store's read
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -634,8 +556,6 @@ cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t 
 	if ((reinterpret_cast<uintptr_t>(a.x) & 15u) || (reinterpret_cast<uintptr_t>(a.llr) & 15u)) return cudaErrorMisalignedAddress;
 	MbDemodArgs args = a;
 	args.n_frames = (unsigned long long)n_frames;
-	const size_t resident = (size_t)g_num_sms * (size_t)v->ctas_per_sm;
-	const unsigned grid = (unsigned)(n_frames < resident ? n_frames : resident);
 	void *params[] = {&args};
-	return cudaLaunchKernel(v->fn, dim3(grid), dim3((unsigned)v->threads), params, (size_t)v->smem, stream);
+	return cudaLaunchKernel(v->fn, dim3((unsigned)n_frames), dim3((unsigned)v->threads), params, (size_t)v->smem, stream);
 }
