@@ -43,13 +43,22 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }  // a + (-i) b
 __device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }  // a + (+i) b
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+// Complex products as FMUL2 + FFMA2.  The sign pattern sits on the broadcast scalar (not on the swapped pair): that is the
+// form ptxas folds into the FFMA2 operand modifiers (.LO_HI swap, .NP half negation) instead of materialising a negation.
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)  // (a.x w.x - a.y w.y, a.x w.y + a.y w.x)
 {
-	return __ffma2_rn(make_float2(a.x, a.x), w, __fmul2_rn(make_float2(a.y, a.y), make_float2(-w.y, w.x)));
+	return __ffma2_rn(make_float2(w.y, w.x), make_float2(-a.y, a.y), __fmul2_rn(make_float2(a.x, a.x), w));
 }
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 h)  // a * conj(h)
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 h)  // a * conj(h) = h.x (a.x, a.y) + h.y (a.y, -a.x)
 {
-	return __ffma2_rn(make_float2(a.x, a.x), make_float2(h.x, -h.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(h.y, h.x)));
+	return __ffma2_rn(make_float2(a.y, a.x), make_float2(h.y, -h.y), __fmul2_rn(make_float2(h.x, h.x), a));
+}
+// Streaming 8-byte load of a sample: no L1 allocation, so the descriptor tables and twiddles stay L1 resident.
+__device__ __forceinline__ float2 ld_stream(const float2 *p)
+{
+	float2 r;
+	asm("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+	return r;
 }
 __device__ __forceinline__ float cnorm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
 __device__ __forceinline__ float fast_rcp(float x)
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 			float2 v[16];
 			if (active) {
 #pragma unroll
-				for (int n1 = 0; n1 < 16; n1++) v[n1] = __ldcs(xs + 16 * n1);  // x[16 n1 + t], GI skipped
+				for (int n1 = 0; n1 < 16; n1++) v[n1] = ld_stream(xs + 16 * n1);  // x[16 n1 + t], GI skipped
 			}
 			if (ch == 0) __syncthreads();  // twiddle table published (the loads above are already in flight)
 			if (active) {
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	if (a.llr_cw) {
 		const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + a.off_var_of_cw);
 		float *__restrict__ o2 = a.llr_cw + frame * (size_t)MB_N;
-		for (int i = tid; i < MB_N; i += T) o2[i] = s_L[g_voc[i]];
+		for (int i = tid; i < MB_N; i += T) o2[i] = s_L[MB_HANDOFF((uint32_t)g_voc[i])];
 	}
 	if (tid == 0) bulk_wait_read();  // shared memory must outlive the bulk store's read
 }

@@ -14,7 +14,7 @@ struct MbRxStats {
 
 struct MbDemodArgs {
 	const float2 *x;       // [B][Nsymb][272] complex64 baseband, preamble stripped
-	float *llr;            // [B][1600] LLRs in the decoder's internal variable order
+	float *llr;            // [B][1600] LLRs in the hand-off layout (internal variable order, 32-float rows rotated: MB_HANDOFF)
 	float *llr_cw;         // optional [B][1600] LLRs in codeword order (parity output)
 	MbRxStats *stats;      // [B]
 	float2 *dbg_Y, *dbg_H, *dbg_Z;  // optional [B][Nsymb*50] stage captures
@@ -26,7 +26,7 @@ struct MbDemodArgs {
 };
 
 struct MbLdpcArgs {
-	const float *llr;      // [B][1600] internal order
+	const float *llr;      // [B][1600] hand-off layout (MB_HANDOFF)
 	uint8_t *payload;      // [B][frame_bytes]
 	MbRxStats *stats;      // [B]  (SNR/variance/mean_H already filled by the demod kernel)
 	const uint8_t *blob;

@@ -118,11 +118,13 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 	}
 
 	{
-		const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.llr + frame * (size_t)MB_N);
-		for (int i = tid; i < MB_N / 4; i += kThreads) {
-			const float4 v = src[i];
-			reinterpret_cast<float4 *>(s_lam)[i] = v;
-			reinterpret_cast<float4 *>(s_lch)[i] = v;
+		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores
+		const float *__restrict__ src = a.llr + frame * (size_t)MB_N;
+		for (int i = tid; i < MB_N; i += kThreads) {
+			const float v = __ldcs(src + i);
+			const unsigned p = MB_HANDOFF_INV((unsigned)i);
+			s_lam[p] = v;
+			s_lch[p] = v;
 		}
 		for (int i = tid; i <= CS; i += kThreads) s_R[i] = 0.f;
 		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);

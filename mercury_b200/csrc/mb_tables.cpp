@@ -431,7 +431,7 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 			uint32_t *rec = &data_rec[(size_t)D * m.data_rec_words];
 			rec[0] = (uint32_t)(cell * 8) | (zs << 15) | ((uint32_t)(t + 2) << 29);
 			for (int e = 0; e < m.bps; e++) {
-				const uint32_t d = (uint32_t)dst[(size_t)q * m.bps + e] * 4u;
+				const uint32_t d = MB_HANDOFF((uint32_t)dst[(size_t)q * m.bps + e]) * 4u;
 				rec[1 + e / 2] |= d << (16 * (e & 1));
 			}
 		}
@@ -439,8 +439,8 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 	std::vector<uint16_t> virt;
 	for (int i = 0; i < m.nBits; i++)
 		if (dst2[i] != MB_NO_DST) {
-			virt.push_back((uint16_t)(dst[i] * 4));
-			virt.push_back((uint16_t)(dst2[i] * 4));
+			virt.push_back((uint16_t)(MB_HANDOFF((uint32_t)dst[i]) * 4));
+			virt.push_back((uint16_t)(MB_HANDOFF((uint32_t)dst2[i]) * 4));
 		}
 	if ((int)virt.size() != 2 * m.nVirtual) return "virtual-bit copy list does not match nVirtual";
 	m.off_zf_src = bl.put(zf_src);

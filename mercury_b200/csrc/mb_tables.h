@@ -29,13 +29,19 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 8u
+#define MB_BLOB_VERSION 9u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
 #define MB_MAX_GROUPS 64  // warp-sized groups of checks / variables (<= 50 used)
 #define MB_ZF_STRIDE 27   // compact pilot row: 4 zeros | <= 17 pilots (columns s%3 + 3j at [4 + j]) | zeros
 #define MB_LS_COLS 18     // distinct clipped 21-column windows per row: start index (c + 4 - s%3) / 3 = 0..17
+// LLR hand-off layout between the two kernels: internal variable v sits at MB_HANDOFF(v): every 32-float row is rotated by
+// its row index.  The de-interleavers send the LLRs of neighbouring cells to variables a multiple of 160 apart (the same
+// shared-memory bank); the rotation spreads them over the banks (10-way -> 2.8-way conflicts on the demodulator's scatter),
+// and the decoder undoes it for free while it stages the vector in shared memory.
+#define MB_HANDOFF(v) (((v) & ~31u) | (((v) + ((v) >> 5)) & 31u))
+#define MB_HANDOFF_INV(i) (((i) & ~31u) | (((i) - ((i) >> 5)) & 31u))
 
 struct MbRate {
 	int32_t rate_num, N, K, P, n_edges;
@@ -85,7 +91,7 @@ struct MbMode {
 	uint32_t off_pilot_f;    // f32[2*nPilots] {1 / (pilots inside the clipped 21x21 window), pilot value}
 	uint32_t off_data_rec;   // u32[data_rec_words*nData] data cells in GRID (deframer) order: word 0 = cell*8 | zslot(r0)*8 << 15 | (t+2) << 29
 	                         //   with channel = H[r0] + (H[r0+3] - H[r0]) * t / 3 (interpolator.cc:163-254 resolved on the host), then
-	                         //   one u16 per emitted LLR (MSB first): byte offset of its destination in the internal-order LLR vector
+	                         //   one u16 per emitted LLR (MSB first): byte offset of its destination in the hand-off LLR vector (MB_HANDOFF)
 	uint32_t off_virt;       // u16[2*nVirtual] (source byte offset, destination byte offset) of the virtual-bit copies (telecom_system.cc:1303-1306)
 	int32_t data_rec_words;  // 2 for bps <= 2, 4 above
 	float pinv_mag;          // |1/p| as float (pilot boost 1.33)

@@ -63,6 +63,12 @@ class Blob:
         return self.arr(self.hdr["off_twiddle"], "<f4", 512).view(np.complex64).reshape(16, 16)
 
 
+def handoff(v):
+    """position of internal variable v in the LLR hand-off vector between the two kernels (MB_HANDOFF, mb_tables.h)"""
+    v = np.asarray(v, np.int64)
+    return (v & ~31) | ((v + (v >> 5)) & 31)
+
+
 def cslot(r, k, cs):
     """check-side slot of edge k of sorted check cs (warp-blocked ELL, see mb_tables.h)"""
     return int(r["cgbase"][cs >> 5]) + 32 * k + (cs & 31)
@@ -165,11 +171,12 @@ def demod(blob, cfg, x):
         q = q_of_cell[int(cell)]
         for e in range(bps):
             off = (int(drec[D_i, 1 + e // 2]) >> (16 * (e & 1))) & 0xFFFF
-            assert off // 4 == int(m["llr_dst"][q * bps + e])
+            assert off // 4 == int(handoff(int(m["llr_dst"][q * bps + e])))
             lam[q * bps + e] = L[off // 4]
     snr = float(10 * np.log10(1.0 / v_rep)) if m["estimator"] == 1 else 0.0
-    return dict(Y=Yg.reshape(S, MB_NC), H=H.reshape(S, MB_NC), Z=Z.reshape(S, MB_NC), llr_demod=lam, llr_internal=L,
-                llr_cw=L[r["var_of_cw"].astype(np.int64)], variance=variance, mean_H=mean_H, snr=snr)
+    L_int = L[handoff(np.arange(MB_N))]  # undo the row rotation of the hand-off layout
+    return dict(Y=Yg.reshape(S, MB_NC), H=H.reshape(S, MB_NC), Z=Z.reshape(S, MB_NC), llr_demod=lam, llr_handoff=L, llr_internal=L_int,
+                llr_cw=L_int[r["var_of_cw"].astype(np.int64)], variance=variance, mean_H=mean_H, snr=snr)
 
 
 def ldpc_decode(blob, cfg, llr_internal, max_iters):

@@ -236,7 +236,7 @@ def test_all_zeros_frame_is_rejected(ts):
     cw = np.full(1600, 1e20, np.float32)
     cw[: geom["nReal"]] = np.where(m["scr"][: geom["nReal"]] == 1, -1e20, 1e20)
     L = np.zeros((1, 1600), np.float32)
-    L[0, r["var_of_cw"].astype(int)] = cw
+    L[0, be.handoff(r["var_of_cw"].astype(int))] = cw  # the kernels' hand-off layout
     st = np.zeros(1, mb.STATS_DTYPE)
     st["mean_H"] = 1.0
     d_llr, d_st = torch.from_numpy(L).cuda(), torch.from_numpy(st.view(np.uint8).reshape(1, 32)).cuda()
