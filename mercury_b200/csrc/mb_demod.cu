@@ -179,8 +179,8 @@ __device__ __forceinline__ void warp_partial1(float a, float *s_part)
 
 // Max-log LLRs of one equalised symbol (psk.cc:278-326): for bit k (mask 1<<k) (min_{bit=1} D - min_{bit=0} D) / variance,
 // emitted MSB first; dw[] holds the byte offsets of the emitted LLRs in the internal-order vector, two per word.
-template <int M, int BPS>
-__device__ __forceinline__ void demap_scatter(const float2 z, const float inv_var, const float2 *s_cons, const uint32_t (&dw)[3],
+template <int M, int BPS, typename ConsT>
+__device__ __forceinline__ void demap_scatter(const float2 z, const float inv_var, const ConsT &s_cons, const uint32_t (&dw)[3],
 					      unsigned char *s_L)
 {
 	float d0[BPS], d1[BPS];
@@ -225,12 +225,11 @@ struct Geo {
 	// shared memory layout (bytes); the FFT transpose scratch is dead before the estimator's arrays are first written
 	static constexpr int OFF_PART = 0;                       // 64 floats of per-warp partial sums
 	static constexpr int OFF_CONS = OFF_PART + 256;          // 32 float2 constellation
-	static constexpr int OFF_TW = OFF_CONS + 256;            // 256 float2 twiddles of the 16 x 16 split
-	static constexpr int OFF_Y = OFF_TW + 2048;              // [S][50] float2 carriers
-	static constexpr int OFF_SCR = OFF_Y + CELLS * 8;        // [SC][16][17] float2 transpose scratch, aliased with:
-	static constexpr int OFF_ZF = OFF_SCR;                   //   [S][27] float2 compact pilot rows, later the channel at pilots
-	static constexpr int OFF_PM = OFF_ZF + ((ZF * 8 + 15) & ~15);  //   [S+1][18] float2 window sums / running sums
-	static constexpr int OFF_L = OFF_PM + PM * 8;            //   [1600] float LLRs, decoder order
+	static constexpr int OFF_Y = OFF_CONS + 256;             // [S][50] float2 carriers
+	static constexpr int OFF_ZF = OFF_Y + CELLS * 8;         // [S][27] float2 compact pilot rows (filled by the FFT epilogue), later the channel at pilots
+	static constexpr int OFF_SCR = OFF_ZF + ((ZF * 8 + 15) & ~15);  // [SC][16][17] float2 transpose scratch, aliased with:
+	static constexpr int OFF_PM = OFF_SCR;                   //   [S+1][18] float2 window sums / running sums
+	static constexpr int OFF_L = OFF_PM + PM * 8;            //   [1600] float LLRs, hand-off order
 	static constexpr int SCR_BYTES = SC * 16 * 17 * 8;
 	static constexpr int EST_BYTES = OFF_L + MB_N * 4 - OFF_SCR;
 	static constexpr int SMEM = OFF_SCR + (SCR_BYTES > EST_BYTES ? SCR_BYTES : EST_BYTES);
@@ -250,7 +249,6 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	const int tid = threadIdx.x;
 	float *s_part = reinterpret_cast<float *>(smem + G::OFF_PART);
 	float2 *s_cons = reinterpret_cast<float2 *>(smem + G::OFF_CONS);
-	float2 *s_tw = reinterpret_cast<float2 *>(smem + G::OFF_TW);
 	float2 *s_Y = reinterpret_cast<float2 *>(smem + G::OFF_Y);
 	unsigned char *s_Yb = smem + G::OFF_Y;
 	float2 *s_zf = reinterpret_cast<float2 *>(smem + G::OFF_ZF);
@@ -261,27 +259,35 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	float *s_L = reinterpret_cast<float *>(s_Lb);
 
 	const size_t frame = blockIdx.x;
-	const uint32_t *__restrict__ g_zf_src = reinterpret_cast<const uint32_t *>(a.blob + m.off_zf_src);
 	const uint4 *__restrict__ g_prec = reinterpret_cast<const uint4 *>(a.blob + m.off_pilot_rec);
 	const float2 *__restrict__ g_pf = reinterpret_cast<const float2 *>(a.blob + m.off_pilot_f);
 	const uint32_t *__restrict__ g_drec = reinterpret_cast<const uint32_t *>(a.blob + m.off_data_rec);
 	const bool dbg = a.dbg_Y || a.dbg_H || a.dbg_Z;
 
 	if (tid < M) s_cons[tid] = reinterpret_cast<const float2 *>(a.blob + m.off_const)[tid];  // published by the barrier after the FFT
-	{
-		const float2 *__restrict__ g_tw = reinterpret_cast<const float2 *>(a.blob + a.off_twiddle);  // tw[k1*16 + n2] = W256^(n2 k1)/256
-		for (int i = tid; i < 256; i += T) s_tw[i] = __ldg(g_tw + i);
+
+	// zero padding of the compact pilot rows: row s holds its pilots (columns s%3 + 3j) at [4 + j], everything else in the
+	// 27-wide row is zero, so that every clipped 21-column window is exactly 7 consecutive entries
+	for (int i = tid; i < S * 11; i += T) {
+		const int sr = i / 11, q = i - sr * 11;
+		const int j = q < 4 ? q : (q < 10 ? 17 + q : (sr % 3 == 2 ? 20 : 26));  // rows with s%3 == 2 hold 16 pilots only
+		s_zf[sr * MB_ZF_STRIDE + j] = make_float2(0.f, 0.f);
 	}
 
 	// ---------------- FFT-256 per symbol (a2, a3), SC symbols per round ---------------------------------------------------
+	const uint32_t pinv_bits = __float_as_uint(m.pinv_mag);
+	float agc = 0.f;
 	{
+		const unsigned long long *__restrict__ g_neg = reinterpret_cast<const unsigned long long *>(a.blob + m.off_pilot_neg);
 		const int grp = tid >> 4, t = tid & 15;
 		const bool active = grp < SC;  // Nsymb = 9: the last half warp has no symbol, but still takes part in the warp syncs
 		// Transpose scratch of one symbol: 16 rows of 17 float2 (the pad makes both the row writes and the column reads
-		// conflict free, and every access is base + immediate).  Twiddles sit in shared memory for the same reason: one base
-		// register instead of 30 loop-invariant values that would not survive the 64-register budget.
+		// conflict free, and every access is base + immediate).
 		float2 *buf = reinterpret_cast<float2 *>(smem + G::OFF_SCR) + (active ? grp : 0) * (16 * 17);
-		const float2 *tw = s_tw + t;  // tw[k1 * 16] = W256^(t k1) / 256
+		// Twiddles W256^(t k1), k1 = 1..15, are powers of w1 = W256^t: generated by a running product (two packed instructions
+		// each, 15 roundings at most: ~1e-6 relative) instead of 15 table reads per round -- the shared-memory / L1 data pipe
+		// is this kernel's busiest unit, the FMA pipe is not.  The table's 1/256 (ofdm.cc:439-442) moves to the 4 outputs.
+		const float2 w1 = cscale(__ldg(reinterpret_cast<const float2 *>(a.blob + a.off_twiddle) + 16 + t), 256.0f);
 		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * MB_NOFDM + MB_NGI + t;
 #pragma unroll 1
 		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * MB_NOFDM) {
@@ -289,14 +295,15 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 			if (active) {
 #pragma unroll
 				for (int n1 = 0; n1 < 16; n1++) v[n1] = ld_stream(xs + 16 * n1);  // x[16 n1 + t], GI skipped
-			}
-			if (ch == 0) __syncthreads();  // twiddle table published (the loads above are already in flight)
-			if (active) {
 				float2 A[16];
 				fft16(v, A);
-				buf[t * 17] = cscale(A[0], 1.0f / 256.0f);
+				buf[t * 17] = A[0];
+				float2 wk = w1;
 #pragma unroll
-				for (int k1 = 1; k1 < 16; k1++) buf[t * 17 + k1] = cmul(A[k1], tw[k1 * 16]);
+				for (int k1 = 1; k1 < 16; k1++) {
+					buf[t * 17 + k1] = cmul(A[k1], wk);
+					if (k1 < 15) wk = cmul(wk, w1);
+				}
 			}
 			__syncwarp();
 			if (active) {
@@ -304,37 +311,35 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 #pragma unroll
 				for (int n2 = 0; n2 < 16; n2++) v[n2] = buf[n2 * 17 + t];
 				fft16_pruned(v, X0, X1, X14, X15);  // bins t, 16+t, 224+t, 240+t
-				float2 *row = s_Y + (ch * SC + grp) * MB_NC;
-				// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49
-				if (t >= 1) row[24 + t] = X0;
-				if (t <= 9) row[40 + t] = X1;
-				if (t >= 7) row[t - 7] = X14;
-				row[9 + t] = X15;
+				// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49.  Carriers that are
+				// pilots (s%3 == c%3) also feed the AGC sum (a4) and, zero-forced (Y/p), the compact pilot rows of the estimator.
+				const int sr = ch * SC + grp;
+				float2 *row = s_Y + sr * MB_NC;
+				float2 *zrow = s_zf + sr * MB_ZF_STRIDE + 4;
+				const int r3 = sr % 3;
+				const unsigned long long neg = __ldg(g_neg + sr);
+				auto emit = [&](const float2 X, const int c) {
+					const float2 y = cscale(X, 1.0f / 256.0f);
+					row[c] = y;
+					if (c % 3 == r3) {
+						agc += fast_sqrt(cnorm2(y));
+						zrow[c / 3] = cscale(y, __uint_as_float(pinv_bits ^ ((unsigned)(neg >> c) << 31)));
+					}
+				};
+				if (t >= 1) emit(X0, 24 + t);
+				if (t <= 9) emit(X1, 40 + t);
+				if (t >= 7) emit(X14, t - 7);
+				emit(X15, 9 + t);
 			}
 			__syncwarp();
 		}
 	}
+	warp_partial1(agc, s_part);
 	__syncthreads();
+	if (LS && tid >= T - MB_LS_COLS) s_pm[S * MB_LS_COLS + (tid - (T - MB_LS_COLS))] = make_float2(0.f, 0.f);  // the "no lower bound" row
 
-	// ---------------- AGC sum (a4) + zero-forced pilots into compact, zero-padded rows ---------------------------
-	const uint32_t pinv_bits = __float_as_uint(m.pinv_mag);
+	// ---------------- AGC gain (a4) -------------------------------------------------------------------------------------
 	const float inv_np = 1.0f / (float)G::NPIL;
-	{
-		float acc = 0.f;
-#pragma unroll 2
-		for (int idx = tid; idx < G::ZF; idx += T) {
-			const uint32_t w = __ldg(g_zf_src + idx);
-			const float2 y = *reinterpret_cast<const float2 *>(s_Yb + (w & 0x7FFFu));
-			const bool valid = (w >> 30) & 1u;
-			const float pinv = __uint_as_float(pinv_bits | (w & 0x80000000u));
-			acc += valid ? fast_sqrt(cnorm2(y)) : 0.f;
-			s_zf[idx] = valid ? cscale(y, pinv) : make_float2(0.f, 0.f);  // ZF estimate Y/p (AGC gain applied later: all linear)
-		}
-		warp_partial1(acc, s_part);
-		if (LS)
-			for (int i = tid; i < MB_LS_COLS; i += T) s_pm[S * MB_LS_COLS + i] = make_float2(0.f, 0.f);  // the "no lower bound" row
-	}
-	__syncthreads();
 	float g;
 	{
 		float acc = 0.f;
@@ -427,6 +432,9 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	const float inv_var = fast_rcp(variance);
 
 	// ---------------- data cells in grid order: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------
+	float2 c_reg[M <= 4 ? M : 1];  // BPSK / QPSK: the constellation lives in registers for the whole loop
+#pragma unroll
+	for (int j = 0; j < (M <= 4 ? M : 1); j++) c_reg[j] = s_cons[j];
 #pragma unroll 2
 	for (int d = tid; d < G::NDATA; d += T) {
 		uint32_t w0, dw[3] = {0u, 0u, 0u};
@@ -464,7 +472,10 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 			if (a.dbg_H) a.dbg_H[o] = heq;
 			if (a.dbg_Z) a.dbg_Z[o] = z;
 		}
-		demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
+		if (M <= 4)
+			demap_scatter<M, BPS>(z, inv_var, c_reg, dw, s_Lb);
+		else
+			demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
 	}
 	if (m.nVirtual > 0) {  // virtual bits are copies of the first LLRs (telecom_system.cc:1303-1306)
 		__syncthreads();
@@ -538,8 +549,6 @@ cudaError_t mb_demod_init()
 	if (e != cudaSuccess) return e;
 	for (Variant &v : g_variants) {
 		e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
-		if (e != cudaSuccess) return e;
-		e = cudaFuncSetAttribute(v.fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		if (e != cudaSuccess) return e;
 		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v.ctas_per_sm, v.fn, v.threads, (size_t)v.smem);
 		if (e != cudaSuccess) return e;

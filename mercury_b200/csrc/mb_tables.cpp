@@ -443,6 +443,12 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 			virt.push_back((uint16_t)(MB_HANDOFF((uint32_t)dst2[i]) * 4));
 		}
 	if ((int)virt.size() != 2 * m.nVirtual) return "virtual-bit copy list does not match nVirtual";
+	{
+		std::vector<uint64_t> neg(S, 0);
+		for (int p = 0; p < m.nPilots; p++)
+			if (pval[pilot_cell[p]] < 0) neg[pilot_cell[p] / C] |= 1ull << (pilot_cell[p] % C);
+		m.off_pilot_neg = bl.put(neg);
+	}
 	m.off_zf_src = bl.put(zf_src);
 	m.off_pilot_rec = bl.put(pilot_rec);
 	m.off_pilot_f = bl.put(pilot_f);
@@ -534,7 +540,8 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16) ||
 		    !in(m.off_zf_src, 4 * (size_t)m.Nsymb * MB_ZF_STRIDE) || !in(m.off_pilot_rec, 16 * (size_t)m.nPilots) ||
 		    !in(m.off_pilot_f, 8 * (size_t)m.nPilots) || (m.data_rec_words != 2 && m.data_rec_words != 4) ||
-		    !in(m.off_data_rec, 4 * (size_t)m.data_rec_words * m.nData) || !in(m.off_virt, 4 * (size_t)m.nVirtual))
+		    !in(m.off_data_rec, 4 * (size_t)m.data_rec_words * m.nData) || !in(m.off_virt, 4 * (size_t)m.nVirtual) ||
+		    !in(m.off_pilot_neg, 8 * (size_t)m.Nsymb))
 			return "table blob: mode table out of range";
 	}
 	return "";

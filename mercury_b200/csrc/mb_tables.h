@@ -29,7 +29,7 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 9u
+#define MB_BLOB_VERSION 10u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
@@ -95,7 +95,7 @@ struct MbMode {
 	uint32_t off_virt;       // u16[2*nVirtual] (source byte offset, destination byte offset) of the virtual-bit copies (telecom_system.cc:1303-1306)
 	int32_t data_rec_words;  // 2 for bps <= 2, 4 above
 	float pinv_mag;          // |1/p| as float (pilot boost 1.33)
-	int32_t reserved2;
+	uint32_t off_pilot_neg;  // u64[Nsymb]   bit c of word s set <=> the pilot at (s, c) is negative (-boost)
 };
 
 struct MbBlobHeader {

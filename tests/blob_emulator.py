@@ -16,7 +16,7 @@ MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate
                    [(n, "<u4") for n in ("off_pinv", "off_pval", "off_invn", "off_pilot_cell", "off_sym_cell", "off_llr_dst",
                                          "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat", "off_zf_src", "off_pilot_rec",
                                          "off_pilot_f", "off_data_rec", "off_virt")] +
-                   [("data_rec_words", "<i4"), ("pinv_mag", "<f4"), ("reserved2", "<i4")])
+                   [("data_rec_words", "<i4"), ("pinv_mag", "<f4"), ("off_pilot_neg", "<u4")])
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("reserved", "<u4"), ("off_twiddle", "<u4"),
                    ("pad", "<u4", (3,)), ("modes", MODE_DT, (17,)), ("rates", RATE_DT, (8,))])
 
@@ -46,7 +46,8 @@ class Blob:
                  pilot_rec=self.arr(m["off_pilot_rec"], "<u4", 4 * int(m["nPilots"])).reshape(-1, 4),
                  pilot_f=self.arr(m["off_pilot_f"], "<f4", 2 * int(m["nPilots"])).reshape(-1, 2),
                  data_rec=self.arr(m["off_data_rec"], "<u4", int(m["data_rec_words"]) * int(m["nData"])).reshape(int(m["nData"]), -1),
-                 virt=self.arr(m["off_virt"], "<u2", 2 * int(m["nVirtual"])).reshape(-1, 2))
+                 virt=self.arr(m["off_virt"], "<u2", 2 * int(m["nVirtual"])).reshape(-1, 2),
+                 pilot_neg=self.arr(m["off_pilot_neg"], "<u8", int(m["Nsymb"])))
         return d
 
     def rate(self, idx):
@@ -104,6 +105,13 @@ def demod(blob, cfg, x):
     assert np.array_equal(np.sort((zs[valid] & 0x7FFF) // 8), np.sort(pc)) and valid.sum() == m["nPilots"]
     assert np.array_equal(pinv[valid], m["pinv"][(zs[valid] & 0x7FFF) // 8])
     zf = np.where(valid, Y[(zs & 0x7FFF) // 8] * pinv, 0).astype(c64)
+    # the kernel's FFT epilogue builds the same rows from the lattice rule (pilot iff s%3 == c%3) and the per-row sign mask
+    zf2 = np.zeros(S * ZF_STRIDE, c64)
+    for s_ in range(S):
+        for c_ in range(s_ % 3, MB_NC, 3):
+            sign = -1.0 if (int(m["pilot_neg"][s_]) >> c_) & 1 else 1.0
+            zf2[s_ * ZF_STRIDE + 4 + c_ // 3] = Y[s_ * MB_NC + c_] * f32(sign * m["pinv_mag"])
+    assert np.array_equal(zf, zf2)
     prec, pf = m["pilot_rec"].astype(np.int64), m["pilot_f"]
     cellb, zslotb = prec[:, 3] & 0xFFFF, prec[:, 3] >> 16
     assert np.array_equal(cellb // 8, pc) and not (cellb % 8).any() and not (zslotb % 8).any()
