@@ -289,6 +289,12 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		// is this kernel's busiest unit, the FMA pipe is not.  The table's 1/256 (ofdm.cc:439-442) moves to the 4 outputs.
 		const float2 w1 = cscale(__ldg(reinterpret_cast<const float2 *>(a.blob + a.off_twiddle) + 16 + t), 256.0f);
 		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * MB_NOFDM + MB_NGI + t;
+		if (NCH > 1 && active) {  // later rounds: one 128-byte line per thread into L2 while round 0 is in flight
+			const char *line = reinterpret_cast<const char *>(a.x + (frame * S + (size_t)grp) * MB_NOFDM + MB_NGI) + t * 128;
+#pragma unroll
+			for (int ch = 1; ch < NCH; ch++)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(line + (size_t)ch * SC * MB_NOFDM * 8));
+		}
 #pragma unroll 1
 		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * MB_NOFDM) {
 			float2 v[16];
@@ -335,6 +341,10 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		}
 	}
 	warp_partial1(agc, s_part);
+	// descriptor records are L2 hits at best: fetch the first ones before the barriers they would otherwise wait behind
+	uint4 rec = __ldg(g_prec + (tid < G::NPIL ? tid : 0));  // Nsymb = 9 has fewer pilots (150) than threads (160)
+	float2 pf = __ldg(g_pf + (tid < G::NPIL ? tid : 0));
+	static_assert(G::NDATA >= T, "first data descriptor of every thread exists");
 	__syncthreads();
 	if (LS && tid >= T - MB_LS_COLS) s_pm[S * MB_LS_COLS + (tid - (T - MB_LS_COLS))] = make_float2(0.f, 0.f);  // the "no lower bound" row
 
@@ -371,8 +381,12 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		float accH = 0.f, accV = 0.f, accVn = 0.f;
 #pragma unroll 1
 		for (int p = tid; p < G::NPIL; p += T) {
-			const uint4 rec = __ldg(g_prec + p);
-			const float2 pf = __ldg(g_pf + p);
+			uint4 rec_n = rec;
+			float2 pf_n = pf;
+			if (p + T < G::NPIL) {
+				rec_n = __ldg(g_prec + p + T);
+				pf_n = __ldg(g_pf + p + T);
+			}
 			const uint32_t cellb = rec.w & 0xFFFFu, zslotb = rec.w >> 16;
 			const float2 yg = cscale(*reinterpret_cast<const float2 *>(s_Yb + cellb), g);
 			float2 h;
@@ -416,8 +430,18 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 				if (a.dbg_H) a.dbg_H[o] = heq;
 				if (a.dbg_Z) a.dbg_Z[o] = z;
 			}
+			rec = rec_n;
+			pf = pf_n;
 		}
 		warp_partials3(accH, accV, accVn, s_part + 8);
+	}
+	uint32_t dr[4] = {0u, 0u, 0u, 0u};
+	if (RECW == 2) {
+		const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + tid);
+		dr[0] = r.x, dr[1] = r.y;
+	} else {
+		const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + tid);
+		dr[0] = r.x, dr[1] = r.y, dr[2] = r.z, dr[3] = r.w;
 	}
 	__syncthreads();
 	float accH = 0.f, accV = 0.f, accVn = 0.f;
@@ -435,15 +459,17 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	float2 c_reg[M <= 4 ? M : 1];  // BPSK / QPSK: the constellation lives in registers for the whole loop
 #pragma unroll
 	for (int j = 0; j < (M <= 4 ? M : 1); j++) c_reg[j] = s_cons[j];
-#pragma unroll 2
+#pragma unroll 1
 	for (int d = tid; d < G::NDATA; d += T) {
-		uint32_t w0, dw[3] = {0u, 0u, 0u};
-		if (RECW == 2) {
-			const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + d);
-			w0 = r.x, dw[0] = r.y;
-		} else {
-			const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + d);
-			w0 = r.x, dw[0] = r.y, dw[1] = r.z, dw[2] = r.w;
+		const uint32_t w0 = dr[0], dw[3] = {dr[1], dr[2], dr[3]};
+		if (d + T < G::NDATA) {  // next record in flight while this cell is equalised and de-mapped
+			if (RECW == 2) {
+				const uint2 r = __ldg(reinterpret_cast<const uint2 *>(g_drec) + d + T);
+				dr[0] = r.x, dr[1] = r.y;
+			} else {
+				const uint4 r = __ldg(reinterpret_cast<const uint4 *>(g_drec) + d + T);
+				dr[0] = r.x, dr[1] = r.y, dr[2] = r.z, dr[3] = r.w;
+			}
 		}
 		const uint32_t cellb = w0 & 0x7FFFu, zs = (w0 >> 15) & 0x3FFFu;
 		const float t3 = (float)((int)(w0 >> 29) - 2) * (1.0f / 3.0f);
