@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +40,7 @@ struct mercury_b200 {
 	MbBlobHeader hdr;
 	uint8_t *d_blob = nullptr;
 	int config = -1, ldpc_iters = 50, decoder = MERCURY_B200_DECODER_SPA;
+	int cheap_test_threads = 16;  // tuning knob of the decoder's early syndrome test (MERCURY_B200_CHEAP_TEST in the environment)
 	std::string err;
 	uint64_t launches = 0;
 	Slot slots[kSlots];
@@ -124,6 +126,7 @@ int launch_ldpc(mercury_b200_t *h, const void *d_llr, size_t n, void *d_payload,
 	a.rate = h->hdr.rates[m.rate_idx];
 	a.max_iters = h->ldpc_iters;
 	a.check_gate = 1;
+	a.cheap_test_threads = h->cheap_test_threads;
 	cudaError_t e = mb_launch_ldpc(a, n, h->decoder, s);
 	if (e != cudaSuccess) return cuda_fail(h, e, "ldpc kernel launch");
 	h->launches++;
@@ -202,6 +205,7 @@ int mercury_b200_create(int device, mercury_b200_t **out)
 	mercury_b200_t *h = new (std::nothrow) mercury_b200;
 	if (!h) return MERCURY_B200_ENOMEM;
 	h->device = device;
+	if (const char *e = getenv("MERCURY_B200_CHEAP_TEST")) h->cheap_test_threads = std::max(0, std::min(256, atoi(e)));
 	*out = h;
 	return MERCURY_B200_OK;
 }

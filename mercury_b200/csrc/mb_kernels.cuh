@@ -34,6 +34,7 @@ struct MbLdpcArgs {
 	MbRate rate;
 	int32_t max_iters;
 	int32_t check_gate;    // 1: honour the mean|H| < 0.3 gate recorded by the demod kernel
+	int32_t cheap_test_threads;  // run the syndrome-only test after an iteration that started with <= this many unhappy threads
 };
 
 size_t mb_ldpc_smem_bytes(int c_slots);

@@ -33,8 +33,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kCheapTestThreads = 64;  // run the syndrome-only test after an iteration that started with <= this many unhappy threads
+constexpr int kThreads = 32 * MB_LDPC_WARPS;
 constexpr float kLn2 = 0.69314718055994531f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
@@ -80,6 +79,19 @@ __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 	return crc;
 }
 
+// shared-memory layout (bytes from the start of the dynamic segment); constant offsets keep every hot access [reg + imm]
+constexpr int kOffLam = 0;                        // float[1601] posterior; [1600] = +inf, the variable every padding slot points at
+constexpr int kOffLch = (MB_N + 4) * 4;           // float[1600] channel LLR
+constexpr int kOffR = kOffLch + MB_N * 4;         // float[c_slots + 1] check -> variable message per check-side slot; [c_slots] == 0 always
+
+// 32-bit shared-window addressing for the gathers of the hot loops (one add per access, base kept in a register)
+__device__ __forceinline__ float lds_f(unsigned sbase, unsigned off)
+{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sbase + off));
+	return v;
+}
+
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
 {
@@ -87,20 +99,20 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 	const MbMode &m = a.mode;
 	const MbRate &rt = a.rate;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int N = MB_N, P = rt.P, CS = rt.c_slots;
-	float *s_lam = reinterpret_cast<float *>(smem_raw);  // posterior
-	float *s_lch = s_lam + MB_N;                         // channel LLR
-	float *s_R = s_lch + MB_N;                           // check -> variable message per check-side slot; s_R[CS] == 0 always
-	uint32_t *s_cgbase = reinterpret_cast<uint32_t *>(s_R + ((CS + 4) & ~3));
-	uint32_t *s_vgbase = s_cgbase + MB_MAX_GROUPS;
-	unsigned char *s_vgdeg = reinterpret_cast<unsigned char *>(s_vgbase + MB_MAX_GROUPS);
-	unsigned char *s_bytes = s_vgdeg + MB_MAX_GROUPS;
+	const int CS = rt.c_slots;
+	float *s_lam = reinterpret_cast<float *>(smem_raw + kOffLam);
+	float *s_lch = reinterpret_cast<float *>(smem_raw + kOffLch);
+	float *s_R = reinterpret_cast<float *>(smem_raw + kOffR);
+	uint32_t *s_csched = reinterpret_cast<uint32_t *>(smem_raw + kOffR + ((CS + 4) & ~3) * 4);  // [8][16] check-group descriptors per warp
+	uint32_t *s_vsched = s_csched + MB_LDPC_WARPS * MB_SCHED_LEN;                              // [8][16] variable-group descriptors per warp
+	unsigned char *s_bytes = reinterpret_cast<unsigned char *>(s_vsched + MB_LDPC_WARPS * MB_SCHED_LEN);
+
+	const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
 
 	const size_t frame = blockIdx.x;
-	const uint8_t *__restrict__ g_cdeg = a.blob + rt.off_cdeg;
-	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_var);
-	const uint8_t *__restrict__ g_vdeg = a.blob + rt.off_vdeg;
-	const uint16_t *__restrict__ g_vedge = reinterpret_cast<const uint16_t *>(a.blob + rt.off_vedge);
+	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);  // byte offsets into s_lam
+	const uint16_t *__restrict__ g_vedge = reinterpret_cast<const uint16_t *>(a.blob + rt.off_vedgeb);        // byte offsets into s_R
+	const uint32_t *__restrict__ g_vtail = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vtail);          // two byte offsets per degree-<=2 variable
 
 	MbRxStats st = a.stats[frame];
 	if (a.check_gate && !(st.mean_H >= 0.3f)) {
@@ -127,33 +139,34 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			s_lch[p] = v;
 		}
 		for (int i = tid; i <= CS; i += kThreads) s_R[i] = 0.f;
-		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);
-		const uint32_t *__restrict__ g_vgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vgbase);
-		if (tid < MB_MAX_GROUPS) {
-			s_cgbase[tid] = g_cgbase[tid];
-			s_vgbase[tid] = g_vgbase[tid];
-			s_vgdeg[tid] = (a.blob + rt.off_vgdeg)[tid];
+		if (tid < MB_LDPC_WARPS * MB_SCHED_LEN) {
+			s_csched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_csched)[tid];
+			s_vsched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vsched)[tid];
 		}
+		if (tid == 0) s_lam[MB_N] = __int_as_float(0x7f800000);  // +inf: a padding edge contributes s = 0, sign +, hard bit 0
 	}
 	__syncthreads();
 
-	const int n_cgroups = (P + 31) >> 5;
+	const int vtail0 = rt.vtail_start;
 	int iterations = 0;
 	for (int pass = 0;; pass++) {
 		// ---- check pass: syndrome of the current posterior + new check->variable messages ----------------
+		// A warp owns a group of 32 checks padded to one degree; padding slots point at the +inf variable, so the loops are
+		// warp-uniform (no per-thread degree, no divergence) and a padding edge is the neutral element of every reduction.
 		unsigned unsat = 0;
-		for (int g = warp; g < n_cgroups; g += kThreads / 32) {
-			const int c = (g << 5) + lane;
-			const int d = c < P ? (int)g_cdeg[c] : 0;
-			const int e0 = (int)s_cgbase[g] + lane;
+		const uint32_t *sched = s_csched + warp * MB_SCHED_LEN;
+		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check groups (static, degree-balanced schedule)
+			const int d = (int)((desc >> 16) & 0xFFu);
+			const int e0 = (int)(desc & 0xFFFFu) + lane;
 			float *__restrict__ Re = s_R + e0;
 			const uint16_t *__restrict__ ve = g_edge_var + e0;
 			unsigned hard = 0, par = 0;
 			if (ALGO == 0) {
 				float big = 0.f, rest = 0.f;  // largest term kept apart: rest = sum of all the others
 				int arg = -1;
+#pragma unroll 4
 				for (int k = 0; k < d; k++) {
-					const float lam = s_lam[ve[k * 32]];
+					const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
 					const float q = lam - Re[k * 32];
 					hard ^= __float_as_uint(lam);  // sign bit only is used
 					par ^= __float_as_uint(q);
@@ -167,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 				}
 				hard = (lam_sign_fix(hard));
 				const unsigned pneg = par & 0x80000000u;
+#pragma unroll 4
 				for (int k = 0; k < d; k++) {
 					const unsigned tb = __float_as_uint(Re[k * 32]);
 					const float so = k == arg ? rest : (rest - __uint_as_float(tb & 0x7fffffffu)) + big;
@@ -174,11 +188,13 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 					Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
 				}
 			} else {
+				const int c = (int)((desc >> 24) - 1u) * 32 + lane;
+				const int dc = c < rt.P ? (int)(a.blob + rt.off_cdeg)[c] : 0;  // the true degree picks the normalisation
 				float m1 = 3.0e38f, m2 = 3.0e38f;
 				int arg = -1;
 				unsigned long long signs = 0ull;
 				for (int k = 0; k < d; k++) {
-					const float lam = s_lam[ve[k * 32]];
+					const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
 					const float q = lam - Re[k * 32];
 					hard ^= __float_as_uint(lam);
 					par ^= __float_as_uint(q);
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 					m1 = lt1 ? aq : m1;
 				}
 				hard = (lam_sign_fix(hard));
-				const float alpha = d <= 2 ? 1.0f : (d == 3 ? 0.85f : 0.75f);
+				const float alpha = dc <= 2 ? 1.0f : (dc == 3 ? 0.85f : 0.75f);
 				const unsigned pneg = par >> 31;
 				for (int k = 0; k < d; k++) {
 					const float mag = fminf(alpha * (k == arg ? m2 : m1), kClampR);
@@ -211,31 +227,50 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			break;
 		}
 		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order) ----------
-		// N = 50 full groups; a group runs to its largest degree, shorter rows read the always-zero slot CS.
-		for (int g = warp; g < MB_N / 32; g += kThreads / 32) {
-			const int v = (g << 5) + lane;
-			const int d = s_vgdeg[g];  // even, warp-uniform
-			const uint16_t *__restrict__ se = g_vedge + (s_vgbase[g] + lane);
+		// Variables are numbered by descending degree.  The head (degree > 2) is walked in warp groups padded to one even
+		// degree (padding reads the always-zero slot); the long tail of degree-<=2 variables (the accumulator chain of the IRA
+		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.
+		sched = s_vsched + warp * MB_SCHED_LEN;
+		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
+			const int d = (int)((desc >> 16) & 0xFFu);
+			const int v = (int)((desc >> 24) - 1u) * 32 + lane;
+			const uint16_t *__restrict__ se = g_vedge + ((desc & 0xFFFFu) + lane);
 			float acc = s_lch[v];
+			int k = 0;
 #pragma unroll 1
-			for (int k = 0; k < d; k += 2) {
-				const unsigned i0 = se[0], i1 = se[32];
-				se += 64;
-				acc += s_R[i0];
-				acc += s_R[i1];
+			for (; k + 4 <= d; k += 4) {
+				const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
+				se += 128;
+				acc += lds_f(sbase, kOffR + i0);
+				acc += lds_f(sbase, kOffR + i1);
+				acc += lds_f(sbase, kOffR + i2);
+				acc += lds_f(sbase, kOffR + i3);
 			}
+			if (k < d) {
+				const unsigned i0 = se[0], i1 = se[32];
+				acc += lds_f(sbase, kOffR + i0);
+				acc += lds_f(sbase, kOffR + i1);
+			}
+			s_lam[v] = acc;
+		}
+		for (int v = vtail0 + tid; v < MB_N; v += kThreads) {
+			const uint32_t w = __ldg(g_vtail + (v - vtail0));
+			float acc = s_lch[v];
+			acc += lds_f(sbase, kOffR + (w & 0xFFFFu));
+			acc += lds_f(sbase, kOffR + (w >> 16));
 			s_lam[v] = acc;
 		}
 		__syncthreads();
 		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
-		if (n_unsat <= kCheapTestThreads) {
+		if (n_unsat <= a.cheap_test_threads) {
 			unsigned bad = 0;
-			for (int g = warp; g < n_cgroups; g += kThreads / 32) {
-				const int c = (g << 5) + lane;
-				const int d = c < P ? (int)g_cdeg[c] : 0;
-				const uint16_t *__restrict__ ve = g_edge_var + s_cgbase[g] + lane;
+			sched = s_csched + warp * MB_SCHED_LEN;
+			for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
+				const int d = (int)((desc >> 16) & 0xFFu);
+				const uint16_t *__restrict__ ve = g_edge_var + (desc & 0xFFFFu) + lane;
 				unsigned hard = 0;
-				for (int k = 0; k < d; k++) hard ^= __float_as_uint(s_lam[ve[k * 32]]);
+#pragma unroll 4
+				for (int k = 0; k < d; k++) hard ^= __float_as_uint(lds_f(sbase, kOffLam + ve[k * 32]));
 				bad |= hard >> 31;
 			}
 			if (__syncthreads_or((int)bad) == 0) {
@@ -290,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 
 size_t mb_ldpc_smem_bytes(int c_slots)
 {
-	return (size_t)(2 * MB_N + ((c_slots + 4) & ~3)) * sizeof(float) + 2 * MB_MAX_GROUPS * sizeof(uint32_t) + MB_MAX_GROUPS + 256;
+	return (size_t)kOffR + (size_t)((c_slots + 4) & ~3) * sizeof(float) + 2 * MB_LDPC_WARPS * MB_SCHED_LEN * sizeof(uint32_t) + 256;
 }
 
 cudaError_t mb_ldpc_init()

@@ -214,6 +214,49 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 		out.off_vgdeg = bl.put(vgdeg);
 	}
 	out.off_vedge = bl.put(vedge);
+	{
+		std::vector<uint16_t> evb(c_slots, 0), veb(v_slots, 0);
+		for (uint32_t i = 0; i < c_slots; i++) evb[i] = (uint16_t)((edge_var[i] == 0xFFFF ? (uint32_t)N : (uint32_t)edge_var[i]) * 4);
+		for (uint32_t i = 0; i < v_slots; i++) veb[i] = (uint16_t)(vedge[i] * 4);
+		if (c_slots * 4 > 0xFFFFu) return "LDPC slot byte offsets exceed 16 bits";
+		out.off_edge_varb = bl.put(evb);
+		out.off_vedgeb = bl.put(veb);
+		// tail of degree-<=2 variables (sorted by descending degree, so it is a suffix), from a multiple of 32
+		int tail = N;
+		while (tail > 0 && t.vrow[vsorted[tail - 1]].size() <= 2) tail--;
+		tail = (tail + 31) / 32 * 32;
+		out.vtail_start = tail;
+		std::vector<uint32_t> vtail((size_t)(N - tail), 0);
+		for (int i = tail; i < N; i++) {
+			uint32_t o[2] = {c_slots * 4u, c_slots * 4u};
+			for (size_t k = 0; k < t.vrow[vsorted[i]].size(); k++) o[k] = (uint32_t)vedge[vslot((int)k, i)] * 4u;
+			vtail[(size_t)(i - tail)] = o[0] | (o[1] << 16);
+		}
+		out.off_vtail = bl.put(vtail);
+		// longest-processing-time-first assignment of groups to warps; weight = padded degree of the group (+1 for its fixed cost)
+		auto schedule = [&](int n_groups, auto weight, auto base, uint32_t &off) -> bool {
+			std::vector<int> order(n_groups);
+			std::iota(order.begin(), order.end(), 0);
+			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+			std::vector<uint32_t> sched(MB_LDPC_WARPS * MB_SCHED_LEN, 0u);
+			int load[MB_LDPC_WARPS] = {0}, cnt[MB_LDPC_WARPS] = {0};
+			for (int g : order) {
+				int w = 0;
+				for (int i = 1; i < MB_LDPC_WARPS; i++)
+					if (load[i] < load[w]) w = i;
+				if (cnt[w] >= MB_SCHED_LEN - 1 || base(g) > 0xFFFFu || weight(g) > 255) return false;
+				sched[w * MB_SCHED_LEN + cnt[w]++] = base(g) | ((uint32_t)weight(g) << 16) | ((uint32_t)(g + 1) << 24);
+				load[w] += weight(g) + 1;
+			}
+			off = bl.put(sched);
+			return true;
+		};
+		if (!schedule((P + 31) / 32, [&](int g) { return (int)t.crow[csorted[g * 32]].size(); }, [&](int g) { return cgbase[g]; }, out.off_csched))
+			return "check schedule overflow";
+		if (!schedule(tail / 32, [&](int g) { return (int)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1); }, [&](int g) { return vgbase[g]; },
+			      out.off_vsched))
+			return "variable schedule overflow";
+	}
 	out.off_var_of_cw = bl.put(var_of_cw);
 	out.off_check_of_sorted = bl.put(check_of_sorted);
 	return "";

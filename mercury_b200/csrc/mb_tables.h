@@ -29,11 +29,13 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 10u
+#define MB_BLOB_VERSION 12u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
 #define MB_MAX_GROUPS 64  // warp-sized groups of checks / variables (<= 50 used)
+#define MB_LDPC_WARPS 8   // warps per decoder CTA (the group schedules below are built for this many)
+#define MB_SCHED_LEN 16   // groups per warp in a schedule, 0xFF terminated
 #define MB_ZF_STRIDE 27   // compact pilot row: 4 zeros | <= 17 pilots (columns s%3 + 3j at [4 + j]) | zeros
 #define MB_LS_COLS 18     // distinct clipped 21-column windows per row: start index (c + 4 - s%3) / 3 = 0..17
 // LLR hand-off layout between the two kernels: internal variable v sits at MB_HANDOFF(v): every 32-float row is rotated by
@@ -61,6 +63,15 @@ struct MbRate {
 	uint32_t off_var_of_cw; // u16[N]             codeword position -> internal variable index
 	uint32_t off_check_of_sorted; // u16[P]       sorted check c' -> reference check index (diagnostics, TX encoder)
 	uint32_t off_vgdeg;     // u8 [MB_MAX_GROUPS] padded degree (largest in the group, rounded up to even) of each group of 32 variables
+	// The decoder kernel's own tables: BYTE offsets into its shared-memory arrays (no index scaling per edge), padding that is
+	// the neutral element of every reduction (so the loops need no per-thread degree), and static schedules that balance the
+	// padded degrees of the groups over the CTA's warps (longest-processing-time first), so no warp idles at the barriers.
+	uint32_t off_edge_varb; // u16[c_slots]  4 * internal variable index of each check-side slot (padding: 4 * N, the +inf variable)
+	uint32_t off_vedgeb;    // u16[v_slots]  4 * check-side slot id held by each variable-side slot (padding: 4 * c_slots, an always-zero message)
+	uint32_t off_csched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check groups of each warp: first slot | padded degree << 16 | (group + 1) << 24; 0 ends
+	uint32_t off_vsched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] variable groups (degree > 2 part) of each warp, same packing
+	uint32_t off_vtail;     // u32[N - vtail_start] variables vtail_start.. (degree <= 2): byte offsets of their two messages, low | high << 16
+	int32_t vtail_start;    // multiple of 32
 };
 
 struct MbMode {

@@ -8,7 +8,8 @@ ZF_STRIDE, LS_COLS = 27, 18
 
 RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "max_cdeg", "max_vdeg", "c_slots", "v_slots", "reserved")] +
                    [(n, "<u4") for n in ("off_cdeg", "off_cgbase", "off_edge_var", "off_vdeg", "off_vgbase", "off_vedge",
-                                         "off_var_of_cw", "off_check_of_sorted", "off_vgdeg")])
+                                         "off_var_of_cw", "off_check_of_sorted", "off_vgdeg", "off_edge_varb", "off_vedgeb",
+                                         "off_csched", "off_vsched", "off_vtail")] + [("vtail_start", "<i4")])
 MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate_num", "Nsymb", "nData", "nPilots", "nBits",
                                          "nReal", "nVirtual", "K", "P", "frame_bytes", "estimator", "phase_only",
                                          "preamble_nSymb", "crc_bytes", "crc_chunk")] +
@@ -57,7 +58,10 @@ class Blob:
                  edge_var=self.arr(r["off_edge_var"], "<u2", r["c_slots"]), vdeg=self.arr(r["off_vdeg"], "u1", r["N"]),
                  vgbase=self.arr(r["off_vgbase"], "<u4", 64), vedge=self.arr(r["off_vedge"], "<u2", r["v_slots"]),
                  var_of_cw=self.arr(r["off_var_of_cw"], "<u2", r["N"]),
-                 check_of_sorted=self.arr(r["off_check_of_sorted"], "<u2", r["P"]), vgdeg=self.arr(r["off_vgdeg"], "u1", 64))
+                 check_of_sorted=self.arr(r["off_check_of_sorted"], "<u2", r["P"]), vgdeg=self.arr(r["off_vgdeg"], "u1", 64),
+                 edge_varb=self.arr(r["off_edge_varb"], "<u2", r["c_slots"]), vedgeb=self.arr(r["off_vedgeb"], "<u2", r["v_slots"]),
+                 csched=self.arr(r["off_csched"], "<u4", 8 * 16).reshape(8, 16), vsched=self.arr(r["off_vsched"], "<u4", 8 * 16).reshape(8, 16),
+                 vtail=self.arr(r["off_vtail"], "<u4", r["N"] - r["vtail_start"]))
         return d
 
     def twiddle(self):

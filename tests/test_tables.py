@@ -56,6 +56,23 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
     assert (r["edge_var"] != 0xFFFF).sum() == r["n_edges"] == (r["vedge"] != r["c_slots"]).sum()
     assert all(int(r["vgdeg"][g]) == (int(r["vdeg"][32 * g]) + 1) // 2 * 2 for g in range(50))
     assert r["c_slots"] <= 1.15 * r["n_edges"] and r["v_slots"] <= 1.25 * r["n_edges"]  # padding stays small
+    # the decoder kernel's byte-offset copies, neutral padding, degree-<=2 tail and static warp schedules
+    real = r["edge_var"] != 0xFFFF
+    assert np.array_equal(r["edge_varb"][real], r["edge_var"][real] * 4) and (r["edge_varb"][~real] == 4 * 1600).all()
+    assert np.array_equal(r["vedgeb"].astype(int), r["vedge"].astype(int) * 4)
+    t0 = r["vtail_start"]
+    assert t0 % 32 == 0 and (r["vdeg"][t0:] <= 2).all() and (t0 < 32 or r["vdeg"][t0 - 32] > 2)
+    for i, w in enumerate(r["vtail"].astype(int)):
+        offs = [int(r["vedge"][be.vslot(r, k, t0 + i)]) * 4 for k in range(int(r["vdeg"][t0 + i]))] + [4 * r["c_slots"]] * 2
+        assert (w & 0xFFFF, w >> 16) == (offs[0], offs[1])
+    for sched, n_groups, weight, base in ((r["csched"], (r["P"] + 31) // 32, lambda g: int(r["cdeg"][32 * g]), r["cgbase"]),
+                                          (r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"])):
+        ent = [int(e) for row in sched for e in row if e != 0]
+        assert sorted((e >> 24) - 1 for e in ent) == list(range(n_groups))     # every group exactly once
+        assert all(e & 0xFFFF == int(base[(e >> 24) - 1]) and (e >> 16) & 0xFF == weight((e >> 24) - 1) for e in ent)
+        assert all(row[-1] == 0 for row in sched)                              # terminated
+        loads = [sum(((int(e) >> 16) & 0xFF) + 1 for e in row if e != 0) for row in sched]
+        assert max(loads) - min(loads) <= max(weight(g) for g in range(n_groups)) + 1  # LPT balance
     for vi in range(1600):
         v = int(cw_of_var[vi])
         ref_row = [int(c) for c in lt["V"][v] if c != -1]
