@@ -235,7 +235,7 @@ def run_own(a):
     d_x, pl_all = synth_batch_on_device(a.config, B, esn0, dev, seed=0x4D455243 + rank, unique=U)
     d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
     d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
-    d_llr = torch.empty((B, 1600), dtype=torch.float32, device=dev)
+    d_llr = torch.empty((B, mb.HANDOFF_FLOATS), dtype=torch.float32, device=dev)  # stage hand-off records
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():

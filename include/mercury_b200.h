@@ -55,6 +55,8 @@ extern "C" {
 #define MERCURY_B200_NUM_CONFIGS 17    /* CONFIG_0 .. CONFIG_16 */
 #define MERCURY_B200_N 1600            /* LDPC block length, one codeword per OFDM frame */
 #define MERCURY_B200_NOFDM 272         /* samples per OFDM symbol at the decimated rate (Nfft 256 + GI 16) */
+#define MERCURY_B200_HANDOFF_FLOATS 2400 /* float32 per frame of the stage hand-off buffer between the two kernels:
+                                            1600 LLRs + (ZF modes) up to 400 equalised data symbols for the SNR report */
 
 typedef struct mercury_b200 mercury_b200_t;
 
@@ -75,7 +77,7 @@ typedef struct mercury_b200_rx_stats {
 	int32_t crc;             /* CRC16 over payload+crc bytes, 0 = good (telecom_system.cc:1337-1341) */
 	int32_t all_zeros;       /* telecom_system.cc:1319-1327 */
 	int32_t message_decoded; /* 1 = YES */
-	float SNR;               /* dB, -99.9 when not decoded (:1347,1368-1375); 0 for ZF modes (re-encode path not built) */
+	float SNR;               /* dB, -99.9 when not decoded (:1347,1368-1375); ZF modes: re-encode path (:1376-1400) */
 	float variance;          /* pilot noise variance used for the LLRs (:1291) */
 	float mean_H;            /* mean |H| over pilots after AGC (:1225-1244) */
 	int32_t reserved;
@@ -118,7 +120,8 @@ int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *baseband, si
 				    mercury_b200_rx_stats *stats, float *llr_cw);
 int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_payload,
 					   void *d_stats, void *d_llr_cw, void *stream);
-/* The two stages separately (device buffers). d_llr is n_frames x 1600 float32 in the decoder's internal order. */
+/* The two stages separately (device buffers). d_llr is the stage hand-off: n_frames x MERCURY_B200_HANDOFF_FLOATS float32
+ * (LLRs in the decoder's internal layout, then -- ZF modes only -- the equalised data symbols the decoder's SNR report needs). */
 int mercury_b200_demod_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_llr, void *d_stats,
 				    void *d_llr_cw, void *stream);
 int mercury_b200_ldpc_decode_batch_device(mercury_b200_t *h, const void *d_llr, size_t n_frames, void *d_payload, void *d_stats,

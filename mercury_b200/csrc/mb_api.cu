@@ -21,6 +21,7 @@ std::string mb_synth_frames(const std::vector<uint8_t> &blob, int config, size_t
 
 static_assert(sizeof(MbRxStats) == sizeof(mercury_b200_rx_stats), "stats record layout");
 static_assert(sizeof(MbRxStats) == 32, "stats record size");
+static_assert(MB_HANDOFF_STRIDE == MERCURY_B200_HANDOFF_FLOATS, "hand-off stride");
 
 namespace {
 constexpr int kSlots = 3;
@@ -155,7 +156,7 @@ int ensure_slot(mercury_b200_t *h, Slot &s, size_t frames, size_t x_bytes, bool 
 	cudaStreamSynchronize(s.stream);
 	free_slot(s);
 	MB_CUDA(h, cudaMalloc(&s.d_x, x_bytes));
-	MB_CUDA(h, cudaMalloc(&s.d_llr, frames * MB_N * sizeof(float)));
+	MB_CUDA(h, cudaMalloc(&s.d_llr, frames * MB_HANDOFF_STRIDE * sizeof(float)));
 	MB_CUDA(h, cudaMalloc(&s.d_payload, frames * 256));
 	MB_CUDA(h, cudaMalloc(&s.d_stats, frames * sizeof(MbRxStats)));
 	if (want_llr_cw) MB_CUDA(h, cudaMalloc(&s.d_llr_cw, frames * MB_N * sizeof(float)));
@@ -358,7 +359,7 @@ int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_x, s
 		if (h->d_scratch_llr) cudaFree(h->d_scratch_llr);
 		h->d_scratch_llr = nullptr;
 		h->scratch_frames = 0;
-		MB_CUDA(h, cudaMalloc(&h->d_scratch_llr, n * MB_N * sizeof(float)));
+		MB_CUDA(h, cudaMalloc(&h->d_scratch_llr, n * MB_HANDOFF_STRIDE * sizeof(float)));
 		h->scratch_frames = n;
 	}
 	cudaStream_t s = static_cast<cudaStream_t>(stream);

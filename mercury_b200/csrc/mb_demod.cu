@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	const float inv_var = fast_rcp(variance);
 
 	// ---------------- data cells in grid order: interpolate, equalise, de-map, scatter (a7-a9, a11-a14) --------------
+	float2 *__restrict__ zf_out = reinterpret_cast<float2 *>(a.llr + frame * (size_t)MB_HANDOFF_STRIDE + MB_N);
 	float2 c_reg[M <= 4 ? M : 1];  // BPSK / QPSK: the constellation lives in registers for the whole loop
 #pragma unroll
 	for (int j = 0; j < (M <= 4 ? M : 1); j++) c_reg[j] = s_cons[j];
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 			if (a.dbg_H) a.dbg_H[o] = heq;
 			if (a.dbg_Z) a.dbg_Z[o] = z;
 		}
+		if (!LS) zf_out[d] = z;  // ZF modes: the decoder's SNR report re-encodes the frame and needs the equalised data symbols (:1376-1400)
 		if (M <= 4)
 			demap_scatter<M, BPS>(z, inv_var, c_reg, dw, s_Lb);
 		else
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 
 	// ---------------- LLRs out (one bulk store, decoder order) and the demod half of the stats record ----------------
 	if (tid == 0) {
-		bulk_s2g(a.llr + frame * (size_t)MB_N, smem_u32(s_L), MB_N * 4);
+		bulk_s2g(a.llr + frame * (size_t)MB_HANDOFF_STRIDE, smem_u32(s_L), MB_N * 4);
 		MbRxStats st;
 		st.iterations_done = -1;
 		st.crc = 0;

@@ -5,6 +5,8 @@
 
 #include "mb_tables.h"
 
+#define MB_HANDOFF_STRIDE 2400  // floats per frame of the stage hand-off buffer (= MERCURY_B200_HANDOFF_FLOATS): 1600 LLRs + ZF-mode data symbols
+
 // Mirrors mercury_b200_rx_stats (include/mercury_b200.h); 32 bytes.
 struct MbRxStats {
 	int32_t iterations_done, crc, all_zeros, message_decoded;

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 
 	{
 		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores
-		const float *__restrict__ src = a.llr + frame * (size_t)MB_N;
+		const float *__restrict__ src = a.llr + frame * (size_t)MB_HANDOFF_STRIDE;
 		for (int i = tid; i < MB_N; i += kThreads) {
 			const float v = __ldcs(src + i);
 			const unsigned p = MB_HANDOFF_INV((unsigned)i);
@@ -316,6 +316,85 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			st.all_zeros = all_zeros;
 			st.message_decoded = decoded;
 			st.SNR = decoded ? st.SNR : -99.9f;
+			if (m.estimator == 1 || !decoded) a.stats[frame] = st;
+			s_bytes[255] = (unsigned char)decoded;
+		}
+	}
+	if (m.estimator == 1) return;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
+
+	// ---- ZF modes: SNR report of a decoded frame (telecom_system.cc:1376-1400) -----------------------------------------
+	// Re-encode the hard decisions (scrambled info bits, virtual copies, IRA parity), re-map them onto the constellation through
+	// the same composed interleaver records the demodulator scatters by, and measure the mean squared distance of the equalised
+	// data symbols (kept by the demodulator behind the LLRs of the hand-off record) to the re-encoded ones (ofdm.cc:1622-1635).
+	__syncthreads();
+	if (!s_bytes[255]) return;
+	uint32_t *s_bit = reinterpret_cast<uint32_t *>(smem_raw + kOffLch);          // [1600] re-encoded bit per internal variable (the channel LLRs are dead)
+	unsigned char *s_d = reinterpret_cast<unsigned char *>(smem_raw + kOffR);    // [P] data parity of every check, reference check order (the messages are dead)
+	const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + rt.off_var_of_cw);
+	const int K = m.K, P = rt.P, nReal = m.nReal, nVirtual = m.nVirtual;
+	for (int v = tid; v < MB_N; v += kThreads) s_bit[v] = 0u;  // parity variables stay 0 while the data parities are formed
+	__syncthreads();
+	for (int i = tid; i < nReal; i += kThreads) {  // hd_decoded_data_bit, scrambled back = the decoder's hard decisions (:1378)
+		const unsigned b = __float_as_uint(s_lam[g_voc[i]]) >> 31;
+		s_bit[g_voc[i]] = b;
+		if (i < nVirtual) s_bit[g_voc[nReal + i]] = b;  // virtual bits are copies of the first ones (:1380-1383)
+	}
+	__syncthreads();
+	{  // cl_ldpc::encode (ldpc.cc:111-132): every check row is {data bits, parity i-1, parity i}, so parity = running XOR of the data parities
+		const uint8_t *__restrict__ g_cdeg = a.blob + rt.off_cdeg;
+		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);
+		const uint16_t *__restrict__ g_cos = reinterpret_cast<const uint16_t *>(a.blob + rt.off_check_of_sorted);
+		for (int c = tid; c < P; c += kThreads) {
+			const uint16_t *__restrict__ ve = g_edge_var + g_cgbase[c >> 5] + (c & 31);
+			unsigned x = 0;
+			for (int k = 0; k < (int)g_cdeg[c]; k++) x ^= s_bit[ve[k * 32] >> 2];
+			s_d[g_cos[c]] = (unsigned char)x;
+		}
+	}
+	__syncthreads();
+	if (warp == 0) {
+		const int chunk = (P + 31) >> 5;
+		unsigned x = 0;
+		for (int i = lane * chunk; i < min(P, (lane + 1) * chunk); i++) x ^= s_d[i];
+		unsigned carry = x;  // inclusive XOR scan of the chunk parities over the lanes
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned y = __shfl_up_sync(0xffffffffu, carry, o);
+			if (lane >= o) carry ^= y;
+		}
+		unsigned run = carry ^ x;  // parity of everything before this lane's chunk
+		for (int i = lane * chunk; i < min(P, (lane + 1) * chunk); i++) {
+			run ^= s_d[i];
+			s_bit[g_voc[K + i]] = run;
+		}
+	}
+	__syncthreads();
+	{
+		const uint32_t *__restrict__ g_drec = reinterpret_cast<const uint32_t *>(a.blob + m.off_data_rec);
+		const float2 *__restrict__ g_cons = reinterpret_cast<const float2 *>(a.blob + m.off_const);
+		const float2 *__restrict__ zf = reinterpret_cast<const float2 *>(a.llr + frame * (size_t)MB_HANDOFF_STRIDE + MB_N);
+		const int bps = m.bps, rw = m.data_rec_words;
+		float acc = 0.f;
+		for (int d = tid; d < m.nData; d += kThreads) {
+			unsigned loc = 0;
+			for (int e = 0; e < bps; e++) {  // interleaver o psk.mod o interleaver (:1389-1391): bits MSB first
+				const uint32_t w = g_drec[d * rw + 1 + (e >> 1)];
+				const uint32_t off = (e & 1) ? (w >> 16) : (w & 0xFFFFu);
+				loc = (loc << 1) | s_bit[MB_HANDOFF_INV(off >> 2)];
+			}
+			const float2 c = g_cons[loc], z = zf[d];
+			acc += (c.x - z.x) * (c.x - z.x) + (c.y - z.y) * (c.y - z.y);
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		float *s_acc = reinterpret_cast<float *>(smem_raw + kOffLam);  // the posteriors are dead now
+		__syncthreads();
+		if (lane == 0) s_acc[warp] = acc;
+		__syncthreads();
+		if (tid == 0) {
+			float tot = 0.f;
+			for (int w = 0; w < kThreads / 32; w++) tot += s_acc[w];
+			st.SNR = -10.0f * log10f(tot / (float)m.nData);  // measure_SNR, ofdm.cc:1622-1635
 			a.stats[frame] = st;
 		}
 	}

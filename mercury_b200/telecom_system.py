@@ -19,6 +19,7 @@ from ._lib import Geometry, RxStats
 
 YES, NO = 1, 0
 DECODER_SPA, DECODER_MINSUM = 0, 1
+HANDOFF_FLOATS = 2400  # MERCURY_B200_HANDOFF_FLOATS: float32 per frame of the stage hand-off buffer between the two kernels
 
 STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("message_decoded", "<i4"),
                         ("SNR", "<f4"), ("variance", "<f4"), ("mean_H", "<f4"), ("reserved", "<i4")])

@@ -788,8 +788,35 @@ void mo_rx_tail(const mo_mode *m, const double complex *bb, mo_rx_out *o)
 				v = (float)(vv / (double)n2);
 			}
 			snr = 10.0 * log10(1.0 / v);
-		} else
-			snr = 0.0; /* ZF SNR (re-encode path, :1376-1400) is outside the exported record */
+		} else {
+			/* ZF: re-encode the decoded frame and measure the distance of the equalised data symbols to it
+			 * (telecom_system.cc:1376-1400; measure_SNR ofdm.cc:1622-1635) */
+			int hd[MO_N], enc[MO_N], il[MO_N];
+			double complex mod[MO_N], tf[MO_N];
+			for (int i = 0; i < m->nReal; i++) hd[i] = bits[i] ^ m->scrambler[i]; /* scramble back: bit_energy_dispersal is an XOR */
+			for (int i = 0; i < m->nVirtual; i++) hd[m->nReal + i] = hd[i];
+			mo_ldpc_encode(m, hd, enc);
+			for (int i = 0; i < m->P; i++) enc[m->nReal + i] = enc[i + m->K];
+			for (int i = 0; i < m->nBits; i++) il[il_src(i, m->nBits, m->bit_il_block)] = enc[i];
+			int b = m->bits_per_symbol;
+			for (int i = 0; i < m->nBits; i += b) {
+				unsigned loc = 0;
+				for (int j = 0; j < b; j++) loc = (loc << 1) | (unsigned)il[i + j];
+				mod[i / b] = m->constellation[loc];
+			}
+			for (int i = 0; i < m->nData; i++) tf[il_src(i, m->nData, m->tf_il_block)] = mod[i];
+			double complex *eq = Z;
+			if (m->phase_only) eq = Zna;
+			double vv = 0;
+			int di2 = 0;
+			for (int c = 0; c < cells; c++)
+				if (!m->is_pilot[c]) {
+					double complex d = tf[di2++] - eq[c];
+					vv += creal(d) * creal(d) + cimag(d) * cimag(d);
+				}
+			vv /= (double)m->nData;
+			snr = -10.0 * log10(vv);
+		}
 	}
 	if (o->stats) {
 		o->stats[0] = iterations;

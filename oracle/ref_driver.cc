@@ -347,7 +347,19 @@ void mref_rx_tail(void *h, const double *baseband, mref_rx_out *o)
 		if (ofdm.channel_estimator_amplitude_restoration == YES) v = ofdm.measure_variance(dc.equalized_data_without_amplitude_restoration);
 		snr = 10.0 * log10(1.0 / v);
 	} else {
-		snr = 0.0; /* ZF: the reference re-encodes the frame for its SNR report (:1376-1400); not exported */
+		/* ZF: the reference re-encodes the decoded frame and measures the distance of the equalised data symbols to it
+		 * (telecom_system.cc:1376-1400), with the reference's own functions in the reference's order */
+		bit_energy_dispersal(dc.hd_decoded_data_bit, dc.bit_energy_dispersal_sequence, dc.hd_decoded_data_bit, nReal);
+		for (int i = 0; i < nVirtual; i++) dc.hd_decoded_data_bit[nReal + i] = dc.hd_decoded_data_bit[i];
+		ts.ldpc.encode(dc.hd_decoded_data_bit, dc.encoded_data);
+		for (int i = 0; i < ts.ldpc.P; i++) dc.encoded_data[nReal + i] = dc.encoded_data[i + ts.ldpc.K];
+		interleaver(dc.encoded_data, dc.bit_interleaved_data, dc.nBits, ts.bit_interleaver_block_size);
+		ts.psk.mod(dc.bit_interleaved_data, dc.nBits, dc.modulated_data);
+		interleaver(dc.modulated_data, dc.ofdm_time_freq_interleaved_data, dc.nData, ts.time_freq_interleaver_block_size);
+		if (ofdm.channel_estimator_amplitude_restoration == YES)
+			snr = ofdm.measure_SNR(dc.ofdm_deframed_data_without_amplitude_restoration, dc.ofdm_time_freq_interleaved_data, dc.nData);
+		else
+			snr = ofdm.measure_SNR(dc.ofdm_deframed_data, dc.ofdm_time_freq_interleaved_data, dc.nData);
 	}
 	if (o->stats) {
 		o->stats[0] = iterations;

@@ -34,7 +34,7 @@ def run_one(ts, cfg, B, iters, esn0, steps, sample, decoder="spa"):
     d_x, pl = bench.synth_batch_on_device(cfg, B, esn0, dev, seed=1000 + cfg)
     d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
     d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
-    d_llr = torch.empty((B, 1600), dtype=torch.float32, device=dev)
+    d_llr = torch.empty((B, mb.HANDOFF_FLOATS), dtype=torch.float32, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     td = tl = 0.0
