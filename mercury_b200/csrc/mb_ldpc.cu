@@ -38,6 +38,7 @@ constexpr float kLn2 = 0.69314718055994531f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
 constexpr float kTanhOne2 = 5.5511151231257827e-17f * kLog2e; // s (base-2 units) below which tanh(|q|/2) == 1.0 in double
+constexpr float kSatQ = 38.123095f;                          // |q| above which tanh(|q|/2) == 1.0 in double (the same boundary as kTanhOne2)
 constexpr float kSMax2 = 115.0f;                             // s of |q| -> 0 (base-2 units; ~80 nats)
 constexpr float kTiny2 = 0.015625f * kLog2e;                 // below this S, 1 - 2^-S would cancel: use log2(2/(S ln2))
 
@@ -66,6 +67,15 @@ __device__ __forceinline__ float phi_bwd(float S)
 	const float num = tiny ? 2.0f * kLog2e : 1.0f + e;
 	const float den = tiny ? S : 1.0f - e;
 	return kLn2 * __log2f(__fdividef(num, den));
+}
+
+// x > 0 ? a : b as an opaque select: phi_bwd is evaluated unconditionally (its inf/NaN at x <= 0 is discarded), which is cheaper
+// than the divergent branch the compiler would otherwise wrap around the three MUFU operations
+__device__ __forceinline__ float sel_gt0(float x, float a, float b)
+{
+	float r;
+	asm("{\n\t.reg .pred p;\n\tsetp.gt.ftz.f32 p, %1, 0f00000000;\n\tselp.f32 %0, %2, %3, p;\n\t}" : "=f"(r) : "f"(x), "f"(a), "f"(b));
+	return r;
 }
 
 // parity of the hard decisions accumulated as XOR of raw sign bits -> 0/1
@@ -161,7 +171,16 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			float *__restrict__ Re = s_R + e0;
 			const uint16_t *__restrict__ ve = g_edge_var + e0;
 			unsigned hard = 0, par = 0;
-			if (ALGO == 0) {
+			if (ALGO == 0 && d == 2) {
+				// Degree-2 check (two thirds of the checks of the low-rate codes): R_a = 2 atanh(tanh(q_b / 2)) is q_b itself until tanh
+				// rounds to 1.0 in double (|q| > 37.43), where the reference's clamp gives 2 atanh(0.9999999) (ldpc_decoder_SPA.cc:147-155).
+				// A padding edge (q = +inf) saturates to the clamp: exactly the reference's empty product of a degree-1 check.
+				const float l0 = lds_f(sbase, kOffLam + ve[0]), l1 = lds_f(sbase, kOffLam + ve[32]);
+				const float q0 = l0 - Re[0], q1 = l1 - Re[32];
+				hard = lam_sign_fix(__float_as_uint(l0) ^ __float_as_uint(l1));
+				Re[0] = fabsf(q1) > kSatQ ? copysignf(kClampR, q1) : q1;
+				Re[32] = fabsf(q0) > kSatQ ? copysignf(kClampR, q0) : q0;
+			} else if (ALGO == 0) {
 				float big = 0.f, rest = 0.f;  // largest term kept apart: rest = sum of all the others
 				int arg = -1;
 #pragma unroll 4
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 				for (int k = 0; k < d; k++) {
 					const unsigned tb = __float_as_uint(Re[k * 32]);
 					const float so = k == arg ? rest : (rest - __uint_as_float(tb & 0x7fffffffu)) + big;
-					const float mag = so > 0.f ? phi_bwd(so) : kClampR;
+					const float mag = sel_gt0(so, phi_bwd(so), kClampR);  // all-saturated product -> 2 atanh(0.9999999)
 					Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
 				}
 			} else {
