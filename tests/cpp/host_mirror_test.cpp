@@ -1,0 +1,48 @@
+// Exercises include/mercury_b200.hpp (the C++ mirror of cl_telecom_system for the RX tail) the way reference code would:
+// construct, load_configuration, receive_byte / receive_bit on one synchronised frame, print what the reference prints.
+//   usage: host_mirror_test <ldpc_tables.bin> <config> <ldpc iterations> <frame.bin: Nsymb*272 complex<double>>
+// Exit codes: 0 ok, 2 usage / IO, 3 no usable device (the library has no CPU fallback and says so).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "mercury_b200.hpp"
+
+int main(int argc, char **argv)
+{
+	if (argc != 5) {
+		fprintf(stderr, "usage: %s ldpc_tables.bin config iterations frame.bin\n", argv[0]);
+		return 2;
+	}
+	try {
+		mb200::cl_telecom_system telecom_system(0, argv[1]);
+		telecom_system.default_configurations_telecom_system.ldpc_nIteration_max = atoi(argv[3]);
+		telecom_system.load_configuration(atoi(argv[2]));
+		const size_t n = (size_t)telecom_system.data_container.Nsymb * telecom_system.data_container.Nofdm;
+		std::vector<std::complex<double>> baseband_data(n);
+		FILE *f = fopen(argv[4], "rb");
+		if (!f || fread(baseband_data.data(), sizeof(std::complex<double>), n, f) != n) {
+			fprintf(stderr, "cannot read %zu samples from %s\n", n, argv[4]);
+			return 2;
+		}
+		fclose(f);
+		std::vector<int> out((size_t)telecom_system.get_frame_size_bytes());
+		mb200::st_receive_stats st = telecom_system.receive_byte(baseband_data.data(), out.data());
+		printf("decoded %d iterations %d crc %d all_zeros %d snr %.6f frame_bytes %d frame_bits %d\n", st.message_decoded, st.iterations_done,
+		       st.crc, st.all_zeros, st.SNR, telecom_system.get_frame_size_bytes(), telecom_system.get_frame_size_bits());
+		printf("bytes");
+		for (int v : out) printf(" %d", v);
+		printf("\n");
+		std::vector<int> bits((size_t)(telecom_system.data_container.nBits - telecom_system.ldpc.P) / 8 * 8);
+		telecom_system.receive_bit(baseband_data.data(), bits.data());
+		printf("bits");
+		for (int v : bits) printf(" %d", v);
+		printf("\n");
+		telecom_system.load_configuration(99);  // ignored, like the reference (telecom_system.cc:2494-2497)
+		printf("after_bad_config frame_bytes %d\n", telecom_system.get_frame_size_bytes());
+	} catch (const std::exception &e) {
+		fprintf(stderr, "mercury_b200: %s\n", e.what());
+		return 3;
+	}
+	return 0;
+}
