@@ -23,6 +23,8 @@
  *   mercury_b200_demod_batch_device      symbol_demod .. psk.demod .. LLR expand   (telecom_system.cc:1135-1308)
  *   mercury_b200_ldpc_decode_batch_device    ldpc.decode .. CRC16                  (telecom_system.cc:1310-1349)
  *   mercury_b200_rx_stats                st_receive_stats (telecom_system.h:63-82), the fields the tail writes
+ *   mercury_b200_batcher_*               (new) many concurrent links' receive calls -> one GPU batch; replaces the one-frame-per-call
+ *                                        pattern of arq_common.cc:2619-2668 / audioio.c:999-1069 for a multi-link gateway
  *   mercury_b200_synth_frames            (test/bench input synthesis) transmit_byte bit chain + the baseband
  *                                        modulation chain of baseband_test_EsN0 (telecom_system.cc:342-416,129-153)
  *
@@ -144,6 +146,26 @@ void mercury_b200_device_free(mercury_b200_t *h, void *p);
 int mercury_b200_memcpy_h2d(mercury_b200_t *h, void *dst, const void *src, size_t bytes);
 int mercury_b200_memcpy_d2h(mercury_b200_t *h, void *dst, const void *src, size_t bytes);
 int mercury_b200_synchronize(mercury_b200_t *h);
+
+/*
+ * Multi-link batcher.  In the reference every link decodes one frame per receive_byte() call on its own
+ * thread (arq_common.cc:2619-2668; the capture thread feeds it under capture_prep_mutex, audioio.c:999-1069).  A gateway that
+ * terminates many links has thousands of such calls in flight: the batcher keeps each call synchronous and per frame (same
+ * contract as mercury_b200_receive_baseband, float samples) and turns the concurrency into GPU batch size.  A batch is closed
+ * when max_batch frames are waiting or when its oldest frame has waited max_wait_us.  Thread safe; bound to the configuration
+ * selected on `h` when it is created (do not call load_configuration on `h` while a batcher is alive).
+ */
+typedef struct mercury_b200_batcher mercury_b200_batcher_t;
+int mercury_b200_batcher_create(mercury_b200_t *h, size_t max_batch, unsigned max_wait_us, mercury_b200_batcher_t **out);
+int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float *baseband /* Nsymb x 272 x (re,im) */, uint8_t *payload,
+					  mercury_b200_rx_stats *stats);
+int mercury_b200_batcher_get_counters(mercury_b200_batcher_t *b, uint64_t *batches, uint64_t *frames, uint64_t *full_batches);
+void mercury_b200_batcher_destroy(mercury_b200_batcher_t *b);
+/* Test hook: the same batching machinery in front of a caller-supplied batch function (plain host memory), so that the
+ * concurrency logic can be exercised on a machine without a GPU.  Not a CPU decode path: the function is the test's. */
+int mercury_b200_batcher_create_with_backend(size_t frame_floats, size_t frame_bytes, size_t max_batch, unsigned max_wait_us,
+					     int (*run)(void *ctx, const float *x, size_t n, uint8_t *payload, mercury_b200_rx_stats *stats),
+					     void *ctx, mercury_b200_batcher_t **out);
 
 /* Number of kernels this library has launched through this handle (bench.py's gpu_launches). */
 uint64_t mercury_b200_kernel_launches(const mercury_b200_t *h);

@@ -76,6 +76,11 @@ def lib():
         "mercury_b200_memcpy_d2h": (i32, [vp, vp, vp, sz]),
         "mercury_b200_synchronize": (i32, [vp]),
         "mercury_b200_kernel_launches": (u64, [vp]),
+        "mercury_b200_batcher_create": (i32, [vp, sz, C.c_uint, C.POINTER(vp)]),
+        "mercury_b200_batcher_receive_baseband": (i32, [vp, vp, vp, C.POINTER(RxStats)]),
+        "mercury_b200_batcher_get_counters": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "mercury_b200_batcher_destroy": (None, [vp]),
+        "mercury_b200_batcher_create_with_backend": (i32, [sz, sz, sz, C.c_uint, vp, vp, C.POINTER(vp)]),
         "mercury_b200_synth_frames": (i32, [C.c_char_p, i32, sz, u64, C.c_double, vp, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
