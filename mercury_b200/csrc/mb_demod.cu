@@ -288,15 +288,16 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		// each, 15 roundings at most: ~1e-6 relative) instead of 15 table reads per round -- the shared-memory / L1 data pipe
 		// is this kernel's busiest unit, the FMA pipe is not.  The table's 1/256 (ofdm.cc:439-442) moves to the 4 outputs.
 		const float2 w1 = cscale(__ldg(reinterpret_cast<const float2 *>(a.blob + a.off_twiddle) + 16 + t), 256.0f);
-		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * MB_NOFDM + MB_NGI + t;
+		const size_t stride = (size_t)a.sym_stride;
+		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * stride + a.sym_skip + t;
 		if (NCH > 1 && active) {  // later rounds: one 128-byte line per thread into L2 while round 0 is in flight
-			const char *line = reinterpret_cast<const char *>(a.x + (frame * S + (size_t)grp) * MB_NOFDM + MB_NGI) + t * 128;
+			const char *line = reinterpret_cast<const char *>(a.x + (frame * S + (size_t)grp) * stride + a.sym_skip) + t * 128;
 #pragma unroll
 			for (int ch = 1; ch < NCH; ch++)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(line + (size_t)ch * SC * MB_NOFDM * 8));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(line + (size_t)ch * SC * stride * 8));
 		}
 #pragma unroll 1
-		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * MB_NOFDM) {
+		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * stride) {
 			float2 v[16];
 			if (active) {
 #pragma unroll

@@ -15,7 +15,9 @@ struct MbRxStats {
 };
 
 struct MbDemodArgs {
-	const float2 *x;       // [B][Nsymb][272] complex64 baseband, preamble stripped
+	const float2 *x;       // [B][Nsymb][sym_stride] complex64 baseband, preamble stripped; the 256 useful samples start at sym_skip
+	int32_t sym_stride;    // 272 = symbols as delivered (guard interval present, skipped: sym_skip 16); 256 = guard interval already removed
+	int32_t sym_skip;
 	float *llr;            // [B][1600] LLRs in the hand-off layout (internal variable order, 32-float rows rotated: MB_HANDOFF)
 	float *llr_cw;         // optional [B][1600] LLRs in codeword order (parity output)
 	MbRxStats *stats;      // [B]
