@@ -39,13 +39,11 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
 constexpr float kTanhOne2 = 5.5511151231257827e-17f * kLog2e; // s (base-2 units) below which tanh(|q|/2) == 1.0 in double
 constexpr float kSatQ = 38.123095f;                          // |q| above which tanh(|q|/2) == 1.0 in double (the same boundary as kTanhOne2)
-constexpr float kSMax2 = 115.0f;                             // s of |q| -> 0 (base-2 units; ~80 nats)
 constexpr float kTiny2 = 0.015625f * kLog2e;                 // below this S, 1 - 2^-S would cancel: use log2(2/(S ln2))
 
 // Forward map, x = |q| (nats) -> s = -log2 tanh(x/2) = log2((1+e)/(1-e)), e = exp(-x).
 //   e < 0.1 : odd series (2/ln2) e (1 + e^2/3 + e^4/5), rel. error < 2e-7  (the logarithm's argument would round to 1)
-//   else    : log2((1+e)/(1-e)).  As x -> 0 the result saturates near 24 instead of growing without bound, which only
-//             says "this edge carries no information" slightly less emphatically (see kSMax2).
+//   else    : log2((1+e)/(1-e)); x == 0 gives +inf ("this edge carries no information"), which the check node handles as such.
 __device__ __forceinline__ float phi_fwd(float x)
 {
 	const float e = exp2f(-x * kLog2e);  // ex2.approx.ftz under -ftz=true
@@ -181,20 +179,21 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 				Re[0] = fabsf(q1) > kSatQ ? copysignf(kClampR, q1) : q1;
 				Re[32] = fabsf(q0) > kSatQ ? copysignf(kClampR, q0) : q0;
 			} else if (ALGO == 0) {
-				float big = 0.f, rest = 0.f;  // largest term kept apart: rest = sum of all the others
-				int arg = -1;
+				// Leave-one-out sums without cancellation: the largest term is kept apart (big) and rest = sum of all the others, by a
+				// running (min, max) pair -- no index tracking: the edge that owns the largest term is recognised by value in the second
+				// loop (ties are harmless: each tied edge's leave-one-out sum is the same `rest`).  s = +inf (q == 0) needs no clamp:
+				// it parks in `big`, every other edge then sees inf -> message 0, and two of them make rest = inf -> all messages 0.
+				float big = 0.f, rest = 0.f;
 #pragma unroll 4
 				for (int k = 0; k < d; k++) {
 					const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
 					const float q = lam - Re[k * 32];
 					hard ^= __float_as_uint(lam);  // sign bit only is used
 					par ^= __float_as_uint(q);
-					float s = fminf(phi_fwd(fabsf(q)), kSMax2);
+					float s = phi_fwd(fabsf(q));
 					s = s < kTanhOne2 ? 0.f : s;
-					const bool bigger = s > big;
-					rest += bigger ? big : s;
-					arg = bigger ? k : arg;
-					big = bigger ? s : big;
+					rest += fminf(s, big);
+					big = fmaxf(s, big);
 					Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
 				}
 				hard = (lam_sign_fix(hard));
@@ -202,7 +201,8 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 #pragma unroll 4
 				for (int k = 0; k < d; k++) {
 					const unsigned tb = __float_as_uint(Re[k * 32]);
-					const float so = k == arg ? rest : (rest - __uint_as_float(tb & 0x7fffffffu)) + big;
+					const float sk = __uint_as_float(tb & 0x7fffffffu);
+					const float so = sk == big ? rest : (rest - sk) + big;
 					const float mag = sel_gt0(so, phi_bwd(so), kClampR);  // all-saturated product -> 2 atanh(0.9999999)
 					Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
 				}
