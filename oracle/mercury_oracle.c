@@ -291,6 +291,7 @@ int mo_mode_init(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_p
 	build_fft_tables(m);
 	mo_srandom(0);				   /* telecom_system.cc:1961-1966 */
 	for (int i = 0; i < m->N; i++) m->scrambler[i] = mo_random() % 2;
+	mo_frontend_init(m);
 	return load_ldpc(m, ldpc_blob_path);
 }
 
@@ -325,7 +326,7 @@ void mo_geometry(const mo_mode *m, int *g)
 {
 	int v[28] = {m->Nsymb, m->Nc, m->Nfft, m->Ngi, m->Nofdm, m->nData, m->nPilots, m->nBits, m->N, m->K, m->P, m->M,
 		     m->preamble_nSymb, m->frame_bytes, m->estimator, m->phase_only, m->bit_il_block, m->tf_il_block,
-		     4, 0, 0, m->Cwidth, m->Vwidth, 0, m->ldpc_iters, 16, m->ls_window, m->ls_window};
+		     4, m->fe.buffer_Nsymb, (m->Nsymb + m->preamble_nSymb) * m->Nofdm * 4, m->Cwidth, m->Vwidth, 0, m->ldpc_iters, 16, m->ls_window, m->ls_window};
 	memcpy(g, v, sizeof(v));
 }
 
@@ -844,6 +845,408 @@ double mo_rx_tail_timed(const mo_mode *m, const double complex *bb, int n_frames
 		mo_rx_tail(m, bb + f * stride, &o);
 		if (decoded) decoded[f] = (int)st[3];
 		if (iterations) iterations[f] = (int)st[0];
+	}
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ================================================================================================
+ * RX FRONT-END: everything receive_byte() does before the tail, and the trial loop
+ * around it.  source/physical_layer/telecom_system.cc:646-1131 and 1343-1518, OFDM branch only
+ * (M != MOD_MFSK, mfsk_fixed_delay < 0, g_gui_state.coarse_freq_sync_enabled == false: the compiled
+ * defaults, gui_state.h:143).  Operation order follows the reference so the results are bit-identical
+ * to oracle/_ref compiled by the same gcc (tests/test_oracle_frontend.py).
+ * ============================================================================================== */
+
+/* cl_FIR::design, LPF + HAMMING: source/physical_layer/fir_filter.cc:45-163. */
+static void fir_design_lpf_hamming(double fcut, double tbw, double fs, int *ntaps_out, double *c)
+{
+	int n = (int)(4.0 / (tbw / (fs / 2.0)));
+	if (n % 2 == 0) n++;
+	double Ts = 1.0 / (fs);
+	double temp;
+	c[n / 2] = 1;
+	for (int i = 0; i < n / 2; i++) {
+		temp = 2 * M_PI * fcut * (double)(n / 2 - i) * Ts;
+		c[i] = sin(temp) / temp;
+		c[n - i - 1] = c[i];
+	}
+	temp = 0;
+	for (int i = 0; i < n; i++) temp += c[i];
+	for (int i = 0; i < n; i++) c[i] /= temp;
+	for (int i = 0; i < n; i++) c[i] *= 0.54 - 0.46 * cos(2.0 * M_PI * (double)i / (n - 1));
+	*ntaps_out = n;
+}
+
+/* Front-end constants: physical_config.cc:59,79-101; telecom_system.cc:69 (carrier_amplitude), data_container.cc:133-143 (buffer_Nsymb). */
+void mo_frontend_init(mo_mode *m)
+{
+	mo_frontend *f = &m->fe;
+	f->interp = 4;
+	f->fs = 48000.0;
+	f->bandwidth = 48000.0 * 50.0 / 256 / 4;
+	f->fc = 0.0 + (f->bandwidth / 2 + 300);
+	f->amp = sqrt(2.0);
+	f->trials_max = 2;
+	f->use_last_time = 1;
+	f->use_last_freq = 1;
+	f->ignore_limit = (double)0.1f; /* stored in a float (ofdm.h) */
+	fir_design_lpf_hamming(0.9 * f->bandwidth / 2, 3000, f->fs, &f->ntaps_ts, f->c_ts);
+	fir_design_lpf_hamming(1.0 * f->bandwidth / 2, 3000, f->fs, &f->ntaps_data, f->c_data);
+	double sym_time_ms = 1000.0 * m->Nofdm * f->interp / 48000.0;
+	int turnaround_symb = (int)ceil(1200.0 / sym_time_ms) + 4;
+	int frame_symb = m->preamble_nSymb + m->Nsymb;
+	int min_buf = frame_symb * 2;
+	if (frame_symb + turnaround_symb > min_buf) min_buf = frame_symb + turnaround_symb;
+	if (min_buf < 32) min_buf = 32;
+	f->buffer_Nsymb = min_buf;
+}
+
+void mo_frontend_tables(const mo_mode *m, int *ntaps, double *ts_coef, double *data_coef, double *consts)
+{
+	const mo_frontend *f = &m->fe;
+	ntaps[0] = f->ntaps_ts;
+	ntaps[1] = f->ntaps_data;
+	memcpy(ts_coef, f->c_ts, sizeof(double) * f->ntaps_ts);
+	memcpy(data_coef, f->c_data, sizeof(double) * f->ntaps_data);
+	double v[8] = {f->fs, f->fc, f->amp, f->bandwidth, f->trials_max, f->use_last_time, f->use_last_freq, f->ignore_limit};
+	memcpy(consts, v, sizeof(v));
+}
+
+/* cl_FIR::apply(complex): fir_filter.cc:164-187 (zero-phase: output delayed by (nTaps-1)/2 is dropped). */
+static void fir_apply(const double *c, int nt, const double complex *in, double complex *out, int n)
+{
+	for (int i = 0; i < n + nt - 1; i++) {
+		double ar = 0, ai = 0;
+		for (int j = 0; j < nt; j++)
+			if ((i - j) >= 0 && (i - j) < n) {
+				ar += creal(in[i - j]) * c[j];
+				ai += cimag(in[i - j]) * c[j];
+			}
+		if (i >= (nt - 1) / 2 && i < n + (nt - 1) / 2) out[i - (nt - 1) / 2] = ar + ai * I;
+	}
+}
+
+/* cl_ofdm::passband_to_baseband with decimation_rate 1: ofdm.cc:2316-2339. */
+static void p2b(const mo_mode *m, const double *in, int n, double complex *out, double fc, int data_filter, double complex *scratch)
+{
+	const mo_frontend *f = &m->fe;
+	double Ts = 1.0 / f->fs;
+	for (int i = 0; i < n; i++) {
+		double re = in[i] * f->amp * cos(2 * M_PI * fc * (double)i * Ts);
+		double im = in[i] * f->amp * sin(2 * M_PI * fc * (double)i * Ts);
+		scratch[i] = re + im * I;
+	}
+	if (data_filter) fir_apply(f->c_data, f->ntaps_data, scratch, out, n);
+	else fir_apply(f->c_ts, f->ntaps_ts, scratch, out, n);
+}
+
+/* cl_ofdm::time_sync_preamble_with_metric / time_sync_preamble: ofdm.cc:1846-1967 / 1735-1845 (Schmidl-Cox self-correlation of
+ * GI vs symbol tail and of the two symbol halves over the preamble, then the reference's partial selection "sort"). */
+static int time_sync(const mo_mode *m, const double complex *in, int size, int rate, int location_to_return, int step,
+		     int nTrials_max, double *corr_out, int *loc, double *vals)
+{
+	int pre = m->preamble_nSymb, S = (MO_NGI + MO_NFFT) * rate;
+	for (int i = 0; i < size; i++) {
+		loc[i] = -1;
+		vals[i] = 0;
+	}
+	for (int i = 0; i < size - pre * S; i += step) {
+		const double complex *data = in + i;
+		double cc = 0, na = 0, nb = 0;
+		for (int l = 0; l < pre; l++) {
+			const double complex *a = data + l * S, *b = data + l * S + MO_NFFT * rate;
+			for (int q = 0; q < MO_NGI * rate; q++) {
+				cc += creal(a[q]) * creal(b[q]);
+				na += creal(a[q]) * creal(a[q]);
+				nb += creal(b[q]) * creal(b[q]);
+				cc += cimag(a[q]) * cimag(b[q]);
+				na += cimag(a[q]) * cimag(a[q]);
+				nb += cimag(b[q]) * cimag(b[q]);
+			}
+			a = data + l * S + MO_NGI * rate;
+			b = data + l * S + (MO_NGI + MO_NFFT / 2) * rate;
+			for (int q = 0; q < (MO_NFFT / 2) * rate; q++) {
+				cc += creal(a[q]) * creal(b[q]);
+				na += creal(a[q]) * creal(a[q]);
+				nb += creal(b[q]) * creal(b[q]);
+				cc += cimag(a[q]) * cimag(b[q]);
+				na += cimag(a[q]) * cimag(a[q]);
+				nb += cimag(b[q]) * cimag(b[q]);
+			}
+		}
+		if (na < 0.001 || nb < 0.001) cc = 0.0;
+		else cc = cc / sqrt(na * nb);
+		vals[i] = cc;
+		loc[i] = i;
+	}
+	if (location_to_return >= nTrials_max) location_to_return = nTrials_max - 1;
+	for (int j = 0; j < nTrials_max; j++) {
+		loc[j] = j;
+		for (int i = j + 1; i < size; i++)
+			if (vals[i] > vals[j]) {
+				vals[j] = vals[i];
+				loc[j] = i;
+			}
+	}
+	if (corr_out) *corr_out = vals[location_to_return];
+	return loc[location_to_return];
+}
+
+/* mean energy of one passband-rate symbol starting at `pos` (the gates of telecom_system.cc:741-753,768-776,818-826,...) */
+static double sym_energy(const double complex *bbi, int pos, int sym_samples, int buf_samples)
+{
+	double e = 0;
+	int cnt = 0;
+	for (int i = 0; i < sym_samples && (pos + i) < buf_samples; i++) {
+		double re = creal(bbi[pos + i]), im = cimag(bbi[pos + i]);
+		e += re * re + im * im;
+		cnt++;
+	}
+	return (cnt > 0) ? e / cnt : 0.0;
+}
+
+/* cl_ofdm::carrier_sampling_frequency_sync (Moose): ofdm.cc:540-595. */
+static double moose(const mo_mode *m, const double complex *in, double carrier_width, int pre)
+{
+	double complex frame[MO_NFFT], d1[MO_NC], d2[MO_NC], mul = 0;
+	pre = (pre / 2 == 0) ? 1 : pre / 2;
+	for (int j = 0; j < pre; j++) {
+		for (int h = 0; h < 2; h++) {
+			for (int i = 0; i < MO_NFFT / 2; i++) {
+				frame[i] = in[j * MO_NOFDM + i + h * MO_NFFT / 2];
+				frame[i + MO_NFFT / 2] = in[j * MO_NOFDM + i + h * MO_NFFT / 2];
+			}
+			fft_core(m, frame, 0);
+			for (int i = 0; i < MO_NFFT; i++) frame[i] = frame[i] / (double)MO_NFFT;
+			double complex *d = h ? d2 : d1;
+			for (int i = 0; i < MO_NC / 2; i++) d[i] = frame[i + MO_NFFT - MO_NC / 2];
+			for (int i = MO_NC / 2; i < MO_NC; i++) d[i] = frame[i - MO_NC / 2 + 1];
+		}
+		for (int i = 0; i < MO_NC; i++) mul += conj(d2[i]) * d1[i];
+	}
+	return (get_angle(mul) / M_PI) * carrier_width;
+}
+
+/*
+ * cl_telecom_system::receive_byte, OFDM branch: telecom_system.cc:646-1518.
+ *   passband : Nofdm*buffer_Nsymb*4 doubles;  out : frame_bytes ints
+ *   stats[12]: iterations, crc, all_zeros, decoded, SNR, delay, sync_trials, freq_offset, coarse_metric, signal_stregth_dbm,
+ *              buffer samples, frame_bytes;  state[2] in/out: delay_of_last_decoded_message, freq_offset_of_last_decoded_message
+ *   baseband_out (optional): the (pre+Nsymb)*272 post-synchronisation samples the last trial's tail consumed.
+ */
+void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats, double *state, double complex *baseband_out)
+{
+	const mo_frontend *f = &m->fe;
+	int rate = f->interp, sym = m->Nofdm * rate, buf = m->Nofdm * f->buffer_Nsymb * rate;
+	int pre = m->preamble_nSymb, S = m->Nsymb;
+	int frame_dec = m->Nofdm * (S + pre);
+	double complex *bbi = malloc(sizeof(double complex) * buf), *scratch = malloc(sizeof(double complex) * buf);
+	double complex *bb = malloc(sizeof(double complex) * frame_dec);
+	int *loc = malloc(sizeof(int) * buf);
+	double *vals = malloc(sizeof(double) * buf);
+	double tail_stats[8] = {0};
+	int payload[MO_N / 8];
+	mo_rx_out ro;
+	memset(&ro, 0, sizeof(ro));
+	ro.payload = payload;
+	ro.stats = tail_stats;
+
+	int last_delay = (int)state[0];
+	double last_freq = state[1];
+	int message_decoded = 0, sync_trials = 0, iterations = 0, crc = 0, all_zeros = 0;
+	double SNR = 0, freq_offset = 0, freq_offset_measured = 0, coarse_metric = 0;
+	int step = 100, delay, pream_symb_loc;
+	double coarse_freq_offset = 0.0;
+
+	p2b(m, passband, buf, bbi, f->fc, 0, scratch); /* :676 */
+	double ss = 0;				       /* measure_signal_stregth: ofdm.cc:1523-1539 */
+	for (int i = 0; i < buf; i++) ss += pow(creal(bbi[i]), 2) + pow(cimag(bbi[i]), 2);
+	ss /= buf;
+	double signal_dbm = 10.0 * log10(ss / 0.001);
+
+	delay = time_sync(m, bbi, buf, rate, 0, step, 1, &coarse_metric, loc, vals); /* :691-693 */
+	pream_symb_loc = delay / sym;
+	if (pream_symb_loc < 1) pream_symb_loc = 1;
+	int lower_bound = pre, upper_bound = f->buffer_Nsymb - (S + pre);
+
+	if (!(pream_symb_loc > lower_bound && pream_symb_loc < upper_bound)) { /* bounds recovery :734-798 */
+		int signal_start_symb = -1;
+		for (int s = lower_bound + 1; s < upper_bound; s++)
+			if (sym_energy(bbi, s * sym, sym, buf) > 0.001) {
+				signal_start_symb = s;
+				break;
+			}
+		if (signal_start_symb >= 0) {
+			int search_start = signal_start_symb * sym, available = buf - search_start;
+			if (available > pre * sym) {
+				double rc;
+				int rd = time_sync(m, bbi + search_start, available, rate, 0, step, 1, &rc, loc, vals) + search_start;
+				int retry_symb = rd / sym;
+				if (retry_symb < 1) retry_symb = 1;
+				double re = sym_energy(bbi, rd, sym, buf);
+				if (re >= 0.001 && rc >= 0.5 && retry_symb > lower_bound && retry_symb < upper_bound) {
+					delay = rd;
+					coarse_metric = rc;
+					pream_symb_loc = retry_symb;
+				}
+			}
+		}
+	}
+
+	if (pream_symb_loc > lower_bound && pream_symb_loc < upper_bound) {
+		int energy_ok = 1;
+		double mean_energy = sym_energy(bbi, delay, sym, buf); /* :811-838 */
+		if (mean_energy < 0.001) energy_ok = 0;
+		if (energy_ok && coarse_metric < 0.5) energy_ok = 0; /* :844-851 */
+		if (!energy_ok) {				     /* silence skip :861-924 */
+			int signal_start_symb = -1;
+			for (int s = pream_symb_loc + 1; s < upper_bound; s++)
+				if (sym_energy(bbi, s * sym, sym, buf) > 0.001) {
+					signal_start_symb = s;
+					break;
+				}
+			if (signal_start_symb >= 0) {
+				int search_start = signal_start_symb * sym, available = buf - search_start;
+				if (available > pre * sym) {
+					double rc;
+					int rd = time_sync(m, bbi + search_start, available, rate, 0, step, 1, &rc, loc, vals) + search_start;
+					int retry_symb = rd / sym;
+					if (retry_symb < 1) retry_symb = 1;
+					double re = sym_energy(bbi, rd, sym, buf);
+					if (re >= 0.001 && rc >= 0.5 && retry_symb > lower_bound && retry_symb < upper_bound) {
+						delay = rd;
+						coarse_metric = rc;
+						pream_symb_loc = retry_symb;
+						energy_ok = 1;
+					}
+				}
+			}
+		}
+		if (energy_ok) {
+			int skip_h_count = 0, skip_h_recovery_attempted = 0;
+		skip_h_retry_point:
+			while (sync_trials <= f->trials_max) {
+				if (sync_trials == f->trials_max && f->use_last_time && last_delay != -1) delay = last_delay; /* :945-948 */
+				else /* :1017 (trial 1's coarse frequency search is off by default, gui_state.h:143) */
+					delay = (pream_symb_loc - 1) * sym +
+						time_sync(m, bbi + (pream_symb_loc - 1) * sym, (pre + 4) * sym, rate, sync_trials, 1, f->trials_max, NULL, loc, vals);
+				if (delay < 0) delay = 0;
+				int max_delay = buf - frame_dec * rate; /* :1022-1031 */
+				if (delay > max_delay) delay = max_delay;
+				{ /* post-fine-sync energy gate :1040-1069 */
+					double fine_energy = 0.0;
+					for (int i = 0; i < sym && (delay + i) < buf; i++)
+						fine_energy += creal(bbi[delay + i]) * creal(bbi[delay + i]) + cimag(bbi[delay + i]) * cimag(bbi[delay + i]);
+					fine_energy /= sym;
+					if (fine_energy < 0.001) {
+						int orig = delay;
+						for (int fwd = sym; fwd <= 3 * sym; fwd += sym) {
+							int cand = orig + fwd;
+							if (cand + sym > buf) break;
+							double e = 0.0;
+							for (int i = 0; i < sym; i++)
+								e += creal(bbi[cand + i]) * creal(bbi[cand + i]) + cimag(bbi[cand + i]) * cimag(bbi[cand + i]);
+							e /= sym;
+							if (e >= 0.001) {
+								delay = cand;
+								break;
+							}
+						}
+					}
+				}
+				double effective_fc = f->fc + coarse_freq_offset;
+				p2b(m, passband, buf, bbi, effective_fc, 1, scratch); /* :1081 */
+				for (int i = 0, k = 0; i < frame_dec * rate; i += rate) bb[k++] = bbi[delay + i]; /* :1103 */
+				if (sync_trials == f->trials_max && f->use_last_freq && last_freq != 0) freq_offset_measured = last_freq;
+				else freq_offset_measured = moose(m, bb + MO_NGI, f->bandwidth / (double)m->Nc, pre); /* :1117 */
+				if (fabs(freq_offset_measured) > f->ignore_limit) {				      /* :1126-1131 */
+					p2b(m, passband, buf, bbi, effective_fc + freq_offset_measured, 1, scratch);
+					for (int i = 0, k = 0; i < frame_dec * rate; i += rate) bb[k++] = bbi[delay + i];
+				}
+				mo_rx_tail(m, bb + pre * m->Nofdm, &ro); /* :1132-1341 */
+				if (tail_stats[7] < 0.3) {		   /* mean_H gate :1271-1281 */
+					skip_h_count++;
+					sync_trials++;
+					continue;
+				}
+				iterations = (int)tail_stats[0];
+				crc = (int)tail_stats[1];
+				all_zeros = (int)tail_stats[2];
+				for (int i = 0; i < m->frame_bytes; i++) out[i] = payload[i]; /* :1329-1332: written before the CRC verdict */
+				if (!(int)tail_stats[3]) { /* :1343-1359 */
+					SNR = -99.9;
+					message_decoded = 0;
+					sync_trials++;
+				} else {
+					SNR = tail_stats[4];
+					message_decoded = 1;
+					last_freq = freq_offset_measured; /* :1421-1427 */
+					freq_offset = freq_offset_measured;
+					last_delay = delay;
+					break;
+				}
+			}
+			if (!message_decoded && skip_h_count >= f->trials_max + 1 && !skip_h_recovery_attempted) { /* :1436-1504 */
+				skip_h_recovery_attempted = 1;
+				int search_start_symb = pream_symb_loc + 2, search_start = search_start_symb * sym;
+				int search_size = m->Nofdm * (2 * pre + S) * rate;
+				int available = buf - search_start;
+				if (available > search_size) available = search_size;
+				if (search_start_symb < upper_bound && available > pre * sym) {
+					p2b(m, passband, buf, bbi, f->fc, 0, scratch);
+					double rc;
+					int rd = time_sync(m, bbi + search_start, available, rate, 0, step, 1, &rc, loc, vals) + search_start;
+					int retry_symb = rd / sym;
+					if (retry_symb < 1) retry_symb = 1;
+					double re = sym_energy(bbi, rd, sym, buf);
+					if (re >= 0.001 && retry_symb > lower_bound && retry_symb < upper_bound) {
+						delay = rd;
+						coarse_metric = rc;
+						pream_symb_loc = retry_symb;
+						sync_trials = 0;
+						skip_h_count = 0;
+						coarse_freq_offset = 0.0;
+						goto skip_h_retry_point;
+					}
+				}
+			}
+		}
+	}
+	stats[0] = iterations;
+	stats[1] = crc;
+	stats[2] = all_zeros;
+	stats[3] = message_decoded;
+	stats[4] = SNR;
+	stats[5] = delay;
+	stats[6] = sync_trials;
+	stats[7] = freq_offset;
+	stats[8] = coarse_metric;
+	stats[9] = signal_dbm;
+	stats[10] = buf;
+	stats[11] = m->frame_bytes;
+	state[0] = last_delay;
+	state[1] = last_freq;
+	if (baseband_out) memcpy(baseband_out, bb, sizeof(double complex) * frame_dec);
+	free(bbi);
+	free(scratch);
+	free(bb);
+	free(loc);
+	free(vals);
+}
+
+/* Wall time (seconds) of n_calls mo_receive_byte() calls on consecutive capture buffers. */
+double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags)
+{
+	int buf = m->Nofdm * m->fe.buffer_Nsymb * m->fe.interp, out[MO_N / 8];
+	double stats[12], state[2];
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int c = 0; c < n_calls; c++) {
+		state[0] = -1;
+		state[1] = 0;
+		mo_receive_byte(m, passband + (size_t)c * buf, out, stats, state, NULL);
+		if (decoded_flags) decoded_flags[c] = (int)stats[3];
 	}
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);

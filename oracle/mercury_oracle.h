@@ -26,6 +26,13 @@
 #define MO_NOFDM 272
 #define MO_MAX_CELLS (48 * MO_NC)
 
+/* RX front-end constants (physical_config.cc:59,79-101) and the two receive FIR designs (fir_filter.cc:45-163). */
+typedef struct mo_frontend {
+	int interp, buffer_Nsymb, trials_max, use_last_time, use_last_freq, ntaps_ts, ntaps_data;
+	double fs, fc, amp, bandwidth, ignore_limit;
+	double c_ts[64], c_data[64];
+} mo_frontend;
+
 typedef struct mo_mode {
 	int config, M, bits_per_symbol, rate_num;
 	int Nsymb, Nc, Nfft, Ngi, Nofdm, nData, nPilots, nBits;
@@ -45,6 +52,7 @@ typedef struct mo_mode {
 	int *vdeg; /* [N]                      (from QCmatrixd) */
 	double complex twiddle[MO_NFFT / 2];
 	int bitrev[MO_NFFT];
+	mo_frontend fe;
 } mo_mode;
 
 typedef struct mo_rx_out {
@@ -77,5 +85,12 @@ void mo_rx_tail(const mo_mode *m, const double complex *baseband, mo_rx_out *o);
 double mo_rx_tail_timed(const mo_mode *m, const double complex *baseband, int n_frames, int *payloads, int *decoded, int *iterations);
 int mo_ldpc_decode(const mo_mode *m, const float *llr_cw, int *bits_out);
 void mo_ldpc_encode(const mo_mode *m, const int *data, int *encoded);
+
+/* RX front-end: the whole receive_byte(), pass-band capture in, payload out. */
+void mo_frontend_init(mo_mode *m);
+void mo_frontend_tables(const mo_mode *m, int *ntaps /*[2]*/, double *ts_coef, double *data_coef, double *consts /*[8]*/);
+void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats /*[12]*/, double *state /*[2]*/,
+		     double complex *baseband_out);
+double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

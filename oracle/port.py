@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmercury_oracle.so")
 LDPC_BLOB = os.path.normpath(os.path.join(_HERE, "..", "mercury_b200", "data", "ldpc_tables.bin"))
 
-from .ref import GEOM_FIELDS, _RxOut, _p  # noqa: E402  (shared record layouts)
+from .ref import GEOM_FIELDS, FrontEndMixin, _RxOut, _p  # noqa: E402  (shared record layouts)
 
 
 def build(force=False):
@@ -46,6 +46,10 @@ def lib():
         L.mo_rx_tail_timed.restype = C.c_double
         L.mo_ldpc_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mo_ldpc_decode.restype = C.c_int
+        L.mo_receive_byte.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.mo_receive_byte_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mo_receive_byte_timed.restype = C.c_double
+        L.mo_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         _lib = L
     return _lib
 
@@ -61,8 +65,14 @@ def port_crc16(data):
     return lib().mo_crc16(_p(a), len(a))
 
 
-class Port:
+class Port(FrontEndMixin):
     """The C restatement loaded with CONFIG_<config> and -I <ldpc_iters>."""
+
+    _fe = "mo_"
+
+    @staticmethod
+    def _felib():
+        return lib()
 
     def __init__(self, config, ldpc_iters=50):
         self.h = lib().mo_mode_new(config, ldpc_iters, LDPC_BLOB.encode())

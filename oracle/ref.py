@@ -62,6 +62,10 @@ def lib():
         L.mref_transmit_byte.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.mref_transmit_byte.restype = C.c_int
         L.mref_receive_byte.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.mref_receive_byte2.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.mref_receive_byte_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mref_receive_byte_timed.restype = C.c_double
+        L.mref_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         _lib = L
     return _lib
 
@@ -96,8 +100,56 @@ def ldpc_tables(rate_num):
     return dict(C=Cm, V=Vm, d=d, Enc=E, N=N, K=K, P=P)
 
 
-class Ref:
+STAT12 = ("iterations", "crc", "all_zeros", "decoded", "snr", "delay", "sync_trials", "freq_offset", "coarse_metric",
+          "signal_dbm", "buffer_samples", "frame_bytes")
+
+
+class FrontEndMixin:
+    """The whole receive_byte() (pass-band capture in), shared by Ref (mref_*) and Port (mo_*); `_fe` = symbol prefix."""
+
+    def capture_samples(self):
+        return self.Nofdm * self.buffer_Nsymb * self.interp_rate
+
+    def receive_byte2(self, passband, last_delay=-1, last_freq=0.0):
+        L = self._felib()
+        n = self.capture_samples()
+        pb = np.ascontiguousarray(passband, np.float64)
+        assert pb.size == n, (pb.size, n)
+        out = np.zeros(self.frame_bytes, np.int32)
+        st = np.zeros(12, np.float64)
+        state = np.array([last_delay, last_freq], np.float64)
+        bb = np.zeros((self.Nsymb + self.preamble_nSymb) * self.Nofdm, np.complex128)
+        getattr(L, self._fe + "receive_byte2" if self._fe == "mref_" else self._fe + "receive_byte")(
+            self.h, _p(pb), _p(out), _p(st), _p(state), _p(bb))
+        r = {k: (float(st[i]) if k in ("snr", "freq_offset", "coarse_metric", "signal_dbm") else int(st[i])) for i, k in enumerate(STAT12)}
+        r.update(payload=out, baseband=bb, last_delay=int(state[0]), last_freq=float(state[1]))
+        return r
+
+    def receive_byte_timed(self, captures):
+        pb = np.ascontiguousarray(captures, np.float64)
+        n = pb.size // self.capture_samples()
+        dec = np.zeros(n, np.int32)
+        secs = getattr(self._felib(), self._fe + "receive_byte_timed")(self.h, _p(pb), n, _p(dec))
+        return secs, dec
+
+    def frontend_tables(self):
+        nt = np.zeros(2, np.int32)
+        a = np.zeros(64, np.float64)
+        b = np.zeros(64, np.float64)
+        c = np.zeros(8, np.float64)
+        getattr(self._felib(), self._fe + "frontend_tables")(self.h, _p(nt), _p(a), _p(b), _p(c))
+        return dict(ts=a[:nt[0]].copy(), data=b[:nt[1]].copy(), fs=c[0], fc=c[1], amp=c[2], bandwidth=c[3], trials_max=int(c[4]),
+                    use_last_time=int(c[5]), use_last_freq=int(c[6]), ignore_limit=c[7])
+
+
+class Ref(FrontEndMixin):
     """One reference cl_telecom_system loaded with CONFIG_<config> and -I <ldpc_iters>."""
+
+    _fe = "mref_"
+
+    @staticmethod
+    def _felib():
+        return lib()
 
     def __init__(self, config, ldpc_iters=50):
         self.h = lib().mref_create(config, ldpc_iters)

@@ -445,4 +445,99 @@ void mref_receive_byte(void *h, const double *passband, int *out, double *stats 
 	if (baseband_out) memcpy(baseband_out, dc.baseband_data, sizeof(double) * 2 * (dc.Nsymb + dc.preamble_nSymb) * dc.Nofdm);
 }
 
+/*
+ * Reference receive_byte() unchanged, with the cross-call link state made explicit: state[0] =
+ * receive_stats.delay_of_last_decoded_message, state[1] = receive_stats.freq_offset_of_last_decoded_message are
+ * written into the object before the call and read back after it (telecom_system.cc:945-947,1108-1110,1423-1427).
+ * stats[12]: iterations, crc, all_zeros, decoded, SNR, delay, sync_trials, freq_offset, coarse_metric,
+ * signal_stregth_dbm, buffer samples, frame_bytes.
+ */
+void mref_receive_byte2(void *h, const double *passband, int *out, double *stats /*[12]*/, double *state /*[2]*/, double *baseband_out)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	cl_data_container &dc = ts.data_container;
+	size_t n = (size_t)dc.Nofdm * dc.buffer_Nsymb * dc.interpolation_rate;
+	double *copy = new double[n];
+	memcpy(copy, passband, sizeof(double) * n);
+	int obuf[N_MAX];
+	memset(obuf, 0, sizeof(obuf));
+	ts.receive_stats.delay_of_last_decoded_message = (int)state[0];
+	ts.receive_stats.freq_offset_of_last_decoded_message = state[1];
+	ts.receive_stats.freq_offset = 0;
+	ts.receive_stats.coarse_metric = 0;
+	ts.receive_stats.iterations_done = 0;
+	ts.receive_stats.crc = 0;
+	ts.receive_stats.all_zeros = 0;
+	ts.receive_stats.SNR = 0;
+	st_receive_stats rs = ts.receive_byte(copy, obuf);
+	delete[] copy;
+	for (int i = 0; i < ts.get_frame_size_bytes(); i++) out[i] = obuf[i];
+	stats[0] = rs.iterations_done;
+	stats[1] = rs.crc;
+	stats[2] = rs.all_zeros;
+	stats[3] = rs.message_decoded;
+	stats[4] = rs.SNR;
+	stats[5] = rs.delay;
+	stats[6] = rs.sync_trials;
+	stats[7] = rs.freq_offset;
+	stats[8] = rs.coarse_metric;
+	stats[9] = rs.signal_stregth_dbm;
+	stats[10] = (double)n;
+	stats[11] = ts.get_frame_size_bytes();
+	state[0] = rs.delay_of_last_decoded_message;
+	state[1] = rs.freq_offset_of_last_decoded_message;
+	if (baseband_out) memcpy(baseband_out, dc.baseband_data, sizeof(double) * 2 * (dc.Nsymb + dc.preamble_nSymb) * dc.Nofdm);
+}
+
+/* Wall time (seconds) of n_calls unchanged receive_byte() calls on consecutive capture buffers (CPU baseline of the front-end row). */
+double mref_receive_byte_timed(void *h, const double *passband, int n_calls, int *decoded_flags)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	cl_data_container &dc = ts.data_container;
+	size_t n = (size_t)dc.Nofdm * dc.buffer_Nsymb * dc.interpolation_rate;
+	double *copy = new double[n];
+	int obuf[N_MAX];
+	auto t0 = std::chrono::steady_clock::now();
+	for (int c = 0; c < n_calls; c++) {
+		memcpy(copy, passband + (size_t)c * n, sizeof(double) * n);
+		ts.receive_stats.delay_of_last_decoded_message = -1;
+		ts.receive_stats.freq_offset_of_last_decoded_message = 0;
+		st_receive_stats rs = ts.receive_byte(copy, obuf);
+		if (decoded_flags) decoded_flags[c] = rs.message_decoded == YES;
+	}
+	auto t1 = std::chrono::steady_clock::now();
+	delete[] copy;
+	return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* The reference's own FIR designs (fir_filter.cc:45-163) and front-end constants, for pinning the restatement. */
+void mref_frontend_tables(void *h, int *ntaps /*[2]*/, double *ts_coef, double *data_coef, double *consts /*[8]*/)
+{
+	cl_telecom_system &ts = T(h);
+	ntaps[0] = ts.ofdm.FIR_rx_time_sync.filter_nTaps;
+	ntaps[1] = ts.ofdm.FIR_rx_data.filter_nTaps;
+	/* the coefficient array is private: read it as the response to a centred unit impulse (apply(), fir_filter.cc:189-210;
+	 * every other product is an exact zero, so the response equals the coefficients bit for bit) */
+	for (int f = 0; f < 2; f++) {
+		cl_FIR &fir = f == 0 ? ts.ofdm.FIR_rx_time_sync : ts.ofdm.FIR_rx_data;
+		int nt = ntaps[f];
+		double *imp = new double[nt](), *resp = new double[nt]();
+		imp[(nt - 1) / 2] = 1.0;
+		fir.apply(imp, resp, nt);
+		for (int i = 0; i < nt; i++) (f == 0 ? ts_coef : data_coef)[i] = resp[i];
+		delete[] imp;
+		delete[] resp;
+	}
+	consts[0] = ts.sampling_frequency;
+	consts[1] = ts.carrier_frequency;
+	consts[2] = ts.carrier_amplitude;
+	consts[3] = ts.bandwidth;
+	consts[4] = ts.time_sync_trials_max;
+	consts[5] = ts.use_last_good_time_sync;
+	consts[6] = ts.use_last_good_freq_offset;
+	consts[7] = ts.ofdm.freq_offset_ignore_limit;
+}
+
 }  // extern "C"
