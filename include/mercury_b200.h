@@ -22,6 +22,8 @@
  *   mercury_b200_demod_decode_batch_device   "  (device-resident buffers, caller's stream)
  *   mercury_b200_demod_batch_device      symbol_demod .. psk.demod .. LLR expand   (telecom_system.cc:1135-1308)
  *   mercury_b200_ldpc_decode_batch_device    ldpc.decode .. CRC16                  (telecom_system.cc:1310-1349)
+ *   mercury_b200_receive_byte(_batch)    st_receive_stats receive_byte(double*,int*) WHOLE (telecom_system.h:142, .cc:646-1518):
+ *                                        pass-band capture in, front-end on the GPU
  *   mercury_b200_rx_stats                st_receive_stats (telecom_system.h:63-82), the fields the tail writes
  *   mercury_b200_batcher_*               (new) many concurrent links' receive calls -> one GPU batch; replaces the one-frame-per-call
  *                                        pattern of arq_common.cc:2619-2668 / audioio.c:999-1069 for a multi-link gateway
@@ -137,6 +139,40 @@ int mercury_b200_set_debug_capture(mercury_b200_t *h, void *d_Y, void *d_H, void
  * per payload byte like receive_byte()'s `int* out`.  Returns the stats record by pointer.
  */
 int mercury_b200_receive_baseband(mercury_b200_t *h, const double *baseband, int *out, mercury_b200_rx_stats *stats);
+
+/*
+ * The WHOLE receive_byte(): pass-band capture in, payload out -- the reference's front-end
+ * (st_receive_stats cl_telecom_system::receive_byte(double* data, int* out), telecom_system.h:142, .cc:646-1518, OFDM branch:
+ * passband_to_baseband ofdm.cc:2316-2339, time_sync_preamble(_with_metric) ofdm.cc:1735-1967, the gates / recoveries / trial
+ * loop of telecom_system.cc:700-1131, carrier_sampling_frequency_sync ofdm.cc:540-595, SKIP-H recovery :1436-1504) runs on the
+ * GPU in front of the same tail.  A capture is mercury_b200_get_capture_samples() = Nofdm * buffer_Nsymb * 4 real samples at
+ * 48 kHz (data_container.cc:133-153), the frame anywhere inside it.
+ *
+ * mercury_b200_receive_stats = st_receive_stats (telecom_system.h:63-82), the fields the OFDM branch writes.  The two
+ * *_of_last_decoded_message fields are the reference's cross-call link state (telecom_system.cc:945-947,1108-1110,1423-1427):
+ * they are INPUTS as well as outputs (initialise to -1 and 0.0 for a new link, then pass the record back in on the next call).
+ * Sync decisions (delay, sync_trials) are bit-identical to the reference; see mb_frontend.cu for how.
+ */
+typedef struct mercury_b200_receive_stats {
+	int32_t iterations_done, delay, delay_of_last_decoded_message, sync_trials;
+	int32_t message_decoded, crc, all_zeros, reserved;
+	double freq_offset, freq_offset_of_last_decoded_message, SNR, signal_stregth_dbm, coarse_metric;
+} mercury_b200_receive_stats;
+
+#define MERCURY_B200_SAMPLES_F64 0  /* double, the reference's own type */
+#define MERCURY_B200_SAMPLES_F32 1  /* float: half the bytes; every float is exactly representable as the double the reference would see */
+
+int mercury_b200_get_capture_samples(const mercury_b200_t *h);
+/* One capture, the reference's own types (out = one int per payload byte). */
+int mercury_b200_receive_byte(mercury_b200_t *h, const double *passband, int *out, mercury_b200_receive_stats *stats);
+/* n captures of independent links: passband n x capture_samples (host), payload n x frame_bytes, stats n records (in/out).
+ * baseband_dbg (optional, host): n x (preamble_nSymb + Nsymb) x 272 complex128 = data_container.baseband_data of the last trial. */
+int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *passband, int sample_format, size_t n_captures, uint8_t *payload,
+				    mercury_b200_receive_stats *stats, double *baseband_dbg);
+/* Same on device-resident buffers.  The per-capture control flow is a device-side state machine, but the loop around it reads
+ * three counters back per round, so this call synchronises `stream` before it returns. */
+int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_passband, int sample_format, size_t n_captures, void *d_payload,
+					   void *d_stats, void *stream);
 
 /* Pinned host memory and plain device memory helpers for callers that do not link the CUDA runtime. */
 void *mercury_b200_host_alloc(size_t bytes);

@@ -25,6 +25,14 @@ class RxStats(C.Structure):
                 ("SNR", C.c_float), ("variance", C.c_float), ("mean_H", C.c_float), ("reserved", C.c_int32)]
 
 
+class ReceiveStats(C.Structure):
+    """mercury_b200_receive_stats = st_receive_stats (telecom_system.h:63-82), fields of the OFDM branch."""
+    _fields_ = [("iterations_done", C.c_int32), ("delay", C.c_int32), ("delay_of_last_decoded_message", C.c_int32), ("sync_trials", C.c_int32),
+                ("message_decoded", C.c_int32), ("crc", C.c_int32), ("all_zeros", C.c_int32), ("reserved", C.c_int32),
+                ("freq_offset", C.c_double), ("freq_offset_of_last_decoded_message", C.c_double), ("SNR", C.c_double),
+                ("signal_stregth_dbm", C.c_double), ("coarse_metric", C.c_double)]
+
+
 def build(force=False):
     """Compile the library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcdir = os.path.join(_HERE, "csrc")
@@ -68,6 +76,10 @@ def lib():
         "mercury_b200_ldpc_decode_batch_device": (i32, [vp, vp, sz, vp, vp, vp]),
         "mercury_b200_set_debug_capture": (i32, [vp, vp, vp, vp]),
         "mercury_b200_receive_baseband": (i32, [vp, vp, vp, C.POINTER(RxStats)]),
+        "mercury_b200_get_capture_samples": (i32, [vp]),
+        "mercury_b200_receive_byte": (i32, [vp, vp, vp, C.POINTER(ReceiveStats)]),
+        "mercury_b200_receive_byte_batch": (i32, [vp, vp, i32, sz, vp, vp, vp]),
+        "mercury_b200_receive_byte_batch_device": (i32, [vp, vp, i32, sz, vp, vp, vp]),
         "mercury_b200_host_alloc": (vp, [sz]),
         "mercury_b200_host_free": (None, [vp]),
         "mercury_b200_device_alloc": (vp, [vp, sz]),

@@ -22,6 +22,7 @@ std::string mb_synth_frames(const std::vector<uint8_t> &blob, int config, size_t
 static_assert(sizeof(MbRxStats) == sizeof(mercury_b200_rx_stats), "stats record layout");
 static_assert(sizeof(MbRxStats) == 32, "stats record size");
 static_assert(MB_HANDOFF_STRIDE == MERCURY_B200_HANDOFF_FLOATS, "hand-off stride");
+static_assert(sizeof(MbReceiveStats) == sizeof(mercury_b200_receive_stats) && sizeof(MbReceiveStats) == 72, "receive stats record layout");
 
 namespace {
 constexpr int kSlots = 3;
@@ -35,7 +36,38 @@ struct Slot {
 };
 }  // namespace
 
+namespace {
+// Device workspace of the RX front-end (mb_frontend.cu), sized for cap captures of buf pass-band samples.
+struct FeWork {
+	size_t cap = 0;
+	int buf = 0;
+	void *d_x = nullptr;  // staged pass-band samples of the host entry point
+	size_t x_bytes = 0;
+	MbFeState *st = nullptr;
+	double2 *bbi = nullptr, *win = nullptr, *dbg_bb = nullptr;
+	double *energy_part = nullptr, *vals = nullptr;
+	float2 *frames = nullptr;
+	float *llr = nullptr;
+	MbRxStats *tail_stats = nullptr;
+	uint8_t *tail_payload = nullptr, *payload = nullptr;
+	MbReceiveStats *stats = nullptr;
+	int32_t *counters = nullptr, *h_counters = nullptr;
+	double2 *carrier = nullptr;  // (cos, sin)(2 pi fc i Ts), host libm
+	int carrier_n = 0;
+	bool want_dbg = false;
+	cudaStream_t stream = nullptr;
+};
+constexpr int kFeVals = 4 * MB_FE_SYM;       // fine search: (pre + 4) - pre symbols of candidate positions, step 1
+constexpr int kFeWin = 8 * MB_FE_SYM;        // fine-sync window, (pre + 4) symbols, pre <= 4
+void fe_free(FeWork &w);
+}  // namespace
+
 struct mercury_b200 {
+	FeWork fe;
+	MbFeConst fe_const;
+	bool fe_ready = false;
+	size_t fe_chunk = 1024;
+	uint64_t fe_rounds = 0;
 	int device = -1;
 	std::vector<uint8_t> blob;
 	MbBlobHeader hdr;
@@ -227,6 +259,7 @@ void mercury_b200_destroy(mercury_b200_t *h)
 	if (h->d_scratch_llr) cudaFree(h->d_scratch_llr);
 	if (h->d_blob) cudaFree(h->d_blob);
 	if (h->h_stage) cudaFreeHost(h->h_stage);
+	fe_free(h->fe);
 	delete h;
 }
 
@@ -436,6 +469,209 @@ int mercury_b200_receive_baseband(mercury_b200_t *h, const double *baseband, int
 	if (rc) return rc;
 	for (int i = 0; i < m.frame_bytes; i++) out[i] = pl[i];  // one int per byte, like receive_byte() (telecom_system.cc:1329-1332)
 	*stats = *st;
+	return MERCURY_B200_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * The whole receive_byte(): RX front-end (mb_frontend.cu) + tail.
+ * ------------------------------------------------------------------------------------------------------------------- */
+}  // extern "C"
+
+namespace {
+
+void fe_free(FeWork &w)
+{
+	void *ptrs[] = {w.d_x, w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
+	for (void *p : ptrs)
+		if (p) cudaFree(p);
+	if (w.h_counters) cudaFreeHost(w.h_counters);
+	if (w.carrier) cudaFree(w.carrier);
+	if (w.stream) cudaStreamDestroy(w.stream);
+	w = FeWork();
+}
+
+int fe_capture_samples(const MbMode &m) { return MB_NOFDM * mb_fe_buffer_nsymb(m.Nsymb, m.preamble_nSymb) * 4; }
+
+int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_dbg, size_t stage_bytes)
+{
+	FeWork &w = h->fe;
+	if (!h->fe_ready) {
+		mb_fe_host_const(&h->fe_const);
+		cudaError_t e = mb_fe_init(h->fe_const);
+		if (e != cudaSuccess) return cuda_fail(h, e, "front-end constants");
+		if (const char *c = getenv("MERCURY_B200_FE_CHUNK")) h->fe_chunk = std::max(1, atoi(c));
+		h->fe_ready = true;
+	}
+	if (!w.stream) MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+	if (w.carrier_n < buf) {
+		if (w.carrier) cudaFree(w.carrier);
+		w.carrier = nullptr;
+		std::vector<double> cs((size_t)2 * buf);
+		mb_fe_host_carrier(h->fe_const, cs.data(), buf);
+		MB_CUDA(h, cudaMalloc(&w.carrier, cs.size() * sizeof(double)));
+		MB_CUDA(h, cudaMemcpy(w.carrier, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice));
+		w.carrier_n = buf;
+	}
+	if (!w.h_counters) {
+		MB_CUDA(h, cudaMallocHost(&w.h_counters, 4 * sizeof(int32_t)));
+		MB_CUDA(h, cudaMalloc(&w.counters, 4 * sizeof(int32_t)));
+	}
+	if (w.x_bytes < stage_bytes) {
+		MB_CUDA(h, cudaDeviceSynchronize());
+		if (w.d_x) cudaFree(w.d_x);
+		w.d_x = nullptr, w.x_bytes = 0;
+		MB_CUDA(h, cudaMalloc(&w.d_x, stage_bytes));
+		w.x_bytes = stage_bytes;
+	}
+	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
+	if (w.cap >= n && w.buf >= buf && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
+	MB_CUDA(h, cudaDeviceSynchronize());
+	void **ptrs[] = {(void **)&w.st, (void **)&w.bbi, (void **)&w.win, (void **)&w.dbg_bb, (void **)&w.energy_part, (void **)&w.vals, (void **)&w.frames,
+			 (void **)&w.llr, (void **)&w.tail_stats, (void **)&w.tail_payload, (void **)&w.payload, (void **)&w.stats};
+	for (void **p : ptrs) {
+		if (*p) cudaFree(*p);
+		*p = nullptr;
+	}
+	w.cap = 0;
+	const int bufmax = std::max(buf, w.buf);
+	const size_t cap = std::max(n, w.cap);
+	MB_CUDA(h, cudaMalloc(&w.st, cap * sizeof(MbFeState)));
+	MB_CUDA(h, cudaMalloc(&w.bbi, cap * bufmax * sizeof(double2)));
+	MB_CUDA(h, cudaMalloc(&w.win, cap * kFeWin * sizeof(double2)));
+	MB_CUDA(h, cudaMalloc(&w.energy_part, cap * ((bufmax + 255) / 256) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
+	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
+	MB_CUDA(h, cudaMalloc(&w.tail_stats, cap * sizeof(MbRxStats)));
+	MB_CUDA(h, cudaMalloc(&w.tail_payload, cap * 256));
+	MB_CUDA(h, cudaMalloc(&w.payload, cap * 256));
+	MB_CUDA(h, cudaMalloc(&w.stats, cap * sizeof(MbReceiveStats)));
+	if (want_dbg) MB_CUDA(h, cudaMalloc(&w.dbg_bb, cap * (size_t)(MB_MAX_SYMB + 4) * MB_NOFDM * sizeof(double2)));
+	(void)bb_n;
+	w.want_dbg = want_dbg;
+	w.cap = cap;
+	w.buf = bufmax;
+	return MERCURY_B200_OK;
+}
+
+// One chunk of captures already on the device: d_x [n][buf], d_stats [n] in/out, d_payload [n][frame_bytes].
+int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_payload, MbReceiveStats *d_stats, bool dbg, cudaStream_t s)
+{
+	const MbMode &m = h->hdr.modes[h->config];
+	FeWork &w = h->fe;
+	MbFeArgs a;
+	memset(&a, 0, sizeof(a));
+	a.x = d_x, a.x_is_f32 = fmt == MERCURY_B200_SAMPLES_F32, a.n = (int)n;
+	a.buffer_Nsymb = mb_fe_buffer_nsymb(m.Nsymb, m.preamble_nSymb);
+	a.buf = MB_NOFDM * a.buffer_Nsymb * 4, a.pre = m.preamble_nSymb, a.S = m.Nsymb, a.frame_bytes = m.frame_bytes;
+	a.carrier = w.carrier, a.st = w.st, a.bbi = w.bbi, a.energy_part = w.energy_part;
+	a.win = w.win, a.win_stride = kFeWin, a.vals = w.vals, a.vals_stride = kFeVals;
+	a.frames = w.frames, a.dbg_bb = dbg ? w.dbg_bb : nullptr;
+	a.tail_stats = w.tail_stats, a.tail_payload = w.tail_payload, a.tail_payload_stride = m.frame_bytes;
+	a.payload_out = d_payload, a.counters = w.counters;
+	if ((a.buf - m.preamble_nSymb * MB_FE_SYM + 99) / 100 > kFeVals) return fail(h, MERCURY_B200_EINVAL, "capture too long for the correlation buffer");
+	MB_CUDA(h, cudaMemsetAsync(d_payload, 0, n * m.frame_bytes, s));
+	MB_CUDA(h, mb_fe_begin(a, d_stats, s));
+	MB_CUDA(h, mb_fe_p2b_full(a, s));
+	h->launches += 2;
+	bool run_sc = true;
+	// every round each capture either finishes or passes one of: coarse run, <= 2 recovery runs, 3 fine runs + 3 tails, SKIP-H
+	// recovery and 3 more trials -- 32 rounds is far above the longest path through receive_byte()
+	for (int round = 0; round < 32; round++) {
+		MB_CUDA(h, cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), s));
+		MB_CUDA(h, mb_fe_step(a, run_sc, s));
+		h->launches += run_sc ? 3 : 1;
+		MB_CUDA(h, cudaMemcpyAsync(w.h_counters, w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		MB_CUDA(h, cudaStreamSynchronize(s));
+		h->fe_rounds++;
+		const int n_slots = w.h_counters[0], not_done = w.h_counters[1];
+		run_sc = w.h_counters[2] > 0;
+		if (n_slots > 0) {
+			MB_CUDA(h, mb_fe_extract(a, s));
+			h->launches++;
+			int rc = launch_demod(h, w.frames, (size_t)n_slots, w.llr, w.tail_stats, nullptr, 0, s);
+			if (rc) return rc;
+			rc = launch_ldpc(h, w.llr, (size_t)n_slots, w.tail_payload, w.tail_stats, s);
+			if (rc) return rc;
+		}
+		if (not_done == 0) break;
+		if (round == 31) return fail(h, MERCURY_B200_ECUDA, "front-end state machine did not terminate");
+	}
+	MB_CUDA(h, mb_fe_finish(a, d_stats, s));
+	h->launches++;
+	MB_CUDA(h, cudaStreamSynchronize(s));
+	return MERCURY_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mercury_b200_get_capture_samples(const mercury_b200_t *h)
+{
+	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
+	return fe_capture_samples(h->hdr.modes[h->config]);
+}
+
+int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_x, int fmt, size_t n, void *d_payload, void *d_stats, void *stream)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n == 0) return MERCURY_B200_OK;
+	if (!d_x || !d_payload || !d_stats || (fmt != MERCURY_B200_SAMPLES_F64 && fmt != MERCURY_B200_SAMPLES_F32)) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	const MbMode &m = h->hdr.modes[h->config];
+	const int buf = fe_capture_samples(m);
+	const size_t ss = fmt == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, false, 0);
+	if (rc) return rc;
+	for (size_t done = 0; done < n; done += h->fe_chunk) {
+		const size_t c = std::min(h->fe_chunk, n - done);
+		rc = fe_run(h, static_cast<const uint8_t *>(d_x) + done * buf * ss, fmt, c, static_cast<uint8_t *>(d_payload) + done * m.frame_bytes,
+			    static_cast<MbReceiveStats *>(d_stats) + done, false, static_cast<cudaStream_t>(stream));
+		if (rc) return rc;
+	}
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, size_t n, uint8_t *payload, mercury_b200_receive_stats *stats,
+				    double *baseband_dbg)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n == 0) return MERCURY_B200_OK;
+	if (!x || !payload || !stats || (fmt != MERCURY_B200_SAMPLES_F64 && fmt != MERCURY_B200_SAMPLES_F32)) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	const MbMode &m = h->hdr.modes[h->config];
+	const int buf = fe_capture_samples(m);
+	const size_t ss = fmt == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	const size_t chunk = std::min(n, h->fe_chunk);
+	rc = fe_ensure(h, chunk, buf, m, baseband_dbg != nullptr, chunk * buf * ss);
+	if (rc) return rc;
+	FeWork &w = h->fe;
+	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
+	for (size_t done = 0; done < n; done += chunk) {
+		const size_t c = std::min(chunk, n - done);
+		MB_CUDA(h, cudaMemcpyAsync(w.d_x, static_cast<const uint8_t *>(x) + done * buf * ss, c * buf * ss, cudaMemcpyHostToDevice, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(w.stats, stats + done, c * sizeof(MbReceiveStats), cudaMemcpyHostToDevice, w.stream));
+		if (baseband_dbg) MB_CUDA(h, cudaMemsetAsync(w.dbg_bb, 0, c * bb_n * sizeof(double2), w.stream));
+		rc = fe_run(h, w.d_x, fmt, c, w.payload, w.stats, baseband_dbg != nullptr, w.stream);
+		if (rc) return rc;
+		MB_CUDA(h, cudaMemcpyAsync(payload + done * m.frame_bytes, w.payload, c * m.frame_bytes, cudaMemcpyDeviceToHost, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(stats + done, w.stats, c * sizeof(MbReceiveStats), cudaMemcpyDeviceToHost, w.stream));
+		if (baseband_dbg)
+			MB_CUDA(h, cudaMemcpyAsync(baseband_dbg + done * bb_n * 2, w.dbg_bb, c * bb_n * sizeof(double2), cudaMemcpyDeviceToHost, w.stream));
+		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+	}
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_receive_byte(mercury_b200_t *h, const double *passband, int *out, mercury_b200_receive_stats *stats)
+{
+	if (!h || !passband || !out || !stats) return MERCURY_B200_EINVAL;
+	uint8_t pl[256];
+	int rc = mercury_b200_receive_byte_batch(h, passband, MERCURY_B200_SAMPLES_F64, 1, pl, stats, nullptr);
+	if (rc) return rc;
+	const int fb = h->hdr.modes[h->config].frame_bytes;
+	for (int i = 0; i < fb; i++) out[i] = pl[i];  // one int per byte (telecom_system.cc:1329-1332)
 	return MERCURY_B200_OK;
 }
 

@@ -1,0 +1,702 @@
+// mb_frontend.cu -- the RX front-end on the GPU: everything cl_telecom_system::receive_byte() does to a
+// pass-band capture buffer before and around the RX tail (reference source/physical_layer/telecom_system.cc:646-1131 and
+// 1343-1518, OFDM branch):
+//   passband_to_baseband        ofdm.cc:2316-2339   mix with the carrier, 33-tap zero-phase FIR (fir_filter.cc:164-187)
+//   measure_signal_stregth      ofdm.cc:1523-1539
+//   time_sync_preamble(_with_metric)  ofdm.cc:1735-1967   Schmidl-Cox self-correlation, coarse (step 100) and fine (step 1)
+//   energy / metric gates, bounds recovery, silence skip   telecom_system.cc:734-924
+//   trial loop, last-good fallbacks, post-fine-sync energy fix   telecom_system.cc:928-1069
+//   data-filter mix + decimation by 4   telecom_system.cc:1081-1103, ofdm.cc:2267-2277
+//   carrier_sampling_frequency_sync (Moose)   ofdm.cc:540-595, re-mix at the corrected carrier   telecom_system.cc:1126-1131
+//   verdict bookkeeping, SKIP-H recovery   telecom_system.cc:1343-1504
+//
+// Numerics.  Every value that feeds an INTEGER decision of the reference (the sync delay) is computed in fp64 with the
+// reference's own operation order and without FMA contraction (__dmul_rn/__dadd_rn), from a carrier table and FIR designs
+// computed on the host by the same libm calls the reference makes: the correlation metrics, hence the chosen delays, are
+// bit-identical to the reference (also in the tie cases a silent capture produces).  The data path behind the decision
+// (mix at the Moose-corrected carrier, FIR, decimation) is fp64 with device sincos and is rounded to the tail's complex64.
+//
+// Control flow is a per-capture state machine in global memory advanced by k_fe_decide; the heavy stages are separate
+// kernels that act on whatever each capture is waiting for (MbFeState::phase), so a batch needs no host-side branching:
+//   k_fe_p2b_full -> loop { k_fe_window, k_fe_sc, k_fe_decide, k_fe_extract, tail (demod + LDPC kernels) } until all captures are done.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "mb_kernels.cuh"
+
+namespace {
+
+__constant__ MbFeConst fe_c;
+
+constexpr int kDecideThreads = 256;
+constexpr int kScThreads = 128;
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+
+// One mixed sample l[i] = (x[i] * amp) * (cos, sin)(2 pi f i Ts)   (ofdm.cc:2330-2334)
+template <typename T>
+__device__ __forceinline__ double2 mixed_sample(const T *x, int i, int buf, const double2 *carrier, bool table, double f)
+{
+	if (i < 0 || i >= buf) return make_double2(0.0, 0.0);
+	const double v = dmul((double)x[i], fe_c.amp);
+	double c, s;
+	if (table) {
+		const double2 cs = carrier[i];
+		c = cs.x, s = cs.y;
+	} else {
+		const double ph = dmul(dmul(dmul(2 * M_PI, f), (double)i), fe_c.Ts);
+		sincos(ph, &s, &c);
+	}
+	return make_double2(dmul(v, c), dmul(v, s));
+}
+
+// FIR output sample o of the zero-phase filter (fir_filter.cc:164-187): sum over j ascending of l[o + 16 - j] * c[j]; samples
+// outside the buffer contribute an exact zero, which leaves the accumulator unchanged like the reference's skipped terms.
+template <typename T>
+__device__ __forceinline__ double2 fir_on_demand(const T *x, int o, int buf, const double2 *carrier, bool table, double f, const double *coef)
+{
+	double ar = 0, ai = 0;
+#pragma unroll 1
+	for (int j = 0; j < MB_FE_TAPS; j++) {
+		const double2 l = mixed_sample(x, o + MB_FE_TAPS / 2 - j, buf, carrier, table, f);
+		ar = dadd(ar, dmul(l.x, coef[j]));
+		ai = dadd(ai, dmul(l.y, coef[j]));
+	}
+	return make_double2(ar, ai);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red)
+{
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double t = 0;
+	for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+	return t;
+}
+
+// ---- full-buffer mix + time-sync FIR (telecom_system.cc:676) and the energy partials of measure_signal_stregth ----
+template <typename T>
+__global__ void __launch_bounds__(256) k_fe_p2b_full(const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, double2 *__restrict__ bbi_all,
+						       double *__restrict__ energy_part, int nblk)
+{
+	__shared__ double2 l[256 + MB_FE_TAPS - 1];
+	__shared__ double red[8];
+	const int b = blockIdx.y, t0 = blockIdx.x * 256;
+	const T *x = x_all + (size_t)b * buf;
+	for (int i = threadIdx.x; i < 256 + MB_FE_TAPS - 1; i += 256) l[i] = mixed_sample(x, t0 - MB_FE_TAPS / 2 + i, buf, carrier, true, 0.0);
+	__syncthreads();
+	const int o = t0 + threadIdx.x;
+	double e = 0;
+	if (o < buf) {
+		double ar = 0, ai = 0;
+#pragma unroll
+		for (int j = 0; j < MB_FE_TAPS; j++) {
+			const double2 v = l[threadIdx.x + MB_FE_TAPS - 1 - j];
+			ar = dadd(ar, dmul(v.x, fe_c.c_ts[j]));
+			ai = dadd(ai, dmul(v.y, fe_c.c_ts[j]));
+		}
+		bbi_all[(size_t)b * buf + o] = make_double2(ar, ai);
+		e = ar * ar + ai * ai;
+	}
+	e = block_sum(e, red);
+	if (threadIdx.x == 0) energy_part[(size_t)b * nblk + blockIdx.x] = e;
+}
+
+// ---- fine-sync window of the data-filter base-band (what baseband_data_interpolated holds after trial 0: telecom_system.cc:1081,1129) ----
+template <typename T>
+__global__ void __launch_bounds__(256) k_fe_window(const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, const MbFeState *__restrict__ st_all,
+						     double2 *__restrict__ win_all, int win_stride)
+{
+	const int b = blockIdx.y;
+	const MbFeState &st = st_all[b];
+	if (!st.sc_pending || st.sc_src != 1) return;
+	const T *x = x_all + (size_t)b * buf;
+	const bool table = st.cur_f == fe_c.fc;
+	for (int i = blockIdx.x * 256 + threadIdx.x; i < st.sc_size; i += gridDim.x * 256)
+		win_all[(size_t)b * win_stride + i] = fir_on_demand(x, st.sc_start + i, buf, carrier, table, st.cur_f, fe_c.c_data);
+}
+
+// ---- Schmidl-Cox metric, one thread per candidate position, the reference's summation order (ofdm.cc:1891-1940) ----
+__global__ void __launch_bounds__(kScThreads) k_fe_sc(const MbFeState *__restrict__ st_all, const double2 *__restrict__ bbi_all, int buf,
+							const double2 *__restrict__ win_all, int win_stride, double *__restrict__ vals_all, int vals_stride, int pre)
+{
+	const int b = blockIdx.y;
+	const MbFeState &st = st_all[b];
+	if (!st.sc_pending) return;
+	const int k = blockIdx.x * kScThreads + threadIdx.x;
+	if (k >= st.sc_npos) return;
+	const double2 *in = (st.sc_src == 0 ? bbi_all + (size_t)b * buf + st.sc_start : win_all + (size_t)b * win_stride) + (size_t)k * st.sc_step;
+	double cc = 0, na = 0, nb = 0;
+	for (int l = 0; l < pre; l++) {
+		const double2 *a = in + l * MB_FE_SYM, *bq = a + MB_NFFT * 4;
+#pragma unroll 4
+		for (int q = 0; q < MB_NGI * 4; q++) {
+			const double2 u = a[q], v = bq[q];
+			cc = dadd(cc, dmul(u.x, v.x));
+			na = dadd(na, dmul(u.x, u.x));
+			nb = dadd(nb, dmul(v.x, v.x));
+			cc = dadd(cc, dmul(u.y, v.y));
+			na = dadd(na, dmul(u.y, u.y));
+			nb = dadd(nb, dmul(v.y, v.y));
+		}
+		a = in + l * MB_FE_SYM + MB_NGI * 4;
+		bq = a + (MB_NFFT / 2) * 4;
+#pragma unroll 4
+		for (int q = 0; q < (MB_NFFT / 2) * 4; q++) {
+			const double2 u = a[q], v = bq[q];
+			cc = dadd(cc, dmul(u.x, v.x));
+			na = dadd(na, dmul(u.x, u.x));
+			nb = dadd(nb, dmul(v.x, v.x));
+			cc = dadd(cc, dmul(u.y, v.y));
+			na = dadd(na, dmul(u.y, u.y));
+			nb = dadd(nb, dmul(v.y, v.y));
+		}
+	}
+	if (na < 0.001 || nb < 0.001) cc = 0.0;
+	else cc = __ddiv_rn(cc, __dsqrt_rn(dmul(na, nb)));
+	vals_all[(size_t)b * vals_stride + k] = cc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_fe_decide: one CTA per capture advances the state machine as far as it can without another kernel.
+// ------------------------------------------------------------------------------------------------------------------
+struct DecideCtx {
+	MbFeState st;
+	int buf, pre, S, buffer_Nsymb, lower, upper;
+	int tmp_i;
+	double tmp_d;
+};
+
+// The reference's partial selection "sort" (ofdm.cc:1946-1958): entry `from` of the result is the FIRST index >= from holding the
+// maximum of the correlation array over [from, size), where the array is the computed metrics at multiples of `step` below the
+// search limit and zero everywhere else.
+__device__ void sc_result(const DecideCtx &c, const double *vals, int from, int *loc_out, double *corr_out, double *red_v, int *red_k)
+{
+	const MbFeState &st = c.st;
+	double best = -CUDART_INF;
+	int bk = 0x7fffffff;
+	for (int k = threadIdx.x; k < st.sc_npos; k += blockDim.x) {
+		if (k * st.sc_step < from) continue;
+		const double v = vals[k];
+		if (v > best) best = v, bk = k;  // ascending k per thread: strict > keeps the first
+	}
+	for (int o = 16; o; o >>= 1) {
+		const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+		const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+		if (ov > best || (ov == best && ok < bk)) best = ov, bk = ok;
+	}
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red_v[threadIdx.x >> 5] = best, red_k[threadIdx.x >> 5] = bk;
+	__syncthreads();
+	best = red_v[0], bk = red_k[0];
+	for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+		if (red_v[w] > best || (red_v[w] == best && red_k[w] < bk)) best = red_v[w], bk = red_k[w];
+	// first index >= from that is NOT a computed position (its array entry is an exact zero)
+	int nz = from;
+	while (nz < st.sc_size && (nz % st.sc_step) == 0 && nz / st.sc_step < st.sc_npos) nz++;
+	const int p = bk == 0x7fffffff ? -1 : bk * st.sc_step;
+	int loc;
+	double corr;
+	if (p >= 0 && best > 0) loc = p, corr = best;
+	else if (p >= 0 && best == 0) loc = (nz < st.sc_size && nz < p) ? nz : p, corr = 0;
+	else if (nz < st.sc_size) loc = nz, corr = 0;
+	else if (p >= 0) loc = p, corr = best;
+	else loc = from, corr = 0;
+	*loc_out = loc, *corr_out = corr;
+}
+
+// mean energy of up to one symbol of the time-sync base-band starting at pos (the gates: telecom_system.cc:741-753 etc.)
+__device__ double energy_ts(const double2 *bbi, int pos, int buf, double *red)
+{
+	double e = 0;
+	int cnt = buf - pos;
+	cnt = cnt < 0 ? 0 : (cnt > MB_FE_SYM ? MB_FE_SYM : cnt);
+	for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+		const double2 v = bbi[pos + i];
+		e += v.x * v.x + v.y * v.y;
+	}
+	e = block_sum(e, red);
+	return cnt > 0 ? e / cnt : 0.0;
+}
+
+// first symbol s in [s0, s1) whose mean energy exceeds 0.001, or -1 (telecom_system.cc:741-761, 868-887)
+__device__ int energy_scan(const double2 *bbi, int s0, int s1, int buf, int *sh_first)
+{
+	if (threadIdx.x == 0) *sh_first = 0x7fffffff;
+	__syncthreads();
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	for (int s = s0 + warp; s < s1; s += nw) {
+		const int pos = s * MB_FE_SYM;
+		int cnt = buf - pos;
+		cnt = cnt < 0 ? 0 : (cnt > MB_FE_SYM ? MB_FE_SYM : cnt);
+		double e = 0;
+		for (int i = lane; i < cnt; i += 32) {
+			const double2 v = bbi[pos + i];
+			e += v.x * v.x + v.y * v.y;
+		}
+		for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+		e = cnt > 0 ? e / cnt : 0.0;
+		if (lane == 0 && e > 0.001) atomicMin(sh_first, s);
+		if (*((volatile int *)sh_first) < s) break;  // a lower symbol already qualified
+	}
+	__syncthreads();
+	const int r = *sh_first;
+	__syncthreads();
+	return r == 0x7fffffff ? -1 : r;
+}
+
+// sum of |.|^2 over one symbol at pos of whatever baseband_data_interpolated currently holds (telecom_system.cc:1040-1069)
+template <typename T>
+__device__ double energy_cur_sum(const DecideCtx &c, const double2 *bbi, const T *x, const double2 *carrier, int pos, int n, double *red)
+{
+	double e = 0;
+	const bool table = c.st.cur_f == fe_c.fc;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		if (pos + i >= c.buf) break;
+		const double2 v = c.st.cur_kind == 0 ? bbi[pos + i] : fir_on_demand(x, pos + i, c.buf, carrier, table, c.st.cur_f, fe_c.c_data);
+		e += v.x * v.x + v.y * v.y;
+	}
+	return block_sum(e, red);
+}
+
+__device__ __forceinline__ void request_sc(MbFeState &st, int src, int start, int size, int step, int pre)
+{
+	st.sc_pending = 1;
+	st.sc_src = src, st.sc_start = start, st.sc_size = size, st.sc_step = step;
+	const int span = size - pre * MB_FE_SYM;
+	st.sc_npos = span > 0 ? (span + step - 1) / step : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restrict__ st_all, const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier,
+								const double2 *__restrict__ bbi_all, const double *__restrict__ vals_all, int vals_stride,
+								const double *__restrict__ energy_part, int nblk, const MbRxStats *__restrict__ tail_stats,
+								const uint8_t *__restrict__ tail_payload, int tail_payload_stride, uint8_t *__restrict__ payload_out,
+								int frame_bytes, int pre, int S, int buffer_Nsymb, int *__restrict__ counters)
+{
+	__shared__ DecideCtx c;
+	__shared__ double red[8];
+	__shared__ double red_v[8];
+	__shared__ int red_k[8];
+	__shared__ int sh_first;
+	const int b = blockIdx.x;
+	if (threadIdx.x == 0) {
+		c.st = st_all[b];
+		c.buf = buf, c.pre = pre, c.S = S, c.buffer_Nsymb = buffer_Nsymb;
+		c.lower = pre, c.upper = buffer_Nsymb - (S + pre);
+	}
+	__syncthreads();
+	if (c.st.phase == MB_FE_DONE) return;
+	const double2 *bbi = bbi_all + (size_t)b * buf;
+	const T *x = x_all + (size_t)b * buf;
+	const double *vals = vals_all + (size_t)b * vals_stride;
+	const int sym = MB_FE_SYM;
+	MbFeState &st = c.st;
+	bool wait = false;
+	while (!wait) {
+		__syncthreads();
+		const int phase = st.phase;
+		__syncthreads();  // thread 0 may rewrite st.phase as soon as it enters the case
+		int loc;
+		double corr;
+		switch (phase) {
+		case MB_FE_COARSE_WAIT: {  // telecom_system.cc:676-697
+			double e = 0;
+			for (int i = threadIdx.x; i < nblk; i += blockDim.x) e += energy_part[(size_t)b * nblk + i];
+			e = block_sum(e, red);
+			sc_result(c, vals, 0, &loc, &corr, red_v, red_k);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.signal_dbm = 10.0 * log10((e / buf) / 0.001);
+				st.sc_pending = 0;
+				st.delay = loc, st.coarse_metric = corr;
+				st.pream_symb_loc = loc / sym < 1 ? 1 : loc / sym;
+				st.phase = MB_FE_GATE;
+			}
+			__syncthreads();
+			if (!(st.pream_symb_loc > c.lower && st.pream_symb_loc < c.upper)) {  // bounds recovery, :734-798
+				const int s0 = energy_scan(bbi, c.lower + 1, c.upper, buf, &sh_first);
+				if (threadIdx.x == 0 && s0 >= 0 && buf - s0 * sym > pre * sym) {
+					request_sc(st, 0, s0 * sym, buf - s0 * sym, 100, pre);
+					st.phase = MB_FE_REC_BOUNDS;
+				}
+				__syncthreads();
+				if (st.phase == MB_FE_REC_BOUNDS) wait = true;
+			}
+			break;
+		}
+		case MB_FE_REC_BOUNDS:
+		case MB_FE_REC_SILENCE:
+		case MB_FE_REC_SKIPH: {  // :763-797, :889-922, :1466-1503
+			sc_result(c, vals, 0, &loc, &corr, red_v, red_k);
+			const int rd = loc + st.sc_start;
+			const int retry_symb = rd / sym < 1 ? 1 : rd / sym;
+			const double re = energy_ts(bbi, rd, buf, red);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.sc_pending = 0;
+				const bool ok = re >= 0.001 && (phase == MB_FE_REC_SKIPH || corr >= 0.5) && retry_symb > c.lower && retry_symb < c.upper;
+				if (ok) st.delay = rd, st.coarse_metric = corr, st.pream_symb_loc = retry_symb;
+				if (phase == MB_FE_REC_BOUNDS) st.phase = MB_FE_GATE;
+				else if (phase == MB_FE_REC_SILENCE) st.phase = ok ? MB_FE_TRIAL : MB_FE_DONE, st.skip_h_count = 0, st.skip_h_recovery_attempted = 0;
+				else {
+					if (ok) st.sync_trials = 0, st.skip_h_count = 0, st.phase = MB_FE_TRIAL;
+					else st.phase = MB_FE_DONE;
+				}
+			}
+			break;
+		}
+		case MB_FE_GATE: {  // :800-926
+			if (!(st.pream_symb_loc > c.lower && st.pream_symb_loc < c.upper)) {
+				if (threadIdx.x == 0) st.phase = MB_FE_DONE;
+				break;
+			}
+			const double mean_energy = energy_ts(bbi, st.delay, buf, red);
+			bool energy_ok = !(mean_energy < 0.001);
+			if (energy_ok && st.coarse_metric < 0.5) energy_ok = false;
+			if (energy_ok) {
+				if (threadIdx.x == 0) st.phase = MB_FE_TRIAL, st.skip_h_count = 0, st.skip_h_recovery_attempted = 0;
+				break;
+			}
+			const int s0 = energy_scan(bbi, st.pream_symb_loc + 1, c.upper, buf, &sh_first);
+			if (threadIdx.x == 0) {
+				if (s0 >= 0 && buf - s0 * sym > pre * sym) {
+					request_sc(st, 0, s0 * sym, buf - s0 * sym, 100, pre);
+					st.phase = MB_FE_REC_SILENCE;
+				} else st.phase = MB_FE_DONE;
+			}
+			__syncthreads();
+			if (st.phase == MB_FE_REC_SILENCE) wait = true;
+			break;
+		}
+		case MB_FE_TRIAL: {  // loop head :931-1019
+			if (threadIdx.x == 0) {
+				if (st.sync_trials > fe_c.trials_max) st.phase = MB_FE_TRIALS_END;
+				else if (st.sync_trials == fe_c.trials_max && fe_c.use_last_time && st.last_delay != -1) {
+					st.delay = st.last_delay;
+					st.phase = MB_FE_POSTDELAY;
+				} else {
+					request_sc(st, st.cur_kind, (st.pream_symb_loc - 1) * sym, (pre + 4) * sym, 1, pre);
+					st.phase = MB_FE_FINE_WAIT;
+				}
+			}
+			__syncthreads();
+			if (st.phase == MB_FE_FINE_WAIT) wait = true;
+			break;
+		}
+		case MB_FE_FINE_WAIT: {
+			const int want = st.sync_trials >= fe_c.trials_max ? fe_c.trials_max - 1 : st.sync_trials;  // location_to_return clamp, ofdm.cc:1821-1823
+			sc_result(c, vals, want, &loc, &corr, red_v, red_k);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.sc_pending = 0;
+				st.delay = st.sc_start + loc;
+				st.phase = MB_FE_POSTDELAY;
+			}
+			break;
+		}
+		case MB_FE_POSTDELAY: {  // :1020-1069
+			int delay = st.delay;
+			if (delay < 0) delay = 0;
+			const int max_delay = buf - (MB_NOFDM * (S + pre)) * 4;
+			if (delay > max_delay) delay = max_delay;
+			double fe = energy_cur_sum(c, bbi, x, carrier, delay, sym, red) / sym;
+			if (fe < 0.001) {
+				const int orig = delay;
+				for (int fwd = sym; fwd <= 3 * sym; fwd += sym) {
+					const int cand = orig + fwd;
+					if (cand + sym > buf) break;
+					const double e = energy_cur_sum(c, bbi, x, carrier, cand, sym, red) / sym;
+					if (e >= 0.001) {
+						delay = cand;
+						break;
+					}
+				}
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.delay = delay;
+				st.slot = atomicAdd(&counters[0], 1);
+				st.phase = MB_FE_EXTRACT;
+			}
+			wait = true;
+			break;
+		}
+		case MB_FE_TAIL_WAIT: {  // verdict :1271-1281, :1310-1429
+			const MbRxStats ts = tail_stats[st.slot];
+			if (ts.iterations_done >= 0)
+				for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x)
+					payload_out[(size_t)b * frame_bytes + i] = tail_payload[(size_t)st.slot * tail_payload_stride + i];
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.slot = -1;
+				if (ts.iterations_done < 0) {  // mean|H| < 0.3: LDPC skipped
+					st.skip_h_count++;
+					st.sync_trials++;
+					st.phase = MB_FE_TRIAL;
+				} else {
+					st.iterations_done = ts.iterations_done, st.crc = ts.crc, st.all_zeros = ts.all_zeros;
+					if (!ts.message_decoded) {
+						st.SNR = -99.9;
+						st.message_decoded = 0;
+						st.sync_trials++;
+						st.phase = MB_FE_TRIAL;
+					} else {
+						st.SNR = ts.SNR;
+						st.message_decoded = 1;
+						st.last_freq = st.freq_offset_measured;
+						st.freq_offset = st.freq_offset_measured;
+						st.last_delay = st.delay;
+						st.phase = MB_FE_DONE;
+					}
+				}
+			}
+			break;
+		}
+		case MB_FE_TRIALS_END: {  // SKIP-H recovery :1436-1504
+			if (threadIdx.x == 0) {
+				st.phase = MB_FE_DONE;
+				if (!st.message_decoded && st.skip_h_count >= fe_c.trials_max + 1 && !st.skip_h_recovery_attempted) {
+					st.skip_h_recovery_attempted = 1;
+					const int ss = st.pream_symb_loc + 2, search_start = ss * sym;
+					const int search_size = MB_NOFDM * (2 * pre + S) * 4;
+					int available = buf - search_start;
+					if (available > search_size) available = search_size;
+					if (ss < c.upper && available > pre * sym) {
+						st.cur_kind = 0, st.cur_f = fe_c.fc;  // the time-sync base-band is restored (:1457-1461)
+						request_sc(st, 0, search_start, available, 100, pre);
+						st.phase = MB_FE_REC_SKIPH;
+					}
+				}
+			}
+			__syncthreads();
+			if (st.phase == MB_FE_REC_SKIPH) wait = true;
+			break;
+		}
+		default:  // MB_FE_DONE, MB_FE_EXTRACT (waiting for k_fe_extract)
+			wait = true;
+			break;
+		}
+		__syncthreads();
+		if (st.phase == MB_FE_DONE) wait = true;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		st_all[b] = st;
+		if (st.phase != MB_FE_DONE) atomicAdd(&counters[1], 1);
+		if (st.sc_pending) atomicAdd(&counters[2], 1);
+	}
+}
+
+// ---- data-filter mix + decimation, Moose, re-mix at the corrected carrier; writes the tail's input frame ----
+template <typename T>
+__global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_all, const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier,
+						      float2 *__restrict__ frames, double2 *__restrict__ dbg_bb, int pre, int S)
+{
+	__shared__ double2 pb[2 * MB_NOFDM];  // the preamble symbols Moose looks at (decimated rate)
+	__shared__ double2 G[2][2][24];
+	__shared__ double f_sh;
+	const int b = blockIdx.x;
+	MbFeState &st = st_all[b];
+	if (st.phase != MB_FE_EXTRACT) return;
+	const T *x = x_all + (size_t)b * buf;
+	const int delay = st.delay;
+	const int np2 = pre / 2 == 0 ? 1 : pre / 2;  // ofdm.cc:548-555
+	const bool use_last = st.sync_trials == fe_c.trials_max && fe_c.use_last_freq && st.last_freq != 0;  // :1108-1111
+	if (!use_last) {
+		for (int k = threadIdx.x; k < np2 * MB_NOFDM; k += blockDim.x)
+			pb[k] = fir_on_demand(x, delay + 4 * k, buf, carrier, true, fe_c.fc, fe_c.c_data);
+		__syncthreads();
+		// Moose (ofdm.cc:540-595): each half symbol is repeated before the 256-point FFT, so only the even bins carry signal and
+		// they equal the 128-point DFT of the half; 24 of the 50 active carriers are even (bins 232..254 and 2..24).
+		double2 mul = make_double2(0.0, 0.0);
+		for (int j = 0; j < np2; j++) {
+			const int bin = threadIdx.x % 24, half = (threadIdx.x / 24) & 1;
+			if (threadIdx.x < 48) {
+				const int k128 = bin < 12 ? 116 + bin : bin - 11;
+				double gr = 0, gi = 0;
+				const double2 *g = pb + j * MB_NOFDM + MB_NGI + half * 128;
+				for (int n = 0; n < 128; n++) {
+					double s, co;
+					sincospi(-2.0 * (double)((k128 * n) & 127) / 128.0, &s, &co);
+					gr += g[n].x * co - g[n].y * s;
+					gi += g[n].x * s + g[n].y * co;
+				}
+				G[j & 1][half][bin] = make_double2(gr, gi);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0)
+				for (int q = 0; q < 24; q++) {  // mul += conj(d2) * d1
+					const double2 d1 = G[j & 1][0][q], d2 = G[j & 1][1][q];
+					mul.x += d2.x * d1.x + d2.y * d1.y;
+					mul.y += d2.x * d1.y - d2.y * d1.x;
+				}
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) {
+			double th;  // get_angle, misc.cc:34-56
+			if (mul.x == 0) th = M_PI / 2;
+			else if (mul.x > 0) th = atan(mul.y / mul.x);
+			else if (mul.y >= 0) th = atan(mul.y / mul.x) + M_PI;
+			else th = atan(mul.y / mul.x) - M_PI;
+			f_sh = (th / M_PI) * (fe_c.bandwidth / (double)MB_NC);
+		}
+	} else if (threadIdx.x == 0) f_sh = st.last_freq;
+	__syncthreads();
+	const double fm = f_sh;
+	const bool corrected = fabs(fm) > fe_c.ignore_limit;  // :1126
+	const double f = corrected ? fe_c.fc + fm : fe_c.fc;
+	float2 *out = frames + (size_t)st.slot * S * MB_NOFDM;
+	for (int k = threadIdx.x; k < (S + pre) * MB_NOFDM; k += blockDim.x) {
+		if (k < pre * MB_NOFDM && !dbg_bb) continue;
+		const double2 v = fir_on_demand(x, delay + 4 * k, buf, carrier, !corrected, f, fe_c.c_data);
+		if (k >= pre * MB_NOFDM) out[k - pre * MB_NOFDM] = make_float2((float)v.x, (float)v.y);
+		if (dbg_bb) dbg_bb[(size_t)b * (S + pre) * MB_NOFDM + k] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		st.freq_offset_measured = fm;
+		st.cur_kind = 1, st.cur_f = f;
+		st.phase = MB_FE_TAIL_WAIT;
+	}
+}
+
+// receive_byte() entry (:646-663): reset the per-call fields, take the link state, ask for the full-buffer coarse run (:691)
+__global__ void k_fe_begin(MbFeState *__restrict__ st_all, const MbReceiveStats *__restrict__ in, int n, int buf, int pre)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	MbFeState st;
+	memset(&st, 0, sizeof(st));
+	st.last_delay = in[b].delay_of_last_decoded_message;
+	st.last_freq = in[b].freq_offset_of_last_decoded_message;
+	st.phase = MB_FE_COARSE_WAIT;
+	st.cur_kind = 0, st.cur_f = fe_c.fc;
+	st.slot = -1;
+	request_sc(st, 0, 0, buf, 100, pre);
+	st_all[b] = st;
+}
+
+__global__ void k_fe_finish(const MbFeState *__restrict__ st_all, MbReceiveStats *__restrict__ out, int n)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	const MbFeState &st = st_all[b];
+	MbReceiveStats r;
+	r.iterations_done = st.iterations_done, r.delay = st.delay, r.delay_of_last_decoded_message = st.last_delay, r.sync_trials = st.sync_trials;
+	r.message_decoded = st.message_decoded, r.crc = st.crc, r.all_zeros = st.all_zeros, r.reserved = 0;
+	r.freq_offset = st.freq_offset, r.freq_offset_of_last_decoded_message = st.last_freq, r.SNR = st.SNR;
+	r.signal_stregth_dbm = st.signal_dbm, r.coarse_metric = st.coarse_metric;
+	out[b] = r;
+}
+
+}  // namespace
+
+// ---- host side: tables and launchers ----
+
+// cl_FIR::design, LPF + HAMMING (fir_filter.cc:45-163) with the receive filters' parameters (physical_config.cc:93-101).
+static void fir_design_lpf_hamming(double fcut, double tbw, double fs, double *c)
+{
+	int n = (int)(4.0 / (tbw / (fs / 2.0)));
+	if (n % 2 == 0) n++;
+	const double Ts = 1.0 / (fs);
+	double temp;
+	c[n / 2] = 1;
+	for (int i = 0; i < n / 2; i++) {
+		temp = 2 * M_PI * fcut * (double)(n / 2 - i) * Ts;
+		c[i] = sin(temp) / temp;
+		c[n - i - 1] = c[i];
+	}
+	temp = 0;
+	for (int i = 0; i < n; i++) temp += c[i];
+	for (int i = 0; i < n; i++) c[i] /= temp;
+	for (int i = 0; i < n; i++) c[i] *= 0.54 - 0.46 * cos(2.0 * M_PI * (double)i / (n - 1));
+}
+
+void mb_fe_host_const(MbFeConst *k)
+{
+	memset(k, 0, sizeof(*k));
+	k->fs = 48000.0;                           // physical_config.cc:78
+	k->bandwidth = 48000.0 * 50.0 / 256 / 4;   // :81
+	k->fc = 0.0 + (k->bandwidth / 2 + 300);    // :88 (carrier_frequency_offset = 0)
+	k->amp = sqrt(2.0);                        // telecom_system.cc:69
+	k->Ts = 1.0 / k->fs;
+	k->ignore_limit = (double)0.1f;            // physical_config.cc:59, stored in a float
+	k->trials_max = 2, k->use_last_time = 1, k->use_last_freq = 1;  // :85-87
+	fir_design_lpf_hamming(0.9 * k->bandwidth / 2, 3000, k->fs, k->c_ts);
+	fir_design_lpf_hamming(1.0 * k->bandwidth / 2, 3000, k->fs, k->c_data);
+}
+
+int mb_fe_buffer_nsymb(int Nsymb, int pre)
+{  // data_container.cc:133-143
+	const double sym_time_ms = 1000.0 * MB_NOFDM * 4 / 48000.0;
+	const int turnaround_symb = (int)ceil(1200.0 / sym_time_ms) + 4;
+	const int frame_symb = pre + Nsymb;
+	int min_buf = frame_symb * 2;
+	if (frame_symb + turnaround_symb > min_buf) min_buf = frame_symb + turnaround_symb;
+	if (min_buf < 32) min_buf = 32;
+	return min_buf;
+}
+
+// (cos, sin)(2 pi fc i Ts) by the host's libm, the same calls in the same expression order as ofdm.cc:2332-2333
+void mb_fe_host_carrier(const MbFeConst &k, double *cs, int n)
+{
+	const double sampling_interval = 1.0 / k.fs;
+	for (int i = 0; i < n; i++) {
+		cs[2 * i] = cos(2 * M_PI * k.fc * (double)i * sampling_interval);
+		cs[2 * i + 1] = sin(2 * M_PI * k.fc * (double)i * sampling_interval);
+	}
+}
+
+cudaError_t mb_fe_init(const MbFeConst &k) { return cudaMemcpyToSymbol(fe_c, &k, sizeof(k)); }
+
+template <typename T>
+static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
+{
+	const int nblk = (a.buf + 255) / 256;
+	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
+	return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
+{
+	const int nblk = (a.buf + 255) / 256;
+	if (run_sc) {
+		k_fe_window<T><<<dim3(8, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.st, a.win, a.win_stride);
+		k_fe_sc<<<dim3((a.vals_stride + kScThreads - 1) / kScThreads, a.n), kScThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.vals, a.vals_stride, a.pre);
+	}
+	k_fe_decide<T><<<a.n, kDecideThreads, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.vals, a.vals_stride, a.energy_part, nblk,
+							a.tail_stats, a.tail_payload, a.tail_payload_stride, a.payload_out, a.frame_bytes, a.pre, a.S,
+							a.buffer_Nsymb, a.counters);
+	return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t fe_extract_t(const MbFeArgs &a, cudaStream_t s)
+{
+	k_fe_extract<T><<<a.n, 256, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.frames, a.dbg_bb, a.pre, a.S);
+	return cudaGetLastError();
+}
+
+cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s) { return a.x_is_f32 ? fe_p2b_full_t<float>(a, s) : fe_p2b_full_t<double>(a, s); }
+cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s) { return a.x_is_f32 ? fe_step_t<float>(a, run_sc, s) : fe_step_t<double>(a, run_sc, s); }
+cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s) { return a.x_is_f32 ? fe_extract_t<float>(a, s) : fe_extract_t<double>(a, s); }
+
+cudaError_t mb_fe_begin(const MbFeArgs &a, const MbReceiveStats *d_stats_in, cudaStream_t s)
+{
+	k_fe_begin<<<(a.n + 127) / 128, 128, 0, s>>>(a.st, d_stats_in, a.n, a.buf, a.pre);
+	return cudaGetLastError();
+}
+
+cudaError_t mb_fe_finish(const MbFeArgs &a, MbReceiveStats *d_stats_out, cudaStream_t s)
+{
+	k_fe_finish<<<(a.n + 127) / 128, 128, 0, s>>>(a.st, d_stats_out, a.n);
+	return cudaGetLastError();
+}

@@ -48,3 +48,77 @@ cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaS
 cudaError_t mb_demod_init();  // opt-in shared memory attributes, occupancy of every instantiation
 int mb_demod_ctas_per_sm(int Nsymb, int M, int estimator, int phase_only);  // resident CTAs per SM (0 = no such instantiation)
 cudaError_t mb_ldpc_init();
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RX front-end (mb_frontend.cu): pass-band capture buffers -> synchronised base-band frames for the tail.
+// ---------------------------------------------------------------------------------------------------------------------
+#define MB_FE_SYM 1088   // pass-band samples per OFDM symbol: Nofdm 272 x frequency_interpolation_rate 4
+#define MB_FE_TAPS 33    // both receive FIRs: (int)(4 / (3000 / 24000)) = 32 -> odd 33 (fir_filter.cc:56-61, physical_config.cc:93-101)
+
+enum MbFePhase {
+	MB_FE_COARSE_WAIT = 0,  // waiting for the full-buffer coarse Schmidl-Cox run
+	MB_FE_REC_BOUNDS,       // waiting for the re-run of the bounds recovery   (telecom_system.cc:734-798)
+	MB_FE_GATE,             // energy / metric gates                           (:800-851)
+	MB_FE_REC_SILENCE,      // waiting for the re-run of the silence skip      (:861-924)
+	MB_FE_TRIAL,            // head of the trial loop                          (:931-1019)
+	MB_FE_FINE_WAIT,        // waiting for the fine Schmidl-Cox run
+	MB_FE_POSTDELAY,        // clamp + post-fine-sync energy fix               (:1020-1069)
+	MB_FE_EXTRACT,          // waiting for k_fe_extract
+	MB_FE_TAIL_WAIT,        // waiting for the tail's verdict
+	MB_FE_TRIALS_END,       // SKIP-H recovery check                           (:1436-1504)
+	MB_FE_REC_SKIPH,
+	MB_FE_DONE
+};
+
+struct MbFeConst {
+	double c_ts[MB_FE_TAPS + 1], c_data[MB_FE_TAPS + 1];  // FIR_rx_time_sync, FIR_rx_data
+	double fs, fc, amp, bandwidth, Ts, ignore_limit;
+	int32_t trials_max, use_last_time, use_last_freq, pad;
+};
+
+// Per-capture state: st_receive_stats fields (telecom_system.h:63-82) + the locals of receive_byte() + what the capture waits for.
+struct MbFeState {
+	double last_freq, SNR, freq_offset, coarse_metric, signal_dbm, cur_f, freq_offset_measured;
+	int32_t last_delay, delay, sync_trials, message_decoded, iterations_done, crc, all_zeros;
+	int32_t phase, pream_symb_loc, skip_h_count, skip_h_recovery_attempted;
+	int32_t cur_kind;    // what baseband_data_interpolated holds: 0 = time-sync filter at fc (materialised), 1 = data filter at cur_f (on demand)
+	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for
+	int32_t slot;        // tail slot of the running trial
+};
+
+struct MbFeArgs {
+	const void *x;       // [n][buf] pass-band samples, double or float
+	int32_t x_is_f32, n, buf, pre, S, buffer_Nsymb, frame_bytes;
+	const double2 *carrier;  // [>= buf] (cos, sin)(2 pi fc i Ts), host libm
+	MbFeState *st;       // [n]
+	double2 *bbi;        // [n][buf]  time-sync base-band
+	double *energy_part; // [n][ceil(buf/256)]
+	double2 *win;        // [n][win_stride] fine-sync window of the data-filter base-band
+	int32_t win_stride;
+	double *vals;        // [n][vals_stride] correlation metrics of the pending run
+	int32_t vals_stride;
+	float2 *frames;      // [n][S][272] tail input, by slot
+	double2 *dbg_bb;     // optional [n][(pre+S)*272] fp64 copy of baseband_data (by capture)
+	const MbRxStats *tail_stats;   // [n] by slot
+	const uint8_t *tail_payload;   // [n][tail_payload_stride] by slot
+	int32_t tail_payload_stride;
+	uint8_t *payload_out;          // [n][frame_bytes] by capture
+	int32_t *counters;   // [4]: tail slots handed out, captures not done, captures waiting for a Schmidl-Cox run
+};
+
+// Mirrors mercury_b200_receive_stats (include/mercury_b200.h); 72 bytes.
+struct MbReceiveStats {
+	int32_t iterations_done, delay, delay_of_last_decoded_message, sync_trials;
+	int32_t message_decoded, crc, all_zeros, reserved;
+	double freq_offset, freq_offset_of_last_decoded_message, SNR, signal_stregth_dbm, coarse_metric;
+};
+
+void mb_fe_host_const(MbFeConst *k);
+cudaError_t mb_fe_begin(const MbFeArgs &a, const MbReceiveStats *d_stats_in, cudaStream_t s);  // states <- link state, first Schmidl-Cox request
+cudaError_t mb_fe_finish(const MbFeArgs &a, MbReceiveStats *d_stats_out, cudaStream_t s);
+int mb_fe_buffer_nsymb(int Nsymb, int pre);
+void mb_fe_host_carrier(const MbFeConst &k, double *cs, int n);
+cudaError_t mb_fe_init(const MbFeConst &k);
+cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s);
+cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s);  // [k_fe_window, k_fe_sc,] k_fe_decide
+cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s);

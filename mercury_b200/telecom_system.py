@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Geometry, RxStats
+from ._lib import Geometry, ReceiveStats, RxStats
 
 YES, NO = 1, 0
 DECODER_SPA, DECODER_MINSUM = 0, 1
@@ -24,6 +24,20 @@ HANDOFF_FLOATS = 2400  # MERCURY_B200_HANDOFF_FLOATS: float32 per frame of the s
 STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("message_decoded", "<i4"),
                         ("SNR", "<f4"), ("variance", "<f4"), ("mean_H", "<f4"), ("reserved", "<i4")])
 assert STATS_DTYPE.itemsize == C.sizeof(RxStats) == 32
+# mercury_b200_receive_stats (the whole receive_byte(), pass-band in): st_receive_stats of the OFDM branch
+RECEIVE_STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("delay", "<i4"), ("delay_of_last_decoded_message", "<i4"), ("sync_trials", "<i4"),
+                                ("message_decoded", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("reserved", "<i4"),
+                                ("freq_offset", "<f8"), ("freq_offset_of_last_decoded_message", "<f8"), ("SNR", "<f8"),
+                                ("signal_stregth_dbm", "<f8"), ("coarse_metric", "<f8")])
+assert RECEIVE_STATS_DTYPE.itemsize == C.sizeof(ReceiveStats) == 72
+SAMPLES_F64, SAMPLES_F32 = 0, 1
+
+
+def new_receive_stats(n):
+    """n link-state records of a fresh link (telecom_system.cc:42,49: no last decoded message yet)."""
+    st = np.zeros(n, RECEIVE_STATS_DTYPE)
+    st["delay_of_last_decoded_message"] = -1
+    return st
 
 
 class MercuryB200Error(RuntimeError):
@@ -109,6 +123,44 @@ class TelecomSystemB200:
         st = RxStats()
         self._check(self._L.mercury_b200_receive_baseband(self._h, _vp(bb), _vp(out), C.byref(st)))
         return out, {n: getattr(st, n) for n, _ in RxStats._fields_ if n != "reserved"}
+
+    def get_capture_samples(self):
+        """Pass-band samples receive_byte() is handed: Nofdm * buffer_Nsymb * 4 (data_container.cc:133-153)."""
+        return self._L.mercury_b200_get_capture_samples(self._h)
+
+    def receive_byte(self, data, stats=None):
+        """st_receive_stats cl_telecom_system::receive_byte(double* data, int* out) (telecom_system.cc:646-1518), whole: `data` is
+        one pass-band capture (float64).  `stats` carries the link state between calls (new_receive_stats(1) for a new link).
+        Returns (out, stats): out = one int per payload byte."""
+        pb = np.ascontiguousarray(data, np.float64).reshape(-1)
+        if pb.size != self.get_capture_samples():
+            raise ValueError("data must hold get_capture_samples() doubles")
+        st = new_receive_stats(1) if stats is None else stats
+        out = np.zeros(self.geometry["frame_bytes"], np.int32)
+        self._check(self._L.mercury_b200_receive_byte(self._h, _vp(pb), _vp(out), st.ctypes.data_as(C.POINTER(ReceiveStats))))
+        return out, st
+
+    def receive_byte_batch(self, captures, stats=None, want_baseband=False):
+        """n captures of independent links, host buffers (float64 or float32 [n, capture_samples]).
+        Returns (payload[n, frame_bytes] u8, stats[n], baseband[n, (pre+Nsymb)*272] complex128 | None)."""
+        x = np.ascontiguousarray(captures)
+        if x.dtype not in (np.float64, np.float32):
+            raise TypeError("captures must be float64 or float32")
+        cs = self.get_capture_samples()
+        if x.size % cs:
+            raise ValueError("captures size is not a whole number of capture buffers")
+        n = x.size // cs
+        st = new_receive_stats(n) if stats is None else stats
+        payload = np.zeros((n, self.geometry["frame_bytes"]), np.uint8)
+        g = self.geometry
+        bb = np.zeros((n, (g["preamble_nSymb"] + g["Nsymb"]) * g["Nofdm"]), np.complex128) if want_baseband else None
+        self._check(self._L.mercury_b200_receive_byte_batch(self._h, _vp(x), SAMPLES_F32 if x.dtype == np.float32 else SAMPLES_F64, n,
+                                                            _vp(payload), _vp(st), _vp(bb)))
+        return payload, st, bb
+
+    def receive_byte_batch_device(self, d_captures, sample_format, n, d_payload, d_stats, stream=0):
+        self._check(self._L.mercury_b200_receive_byte_batch_device(self._h, _vp(d_captures), int(sample_format), int(n), _vp(d_payload),
+                                                                   _vp(d_stats), C.c_void_p(stream)))
 
     # ---- batched entry points ----------------------------------------------------------------------------
     def demod_decode_batch(self, baseband, want_llr=False, out=None):

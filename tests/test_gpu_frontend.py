@@ -1,0 +1,105 @@
+"""GPU parity of the RX front-end row: mercury_b200_receive_byte(_batch) -- pass-band capture in, payload
+out -- against the oracle's whole receive_byte() (the unmodified reference when oracle/_ref travelled to this box, else the C
+restatement) on the capture scenarios of tests/frontend_cases.py and against the committed reference fixtures.
+
+Bars: the sync decisions (delay, sync_trials), the Schmidl-Cox metric, the verdict fields and the payload bytes are bit-exact;
+continuous reported values within the tolerances written below; the post-synchronisation base-band within 1e-9 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import mercury_b200 as mb
+from oracle import port, ref
+from tests import frontend_cases as fc
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ("delay", "sync_trials", "decoded", "crc", "all_zeros", "iterations", "coarse_metric")
+
+
+@pytest.fixture(scope="module")
+def ts():
+    t = mb.TelecomSystemB200(0)
+    yield t
+    t.close()
+
+
+def _compare(o, st, payload, bb, label):
+    got = dict(delay=int(st["delay"]), sync_trials=int(st["sync_trials"]), decoded=int(st["message_decoded"]), crc=int(st["crc"]),
+               all_zeros=int(st["all_zeros"]), iterations=int(st["iterations_done"]), coarse_metric=float(st["coarse_metric"]))
+    for k in EXACT:
+        assert got[k] == o[k], (label, k, got[k], o[k])
+    assert int(st["delay_of_last_decoded_message"]) == o["last_delay"], label
+    assert abs(float(st["freq_offset_of_last_decoded_message"]) - o["last_freq"]) <= 1e-9, label
+    assert abs(float(st["freq_offset"]) - o["freq_offset"]) <= 1e-9, (label, float(st["freq_offset"]), o["freq_offset"])
+    assert abs(float(st["signal_stregth_dbm"]) - o["signal_dbm"]) <= 1e-9 or (np.isinf(o["signal_dbm"]) and np.isinf(st["signal_stregth_dbm"])), label
+    assert abs(float(st["SNR"]) - o["snr"]) <= 2e-3 * max(1.0, abs(o["snr"])), (label, float(st["SNR"]), o["snr"])
+    assert np.array_equal(payload.astype(np.int32), np.asarray(o["payload"], np.int32)), label
+    if bb is not None and (o["sync_trials"] > 0 or o["decoded"]):
+        ref_bb = o["baseband"]
+        err = np.abs(bb - ref_bb).max() / max(np.abs(ref_bb).max(), 1e-30)
+        assert err <= 1e-9, (label, err)
+
+
+@pytest.mark.parametrize("cfg", [0, 8, 10, 13, 16])
+def test_receive_byte_scenarios(ts, cfg):
+    if not ref.available():
+        pytest.skip("scenario frames come from the reference's transmit_byte (oracle/_ref not on this box)")
+    r = ref.Ref(cfg, 50)
+    ts.load_configuration(cfg, 50)
+    assert ts.get_capture_samples() == r.capture_samples()
+    cases = fc.CASES if cfg in (8, 16) else ["clean", "noise_light", "freq_offset", "late", "silence", "last_good_state"]
+    caps, oracle_out, states = [], [], mb.new_receive_stats(len(cases))
+    for i, case in enumerate(cases):
+        cap, pl, state = fc.make_capture(r, case, 100 * cfg + i)
+        caps.append(cap)
+        states["delay_of_last_decoded_message"][i] = state[0]
+        states["freq_offset_of_last_decoded_message"][i] = state[1]
+        oracle_out.append(r.receive_byte2(cap, *state))
+    caps = np.stack(caps)
+    # the whole batch in one call (exercises the per-capture state machine with captures in different phases) ...
+    payload, st, bb = ts.receive_byte_batch(caps, states.copy(), want_baseband=True)
+    for i, case in enumerate(cases):
+        _compare(oracle_out[i], st[i], payload[i], bb[i], f"cfg{cfg}/{case}/batch")
+    assert sum(o["decoded"] for o in oracle_out) >= 3
+    # ... float32 samples (exactly the values the reference saw: the scenario captures are float32-representable) ...
+    payload32, st32, _ = ts.receive_byte_batch(caps.astype(np.float32), states.copy())
+    assert np.array_equal(payload32, payload) and st32.tobytes() == st.tobytes()
+    # ... and the single-capture call in the reference's own types
+    for i in (0, len(cases) - 1):
+        one = states[i:i + 1].copy()
+        out, one = ts.receive_byte(caps[i], one)
+        _compare(oracle_out[i], one[0], out, None, f"cfg{cfg}/{cases[i]}/single")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "frontend_*.npz"))))
+def test_receive_byte_reference_fixture(ts, path):
+    g = np.load(path)
+    ts.load_configuration(int(g["config"]), int(g["ldpc_iters"]))
+    st = mb.new_receive_stats(1)
+    st["delay_of_last_decoded_message"][0] = int(g["state_in"][0])
+    st["freq_offset_of_last_decoded_message"][0] = float(g["state_in"][1])
+    payload, st, bb = ts.receive_byte_batch(g["capture"].astype(np.float64), st, want_baseband=True)
+    o = {k: (float(g["stats"][i]) if k in ("snr", "freq_offset", "coarse_metric", "signal_dbm") else int(g["stats"][i])) for i, k in enumerate(ref.STAT12)}
+    o.update(payload=g["rx_payload"], baseband=g["baseband"], last_delay=int(g["state_out"][0]), last_freq=float(g["state_out"][1]))
+    _compare(o, st[0], payload[0], bb[0], os.path.basename(path))
+
+
+def test_receive_byte_many_links_against_port(ts):
+    """256 captures of one mode in one call (several chunks when MERCURY_B200_FE_CHUNK is small): every capture against the C restatement."""
+    cfg = 16
+    src = ref.Ref(cfg, 50) if ref.available() else None
+    if src is None:
+        pytest.skip("needs the reference's transmit_byte for frames")
+    p = port.Port(cfg, 50)
+    ts.load_configuration(cfg, 50)
+    rng = np.random.default_rng(5)
+    n = 96
+    caps = np.stack([fc.make_capture(src, fc.CASES[int(rng.integers(0, 4))], 7000 + i)[0] for i in range(n)])
+    payload, st, _ = ts.receive_byte_batch(caps)
+    for i in range(n):
+        o = p.receive_byte2(caps[i])
+        _compare(o, st[i], payload[i], None, f"link{i}")
+    assert int(st["message_decoded"].sum()) >= n // 2
