@@ -45,7 +45,8 @@ struct FeWork {
 	size_t x_bytes = 0;
 	MbFeState *st = nullptr;
 	double2 *bbi = nullptr, *win = nullptr, *dbg_bb = nullptr;
-	double *energy_part = nullptr, *vals = nullptr;
+	double *energy_part = nullptr, *vals = nullptr, *pref_ts = nullptr, *pref_win = nullptr;
+	uint8_t *flags = nullptr;
 	float2 *frames = nullptr;
 	float *llr = nullptr;
 	MbRxStats *tail_stats = nullptr;
@@ -67,7 +68,7 @@ struct mercury_b200 {
 	MbFeConst fe_const;
 	bool fe_ready = false;
 	size_t fe_chunk = 1024;
-	uint64_t fe_rounds = 0;
+	uint64_t fe_rounds = 0, fe_exact = 0;
 	int device = -1;
 	std::vector<uint8_t> blob;
 	MbBlobHeader hdr;
@@ -481,7 +482,7 @@ namespace {
 
 void fe_free(FeWork &w)
 {
-	void *ptrs[] = {w.d_x, w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
+	void *ptrs[] = {w.d_x, w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.pref_ts, w.pref_win, w.flags, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	if (w.h_counters) cudaFreeHost(w.h_counters);
@@ -527,6 +528,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	if (w.cap >= n && w.buf >= buf && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
 	MB_CUDA(h, cudaDeviceSynchronize());
 	void **ptrs[] = {(void **)&w.st, (void **)&w.bbi, (void **)&w.win, (void **)&w.dbg_bb, (void **)&w.energy_part, (void **)&w.vals, (void **)&w.frames,
+			 (void **)&w.pref_ts, (void **)&w.pref_win, (void **)&w.flags,
 			 (void **)&w.llr, (void **)&w.tail_stats, (void **)&w.tail_payload, (void **)&w.payload, (void **)&w.stats};
 	for (void **p : ptrs) {
 		if (*p) cudaFree(*p);
@@ -540,6 +542,9 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.win, cap * kFeWin * sizeof(double2)));
 	MB_CUDA(h, cudaMalloc(&w.energy_part, cap * ((bufmax + 255) / 256) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.flags, cap * kFeVals));
+	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax + 1) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
 	MB_CUDA(h, cudaMalloc(&w.tail_stats, cap * sizeof(MbRxStats)));
@@ -566,6 +571,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	a.buf = MB_NOFDM * a.buffer_Nsymb * 4, a.pre = m.preamble_nSymb, a.S = m.Nsymb, a.frame_bytes = m.frame_bytes;
 	a.carrier = w.carrier, a.st = w.st, a.bbi = w.bbi, a.energy_part = w.energy_part;
 	a.win = w.win, a.win_stride = kFeWin, a.vals = w.vals, a.vals_stride = kFeVals;
+	a.flags = w.flags, a.pref_ts = w.pref_ts, a.pref_win = w.pref_win;
 	a.frames = w.frames, a.dbg_bb = dbg ? w.dbg_bb : nullptr;
 	a.tail_stats = w.tail_stats, a.tail_payload = w.tail_payload, a.tail_payload_stride = m.frame_bytes;
 	a.payload_out = d_payload, a.counters = w.counters;
@@ -573,18 +579,19 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	MB_CUDA(h, cudaMemsetAsync(d_payload, 0, n * m.frame_bytes, s));
 	MB_CUDA(h, mb_fe_begin(a, d_stats, s));
 	MB_CUDA(h, mb_fe_p2b_full(a, s));
-	h->launches += 2;
+	h->launches += 3;
 	bool run_sc = true;
 	// every round each capture either finishes or passes one of: coarse run, <= 2 recovery runs, 3 fine runs + 3 tails, SKIP-H
 	// recovery and 3 more trials -- 32 rounds is far above the longest path through receive_byte()
 	for (int round = 0; round < 32; round++) {
 		MB_CUDA(h, cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), s));
 		MB_CUDA(h, mb_fe_step(a, run_sc, s));
-		h->launches += run_sc ? 3 : 1;
+		h->launches += run_sc ? 5 : 1;
 		MB_CUDA(h, cudaMemcpyAsync(w.h_counters, w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 		MB_CUDA(h, cudaStreamSynchronize(s));
 		h->fe_rounds++;
 		const int n_slots = w.h_counters[0], not_done = w.h_counters[1];
+		h->fe_exact += (uint64_t)w.h_counters[3];
 		run_sc = w.h_counters[2] > 0;
 		if (n_slots > 0) {
 			MB_CUDA(h, mb_fe_extract(a, s));

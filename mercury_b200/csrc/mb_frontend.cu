@@ -18,7 +18,8 @@
 //
 // Control flow is a per-capture state machine in global memory advanced by k_fe_decide; the heavy stages are separate
 // kernels that act on whatever each capture is waiting for (MbFeState::phase), so a batch needs no host-side branching:
-//   k_fe_p2b_full -> loop { k_fe_window, k_fe_sc, k_fe_decide, k_fe_extract, tail (demod + LDPC kernels) } until all captures are done.
+//   k_fe_p2b_full, k_fe_prefix -> loop { k_fe_window, k_fe_prefix, k_fe_sc_approx, k_fe_sc_exact, k_fe_decide, k_fe_extract, tail (demod + LDPC
+//   kernels) } until all captures are done.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -122,15 +123,136 @@ __global__ void __launch_bounds__(256) k_fe_window(const T *__restrict__ x_all, 
 		win_all[(size_t)b * win_stride + i] = fir_on_demand(x, st.sc_start + i, buf, carrier, table, st.cur_f, fe_c.c_data);
 }
 
-// ---- Schmidl-Cox metric, one thread per candidate position, the reference's summation order (ofdm.cc:1891-1940) ----
-__global__ void __launch_bounds__(kScThreads) k_fe_sc(const MbFeState *__restrict__ st_all, const double2 *__restrict__ bbi_all, int buf,
-							const double2 *__restrict__ win_all, int win_stride, double *__restrict__ vals_all, int vals_stride, int pre)
+// ---- Schmidl-Cox metric (ofdm.cc:1891-1940) in two passes -------------------------------------------------------------
+// The reference's metric at a position is three running sums over 576 * pre sample pairs in a fixed order; only the ARGMAX over
+// the positions reaches the output (the delay), and it has to be the reference's own, ties included.  So:
+//   pass A  every position from exclusive prefix sums of |w|^2 and of the two lagged dot products (any summation order,
+//           absolute error ~1e-11): an approximate metric, and the capture's approximate maximum;
+//   pass B  the positions within kScTol of that maximum, and those whose norm sits on the 0.001 threshold, are re-evaluated
+//           with the reference's operation order in fp64 without FMA -> bit-identical values where it matters.
+// A position outside that band cannot hold the exact maximum (error bound << kScTol), and one whose norms are clearly below
+// the threshold is exactly 0 in the reference too, so the selection over {exact band values, approximate rest} returns the
+// reference's index.  Pass B is typically 1-3 positions per run (hundreds when a clean frame sits in exact silence).
+constexpr double kScTol = 1e-6;
+constexpr double kScThrBand = 1e-8;
+constexpr int kPrefThreads = 1024;
+
+struct Pref3 {
+	double e, p1, p2;
+};
+
+__device__ __forceinline__ Pref3 pref_terms(const double2 *w, int m, int len)
+{
+	Pref3 t;
+	const double2 u = w[m];
+	t.e = u.x * u.x + u.y * u.y;
+	t.p1 = t.p2 = 0.0;
+	if (m + MB_NFFT * 4 < len) {
+		const double2 v = w[m + MB_NFFT * 4];
+		t.p1 = u.x * v.x + u.y * v.y;
+	}
+	if (m + (MB_NFFT / 2) * 4 < len) {
+		const double2 v = w[m + (MB_NFFT / 2) * 4];
+		t.p2 = u.x * v.x + u.y * v.y;
+	}
+	return t;
+}
+
+// exclusive prefix sums CE, C1, C2 (each len + 1 doubles, stride pstride) of one source per capture: the time-sync base-band
+// (which = 0, once per capture) or the fine-sync window of the data-filter base-band (which = 1, when a run on it is pending)
+__global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__restrict__ st_all, const double2 *__restrict__ src_all, size_t src_stride, int len_fixed,
+							      int which, double *__restrict__ pref_all, size_t pstride)
+{
+	__shared__ Pref3 wsum[kPrefThreads / 32];
+	const int b = blockIdx.x;
+	int len = len_fixed;
+	if (which == 1) {
+		const MbFeState &st = st_all[b];
+		if (!st.sc_pending || st.sc_src != 1) return;
+		len = st.sc_size;
+	}
+	const double2 *w = src_all + (size_t)b * src_stride;
+	double *CE = pref_all + (size_t)b * 3 * pstride, *C1 = CE + pstride, *C2 = C1 + pstride;
+	const int per = (len + kPrefThreads - 1) / kPrefThreads;
+	const int m0 = threadIdx.x * per, m1 = min(len, m0 + per);
+	Pref3 acc = {0.0, 0.0, 0.0};
+	for (int m = m0; m < m1; m++) {
+		const Pref3 t = pref_terms(w, m, len);
+		acc.e += t.e, acc.p1 += t.p1, acc.p2 += t.p2;
+	}
+	// block-wide exclusive scan of the per-thread sums
+	Pref3 inc = acc;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int o = 1; o < 32; o <<= 1) {
+		const double e = __shfl_up_sync(0xffffffffu, inc.e, o), p1 = __shfl_up_sync(0xffffffffu, inc.p1, o), p2 = __shfl_up_sync(0xffffffffu, inc.p2, o);
+		if (lane >= o) inc.e += e, inc.p1 += p1, inc.p2 += p2;
+	}
+	if (lane == 31) wsum[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		Pref3 v = wsum[lane];
+		for (int o = 1; o < 32; o <<= 1) {
+			const double e = __shfl_up_sync(0xffffffffu, v.e, o), p1 = __shfl_up_sync(0xffffffffu, v.p1, o), p2 = __shfl_up_sync(0xffffffffu, v.p2, o);
+			if (lane >= o) v.e += e, v.p1 += p1, v.p2 += p2;
+		}
+		wsum[lane] = v;
+	}
+	__syncthreads();
+	Pref3 run = {inc.e - acc.e, inc.p1 - acc.p1, inc.p2 - acc.p2};
+	if (warp > 0) run.e += wsum[warp - 1].e, run.p1 += wsum[warp - 1].p1, run.p2 += wsum[warp - 1].p2;
+	for (int m = m0; m < m1; m++) {
+		CE[m] = run.e, C1[m] = run.p1, C2[m] = run.p2;
+		const Pref3 t = pref_terms(w, m, len);
+		run.e += t.e, run.p1 += t.p1, run.p2 += t.p2;
+	}
+	if (m1 == len && m0 < len) CE[len] = run.e, C1[len] = run.p1, C2[len] = run.p2;
+}
+
+__device__ __forceinline__ unsigned long long metric_key(double v) { return (unsigned long long)__double_as_longlong(v + 2.0); }  // monotone for v in [-1, 1]
+
+// pass A
+__global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restrict__ st_all, const double *__restrict__ pref_ts, size_t pstride_ts,
+							       const double *__restrict__ pref_win, size_t pstride_win, double *__restrict__ vals_all, int vals_stride,
+							       uint8_t *__restrict__ flags_all, int pre)
+{
+	const int b = blockIdx.y;
+	MbFeState &st = st_all[b];
+	if (!st.sc_pending) return;
+	const int k = blockIdx.x * kScThreads + threadIdx.x;
+	double v = -3.0;
+	if (k < st.sc_npos) {
+		const size_t ps = st.sc_src == 0 ? pstride_ts : pstride_win;
+		const double *CE = (st.sc_src == 0 ? pref_ts + (size_t)b * 3 * pstride_ts + st.sc_start : pref_win + (size_t)b * 3 * pstride_win) + (size_t)k * st.sc_step;
+		const double *C1 = CE + ps, *C2 = C1 + ps;
+		double cc = 0, na = 0, nb = 0;
+		for (int l = 0; l < pre; l++) {
+			const int o = l * MB_FE_SYM;
+			cc += (C1[o + 64] - C1[o]) + (C2[o + 576] - C2[o + 64]);
+			na += CE[o + 576] - CE[o];
+			nb += (CE[o + 1088] - CE[o + 576]) + (CE[o + 1088] - CE[o + 1024]);
+		}
+		const bool amb = fabs(na - 0.001) <= kScThrBand || fabs(nb - 0.001) <= kScThrBand;
+		v = (na < 0.001 || nb < 0.001) ? 0.0 : cc / sqrt(na * nb);
+		vals_all[(size_t)b * vals_stride + k] = v;
+		flags_all[(size_t)b * vals_stride + k] = amb ? 1 : 0;
+	}
+	for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0 && v > -3.0) atomicMax(&st.sc_max_key, metric_key(v));
+}
+
+// pass B: the reference's summation order (ofdm.cc:1901-1930), one thread per band position
+__global__ void __launch_bounds__(kScThreads) k_fe_sc_exact(const MbFeState *__restrict__ st_all, const double2 *__restrict__ bbi_all, int buf,
+							      const double2 *__restrict__ win_all, int win_stride, double *__restrict__ vals_all, int vals_stride,
+							      const uint8_t *__restrict__ flags_all, int pre, int *__restrict__ counters)
 {
 	const int b = blockIdx.y;
 	const MbFeState &st = st_all[b];
 	if (!st.sc_pending) return;
 	const int k = blockIdx.x * kScThreads + threadIdx.x;
 	if (k >= st.sc_npos) return;
+	const double approx = vals_all[(size_t)b * vals_stride + k];
+	if (!flags_all[(size_t)b * vals_stride + k] && metric_key(approx + kScTol) < st.sc_max_key) return;
+	atomicAdd(&counters[3], 1);
 	const double2 *in = (st.sc_src == 0 ? bbi_all + (size_t)b * buf + st.sc_start : win_all + (size_t)b * win_stride) + (size_t)k * st.sc_step;
 	double cc = 0, na = 0, nb = 0;
 	for (int l = 0; l < pre; l++) {
@@ -271,6 +393,7 @@ __device__ __forceinline__ void request_sc(MbFeState &st, int src, int start, in
 	st.sc_src = src, st.sc_start = start, st.sc_size = size, st.sc_step = step;
 	const int span = size - pre * MB_FE_SYM;
 	st.sc_npos = span > 0 ? (span + step - 1) / step : 0;
+	st.sc_max_key = 0;
 }
 
 template <typename T>
@@ -500,6 +623,7 @@ __global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_a
 						      float2 *__restrict__ frames, double2 *__restrict__ dbg_bb, int pre, int S)
 {
 	__shared__ double2 pb[2 * MB_NOFDM];  // the preamble symbols Moose looks at (decimated rate)
+	__shared__ double2 lt[1024 + MB_FE_TAPS - 1];
 	__shared__ double2 G[2][2][24];
 	__shared__ double f_sh;
 	const int b = blockIdx.x;
@@ -553,11 +677,26 @@ __global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_a
 	const bool corrected = fabs(fm) > fe_c.ignore_limit;  // :1126
 	const double f = corrected ? fe_c.fc + fm : fe_c.fc;
 	float2 *out = frames + (size_t)st.slot * S * MB_NOFDM;
-	for (int k = threadIdx.x; k < (S + pre) * MB_NOFDM; k += blockDim.x) {
-		if (k < pre * MB_NOFDM && !dbg_bb) continue;
-		const double2 v = fir_on_demand(x, delay + 4 * k, buf, carrier, !corrected, f, fe_c.c_data);
-		if (k >= pre * MB_NOFDM) out[k - pre * MB_NOFDM] = make_float2((float)v.x, (float)v.y);
-		if (dbg_bb) dbg_bb[(size_t)b * (S + pre) * MB_NOFDM + k] = v;
+	// tiles of 256 decimated outputs = 1024 pass-band samples (+ 32 of filter halo): every pass-band sample is mixed once (one sincos
+	// when the carrier is the Moose-corrected one), then each thread runs the 33 taps of its output from shared memory
+	const int k_begin = dbg_bb ? 0 : pre * MB_NOFDM, k_end = (S + pre) * MB_NOFDM;
+	for (int k0 = k_begin; k0 < k_end; k0 += 256) {
+		const int p0 = delay + 4 * k0 - MB_FE_TAPS / 2;
+		__syncthreads();
+		for (int i = threadIdx.x; i < 1024 + MB_FE_TAPS - 1; i += 256) lt[i] = mixed_sample(x, p0 + i, buf, carrier, !corrected, f);
+		__syncthreads();
+		const int k = k0 + threadIdx.x;
+		if (k < k_end) {
+			double ar = 0, ai = 0;
+#pragma unroll
+			for (int j = 0; j < MB_FE_TAPS; j++) {
+				const double2 l = lt[4 * threadIdx.x + MB_FE_TAPS - 1 - j];
+				ar = dadd(ar, dmul(l.x, fe_c.c_data[j]));
+				ai = dadd(ai, dmul(l.y, fe_c.c_data[j]));
+			}
+			if (k >= pre * MB_NOFDM) out[k - pre * MB_NOFDM] = make_float2((float)ar, (float)ai);
+			if (dbg_bb) dbg_bb[(size_t)b * (S + pre) * MB_NOFDM + k] = make_double2(ar, ai);
+		}
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -661,6 +800,7 @@ static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
 {
 	const int nblk = (a.buf + 255) / 256;
 	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
+	k_fe_prefix<<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, (size_t)a.buf, a.buf, 0, a.pref_ts, (size_t)a.buf + 1);
 	return cudaGetLastError();
 }
 
@@ -670,7 +810,10 @@ static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
 	const int nblk = (a.buf + 255) / 256;
 	if (run_sc) {
 		k_fe_window<T><<<dim3(8, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.st, a.win, a.win_stride);
-		k_fe_sc<<<dim3((a.vals_stride + kScThreads - 1) / kScThreads, a.n), kScThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.vals, a.vals_stride, a.pre);
+		k_fe_prefix<<<a.n, kPrefThreads, 0, s>>>(a.st, a.win, (size_t)a.win_stride, 0, 1, a.pref_win, (size_t)a.win_stride + 1);
+		const dim3 grid((a.vals_stride + kScThreads - 1) / kScThreads, a.n);
+		k_fe_sc_approx<<<grid, kScThreads, 0, s>>>(a.st, a.pref_ts, (size_t)a.buf + 1, a.pref_win, (size_t)a.win_stride + 1, a.vals, a.vals_stride, a.flags, a.pre);
+		k_fe_sc_exact<<<grid, kScThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.vals, a.vals_stride, a.flags, a.pre, a.counters);
 	}
 	k_fe_decide<T><<<a.n, kDecideThreads, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.vals, a.vals_stride, a.energy_part, nblk,
 							a.tail_stats, a.tail_payload, a.tail_payload_stride, a.payload_out, a.frame_bytes, a.pre, a.S,

@@ -84,6 +84,7 @@ struct MbFeState {
 	int32_t cur_kind;    // what baseband_data_interpolated holds: 0 = time-sync filter at fc (materialised), 1 = data filter at cur_f (on demand)
 	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for
 	int32_t slot;        // tail slot of the running trial
+	unsigned long long sc_max_key;  // approximate maximum of the pending run (pass A of the two-pass Schmidl-Cox), order-preserving key
 };
 
 struct MbFeArgs {
@@ -97,13 +98,16 @@ struct MbFeArgs {
 	int32_t win_stride;
 	double *vals;        // [n][vals_stride] correlation metrics of the pending run
 	int32_t vals_stride;
+	uint8_t *flags;      // [n][vals_stride] positions whose norms sit on the 0.001 threshold (forced into the exact pass)
+	double *pref_ts;     // [n][3][buf + 1]        exclusive prefix sums over the time-sync base-band: |w|^2, lag-1024 and lag-512 dot products
+	double *pref_win;    // [n][3][win_stride + 1] the same over the fine-sync window of the data-filter base-band
 	float2 *frames;      // [n][S][272] tail input, by slot
 	double2 *dbg_bb;     // optional [n][(pre+S)*272] fp64 copy of baseband_data (by capture)
 	const MbRxStats *tail_stats;   // [n] by slot
 	const uint8_t *tail_payload;   // [n][tail_payload_stride] by slot
 	int32_t tail_payload_stride;
 	uint8_t *payload_out;          // [n][frame_bytes] by capture
-	int32_t *counters;   // [4]: tail slots handed out, captures not done, captures waiting for a Schmidl-Cox run
+	int32_t *counters;   // [4]: tail slots handed out, captures not done, captures waiting for a Schmidl-Cox run, exact (pass B) evaluations
 };
 
 // Mirrors mercury_b200_receive_stats (include/mercury_b200.h); 72 bytes.
