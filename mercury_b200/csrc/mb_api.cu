@@ -540,10 +540,10 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.st, cap * sizeof(MbFeState)));
 	MB_CUDA(h, cudaMalloc(&w.bbi, cap * bufmax * sizeof(double2)));
 	MB_CUDA(h, cudaMalloc(&w.win, cap * kFeWin * sizeof(double2)));
-	MB_CUDA(h, cudaMalloc(&w.energy_part, cap * ((bufmax + 255) / 256) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.energy_part, cap * ((bufmax + 255) / 256) * sizeof(double)));  // >= one partial per 1024-sample tile
 	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.flags, cap * kFeVals));
-	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax + 1) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));

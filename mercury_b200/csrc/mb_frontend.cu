@@ -82,28 +82,48 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 }
 
 // ---- full-buffer mix + time-sync FIR (telecom_system.cc:676) and the energy partials of measure_signal_stregth ----
+// A CTA owns 1024 consecutive outputs; each thread runs the 33 taps of FOUR neighbouring outputs off a 4-deep sliding register
+// window (9 shared-memory reads per output instead of 33: the kernel is bound by the fp64 pipe, not by shared memory).  The
+// staging array is skewed by one element per four so that the stride-4 accesses of a quarter warp fall in distinct banks.
+constexpr int kP2bTile = 1024;
+__device__ __forceinline__ int p2b_skew(int i) { return i + (i >> 2); }
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_fe_p2b_full(const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, double2 *__restrict__ bbi_all,
+__global__ void __launch_bounds__(256, 2) k_fe_p2b_full(const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, double2 *__restrict__ bbi_all,
 						       double *__restrict__ energy_part, int nblk)
 {
-	__shared__ double2 l[256 + MB_FE_TAPS - 1];
+	__shared__ double2 l[(kP2bTile + MB_FE_TAPS - 1) * 5 / 4 + 2];
 	__shared__ double red[8];
-	const int b = blockIdx.y, t0 = blockIdx.x * 256;
+	const int b = blockIdx.y, t0 = blockIdx.x * kP2bTile;
 	const T *x = x_all + (size_t)b * buf;
-	for (int i = threadIdx.x; i < 256 + MB_FE_TAPS - 1; i += 256) l[i] = mixed_sample(x, t0 - MB_FE_TAPS / 2 + i, buf, carrier, true, 0.0);
+	for (int i = threadIdx.x; i < kP2bTile + MB_FE_TAPS - 1; i += 256) l[p2b_skew(i)] = mixed_sample(x, t0 - MB_FE_TAPS / 2 + i, buf, carrier, true, 0.0);
 	__syncthreads();
-	const int o = t0 + threadIdx.x;
+	const int o = t0 + 4 * threadIdx.x;
 	double e = 0;
-	if (o < buf) {
-		double ar = 0, ai = 0;
+	if (o < buf) {  // buf is a multiple of 4
+		// output o + r, tap j uses l[o + r + 16 - j] = staged index 4 t + r + 32 - j
+		double ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
+		const int base = 5 * threadIdx.x;  // p2b_skew(4 t + c) = 5 t + c + (c >> 2)
+		double2 w[4];
+#pragma unroll
+		for (int r = 1; r < 4; r++) w[r] = l[base + (32 + r) + ((32 + r) >> 2)];
 #pragma unroll
 		for (int j = 0; j < MB_FE_TAPS; j++) {
-			const double2 v = l[threadIdx.x + MB_FE_TAPS - 1 - j];
-			ar = dadd(ar, dmul(v.x, fe_c.c_ts[j]));
-			ai = dadd(ai, dmul(v.y, fe_c.c_ts[j]));
+			w[0] = l[base + (32 - j) + ((32 - j) >> 2)];
+			const double cj = fe_c.c_ts[j];
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				ar[r] = dadd(ar[r], dmul(w[r].x, cj));
+				ai[r] = dadd(ai[r], dmul(w[r].y, cj));
+			}
+			w[3] = w[2], w[2] = w[1], w[1] = w[0];
 		}
-		bbi_all[(size_t)b * buf + o] = make_double2(ar, ai);
-		e = ar * ar + ai * ai;
+		double2 *out = bbi_all + (size_t)b * buf + o;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			out[r] = make_double2(ar[r], ai[r]);
+			e += ar[r] * ar[r] + ai[r] * ai[r];
+		}
 	}
 	e = block_sum(e, red);
 	if (threadIdx.x == 0) energy_part[(size_t)b * nblk + blockIdx.x] = e;
@@ -158,54 +178,60 @@ __device__ __forceinline__ Pref3 pref_terms(const double2 *w, int m, int len)
 	return t;
 }
 
-// exclusive prefix sums CE, C1, C2 (each len + 1 doubles, stride pstride) of one source per capture: the time-sync base-band
-// (which = 0, once per capture) or the fine-sync window of the data-filter base-band (which = 1, when a run on it is pending)
-__global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__restrict__ st_all, const double2 *__restrict__ src_all, size_t src_stride, int len_fixed,
-							      int which, double *__restrict__ pref_all, size_t pstride)
+// Exclusive prefix sums CE, C1, C2 of one source per capture, one entry every RES samples (entry r = sum over samples < RES * r):
+//   RES 4, once per capture: the whole time-sync base-band, for the coarse runs (their positions and every segment edge are
+//          multiples of 4: step 100, symbol 1088, GI 64, half symbol 512);
+//   RES 1, per fine run: the (pre + 4)-symbol search window, of the time-sync base-band (trial 0) or of the data-filter window.
+// A CTA walks its capture in coalesced tiles of 1024 * RES samples with a running carry.
+template <int RES>
+__global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__restrict__ st_all, const double2 *__restrict__ bbi_all, int buf,
+							      const double2 *__restrict__ win_all, int win_stride, double *__restrict__ pref_all, size_t pstride)
 {
 	__shared__ Pref3 wsum[kPrefThreads / 32];
 	const int b = blockIdx.x;
-	int len = len_fixed;
-	if (which == 1) {
+	const double2 *w = bbi_all + (size_t)b * buf;
+	int len = buf;
+	if (RES == 1) {
 		const MbFeState &st = st_all[b];
-		if (!st.sc_pending || st.sc_src != 1) return;
+		if (!st.sc_pending || st.sc_step != 1) return;
 		len = st.sc_size;
+		w = st.sc_src == 0 ? w + st.sc_start : win_all + (size_t)b * win_stride;
 	}
-	const double2 *w = src_all + (size_t)b * src_stride;
 	double *CE = pref_all + (size_t)b * 3 * pstride, *C1 = CE + pstride, *C2 = C1 + pstride;
-	const int per = (len + kPrefThreads - 1) / kPrefThreads;
-	const int m0 = threadIdx.x * per, m1 = min(len, m0 + per);
-	Pref3 acc = {0.0, 0.0, 0.0};
-	for (int m = m0; m < m1; m++) {
-		const Pref3 t = pref_terms(w, m, len);
-		acc.e += t.e, acc.p1 += t.p1, acc.p2 += t.p2;
-	}
-	// block-wide exclusive scan of the per-thread sums
-	Pref3 inc = acc;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (int o = 1; o < 32; o <<= 1) {
-		const double e = __shfl_up_sync(0xffffffffu, inc.e, o), p1 = __shfl_up_sync(0xffffffffu, inc.p1, o), p2 = __shfl_up_sync(0xffffffffu, inc.p2, o);
-		if (lane >= o) inc.e += e, inc.p1 += p1, inc.p2 += p2;
-	}
-	if (lane == 31) wsum[warp] = inc;
-	__syncthreads();
-	if (warp == 0) {
-		Pref3 v = wsum[lane];
+	Pref3 carry = {0.0, 0.0, 0.0};
+	for (int t0 = 0; t0 < len; t0 += kPrefThreads * RES) {
+		const int m = t0 + threadIdx.x * RES;
+		Pref3 acc = {0.0, 0.0, 0.0};
+#pragma unroll
+		for (int r = 0; r < RES; r++)
+			if (m + r < len) {
+				const Pref3 t = pref_terms(w, m + r, len);
+				acc.e += t.e, acc.p1 += t.p1, acc.p2 += t.p2;
+			}
+		Pref3 inc = acc;
 		for (int o = 1; o < 32; o <<= 1) {
-			const double e = __shfl_up_sync(0xffffffffu, v.e, o), p1 = __shfl_up_sync(0xffffffffu, v.p1, o), p2 = __shfl_up_sync(0xffffffffu, v.p2, o);
-			if (lane >= o) v.e += e, v.p1 += p1, v.p2 += p2;
+			const double e = __shfl_up_sync(0xffffffffu, inc.e, o), p1 = __shfl_up_sync(0xffffffffu, inc.p1, o), p2 = __shfl_up_sync(0xffffffffu, inc.p2, o);
+			if (lane >= o) inc.e += e, inc.p1 += p1, inc.p2 += p2;
 		}
-		wsum[lane] = v;
+		__syncthreads();  // wsum of the previous tile has been consumed
+		if (lane == 31) wsum[warp] = inc;
+		__syncthreads();
+		if (warp == 0) {
+			Pref3 v = wsum[lane];
+			for (int o = 1; o < 32; o <<= 1) {
+				const double e = __shfl_up_sync(0xffffffffu, v.e, o), p1 = __shfl_up_sync(0xffffffffu, v.p1, o), p2 = __shfl_up_sync(0xffffffffu, v.p2, o);
+				if (lane >= o) v.e += e, v.p1 += p1, v.p2 += p2;
+			}
+			wsum[lane] = v;
+		}
+		__syncthreads();
+		Pref3 ex = {carry.e + (inc.e - acc.e), carry.p1 + (inc.p1 - acc.p1), carry.p2 + (inc.p2 - acc.p2)};
+		if (warp > 0) ex.e += wsum[warp - 1].e, ex.p1 += wsum[warp - 1].p1, ex.p2 += wsum[warp - 1].p2;
+		if (m <= len) CE[m / RES] = ex.e, C1[m / RES] = ex.p1, C2[m / RES] = ex.p2;
+		carry.e += wsum[31].e, carry.p1 += wsum[31].p1, carry.p2 += wsum[31].p2;
 	}
-	__syncthreads();
-	Pref3 run = {inc.e - acc.e, inc.p1 - acc.p1, inc.p2 - acc.p2};
-	if (warp > 0) run.e += wsum[warp - 1].e, run.p1 += wsum[warp - 1].p1, run.p2 += wsum[warp - 1].p2;
-	for (int m = m0; m < m1; m++) {
-		CE[m] = run.e, C1[m] = run.p1, C2[m] = run.p2;
-		const Pref3 t = pref_terms(w, m, len);
-		run.e += t.e, run.p1 += t.p1, run.p2 += t.p2;
-	}
-	if (m1 == len && m0 < len) CE[len] = run.e, C1[len] = run.p1, C2[len] = run.p2;
+	if (len % (kPrefThreads * RES) == 0 && threadIdx.x == 0) CE[len / RES] = carry.e, C1[len / RES] = carry.p1, C2[len / RES] = carry.p2;
 }
 
 __device__ __forceinline__ unsigned long long metric_key(double v) { return (unsigned long long)__double_as_longlong(v + 2.0); }  // monotone for v in [-1, 1]
@@ -221,15 +247,18 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 	const int k = blockIdx.x * kScThreads + threadIdx.x;
 	double v = -3.0;
 	if (k < st.sc_npos) {
-		const size_t ps = st.sc_src == 0 ? pstride_ts : pstride_win;
-		const double *CE = (st.sc_src == 0 ? pref_ts + (size_t)b * 3 * pstride_ts + st.sc_start : pref_win + (size_t)b * 3 * pstride_win) + (size_t)k * st.sc_step;
+		// coarse runs (step 100) read the RES-4 prefix of the whole time-sync base-band, fine runs (step 1) the RES-1 prefix of their window
+		const bool fine = st.sc_step == 1;
+		const size_t ps = fine ? pstride_win : pstride_ts;
+		const int sh = fine ? 0 : 2;
+		const double *CE = fine ? pref_win + (size_t)b * 3 * pstride_win + k : pref_ts + (size_t)b * 3 * pstride_ts + ((st.sc_start + k * st.sc_step) >> 2);
 		const double *C1 = CE + ps, *C2 = C1 + ps;
 		double cc = 0, na = 0, nb = 0;
 		for (int l = 0; l < pre; l++) {
 			const int o = l * MB_FE_SYM;
-			cc += (C1[o + 64] - C1[o]) + (C2[o + 576] - C2[o + 64]);
-			na += CE[o + 576] - CE[o];
-			nb += (CE[o + 1088] - CE[o + 576]) + (CE[o + 1088] - CE[o + 1024]);
+			cc += (C1[(o + 64) >> sh] - C1[o >> sh]) + (C2[(o + 576) >> sh] - C2[(o + 64) >> sh]);
+			na += CE[(o + 576) >> sh] - CE[o >> sh];
+			nb += (CE[(o + 1088) >> sh] - CE[(o + 576) >> sh]) + (CE[(o + 1088) >> sh] - CE[(o + 1024) >> sh]);
 		}
 		const bool amb = fabs(na - 0.001) <= kScThrBand || fabs(nb - 0.001) <= kScThrBand;
 		v = (na < 0.001 || nb < 0.001) ? 0.0 : cc / sqrt(na * nb);
@@ -240,49 +269,73 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 	if ((threadIdx.x & 31) == 0 && v > -3.0) atomicMax(&st.sc_max_key, metric_key(v));
 }
 
-// pass B: the reference's summation order (ofdm.cc:1901-1930), one thread per band position
+// pass B: the reference's summation order (ofdm.cc:1901-1930).  The three running sums of a position are serial chains of 4,608
+// additions; to keep their latency off the memory system a whole warp serves one band position at a time: the lanes fetch 32
+// sample pairs (coalesced, the next chunk already in flight) and form the six products of each, the owner lane then adds them
+// in the reference's order out of shared memory.
 __global__ void __launch_bounds__(kScThreads) k_fe_sc_exact(const MbFeState *__restrict__ st_all, const double2 *__restrict__ bbi_all, int buf,
 							      const double2 *__restrict__ win_all, int win_stride, double *__restrict__ vals_all, int vals_stride,
 							      const uint8_t *__restrict__ flags_all, int pre, int *__restrict__ counters)
 {
+	__shared__ double prod[kScThreads / 32][32][6];
 	const int b = blockIdx.y;
 	const MbFeState &st = st_all[b];
 	if (!st.sc_pending) return;
-	const int k = blockIdx.x * kScThreads + threadIdx.x;
-	if (k >= st.sc_npos) return;
-	const double approx = vals_all[(size_t)b * vals_stride + k];
-	if (!flags_all[(size_t)b * vals_stride + k] && metric_key(approx + kScTol) < st.sc_max_key) return;
-	atomicAdd(&counters[3], 1);
-	const double2 *in = (st.sc_src == 0 ? bbi_all + (size_t)b * buf + st.sc_start : win_all + (size_t)b * win_stride) + (size_t)k * st.sc_step;
-	double cc = 0, na = 0, nb = 0;
-	for (int l = 0; l < pre; l++) {
-		const double2 *a = in + l * MB_FE_SYM, *bq = a + MB_NFFT * 4;
-#pragma unroll 4
-		for (int q = 0; q < MB_NGI * 4; q++) {
-			const double2 u = a[q], v = bq[q];
-			cc = dadd(cc, dmul(u.x, v.x));
-			na = dadd(na, dmul(u.x, u.x));
-			nb = dadd(nb, dmul(v.x, v.x));
-			cc = dadd(cc, dmul(u.y, v.y));
-			na = dadd(na, dmul(u.y, u.y));
-			nb = dadd(nb, dmul(v.y, v.y));
+	const int k = blockIdx.x * kScThreads + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	bool cand = false;
+	if (k < st.sc_npos) {
+		const double approx = vals_all[(size_t)b * vals_stride + k];
+		cand = flags_all[(size_t)b * vals_stride + k] || metric_key(approx + kScTol) >= st.sc_max_key;
+	}
+	unsigned todo = __ballot_sync(0xffffffffu, cand);
+	if (todo == 0) return;
+	if (lane == 0) atomicAdd(&counters[3], __popc(todo));
+	const double2 *src = st.sc_src == 0 ? bbi_all + (size_t)b * buf + st.sc_start : win_all + (size_t)b * win_stride;
+	// chunk c of a position: symbol l = c / 18, within it chunks 0-1 = guard interval vs symbol tail (lag 1024), 2-17 = the two halves (lag 512)
+	const int nchunks = pre * 18;
+	while (todo) {
+		const int owner = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const double2 *in = src + (size_t)(blockIdx.x * kScThreads + warp * 32 + owner) * st.sc_step;
+		double cc = 0, na = 0, nb = 0;
+		auto chunk_ptr = [&](int c, const double2 *&a, const double2 *&bq) {
+			const int l = c / 18, r = c % 18;
+			if (r < 2) a = in + l * MB_FE_SYM + 32 * r, bq = a + MB_NFFT * 4;
+			else a = in + l * MB_FE_SYM + MB_NGI * 4 + 32 * (r - 2), bq = a + (MB_NFFT / 2) * 4;
+		};
+		const double2 *pa, *pb;
+		chunk_ptr(0, pa, pb);
+		double2 u = pa[lane], v = pb[lane];
+		for (int c = 0; c < nchunks; c++) {
+			const double2 cu = u, cv = v;
+			if (c + 1 < nchunks) {
+				chunk_ptr(c + 1, pa, pb);
+				u = pa[lane], v = pb[lane];
+			}
+			double *pr = prod[warp][lane];
+			pr[0] = dmul(cu.x, cv.x), pr[1] = dmul(cu.x, cu.x), pr[2] = dmul(cv.x, cv.x);
+			pr[3] = dmul(cu.y, cv.y), pr[4] = dmul(cu.y, cu.y), pr[5] = dmul(cv.y, cv.y);
+			__syncwarp();
+			if (lane == owner) {
+#pragma unroll 8
+				for (int q = 0; q < 32; q++) {
+					const double *p = prod[warp][q];
+					cc = dadd(cc, p[0]);
+					na = dadd(na, p[1]);
+					nb = dadd(nb, p[2]);
+					cc = dadd(cc, p[3]);
+					na = dadd(na, p[4]);
+					nb = dadd(nb, p[5]);
+				}
+			}
+			__syncwarp();
 		}
-		a = in + l * MB_FE_SYM + MB_NGI * 4;
-		bq = a + (MB_NFFT / 2) * 4;
-#pragma unroll 4
-		for (int q = 0; q < (MB_NFFT / 2) * 4; q++) {
-			const double2 u = a[q], v = bq[q];
-			cc = dadd(cc, dmul(u.x, v.x));
-			na = dadd(na, dmul(u.x, u.x));
-			nb = dadd(nb, dmul(v.x, v.x));
-			cc = dadd(cc, dmul(u.y, v.y));
-			na = dadd(na, dmul(u.y, u.y));
-			nb = dadd(nb, dmul(v.y, v.y));
+		if (lane == owner) {
+			if (na < 0.001 || nb < 0.001) cc = 0.0;
+			else cc = __ddiv_rn(cc, __dsqrt_rn(dmul(na, nb)));
+			vals_all[(size_t)b * vals_stride + k] = cc;
 		}
 	}
-	if (na < 0.001 || nb < 0.001) cc = 0.0;
-	else cc = __ddiv_rn(cc, __dsqrt_rn(dmul(na, nb)));
-	vals_all[(size_t)b * vals_stride + k] = cc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -320,8 +373,9 @@ __device__ void sc_result(const DecideCtx &c, const double *vals, int from, int 
 	for (int w = 1; w < (int)(blockDim.x >> 5); w++)
 		if (red_v[w] > best || (red_v[w] == best && red_k[w] < bk)) best = red_v[w], bk = red_k[w];
 	// first index >= from that is NOT a computed position (its array entry is an exact zero)
-	int nz = from;
-	while (nz < st.sc_size && (nz % st.sc_step) == 0 && nz / st.sc_step < st.sc_npos) nz++;
+	int nz;
+	if (st.sc_step == 1) nz = from < st.sc_npos ? st.sc_npos : from;
+	else nz = ((from % st.sc_step) == 0 && from / st.sc_step < st.sc_npos) ? from + 1 : from;
 	const int p = bk == 0x7fffffff ? -1 : bk * st.sc_step;
 	int loc;
 	double corr;
@@ -680,10 +734,32 @@ __global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_a
 	// tiles of 256 decimated outputs = 1024 pass-band samples (+ 32 of filter halo): every pass-band sample is mixed once (one sincos
 	// when the carrier is the Moose-corrected one), then each thread runs the 33 taps of its output from shared memory
 	const int k_begin = dbg_bb ? 0 : pre * MB_NOFDM, k_end = (S + pre) * MB_NOFDM;
+	// corrected carrier: one sincos per thread for its first staged sample, then exact complex rotations by 256 samples (within a
+	// tile) and by 1024 samples (tile to tile) -- ~150 rotations per capture, ~1e-14 of accumulated rounding
+	double2 ph = make_double2(1.0, 0.0), r256 = ph, r1024 = ph;
+	if (corrected) {
+		const int n0 = delay + 4 * k_begin - MB_FE_TAPS / 2 + (int)threadIdx.x;
+		sincos(dmul(dmul(dmul(2 * M_PI, f), (double)n0), fe_c.Ts), &ph.y, &ph.x);
+		sincos(dmul(dmul(dmul(2 * M_PI, f), 256.0), fe_c.Ts), &r256.y, &r256.x);
+		sincos(dmul(dmul(dmul(2 * M_PI, f), 1024.0), fe_c.Ts), &r1024.y, &r1024.x);
+	}
 	for (int k0 = k_begin; k0 < k_end; k0 += 256) {
 		const int p0 = delay + 4 * k0 - MB_FE_TAPS / 2;
 		__syncthreads();
-		for (int i = threadIdx.x; i < 1024 + MB_FE_TAPS - 1; i += 256) lt[i] = mixed_sample(x, p0 + i, buf, carrier, !corrected, f);
+		double2 cur = ph;
+		for (int i = threadIdx.x; i < 1024 + MB_FE_TAPS - 1; i += 256) {
+			const int n = p0 + i;
+			double2 cs = cur;
+			if (corrected) cur = make_double2(cur.x * r256.x - cur.y * r256.y, cur.x * r256.y + cur.y * r256.x);
+			else if (n >= 0 && n < buf) cs = carrier[n];
+			double2 m = make_double2(0.0, 0.0);
+			if (n >= 0 && n < buf) {
+				const double v = dmul((double)x[n], fe_c.amp);
+				m = make_double2(dmul(v, cs.x), dmul(v, cs.y));
+			}
+			lt[i] = m;
+		}
+		ph = make_double2(ph.x * r1024.x - ph.y * r1024.y, ph.x * r1024.y + ph.y * r1024.x);
 		__syncthreads();
 		const int k = k0 + threadIdx.x;
 		if (k < k_end) {
@@ -798,21 +874,21 @@ cudaError_t mb_fe_init(const MbFeConst &k) { return cudaMemcpyToSymbol(fe_c, &k,
 template <typename T>
 static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
 {
-	const int nblk = (a.buf + 255) / 256;
+	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
 	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
-	k_fe_prefix<<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, (size_t)a.buf, a.buf, 0, a.pref_ts, (size_t)a.buf + 1);
+	k_fe_prefix<4><<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.pref_ts, (size_t)a.buf / 4 + 1);
 	return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
 {
-	const int nblk = (a.buf + 255) / 256;
+	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
 	if (run_sc) {
 		k_fe_window<T><<<dim3(8, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.st, a.win, a.win_stride);
-		k_fe_prefix<<<a.n, kPrefThreads, 0, s>>>(a.st, a.win, (size_t)a.win_stride, 0, 1, a.pref_win, (size_t)a.win_stride + 1);
+		k_fe_prefix<1><<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.pref_win, (size_t)a.win_stride + 1);
 		const dim3 grid((a.vals_stride + kScThreads - 1) / kScThreads, a.n);
-		k_fe_sc_approx<<<grid, kScThreads, 0, s>>>(a.st, a.pref_ts, (size_t)a.buf + 1, a.pref_win, (size_t)a.win_stride + 1, a.vals, a.vals_stride, a.flags, a.pre);
+		k_fe_sc_approx<<<grid, kScThreads, 0, s>>>(a.st, a.pref_ts, (size_t)a.buf / 4 + 1, a.pref_win, (size_t)a.win_stride + 1, a.vals, a.vals_stride, a.flags, a.pre);
 		k_fe_sc_exact<<<grid, kScThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.vals, a.vals_stride, a.flags, a.pre, a.counters);
 	}
 	k_fe_decide<T><<<a.n, kDecideThreads, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.vals, a.vals_stride, a.energy_part, nblk,

@@ -93,14 +93,14 @@ struct MbFeArgs {
 	const double2 *carrier;  // [>= buf] (cos, sin)(2 pi fc i Ts), host libm
 	MbFeState *st;       // [n]
 	double2 *bbi;        // [n][buf]  time-sync base-band
-	double *energy_part; // [n][ceil(buf/256)]
+	double *energy_part; // [n][ceil(buf/1024)]
 	double2 *win;        // [n][win_stride] fine-sync window of the data-filter base-band
 	int32_t win_stride;
 	double *vals;        // [n][vals_stride] correlation metrics of the pending run
 	int32_t vals_stride;
 	uint8_t *flags;      // [n][vals_stride] positions whose norms sit on the 0.001 threshold (forced into the exact pass)
-	double *pref_ts;     // [n][3][buf + 1]        exclusive prefix sums over the time-sync base-band: |w|^2, lag-1024 and lag-512 dot products
-	double *pref_win;    // [n][3][win_stride + 1] the same over the fine-sync window of the data-filter base-band
+	double *pref_ts;     // [n][3][buf / 4 + 1]    exclusive prefix sums over the time-sync base-band, one entry per 4 samples: |w|^2, lag-1024 and lag-512 dot products
+	double *pref_win;    // [n][3][win_stride + 1] the same at full resolution over the window of the pending fine run
 	float2 *frames;      // [n][S][272] tail input, by slot
 	double2 *dbg_bb;     // optional [n][(pre+S)*272] fp64 copy of baseband_data (by capture)
 	const MbRxStats *tail_stats;   // [n] by slot
