@@ -15,6 +15,8 @@ the 126 MB L2, so no flush is needed between timed steps.
   roofline : the demod kernel (FFT / estimate / equalise / de-map), algorithmic bytes per frame from SURVEY.md 8d
   ldpc  : edge-updates/s of the decoder kernel = edges(rate) x iterations actually run / kernel time
   cpu_baseline : the reference CPU path (oracle/_ref when built, else the C port) on a bounded sample, 1 core
+  receive_byte : the next row -- captures/s through the whole receive_byte(), pass-band capture buffers in,
+                 front-end + tail on the GPU, with its own e2e and cpu_baseline (tools/bench_frontend.py)
 """
 import argparse
 import json
@@ -353,6 +355,17 @@ def run_own(a):
         single = {"median_us": float(np.median(lat) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6),
                   "api": "mercury_b200_receive_baseband (double samples in, int bytes out, H2D + 2 kernels + D2H per call)"}
 
+    # ---- next row: the WHOLE receive_byte(), pass-band captures in, front-end + tail on the GPU --------------
+    receive_byte = None
+    if rank == 0 and world == 1 and not a.no_e2e:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_frontend
+            receive_byte = bench_frontend.run(config=8, captures=512, steps=3, warmup=1, cpu_captures=8 if a.cpu_frames > 0 else 0, ts=ts)
+            ts.load_configuration(a.config, a.iters)
+        except Exception as e:  # never let the extra leg take the headline line down
+            receive_byte = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and a.cpu_frames > 0:
         n = min(a.cpu_frames, B)
@@ -367,7 +380,7 @@ def run_own(a):
                        "l2_policy": f"inputs {B * S * 272 * 8 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
                        "input": f"{U} distinct host-synthesised frames tiled to {B}, independent AWGN per frame (torch.randn on device)",
                        "parallelism": f"frame shards x{world}, tables broadcast once ({'NCCL' if world > 1 else 'local'}), no data-path collective"},
-            "roofline": roofline, "ldpc": ldpc, "cpu_baseline": cpu, "e2e": e2e, "single_frame_call": single, "gpu_launches": int(launches),
+            "roofline": roofline, "ldpc": ldpc, "cpu_baseline": cpu, "e2e": e2e, "single_frame_call": single, "receive_byte": receive_byte, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "integrity": {"frames_decoded": int(dec.sum()), "frames": int(B), "payload_mismatches_among_decoded": mism,
                           "fer": float(1.0 - dec.mean())},

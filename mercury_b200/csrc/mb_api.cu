@@ -41,8 +41,11 @@ namespace {
 struct FeWork {
 	size_t cap = 0;
 	int buf = 0;
-	void *d_x = nullptr;  // staged pass-band samples of the host entry point
+	void *d_x[2] = {nullptr, nullptr};  // staged pass-band samples of the host entry point, double buffered
 	size_t x_bytes = 0;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+	size_t host_chunk = 256;  // captures per H2D chunk of the host entry point (copy of chunk i+1 overlaps the kernels of chunk i)
 	MbFeState *st = nullptr;
 	double2 *bbi = nullptr, *win = nullptr, *dbg_bb = nullptr;
 	double *energy_part = nullptr, *vals = nullptr, *pref_ts = nullptr, *pref_win = nullptr;
@@ -482,12 +485,17 @@ namespace {
 
 void fe_free(FeWork &w)
 {
-	void *ptrs[] = {w.d_x, w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.pref_ts, w.pref_win, w.flags, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
+	void *ptrs[] = {w.d_x[0], w.d_x[1], w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.pref_ts, w.pref_win, w.flags, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	if (w.h_counters) cudaFreeHost(w.h_counters);
 	if (w.carrier) cudaFree(w.carrier);
 	if (w.stream) cudaStreamDestroy(w.stream);
+	if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+	for (int i = 0; i < 2; i++) {
+		if (w.copied[i]) cudaEventDestroy(w.copied[i]);
+		if (w.consumed[i]) cudaEventDestroy(w.consumed[i]);
+	}
 	w = FeWork();
 }
 
@@ -503,7 +511,15 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 		if (const char *c = getenv("MERCURY_B200_FE_CHUNK")) h->fe_chunk = std::max(1, atoi(c));
 		h->fe_ready = true;
 	}
-	if (!w.stream) MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+	if (!w.stream) {
+		MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+		MB_CUDA(h, cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			MB_CUDA(h, cudaEventCreateWithFlags(&w.copied[i], cudaEventDisableTiming));
+			MB_CUDA(h, cudaEventCreateWithFlags(&w.consumed[i], cudaEventDisableTiming));
+		}
+		if (const char *c = getenv("MERCURY_B200_FE_HOST_CHUNK")) w.host_chunk = std::max(1, atoi(c));
+	}
 	if (w.carrier_n < buf) {
 		if (w.carrier) cudaFree(w.carrier);
 		w.carrier = nullptr;
@@ -519,9 +535,12 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	}
 	if (w.x_bytes < stage_bytes) {
 		MB_CUDA(h, cudaDeviceSynchronize());
-		if (w.d_x) cudaFree(w.d_x);
-		w.d_x = nullptr, w.x_bytes = 0;
-		MB_CUDA(h, cudaMalloc(&w.d_x, stage_bytes));
+		for (int i = 0; i < 2; i++) {
+			if (w.d_x[i]) cudaFree(w.d_x[i]);
+			w.d_x[i] = nullptr;
+		}
+		w.x_bytes = 0;
+		for (int i = 0; i < 2; i++) MB_CUDA(h, cudaMalloc(&w.d_x[i], stage_bytes));
 		w.x_bytes = stage_bytes;
 	}
 	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
@@ -650,18 +669,34 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 	const MbMode &m = h->hdr.modes[h->config];
 	const int buf = fe_capture_samples(m);
 	const size_t ss = fmt == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
-	const size_t chunk = std::min(n, h->fe_chunk);
+	// chunks of host_chunk captures: the H2D copy of chunk i+1 (copy stream, second staging buffer) runs while the kernels of chunk i
+	// do -- this path is bound by PCIe (one capture is 0.37-0.95 MB), so hiding the compute behind the copies is what matters
+	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, baseband_dbg != nullptr, 0);
+	if (rc) return rc;
+	const size_t chunk = std::min(std::min(n, h->fe_chunk), h->fe.host_chunk);
 	rc = fe_ensure(h, chunk, buf, m, baseband_dbg != nullptr, chunk * buf * ss);
 	if (rc) return rc;
 	FeWork &w = h->fe;
 	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
-	for (size_t done = 0; done < n; done += chunk) {
+	const uint8_t *xb = static_cast<const uint8_t *>(x);
+	MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], xb, std::min(chunk, n) * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
+	MB_CUDA(h, cudaEventRecord(w.copied[0], w.copy_stream));
+	int i = 0;
+	for (size_t done = 0; done < n; done += chunk, i++) {
 		const size_t c = std::min(chunk, n - done);
-		MB_CUDA(h, cudaMemcpyAsync(w.d_x, static_cast<const uint8_t *>(x) + done * buf * ss, c * buf * ss, cudaMemcpyHostToDevice, w.stream));
+		const int cur = i & 1, nxt = cur ^ 1;
+		if (done + chunk < n) {  // prefetch the next chunk once its staging buffer has been consumed
+			const size_t c2 = std::min(chunk, n - done - chunk);
+			if (i >= 1) MB_CUDA(h, cudaStreamWaitEvent(w.copy_stream, w.consumed[nxt], 0));
+			MB_CUDA(h, cudaMemcpyAsync(w.d_x[nxt], xb + (done + chunk) * buf * ss, c2 * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
+			MB_CUDA(h, cudaEventRecord(w.copied[nxt], w.copy_stream));
+		}
+		MB_CUDA(h, cudaStreamWaitEvent(w.stream, w.copied[cur], 0));
 		MB_CUDA(h, cudaMemcpyAsync(w.stats, stats + done, c * sizeof(MbReceiveStats), cudaMemcpyHostToDevice, w.stream));
 		if (baseband_dbg) MB_CUDA(h, cudaMemsetAsync(w.dbg_bb, 0, c * bb_n * sizeof(double2), w.stream));
-		rc = fe_run(h, w.d_x, fmt, c, w.payload, w.stats, baseband_dbg != nullptr, w.stream);
+		rc = fe_run(h, w.d_x[cur], fmt, c, w.payload, w.stats, baseband_dbg != nullptr, w.stream);
 		if (rc) return rc;
+		MB_CUDA(h, cudaEventRecord(w.consumed[cur], w.stream));
 		MB_CUDA(h, cudaMemcpyAsync(payload + done * m.frame_bytes, w.payload, c * m.frame_bytes, cudaMemcpyDeviceToHost, w.stream));
 		MB_CUDA(h, cudaMemcpyAsync(stats + done, w.stats, c * sizeof(MbReceiveStats), cudaMemcpyDeviceToHost, w.stream));
 		if (baseband_dbg)
