@@ -161,6 +161,9 @@ typedef struct mercury_b200_receive_stats {
 
 #define MERCURY_B200_SAMPLES_F64 0  /* double, the reference's own type */
 #define MERCURY_B200_SAMPLES_F32 1  /* float: half the bytes; every float is exactly representable as the double the reference would see */
+/* The other capture formats of the reference's audio layer, converted on the device exactly as source/audioio/audioio.c:893-940 does: */
+#define MERCURY_B200_SAMPLES_I16 2  /* int16 PCM, x / 32768.0 (a quarter of the bytes of double) */
+#define MERCURY_B200_SAMPLES_I32 3  /* int32 PCM, x / (double)INT_MAX (the reference's default capture format, audioio.c:744) */
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h);
 /* One capture, the reference's own types (out = one int per payload byte). */

@@ -11,7 +11,10 @@
 //   default_configurations_telecom_system
 //       .ldpc_nIteration_max            (main.cc:550)   default_configurations_telecom_system.ldpc_nIteration_max
 //   int get_frame_size_bytes()/bits()   (.h:180-181)    get_frame_size_bytes() / get_frame_size_bits()
-//   st_receive_stats receive_byte(double*, int*)        receive_byte(const std::complex<double>* baseband_data, int* out)
+//   st_receive_stats receive_byte(double*, int*)        receive_byte(double* data, int* out)  -- THE reference signature, whole: `data` is the
+//                                       (.h:142)            pass-band capture (data_container.Nofdm * buffer_Nsymb * interpolation_rate
+//                                                           doubles); front-end + tail on the GPU (.cc:646-1518, OFDM branch)
+//                                                       receive_byte(const std::complex<double>* baseband_data, int* out)
 //                                       (.h:142)            = the tail of receive_byte (.cc:1132-1429) on the
 //                                                             post-synchronisation data_container.baseband_data
 //   st_receive_stats receive_bit(double*, int*) (.h:139) receive_bit(const std::complex<double>*, int* out)
@@ -42,6 +45,12 @@ enum { NO = 0, YES = 1 };  // reference: include/physical_layer/physical_defines
 // The st_receive_stats fields written by telecom_system.cc:1310-1429 (same names; front-end fields are not produced here).
 struct st_receive_stats {
 	int iterations_done = 0;   // 0..I, I+1 = not converged, -1 = decode skipped by the mean|H| < 0.3 gate (:1271)
+	int delay = 0;             // front-end fields (telecom_system.h:65-82), written by receive_byte(double*, int*)
+	int delay_of_last_decoded_message = -1;
+	double freq_offset = 0;
+	double freq_offset_of_last_decoded_message = 0;
+	double signal_stregth_dbm = 0;
+	double coarse_metric = 0;
 	int sync_trials = 0;       // incremented on a failed decode like :1358
 	int message_decoded = NO;
 	double SNR = -99.9;
@@ -58,6 +67,7 @@ public:
 	} default_configurations_telecom_system;
 	struct {
 		int Nsymb = 0, Nofdm = MERCURY_B200_NOFDM, Nc = 0, nBits = 0, nData = 0, preamble_nSymb = 0;
+		int buffer_Nsymb = 0, interpolation_rate = 4;  // capture = Nofdm * buffer_Nsymb * interpolation_rate samples (data_container.cc:133-153)
 	} data_container;
 	struct {
 		int N = MERCURY_B200_N, K = 0, P = 0;
@@ -90,12 +100,32 @@ public:
 		mercury_b200_get_geometry(h_, &g);
 		data_container.Nsymb = g.Nsymb, data_container.Nc = g.Nc, data_container.nBits = g.nBits, data_container.nData = g.nData;
 		data_container.preamble_nSymb = g.preamble_nSymb;
+		data_container.buffer_Nsymb = mercury_b200_get_capture_samples(h_) / (data_container.Nofdm * data_container.interpolation_rate);
 		ldpc.K = g.K, ldpc.P = g.P;
 		M = g.M;
 		nReal_ = g.nReal;
 	}
 	int get_frame_size_bytes() const { return mercury_b200_get_frame_size_bytes(h_); }
 	int get_frame_size_bits() const { return mercury_b200_get_frame_size_bits(h_); }
+
+	// The reference's own call (telecom_system.h:142): data = one pass-band capture buffer, out = one int per payload byte.  The link
+	// state the reference keeps in receive_stats between calls (delay / frequency offset of the last decoded message) lives in this
+	// object's receive_stats the same way.
+	st_receive_stats receive_byte(double *data, int *out)
+	{
+		mercury_b200_receive_stats rs;
+		rs.delay_of_last_decoded_message = receive_stats.delay_of_last_decoded_message;
+		rs.freq_offset_of_last_decoded_message = receive_stats.freq_offset_of_last_decoded_message;
+		const int rc = mercury_b200_receive_byte(h_, data, out, &rs);
+		if (rc != MERCURY_B200_OK) throw std::runtime_error(std::string("mercury_b200_receive_byte: ") + mercury_b200_last_error(h_));
+		receive_stats.iterations_done = rs.iterations_done, receive_stats.delay = rs.delay, receive_stats.sync_trials = rs.sync_trials;
+		receive_stats.delay_of_last_decoded_message = rs.delay_of_last_decoded_message;
+		receive_stats.freq_offset = rs.freq_offset, receive_stats.freq_offset_of_last_decoded_message = rs.freq_offset_of_last_decoded_message;
+		receive_stats.message_decoded = rs.message_decoded ? YES : NO, receive_stats.SNR = rs.SNR;
+		receive_stats.crc = rs.crc, receive_stats.all_zeros = rs.all_zeros;
+		receive_stats.signal_stregth_dbm = rs.signal_stregth_dbm, receive_stats.coarse_metric = rs.coarse_metric;
+		return receive_stats;
+	}
 
 	// baseband_data: Nsymb * Nofdm samples, the frame's data symbols after time/frequency synchronisation (the reference
 	// indexes data_container.baseband_data at (preamble_nSymb + i) * Nofdm, telecom_system.cc:1137).  out: one int per byte.

@@ -45,7 +45,7 @@ struct FeWork {
 	size_t x_bytes = 0;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-	size_t host_chunk = 256;  // captures per H2D chunk of the host entry point (copy of chunk i+1 overlaps the kernels of chunk i)
+	size_t host_chunk = 384;  // captures per H2D chunk of the host entry point (copy of chunk i+1 overlaps the kernels of chunk i)
 	MbFeState *st = nullptr;
 	double2 *bbi = nullptr, *win = nullptr, *dbg_bb = nullptr;
 	double *energy_part = nullptr, *vals = nullptr, *pref_ts = nullptr, *pref_win = nullptr;
@@ -499,6 +499,17 @@ void fe_free(FeWork &w)
 	w = FeWork();
 }
 
+size_t fe_sample_bytes(int fmt)
+{
+	switch (fmt) {
+	case MERCURY_B200_SAMPLES_F64: return 8;
+	case MERCURY_B200_SAMPLES_F32: return 4;
+	case MERCURY_B200_SAMPLES_I16: return 2;
+	case MERCURY_B200_SAMPLES_I32: return 4;
+	}
+	return 0;
+}
+
 int fe_capture_samples(const MbMode &m) { return MB_NOFDM * mb_fe_buffer_nsymb(m.Nsymb, m.preamble_nSymb) * 4; }
 
 int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_dbg, size_t stage_bytes)
@@ -585,7 +596,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	FeWork &w = h->fe;
 	MbFeArgs a;
 	memset(&a, 0, sizeof(a));
-	a.x = d_x, a.x_is_f32 = fmt == MERCURY_B200_SAMPLES_F32, a.n = (int)n;
+	a.x = d_x, a.x_format = fmt, a.n = (int)n;
 	a.buffer_Nsymb = mb_fe_buffer_nsymb(m.Nsymb, m.preamble_nSymb);
 	a.buf = MB_NOFDM * a.buffer_Nsymb * 4, a.pre = m.preamble_nSymb, a.S = m.Nsymb, a.frame_bytes = m.frame_bytes;
 	a.carrier = w.carrier, a.st = w.st, a.bbi = w.bbi, a.energy_part = w.energy_part;
@@ -644,10 +655,10 @@ int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_x, i
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
-	if (!d_x || !d_payload || !d_stats || (fmt != MERCURY_B200_SAMPLES_F64 && fmt != MERCURY_B200_SAMPLES_F32)) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	if (!d_x || !d_payload || !d_stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	const MbMode &m = h->hdr.modes[h->config];
 	const int buf = fe_capture_samples(m);
-	const size_t ss = fmt == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	const size_t ss = fe_sample_bytes(fmt);
 	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, false, 0);
 	if (rc) return rc;
 	for (size_t done = 0; done < n; done += h->fe_chunk) {
@@ -665,30 +676,32 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
-	if (!x || !payload || !stats || (fmt != MERCURY_B200_SAMPLES_F64 && fmt != MERCURY_B200_SAMPLES_F32)) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	if (!x || !payload || !stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	const MbMode &m = h->hdr.modes[h->config];
 	const int buf = fe_capture_samples(m);
-	const size_t ss = fmt == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	const size_t ss = fe_sample_bytes(fmt);
 	// chunks of host_chunk captures: the H2D copy of chunk i+1 (copy stream, second staging buffer) runs while the kernels of chunk i
 	// do -- this path is bound by PCIe (one capture is 0.37-0.95 MB), so hiding the compute behind the copies is what matters
-	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, baseband_dbg != nullptr, 0);
-	if (rc) return rc;
-	const size_t chunk = std::min(std::min(n, h->fe_chunk), h->fe.host_chunk);
-	rc = fe_ensure(h, chunk, buf, m, baseband_dbg != nullptr, chunk * buf * ss);
+	// chunk schedule: a small first chunk (its copy is the only one nothing hides), then host_chunk captures (scaled up for the
+	// narrower sample formats so that a chunk stays around 100-200 MB)
+	size_t big = h->fe.host_chunk * (ss <= 2 ? 2 : 1);
+	big = std::min(std::min(n, h->fe_chunk), big);
+	const size_t first = std::min(big, std::max<size_t>(64, big / 4));
+	rc = fe_ensure(h, big, buf, m, baseband_dbg != nullptr, big * buf * ss);
 	if (rc) return rc;
 	FeWork &w = h->fe;
 	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
 	const uint8_t *xb = static_cast<const uint8_t *>(x);
-	MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], xb, std::min(chunk, n) * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
+	MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], xb, std::min(first, n) * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
 	MB_CUDA(h, cudaEventRecord(w.copied[0], w.copy_stream));
 	int i = 0;
-	for (size_t done = 0; done < n; done += chunk, i++) {
-		const size_t c = std::min(chunk, n - done);
+	size_t c = std::min(first, n);
+	for (size_t done = 0; done < n; i++) {
 		const int cur = i & 1, nxt = cur ^ 1;
-		if (done + chunk < n) {  // prefetch the next chunk once its staging buffer has been consumed
-			const size_t c2 = std::min(chunk, n - done - chunk);
+		const size_t c2 = std::min(big, n - done - c);  // the chunk after this one
+		if (c2 > 0) {  // prefetch it once its staging buffer has been consumed
 			if (i >= 1) MB_CUDA(h, cudaStreamWaitEvent(w.copy_stream, w.consumed[nxt], 0));
-			MB_CUDA(h, cudaMemcpyAsync(w.d_x[nxt], xb + (done + chunk) * buf * ss, c2 * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
+			MB_CUDA(h, cudaMemcpyAsync(w.d_x[nxt], xb + (done + c) * buf * ss, c2 * buf * ss, cudaMemcpyHostToDevice, w.copy_stream));
 			MB_CUDA(h, cudaEventRecord(w.copied[nxt], w.copy_stream));
 		}
 		MB_CUDA(h, cudaStreamWaitEvent(w.stream, w.copied[cur], 0));
@@ -702,6 +715,8 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 		if (baseband_dbg)
 			MB_CUDA(h, cudaMemcpyAsync(baseband_dbg + done * bb_n * 2, w.dbg_bb, c * bb_n * sizeof(double2), cudaMemcpyDeviceToHost, w.stream));
 		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+		done += c;
+		c = c2;
 	}
 	return MERCURY_B200_OK;
 }

@@ -38,12 +38,19 @@ constexpr int kScThreads = 128;
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
+// The capture formats of the reference's audio layer and their conversion to its double samples (source/audioio/audioio.c:893-940):
+// FLOAT32 (double)x, INT16 x / 32768.0, INT32 x / (double)INT_MAX -- all reproduced exactly (the last by an IEEE division).
+__device__ __forceinline__ double sample_to_double(double x) { return x; }
+__device__ __forceinline__ double sample_to_double(float x) { return (double)x; }
+__device__ __forceinline__ double sample_to_double(int16_t x) { return (double)x * (1.0 / 32768.0); }
+__device__ __forceinline__ double sample_to_double(int32_t x) { return __ddiv_rn((double)x, 2147483647.0); }
+
 // One mixed sample l[i] = (x[i] * amp) * (cos, sin)(2 pi f i Ts)   (ofdm.cc:2330-2334)
 template <typename T>
 __device__ __forceinline__ double2 mixed_sample(const T *x, int i, int buf, const double2 *carrier, bool table, double f)
 {
 	if (i < 0 || i >= buf) return make_double2(0.0, 0.0);
-	const double v = dmul((double)x[i], fe_c.amp);
+	const double v = dmul(sample_to_double(x[i]), fe_c.amp);
 	double c, s;
 	if (table) {
 		const double2 cs = carrier[i];
@@ -754,7 +761,7 @@ __global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_a
 			else if (n >= 0 && n < buf) cs = carrier[n];
 			double2 m = make_double2(0.0, 0.0);
 			if (n >= 0 && n < buf) {
-				const double v = dmul((double)x[n], fe_c.amp);
+				const double v = dmul(sample_to_double(x[n]), fe_c.amp);
 				m = make_double2(dmul(v, cs.x), dmul(v, cs.y));
 			}
 			lt[i] = m;
@@ -904,9 +911,18 @@ static cudaError_t fe_extract_t(const MbFeArgs &a, cudaStream_t s)
 	return cudaGetLastError();
 }
 
-cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s) { return a.x_is_f32 ? fe_p2b_full_t<float>(a, s) : fe_p2b_full_t<double>(a, s); }
-cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s) { return a.x_is_f32 ? fe_step_t<float>(a, run_sc, s) : fe_step_t<double>(a, run_sc, s); }
-cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s) { return a.x_is_f32 ? fe_extract_t<float>(a, s) : fe_extract_t<double>(a, s); }
+#define MB_FE_DISPATCH(fn, ...)                                      \
+	switch (a.x_format) {                                        \
+	case 0: return fn<double>(__VA_ARGS__);                      \
+	case 1: return fn<float>(__VA_ARGS__);                       \
+	case 2: return fn<int16_t>(__VA_ARGS__);                     \
+	case 3: return fn<int32_t>(__VA_ARGS__);                     \
+	}                                                            \
+	return cudaErrorInvalidValue
+
+cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_p2b_full_t, a, s); }
+cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s) { MB_FE_DISPATCH(fe_step_t, a, run_sc, s); }
+cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_extract_t, a, s); }
 
 cudaError_t mb_fe_begin(const MbFeArgs &a, const MbReceiveStats *d_stats_in, cudaStream_t s)
 {

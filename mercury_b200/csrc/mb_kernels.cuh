@@ -88,8 +88,8 @@ struct MbFeState {
 };
 
 struct MbFeArgs {
-	const void *x;       // [n][buf] pass-band samples, double or float
-	int32_t x_is_f32, n, buf, pre, S, buffer_Nsymb, frame_bytes;
+	const void *x;       // [n][buf] pass-band samples
+	int32_t x_format /* MERCURY_B200_SAMPLES_*: 0 f64, 1 f32, 2 i16, 3 i32 */, n, buf, pre, S, buffer_Nsymb, frame_bytes;
 	const double2 *carrier;  // [>= buf] (cos, sin)(2 pi fc i Ts), host libm
 	MbFeState *st;       // [n]
 	double2 *bbi;        // [n][buf]  time-sync base-band

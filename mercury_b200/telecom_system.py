@@ -30,7 +30,8 @@ RECEIVE_STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("delay", "<i4"), ("
                                 ("freq_offset", "<f8"), ("freq_offset_of_last_decoded_message", "<f8"), ("SNR", "<f8"),
                                 ("signal_stregth_dbm", "<f8"), ("coarse_metric", "<f8")])
 assert RECEIVE_STATS_DTYPE.itemsize == C.sizeof(ReceiveStats) == 72
-SAMPLES_F64, SAMPLES_F32 = 0, 1
+SAMPLES_F64, SAMPLES_F32, SAMPLES_I16, SAMPLES_I32 = 0, 1, 2, 3
+_SAMPLE_FORMATS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2, np.dtype(np.int32): 3}
 
 
 def new_receive_stats(n):
@@ -141,11 +142,12 @@ class TelecomSystemB200:
         return out, st
 
     def receive_byte_batch(self, captures, stats=None, want_baseband=False):
-        """n captures of independent links, host buffers (float64 or float32 [n, capture_samples]).
+        """n captures of independent links, host buffers [n, capture_samples]: float64 / float32, or the PCM formats of the reference's
+        audio layer int16 (x / 32768.0) / int32 (x / INT_MAX) converted on the device like audioio.c:893-940.
         Returns (payload[n, frame_bytes] u8, stats[n], baseband[n, (pre+Nsymb)*272] complex128 | None)."""
         x = np.ascontiguousarray(captures)
-        if x.dtype not in (np.float64, np.float32):
-            raise TypeError("captures must be float64 or float32")
+        if x.dtype not in _SAMPLE_FORMATS:
+            raise TypeError("captures must be float64, float32, int16 or int32")
         cs = self.get_capture_samples()
         if x.size % cs:
             raise ValueError("captures size is not a whole number of capture buffers")
@@ -154,7 +156,7 @@ class TelecomSystemB200:
         payload = np.zeros((n, self.geometry["frame_bytes"]), np.uint8)
         g = self.geometry
         bb = np.zeros((n, (g["preamble_nSymb"] + g["Nsymb"]) * g["Nofdm"]), np.complex128) if want_baseband else None
-        self._check(self._L.mercury_b200_receive_byte_batch(self._h, _vp(x), SAMPLES_F32 if x.dtype == np.float32 else SAMPLES_F64, n,
+        self._check(self._L.mercury_b200_receive_byte_batch(self._h, _vp(x), _SAMPLE_FORMATS[x.dtype], n,
                                                             _vp(payload), _vp(st), _vp(bb)))
         return payload, st, bb
 

@@ -1,6 +1,8 @@
 // Exercises include/mercury_b200.hpp (the C++ mirror of cl_telecom_system for the RX tail) the way reference code would:
 // construct, load_configuration, receive_byte / receive_bit on one synchronised frame, print what the reference prints.
-//   usage: host_mirror_test <ldpc_tables.bin> <config> <ldpc iterations> <frame.bin: Nsymb*272 complex<double>>
+//   usage: host_mirror_test <ldpc_tables.bin> <config> <ldpc iterations> <frame.bin: Nsymb*272 complex<double>> [capture.bin: pass-band doubles]
+// With a capture file it also makes the reference's own call, receive_byte(double* data, int* out) on a whole pass-band capture, twice
+// (the second call sees the link state the first one left, like consecutive calls on the reference object).
 // Exit codes: 0 ok, 2 usage / IO, 3 no usable device (the library has no CPU fallback and says so).
 #include <cstdio>
 #include <cstdlib>
@@ -10,7 +12,7 @@
 
 int main(int argc, char **argv)
 {
-	if (argc != 5) {
+	if (argc != 5 && argc != 6) {
 		fprintf(stderr, "usage: %s ldpc_tables.bin config iterations frame.bin\n", argv[0]);
 		return 2;
 	}
@@ -38,6 +40,26 @@ int main(int argc, char **argv)
 		printf("bits");
 		for (int v : bits) printf(" %d", v);
 		printf("\n");
+		if (argc == 6) {
+			const size_t cs = (size_t)telecom_system.data_container.Nofdm * telecom_system.data_container.buffer_Nsymb *
+					  telecom_system.data_container.interpolation_rate;
+			std::vector<double> data(cs);
+			FILE *c = fopen(argv[5], "rb");
+			if (!c || fread(data.data(), sizeof(double), cs, c) != cs) {
+				fprintf(stderr, "cannot read %zu pass-band samples from %s\n", cs, argv[5]);
+				return 2;
+			}
+			fclose(c);
+			for (int call = 0; call < 2; call++) {
+				std::vector<int> o2((size_t)telecom_system.get_frame_size_bytes());
+				mb200::st_receive_stats r = telecom_system.receive_byte(data.data(), o2.data());
+				printf("capture%d %d delay %d trials %d iterations %d crc %d freq %.9f metric %.17g last_delay %d\n", call, r.message_decoded, r.delay,
+				       r.sync_trials, r.iterations_done, r.crc, r.freq_offset, r.coarse_metric, r.delay_of_last_decoded_message);
+				printf("capture%d_bytes", call);
+				for (int v : o2) printf(" %d", v);
+				printf("\n");
+			}
+		}
 		telecom_system.load_configuration(99);  // ignored, like the reference (telecom_system.cc:2494-2497)
 		printf("after_bad_config frame_bytes %d\n", telecom_system.get_frame_size_bytes());
 	} catch (const std::exception &e) {

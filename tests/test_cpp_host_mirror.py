@@ -24,10 +24,15 @@ def exe(tmp_path_factory):
     return out
 
 
-def run(exe, cfg, iters, x):
+def run(exe, cfg, iters, x, capture=None):
     path = os.path.join(os.path.dirname(exe), f"frame{cfg}.bin")
     np.ascontiguousarray(x, np.complex128).tofile(path)
-    return subprocess.run([exe, _lib.LDPC_TABLES, str(cfg), str(iters), path], capture_output=True, text=True)
+    args = [exe, _lib.LDPC_TABLES, str(cfg), str(iters), path]
+    if capture is not None:
+        cpath = os.path.join(os.path.dirname(exe), f"capture{cfg}.bin")
+        np.ascontiguousarray(capture, np.float64).tofile(cpath)
+        args.append(cpath)
+    return subprocess.run(args, capture_output=True, text=True)
 
 
 def test_cpp_mirror_compiles_and_refuses_to_run_without_a_device(exe, golden_dir):
@@ -58,3 +63,26 @@ def test_cpp_mirror_reproduces_the_reference_frame(exe, golden_dir, cfg):
     want = ((ref_bytes[:, None] >> np.arange(8)[None, :]) & 1).reshape(-1)
     assert np.array_equal(bits, want)  # receive_bit: LSB first, CRC bytes included (telecom_system.cc:636-644)
     assert int(lines["after_bad_config"].split()[1]) == fb
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_whole_receive_byte_on_a_reference_capture(exe, golden_dir):
+    """receive_byte(double* data, int* out) with the reference's own signature on the committed pass-band capture fixture."""
+    g = np.load(os.path.join(golden_dir, "frontend_mode08_clean.npz"))
+    x = np.load(os.path.join(golden_dir, "rx_mode08.npz"))["x"]
+    r = run(exe, 8, 50, x, capture=g["capture"].astype(np.float64))
+    assert r.returncode == 0, r.stderr
+    lines = dict(l.split(" ", 1) for l in r.stdout.strip().splitlines())
+    st = dict(zip(ref_fields(), g["stats"]))
+    for call in (0, 1):  # the second call carries the first one's link state; trial 0 decodes, so the outcome is the same
+        f = lines[f"capture{call}"].split()
+        assert int(f[0]) == int(st["decoded"]) == 1 and int(f[2]) == int(st["delay"]) and int(f[4]) == int(st["sync_trials"])
+        assert int(f[6]) == int(st["iterations"]) and int(f[8]) == int(st["crc"])
+        assert abs(float(f[10]) - st["freq_offset"]) < 1e-8 and float(f[12]) == st["coarse_metric"]
+        assert int(f[14]) == int(g["state_out"][0])
+        assert np.array_equal(np.array(lines[f"capture{call}_bytes"].split(), int), g["rx_payload"].astype(int))
+
+
+def ref_fields():
+    from oracle.ref import STAT12
+    return STAT12

@@ -67,6 +67,17 @@ def test_receive_byte_scenarios(ts, cfg):
     # ... float32 samples (exactly the values the reference saw: the scenario captures are float32-representable) ...
     payload32, st32, _ = ts.receive_byte_batch(caps.astype(np.float32), states.copy())
     assert np.array_equal(payload32, payload) and st32.tobytes() == st.tobytes()
+    # ... the PCM capture formats of the reference's audio layer (audioio.c:893-940): int16 (x / 32768.0) and int32 (x / INT_MAX),
+    # converted on the device, against the double entry point fed with the host-converted values and (first captures) the oracle
+    pcm16 = np.clip(np.rint(caps * 32768.0 * 0.5), -32768, 32767).astype(np.int16)
+    pcm32 = np.clip(np.rint(caps * 2147483647.0 * 0.5), -2147483647, 2147483647).astype(np.int32)
+    for pcm, conv in ((pcm16, pcm16.astype(np.float64) / 32768.0), (pcm32, pcm32.astype(np.float64) / float(2147483647))):
+        p_i, st_i, _ = ts.receive_byte_batch(pcm, states.copy())
+        p_d, st_d, _ = ts.receive_byte_batch(conv, states.copy())
+        assert np.array_equal(p_i, p_d) and st_i.tobytes() == st_d.tobytes(), pcm.dtype
+        for i in (0, 1):
+            _compare(r.receive_byte2(conv[i], int(states["delay_of_last_decoded_message"][i]), float(states["freq_offset_of_last_decoded_message"][i])),
+                     st_i[i], p_i[i], None, f"cfg{cfg}/{cases[i]}/{pcm.dtype}")
     # ... and the single-capture call in the reference's own types
     for i in (0, len(cases) - 1):
         one = states[i:i + 1].copy()

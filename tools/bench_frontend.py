@@ -76,8 +76,13 @@ def run(config=8, captures=1024, steps=5, warmup=2, noise=0.02, fmt="f32", cpu_c
     g = ts.load_configuration(config, 50)
     n, buf, fb = captures, ts.get_capture_samples(), g["frame_bytes"]
     caps64, pls, delays = make_captures(config, n, noise, dev, buf, g["preamble_nSymb"])
-    d_x = caps64.float().contiguous() if fmt == "f32" else caps64
-    sfmt = mb.SAMPLES_F32 if fmt == "f32" else mb.SAMPLES_F64
+    if fmt == "i16":  # 16-bit PCM capture (audioio.c:907: x / 32768.0); the CPU baseline below sees the same converted values
+        import torch as _t
+        d_x = _t.clamp(_t.round(caps64 * 32768.0), -32768, 32767).to(_t.int16).contiguous()
+        caps64 = d_x.double() / 32768.0
+    else:
+        d_x = caps64.float().contiguous() if fmt == "f32" else caps64
+    sfmt = {"f64": mb.SAMPLES_F64, "f32": mb.SAMPLES_F32, "i16": mb.SAMPLES_I16}[fmt]
     st0 = torch.from_numpy(mb.new_receive_stats(n).view(np.uint8).reshape(n, -1)).to(dev)
     d_st = st0.clone()
     d_pay = torch.zeros((n, fb), dtype=torch.uint8, device=dev)
@@ -109,7 +114,7 @@ def run(config=8, captures=1024, steps=5, warmup=2, noise=0.02, fmt="f32", cpu_c
         h_x = torch.empty(d_x.shape, dtype=d_x.dtype, pin_memory=True)
         h_x.copy_(d_x)
         hx = h_x.numpy()
-        ts.receive_byte_batch(hx)
+        ts.receive_byte_batch(hx)  # (dtype int16 / float32 / float64 selects the sample format)
         t0 = time.perf_counter()
         for _ in range(steps):
             p2, s2, _ = ts.receive_byte_batch(hx)
@@ -150,7 +155,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--noise", type=float, default=0.02)
-    ap.add_argument("--fmt", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--fmt", default="f32", choices=["f32", "f64", "i16"])
     ap.add_argument("--cpu-captures", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
