@@ -198,6 +198,11 @@ typedef struct mercury_b200_batcher mercury_b200_batcher_t;
 int mercury_b200_batcher_create(mercury_b200_t *h, size_t max_batch, unsigned max_wait_us, mercury_b200_batcher_t **out);
 int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float *baseband /* Nsymb x 272 x (re,im) */, uint8_t *payload,
 					  mercury_b200_rx_stats *stats);
+/* Pass-band flavour: every link's synchronous call hands over its whole capture buffer (capture_samples samples of `sample_format`)
+ * and its link-state record, like cl_telecom_system::receive_byte(double* data, int* out) (arq_common.cc:2668); one batch = one
+ * mercury_b200_receive_byte_batch over all waiting links. */
+int mercury_b200_batcher_create_passband(mercury_b200_t *h, int sample_format, size_t max_batch, unsigned max_wait_us, mercury_b200_batcher_t **out);
+int mercury_b200_batcher_receive_byte(mercury_b200_batcher_t *b, const void *passband, uint8_t *payload, mercury_b200_receive_stats *stats /* in/out */);
 int mercury_b200_batcher_get_counters(mercury_b200_batcher_t *b, uint64_t *batches, uint64_t *frames, uint64_t *full_batches);
 void mercury_b200_batcher_destroy(mercury_b200_batcher_t *b);
 /* Test hook: the same batching machinery in front of a caller-supplied batch function (plain host memory), so that the

@@ -90,6 +90,8 @@ def lib():
         "mercury_b200_kernel_launches": (u64, [vp]),
         "mercury_b200_batcher_create": (i32, [vp, sz, C.c_uint, C.POINTER(vp)]),
         "mercury_b200_batcher_receive_baseband": (i32, [vp, vp, vp, C.POINTER(RxStats)]),
+        "mercury_b200_batcher_create_passband": (i32, [vp, i32, sz, C.c_uint, C.POINTER(vp)]),
+        "mercury_b200_batcher_receive_byte": (i32, [vp, vp, vp, vp]),
         "mercury_b200_batcher_get_counters": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "mercury_b200_batcher_destroy": (None, [vp]),
         "mercury_b200_batcher_create_with_backend": (i32, [sz, sz, sz, C.c_uint, vp, vp, C.POINTER(vp)]),

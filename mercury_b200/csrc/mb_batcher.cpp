@@ -9,6 +9,8 @@
 //
 //   * callers copy their frame into the next free slot of a pinned staging buffer (two buffers, ping-pong) and sleep on
 //     the buffer's condition variable;
+//   (the pass-band flavour, mercury_b200_batcher_create_passband / _receive_byte, does the same with whole capture buffers and the
+//   whole receive_byte(): front-end + tail, link state in and out)
 //   * one worker thread closes a buffer when it is full or when its oldest frame has waited max_wait_us, runs ONE
 //     mercury_b200_demod_decode_batch over it (H2D, two kernels, D2H, pipelined in chunks), and wakes the callers, who copy
 //     their own payload / stats out.
@@ -28,9 +30,9 @@
 namespace {
 
 struct Buffer {
-	float *x = nullptr;                       // pinned: capacity x frame_floats
+	uint8_t *x = nullptr;                     // pinned: capacity x in_bytes (one frame / one capture per slot)
 	uint8_t *payload = nullptr;               // pinned: capacity x frame_bytes
-	mercury_b200_rx_stats *stats = nullptr;   // pinned: capacity records
+	uint8_t *stats = nullptr;                 // pinned: capacity x stats_bytes records
 	size_t filled = 0;                        // slots handed out
 	size_t written = 0;                       // slots whose copy-in has finished
 	size_t readers = 0;                       // callers that still have to copy their result out
@@ -43,14 +45,18 @@ struct Buffer {
 
 }  // namespace
 
-typedef int (*mb_batch_fn)(void *ctx, const float *x, size_t n, uint8_t *payload, mercury_b200_rx_stats *stats);
+typedef int (*mb_batch_fn)(void *ctx, const void *x, size_t n, uint8_t *payload, void *stats);
 
 struct mercury_b200_batcher {
 	mercury_b200_t *h = nullptr;
 	mb_batch_fn run = nullptr;  // what decodes a closed batch: the library's host-buffer batch call, or a test double
 	void *run_ctx = nullptr;
 	bool pinned = true;
-	size_t capacity = 0, frame_floats = 0, frame_bytes = 0;
+	size_t capacity = 0, in_bytes = 0, frame_bytes = 0, stats_bytes = 0;
+	bool stats_in = false;  // the caller's stats record is an input too (the link state of the whole receive_byte())
+	int sample_format = 0;
+	int (*user_run)(void *, const float *, size_t, uint8_t *, mercury_b200_rx_stats *) = nullptr;  // test double of the baseband flavour
+	void *user_ctx = nullptr;
 	std::chrono::microseconds max_wait{200};
 	std::mutex mu;
 	std::condition_variable work;   // worker: a buffer has frames / shutdown
@@ -109,9 +115,22 @@ void worker_loop(mercury_b200_batcher *b)
 
 extern "C" {
 
-static int run_on_gpu(void *ctx, const float *x, size_t n, uint8_t *payload, mercury_b200_rx_stats *stats)
+static int run_on_gpu(void *ctx, const void *x, size_t n, uint8_t *payload, void *stats)
 {
-	return mercury_b200_demod_decode_batch(static_cast<mercury_b200_t *>(ctx), x, n, payload, stats, nullptr);
+	mercury_b200_batcher *b = static_cast<mercury_b200_batcher *>(ctx);
+	return mercury_b200_demod_decode_batch(b->h, static_cast<const float *>(x), n, payload, static_cast<mercury_b200_rx_stats *>(stats), nullptr);
+}
+
+static int run_passband_on_gpu(void *ctx, const void *x, size_t n, uint8_t *payload, void *stats)
+{
+	mercury_b200_batcher *b = static_cast<mercury_b200_batcher *>(ctx);
+	return mercury_b200_receive_byte_batch(b->h, x, b->sample_format, n, payload, static_cast<mercury_b200_receive_stats *>(stats), nullptr);
+}
+
+static int run_user(void *ctx, const void *x, size_t n, uint8_t *payload, void *stats)
+{
+	mercury_b200_batcher *b = static_cast<mercury_b200_batcher *>(ctx);
+	return b->user_run(b->user_ctx, static_cast<const float *>(x), n, payload, static_cast<mercury_b200_rx_stats *>(stats));
 }
 
 static void free_buffers(mercury_b200_batcher *b)
@@ -129,21 +148,22 @@ static void free_buffers(mercury_b200_batcher *b)
 	}
 }
 
-static int create(size_t frame_floats, size_t frame_bytes, size_t max_batch, unsigned max_wait_us, mb_batch_fn run, void *ctx, bool pinned,
+static int create(size_t in_bytes, size_t frame_bytes, size_t stats_bytes, size_t max_batch, unsigned max_wait_us, mb_batch_fn run, bool pinned,
 		  mercury_b200_batcher_t **out)
 {
 	mercury_b200_batcher *b = new (std::nothrow) mercury_b200_batcher;
 	if (!b) return MERCURY_B200_ENOMEM;
-	b->run = run, b->run_ctx = ctx, b->pinned = pinned;
+	b->run = run, b->run_ctx = b, b->pinned = pinned;
 	b->capacity = max_batch;
-	b->frame_floats = frame_floats;
+	b->in_bytes = in_bytes;
 	b->frame_bytes = frame_bytes;
+	b->stats_bytes = stats_bytes;
 	b->max_wait = std::chrono::microseconds(max_wait_us);
 	for (Buffer &B : b->buf) {
 		auto alloc = [&](size_t bytes) { return pinned ? mercury_b200_host_alloc(bytes) : malloc(bytes); };
-		B.x = static_cast<float *>(alloc(max_batch * frame_floats * sizeof(float)));
+		B.x = static_cast<uint8_t *>(alloc(max_batch * in_bytes));
 		B.payload = static_cast<uint8_t *>(alloc(max_batch * frame_bytes));
-		B.stats = static_cast<mercury_b200_rx_stats *>(alloc(max_batch * sizeof(mercury_b200_rx_stats)));
+		B.stats = static_cast<uint8_t *>(alloc(max_batch * stats_bytes));
 	}
 	for (Buffer &B : b->buf)
 		if (!B.x || !B.payload || !B.stats) {
@@ -151,10 +171,11 @@ static int create(size_t frame_floats, size_t frame_bytes, size_t max_batch, uns
 			delete b;
 			return MERCURY_B200_ENOMEM;
 		}
-	b->worker = std::thread(worker_loop, b);
 	*out = b;
 	return MERCURY_B200_OK;
 }
+
+static void start(mercury_b200_batcher *b) { b->worker = std::thread(worker_loop, b); }
 
 int mercury_b200_batcher_create(mercury_b200_t *h, size_t max_batch, unsigned max_wait_us, mercury_b200_batcher_t **out)
 {
@@ -163,7 +184,40 @@ int mercury_b200_batcher_create(mercury_b200_t *h, size_t max_batch, unsigned ma
 	mercury_b200_geometry g;
 	const int rc = mercury_b200_get_geometry(h, &g);
 	if (rc != MERCURY_B200_OK) return rc;
-	return create((size_t)g.Nsymb * MERCURY_B200_NOFDM * 2, (size_t)g.frame_bytes, max_batch, max_wait_us, run_on_gpu, h, true, out);
+	const int rc2 = create((size_t)g.Nsymb * MERCURY_B200_NOFDM * 2 * sizeof(float), (size_t)g.frame_bytes, sizeof(mercury_b200_rx_stats), max_batch, max_wait_us,
+			       run_on_gpu, true, out);
+	if (rc2 != MERCURY_B200_OK) return rc2;
+	(*out)->h = h;
+	start(*out);
+	return MERCURY_B200_OK;
+}
+
+// The same machinery one level up (SURVEY.md 8f rows 1 + 4): every link hands its whole pass-band capture buffer to a synchronous
+// receive_byte()-shaped call (arq_common.cc:2619-2668); the batch runs the GPU front-end + tail over all of them at once.
+int mercury_b200_batcher_create_passband(mercury_b200_t *h, int sample_format, size_t max_batch, unsigned max_wait_us, mercury_b200_batcher_t **out)
+{
+	if (!h || !out || max_batch == 0) return MERCURY_B200_EINVAL;
+	*out = nullptr;
+	mercury_b200_geometry g;
+	const int rc = mercury_b200_get_geometry(h, &g);
+	if (rc != MERCURY_B200_OK) return rc;
+	size_t ss;
+	switch (sample_format) {
+	case MERCURY_B200_SAMPLES_F64: ss = 8; break;
+	case MERCURY_B200_SAMPLES_F32: ss = 4; break;
+	case MERCURY_B200_SAMPLES_I16: ss = 2; break;
+	case MERCURY_B200_SAMPLES_I32: ss = 4; break;
+	default: return MERCURY_B200_EINVAL;
+	}
+	const int cs = mercury_b200_get_capture_samples(h);
+	if (cs <= 0) return MERCURY_B200_ESTATE;
+	const int rc2 = create((size_t)cs * ss, (size_t)g.frame_bytes, sizeof(mercury_b200_receive_stats), max_batch, max_wait_us, run_passband_on_gpu, true, out);
+	if (rc2 != MERCURY_B200_OK) return rc2;
+	(*out)->h = h;
+	(*out)->sample_format = sample_format;
+	(*out)->stats_in = true;
+	start(*out);
+	return MERCURY_B200_OK;
 }
 
 // Test hook (not part of the product surface): the same batching machinery in front of a caller-supplied batch function, so
@@ -174,12 +228,15 @@ int mercury_b200_batcher_create_with_backend(size_t frame_floats, size_t frame_b
 {
 	if (!run || !out || max_batch == 0 || frame_floats == 0 || frame_bytes == 0) return MERCURY_B200_EINVAL;
 	*out = nullptr;
-	return create(frame_floats, frame_bytes, max_batch, max_wait_us, run, ctx, false, out);
+	const int rc = create(frame_floats * sizeof(float), frame_bytes, sizeof(mercury_b200_rx_stats), max_batch, max_wait_us, run_user, false, out);
+	if (rc != MERCURY_B200_OK) return rc;
+	(*out)->user_run = run, (*out)->user_ctx = ctx;
+	start(*out);
+	return MERCURY_B200_OK;
 }
 
-int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float *baseband, uint8_t *payload, mercury_b200_rx_stats *stats)
+static int submit(mercury_b200_batcher_t *b, const void *in, uint8_t *payload, void *stats)
 {
-	if (!b || !baseband || !payload || !stats) return MERCURY_B200_EINVAL;
 	std::unique_lock<std::mutex> lk(b->mu);
 	Buffer *B;
 	for (;;) {  // a buffer that accepts frames: not closed, not full, previous results all read out
@@ -193,7 +250,8 @@ int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float
 	if (slot == 0) B->first = std::chrono::steady_clock::now();
 	if (slot == 0 || B->filled == b->capacity) b->work.notify_one();
 	lk.unlock();
-	memcpy(B->x + slot * b->frame_floats, baseband, b->frame_floats * sizeof(float));  // outside the lock: links copy in parallel
+	memcpy(B->x + slot * b->in_bytes, in, b->in_bytes);  // outside the lock: links copy in parallel
+	if (b->stats_in) memcpy(B->stats + slot * b->stats_bytes, stats, b->stats_bytes);
 	lk.lock();
 	B->written++;
 	if (B->closed && B->written == B->filled) b->work.notify_one();
@@ -202,7 +260,7 @@ int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float
 	lk.unlock();
 	if (rc == MERCURY_B200_OK) {
 		memcpy(payload, B->payload + slot * b->frame_bytes, b->frame_bytes);
-		*stats = B->stats[slot];
+		memcpy(stats, B->stats + slot * b->stats_bytes, b->stats_bytes);
 	}
 	lk.lock();
 	if (--B->readers == 0) {  // last reader re-opens the buffer
@@ -212,6 +270,18 @@ int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float
 		b->work.notify_one();
 	}
 	return rc;
+}
+
+int mercury_b200_batcher_receive_baseband(mercury_b200_batcher_t *b, const float *baseband, uint8_t *payload, mercury_b200_rx_stats *stats)
+{
+	if (!b || !baseband || !payload || !stats || b->stats_in) return MERCURY_B200_EINVAL;
+	return submit(b, baseband, payload, stats);
+}
+
+int mercury_b200_batcher_receive_byte(mercury_b200_batcher_t *b, const void *passband, uint8_t *payload, mercury_b200_receive_stats *stats)
+{
+	if (!b || !passband || !payload || !stats || !b->stats_in) return MERCURY_B200_EINVAL;
+	return submit(b, passband, payload, stats);
 }
 
 int mercury_b200_batcher_get_counters(mercury_b200_batcher_t *b, uint64_t *batches, uint64_t *frames, uint64_t *full_batches)

@@ -14,10 +14,10 @@ SRC = os.path.join(ROOT, "tests", "cpp", "batcher_test.cpp")
 LIBDIR = os.path.join(ROOT, "mercury_b200")
 
 
-def build(tmp, name, extra=(), extra_src=()):
+def build(tmp, name, extra=(), extra_src=(), src=None):
     _lib.lib()
     out = str(tmp / name)
-    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1", "-pthread", *extra, "-I", os.path.join(ROOT, "include"), SRC,
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1", "-pthread", *extra, "-I", os.path.join(ROOT, "include"), src or SRC,
                            *extra_src, "-o", out, "-L", LIBDIR, "-lmercury_b200", f"-Wl,-rpath,{LIBDIR}"])
     return out
 
@@ -64,3 +64,22 @@ def test_links_share_gpu_batches_and_get_identical_results(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     s = summary(r.stdout)
     assert s["bad"] == 0 and s["frames"] == 128 * 40 and s["mean_batch"] > 16
+
+
+def test_passband_batcher_program_compiles(tmp_path):
+    build(tmp_path, "batcher_passband_test", src=os.path.join(ROOT, "tests", "cpp", "batcher_passband_test.cpp"))
+
+
+@pytest.mark.gpu
+def test_links_share_whole_receive_byte_batches(tmp_path, golden_dir):
+    """Pass-band flavour: 48 link threads x 6 synchronous receive_byte()-shaped calls on whole capture buffers (the committed reference
+    capture at 288 different delays); every payload and stats record identical to one direct mercury_b200_receive_byte_batch call."""
+    import numpy as np
+    exe = build(tmp_path, "batcher_passband_test", src=os.path.join(ROOT, "tests", "cpp", "batcher_passband_test.cpp"))
+    cap = np.load(os.path.join(golden_dir, "frontend_mode08_clean.npz"))["capture"].astype(np.float32)
+    path = str(tmp_path / "capture.f32")
+    cap.tofile(path)
+    r = subprocess.run([exe, _lib.LDPC_TABLES, "8", path, "48", "6", "64", "2000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    s = summary(r.stdout)
+    assert s["bad"] == 0 and s["calls"] == 288 and s["mean_batch"] > 4 and s["decoded"] >= 280
