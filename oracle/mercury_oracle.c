@@ -1251,3 +1251,197 @@ double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_cal
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ================================================================================================
+ * TX CHAIN to pass-band: cl_telecom_system::transmit_byte / transmit_bit with
+ * message_location == SINGLE_MESSAGE, source/physical_layer/telecom_system.cc:342-553, OFDM branch.
+ * ============================================================================================== */
+
+/* cl_FIR::design for the two transmit filters (fir_filter.cc:45-163): tx1 = HPF (spectral inversion of the LPF at the HPF cut) +
+ * HAMMING, tx2 = LPF + BLACKMAN; 1000 Hz transition -> 97 taps (physical_config.cc:103-113). */
+static void fir_design_tx(int type_hpf, int blackman, double fcut, double tbw, double fs, int *ntaps_out, double *c)
+{
+	int n = (int)(4.0 / (tbw / (fs / 2.0)));
+	if (n % 2 == 0) n++;
+	double Ts = 1.0 / (fs), temp;
+	c[n / 2] = 1;
+	for (int i = 0; i < n / 2; i++) {
+		temp = 2 * M_PI * fcut * (double)(n / 2 - i) * Ts;
+		c[i] = sin(temp) / temp;
+		c[n - i - 1] = c[i];
+	}
+	temp = 0;
+	for (int i = 0; i < n; i++) temp += c[i];
+	for (int i = 0; i < n; i++) c[i] /= temp;
+	if (type_hpf) {
+		for (int i = 0; i < n; i++) c[i] *= -1;
+		c[(int)(n - 1) / 2] += 1;
+	}
+	if (!blackman)
+		for (int i = 0; i < n; i++) c[i] *= 0.54 - 0.46 * cos(2.0 * M_PI * (double)i / (n - 1));
+	else
+		for (int i = 0; i < n; i++) c[i] *= 0.42 - 0.5 * cos(2.0 * M_PI * (double)i / n) + 0.08 * cos(4.0 * M_PI * (double)i / n);
+	*ntaps_out = n;
+}
+
+/* cl_FIR::apply(double*): fir_filter.cc:189-210. */
+static void fir_apply_real(const double *c, int nt, const double *in, double *out, int n)
+{
+	for (int i = 0; i < n + nt - 1; i++) {
+		double acc = 0;
+		for (int j = 0; j < nt; j++)
+			if ((i - j) >= 0 && (i - j) < n) acc += in[i - j] * c[j];
+		if (i >= (nt - 1) / 2 && i < n + (nt - 1) / 2) out[i - (nt - 1) / 2] = acc;
+	}
+}
+
+/* cl_ofdm::baseband_to_passband: ofdm.cc:2294-2315 (rational_resampler INTERPOLATION :2279-2292, then the mix with the RUNNING
+ * carrier sample counter passband_start_sample). */
+static void b2p(const mo_mode *m, const double complex *in, int n, double *out, double fc, unsigned long *start_sample)
+{
+	const mo_frontend *f = &m->fe;
+	int rate = f->interp;
+	double complex *di = malloc(sizeof(double complex) * n * rate);
+	double Ts = 1.0 / f->fs;
+	for (int i = 0; i < n - 1; i++)
+		for (int j = 0; j < rate; j++) di[i * rate + j] = lerp(in[i], 0, in[i + 1], rate, j);
+	for (int j = 0; j < rate; j++) di[(n - 1) * rate + j] = lerp(in[n - 2], 0, in[n - 1], rate, rate + j);
+	for (int i = 0; i < n * rate; i++) {
+		out[i] = creal(di[i]) * f->amp * cos(2 * M_PI * fc * (double)(*start_sample) * Ts);
+		out[i] += cimag(di[i]) * f->amp * sin(2 * M_PI * fc * (double)(*start_sample) * Ts);
+		(*start_sample)++;
+	}
+	free(di);
+}
+
+/* cl_ofdm::peak_clip(double*): ofdm.cc:1565-1592. */
+static void peak_clip(double *x, int n, double papr)
+{
+	double avg = 0;
+	for (int i = 0; i < n; i++) avg += pow(x[i], 2);
+	avg /= n;
+	double peak = sqrt(avg * pow(10, papr / 10.0));
+	for (int i = 0; i < n; i++) {
+		if (x[i] > 0 && x[i] > peak) x[i] = peak;
+		if (x[i] < 0 && x[i] < -peak) x[i] = -peak;
+	}
+}
+
+/* TX-side tables: preamble (cl_preamble_configurator::init/configure, ofdm.cc:1128-1239; QPSK, boost sqrt(2), seed 1,
+ * physical_config.cc:50-54), the pilot PRNG stream that precedes it, the transmit FIRs and the pre-equalisation channel
+ * (get_pre_equalization_channel, telecom_system.cc:3108-3146: 1000 random symbols through TX filters -> RX filter -> FFT). */
+void mo_tx_init(mo_mode *m)
+{
+	mo_tx *t = &m->tx;
+	mo_frontend *f = &m->fe;
+	int pre = m->preamble_nSymb;
+	/* the preamble is configured BEFORE the pilots (ofdm.cc:112-113): srandom(seed 1), two draws per carrier slot of the sequence */
+	mo_srandom(1);
+	double complex seq[4 * MO_NC];
+	for (int i = 0; i < pre * MO_NC; i++) {
+		/* std::complex<double>(2*(__random()%2)-1, 2*(__random()%2)-1): g++ evaluates the constructor arguments right to left */
+		int second = mo_random() % 2, first = mo_random() % 2;
+		seq[i] = ((double)(2 * first - 1) + (double)(2 * second - 1) * I) / sqrt(2);
+	}
+	int k = 0;
+	for (int s = 0; s < pre; s++)
+		for (int c = 0; c < MO_NC; c++) {
+			int bin = c < MO_NC / 2 ? c + MO_NFFT - MO_NC / 2 : c - MO_NC / 2 + 1; /* start_shift = 1 */
+			int is_pre = (bin % 2 == 0);
+			t->preamble_type[s * MO_NC + c] = is_pre;
+			t->preamble[s * MO_NC + c] = is_pre ? seq[k++] : 0;
+		}
+	t->preamble_boost = sqrt(2);
+	t->output_power = 0.1;
+	t->preamble_papr = 7, t->data_papr = 10;
+	fir_design_tx(1, 0, f->fc - f->bandwidth / 2, 1000, f->fs, &t->ntaps1, t->c1);
+	fir_design_tx(0, 1, f->fc + f->bandwidth / 2, 1000, f->fs, &t->ntaps2, t->c2);
+	/* pre-equalisation: the PRNG continues from where the pilot sequence left it (srandom(0), one draw per pilot, ofdm.cc:940-951) */
+	mo_srandom(0);
+	for (int i = 0; i < m->nPilots; i++) (void)mo_random();
+	int nb = (int)(MO_NC * log2(m->M)), b = m->bits_per_symbol, sym = m->Nofdm * f->interp;
+	double complex acc[MO_NC], mod[MO_NC], smod[MO_NOFDM], bb[MO_NOFDM], dem[MO_NC];
+	double complex *l = malloc(sizeof(double complex) * sym), *lf = malloc(sizeof(double complex) * sym);
+	double *pb = malloc(sizeof(double) * sym), *p1 = malloc(sizeof(double) * sym), *p2 = malloc(sizeof(double) * sym);
+	int bits[MO_NC * 8];
+	for (int i = 0; i < MO_NC; i++) acc[i] = 0;
+	for (int trial = 0; trial < 1000; trial++) {
+		for (int i = 0; i < nb; i++) bits[i] = mo_random() % 2;
+		for (int i = 0; i < nb; i += b) {
+			unsigned loc = 0;
+			for (int j = 0; j < b; j++) loc = (loc << 1) | (unsigned)bits[i + j];
+			mod[i / b] = m->constellation[loc];
+		}
+		symbol_mod(m, mod, smod);
+		unsigned long start = 0;
+		b2p(m, smod, m->Nofdm, pb, f->fc, &start);
+		fir_apply_real(t->c1, t->ntaps1, pb, p1, sym);
+		fir_apply_real(t->c2, t->ntaps2, p1, p2, sym);
+		p2b(m, p2, sym, lf, f->fc, 1, l);
+		for (int i = 0, q = 0; i < sym; i += f->interp) bb[q++] = lf[i];
+		symbol_demod(m, bb, dem);
+		for (int i = 0; i < MO_NC; i++) acc[i] += mod[i] / dem[i];
+	}
+	for (int i = 0; i < MO_NC; i++) t->pre_eq[i] = acc[i] / (double)1000;
+	t->start_sample_after_init = (unsigned long)sym;
+	free(l), free(lf), free(pb), free(p1), free(p2);
+	t->ready = 1;
+}
+
+void mo_tx_tables(mo_mode *m, double complex *preamble, int *preamble_type, double complex *pre_eq, int *ntaps, double *c1, double *c2, double *consts)
+{
+	if (!m->tx.ready) mo_tx_init(m);
+	const mo_tx *t = &m->tx;
+	memcpy(preamble, t->preamble, sizeof(double complex) * m->preamble_nSymb * MO_NC);
+	memcpy(preamble_type, t->preamble_type, sizeof(int) * m->preamble_nSymb * MO_NC);
+	memcpy(pre_eq, t->pre_eq, sizeof(double complex) * MO_NC);
+	ntaps[0] = t->ntaps1, ntaps[1] = t->ntaps2;
+	memcpy(c1, t->c1, sizeof(double) * t->ntaps1);
+	memcpy(c2, t->c2, sizeof(double) * t->ntaps2);
+	double v[8] = {t->output_power, t->preamble_boost, t->preamble_papr, t->data_papr, (double)t->start_sample_after_init,
+		       (double)((m->Nsymb + m->preamble_nSymb) * m->Nofdm * m->fe.interp), 1, 0};
+	memcpy(consts, v, sizeof(v));
+}
+
+/* transmit_byte + transmit_bit, SINGLE_MESSAGE: telecom_system.cc:342-553.  Returns total_frame_size; *start_sample is the running
+ * carrier sample counter (ofdm.passband_start_sample), in and out. */
+int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout)
+{
+	if (!m->tx.ready) mo_tx_init(m);
+	const mo_tx *t = &m->tx;
+	const mo_frontend *f = &m->fe;
+	int pre = m->preamble_nSymb, S = m->Nsymb, rate = f->interp, No = m->Nofdm;
+	int total = (S + pre) * No * rate;
+	double complex framed[MO_MAX_CELLS], pdata[4 * MO_NC];
+	double complex *bbp = malloc(sizeof(double complex) * pre * No), *bbd = malloc(sizeof(double complex) * S * No);
+	double complex *scratch = malloc(sizeof(double complex) * S * No);
+	mo_tx_baseband(m, payload, nBytes, scratch, NULL, NULL, framed); /* bit chain + framer (:384-462) */
+	free(scratch);
+	for (int i = 0; i < pre * MO_NC; i++) pdata[i] = t->preamble[i]; /* :466-473 */
+	for (int i = 0; i < pre; i++)
+		for (int j = 0; j < MO_NC; j++) pdata[i * MO_NC + j] *= t->pre_eq[j]; /* :477-492 */
+	for (int i = 0; i < S; i++)
+		for (int j = 0; j < MO_NC; j++) framed[i * MO_NC + j] *= t->pre_eq[j];
+	for (int i = 0; i < pre; i++) symbol_mod(m, pdata + i * MO_NC, bbp + i * No); /* :495-505 */
+	for (int i = 0; i < S; i++) symbol_mod(m, framed + i * MO_NC, bbd + i * No);
+	float power_normalization = sqrt((double)(MO_NFFT * rate)); /* :388 */
+	for (int j = 0; j < No * pre; j++) {			     /* :517-527 */
+		bbp[j] /= power_normalization;
+		bbp[j] *= sqrt(t->output_power) * t->preamble_boost * 1.0;
+	}
+	for (int j = 0; j < No * S; j++) {
+		bbd[j] /= power_normalization;
+		bbd[j] *= sqrt(t->output_power) * 1.0;
+	}
+	unsigned long start = (unsigned long)*start_sample_inout;
+	double *pb = malloc(sizeof(double) * total), *p1 = malloc(sizeof(double) * total);
+	b2p(m, bbp, No * pre, pb, f->fc, &start); /* :531-532 */
+	b2p(m, bbd, No * S, pb + No * pre * rate, f->fc, &start);
+	peak_clip(pb, No * pre * rate, t->preamble_papr); /* :534-535 */
+	peak_clip(pb + No * pre * rate, No * S * rate, t->data_papr);
+	fir_apply_real(t->c1, t->ntaps1, pb, p1, total); /* :546-553 */
+	fir_apply_real(t->c2, t->ntaps2, p1, out, total);
+	*start_sample_inout = (double)start;
+	free(bbp), free(bbd), free(pb), free(p1);
+	return total;
+}

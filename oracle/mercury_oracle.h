@@ -33,6 +33,17 @@ typedef struct mo_frontend {
 	double c_ts[64], c_data[64];
 } mo_frontend;
 
+/* TX-side tables, built lazily by mo_tx_init(). */
+typedef struct mo_tx {
+	int ready, ntaps1, ntaps2;
+	int preamble_type[4 * MO_NC];		 /* 1 = PREAMBLE carrier, 0 = ZERO */
+	double complex preamble[4 * MO_NC];
+	double complex pre_eq[MO_NC];
+	double c1[128], c2[128];
+	double output_power, preamble_boost, preamble_papr, data_papr;
+	unsigned long start_sample_after_init;
+} mo_tx;
+
 typedef struct mo_mode {
 	int config, M, bits_per_symbol, rate_num;
 	int Nsymb, Nc, Nfft, Ngi, Nofdm, nData, nPilots, nBits;
@@ -53,6 +64,7 @@ typedef struct mo_mode {
 	double complex twiddle[MO_NFFT / 2];
 	int bitrev[MO_NFFT];
 	mo_frontend fe;
+	mo_tx tx;
 } mo_mode;
 
 typedef struct mo_rx_out {
@@ -91,6 +103,10 @@ void mo_frontend_init(mo_mode *m);
 void mo_frontend_tables(const mo_mode *m, int *ntaps /*[2]*/, double *ts_coef, double *data_coef, double *consts /*[8]*/);
 void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats /*[12]*/, double *state /*[2]*/,
 		     double complex *baseband_out);
+/* TX chain to pass-band: transmit_byte(SINGLE_MESSAGE). */
+void mo_tx_init(mo_mode *m);
+void mo_tx_tables(mo_mode *m, double complex *preamble, int *preamble_type, double complex *pre_eq, int *ntaps, double *c1, double *c2, double *consts);
+int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

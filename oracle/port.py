@@ -50,6 +50,9 @@ def lib():
         L.mo_receive_byte_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.mo_receive_byte_timed.restype = C.c_double
         L.mo_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.mo_tx_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.mo_transmit_byte.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mo_transmit_byte.restype = C.c_int
         _lib = L
     return _lib
 

@@ -66,6 +66,9 @@ def lib():
         L.mref_receive_byte_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.mref_receive_byte_timed.restype = C.c_double
         L.mref_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.mref_tx_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.mref_transmit_byte2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mref_transmit_byte2.restype = C.c_int
         _lib = L
     return _lib
 
@@ -131,6 +134,30 @@ class FrontEndMixin:
         dec = np.zeros(n, np.int32)
         secs = getattr(self._felib(), self._fe + "receive_byte_timed")(self.h, _p(pb), n, _p(dec))
         return secs, dec
+
+    def tx_tables(self):
+        """Preamble carriers, pre-equalisation channel, transmit FIRs, TX constants (row 2)."""
+        n = self.preamble_nSymb * self.Nc
+        pre = np.zeros(n, np.complex128)
+        typ = np.zeros(n, np.int32)
+        peq = np.zeros(self.Nc, np.complex128)
+        nt = np.zeros(2, np.int32)
+        c1 = np.zeros(128, np.float64)
+        c2 = np.zeros(128, np.float64)
+        k = np.zeros(8, np.float64)
+        getattr(self._felib(), self._fe + "tx_tables")(self.h, _p(pre), _p(typ), _p(peq), _p(nt), _p(c1), _p(c2), _p(k))
+        return dict(preamble=pre, preamble_is_carrier=(typ == int(k[6])).astype(np.int32), pre_eq=peq, tx1=c1[:nt[0]].copy(), tx2=c2[:nt[1]].copy(),
+                    output_power=k[0], preamble_boost=k[1], preamble_papr=k[2], data_papr=k[3], start_sample_after_init=int(k[4]),
+                    total_frame_size=int(k[5]))
+
+    def transmit_byte2(self, payload, start_sample):
+        """transmit_byte(SINGLE_MESSAGE) from a chosen running carrier sample counter -> (passband[total_frame_size], counter after)."""
+        pl = np.asarray(list(payload), np.int32)
+        out = np.zeros(self.total_frame_size + 16, np.float64)
+        st = np.array([float(start_sample)], np.float64)
+        name = "mref_transmit_byte2" if self._fe == "mref_" else "mo_transmit_byte"
+        n = getattr(self._felib(), name)(self.h, _p(pl), len(pl), _p(out), _p(st))
+        return out[:n], int(st[0])
 
     def frontend_tables(self):
         nt = np.zeros(2, np.int32)

@@ -540,4 +540,56 @@ void mref_frontend_tables(void *h, int *ntaps /*[2]*/, double *ts_coef, double *
 	consts[7] = ts.ofdm.freq_offset_ignore_limit;
 }
 
+/* TX-side tables of the reference for pinning the restatement: preamble carriers (value, type), pre-equalisation channel
+ * (telecom_system.cc:3108-3146), the two transmit FIRs read as impulse responses, and the running carrier sample counter. */
+void mref_tx_tables(void *h, double *preamble /*[pre*Nc*2]*/, int *preamble_type /*[pre*Nc]*/, double *pre_eq /*[Nc*2]*/, int *ntaps /*[2]*/,
+		    double *tx1_coef, double *tx2_coef, double *consts /*[8]*/)
+{
+	cl_telecom_system &ts = T(h);
+	int n = ts.data_container.preamble_nSymb * ts.data_container.Nc;
+	for (int i = 0; i < n; i++) {
+		preamble[2 * i] = ts.ofdm.ofdm_preamble[i].value.real();
+		preamble[2 * i + 1] = ts.ofdm.ofdm_preamble[i].value.imag();
+		preamble_type[i] = ts.ofdm.ofdm_preamble[i].type;
+	}
+	for (int j = 0; j < ts.data_container.Nc; j++) {
+		pre_eq[2 * j] = ts.pre_equalization_channel[j].value.real();
+		pre_eq[2 * j + 1] = ts.pre_equalization_channel[j].value.imag();
+	}
+	ntaps[0] = ts.ofdm.FIR_tx1.filter_nTaps;
+	ntaps[1] = ts.ofdm.FIR_tx2.filter_nTaps;
+	for (int f = 0; f < 2; f++) {
+		cl_FIR &fir = f == 0 ? ts.ofdm.FIR_tx1 : ts.ofdm.FIR_tx2;
+		int nt = ntaps[f];
+		double *imp = new double[nt](), *resp = new double[nt]();
+		imp[(nt - 1) / 2] = 1.0;
+		fir.apply(imp, resp, nt);
+		for (int i = 0; i < nt; i++) (f == 0 ? tx1_coef : tx2_coef)[i] = resp[i];
+		delete[] imp;
+		delete[] resp;
+	}
+	consts[0] = ts.output_power_Watt;
+	consts[1] = ts.ofdm.preamble_configurator.boost;
+	consts[2] = ts.ofdm.preamble_papr_cut;
+	consts[3] = ts.ofdm.data_papr_cut;
+	consts[4] = (double)ts.ofdm.passband_start_sample;
+	consts[5] = ts.data_container.total_frame_size;
+	consts[6] = PREAMBLE;
+	consts[7] = ZERO;
+}
+
+/* transmit_byte(SINGLE_MESSAGE) from a chosen carrier phase: sets ofdm.passband_start_sample first, returns it afterwards. */
+int mref_transmit_byte2(void *h, const int *payload, int nBytes, double *passband_out, double *start_sample_inout)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	int buf[N_MAX];
+	memset(buf, 0, sizeof(buf));
+	for (int i = 0; i < nBytes; i++) buf[i] = payload[i];
+	ts.ofdm.passband_start_sample = (long unsigned)*start_sample_inout;
+	ts.transmit_byte(buf, nBytes, passband_out, SINGLE_MESSAGE);
+	*start_sample_inout = (double)ts.ofdm.passband_start_sample;
+	return ts.data_container.total_frame_size;
+}
+
 }  // extern "C"

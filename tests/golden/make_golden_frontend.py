@@ -35,5 +35,20 @@ def main():
         r.close()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--tx" not in sys.argv:
     main()
+
+
+def tx_fixture():
+    """tx_mode16.npz: one reference transmit_byte(SINGLE_MESSAGE) frame with its TX tables."""
+    r = ref.Ref(16, 50)
+    t = r.tx_tables()
+    pl = np.random.default_rng(16).integers(0, 256, r.frame_bytes).astype(np.int32)
+    out, after = r.transmit_byte2(pl, 4321)
+    np.savez_compressed(os.path.join(HERE, "tx_mode16.npz"), config=16, payload=pl, start_sample=4321, start_sample_after=after, passband=out,
+                        pre_eq=t["pre_eq"], preamble=t["preamble"], tx1=t["tx1"], tx2=t["tx2"])
+    print("tx fixture", out.size, after)
+
+
+if __name__ == "__main__" and "--tx" in sys.argv:
+    tx_fixture()
