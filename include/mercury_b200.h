@@ -24,6 +24,8 @@
  *   mercury_b200_ldpc_decode_batch_device    ldpc.decode .. CRC16                  (telecom_system.cc:1310-1349)
  *   mercury_b200_receive_byte(_batch)    st_receive_stats receive_byte(double*,int*) WHOLE (telecom_system.h:142, .cc:646-1518):
  *                                        pass-band capture in, front-end on the GPU
+ *   mercury_b200_transmit_byte(_batch)   void transmit_byte(int*, int, double*, SINGLE_MESSAGE) (telecom_system.h:138, .cc:342-553): the TX chain
+ *                                        to pass-band on the GPU
  *   mercury_b200_rx_stats                st_receive_stats (telecom_system.h:63-82), the fields the tail writes
  *   mercury_b200_batcher_*               (new) many concurrent links' receive calls -> one GPU batch; replaces the one-frame-per-call
  *                                        pattern of arq_common.cc:2619-2668 / audioio.c:999-1069 for a multi-link gateway
@@ -176,6 +178,26 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *passband, int
  * three counters back per round, so this call synchronises `stream` before it returns. */
 int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_passband, int sample_format, size_t n_captures, void *d_payload,
 					   void *d_stats, void *stream);
+
+/*
+ * TX chain on the GPU: void cl_telecom_system::transmit_byte(int* data, int nBytes, double* out, int message_location)
+ * with message_location == SINGLE_MESSAGE (telecom_system.h:138, .cc:342-553, OFDM branch): zero pad + CRC16, scrambler, LDPC encode,
+ * interleavers, mapper, framer, preamble, pre-equalisation (telecom_system.cc:3108-3146), IFFT + guard interval, x4 interpolation and mixing
+ * (ofdm.cc:2279-2315), PAPR clip (ofdm.cc:1565-1592), FIR_tx1, FIR_tx2 -> mercury_b200_get_total_frame_size() pass-band samples per frame.
+ * The reference's running carrier sample counter (ofdm.passband_start_sample, advanced by every baseband_to_passband call) is explicit:
+ * start_sample[i] for frame i (NULL = the value a freshly initialised reference object has, one symbol = 1088 samples).
+ */
+int mercury_b200_get_total_frame_size(const mercury_b200_t *h);
+/* Host-only table construction for one configuration (no device needed): pre_eq 50 complex, preamble preamble_nSymb x 50 complex, 97 + 97 taps. */
+int mercury_b200_build_tx_tables_host(const char *ldpc_table_path, int config, double *pre_eq, double *preamble, double *tx1, double *tx2);
+/* One frame, the reference's own types; *passband_start_sample is advanced like the reference's counter (may be NULL). */
+int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, double *out, uint64_t *passband_start_sample);
+/* n frames: payload n x frame_bytes (zero-padded), passband n x total_frame_size of out_format (MERCURY_B200_SAMPLES_F64 or _F32);
+ * codeword_dbg (optional, host variant): n x 1600 LDPC codeword bits for parity tests. */
+int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n_frames, void *passband,
+				     int out_format, uint8_t *codeword_dbg);
+int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n_frames, void *d_passband,
+					    int out_format, void *stream);
 
 /* Pinned host memory and plain device memory helpers for callers that do not link the CUDA runtime. */
 void *mercury_b200_host_alloc(size_t bytes);

@@ -80,6 +80,11 @@ def lib():
         "mercury_b200_receive_byte": (i32, [vp, vp, vp, C.POINTER(ReceiveStats)]),
         "mercury_b200_receive_byte_batch": (i32, [vp, vp, i32, sz, vp, vp, vp]),
         "mercury_b200_receive_byte_batch_device": (i32, [vp, vp, i32, sz, vp, vp, vp]),
+        "mercury_b200_get_total_frame_size": (i32, [vp]),
+        "mercury_b200_build_tx_tables_host": (i32, [C.c_char_p, i32, vp, vp, vp, vp]),
+        "mercury_b200_transmit_byte": (i32, [vp, vp, i32, vp, vp]),
+        "mercury_b200_transmit_byte_batch": (i32, [vp, vp, vp, sz, vp, i32, vp]),
+        "mercury_b200_transmit_byte_batch_device": (i32, [vp, vp, vp, sz, vp, i32, vp]),
         "mercury_b200_host_alloc": (vp, [sz]),
         "mercury_b200_host_free": (None, [vp]),
         "mercury_b200_device_alloc": (vp, [vp, sz]),

@@ -66,7 +66,27 @@ constexpr int kFeWin = 8 * MB_FE_SYM;        // fine-sync window, (pre + 4) symb
 void fe_free(FeWork &w);
 }  // namespace
 
+namespace {
+// TX chain (mb_tx.cu): per-mode tables built lazily on the first transmit of the mode, plus the batch workspace.
+struct TxWork {
+	bool built[MB_NMODES] = {};
+	MbTxMode mode_host[MB_NMODES];
+	MbTxMode *mode_dev[MB_NMODES] = {};
+	uint8_t *tables[MB_NMODES] = {};
+	size_t cap = 0, cap_total = 0;
+	uint8_t *payload = nullptr, *dbg_cw = nullptr;
+	unsigned long long *start = nullptr;
+	double2 *bb = nullptr;
+	double *pb = nullptr, *p1 = nullptr, *power_part = nullptr;
+	void *out = nullptr;
+	cudaStream_t stream = nullptr;
+	bool init_done = false;
+};
+void tx_free(TxWork &w);
+}  // namespace
+
 struct mercury_b200 {
+	TxWork tx;
 	FeWork fe;
 	MbFeConst fe_const;
 	bool fe_ready = false;
@@ -264,6 +284,7 @@ void mercury_b200_destroy(mercury_b200_t *h)
 	if (h->d_blob) cudaFree(h->d_blob);
 	if (h->h_stage) cudaFreeHost(h->h_stage);
 	fe_free(h->fe);
+	tx_free(h->tx);
 	delete h;
 }
 
@@ -729,6 +750,193 @@ int mercury_b200_receive_byte(mercury_b200_t *h, const double *passband, int *ou
 	if (rc) return rc;
 	const int fb = h->hdr.modes[h->config].frame_bytes;
 	for (int i = 0; i < fb; i++) out[i] = pl[i];  // one int per byte (telecom_system.cc:1329-1332)
+	return MERCURY_B200_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * TX chain (mb_tx.cu): transmit_byte(SINGLE_MESSAGE), batched.
+ * ------------------------------------------------------------------------------------------------------------------- */
+}  // extern "C"
+
+namespace {
+
+void tx_free(TxWork &w)
+{
+	for (int i = 0; i < MB_NMODES; i++) {
+		if (w.mode_dev[i]) cudaFree(w.mode_dev[i]);
+		if (w.tables[i]) cudaFree(w.tables[i]);
+	}
+	void *ptrs[] = {w.payload, w.dbg_cw, w.start, w.bb, w.pb, w.p1, w.power_part, w.out};
+	for (void *p : ptrs)
+		if (p) cudaFree(p);
+	if (w.stream) cudaStreamDestroy(w.stream);
+	w = TxWork();
+}
+
+int tx_total(const MbMode &m) { return (m.Nsymb + m.preamble_nSymb) * MB_FE_SYM; }
+
+int tx_ensure_mode(mercury_b200_t *h)
+{
+	TxWork &w = h->tx;
+	if (!w.init_done) {
+		if (!h->fe_ready) {
+			mb_fe_host_const(&h->fe_const);
+			cudaError_t e = mb_fe_init(h->fe_const);
+			if (e != cudaSuccess) return cuda_fail(h, e, "front-end constants");
+			h->fe_ready = true;
+		}
+		MB_CUDA(h, mb_tx_init());
+		MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+		w.init_done = true;
+	}
+	const int c = h->config;
+	if (w.built[c]) return MERCURY_B200_OK;
+	std::vector<uint8_t> bytes;
+	const std::string e = mb_tx_build(h->blob, c, h->fe_const, &w.mode_host[c], &bytes);
+	if (!e.empty()) return fail(h, MERCURY_B200_EINVAL, e);
+	MB_CUDA(h, cudaMalloc(&w.tables[c], bytes.size()));
+	MB_CUDA(h, cudaMemcpy(w.tables[c], bytes.data(), bytes.size(), cudaMemcpyHostToDevice));
+	MB_CUDA(h, cudaMalloc(&w.mode_dev[c], sizeof(MbTxMode)));
+	MB_CUDA(h, cudaMemcpy(w.mode_dev[c], &w.mode_host[c], sizeof(MbTxMode), cudaMemcpyHostToDevice));
+	w.built[c] = true;
+	return MERCURY_B200_OK;
+}
+
+int tx_ensure_work(mercury_b200_t *h, size_t n, int total, bool want_cw)
+{
+	TxWork &w = h->tx;
+	if (w.cap >= n && w.cap_total >= (size_t)total && (!want_cw || w.dbg_cw)) return MERCURY_B200_OK;
+	MB_CUDA(h, cudaDeviceSynchronize());
+	void **ptrs[] = {(void **)&w.payload, (void **)&w.dbg_cw, (void **)&w.start, (void **)&w.bb, (void **)&w.pb, (void **)&w.p1, (void **)&w.power_part, &w.out};
+	for (void **p : ptrs) {
+		if (*p) cudaFree(*p);
+		*p = nullptr;
+	}
+	const size_t cap = std::max(n, w.cap), tot = std::max((size_t)total, w.cap_total);
+	w.cap = w.cap_total = 0;
+	MB_CUDA(h, cudaMalloc(&w.payload, cap * 256));
+	MB_CUDA(h, cudaMalloc(&w.start, cap * sizeof(unsigned long long)));
+	MB_CUDA(h, cudaMalloc(&w.bb, cap * (tot / 4) * sizeof(double2)));
+	MB_CUDA(h, cudaMalloc(&w.pb, cap * tot * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.p1, cap * tot * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.power_part, cap * ((tot + 255) / 256) * 2 * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.out, cap * tot * sizeof(double)));
+	if (want_cw) MB_CUDA(h, cudaMalloc(&w.dbg_cw, cap * MB_N));
+	w.cap = cap, w.cap_total = tot;
+	return MERCURY_B200_OK;
+}
+
+// d_payload [n][frame_bytes], d_start [n] or NULL, d_out [n][total] (double, or float when out_f32), d_cw optional [n][1600]
+int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long *d_start, size_t n, void *d_out, bool out_f32, uint8_t *d_cw, cudaStream_t s)
+{
+	TxWork &w = h->tx;
+	const int c = h->config;
+	MbTxArgs a;
+	memset(&a, 0, sizeof(a));
+	a.tm = w.mode_dev[c], a.tm_host = &w.mode_host[c], a.tables = w.tables[c];
+	a.payload = d_payload, a.start_sample = d_start, a.n = (int)n, a.out_f32 = out_f32;
+	a.bb = w.bb, a.pb = w.pb, a.p1 = w.p1, a.power_part = w.power_part, a.out = d_out, a.dbg_cw = d_cw;
+	MB_CUDA(h, mb_tx_launch(a, s));
+	h->launches += 4;
+	return MERCURY_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Host-only (no device needed): the TX tables of one configuration, for pinning them against the oracle on a CPU-only machine.
+int mercury_b200_build_tx_tables_host(const char *ldpc_table_path, int config, double *pre_eq /*[100]*/, double *preamble /*[<=400]*/, double *tx1 /*[97]*/,
+				      double *tx2 /*[97]*/)
+{
+	if (!ldpc_table_path || config < 0 || config >= MB_NMODES) return MERCURY_B200_EINVAL;
+	std::vector<uint8_t> blob;
+	if (!mb_build_blob(ldpc_table_path, blob).empty()) return MERCURY_B200_EIO;
+	MbFeConst fe;
+	mb_fe_host_const(&fe);
+	MbTxMode tm;
+	std::vector<uint8_t> bytes;
+	if (!mb_tx_build(blob, config, fe, &tm, &bytes).empty()) return MERCURY_B200_EINVAL;
+	if (pre_eq) memcpy(pre_eq, bytes.data() + tm.off_pre_eq, sizeof(double) * 2 * MB_NC);
+	if (preamble) memcpy(preamble, bytes.data() + tm.off_preamble, sizeof(double) * 2 * MB_NC * tm.pre);
+	if (tx1) memcpy(tx1, bytes.data() + tm.off_c1, sizeof(double) * 97);
+	if (tx2) memcpy(tx2, bytes.data() + tm.off_c2, sizeof(double) * 97);
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_get_total_frame_size(const mercury_b200_t *h)
+{
+	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
+	return tx_total(h->hdr.modes[h->config]);
+}
+
+int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n, void *d_passband, int out_format,
+					    void *stream)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n == 0) return MERCURY_B200_OK;
+	if (!d_payload || !d_passband || (out_format != MERCURY_B200_SAMPLES_F64 && out_format != MERCURY_B200_SAMPLES_F32))
+		return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	rc = tx_ensure_mode(h);
+	if (rc) return rc;
+	const MbMode &m = h->hdr.modes[h->config];
+	const int total = tx_total(m);
+	const size_t chunk = std::min<size_t>(n, 8192), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	rc = tx_ensure_work(h, chunk, total, false);
+	if (rc) return rc;
+	for (size_t done = 0; done < n; done += chunk) {
+		const size_t c = std::min(chunk, n - done);
+		rc = tx_run(h, static_cast<const uint8_t *>(d_payload) + done * m.frame_bytes,
+			    d_start_sample ? static_cast<const unsigned long long *>(d_start_sample) + done : nullptr, c,
+			    static_cast<uint8_t *>(d_passband) + done * total * ob, out_format == MERCURY_B200_SAMPLES_F32, nullptr, static_cast<cudaStream_t>(stream));
+		if (rc) return rc;
+	}
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n, void *passband, int out_format,
+				     uint8_t *codeword_dbg)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n == 0) return MERCURY_B200_OK;
+	if (!payload || !passband || (out_format != MERCURY_B200_SAMPLES_F64 && out_format != MERCURY_B200_SAMPLES_F32))
+		return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	rc = tx_ensure_mode(h);
+	if (rc) return rc;
+	const MbMode &m = h->hdr.modes[h->config];
+	const int total = tx_total(m);
+	const size_t chunk = std::min<size_t>(n, 2048), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	rc = tx_ensure_work(h, chunk, total, codeword_dbg != nullptr);
+	if (rc) return rc;
+	TxWork &w = h->tx;
+	for (size_t done = 0; done < n; done += chunk) {
+		const size_t c = std::min(chunk, n - done);
+		MB_CUDA(h, cudaMemcpyAsync(w.payload, payload + done * m.frame_bytes, c * m.frame_bytes, cudaMemcpyHostToDevice, w.stream));
+		if (start_sample) MB_CUDA(h, cudaMemcpyAsync(w.start, start_sample + done, c * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream));
+		rc = tx_run(h, w.payload, start_sample ? w.start : nullptr, c, w.out, out_format == MERCURY_B200_SAMPLES_F32, codeword_dbg ? w.dbg_cw : nullptr, w.stream);
+		if (rc) return rc;
+		MB_CUDA(h, cudaMemcpyAsync(static_cast<uint8_t *>(passband) + done * total * ob, w.out, c * total * ob, cudaMemcpyDeviceToHost, w.stream));
+		if (codeword_dbg) MB_CUDA(h, cudaMemcpyAsync(codeword_dbg + done * MB_N, w.dbg_cw, c * MB_N, cudaMemcpyDeviceToHost, w.stream));
+		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+	}
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, double *out, uint64_t *passband_start_sample)
+{
+	if (!h || !data || !out) return MERCURY_B200_EINVAL;
+	int rc = check_ready(h);
+	if (rc) return rc;
+	const MbMode &m = h->hdr.modes[h->config];
+	if (nBytes < 0 || nBytes > m.frame_bytes) return fail(h, MERCURY_B200_EINVAL, "message too long.. not sent.");  // telecom_system.cc:348-352
+	uint8_t pl[256] = {0};
+	for (int i = 0; i < nBytes; i++) pl[i] = (uint8_t)data[i];
+	uint64_t start = passband_start_sample ? *passband_start_sample : (uint64_t)MB_FE_SYM;
+	rc = mercury_b200_transmit_byte_batch(h, pl, &start, 1, out, MERCURY_B200_SAMPLES_F64, nullptr);
+	if (rc) return rc;
+	if (passband_start_sample) *passband_start_sample = start + (uint64_t)tx_total(m);  // ofdm.cc:2313
 	return MERCURY_B200_OK;
 }
 

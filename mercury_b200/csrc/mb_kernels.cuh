@@ -126,3 +126,42 @@ cudaError_t mb_fe_init(const MbFeConst &k);
 cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s);
 cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s);  // [k_fe_window, k_fe_sc,] k_fe_decide
 cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TX chain (mb_tx.cu): payload bytes -> pass-band frames, transmit_byte(SINGLE_MESSAGE).
+// ---------------------------------------------------------------------------------------------------------------------
+struct MbTxMode {
+	int32_t S, pre, nData, nPilots, nBits, nReal, nVirtual, K, P, bps, M, frame_bytes;
+	double fc, Ts, amp, scale_data, scale_pre, papr_pre_lin, papr_data_lin;
+	unsigned long long start_after_init;  // ofdm.passband_start_sample right after init (one symbol: telecom_system.cc:3125-3126)
+	// byte offsets into the mode's TX table buffer
+	uint32_t off_bit_src;   // u16[nBits]   codeword position of mapped bit i (bit interleave o parity compaction, inverted)
+	uint32_t off_sym_cell;  // u16[nData]   grid cell of data symbol q (T/F interleave o framer)
+	uint32_t off_scr;       // u8 [1600]    bit_energy_dispersal sequence
+	uint32_t off_row_off;   // u16[P + 1]   CSR of the data variables of each check row (reference check order)
+	uint32_t off_row_var;   // u16[...]
+	uint32_t off_pilot;     // f64[S * 50]  pilot value at pilot cells, 0 at data cells
+	uint32_t off_cons;      // c128[M]
+	uint32_t off_preamble;  // c128[pre * 50]
+	uint32_t off_pre_eq;    // c128[50]     pre_equalization_channel
+	uint32_t off_c1, off_c2;  // f64[97]    FIR_tx1, FIR_tx2
+	uint32_t pad;
+};
+
+struct MbTxArgs {
+	const MbTxMode *tm;        // device copy
+	const MbTxMode *tm_host;
+	const uint8_t *tables;     // device: the mode's TX table buffer
+	const uint8_t *payload;    // [n][frame_bytes] zero-padded payloads
+	const unsigned long long *start_sample;  // [n] running carrier sample counter per frame, or NULL (= start_after_init)
+	int32_t n, out_f32;
+	double2 *bb;               // [n][(pre + S) * 272] scaled base-band symbols
+	double *pb, *p1;           // [n][total] pass-band before / after FIR_tx1
+	double *power_part;        // [n][ceil(total / 256)][2]
+	void *out;                 // [n][total] double or float
+	uint8_t *dbg_cw;           // optional [n][1600] codewords (parity tests)
+};
+
+std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
+cudaError_t mb_tx_init();
+cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);

@@ -164,6 +164,34 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_receive_byte_batch_device(self._h, _vp(d_captures), int(sample_format), int(n), _vp(d_payload),
                                                                    _vp(d_stats), C.c_void_p(stream)))
 
+    # ---- TX chain --------------------------------------------------------------------
+    def get_total_frame_size(self):
+        """Pass-band samples of one transmitted frame: (preamble_nSymb + Nsymb) * Nofdm * 4 (data_container.total_frame_size)."""
+        return self._L.mercury_b200_get_total_frame_size(self._h)
+
+    def transmit_byte(self, data, passband_start_sample=None):
+        """void cl_telecom_system::transmit_byte(int* data, int nBytes, double* out, SINGLE_MESSAGE) (telecom_system.cc:342-553).
+        Returns (out float64[total_frame_size], counter after); passband_start_sample=None = a freshly initialised reference object."""
+        d = np.asarray(list(data), np.int32)
+        out = np.zeros(self.get_total_frame_size(), np.float64)
+        st = np.array([1088 if passband_start_sample is None else int(passband_start_sample)], np.uint64)
+        self._check(self._L.mercury_b200_transmit_byte(self._h, _vp(d), int(d.size), _vp(out), _vp(st)))
+        return out, int(st[0])
+
+    def transmit_byte_batch(self, payload, start_sample=None, dtype=np.float64, want_codeword=False):
+        """payload [n, frame_bytes] uint8 -> pass-band frames [n, total_frame_size] (float64 or float32) [, codewords [n, 1600] u8]."""
+        pl = np.ascontiguousarray(payload, np.uint8).reshape(-1, self.geometry["frame_bytes"])
+        n = pl.shape[0]
+        out = np.zeros((n, self.get_total_frame_size()), dtype)
+        st = None if start_sample is None else np.ascontiguousarray(start_sample, np.uint64)
+        cw = np.zeros((n, self.geometry["N"]), np.uint8) if want_codeword else None
+        self._check(self._L.mercury_b200_transmit_byte_batch(self._h, _vp(pl), _vp(st), n, _vp(out), _SAMPLE_FORMATS[np.dtype(dtype)], _vp(cw)))
+        return (out, cw) if want_codeword else out
+
+    def transmit_byte_batch_device(self, d_payload, d_start_sample, n, d_passband, out_format, stream=0):
+        self._check(self._L.mercury_b200_transmit_byte_batch_device(self._h, _vp(d_payload), _vp(d_start_sample), int(n), _vp(d_passband),
+                                                                    int(out_format), C.c_void_p(stream)))
+
     # ---- batched entry points ----------------------------------------------------------------------------
     def demod_decode_batch(self, baseband, want_llr=False, out=None):
         """Host buffers: baseband [B, Nsymb, 272] complex64 (or float32 [..., 2]). Returns (payload[B,frame_bytes] u8, stats[B], llr_cw|None)."""

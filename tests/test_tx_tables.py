@@ -1,0 +1,25 @@
+"""The product's host-built TX tables (csrc/mb_tx.cu: preamble, pre-equalisation channel, transmit FIR designs) against the oracle,
+on the CPU.  FIRs and preamble are bit-exact; the pre-equalisation channel goes through 1000 symbols of TX filters -> RX filter ->
+DFT with a different (direct) transform, so it is compared to 1e-12."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from mercury_b200 import _lib
+from oracle import port
+
+
+@pytest.mark.parametrize("cfg", [0, 8, 10, 13, 16])
+def test_tx_tables_match_the_oracle(cfg):
+    L = _lib.lib()
+    p = port.Port(cfg, 50)
+    t = p.tx_tables()
+    pre_eq = np.zeros(50, np.complex128)
+    preamble = np.zeros(4 * 50, np.complex128)
+    c1, c2 = np.zeros(97), np.zeros(97)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.mercury_b200_build_tx_tables_host(_lib.LDPC_TABLES.encode(), cfg, vp(pre_eq), vp(preamble), vp(c1), vp(c2)) == 0
+    assert np.array_equal(c1, t["tx1"]) and np.array_equal(c2, t["tx2"])
+    assert np.array_equal(preamble[:p.preamble_nSymb * 50], t["preamble"])
+    assert np.abs(pre_eq - t["pre_eq"]).max() <= 1e-12 * np.abs(t["pre_eq"]).max()
