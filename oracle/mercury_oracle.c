@@ -258,8 +258,59 @@ static int load_ldpc(mo_mode *m, const char *path)
 }
 
 /* cl_telecom_system::load_configuration(int) + init(): source/physical_layer/telecom_system.cc:2487-3025, 1804-1982. */
+/* cl_mfsk::init: source/physical_layer/mfsk.cc:49-160 (tone plan, hop step, preamble / ACK / BREAK tone sequences). */
+static void mfsk_init(mo_mfsk *f, int M, int Nc, int nStreams)
+{
+	static const int pre32[4] = {4, 20, 12, 28}, pre16[4] = {2, 10, 6, 14};
+	static const int ack32[8] = {8, 14, 10, 24, 26, 2, 18, 30}, ack16[8] = {4, 7, 5, 12, 13, 1, 9, 15};
+	static const int brk32[8] = {12, 28, 4, 6, 20, 16, 22, 30}, brk16[8] = {6, 14, 2, 3, 10, 8, 11, 15};
+	f->M = M, f->Nc = Nc, f->nStreams = nStreams;
+	f->nBits = 0;
+	for (int t = M; t > 1; t >>= 1) f->nBits++;
+	f->tone_hop_step = M == 32 ? 13 : (M == 16 ? 7 : 1);
+	int global_offset = (Nc - nStreams * M) / 2;
+	if (global_offset < 0) global_offset = 0;
+	for (int k = 0; k < nStreams; k++) f->stream_offsets[k] = global_offset + k * M;
+	f->preamble_nSymb = 4;
+	for (int i = 0; i < 4; i++) f->preamble_tones[i] = M == 32 ? pre32[i] : pre16[i];
+	for (int i = 0; i < 8; i++) f->ack_tones[i] = M == 32 ? ack32[i] : ack16[i];
+	for (int i = 0; i < 8; i++) f->break_tones[i] = M == 32 ? brk32[i] : brk16[i];
+}
+
+/* ROBUST_0..2 (common_defines.h:63-65, telecom_system.cc:2625-2645,2694-2700,1812-1817): MFSK modes, Nsymb = N / (nBits * nStreams). */
+static int mo_mode_init_mfsk(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_path)
+{
+	memset(m, 0, sizeof(*m));
+	m->config = config;
+	m->M = 200; /* MOD_MFSK */
+	m->rate_num = config == 102 ? 4 : 1;
+	m->preamble_nSymb = 4;
+	m->estimator = 1;
+	mfsk_init(&m->mfsk, config == 100 ? 32 : 16, MO_NC, config == 100 ? 1 : 2);
+	m->bits_per_symbol = m->mfsk.nBits * m->mfsk.nStreams;
+	m->Nsymb = MO_N / m->bits_per_symbol;
+	m->Nc = MO_NC, m->Nfft = MO_NFFT, m->Ngi = MO_NGI, m->Nofdm = MO_NOFDM;
+	m->boost = (double)1.33f;
+	m->ls_window = 21;
+	m->ldpc_iters = ldpc_iters;
+	m->N = MO_N;
+	m->K = (int)((float)m->N * ((float)m->rate_num / 16.0f));
+	m->P = m->N - m->K;
+	m->nData = m->Nsymb, m->nPilots = 0;
+	m->nBits = m->nData * m->bits_per_symbol;
+	m->nReal = m->nBits - m->P, m->nVirtual = m->N - m->nBits;
+	m->frame_bytes = (m->nReal - 16) / 8;
+	m->bit_il_block = m->nBits / 10, m->tf_il_block = m->nData / 10;
+	build_fft_tables(m);
+	mo_srandom(0);
+	for (int i = 0; i < m->N; i++) m->scrambler[i] = mo_random() % 2;
+	mo_frontend_init(m);
+	return load_ldpc(m, ldpc_blob_path);
+}
+
 int mo_mode_init(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_path)
 {
+	if (config >= 100 && config <= 102) return mo_mode_init_mfsk(m, config, ldpc_iters, ldpc_blob_path);
 	if (config < 0 || config > 16) return -1;
 	memset(m, 0, sizeof(*m));
 	m->config = config;
@@ -470,6 +521,25 @@ void mo_tx_baseband(const mo_mode *m, const int *payload, int nBytes, double com
 	if (codeword) memcpy(codeword, enc, sizeof(int) * m->N);
 	for (int i = 0; i < m->P; i++) enc[m->nReal + i] = enc[i + m->K];
 	for (int i = 0; i < m->nBits; i++) il[il_src(i, m->nBits, m->bit_il_block)] = enc[i];
+	if (m->M == 200) { /* cl_mfsk::mod, mfsk.cc:254-303: Gray-mapped one-hot tones with hopping, no pilots, no T/F interleaver */
+		const mo_mfsk *f = &m->mfsk;
+		double complex *fr = calloc((size_t)m->Nsymb * MO_NC, sizeof(double complex));
+		double amp = sqrt((double)MO_NC / f->nStreams);
+		for (int s = 0; s < m->Nsymb; s++)
+			for (int st = 0; st < f->nStreams; st++) {
+				int off = s * m->bits_per_symbol + st * f->nBits, tone = 0;
+				for (int bb = 0; bb < f->nBits; bb++)
+					if (il[off + bb]) tone |= (1 << (f->nBits - 1 - bb));
+				int bin = tone;
+				for (int sh = 1; sh < f->nBits; sh++) bin ^= (tone >> sh);
+				if (bin >= f->M) bin = f->M - 1;
+				fr[s * MO_NC + f->stream_offsets[st] + (bin + s * f->tone_hop_step) % f->M] = amp;
+			}
+		if (framed_out) memcpy(framed_out, fr, sizeof(double complex) * m->Nsymb * MO_NC);
+		for (int s = 0; s < m->Nsymb; s++) symbol_mod(m, fr + s * MO_NC, out + s * m->Nofdm);
+		free(fr);
+		return;
+	}
 	int b = m->bits_per_symbol;
 	for (int i = 0; i < m->nBits; i += b) {
 		unsigned loc = 0;
@@ -614,8 +684,105 @@ int mo_ldpc_decode(const mo_mode *m, const float *LLRi, int *LLRo)
 }
 
 /* The RX tail: source/physical_layer/telecom_system.cc:1132-1341 (+ success bookkeeping :1343-1375). */
+/* cl_mfsk::demod: mfsk.cc:305-390 (per symbol: noise variance from the carriers outside the tone bands, per stream the hop-reversed
+ * tone energies, max-log LLR over the Gray-mapped tones scaled by 1/(2 sigma^2), clamped to +-5). */
+static void mfsk_demod(const mo_mfsk *f, const double complex *fft_in, int total_bits, float *llr_out)
+{
+	int bps = f->nBits * f->nStreams, nSymbols = total_bits / bps;
+	for (int s = 0; s < nSymbols; s++) {
+		int band_start = f->stream_offsets[0], band_end = f->stream_offsets[f->nStreams - 1] + f->M;
+		double noise_sum = 0.0;
+		int noise_bins = 0;
+		for (int k = 0; k < f->Nc; k++)
+			if (k < band_start || k >= band_end) {
+				double complex v = fft_in[s * f->Nc + k];
+				double e = creal(v) * creal(v) + cimag(v) * cimag(v);
+				if (isfinite(e)) {
+					noise_sum += e;
+					noise_bins++;
+				}
+			}
+		double noise_var = (noise_bins > 0) ? noise_sum / noise_bins : 1e-30;
+		if (noise_var < 1e-30) noise_var = 1e-30;
+		double llr_scale = 1.0 / (2.0 * noise_var);
+		for (int st = 0; st < f->nStreams; st++) {
+			double E_raw[64], E[64];
+			for (int q = 0; q < f->M; q++) {
+				double complex v = fft_in[s * f->Nc + f->stream_offsets[st] + q];
+				E_raw[q] = creal(v) * creal(v) + cimag(v) * cimag(v);
+				if (!isfinite(E_raw[q])) E_raw[q] = 0.0;
+			}
+			int hop = (s * f->tone_hop_step) % f->M;
+			for (int q = 0; q < f->M; q++) E[q] = E_raw[(q + hop) % f->M];
+			int off = s * bps + st * f->nBits;
+			for (int k = 0; k < f->nBits; k++) {
+				int mask = 1 << (f->nBits - 1 - k);
+				double max_E1 = -1e30, max_E0 = -1e30;
+				for (int q = 0; q < f->M; q++) {
+					int gray = q ^ (q >> 1);
+					if (gray & mask) {
+						if (E[q] > max_E1) max_E1 = E[q];
+					} else if (E[q] > max_E0)
+						max_E0 = E[q];
+				}
+				double llr = (max_E0 - max_E1) * llr_scale;
+				if (!isfinite(llr)) llr = 0.0;
+				else if (llr > 5.0) llr = 5.0;
+				else if (llr < -5.0) llr = -5.0;
+				llr_out[off + k] = (float)llr;
+			}
+		}
+	}
+}
+
+/* The MFSK branch of the RX tail: telecom_system.cc:1132-1198 then the common :1296-1367 (no AGC, no channel estimate, no gate; SNR 0). */
+static void mo_rx_tail_mfsk(const mo_mode *m, const double complex *bb, mo_rx_out *o)
+{
+	int S = m->Nsymb, cells = S * MO_NC;
+	double complex *Y = malloc(sizeof(double complex) * cells);
+	float llr[MO_N], llr_cw[MO_N + 8];
+	int bits[MO_N], bytes[MO_N / 8 + 1];
+	for (int s = 0; s < S; s++) symbol_demod(m, bb + (size_t)s * m->Nofdm, Y + s * MO_NC);
+	if (o->Y) memcpy(o->Y, Y, sizeof(double complex) * cells);
+	mfsk_demod(&m->mfsk, Y, m->nBits, llr);
+	free(Y);
+	if (o->llr_demod) memcpy(o->llr_demod, llr, sizeof(float) * m->nBits);
+	int bs = m->bit_il_block, nb = m->nBits / bs;
+	for (int i = 0; i < nb; i++)
+		for (int j = 0; j < bs; j++) llr_cw[i * bs + j] = llr[j * nb + i];
+	for (int i = nb * bs; i < m->nBits; i++) llr_cw[i] = llr[i];
+	for (int i = m->P - 1; i >= 0; i--) llr_cw[i + m->nReal + m->nVirtual] = llr_cw[i + m->nReal];
+	for (int i = 0; i < m->nVirtual; i++) llr_cw[m->nReal + i] = llr_cw[i];
+	if (o->llr_cw) memcpy(o->llr_cw, llr_cw, sizeof(float) * m->N);
+	int iterations = mo_ldpc_decode(m, llr_cw, bits);
+	if (o->bits) memcpy(o->bits, bits, sizeof(int) * m->K);
+	for (int i = 0; i < m->nReal; i++) bits[i] ^= m->scrambler[i];
+	for (int i = 0; i < m->nReal / 8; i++) {
+		bytes[i] = 0;
+		for (int j = 0; j < 8; j++) bytes[i] |= bits[i * 8 + j] << j;
+	}
+	int all_zeros = 1;
+	for (int i = 0; i < m->nReal / 8; i++)
+		if (bytes[i] != 0) {
+			all_zeros = 0;
+			break;
+		}
+	if (o->bytes) memcpy(o->bytes, bytes, sizeof(int) * (m->nReal / 8));
+	if (o->payload) memcpy(o->payload, bytes, sizeof(int) * m->frame_bytes);
+	int crc = all_zeros ? 0 : mo_crc16(bytes, m->nReal / 8);
+	int decoded = !(all_zeros || crc != 0);
+	if (o->stats) {
+		o->stats[0] = iterations, o->stats[1] = crc, o->stats[2] = all_zeros, o->stats[3] = decoded;
+		o->stats[4] = decoded ? 0.0 : -99.9, o->stats[5] = 0, o->stats[6] = 0, o->stats[7] = 1.0;
+	}
+}
+
 void mo_rx_tail(const mo_mode *m, const double complex *bb, mo_rx_out *o)
 {
+	if (m->M == 200) {
+		mo_rx_tail_mfsk(m, bb, o);
+		return;
+	}
 	int S = m->Nsymb, C = m->Nc, cells = S * C;
 	double complex Y[MO_MAX_CELLS], H[MO_MAX_CELLS], Hna[MO_MAX_CELLS], Z[MO_MAX_CELLS], Zna[MO_MAX_CELLS];
 	unsigned char st[MO_MAX_CELLS];
@@ -1444,4 +1611,134 @@ int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, do
 	*start_sample_inout = (double)start;
 	free(bbp), free(bbd), free(pb), free(p1);
 	return total;
+}
+
+
+/* ================================================================================================
+ * MFSK pattern functions on a pass-band-rate base-band buffer.
+ * ============================================================================================== */
+static int carrier_to_bin(int sub) { return sub < MO_NC / 2 ? MO_NFFT - MO_NC / 2 + sub : 1 + (sub - MO_NC / 2); }
+
+/* energies of the 50 active carriers of the symbol starting at sample `offset` (every 4th sample, 256-point FFT scaled 1/N:
+ * the loop bodies of ofdm.cc:2013-2021 / 2104-2112) */
+static void symbol_energies(const mo_mode *m, const double complex *bbi, int offset, int rate, double complex *fft_out)
+{
+	for (int i = 0; i < MO_NFFT; i++) fft_out[i] = bbi[offset + i * rate];
+	fft_core(m, fft_out, 0);
+	for (int i = 0; i < MO_NFFT; i++) fft_out[i] = fft_out[i] / (double)MO_NFFT;
+}
+
+/* cl_ofdm::time_sync_mfsk: ofdm.cc:1969-2065. */
+int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int search_start_symb)
+{
+	const mo_mfsk *f = &m->mfsk;
+	int rate = m->fe.interp, sym = MO_NOFDM * rate, buffer_nsymb = n / sym, pre = m->preamble_nSymb;
+	int bins[8][4];
+	for (int p = 0; p < pre; p++)
+		for (int st = 0; st < f->nStreams; st++) bins[p][st] = carrier_to_bin(f->stream_offsets[st] + f->preamble_tones[p % pre]);
+	double best_metric = -1;
+	int best = 0;
+	double complex fo[MO_NFFT];
+	for (int s = search_start_symb > 0 ? search_start_symb : 0; s <= buffer_nsymb - pre; s++) {
+		double metric = 0;
+		for (int p = 0; p < pre; p++) {
+			int offset = (s + p) * sym + MO_NGI * rate;
+			if (offset + MO_NFFT * rate > n) break;
+			symbol_energies(m, bbi, offset, rate, fo);
+			double e_target = 0, e_total = 0;
+			for (int st = 0; st < f->nStreams; st++) {
+				int b = bins[p][st];
+				e_target += creal(fo[b]) * creal(fo[b]) + cimag(fo[b]) * cimag(fo[b]);
+			}
+			for (int k = 0; k < MO_NC; k++) {
+				int b = carrier_to_bin(k);
+				double e = creal(fo[b]) * creal(fo[b]) + cimag(fo[b]) * cimag(fo[b]);
+				e_total += e;
+			}
+			if (e_total > 0) metric += e_target / e_total;
+		}
+		if (metric > best_metric) {
+			best_metric = metric;
+			best = s;
+		}
+	}
+	return best * sym;
+}
+
+/* cl_ofdm::detect_ack_pattern: ofdm.cc:2067-2186, with the ACK or the BREAK tone sequence (mfsk.cc:113-160). */
+double mo_detect_ack_pattern(const mo_mode *m, const double complex *bbi, int n, int use_break_tones, int *matched_out)
+{
+	const mo_mfsk *f = &m->mfsk;
+	const int *tones = use_break_tones ? f->break_tones : f->ack_tones;
+	int rate = m->fe.interp, sym = MO_NOFDM * rate, buffer_nsymb = n / sym, ack_nsymb = 16;
+	if (matched_out) *matched_out = 0;
+	if (buffer_nsymb < ack_nsymb) return 0.0;
+	double best_metric = 0.0;
+	int best_matched = 0;
+	double complex fo[MO_NFFT];
+	for (int s = 0; s <= buffer_nsymb - ack_nsymb; s++) {
+		double metric = 0;
+		int matched = 0;
+		for (int p = 0; p < ack_nsymb; p++) {
+			int offset = (s + p) * sym + MO_NGI * rate;
+			if (offset + MO_NFFT * rate > n) break;
+			symbol_energies(m, bbi, offset, rate, fo);
+			int actual_tone = (tones[p % 8] + p * f->tone_hop_step) % f->M;
+			int any_peak = 0;
+			double e_target = 0;
+			for (int st = 0; st < f->nStreams; st++) {
+				int eb = carrier_to_bin(f->stream_offsets[st] + actual_tone);
+				double e_exp = creal(fo[eb]) * creal(fo[eb]) + cimag(fo[eb]) * cimag(fo[eb]);
+				e_target += e_exp;
+				double peak = -1.0;
+				for (int t = 0; t < f->M; t++) {
+					int b = carrier_to_bin(f->stream_offsets[st] + t);
+					double e = creal(fo[b]) * creal(fo[b]) + cimag(fo[b]) * cimag(fo[b]);
+					if (e > peak) peak = e;
+				}
+				if (e_exp >= peak) any_peak = 1;
+			}
+			if (!any_peak) continue;
+			matched++;
+			double e_total = 0;
+			for (int k = 0; k < MO_NC; k++) {
+				int b = carrier_to_bin(k);
+				double e = creal(fo[b]) * creal(fo[b]) + cimag(fo[b]) * cimag(fo[b]);
+				e_total += e;
+			}
+			if (e_total > 0) metric += e_target / e_total;
+		}
+		if (metric > best_metric) {
+			best_metric = metric;
+			best_matched = matched;
+		}
+	}
+	if (matched_out) *matched_out = best_matched;
+	return best_metric;
+}
+
+/* cl_mfsk::generate_ack_pattern / generate_break_pattern (mfsk.cc:197-252) + symbol_mod: 16 symbols of base-band. */
+void mo_ack_pattern_baseband(const mo_mode *m, int use_break_tones, double complex *out)
+{
+	const mo_mfsk *f = &m->mfsk;
+	const int *tones = use_break_tones ? f->break_tones : f->ack_tones;
+	double amp = sqrt((double)MO_NC / f->nStreams);
+	for (int s = 0; s < 16; s++) {
+		double complex pat[MO_NC];
+		for (int k = 0; k < MO_NC; k++) pat[k] = 0;
+		int actual = (tones[s % 8] + s * f->tone_hop_step) % f->M;
+		for (int st = 0; st < f->nStreams; st++) pat[f->stream_offsets[st] + actual] = amp;
+		symbol_mod(m, pat, out + s * MO_NOFDM);
+	}
+}
+
+void mo_mfsk_tables(const mo_mode *m, int *out)
+{
+	const mo_mfsk *f = &m->mfsk;
+	int k = 0;
+	out[k++] = f->M, out[k++] = f->nBits, out[k++] = f->nStreams, out[k++] = f->tone_hop_step;
+	for (int i = 0; i < 4; i++) out[k++] = f->stream_offsets[i];
+	for (int i = 0; i < 4; i++) out[k++] = f->preamble_tones[i];
+	for (int i = 0; i < 8; i++) out[k++] = f->ack_tones[i];
+	for (int i = 0; i < 8; i++) out[k++] = f->break_tones[i];
 }

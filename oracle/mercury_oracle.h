@@ -33,6 +33,12 @@ typedef struct mo_frontend {
 	double c_ts[64], c_data[64];
 } mo_frontend;
 
+/* MFSK tone plan of the ROBUST modes (cl_mfsk, include/physical_layer/mfsk.h). */
+typedef struct mo_mfsk {
+	int M, nBits, Nc, nStreams, tone_hop_step, preamble_nSymb;
+	int stream_offsets[4], preamble_tones[8], ack_tones[8], break_tones[8];
+} mo_mfsk;
+
 /* TX-side tables, built lazily by mo_tx_init(). */
 typedef struct mo_tx {
 	int ready, ntaps1, ntaps2;
@@ -65,6 +71,7 @@ typedef struct mo_mode {
 	int bitrev[MO_NFFT];
 	mo_frontend fe;
 	mo_tx tx;
+	mo_mfsk mfsk; /* ROBUST_0..2 (config 100..102, M == 200) only */
 } mo_mode;
 
 typedef struct mo_rx_out {
@@ -107,6 +114,11 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 void mo_tx_init(mo_mode *m);
 void mo_tx_tables(mo_mode *m, double complex *preamble, int *preamble_type, double complex *pre_eq, int *ntaps, double *c1, double *c2, double *consts);
 int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout);
+/* MFSK pattern functions: bbi = n complex samples at the pass-band rate. */
+int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int search_start_symb);
+double mo_detect_ack_pattern(const mo_mode *m, const double complex *bbi, int n, int use_break_tones, int *matched_out);
+void mo_ack_pattern_baseband(const mo_mode *m, int use_break_tones, double complex *out /*[16 * 272]*/);
+void mo_mfsk_tables(const mo_mode *m, int *out /*[32]*/);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

@@ -51,6 +51,12 @@ def lib():
         L.mo_receive_byte_timed.restype = C.c_double
         L.mo_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.mo_tx_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.mo_time_sync_mfsk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.mo_time_sync_mfsk.restype = C.c_int
+        L.mo_detect_ack_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.mo_detect_ack_pattern.restype = C.c_double
+        L.mo_ack_pattern_baseband.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mo_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mo_transmit_byte.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mo_transmit_byte.restype = C.c_int
         _lib = L

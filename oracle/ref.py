@@ -67,6 +67,12 @@ def lib():
         L.mref_receive_byte_timed.restype = C.c_double
         L.mref_frontend_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.mref_tx_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.mref_time_sync_mfsk.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.mref_time_sync_mfsk.restype = C.c_int
+        L.mref_detect_ack_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.mref_detect_ack_pattern.restype = C.c_double
+        L.mref_ack_pattern_baseband.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mref_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mref_transmit_byte2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_transmit_byte2.restype = C.c_int
         _lib = L
@@ -158,6 +164,28 @@ class FrontEndMixin:
         name = "mref_transmit_byte2" if self._fe == "mref_" else "mo_transmit_byte"
         n = getattr(self._felib(), name)(self.h, _p(pl), len(pl), _p(out), _p(st))
         return out[:n], int(st[0])
+
+    # ---- MFSK pattern functions (row 3): bbi = complex128 buffer at the pass-band rate --------------------------------
+    def time_sync_mfsk(self, bbi, search_start_symb=0):
+        b = np.ascontiguousarray(bbi, np.complex128)
+        return int(getattr(self._felib(), self._fe + "time_sync_mfsk")(self.h, _p(b), b.size, int(search_start_symb)))
+
+    def detect_ack_pattern(self, bbi, use_break_tones=False):
+        b = np.ascontiguousarray(bbi, np.complex128)
+        m = np.zeros(1, np.int32)
+        v = getattr(self._felib(), self._fe + "detect_ack_pattern")(self.h, _p(b), b.size, int(use_break_tones), _p(m))
+        return float(v), int(m[0])
+
+    def ack_pattern_baseband(self, use_break_tones=False):
+        out = np.zeros(16 * self.Nofdm, np.complex128)
+        getattr(self._felib(), self._fe + "ack_pattern_baseband")(self.h, int(use_break_tones), _p(out))
+        return out
+
+    def mfsk_tables(self):
+        t = np.zeros(32, np.int32)
+        getattr(self._felib(), self._fe + "mfsk_tables")(self.h, _p(t))
+        return dict(M=int(t[0]), nBits=int(t[1]), nStreams=int(t[2]), tone_hop_step=int(t[3]), stream_offsets=t[4:8].copy(),
+                    preamble_tones=t[8:12].copy(), ack_tones=t[12:20].copy(), break_tones=t[20:28].copy())
 
     def frontend_tables(self):
         nt = np.zeros(2, np.int32)

@@ -234,9 +234,13 @@ void mref_tx_baseband(void *h, const int *payload, int nBytes, double *out_cplx,
 	if (codeword) memcpy(codeword, dc.encoded_data, sizeof(int) * ts.ldpc.N);
 	for (int i = 0; i < ts.ldpc.P; i++) dc.encoded_data[nReal + i] = dc.encoded_data[i + ts.ldpc.K];
 	interleaver(dc.encoded_data, dc.bit_interleaved_data, dc.nBits, ts.bit_interleaver_block_size);
-	ts.psk.mod(dc.bit_interleaved_data, dc.nBits, dc.modulated_data);
-	interleaver(dc.modulated_data, dc.ofdm_time_freq_interleaved_data, dc.nData, ts.time_freq_interleaver_block_size);
-	ts.ofdm.framer(dc.ofdm_time_freq_interleaved_data, dc.ofdm_framed_data);
+	if (ts.M == MOD_MFSK) {
+		ts.mfsk.mod(dc.bit_interleaved_data, dc.nBits, dc.ofdm_framed_data); /* telecom_system.cc:411-416: one-hot tones, no framer */
+	} else {
+		ts.psk.mod(dc.bit_interleaved_data, dc.nBits, dc.modulated_data);
+		interleaver(dc.modulated_data, dc.ofdm_time_freq_interleaved_data, dc.nData, ts.time_freq_interleaver_block_size);
+		ts.ofdm.framer(dc.ofdm_time_freq_interleaved_data, dc.ofdm_framed_data);
+	}
 	if (framed) memcpy(framed, dc.ofdm_framed_data, sizeof(double) * 2 * dc.Nsymb * dc.Nc);
 	for (int i = 0; i < dc.Nsymb; i++)
 		ts.ofdm.symbol_mod(&dc.ofdm_framed_data[i * dc.Nc], &dc.ofdm_symbol_modulated_data[i * dc.Nofdm]);
@@ -278,6 +282,38 @@ void mref_rx_tail(void *h, const double *baseband, mref_rx_out *o)
 		ofdm.symbol_demod(sym, &dc.ofdm_symbol_demodulated_data[i * dc.Nc]);
 	}
 	delete[] sym;
+	if (ts.M == MOD_MFSK) {
+		/* MFSK branch of the tail (telecom_system.cc:1142-1198): non-coherent energy detection, no AGC / channel estimate / gate */
+		if (o->Y) memcpy(o->Y, dc.ofdm_symbol_demodulated_data, sizeof(double) * 2 * cells);
+		ts.mfsk.demod(dc.ofdm_symbol_demodulated_data, dc.nBits, dc.demodulated_data);
+		if (o->llr_demod) memcpy(o->llr_demod, dc.demodulated_data, sizeof(float) * dc.nBits);
+		deinterleaver(dc.demodulated_data, dc.deinterleaved_data, dc.nBits, ts.bit_interleaver_block_size);
+		for (int i = ts.ldpc.P - 1; i >= 0; i--) dc.deinterleaved_data[i + nReal + nVirtual] = dc.deinterleaved_data[i + nReal];
+		for (int i = 0; i < nVirtual; i++) dc.deinterleaved_data[nReal + i] = dc.deinterleaved_data[i];
+		if (o->llr_cw) memcpy(o->llr_cw, dc.deinterleaved_data, sizeof(float) * ts.ldpc.N);
+		int iterations = ts.ldpc.decode(dc.deinterleaved_data, dc.hd_decoded_data_bit);
+		if (o->bits) memcpy(o->bits, dc.hd_decoded_data_bit, sizeof(int) * ts.ldpc.K);
+		bit_energy_dispersal(dc.hd_decoded_data_bit, dc.bit_energy_dispersal_sequence, dc.hd_decoded_data_bit, nReal);
+		bit_to_byte(dc.hd_decoded_data_bit, dc.hd_decoded_data_byte, nReal);
+		int all_zeros = YES;
+		for (int i = 0; i < nReal / 8; i++)
+			if (dc.hd_decoded_data_byte[i] != 0) {
+				all_zeros = NO;
+				break;
+			}
+		if (o->bytes) memcpy(o->bytes, dc.hd_decoded_data_byte, sizeof(int) * (nReal / 8));
+		if (o->payload)
+			for (int i = 0; i < (nReal - ts.outer_code_reserved_bits) / 8; i++) o->payload[i] = dc.hd_decoded_data_byte[i];
+		int crc = 0;
+		if (ts.outer_code == CRC16_MODBUS_RTU && all_zeros == NO) crc = CRC16_MODBUS_RTU_calc(dc.hd_decoded_data_byte, nReal / 8);
+		int decoded = !(all_zeros == YES || crc != 0);
+		if (o->stats) {
+			o->stats[0] = iterations, o->stats[1] = crc, o->stats[2] = all_zeros, o->stats[3] = decoded;
+			o->stats[4] = decoded ? 0.0 : -99.9; /* :1362-1367: MFSK reports SNR 0 */
+			o->stats[5] = 0, o->stats[6] = 0, o->stats[7] = 1.0;
+		}
+		return;
+	}
 	ofdm.automatic_gain_control(dc.ofdm_symbol_demodulated_data);
 	if (o->Y) memcpy(o->Y, dc.ofdm_symbol_demodulated_data, sizeof(double) * 2 * cells);
 
@@ -590,6 +626,51 @@ int mref_transmit_byte2(void *h, const int *payload, int nBytes, double *passban
 	ts.transmit_byte(buf, nBytes, passband_out, SINGLE_MESSAGE);
 	*start_sample_inout = (double)ts.ofdm.passband_start_sample;
 	return ts.data_container.total_frame_size;
+}
+
+/* MFSK pattern functions on a pass-band-rate base-band buffer: time_sync_mfsk (ofdm.cc:1969-2065) and
+ * detect_ack_pattern (ofdm.cc:2067-2186) with the ACK or BREAK tones of the loaded ROBUST configuration; bbi = n complex doubles. */
+int mref_time_sync_mfsk(void *h, const double *bbi, int n, int search_start_symb)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	std::complex<double> *b = const_cast<std::complex<double> *>(reinterpret_cast<const std::complex<double> *>(bbi));
+	return ts.ofdm.time_sync_mfsk(b, n, ts.data_container.interpolation_rate, ts.data_container.preamble_nSymb, ts.mfsk.preamble_tones, ts.mfsk.M,
+				      ts.mfsk.nStreams, ts.mfsk.stream_offsets, search_start_symb);
+}
+
+double mref_detect_ack_pattern(void *h, const double *bbi, int n, int use_break_tones, int *matched)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	std::complex<double> *b = const_cast<std::complex<double> *>(reinterpret_cast<const std::complex<double> *>(bbi));
+	return ts.ofdm.detect_ack_pattern(b, n, ts.data_container.interpolation_rate, cl_mfsk::ACK_PATTERN_NSYMB,
+					  use_break_tones ? ts.mfsk.break_tones : ts.mfsk.ack_tones, cl_mfsk::ACK_PATTERN_LEN, ts.mfsk.tone_hop_step,
+					  ts.mfsk.M, ts.mfsk.nStreams, ts.mfsk.stream_offsets, matched);
+}
+
+/* The ACK / BREAK pattern as carriers (mfsk.cc:197-252) and symbol-modulated base-band (16 symbols x Nofdm), for building test buffers. */
+void mref_ack_pattern_baseband(void *h, int use_break_tones, double *out_cplx)
+{
+	cl_telecom_system &ts = T(h);
+	int Nc = ts.data_container.Nc, No = ts.data_container.Nofdm;
+	std::complex<double> *pat = new std::complex<double>[cl_mfsk::ACK_PATTERN_NSYMB * Nc];
+	if (use_break_tones) ts.mfsk.generate_break_pattern(pat);
+	else ts.mfsk.generate_ack_pattern(pat);
+	std::complex<double> *o = reinterpret_cast<std::complex<double> *>(out_cplx);
+	for (int s = 0; s < cl_mfsk::ACK_PATTERN_NSYMB; s++) ts.ofdm.symbol_mod(pat + s * Nc, o + s * No);
+	delete[] pat;
+}
+
+void mref_mfsk_tables(void *h, int *out /*[32]: M, nBits, nStreams, tone_hop_step, stream_offsets[4], preamble_tones[4], ack_tones[8], break_tones[8]*/)
+{
+	cl_telecom_system &ts = T(h);
+	int k = 0;
+	out[k++] = ts.mfsk.M, out[k++] = ts.mfsk.nBits, out[k++] = ts.mfsk.nStreams, out[k++] = ts.mfsk.tone_hop_step;
+	for (int i = 0; i < 4; i++) out[k++] = ts.mfsk.stream_offsets[i];
+	for (int i = 0; i < 4; i++) out[k++] = ts.mfsk.preamble_tones[i];
+	for (int i = 0; i < 8; i++) out[k++] = ts.mfsk.ack_tones[i];
+	for (int i = 0; i < 8; i++) out[k++] = ts.mfsk.break_tones[i];
 }
 
 }  // extern "C"

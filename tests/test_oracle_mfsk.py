@@ -1,0 +1,58 @@
+"""MFSK row: the C restatement of the ROBUST modes' tail (cl_mfsk::mod / demod, mfsk.cc:254-390) and of the
+pattern functions (time_sync_mfsk, detect_ack_pattern, ofdm.cc:1969-2186) against the UNMODIFIED reference, bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import port, ref
+from tests import mfsk_cases as mc
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libmercury_ref.so not built")
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_mfsk_tail_bit_exact(cfg):
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    gr, gp = dict(r.geom), dict(p.geom)
+    for k in ("Cwidth", "Vwidth", "dwidth", "nPilots"):  # (the reference's pilot configurator still counts a dummy lattice in MFSK modes)
+        gr.pop(k), gp.pop(k)
+    assert gr == gp
+    tr, tp = r.mfsk_tables(), p.mfsk_tables()
+    for k in tr:
+        assert np.array_equal(np.asarray(tr[k]), np.asarray(tp[k])), k
+    rng = np.random.default_rng(cfg)
+    n_dec = 0
+    for sigma in (0.0, 10.0, 25.0, 45.0, 80.0):
+        pl = rng.integers(0, 256, r.frame_bytes)
+        xr, ar = r.tx_baseband(pl, True)
+        xp, ap = p.tx_baseband(pl, True)
+        assert np.array_equal(xr, xp)
+        for k in ar:
+            assert np.array_equal(ar[k], ap[k]), k
+        x = xr + sigma * (rng.standard_normal(xr.size) + 1j * rng.standard_normal(xr.size))
+        a, b = r.rx_tail(x), p.rx_tail(x)
+        for k in ("llr_demod", "llr_cw", "bits", "bytes", "payload"):
+            assert np.array_equal(a[k], b[k]), (sigma, k)
+        for k in ("iterations", "crc", "all_zeros", "decoded", "snr"):
+            assert a[k] == b[k], (sigma, k)
+        if a["decoded"]:
+            assert np.array_equal(a["payload"], pl)
+            n_dec += 1
+    assert n_dec >= 3
+
+
+@pytest.mark.parametrize("cfg", [100, 101])
+def test_mfsk_pattern_functions_bit_exact(cfg):
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    assert np.array_equal(r.ack_pattern_baseband(False), p.ack_pattern_baseband(False))
+    assert np.array_equal(r.ack_pattern_baseband(True), p.ack_pattern_baseband(True))
+    for i, kind in enumerate(("ack", "break", "frame", "noise")):
+        buf, pos = mc.pattern_buffer(r, kind, 10 * cfg + i)
+        for brk in (False, True):
+            assert r.detect_ack_pattern(buf, brk) == p.detect_ack_pattern(buf, brk), (kind, brk)
+        for start in (0, 5):
+            assert r.time_sync_mfsk(buf, start) == p.time_sync_mfsk(buf, start), (kind, start)
+        if kind == "ack":
+            m, matched = r.detect_ack_pattern(buf, False)
+            assert matched >= 14 and m > 8 and r.detect_ack_pattern(buf, True)[0] < m / 2
+        if kind == "frame":
+            assert r.time_sync_mfsk(buf) == (pos // (r.Nofdm * 4)) * r.Nofdm * 4
