@@ -199,6 +199,24 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n_frames, void *d_passband,
 					    int out_format, void *stream);
 
+/*
+ * MFSK row.  mercury_b200_load_configuration also accepts the ROBUST configurations 100..102 (ROBUST_0..2,
+ * common_defines.h:63-65: 32-MFSK x1 / 16-MFSK x2, LDPC 1/16, 1/16, 4/16): the batch and single-frame TAIL entry points above then run the
+ * MFSK branch of the tail (telecom_system.cc:1132-1198: symbol_demod + cl_mfsk::demod, mfsk.cc:305-390) in front of the same decoder, on
+ * Nsymb = 320 / 200 / 200 synchronised symbols per frame; SNR reads 0 for a decoded frame like the reference's.  The pass-band entry
+ * points (receive_byte / transmit_byte) remain OFDM-only.
+ * The tone-pattern detectors work on base-band buffers at the pass-band rate (baseband_data_interpolated), n_samples complex samples each:
+ *   time_sync_delay            int cl_ofdm::time_sync_mfsk(...)            ofdm.cc:1969-2065 (preamble tones of the loaded configuration)
+ *   ack_metric / ack_matched   double cl_ofdm::detect_ack_pattern(...)     ofdm.cc:2067-2186 with mfsk.ack_tones   (mfsk.cc:113-136)
+ *   break_metric / _matched    the same with mfsk.break_tones              (mfsk.cc:138-160)
+ */
+typedef struct mercury_b200_mfsk_pattern_result {
+	int32_t time_sync_delay, ack_matched, break_matched, reserved;
+	double ack_metric, break_metric;
+} mercury_b200_mfsk_pattern_result;
+int mercury_b200_mfsk_patterns_batch(mercury_b200_t *h, const void *bbi /* n_buffers x n_samples x (re, im) */, int complex_format /* _F64 | _F32 */,
+				     size_t n_buffers, int n_samples, int search_start_symb, mercury_b200_mfsk_pattern_result *out);
+
 /* Pinned host memory and plain device memory helpers for callers that do not link the CUDA runtime. */
 void *mercury_b200_host_alloc(size_t bytes);
 void mercury_b200_host_free(void *p);

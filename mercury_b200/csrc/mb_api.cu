@@ -22,6 +22,7 @@ std::string mb_synth_frames(const std::vector<uint8_t> &blob, int config, size_t
 static_assert(sizeof(MbRxStats) == sizeof(mercury_b200_rx_stats), "stats record layout");
 static_assert(sizeof(MbRxStats) == 32, "stats record size");
 static_assert(MB_HANDOFF_STRIDE == MERCURY_B200_HANDOFF_FLOATS, "hand-off stride");
+static_assert(sizeof(MbMfskPatternResult) == sizeof(mercury_b200_mfsk_pattern_result) && sizeof(MbMfskPatternResult) == 32, "pattern result layout");
 static_assert(sizeof(MbReceiveStats) == sizeof(mercury_b200_receive_stats) && sizeof(MbReceiveStats) == 72, "receive stats record layout");
 
 namespace {
@@ -86,6 +87,12 @@ void tx_free(TxWork &w);
 }  // namespace
 
 struct mercury_b200 {
+	MbMode mfsk_modes[3];  // ROBUST_0..2 (config 100..102): tables in the extension region behind the device blob
+	MbMfsk mfsk_tones[3];
+	double *d_mfsk_energies = nullptr;
+	MbMfskPatternResult *d_mfsk_out = nullptr;
+	void *d_mfsk_in = nullptr;
+	size_t mfsk_cap_bytes = 0, mfsk_cap_buffers = 0, mfsk_cap_energies = 0;
 	TxWork tx;
 	FeWork fe;
 	MbFeConst fe_const;
@@ -110,6 +117,9 @@ struct mercury_b200 {
 
 namespace {
 
+inline bool is_mfsk_config(int c) { return c >= 100 && c <= 102; }
+inline const MbMode &cur_mode(const mercury_b200_t *h) { return is_mfsk_config(h->config) ? h->mfsk_modes[h->config - 100] : h->hdr.modes[h->config]; }
+
 int fail(mercury_b200_t *h, int code, const std::string &msg)
 {
 	if (h) h->err = msg;
@@ -132,8 +142,14 @@ int upload_blob(mercury_b200_t *h)
 	memcpy(&h->hdr, h->blob.data(), sizeof(MbBlobHeader));
 	if (h->d_blob) cudaFree(h->d_blob);
 	h->d_blob = nullptr;
-	MB_CUDA(h, cudaMalloc(&h->d_blob, h->blob.size()));
+	// the MFSK modes' tables are derived from the blob and appended behind its device copy (mb_build_mfsk_ext)
+	const uint32_t base = (uint32_t)((h->blob.size() + 255) / 256 * 256);
+	std::vector<uint8_t> ext;
+	const std::string e = mb_build_mfsk_ext(h->blob, base, h->mfsk_modes, h->mfsk_tones, ext);
+	if (!e.empty()) return fail(h, MERCURY_B200_EINVAL, e);
+	MB_CUDA(h, cudaMalloc(&h->d_blob, base + ext.size()));
 	MB_CUDA(h, cudaMemcpy(h->d_blob, h->blob.data(), h->blob.size(), cudaMemcpyHostToDevice));
+	MB_CUDA(h, cudaMemcpy(h->d_blob + base, ext.data(), ext.size(), cudaMemcpyHostToDevice));
 	return MERCURY_B200_OK;
 }
 
@@ -150,9 +166,21 @@ int check_ready(mercury_b200_t *h)
 int launch_demod(mercury_b200_t *h, const void *d_x, size_t n, void *d_llr, void *d_stats, void *d_llr_cw, size_t dbg_frame_off, cudaStream_t s,
 		 bool gi_removed = false)
 {
+	const MbMode &m = cur_mode(h);
+	if (m.M == 200) {  // ROBUST modes: FFT + non-coherent tone detection instead of the coherent OFDM demodulator
+		MbMfskArgs f;
+		memset(&f, 0, sizeof(f));
+		f.x = static_cast<const float2 *>(d_x);
+		f.sym_stride = gi_removed ? MB_NFFT : MB_NOFDM, f.sym_skip = gi_removed ? 0 : MB_NGI;
+		f.llr = static_cast<float *>(d_llr), f.llr_cw = static_cast<float *>(d_llr_cw), f.stats = static_cast<MbRxStats *>(d_stats);
+		f.blob = h->d_blob, f.mode = m, f.tone = h->mfsk_tones[h->config - 100];
+		cudaError_t e = mb_launch_mfsk_demod(f, n, s);
+		if (e != cudaSuccess) return cuda_fail(h, e, "mfsk demod kernel launch");
+		h->launches++;
+		return MERCURY_B200_OK;
+	}
 	MbDemodArgs a;
 	memset(&a, 0, sizeof(a));
-	const MbMode &m = h->hdr.modes[h->config];
 	a.x = static_cast<const float2 *>(d_x);
 	a.sym_stride = gi_removed ? MB_NFFT : MB_NOFDM;
 	a.sym_skip = gi_removed ? 0 : MB_NGI;
@@ -177,7 +205,7 @@ int launch_ldpc(mercury_b200_t *h, const void *d_llr, size_t n, void *d_payload,
 {
 	MbLdpcArgs a;
 	memset(&a, 0, sizeof(a));
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	a.llr = static_cast<const float *>(d_llr);
 	a.payload = static_cast<uint8_t *>(d_payload);
 	a.stats = static_cast<MbRxStats *>(d_stats);
@@ -282,6 +310,9 @@ void mercury_b200_destroy(mercury_b200_t *h)
 	}
 	if (h->d_scratch_llr) cudaFree(h->d_scratch_llr);
 	if (h->d_blob) cudaFree(h->d_blob);
+	if (h->d_mfsk_energies) cudaFree(h->d_mfsk_energies);
+	if (h->d_mfsk_out) cudaFree(h->d_mfsk_out);
+	if (h->d_mfsk_in) cudaFree(h->d_mfsk_in);
 	if (h->h_stage) cudaFreeHost(h->h_stage);
 	fe_free(h->fe);
 	tx_free(h->tx);
@@ -340,7 +371,8 @@ int mercury_b200_load_configuration(mercury_b200_t *h, int config, int ldpc_iter
 	if (!h) return MERCURY_B200_EINVAL;
 	if (h->blob.empty()) return fail(h, MERCURY_B200_ESTATE, "tables not loaded");
 	// telecom_system.cc:2494-2497: out-of-range configurations are ignored by the reference; here they are an error
-	if (config < 0 || config >= MB_NMODES) return fail(h, MERCURY_B200_EINVAL, "configuration must be 0..16 (CONFIG_0..CONFIG_16)");
+	if (!is_mfsk_config(config) && (config < 0 || config >= MB_NMODES))
+		return fail(h, MERCURY_B200_EINVAL, "configuration must be 0..16 (CONFIG_0..CONFIG_16) or 100..102 (ROBUST_0..ROBUST_2)");
 	h->config = config;
 	h->ldpc_iters = std::min(50, std::max(5, ldpc_iters));  // main.cc:303-311
 	return MERCURY_B200_OK;
@@ -357,7 +389,7 @@ int mercury_b200_get_geometry(const mercury_b200_t *h, mercury_b200_geometry *g)
 {
 	if (!h || !g) return MERCURY_B200_EINVAL;
 	if (h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	const MbRate &r = h->hdr.rates[m.rate_idx];
 	g->config = m.config, g->M = m.M, g->bits_per_symbol = m.bps, g->ldpc_rate_num = m.rate_num;
 	g->Nsymb = m.Nsymb, g->Nc = MB_NC, g->Nfft = MB_NFFT, g->Ngi = MB_NGI, g->Nofdm = MB_NOFDM;
@@ -372,13 +404,13 @@ int mercury_b200_get_geometry(const mercury_b200_t *h, mercury_b200_geometry *g)
 int mercury_b200_get_frame_size_bytes(const mercury_b200_t *h)
 {
 	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
-	return h->hdr.modes[h->config].frame_bytes;
+	return cur_mode(h).frame_bytes;
 }
 
 int mercury_b200_get_frame_size_bits(const mercury_b200_t *h)
 {
 	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
-	return h->hdr.modes[h->config].nReal - 16;
+	return cur_mode(h).nReal - 16;
 }
 
 int mercury_b200_set_debug_capture(mercury_b200_t *h, void *d_Y, void *d_H, void *d_Z)
@@ -435,7 +467,7 @@ int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *x, size_t n,
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
 	if (!x || !payload || !stats) return fail(h, MERCURY_B200_EINVAL, "null host buffer");
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	const size_t frame_x = (size_t)m.Nsymb * MB_NOFDM * sizeof(float2);
 	// The guard interval never crosses PCIe: a strided (2-D) copy moves the 2,048 useful bytes of every 2,176-byte symbol, so the
 	// device copy of a chunk is [frames][Nsymb][256] and the demodulator is told that the GI is already gone (-5.9 % of the bytes
@@ -477,7 +509,7 @@ int mercury_b200_receive_baseband(mercury_b200_t *h, const double *baseband, int
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (!baseband || !out || !stats) return fail(h, MERCURY_B200_EINVAL, "null buffer");
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	const size_t n = (size_t)m.Nsymb * MB_NOFDM * 2;
 	const size_t need = n * sizeof(float) + 256 + sizeof(mercury_b200_rx_stats);
 	if (h->h_stage_bytes < need) {
@@ -613,7 +645,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 // One chunk of captures already on the device: d_x [n][buf], d_stats [n] in/out, d_payload [n][frame_bytes].
 int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_payload, MbReceiveStats *d_stats, bool dbg, cudaStream_t s)
 {
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	FeWork &w = h->fe;
 	MbFeArgs a;
 	memset(&a, 0, sizeof(a));
@@ -668,7 +700,7 @@ extern "C" {
 int mercury_b200_get_capture_samples(const mercury_b200_t *h)
 {
 	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
-	return fe_capture_samples(h->hdr.modes[h->config]);
+	return fe_capture_samples(cur_mode(h));
 }
 
 int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_x, int fmt, size_t n, void *d_payload, void *d_stats, void *stream)
@@ -677,7 +709,8 @@ int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_x, i
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
 	if (!d_x || !d_payload || !d_stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
+	if (m.M == 200) return fail(h, MERCURY_B200_EINVAL, "receive_byte front-end: OFDM configurations only (the MFSK branch of receive_byte() is not built)");
 	const int buf = fe_capture_samples(m);
 	const size_t ss = fe_sample_bytes(fmt);
 	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, false, 0);
@@ -698,7 +731,8 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
 	if (!x || !payload || !stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
+	if (m.M == 200) return fail(h, MERCURY_B200_EINVAL, "receive_byte front-end: OFDM configurations only (the MFSK branch of receive_byte() is not built)");
 	const int buf = fe_capture_samples(m);
 	const size_t ss = fe_sample_bytes(fmt);
 	// chunks of host_chunk captures: the H2D copy of chunk i+1 (copy stream, second staging buffer) runs while the kernels of chunk i
@@ -748,7 +782,7 @@ int mercury_b200_receive_byte(mercury_b200_t *h, const double *passband, int *ou
 	uint8_t pl[256];
 	int rc = mercury_b200_receive_byte_batch(h, passband, MERCURY_B200_SAMPLES_F64, 1, pl, stats, nullptr);
 	if (rc) return rc;
-	const int fb = h->hdr.modes[h->config].frame_bytes;
+	const int fb = cur_mode(h).frame_bytes;
 	for (int i = 0; i < fb; i++) out[i] = pl[i];  // one int per byte (telecom_system.cc:1329-1332)
 	return MERCURY_B200_OK;
 }
@@ -778,6 +812,7 @@ int tx_total(const MbMode &m) { return (m.Nsymb + m.preamble_nSymb) * MB_FE_SYM;
 int tx_ensure_mode(mercury_b200_t *h)
 {
 	TxWork &w = h->tx;
+	if (is_mfsk_config(h->config)) return fail(h, MERCURY_B200_EINVAL, "transmit_byte: OFDM configurations only");
 	if (!w.init_done) {
 		if (!h->fe_ready) {
 			mb_fe_host_const(&h->fe_const);
@@ -867,7 +902,7 @@ int mercury_b200_build_tx_tables_host(const char *ldpc_table_path, int config, d
 int mercury_b200_get_total_frame_size(const mercury_b200_t *h)
 {
 	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
-	return tx_total(h->hdr.modes[h->config]);
+	return tx_total(cur_mode(h));
 }
 
 int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n, void *d_passband, int out_format,
@@ -880,7 +915,7 @@ int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_pay
 		return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	rc = tx_ensure_mode(h);
 	if (rc) return rc;
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	const int total = tx_total(m);
 	const size_t chunk = std::min<size_t>(n, 8192), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
 	rc = tx_ensure_work(h, chunk, total, false);
@@ -905,7 +940,7 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 		return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	rc = tx_ensure_mode(h);
 	if (rc) return rc;
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	const int total = tx_total(m);
 	const size_t chunk = std::min<size_t>(n, 2048), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
 	rc = tx_ensure_work(h, chunk, total, codeword_dbg != nullptr);
@@ -929,7 +964,7 @@ int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, d
 	if (!h || !data || !out) return MERCURY_B200_EINVAL;
 	int rc = check_ready(h);
 	if (rc) return rc;
-	const MbMode &m = h->hdr.modes[h->config];
+	const MbMode &m = cur_mode(h);
 	if (nBytes < 0 || nBytes > m.frame_bytes) return fail(h, MERCURY_B200_EINVAL, "message too long.. not sent.");  // telecom_system.cc:348-352
 	uint8_t pl[256] = {0};
 	for (int i = 0; i < nBytes; i++) pl[i] = (uint8_t)data[i];
@@ -937,6 +972,43 @@ int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, d
 	rc = mercury_b200_transmit_byte_batch(h, pl, &start, 1, out, MERCURY_B200_SAMPLES_F64, nullptr);
 	if (rc) return rc;
 	if (passband_start_sample) *passband_start_sample = start + (uint64_t)tx_total(m);  // ofdm.cc:2313
+	return MERCURY_B200_OK;
+}
+
+/* MFSK tone-pattern detectors (mb_mfsk.cu): time_sync_mfsk + detect_ack_pattern (ACK and BREAK) over n_buffers base-band buffers. */
+int mercury_b200_mfsk_patterns_batch(mercury_b200_t *h, const void *bbi, int complex_format, size_t n_buffers, int n_samples, int search_start_symb,
+				     mercury_b200_mfsk_pattern_result *out)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n_buffers == 0) return MERCURY_B200_OK;
+	if (!bbi || !out || n_samples < MB_FE_SYM || (complex_format != MERCURY_B200_SAMPLES_F64 && complex_format != MERCURY_B200_SAMPLES_F32))
+		return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	if (!is_mfsk_config(h->config)) return fail(h, MERCURY_B200_EINVAL, "the tone-pattern detectors need a ROBUST configuration (100..102)");
+	const size_t es = complex_format == MERCURY_B200_SAMPLES_F32 ? 8 : 16;
+	const int nsymb = n_samples / MB_FE_SYM;
+	const size_t chunk = std::min<size_t>(n_buffers, std::max<size_t>(1, (512u << 20) / ((size_t)n_samples * es)));
+	if (h->mfsk_cap_bytes < chunk * n_samples * es || h->mfsk_cap_buffers < chunk || h->mfsk_cap_energies < chunk * nsymb * MB_NC) {
+		MB_CUDA(h, cudaDeviceSynchronize());
+		if (h->d_mfsk_in) cudaFree(h->d_mfsk_in);
+		if (h->d_mfsk_out) cudaFree(h->d_mfsk_out);
+		if (h->d_mfsk_energies) cudaFree(h->d_mfsk_energies);
+		h->d_mfsk_in = nullptr, h->d_mfsk_out = nullptr, h->d_mfsk_energies = nullptr;
+		h->mfsk_cap_bytes = h->mfsk_cap_buffers = h->mfsk_cap_energies = 0;
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_in, chunk * n_samples * es));
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_out, chunk * sizeof(MbMfskPatternResult)));
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_energies, chunk * nsymb * MB_NC * sizeof(double)));
+		h->mfsk_cap_bytes = chunk * n_samples * es, h->mfsk_cap_buffers = chunk, h->mfsk_cap_energies = chunk * nsymb * MB_NC;
+	}
+	const MbMode &m = cur_mode(h);
+	for (size_t done = 0; done < n_buffers; done += chunk) {
+		const size_t c = std::min(chunk, n_buffers - done);
+		MB_CUDA(h, cudaMemcpy(h->d_mfsk_in, static_cast<const uint8_t *>(bbi) + done * n_samples * es, c * n_samples * es, cudaMemcpyHostToDevice));
+		MB_CUDA(h, mb_launch_mfsk_patterns(h->d_mfsk_in, complex_format == MERCURY_B200_SAMPLES_F32, c, n_samples, search_start_symb,
+						   h->mfsk_tones[h->config - 100], m.preamble_nSymb, h->d_mfsk_energies, h->d_mfsk_out, nullptr));
+		h->launches += 2;
+		MB_CUDA(h, cudaMemcpy(out + done, h->d_mfsk_out, c * sizeof(MbMfskPatternResult), cudaMemcpyDeviceToHost));
+	}
 	return MERCURY_B200_OK;
 }
 

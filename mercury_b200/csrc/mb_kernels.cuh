@@ -165,3 +165,27 @@ struct MbTxArgs {
 std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
 cudaError_t mb_tx_init();
 cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MFSK row (mb_mfsk.cu): ROBUST_0..2 demodulator + tone-pattern detectors.
+// ---------------------------------------------------------------------------------------------------------------------
+struct MbMfskArgs {
+	const float2 *x;       // [B][Nsymb][sym_stride] complex64 base-band, preamble stripped; useful samples start at sym_skip
+	int32_t sym_stride, sym_skip;
+	float *llr;            // [B][MB_HANDOFF_STRIDE] hand-off records for the LDPC kernel
+	float *llr_cw;         // optional [B][1600] LLRs in codeword order
+	MbRxStats *stats;      // [B]
+	const uint8_t *blob;   // device blob + MFSK extension
+	MbMode mode;
+	MbMfsk tone;
+};
+
+// Mirrors mercury_b200_mfsk_pattern_result (include/mercury_b200.h); 32 bytes.
+struct MbMfskPatternResult {
+	int32_t time_sync_delay, ack_matched, break_matched, reserved;
+	double ack_metric, break_metric;
+};
+
+cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStream_t s);
+cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const MbMfsk &t, int pre,
+				    double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s);

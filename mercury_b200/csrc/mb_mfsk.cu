@@ -1,0 +1,230 @@
+// mb_mfsk.cu -- the MFSK row: the ROBUST_0..2 modes' demodulator and the tone-pattern detectors.
+//   k_mfsk_demod     symbol_demod (ofdm.cc:862-867) + cl_mfsk::demod (mfsk.cc:305-390) + bit de-interleaver (interleaver.cc:77-92)
+//                    on synchronised base-band frames -> LLRs in the LDPC kernel's hand-off layout ("same FFT, different demapper":
+//                    the MFSK branch of the RX tail, telecom_system.cc:1132-1198; the decoder kernel is the OFDM modes' own)
+//   k_mfsk_energies  per-symbol energies of the 50 active carriers of a pass-band-rate base-band buffer (every 4th sample,
+//   k_mfsk_patterns  256-point DFT / 256), then cl_ofdm::time_sync_mfsk (ofdm.cc:1969-2065) and cl_ofdm::detect_ack_pattern
+//                    (ofdm.cc:2067-2186) for the ACK and the BREAK tone sequences (mfsk.cc:113-160) in one pass
+// The demodulator is fp32 like the OFDM one (LLRs within 1e-4 of the reference's); the pattern detectors are fp64 because their
+// outputs are an ARGMAX (the sync delay) and a thresholded metric.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "mb_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ int carrier_bin(int c) { return c < MB_NC / 2 ? c + MB_NFFT - MB_NC / 2 : c - MB_NC / 2 + 1; }
+
+constexpr int kSymPerIter = 8;  // one warp per symbol
+
+__global__ void __launch_bounds__(256) k_mfsk_demod(const MbMfskArgs a)
+{
+	__shared__ float2 xs[kSymPerIter][MB_NFFT];
+	__shared__ float2 W[MB_NFFT];
+	__shared__ float E[kSymPerIter][MB_NC + 2];
+	const MbMode &m = a.mode;
+	const MbMfsk &t = a.tone;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const size_t frame = blockIdx.x;
+	const float2 *x = a.x + frame * (size_t)m.Nsymb * a.sym_stride + a.sym_skip;
+	const uint16_t *__restrict__ dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
+	float *llr = a.llr + frame * MB_HANDOFF_STRIDE;
+	{
+		float s, c;
+		sincospif(-2.0f * tid / 256.0f, &s, &c);
+		W[tid] = make_float2(c, s);
+	}
+	const int band_start = t.stream_offsets[0], band_end = t.stream_offsets[t.nStreams - 1] + t.M;
+	const int bs = m.nBits / 10, nb = 10;
+	for (int s0 = 0; s0 < m.Nsymb; s0 += kSymPerIter) {
+		const int s = s0 + warp;
+		__syncthreads();
+		if (s < m.Nsymb)
+			for (int i = lane; i < MB_NFFT; i += 32) xs[warp][i] = x[(size_t)s * a.sym_stride + i];
+		__syncthreads();
+		if (s >= m.Nsymb) continue;
+		for (int c = lane; c < MB_NC; c += 32) {  // 256-point DFT / 256 at the active carriers
+			const int bin = carrier_bin(c);
+			float ar = 0.f, ai = 0.f;
+#pragma unroll 8
+			for (int n = 0; n < MB_NFFT; n++) {
+				const float2 w = W[(bin * n) & 255], v = xs[warp][n];
+				ar = fmaf(v.x, w.x, fmaf(-v.y, w.y, ar));
+				ai = fmaf(v.x, w.y, fmaf(v.y, w.x, ai));
+			}
+			ar *= (1.0f / 256.0f), ai *= (1.0f / 256.0f);
+			E[warp][c] = ar * ar + ai * ai;
+		}
+		__syncwarp();
+		// noise variance from the carriers outside the tone bands (mfsk.cc:318-338)
+		float ns = 0.f;
+		int nbins = 0;
+		for (int c = lane; c < MB_NC; c += 32)
+			if (c < band_start || c >= band_end) {
+				const float e = E[warp][c];
+				if (isfinite(e)) ns += e, nbins++;
+			}
+		for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o), nbins += __shfl_xor_sync(0xffffffffu, nbins, o);
+		float nv = nbins > 0 ? ns / nbins : 1e-30f;
+		if (nv < 1e-30f) nv = 1e-30f;
+		const float scale = 1.0f / (2.0f * nv);
+		if (lane < m.bps) {  // one LLR per lane: stream st, bit k (mfsk.cc:341-387)
+			const int st = lane / t.nBits, k = lane % t.nBits, mask = 1 << (t.nBits - 1 - k);
+			const int hop = (s * t.tone_hop_step) % t.M;
+			float m1 = -1e30f, m0 = -1e30f;
+			for (int q = 0; q < t.M; q++) {
+				float e = E[warp][t.stream_offsets[st] + (q + hop) % t.M];
+				if (!isfinite(e)) e = 0.f;
+				if ((q ^ (q >> 1)) & mask) m1 = fmaxf(m1, e);
+				else m0 = fmaxf(m0, e);
+			}
+			float l = (m0 - m1) * scale;
+			if (!isfinite(l)) l = 0.f;
+			else l = fminf(5.f, fmaxf(-5.f, l));
+			const int i = s * m.bps + lane;
+			llr[dst[i]] = l;
+			if (a.llr_cw) a.llr_cw[frame * MB_N + (i < nb * bs ? (i % nb) * bs + i / nb : i)] = l;
+		}
+	}
+	if (tid == 0) {
+		MbRxStats st;
+		st.iterations_done = 0, st.crc = 0, st.all_zeros = 0, st.message_decoded = 0;
+		st.SNR = 0.0f;       // telecom_system.cc:1362-1367: MFSK reports SNR 0 for a decoded frame
+		st.variance = 0.0f;
+		st.mean_H = 1.0f;    // no channel estimate, no mean|H| gate in the MFSK branch
+		st.reserved = 0;
+		a.stats[frame] = st;
+	}
+}
+
+// energies[b][s][c] = |DFT256(bbi[s * 1088 + 64 + 4 i])[bin(c)] / 256|^2, fp64
+template <typename T2>
+__global__ void __launch_bounds__(256) k_mfsk_energies(const T2 *__restrict__ bbi_all, int n_samples, int nsymb, double *__restrict__ en_all)
+{
+	__shared__ double2 xs[MB_NFFT];
+	__shared__ double2 W[MB_NFFT];
+	const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
+	const T2 *bbi = bbi_all + (size_t)b * n_samples + (size_t)s * MB_FE_SYM + MB_NGI * 4;
+	{
+		double sn, cs;
+		sincospi(-2.0 * tid / 256.0, &sn, &cs);
+		W[tid] = make_double2(cs, sn);
+		const T2 v = bbi[4 * tid];
+		xs[tid] = make_double2((double)v.x, (double)v.y);
+	}
+	__syncthreads();
+	if (tid < MB_NC) {
+		const int bin = carrier_bin(tid);
+		double ar = 0, ai = 0;
+		for (int n = 0; n < MB_NFFT; n++) {
+			const double2 w = W[(bin * n) & 255], v = xs[n];
+			ar += v.x * w.x - v.y * w.y;
+			ai += v.x * w.y + v.y * w.x;
+		}
+		ar /= 256.0, ai /= 256.0;
+		en_all[((size_t)b * nsymb + s) * MB_NC + tid] = ar * ar + ai * ai;
+	}
+}
+
+// one CTA per buffer: time_sync_mfsk + detect_ack_pattern (ACK and BREAK) over the per-symbol carrier energies
+__global__ void __launch_bounds__(256) k_mfsk_patterns(const double *__restrict__ en_all, int nsymb, int n_samples, int search_start_symb, const MbMfsk t, int pre,
+							 MbMfskPatternResult *__restrict__ out)
+{
+	__shared__ double red_v[256];
+	__shared__ int red_i[256], red_m[256];
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const double *en = en_all + (size_t)b * nsymb * MB_NC;
+	auto e_total = [&](int s) {
+		double tot = 0;
+		for (int k = 0; k < MB_NC; k++) tot += en[(size_t)s * MB_NC + k];
+		return tot;
+	};
+	// ---- time_sync_mfsk: metric(s) = sum over the preamble symbols of (energy at the expected tones) / (energy of all carriers) ----
+	{
+		double best = -1;
+		int bi = 0x7fffffff;
+		for (int s = (search_start_symb > 0 ? search_start_symb : 0) + tid; s <= nsymb - pre; s += 256) {
+			double metric = 0;
+			for (int p = 0; p < pre; p++) {
+				double et = 0;
+				for (int st = 0; st < t.nStreams; st++) et += en[(size_t)(s + p) * MB_NC + t.stream_offsets[st] + t.preamble_tones[p % pre]];
+				const double tot = e_total(s + p);
+				if (tot > 0) metric += et / tot;
+			}
+			if (metric > best) best = metric, bi = s;
+		}
+		red_v[tid] = best, red_i[tid] = bi;
+		__syncthreads();
+		if (tid == 0) {
+			double bv = -1;
+			int bs_ = 0;
+			bool any = false;
+			for (int i = 0; i < 256; i++)
+				if (red_i[i] != 0x7fffffff && (red_v[i] > bv || (red_v[i] == bv && any && red_i[i] < bs_))) bv = red_v[i], bs_ = red_i[i], any = true;
+			out[b].time_sync_delay = bs_ * MB_FE_SYM;
+		}
+		__syncthreads();
+	}
+	// ---- detect_ack_pattern for the ACK tones (which = 0) and the BREAK tones (which = 1) ----
+	for (int which = 0; which < 2; which++) {
+		const int *tones = which ? t.break_tones : t.ack_tones;
+		double best = 0.0;
+		int bi = 0x7fffffff, bm = 0;
+		if (nsymb >= 16)
+			for (int s = tid; s <= nsymb - 16; s += 256) {
+				double metric = 0;
+				int matched = 0;
+				for (int p = 0; p < 16; p++) {
+					const double *e = en + (size_t)(s + p) * MB_NC;
+					const int actual = (tones[p % 8] + p * t.tone_hop_step) % t.M;
+					bool any_peak = false;
+					double et = 0;
+					for (int st = 0; st < t.nStreams; st++) {
+						const double ex = e[t.stream_offsets[st] + actual];
+						et += ex;
+						double peak = -1.0;
+						for (int q = 0; q < t.M; q++) peak = fmax(peak, e[t.stream_offsets[st] + q]);
+						if (ex >= peak) any_peak = true;
+					}
+					if (!any_peak) continue;
+					matched++;
+					const double tot = e_total(s + p);
+					if (tot > 0) metric += et / tot;
+				}
+				if (metric > best) best = metric, bi = s, bm = matched;
+			}
+		red_v[tid] = best, red_i[tid] = bi, red_m[tid] = bm;
+		__syncthreads();
+		if (tid == 0) {
+			double bv = 0.0;
+			int bs_ = 0x7fffffff, bmm = 0;
+			for (int i = 0; i < 256; i++)
+				if (red_i[i] != 0x7fffffff && (red_v[i] > bv || (red_v[i] == bv && red_i[i] < bs_))) bv = red_v[i], bs_ = red_i[i], bmm = red_m[i];
+			if (which == 0) out[b].ack_metric = bv, out[b].ack_matched = bmm;
+			else out[b].break_metric = bv, out[b].break_matched = bmm;
+		}
+		__syncthreads();
+	}
+	(void)n_samples;
+}
+
+}  // namespace
+
+cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStream_t s)
+{
+	k_mfsk_demod<<<(unsigned)n_frames, 256, 0, s>>>(a);
+	return cudaGetLastError();
+}
+
+cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const MbMfsk &t, int pre,
+				    double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s)
+{
+	const int nsymb = n_samples / MB_FE_SYM;
+	if (nsymb <= 0) return cudaErrorInvalidValue;
+	const dim3 grid(nsymb, (unsigned)n_buffers);
+	if (is_f32) k_mfsk_energies<float2><<<grid, 256, 0, s>>>(static_cast<const float2 *>(d_bbi), n_samples, nsymb, d_energies);
+	else k_mfsk_energies<double2><<<grid, 256, 0, s>>>(static_cast<const double2 *>(d_bbi), n_samples, nsymb, d_energies);
+	k_mfsk_patterns<<<(unsigned)n_buffers, 256, 0, s>>>(d_energies, nsymb, n_samples, search_start_symb, t, pre, d_out);
+	return cudaGetLastError();
+}

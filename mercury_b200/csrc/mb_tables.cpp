@@ -589,3 +589,74 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 	}
 	return "";
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ROBUST_0..2 (MFSK modes).  Their tables are NOT part of the blob (its layout and version are what other
+// ranks import): they are derived from it on every handle and live in an extension region appended to the device copy, so the
+// offsets below are relative to the same base as the blob's own (the decoder kernel addresses blob + off).
+// Reference: common_defines.h:63-65, telecom_system.cc:2625-2645,2694-2700,1812-1817 (geometry), mfsk.cc:49-160 (tone plan).
+// ---------------------------------------------------------------------------------------------------------------------
+std::string mb_build_mfsk_ext(const std::vector<uint8_t> &blob, uint32_t base, MbMode modes[3], MbMfsk tones[3], std::vector<uint8_t> &ext)
+{
+	MbBlobHeader h;
+	memcpy(&h, blob.data(), sizeof(h));
+	Blob bl;
+	static const int pre32[4] = {4, 20, 12, 28}, pre16[4] = {2, 10, 6, 14};
+	static const int ack32[8] = {8, 14, 10, 24, 26, 2, 18, 30}, ack16[8] = {4, 7, 5, 12, 13, 1, 9, 15};
+	static const int brk32[8] = {12, 28, 4, 6, 20, 16, 22, 30}, brk16[8] = {6, 14, 2, 3, 10, 8, 11, 15};
+	for (int i = 0; i < 3; i++) {
+		MbMode &m = modes[i];
+		MbMfsk &t = tones[i];
+		memset(&m, 0, sizeof(m));
+		memset(&t, 0, sizeof(t));
+		t.M = i == 0 ? 32 : 16, t.nStreams = i == 0 ? 1 : 2;
+		t.nBits = i == 0 ? 5 : 4, t.tone_hop_step = i == 0 ? 13 : 7;
+		const int global_offset = std::max(0, (MB_NC - t.nStreams * t.M) / 2);
+		for (int k = 0; k < t.nStreams; k++) t.stream_offsets[k] = global_offset + k * t.M;
+		for (int k = 0; k < 4; k++) t.preamble_tones[k] = i == 0 ? pre32[k] : pre16[k];
+		for (int k = 0; k < 8; k++) t.ack_tones[k] = i == 0 ? ack32[k] : ack16[k], t.break_tones[k] = i == 0 ? brk32[k] : brk16[k];
+		const int rate_num = i == 2 ? 4 : 1;
+		m.config = 100 + i, m.M = 200 /* MOD_MFSK */, m.bps = t.nBits * t.nStreams, m.rate_num = rate_num, m.rate_idx = mb_rate_index(rate_num);
+		const MbRate &r = h.rates[m.rate_idx];
+		m.Nsymb = MB_N / m.bps, m.nData = m.Nsymb, m.nPilots = 0, m.nBits = MB_N;
+		m.K = r.K, m.P = r.P, m.nReal = m.nBits - m.P, m.nVirtual = MB_N - m.nBits;
+		m.frame_bytes = (m.nReal - 16) / 8, m.estimator = 1, m.phase_only = 0, m.preamble_nSymb = 4, m.boost = 1.33f;
+		const uint16_t *var_of_cw = reinterpret_cast<const uint16_t *>(blob.data() + r.off_var_of_cw);
+		// LLR i of cl_mfsk::demod (i = symbol * bps + stream * nBits + bit) -> bit de-interleaver (interleaver.cc:77-92, block nBits/10)
+		// -> codeword position (no virtual bits, so the parity move of telecom_system.cc:1300-1308 is the identity) -> internal
+		// variable -> hand-off slot
+		const int bs = m.nBits / 10, nb = m.nBits / bs;
+		std::vector<uint16_t> dst(m.nBits);
+		for (int q = 0; q < m.nBits; q++) {
+			const int cw = q < nb * bs ? (q % nb) * bs + q / nb : q;
+			dst[q] = (uint16_t)MB_HANDOFF((unsigned)var_of_cw[cw]);
+		}
+		m.off_llr_dst = base + bl.put(dst);
+		m.crc_bytes = m.nReal / 8;
+		std::vector<uint16_t> bit_var(8 * m.crc_bytes);
+		for (int q = 0; q < 8 * m.crc_bytes; q++) bit_var[q] = var_of_cw[q];
+		m.off_bit_var = base + bl.put(bit_var);
+		std::vector<uint8_t> scr(MB_N);
+		uint32_t st[35];
+		mb_srandom(st, 0);
+		for (int q = 0; q < MB_N; q++) scr[q] = (uint8_t)(mb_random(st) % 2);
+		m.off_scr = base + bl.put(scr);
+		m.crc_chunk = (m.crc_bytes + 31) / 32;
+		std::vector<uint16_t> crcmat(32 * 16, 0);
+		for (int l = 0; l < 32; l++) {
+			const int end = std::min(m.crc_bytes, (l + 1) * m.crc_chunk), follow = std::max(0, m.crc_bytes - end);
+			for (int b = 0; b < 16; b++) {
+				uint16_t sreg = (uint16_t)(1u << b);
+				for (int k = 0; k < follow; k++) sreg = crc_zero_byte(sreg);
+				crcmat[l * 16 + b] = sreg;
+			}
+		}
+		m.off_crcmat = base + bl.put(crcmat);
+		uint16_t sreg = 0xFFFF;
+		for (int k = 0; k < m.crc_bytes; k++) sreg = crc_zero_byte(sreg);
+		m.crc_init = sreg;
+	}
+	bl.reserve(0, 256);
+	ext.swap(bl.b);
+	return "";
+}

@@ -127,3 +127,11 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size);
 void mb_srandom(uint32_t state[35], unsigned seed);
 int mb_random(uint32_t state[35]);
 int mb_rate_index(int rate_num);
+
+// Tone plan of a ROBUST (MFSK) mode: cl_mfsk (include/physical_layer/mfsk.h, mfsk.cc:49-160).
+struct MbMfsk {
+	int32_t M, nBits, nStreams, tone_hop_step;
+	int32_t stream_offsets[4], preamble_tones[4], ack_tones[8], break_tones[8];
+};
+// MbMode records + tables of ROBUST_0..2, as an extension region that starts `base` bytes after the start of the blob.
+std::string mb_build_mfsk_ext(const std::vector<uint8_t> &blob, uint32_t base, MbMode modes[3], MbMfsk tones[3], std::vector<uint8_t> &ext);

@@ -33,3 +33,12 @@ def _mode(cfg):
 
 
 MODES = [_mode(c) for c in range(17)]
+
+# ROBUST_0..2 (MFSK, include/common/common_defines.h:63-65): tones per stream, streams, LDPC rate
+ROBUST_MODES = {}
+for _cfg, (_M, _streams, _rate) in {100: (32, 1, 1), 101: (16, 2, 1), 102: (16, 2, 4)}.items():
+    _bps = (_M.bit_length() - 1) * _streams
+    _K = 100 * _rate
+    ROBUST_MODES[_cfg] = dict(config=_cfg, M=200, mfsk_M=_M, nStreams=_streams, bps=_bps, rate_num=_rate, Nsymb=1600 // _bps, nData=1600 // _bps,
+                              nPilots=0, nBits=1600, K=_K, P=1600 - _K, nReal=_K, nVirtual=0, frame_bytes=(_K - 16) // 8, preamble_nSymb=4,
+                              estimator=1, phase_only=0, edges=LDPC_EDGES[_rate])

@@ -30,6 +30,8 @@ RECEIVE_STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("delay", "<i4"), ("
                                 ("freq_offset", "<f8"), ("freq_offset_of_last_decoded_message", "<f8"), ("SNR", "<f8"),
                                 ("signal_stregth_dbm", "<f8"), ("coarse_metric", "<f8")])
 assert RECEIVE_STATS_DTYPE.itemsize == C.sizeof(ReceiveStats) == 72
+MFSK_PATTERN_DTYPE = np.dtype([("time_sync_delay", "<i4"), ("ack_matched", "<i4"), ("break_matched", "<i4"), ("reserved", "<i4"),
+                               ("ack_metric", "<f8"), ("break_metric", "<f8")])
 SAMPLES_F64, SAMPLES_F32, SAMPLES_I16, SAMPLES_I32 = 0, 1, 2, 3
 _SAMPLE_FORMATS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2, np.dtype(np.int32): 3}
 
@@ -163,6 +165,19 @@ class TelecomSystemB200:
     def receive_byte_batch_device(self, d_captures, sample_format, n, d_payload, d_stats, stream=0):
         self._check(self._L.mercury_b200_receive_byte_batch_device(self._h, _vp(d_captures), int(sample_format), int(n), _vp(d_payload),
                                                                    _vp(d_stats), C.c_void_p(stream)))
+
+    # ---- MFSK tone-pattern detectors --------------------------------------------------
+    def mfsk_patterns_batch(self, bbi, search_start_symb=0):
+        """bbi [n_buffers, n_samples] complex128 / complex64 base-band at the pass-band rate -> structured array per buffer:
+        time_sync_delay (cl_ofdm::time_sync_mfsk), ack_metric / ack_matched, break_metric / break_matched (cl_ofdm::detect_ack_pattern)."""
+        b = np.ascontiguousarray(bbi)
+        if b.dtype not in (np.complex128, np.complex64):
+            raise TypeError("bbi must be complex128 or complex64")
+        b = b.reshape(-1, b.shape[-1])
+        out = np.zeros(b.shape[0], MFSK_PATTERN_DTYPE)
+        self._check(self._L.mercury_b200_mfsk_patterns_batch(self._h, _vp(b), SAMPLES_F32 if b.dtype == np.complex64 else SAMPLES_F64, b.shape[0],
+                                                             b.shape[1], int(search_start_symb), _vp(out)))
+        return out
 
     # ---- TX chain (SURVEY.md 8f row 2) --------------------------------------------------------------------
     def get_total_frame_size(self):

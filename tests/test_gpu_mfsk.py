@@ -1,0 +1,96 @@
+"""GPU parity of the MFSK row: the ROBUST_0..2 tail (FFT + cl_mfsk::demod + de-interleave + LDPC + CRC) through
+the same batch entry points as the OFDM modes, and the tone-pattern detectors (time_sync_mfsk, detect_ack_pattern with the ACK and
+BREAK tones), against the oracle (the unmodified reference when oracle/_ref travelled to this box, else the C restatement).
+
+Bars: payload / CRC / decision exact, iteration count exact, LLRs within 1e-4 of max(|llr|, median|llr|) (the demodulator is fp32, the
+reference double; LLRs are clamped to +-5), SNR exactly the reference's 0 / -99.9; sync delay and matched counts exact, pattern
+metrics within 1e-9."""
+import numpy as np
+import pytest
+
+import mercury_b200 as mb
+from oracle import port, ref
+from tests import mfsk_cases as mc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    t = mb.TelecomSystemB200(0)
+    yield t
+    t.close()
+
+
+def _oracle(cfg):
+    return ref.Ref(cfg, 50) if ref.available() else port.Port(cfg, 50)
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_robust_tail_against_oracle(ts, cfg):
+    o = _oracle(cfg)
+    g = ts.load_configuration(cfg, 50)
+    R = mb.ROBUST_MODES[cfg]
+    assert (g["Nsymb"], g["K"], g["frame_bytes"], g["nBits"], g["M"]) == (R["Nsymb"], R["K"], R["frame_bytes"], 1600, 200)
+    assert (o.Nsymb, o.frame_bytes) == (g["Nsymb"], g["frame_bytes"])
+    rng = np.random.default_rng(900 + cfg)
+    sigmas = [0.0, 10.0, 25.0, 40.0, 55.0, 70.0, 90.0, 120.0]
+    xs, pls = [], []
+    for sg in sigmas:
+        pl = rng.integers(0, 256, g["frame_bytes"])
+        x = o.tx_baseband(pl)
+        xs.append((x + sg * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64))
+        pls.append(pl)
+    x = np.stack(xs).reshape(len(sigmas), g["Nsymb"], 272)
+    payload, st, llr = ts.demod_decode_batch(x, want_llr=True)
+    n_dec = 0
+    for i in range(len(sigmas)):
+        r = o.rx_tail(x[i].reshape(-1).astype(np.complex128))
+        tol = 1e-4 * np.maximum(np.abs(r["llr_cw"]), np.median(np.abs(r["llr_cw"])))
+        assert (np.abs(llr[i] - r["llr_cw"]) <= tol).all(), (cfg, sigmas[i], np.abs(llr[i] - r["llr_cw"]).max())
+        assert int(st["message_decoded"][i]) == r["decoded"], (cfg, sigmas[i])
+        assert int(st["iterations_done"][i]) == r["iterations"], (cfg, sigmas[i], int(st["iterations_done"][i]), r["iterations"])
+        assert float(st["SNR"][i]) == pytest.approx(r["snr"], abs=1e-4)
+        if r["decoded"]:
+            assert int(st["crc"][i]) == 0 and np.array_equal(payload[i], np.asarray(pls[i], np.uint8)) and np.array_equal(payload[i], r["payload"].astype(np.uint8))
+            n_dec += 1
+    assert n_dec >= 3 and n_dec < len(sigmas)  # both outcomes exercised
+    # the single-frame call in the reference's types
+    out, s1 = ts.receive_baseband(x[1].reshape(-1).astype(np.complex128))
+    assert s1["message_decoded"] == 1 and np.array_equal(out, np.asarray(pls[1], np.int32))
+
+
+@pytest.mark.parametrize("cfg", [100, 101])
+def test_pattern_detectors_against_oracle(ts, cfg):
+    o = _oracle(cfg)
+    ts.load_configuration(cfg, 50)
+    kinds = ["ack", "break", "frame", "noise", "ack", "frame"]
+    bufs, poss = zip(*[mc.pattern_buffer(o, k, 50 * cfg + i) for i, k in enumerate(kinds)])
+    b = np.stack(bufs)
+    for start in (0, 3):
+        res = ts.mfsk_patterns_batch(b, search_start_symb=start)
+        for i, k in enumerate(kinds):
+            assert int(res["time_sync_delay"][i]) == o.time_sync_mfsk(b[i], start), (k, start)
+            for brk, name in ((False, "ack"), (True, "break")):
+                m, matched = o.detect_ack_pattern(b[i], brk)
+                assert abs(float(res[name + "_metric"][i]) - m) <= 1e-9 * max(1.0, m), (k, name)
+                assert int(res[name + "_matched"][i]) == matched, (k, name)
+    res = ts.mfsk_patterns_batch(b)
+    assert res["ack_metric"][0] > 8 and res["ack_matched"][0] >= 14 and res["break_metric"][0] < res["ack_metric"][0] / 2
+    assert res["break_metric"][1] > 8 and res["ack_metric"][1] < res["break_metric"][1] / 2
+    assert int(res["time_sync_delay"][2]) == (poss[2] // 1088) * 1088
+    # complex64 buffers: compared with the oracle on exactly those values widened to double
+    b32 = b.astype(np.complex64)
+    res32 = ts.mfsk_patterns_batch(b32)
+    for i in range(len(kinds)):
+        w = b32[i].astype(np.complex128)
+        assert int(res32["time_sync_delay"][i]) == o.time_sync_mfsk(w, 0)
+        assert abs(float(res32["ack_metric"][i]) - o.detect_ack_pattern(w, False)[0]) <= 1e-9 * max(1.0, float(res32["ack_metric"][i]))
+
+
+def test_pass_band_entry_points_reject_robust_modes(ts):
+    ts.load_configuration(100, 50)
+    with pytest.raises(mb.MercuryB200Error):
+        ts.receive_byte_batch(np.zeros(ts.get_capture_samples() if ts.get_capture_samples() > 0 else 1088, np.float32))
+    with pytest.raises(mb.MercuryB200Error):
+        ts.transmit_byte([1, 2, 3])
