@@ -10,82 +10,100 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "mb_fft.cuh"
 #include "mb_kernels.cuh"
 
 namespace {
 
 __device__ __forceinline__ int carrier_bin(int c) { return c < MB_NC / 2 ? c + MB_NFFT - MB_NC / 2 : c - MB_NC / 2 + 1; }
 
-constexpr int kSymPerIter = 8;  // one warp per symbol
+// 16 threads per symbol (the OFDM demodulator's FFT-256: two radix-4x4 16-point DFTs in registers around a padded shared-memory
+// transpose, twiddles by running product, second DFT pruned to the 4 outputs per thread that reach the 50 active carriers);
+// a 256-thread CTA handles 16 symbols per round.
+constexpr int kSymPerRound = 16;
 
 __global__ void __launch_bounds__(256) k_mfsk_demod(const MbMfskArgs a)
 {
-	__shared__ float2 xs[kSymPerIter][MB_NFFT];
-	__shared__ float2 W[MB_NFFT];
-	__shared__ float E[kSymPerIter][MB_NC + 2];
+	__shared__ float2 scr[kSymPerRound][16 * 17];
+	__shared__ float E[kSymPerRound][MB_NC + 2];
 	const MbMode &m = a.mode;
 	const MbMfsk &t = a.tone;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tid = threadIdx.x, grp = tid >> 4, q = tid & 15;
 	const size_t frame = blockIdx.x;
-	const float2 *x = a.x + frame * (size_t)m.Nsymb * a.sym_stride + a.sym_skip;
 	const uint16_t *__restrict__ dst = reinterpret_cast<const uint16_t *>(a.blob + m.off_llr_dst);
 	float *llr = a.llr + frame * MB_HANDOFF_STRIDE;
+	float2 w1;
 	{
 		float s, c;
-		sincospif(-2.0f * tid / 256.0f, &s, &c);
-		W[tid] = make_float2(c, s);
+		sincospif(-2.0f * q / 256.0f, &s, &c);
+		w1 = make_float2(c, s);  // W256^q
 	}
 	const int band_start = t.stream_offsets[0], band_end = t.stream_offsets[t.nStreams - 1] + t.M;
 	const int bs = m.nBits / 10, nb = 10;
-	for (int s0 = 0; s0 < m.Nsymb; s0 += kSymPerIter) {
-		const int s = s0 + warp;
-		__syncthreads();
-		if (s < m.Nsymb)
-			for (int i = lane; i < MB_NFFT; i += 32) xs[warp][i] = x[(size_t)s * a.sym_stride + i];
-		__syncthreads();
-		if (s >= m.Nsymb) continue;
-		for (int c = lane; c < MB_NC; c += 32) {  // 256-point DFT / 256 at the active carriers
-			const int bin = carrier_bin(c);
-			float ar = 0.f, ai = 0.f;
-#pragma unroll 8
-			for (int n = 0; n < MB_NFFT; n++) {
-				const float2 w = W[(bin * n) & 255], v = xs[warp][n];
-				ar = fmaf(v.x, w.x, fmaf(-v.y, w.y, ar));
-				ai = fmaf(v.x, w.y, fmaf(v.y, w.x, ai));
+	float2 *buf = scr[grp];
+	for (int s0 = 0; s0 < m.Nsymb; s0 += kSymPerRound) {
+		const int s = s0 + grp;
+		const bool active = s < m.Nsymb;
+		float2 v[16];
+		if (active) {
+			const float2 *xs = a.x + (frame * m.Nsymb + (size_t)s) * a.sym_stride + a.sym_skip + q;
+#pragma unroll
+			for (int n1 = 0; n1 < 16; n1++) v[n1] = mbfft::ld_stream(xs + 16 * n1);  // x[16 n1 + q], guard interval skipped
+			float2 A[16];
+			mbfft::fft16(v, A);
+			buf[q * 17] = A[0];
+			float2 wk = w1;
+#pragma unroll
+			for (int k1 = 1; k1 < 16; k1++) {
+				buf[q * 17 + k1] = mbfft::cmul(A[k1], wk);
+				if (k1 < 15) wk = mbfft::cmul(wk, w1);
 			}
-			ar *= (1.0f / 256.0f), ai *= (1.0f / 256.0f);
-			E[warp][c] = ar * ar + ai * ai;
 		}
 		__syncwarp();
-		// noise variance from the carriers outside the tone bands (mfsk.cc:318-338)
+		if (active) {
+			float2 X0, X1, X14, X15;
+#pragma unroll
+			for (int n2 = 0; n2 < 16; n2++) v[n2] = buf[n2 * 17 + q];
+			mbfft::fft16_pruned(v, X0, X1, X14, X15);  // bins q, 16 + q, 224 + q, 240 + q
+			// zero_depadder (ofdm.cc:401-411): bins 231..255 -> carriers 0..24, bins 1..25 -> carriers 25..49; fft() scales by 1/N
+			auto emit = [&](const float2 X, const int c) { E[grp][c] = mbfft::cnorm2(X) * (1.0f / 65536.0f); };
+			if (q >= 1) emit(X0, 24 + q);
+			if (q <= 9) emit(X1, 40 + q);
+			if (q >= 7) emit(X14, q - 7);
+			emit(X15, 9 + q);
+		}
+		__syncwarp();
+		// noise variance from the carriers outside the tone bands (mfsk.cc:318-338): 16 lanes per symbol
 		float ns = 0.f;
 		int nbins = 0;
-		for (int c = lane; c < MB_NC; c += 32)
-			if (c < band_start || c >= band_end) {
-				const float e = E[warp][c];
-				if (isfinite(e)) ns += e, nbins++;
-			}
-		for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o), nbins += __shfl_xor_sync(0xffffffffu, nbins, o);
+		if (active)
+			for (int c = q; c < MB_NC; c += 16)
+				if (c < band_start || c >= band_end) {
+					const float e = E[grp][c];
+					if (isfinite(e)) ns += e, nbins++;
+				}
+		for (int o = 8; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o), nbins += __shfl_xor_sync(0xffffffffu, nbins, o);
 		float nv = nbins > 0 ? ns / nbins : 1e-30f;
 		if (nv < 1e-30f) nv = 1e-30f;
 		const float scale = 1.0f / (2.0f * nv);
-		if (lane < m.bps) {  // one LLR per lane: stream st, bit k (mfsk.cc:341-387)
-			const int st = lane / t.nBits, k = lane % t.nBits, mask = 1 << (t.nBits - 1 - k);
+		if (active && q < m.bps) {  // one LLR per lane: stream st, bit k (mfsk.cc:341-387)
+			const int st = q / t.nBits, k = q % t.nBits, mask = 1 << (t.nBits - 1 - k);
 			const int hop = (s * t.tone_hop_step) % t.M;
 			float m1 = -1e30f, m0 = -1e30f;
-			for (int q = 0; q < t.M; q++) {
-				float e = E[warp][t.stream_offsets[st] + (q + hop) % t.M];
+			for (int j = 0; j < t.M; j++) {
+				float e = E[grp][t.stream_offsets[st] + ((j + hop) & (t.M - 1))];
 				if (!isfinite(e)) e = 0.f;
-				if ((q ^ (q >> 1)) & mask) m1 = fmaxf(m1, e);
+				if ((j ^ (j >> 1)) & mask) m1 = fmaxf(m1, e);
 				else m0 = fmaxf(m0, e);
 			}
 			float l = (m0 - m1) * scale;
 			if (!isfinite(l)) l = 0.f;
 			else l = fminf(5.f, fmaxf(-5.f, l));
-			const int i = s * m.bps + lane;
+			const int i = s * m.bps + q;
 			llr[dst[i]] = l;
 			if (a.llr_cw) a.llr_cw[frame * MB_N + (i < nb * bs ? (i % nb) * bs + i / nb : i)] = l;
 		}
+		__syncwarp();
 	}
 	if (tid == 0) {
 		MbRxStats st;
