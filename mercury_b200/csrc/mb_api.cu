@@ -49,7 +49,7 @@ struct FeWork {
 	size_t host_chunk = 384;  // captures per H2D chunk of the host entry point (copy of chunk i+1 overlaps the kernels of chunk i)
 	MbFeState *st = nullptr;
 	double2 *bbi = nullptr, *win = nullptr, *dbg_bb = nullptr;
-	double *energy_part = nullptr, *vals = nullptr, *pref_ts = nullptr, *pref_win = nullptr;
+	double *energy_part = nullptr, *vals = nullptr, *pref_ts = nullptr, *pref_win = nullptr, *tile_base = nullptr;
 	uint8_t *flags = nullptr;
 	float2 *frames = nullptr;
 	float *llr = nullptr;
@@ -538,7 +538,7 @@ namespace {
 
 void fe_free(FeWork &w)
 {
-	void *ptrs[] = {w.d_x[0], w.d_x[1], w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.pref_ts, w.pref_win, w.flags, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
+	void *ptrs[] = {w.d_x[0], w.d_x[1], w.st, w.bbi, w.win, w.dbg_bb, w.energy_part, w.vals, w.pref_ts, w.pref_win, w.flags, w.tile_base, w.frames, w.llr, w.tail_stats, w.tail_payload, w.payload, w.stats, w.counters};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	if (w.h_counters) cudaFreeHost(w.h_counters);
@@ -611,7 +611,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	if (w.cap >= n && w.buf >= buf && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
 	MB_CUDA(h, cudaDeviceSynchronize());
 	void **ptrs[] = {(void **)&w.st, (void **)&w.bbi, (void **)&w.win, (void **)&w.dbg_bb, (void **)&w.energy_part, (void **)&w.vals, (void **)&w.frames,
-			 (void **)&w.pref_ts, (void **)&w.pref_win, (void **)&w.flags,
+			 (void **)&w.pref_ts, (void **)&w.pref_win, (void **)&w.flags, (void **)&w.tile_base,
 			 (void **)&w.llr, (void **)&w.tail_stats, (void **)&w.tail_payload, (void **)&w.payload, (void **)&w.stats};
 	for (void **p : ptrs) {
 		if (*p) cudaFree(*p);
@@ -627,6 +627,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.flags, cap * kFeVals));
 	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 4096 + 3) * 3 * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
@@ -654,7 +655,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	a.buf = MB_NOFDM * a.buffer_Nsymb * 4, a.pre = m.preamble_nSymb, a.S = m.Nsymb, a.frame_bytes = m.frame_bytes;
 	a.carrier = w.carrier, a.st = w.st, a.bbi = w.bbi, a.energy_part = w.energy_part;
 	a.win = w.win, a.win_stride = kFeWin, a.vals = w.vals, a.vals_stride = kFeVals;
-	a.flags = w.flags, a.pref_ts = w.pref_ts, a.pref_win = w.pref_win;
+	a.flags = w.flags, a.pref_ts = w.pref_ts, a.pref_win = w.pref_win, a.tile_base = w.tile_base;
 	a.frames = w.frames, a.dbg_bb = dbg ? w.dbg_bb : nullptr;
 	a.tail_stats = w.tail_stats, a.tail_payload = w.tail_payload, a.tail_payload_stride = m.frame_bytes;
 	a.payload_out = d_payload, a.counters = w.counters;
@@ -662,7 +663,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	MB_CUDA(h, cudaMemsetAsync(d_payload, 0, n * m.frame_bytes, s));
 	MB_CUDA(h, mb_fe_begin(a, d_stats, s));
 	MB_CUDA(h, mb_fe_p2b_full(a, s));
-	h->launches += 3;
+	h->launches += 4;
 	bool run_sc = true;
 	// every round each capture either finishes or passes one of: coarse run, <= 2 recovery runs, 3 fine runs + 3 tails, SKIP-H
 	// recovery and 3 more trials -- 32 rounds is far above the longest path through receive_byte()
@@ -678,7 +679,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 		run_sc = w.h_counters[2] > 0;
 		if (n_slots > 0) {
 			MB_CUDA(h, mb_fe_extract(a, s));
-			h->launches++;
+			h->launches += 2;
 			int rc = launch_demod(h, w.frames, (size_t)n_slots, w.llr, w.tail_stats, nullptr, 0, s);
 			if (rc) return rc;
 			rc = launch_ldpc(h, w.llr, (size_t)n_slots, w.tail_payload, w.tail_stats, s);

@@ -18,7 +18,7 @@
 //
 // Control flow is a per-capture state machine in global memory advanced by k_fe_decide; the heavy stages are separate
 // kernels that act on whatever each capture is waiting for (MbFeState::phase), so a batch needs no host-side branching:
-//   k_fe_p2b_full, k_fe_prefix -> loop { k_fe_window, k_fe_prefix, k_fe_sc_approx, k_fe_sc_exact, k_fe_decide, k_fe_extract, tail (demod + LDPC
+//   k_fe_p2b_full, k_fe_prefix -> loop { k_fe_window, k_fe_prefix, k_fe_sc_approx, k_fe_sc_exact, k_fe_decide, k_fe_moose, k_fe_extract_tiles, tail (demod + LDPC
 //   kernels) } until all captures are done.
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -241,12 +241,76 @@ __global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__r
 	if (len % (kPrefThreads * RES) == 0 && threadIdx.x == 0) CE[len / RES] = carry.e, C1[len / RES] = carry.p1, C2[len / RES] = carry.p2;
 }
 
+// The coarse (RES 4) prefix of the whole time-sync base-band, fully parallel: every CTA scans ONE tile of 4096 samples (local
+// exclusive prefix, one entry per 4 samples, + the tile's totals); k_fe_prefix4_base turns the totals into per-tile bases.
+// A reader adds the two: C(r) = local[r] + base[r >> 10].
+constexpr int kTileEntries = 1024;
+__global__ void __launch_bounds__(kPrefThreads) k_fe_prefix4_tiles(const double2 *__restrict__ bbi_all, int buf, double *__restrict__ pref_all, size_t pstride,
+								     double *__restrict__ tile_tot, int ntile)
+{
+	__shared__ Pref3 wsum[kPrefThreads / 32];
+	const int b = blockIdx.y, tile = blockIdx.x;
+	const double2 *w = bbi_all + (size_t)b * buf;
+	double *CE = pref_all + (size_t)b * 3 * pstride, *C1 = CE + pstride, *C2 = C1 + pstride;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int m = tile * kTileEntries * 4 + threadIdx.x * 4;
+	Pref3 acc = {0.0, 0.0, 0.0};
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+		if (m + r < buf) {
+			const Pref3 t = pref_terms(w, m + r, buf);
+			acc.e += t.e, acc.p1 += t.p1, acc.p2 += t.p2;
+		}
+	Pref3 inc = acc;
+	for (int o = 1; o < 32; o <<= 1) {
+		const double e = __shfl_up_sync(0xffffffffu, inc.e, o), p1 = __shfl_up_sync(0xffffffffu, inc.p1, o), p2 = __shfl_up_sync(0xffffffffu, inc.p2, o);
+		if (lane >= o) inc.e += e, inc.p1 += p1, inc.p2 += p2;
+	}
+	if (lane == 31) wsum[warp] = inc;
+	__syncthreads();
+	if (warp == 0) {
+		Pref3 v = wsum[lane];
+		for (int o = 1; o < 32; o <<= 1) {
+			const double e = __shfl_up_sync(0xffffffffu, v.e, o), p1 = __shfl_up_sync(0xffffffffu, v.p1, o), p2 = __shfl_up_sync(0xffffffffu, v.p2, o);
+			if (lane >= o) v.e += e, v.p1 += p1, v.p2 += p2;
+		}
+		wsum[lane] = v;
+	}
+	__syncthreads();
+	Pref3 ex = {inc.e - acc.e, inc.p1 - acc.p1, inc.p2 - acc.p2};
+	if (warp > 0) ex.e += wsum[warp - 1].e, ex.p1 += wsum[warp - 1].p1, ex.p2 += wsum[warp - 1].p2;
+	if (m <= buf) CE[m >> 2] = ex.e, C1[m >> 2] = ex.p1, C2[m >> 2] = ex.p2;
+	if (threadIdx.x == 0) {
+		double *tt = tile_tot + ((size_t)b * (ntile + 1) + tile) * 3;
+		tt[0] = wsum[31].e, tt[1] = wsum[31].p1, tt[2] = wsum[31].p2;
+	}
+}
+
+// per capture: exclusive scan of the tile totals -> bases (in place); the terminal entry when the buffer ends on a tile edge
+__global__ void k_fe_prefix4_base(double *__restrict__ tile_tot, int ntile, int buf, double *__restrict__ pref_all, size_t pstride, int n)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	double *tt = tile_tot + (size_t)b * (ntile + 1) * 3;
+	double e = 0, p1 = 0, p2 = 0;
+	for (int t = 0; t < ntile; t++) {
+		const double te = tt[3 * t], t1 = tt[3 * t + 1], t2 = tt[3 * t + 2];
+		tt[3 * t] = e, tt[3 * t + 1] = p1, tt[3 * t + 2] = p2;
+		e += te, p1 += t1, p2 += t2;
+	}
+	tt[3 * ntile] = e, tt[3 * ntile + 1] = p1, tt[3 * ntile + 2] = p2;
+	if ((buf >> 2) % kTileEntries == 0) {
+		double *CE = pref_all + (size_t)b * 3 * pstride;
+		CE[buf >> 2] = 0, CE[pstride + (buf >> 2)] = 0, CE[2 * pstride + (buf >> 2)] = 0;
+	}
+}
+
 __device__ __forceinline__ unsigned long long metric_key(double v) { return (unsigned long long)__double_as_longlong(v + 2.0); }  // monotone for v in [-1, 1]
 
 // pass A
 __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restrict__ st_all, const double *__restrict__ pref_ts, size_t pstride_ts,
-							       const double *__restrict__ pref_win, size_t pstride_win, double *__restrict__ vals_all, int vals_stride,
-							       uint8_t *__restrict__ flags_all, int pre)
+							       const double *__restrict__ pref_win, size_t pstride_win, const double *__restrict__ tile_base, int ntile,
+							       double *__restrict__ vals_all, int vals_stride, uint8_t *__restrict__ flags_all, int pre)
 {
 	const int b = blockIdx.y;
 	MbFeState &st = st_all[b];
@@ -254,18 +318,31 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 	const int k = blockIdx.x * kScThreads + threadIdx.x;
 	double v = -3.0;
 	if (k < st.sc_npos) {
-		// coarse runs (step 100) read the RES-4 prefix of the whole time-sync base-band, fine runs (step 1) the RES-1 prefix of their window
-		const bool fine = st.sc_step == 1;
-		const size_t ps = fine ? pstride_win : pstride_ts;
-		const int sh = fine ? 0 : 2;
-		const double *CE = fine ? pref_win + (size_t)b * 3 * pstride_win + k : pref_ts + (size_t)b * 3 * pstride_ts + ((st.sc_start + k * st.sc_step) >> 2);
-		const double *C1 = CE + ps, *C2 = C1 + ps;
+		// coarse runs (step 100) read the tiled RES-4 prefix of the whole time-sync base-band (local + tile base), fine runs (step 1) the
+		// RES-1 prefix of their window
 		double cc = 0, na = 0, nb = 0;
-		for (int l = 0; l < pre; l++) {
-			const int o = l * MB_FE_SYM;
-			cc += (C1[(o + 64) >> sh] - C1[o >> sh]) + (C2[(o + 576) >> sh] - C2[(o + 64) >> sh]);
-			na += CE[(o + 576) >> sh] - CE[o >> sh];
-			nb += (CE[(o + 1088) >> sh] - CE[(o + 576) >> sh]) + (CE[(o + 1088) >> sh] - CE[(o + 1024) >> sh]);
+		if (st.sc_step == 1) {
+			const double *CE = pref_win + (size_t)b * 3 * pstride_win + k, *C1 = CE + pstride_win, *C2 = C1 + pstride_win;
+			for (int l = 0; l < pre; l++) {
+				const int o = l * MB_FE_SYM;
+				cc += (C1[o + 64] - C1[o]) + (C2[o + 576] - C2[o + 64]);
+				na += CE[o + 576] - CE[o];
+				nb += (CE[o + 1088] - CE[o + 576]) + (CE[o + 1088] - CE[o + 1024]);
+			}
+		} else {
+			const double *L = pref_ts + (size_t)b * 3 * pstride_ts;
+			const double *B = tile_base + (size_t)b * (ntile + 1) * 3;
+			const int r0 = (st.sc_start + k * st.sc_step) >> 2;
+			auto C = [&](int which, int off) {
+				const int r = r0 + (off >> 2);
+				return L[(size_t)which * pstride_ts + r] + B[3 * (r >> 10) + which];
+			};
+			for (int l = 0; l < pre; l++) {
+				const int o = l * MB_FE_SYM;
+				cc += (C(1, o + 64) - C(1, o)) + (C(2, o + 576) - C(2, o + 64));
+				na += C(0, o + 576) - C(0, o);
+				nb += (C(0, o + 1088) - C(0, o + 576)) + (C(0, o + 1088) - C(0, o + 1024));
+			}
 		}
 		const bool amb = fabs(na - 0.001) <= kScThrBand || fabs(nb - 0.001) <= kScThrBand;
 		v = (na < 0.001 || nb < 0.001) ? 0.0 : cc / sqrt(na * nb);
@@ -620,6 +697,7 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 			__syncthreads();
 			if (threadIdx.x == 0) {
 				st.slot = -1;
+				st.extract_pending = 0;
 				if (ts.iterations_done < 0) {  // mean|H| < 0.3: LDPC skipped
 					st.skip_h_count++;
 					st.sync_trials++;
@@ -678,114 +756,139 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 	}
 }
 
-// ---- data-filter mix + decimation, Moose, re-mix at the corrected carrier; writes the tail's input frame ----
+// ---- Moose on the data-filter base-band of the preamble (telecom_system.cc:1081-1117, ofdm.cc:540-595): one CTA per capture ----
 template <typename T>
-__global__ void __launch_bounds__(256) k_fe_extract(MbFeState *__restrict__ st_all, const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier,
-						      float2 *__restrict__ frames, double2 *__restrict__ dbg_bb, int pre, int S)
+__global__ void __launch_bounds__(256) k_fe_moose(MbFeState *__restrict__ st_all, const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, int pre)
 {
 	__shared__ double2 pb[2 * MB_NOFDM];  // the preamble symbols Moose looks at (decimated rate)
-	__shared__ double2 lt[1024 + MB_FE_TAPS - 1];
-	__shared__ double2 G[2][2][24];
-	__shared__ double f_sh;
-	const int b = blockIdx.x;
+	__shared__ double2 W128[128];
+	__shared__ double2 G[2][2][24][4];
+	__shared__ double2 mul_sh;
+	const int b = blockIdx.x, tid = threadIdx.x;
 	MbFeState &st = st_all[b];
 	if (st.phase != MB_FE_EXTRACT) return;
 	const T *x = x_all + (size_t)b * buf;
 	const int delay = st.delay;
 	const int np2 = pre / 2 == 0 ? 1 : pre / 2;  // ofdm.cc:548-555
 	const bool use_last = st.sync_trials == fe_c.trials_max && fe_c.use_last_freq && st.last_freq != 0;  // :1108-1111
+	double fm = st.last_freq;
 	if (!use_last) {
-		for (int k = threadIdx.x; k < np2 * MB_NOFDM; k += blockDim.x)
-			pb[k] = fir_on_demand(x, delay + 4 * k, buf, carrier, true, fe_c.fc, fe_c.c_data);
-		__syncthreads();
-		// Moose (ofdm.cc:540-595): each half symbol is repeated before the 256-point FFT, so only the even bins carry signal and
-		// they equal the 128-point DFT of the half; 24 of the 50 active carriers are even (bins 232..254 and 2..24).
-		double2 mul = make_double2(0.0, 0.0);
-		for (int j = 0; j < np2; j++) {
-			const int bin = threadIdx.x % 24, half = (threadIdx.x / 24) & 1;
-			if (threadIdx.x < 48) {
-				const int k128 = bin < 12 ? 116 + bin : bin - 11;
-				double gr = 0, gi = 0;
-				const double2 *g = pb + j * MB_NOFDM + MB_NGI + half * 128;
-				for (int n = 0; n < 128; n++) {
-					double s, co;
-					sincospi(-2.0 * (double)((k128 * n) & 127) / 128.0, &s, &co);
-					gr += g[n].x * co - g[n].y * s;
-					gi += g[n].x * s + g[n].y * co;
-				}
-				G[j & 1][half][bin] = make_double2(gr, gi);
-			}
-			__syncthreads();
-			if (threadIdx.x == 0)
-				for (int q = 0; q < 24; q++) {  // mul += conj(d2) * d1
-					const double2 d1 = G[j & 1][0][q], d2 = G[j & 1][1][q];
-					mul.x += d2.x * d1.x + d2.y * d1.y;
-					mul.y += d2.x * d1.y - d2.y * d1.x;
-				}
-			__syncthreads();
+		if (tid < 128) {
+			double sn, cs;
+			sincospi(-2.0 * tid / 128.0, &sn, &cs);
+			W128[tid] = make_double2(cs, sn);
 		}
-		if (threadIdx.x == 0) {
-			double th;  // get_angle, misc.cc:34-56
-			if (mul.x == 0) th = M_PI / 2;
-			else if (mul.x > 0) th = atan(mul.y / mul.x);
-			else if (mul.y >= 0) th = atan(mul.y / mul.x) + M_PI;
-			else th = atan(mul.y / mul.x) - M_PI;
-			f_sh = (th / M_PI) * (fe_c.bandwidth / (double)MB_NC);
-		}
-	} else if (threadIdx.x == 0) f_sh = st.last_freq;
-	__syncthreads();
-	const double fm = f_sh;
-	const bool corrected = fabs(fm) > fe_c.ignore_limit;  // :1126
-	const double f = corrected ? fe_c.fc + fm : fe_c.fc;
-	float2 *out = frames + (size_t)st.slot * S * MB_NOFDM;
-	// tiles of 256 decimated outputs = 1024 pass-band samples (+ 32 of filter halo): every pass-band sample is mixed once (one sincos
-	// when the carrier is the Moose-corrected one), then each thread runs the 33 taps of its output from shared memory
-	const int k_begin = dbg_bb ? 0 : pre * MB_NOFDM, k_end = (S + pre) * MB_NOFDM;
-	// corrected carrier: one sincos per thread for its first staged sample, then exact complex rotations by 256 samples (within a
-	// tile) and by 1024 samples (tile to tile) -- ~150 rotations per capture, ~1e-14 of accumulated rounding
-	double2 ph = make_double2(1.0, 0.0), r256 = ph, r1024 = ph;
-	if (corrected) {
-		const int n0 = delay + 4 * k_begin - MB_FE_TAPS / 2 + (int)threadIdx.x;
-		sincos(dmul(dmul(dmul(2 * M_PI, f), (double)n0), fe_c.Ts), &ph.y, &ph.x);
-		sincos(dmul(dmul(dmul(2 * M_PI, f), 256.0), fe_c.Ts), &r256.y, &r256.x);
-		sincos(dmul(dmul(dmul(2 * M_PI, f), 1024.0), fe_c.Ts), &r1024.y, &r1024.x);
-	}
-	for (int k0 = k_begin; k0 < k_end; k0 += 256) {
-		const int p0 = delay + 4 * k0 - MB_FE_TAPS / 2;
-		__syncthreads();
-		double2 cur = ph;
-		for (int i = threadIdx.x; i < 1024 + MB_FE_TAPS - 1; i += 256) {
-			const int n = p0 + i;
-			double2 cs = cur;
-			if (corrected) cur = make_double2(cur.x * r256.x - cur.y * r256.y, cur.x * r256.y + cur.y * r256.x);
-			else if (n >= 0 && n < buf) cs = carrier[n];
-			double2 m = make_double2(0.0, 0.0);
-			if (n >= 0 && n < buf) {
-				const double v = dmul(sample_to_double(x[n]), fe_c.amp);
-				m = make_double2(dmul(v, cs.x), dmul(v, cs.y));
-			}
-			lt[i] = m;
-		}
-		ph = make_double2(ph.x * r1024.x - ph.y * r1024.y, ph.x * r1024.y + ph.y * r1024.x);
-		__syncthreads();
-		const int k = k0 + threadIdx.x;
-		if (k < k_end) {
+		for (int k = tid; k < np2 * MB_NOFDM; k += 256) {  // FIR_rx_data at the decimated positions, carrier from the table
+			const int o = delay + 4 * k;
 			double ar = 0, ai = 0;
 #pragma unroll
 			for (int j = 0; j < MB_FE_TAPS; j++) {
-				const double2 l = lt[4 * threadIdx.x + MB_FE_TAPS - 1 - j];
+				const double2 l = mixed_sample(x, o + MB_FE_TAPS / 2 - j, buf, carrier, true, 0.0);
 				ar = dadd(ar, dmul(l.x, fe_c.c_data[j]));
 				ai = dadd(ai, dmul(l.y, fe_c.c_data[j]));
 			}
-			if (k >= pre * MB_NOFDM) out[k - pre * MB_NOFDM] = make_float2((float)ar, (float)ai);
-			if (dbg_bb) dbg_bb[(size_t)b * (S + pre) * MB_NOFDM + k] = make_double2(ar, ai);
+			pb[k] = make_double2(ar, ai);
 		}
+		__syncthreads();
+		// each half symbol is repeated before the reference's 256-point FFT, so only the even bins carry signal and they equal the
+		// 128-point DFT of the half; 24 of the 50 active carriers are even (bins 232..254 and 2..24).  192 threads: (bin, half, quarter).
+		if (tid == 0) mul_sh = make_double2(0.0, 0.0);
+		for (int j = 0; j < np2; j++) {
+			if (tid < 192) {
+				const int bin = tid % 24, half = (tid / 24) & 1, quarter = tid / 48;
+				const int k128 = bin < 12 ? 116 + bin : bin - 11;
+				double gr = 0, gi = 0;
+				const double2 *g = pb + j * MB_NOFDM + MB_NGI + half * 128;
+				for (int n = quarter * 32; n < quarter * 32 + 32; n++) {
+					const double2 w = W128[(k128 * n) & 127];
+					gr += g[n].x * w.x - g[n].y * w.y;
+					gi += g[n].x * w.y + g[n].y * w.x;
+				}
+				G[j & 1][half][bin][quarter] = make_double2(gr, gi);
+			}
+			__syncthreads();
+			if (tid == 0) {
+				double2 mul = mul_sh;
+				for (int q = 0; q < 24; q++) {  // mul += conj(d2) * d1
+					double2 d1 = make_double2(0.0, 0.0), d2 = d1;
+					for (int r = 0; r < 4; r++) {
+						d1.x += G[j & 1][0][q][r].x, d1.y += G[j & 1][0][q][r].y;
+						d2.x += G[j & 1][1][q][r].x, d2.y += G[j & 1][1][q][r].y;
+					}
+					mul.x += d2.x * d1.x + d2.y * d1.y;
+					mul.y += d2.x * d1.y - d2.y * d1.x;
+				}
+				mul_sh = mul;
+			}
+			__syncthreads();
+		}
+		const double2 mul = mul_sh;
+		double th;  // get_angle, misc.cc:34-56
+		if (mul.x == 0) th = M_PI / 2;
+		else if (mul.x > 0) th = atan(mul.y / mul.x);
+		else if (mul.y >= 0) th = atan(mul.y / mul.x) + M_PI;
+		else th = atan(mul.y / mul.x) - M_PI;
+		fm = (th / M_PI) * (fe_c.bandwidth / (double)MB_NC);
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
+	if (tid == 0) {
+		const bool corrected = fabs(fm) > fe_c.ignore_limit;  // :1126
 		st.freq_offset_measured = fm;
-		st.cur_kind = 1, st.cur_f = f;
+		st.cur_kind = 1, st.cur_f = corrected ? fe_c.fc + fm : fe_c.fc;
+		st.extract_pending = 1;
 		st.phase = MB_FE_TAIL_WAIT;
+	}
+}
+
+// ---- data-filter mix at the final carrier + decimation by 4 (:1081-1103,1126-1131): one CTA per tile of 256 decimated outputs ----
+template <typename T>
+__global__ void __launch_bounds__(256) k_fe_extract_tiles(const MbFeState *__restrict__ st_all, const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier,
+							    float2 *__restrict__ frames, double2 *__restrict__ dbg_bb, int pre, int S)
+{
+	__shared__ double2 lt[1024 + MB_FE_TAPS - 1];
+	__shared__ double2 r256_sh;
+	const int b = blockIdx.y, tid = threadIdx.x;
+	const MbFeState &st = st_all[b];
+	if (!st.extract_pending) return;
+	const int k_begin = dbg_bb ? 0 : pre * MB_NOFDM, k_end = (S + pre) * MB_NOFDM;
+	const int k0 = k_begin + blockIdx.x * 256;
+	if (k0 >= k_end) return;
+	const T *x = x_all + (size_t)b * buf;
+	const double f = st.cur_f;
+	const bool corrected = f != fe_c.fc;
+	const int p0 = st.delay + 4 * k0 - MB_FE_TAPS / 2;
+	// corrected carrier: one sincos per thread for its first staged sample, then rotations by 256 samples
+	double2 cur = make_double2(1.0, 0.0);
+	if (corrected) {
+		sincos(dmul(dmul(dmul(2 * M_PI, f), (double)(p0 + tid)), fe_c.Ts), &cur.y, &cur.x);
+		if (tid == 0) sincos(dmul(dmul(dmul(2 * M_PI, f), 256.0), fe_c.Ts), &r256_sh.y, &r256_sh.x);
+		__syncthreads();
+	}
+	const double2 r256 = corrected ? r256_sh : cur;
+	for (int i = tid; i < 1024 + MB_FE_TAPS - 1; i += 256) {
+		const int n = p0 + i;
+		double2 cs = cur;
+		if (corrected) cur = make_double2(cur.x * r256.x - cur.y * r256.y, cur.x * r256.y + cur.y * r256.x);
+		else if (n >= 0 && n < buf) cs = carrier[n];
+		double2 m = make_double2(0.0, 0.0);
+		if (n >= 0 && n < buf) {
+			const double v = dmul(sample_to_double(x[n]), fe_c.amp);
+			m = make_double2(dmul(v, cs.x), dmul(v, cs.y));
+		}
+		lt[i] = m;
+	}
+	__syncthreads();
+	const int k = k0 + tid;
+	if (k < k_end) {
+		double ar = 0, ai = 0;
+#pragma unroll
+		for (int j = 0; j < MB_FE_TAPS; j++) {
+			const double2 l = lt[4 * tid + MB_FE_TAPS - 1 - j];
+			ar = dadd(ar, dmul(l.x, fe_c.c_data[j]));
+			ai = dadd(ai, dmul(l.y, fe_c.c_data[j]));
+		}
+		if (k >= pre * MB_NOFDM) frames[(size_t)st.slot * S * MB_NOFDM + k - pre * MB_NOFDM] = make_float2((float)ar, (float)ai);
+		if (dbg_bb) dbg_bb[(size_t)b * (S + pre) * MB_NOFDM + k] = make_double2(ar, ai);
 	}
 }
 
@@ -883,7 +986,9 @@ static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
 {
 	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
 	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
-	k_fe_prefix<4><<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.pref_ts, (size_t)a.buf / 4 + 1);
+	const int ntile = (a.buf / 4 + kTileEntries - 1) / kTileEntries;
+	k_fe_prefix4_tiles<<<dim3(ntile, a.n), kPrefThreads, 0, s>>>(a.bbi, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.tile_base, ntile);
+	k_fe_prefix4_base<<<(a.n + 63) / 64, 64, 0, s>>>(a.tile_base, ntile, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.n);
 	return cudaGetLastError();
 }
 
@@ -895,7 +1000,8 @@ static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
 		k_fe_window<T><<<dim3(8, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.st, a.win, a.win_stride);
 		k_fe_prefix<1><<<a.n, kPrefThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.pref_win, (size_t)a.win_stride + 1);
 		const dim3 grid((a.vals_stride + kScThreads - 1) / kScThreads, a.n);
-		k_fe_sc_approx<<<grid, kScThreads, 0, s>>>(a.st, a.pref_ts, (size_t)a.buf / 4 + 1, a.pref_win, (size_t)a.win_stride + 1, a.vals, a.vals_stride, a.flags, a.pre);
+		k_fe_sc_approx<<<grid, kScThreads, 0, s>>>(a.st, a.pref_ts, (size_t)a.buf / 4 + 1, a.pref_win, (size_t)a.win_stride + 1, a.tile_base,
+							   (a.buf / 4 + kTileEntries - 1) / kTileEntries, a.vals, a.vals_stride, a.flags, a.pre);
 		k_fe_sc_exact<<<grid, kScThreads, 0, s>>>(a.st, a.bbi, a.buf, a.win, a.win_stride, a.vals, a.vals_stride, a.flags, a.pre, a.counters);
 	}
 	k_fe_decide<T><<<a.n, kDecideThreads, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.vals, a.vals_stride, a.energy_part, nblk,
@@ -907,7 +1013,9 @@ static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
 template <typename T>
 static cudaError_t fe_extract_t(const MbFeArgs &a, cudaStream_t s)
 {
-	k_fe_extract<T><<<a.n, 256, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.frames, a.dbg_bb, a.pre, a.S);
+	k_fe_moose<T><<<a.n, 256, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.pre);
+	const int outs = (a.dbg_bb ? a.S + a.pre : a.S) * MB_NOFDM;
+	k_fe_extract_tiles<T><<<dim3((outs + 255) / 256, a.n), 256, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.frames, a.dbg_bb, a.pre, a.S);
 	return cudaGetLastError();
 }
 

@@ -84,6 +84,7 @@ struct MbFeState {
 	int32_t cur_kind;    // what baseband_data_interpolated holds: 0 = time-sync filter at fc (materialised), 1 = data filter at cur_f (on demand)
 	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for
 	int32_t slot;        // tail slot of the running trial
+	int32_t extract_pending;  // k_fe_moose has chosen the carrier, k_fe_extract_tiles still has to write the frame
 	unsigned long long sc_max_key;  // approximate maximum of the pending run (pass A of the two-pass Schmidl-Cox), order-preserving key
 };
 
@@ -100,6 +101,7 @@ struct MbFeArgs {
 	int32_t vals_stride;
 	uint8_t *flags;      // [n][vals_stride] positions whose norms sit on the 0.001 threshold (forced into the exact pass)
 	double *pref_ts;     // [n][3][buf / 4 + 1]    exclusive prefix sums over the time-sync base-band, one entry per 4 samples: |w|^2, lag-1024 and lag-512 dot products
+	double *tile_base;   // [n][ceil(buf / 4096) + 1][3] per-tile bases of pref_ts (its entries are tile-local)
 	double *pref_win;    // [n][3][win_stride + 1] the same at full resolution over the window of the pending fine run
 	float2 *frames;      // [n][S][272] tail input, by slot
 	double2 *dbg_bb;     // optional [n][(pre+S)*272] fp64 copy of baseband_data (by capture)
