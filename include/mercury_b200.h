@@ -168,6 +168,9 @@ typedef struct mercury_b200_receive_stats {
 #define MERCURY_B200_SAMPLES_I32 3  /* int32 PCM, x / (double)INT_MAX (the reference's default capture format, audioio.c:744) */
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h);
+/* Host-only (no device needed): the two receive FIR designs (33 taps each), {fs, fc, carrier amplitude, bandwidth, time_sync_trials_max,
+ * use_last_good_time_sync, use_last_good_freq_offset, freq_offset_ignore_limit} and the first n_carrier (cos, sin) pairs of the carrier table. */
+int mercury_b200_build_frontend_tables_host(double *ts_coef, double *data_coef, double *consts, double *carrier, int n_carrier);
 /* One capture, the reference's own types (out = one int per payload byte). */
 int mercury_b200_receive_byte(mercury_b200_t *h, const double *passband, int *out, mercury_b200_receive_stats *stats);
 /* n captures of independent links: passband n x capture_samples (host), payload n x frame_bytes, stats n records (in/out).

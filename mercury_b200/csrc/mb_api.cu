@@ -627,7 +627,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.flags, cap * kFeVals));
 	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
-	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 4096 + 3) * 3 * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 1024 + 3) * 3 * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
@@ -697,6 +697,22 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 }  // namespace
 
 extern "C" {
+
+// Host-only (no device needed): the front-end's host-derived constants, for pinning them against the oracle on a CPU-only machine.
+int mercury_b200_build_frontend_tables_host(double *ts_coef /*[33]*/, double *data_coef /*[33]*/, double *consts /*[8]*/, double *carrier /*[2 * n_carrier]*/,
+					    int n_carrier)
+{
+	MbFeConst k;
+	mb_fe_host_const(&k);
+	if (ts_coef) memcpy(ts_coef, k.c_ts, sizeof(double) * MB_FE_TAPS);
+	if (data_coef) memcpy(data_coef, k.c_data, sizeof(double) * MB_FE_TAPS);
+	if (consts) {
+		const double v[8] = {k.fs, k.fc, k.amp, k.bandwidth, (double)k.trials_max, (double)k.use_last_time, (double)k.use_last_freq, k.ignore_limit};
+		memcpy(consts, v, sizeof(v));
+	}
+	if (carrier && n_carrier > 0) mb_fe_host_carrier(k, carrier, n_carrier);
+	return MERCURY_B200_OK;
+}
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h)
 {

@@ -243,12 +243,14 @@ __global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__r
 
 // The coarse (RES 4) prefix of the whole time-sync base-band, fully parallel: every CTA scans ONE tile of 4096 samples (local
 // exclusive prefix, one entry per 4 samples, + the tile's totals); k_fe_prefix4_base turns the totals into per-tile bases.
-// A reader adds the two: C(r) = local[r] + base[r >> 10].
-constexpr int kTileEntries = 1024;
-__global__ void __launch_bounds__(kPrefThreads) k_fe_prefix4_tiles(const double2 *__restrict__ bbi_all, int buf, double *__restrict__ pref_all, size_t pstride,
+// A reader adds the two: C(r) = local[r] + base[r >> kTileShift].
+constexpr int kTileEntries = 256;   // entries (= threads) per tile: small CTAs, 8 per SM, so that loads of one overlap the scans of others
+constexpr int kTileShift = 8;
+__global__ void __launch_bounds__(kTileEntries) k_fe_prefix4_tiles(const double2 *__restrict__ bbi_all, int buf, double *__restrict__ pref_all, size_t pstride,
 								     double *__restrict__ tile_tot, int ntile)
 {
-	__shared__ Pref3 wsum[kPrefThreads / 32];
+	constexpr int NW = kTileEntries / 32;
+	__shared__ Pref3 wsum[NW];
 	const int b = blockIdx.y, tile = blockIdx.x;
 	const double2 *w = bbi_all + (size_t)b * buf;
 	double *CE = pref_all + (size_t)b * 3 * pstride, *C1 = CE + pstride, *C2 = C1 + pstride;
@@ -269,12 +271,13 @@ __global__ void __launch_bounds__(kPrefThreads) k_fe_prefix4_tiles(const double2
 	if (lane == 31) wsum[warp] = inc;
 	__syncthreads();
 	if (warp == 0) {
-		Pref3 v = wsum[lane];
+		Pref3 v = wsum[lane < NW ? lane : NW - 1];
+		if (lane >= NW) v.e = v.p1 = v.p2 = 0.0;
 		for (int o = 1; o < 32; o <<= 1) {
 			const double e = __shfl_up_sync(0xffffffffu, v.e, o), p1 = __shfl_up_sync(0xffffffffu, v.p1, o), p2 = __shfl_up_sync(0xffffffffu, v.p2, o);
 			if (lane >= o) v.e += e, v.p1 += p1, v.p2 += p2;
 		}
-		wsum[lane] = v;
+		if (lane < NW) wsum[lane] = v;
 	}
 	__syncthreads();
 	Pref3 ex = {inc.e - acc.e, inc.p1 - acc.p1, inc.p2 - acc.p2};
@@ -282,26 +285,37 @@ __global__ void __launch_bounds__(kPrefThreads) k_fe_prefix4_tiles(const double2
 	if (m <= buf) CE[m >> 2] = ex.e, C1[m >> 2] = ex.p1, C2[m >> 2] = ex.p2;
 	if (threadIdx.x == 0) {
 		double *tt = tile_tot + ((size_t)b * (ntile + 1) + tile) * 3;
-		tt[0] = wsum[31].e, tt[1] = wsum[31].p1, tt[2] = wsum[31].p2;
+		tt[0] = wsum[NW - 1].e, tt[1] = wsum[NW - 1].p1, tt[2] = wsum[NW - 1].p2;
 	}
 }
 
 // per capture: exclusive scan of the tile totals -> bases (in place); the terminal entry when the buffer ends on a tile edge
 __global__ void k_fe_prefix4_base(double *__restrict__ tile_tot, int ntile, int buf, double *__restrict__ pref_all, size_t pstride, int n)
-{
-	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+{  // one warp per capture: every lane scans a contiguous chunk of tiles, a warp scan joins the chunks
+	const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (b >= n) return;
 	double *tt = tile_tot + (size_t)b * (ntile + 1) * 3;
+	const int per = (ntile + 31) / 32, t0 = lane * per, t1 = min(ntile, t0 + per);
 	double e = 0, p1 = 0, p2 = 0;
-	for (int t = 0; t < ntile; t++) {
-		const double te = tt[3 * t], t1 = tt[3 * t + 1], t2 = tt[3 * t + 2];
-		tt[3 * t] = e, tt[3 * t + 1] = p1, tt[3 * t + 2] = p2;
-		e += te, p1 += t1, p2 += t2;
+	for (int t = t0; t < t1; t++) e += tt[3 * t], p1 += tt[3 * t + 1], p2 += tt[3 * t + 2];
+	double ie = e, i1 = p1, i2 = p2;
+	for (int o = 1; o < 32; o <<= 1) {
+		const double a = __shfl_up_sync(0xffffffffu, ie, o), c = __shfl_up_sync(0xffffffffu, i1, o), d = __shfl_up_sync(0xffffffffu, i2, o);
+		if (lane >= o) ie += a, i1 += c, i2 += d;
 	}
-	tt[3 * ntile] = e, tt[3 * ntile + 1] = p1, tt[3 * ntile + 2] = p2;
-	if ((buf >> 2) % kTileEntries == 0) {
-		double *CE = pref_all + (size_t)b * 3 * pstride;
-		CE[buf >> 2] = 0, CE[pstride + (buf >> 2)] = 0, CE[2 * pstride + (buf >> 2)] = 0;
+	const double te = __shfl_sync(0xffffffffu, ie, 31), tp1 = __shfl_sync(0xffffffffu, i1, 31), tp2 = __shfl_sync(0xffffffffu, i2, 31);
+	double re = ie - e, r1 = i1 - p1, r2 = i2 - p2;  // exclusive base of this lane's chunk
+	for (int t = t0; t < t1; t++) {
+		const double ve = tt[3 * t], v1 = tt[3 * t + 1], v2 = tt[3 * t + 2];
+		tt[3 * t] = re, tt[3 * t + 1] = r1, tt[3 * t + 2] = r2;
+		re += ve, r1 += v1, r2 += v2;
+	}
+	if (lane == 0) {
+		tt[3 * ntile] = te, tt[3 * ntile + 1] = tp1, tt[3 * ntile + 2] = tp2;
+		if ((buf >> 2) % kTileEntries == 0) {
+			double *CE = pref_all + (size_t)b * 3 * pstride;
+			CE[buf >> 2] = 0, CE[pstride + (buf >> 2)] = 0, CE[2 * pstride + (buf >> 2)] = 0;
+		}
 	}
 }
 
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 			const int r0 = (st.sc_start + k * st.sc_step) >> 2;
 			auto C = [&](int which, int off) {
 				const int r = r0 + (off >> 2);
-				return L[(size_t)which * pstride_ts + r] + B[3 * (r >> 10) + which];
+				return L[(size_t)which * pstride_ts + r] + B[3 * (r >> kTileShift) + which];
 			};
 			for (int l = 0; l < pre; l++) {
 				const int o = l * MB_FE_SYM;
@@ -979,7 +993,10 @@ void mb_fe_host_carrier(const MbFeConst &k, double *cs, int n)
 	}
 }
 
-cudaError_t mb_fe_init(const MbFeConst &k) { return cudaMemcpyToSymbol(fe_c, &k, sizeof(k)); }
+cudaError_t mb_fe_init(const MbFeConst &k)
+{
+	return cudaMemcpyToSymbol(fe_c, &k, sizeof(k));
+}
 
 template <typename T>
 static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
@@ -987,8 +1004,8 @@ static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
 	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
 	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
 	const int ntile = (a.buf / 4 + kTileEntries - 1) / kTileEntries;
-	k_fe_prefix4_tiles<<<dim3(ntile, a.n), kPrefThreads, 0, s>>>(a.bbi, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.tile_base, ntile);
-	k_fe_prefix4_base<<<(a.n + 63) / 64, 64, 0, s>>>(a.tile_base, ntile, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.n);
+	k_fe_prefix4_tiles<<<dim3(ntile, a.n), kTileEntries, 0, s>>>(a.bbi, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.tile_base, ntile);
+	k_fe_prefix4_base<<<(a.n * 32 + 127) / 128, 128, 0, s>>>(a.tile_base, ntile, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.n);
 	return cudaGetLastError();
 }
 

@@ -101,7 +101,7 @@ struct MbFeArgs {
 	int32_t vals_stride;
 	uint8_t *flags;      // [n][vals_stride] positions whose norms sit on the 0.001 threshold (forced into the exact pass)
 	double *pref_ts;     // [n][3][buf / 4 + 1]    exclusive prefix sums over the time-sync base-band, one entry per 4 samples: |w|^2, lag-1024 and lag-512 dot products
-	double *tile_base;   // [n][ceil(buf / 4096) + 1][3] per-tile bases of pref_ts (its entries are tile-local)
+	double *tile_base;   // [n][ceil(buf / 1024) + 1][3] per-tile bases of pref_ts (its entries are tile-local)
 	double *pref_win;    // [n][3][win_stride + 1] the same at full resolution over the window of the pending fine run
 	float2 *frames;      // [n][S][272] tail input, by slot
 	double2 *dbg_bb;     // optional [n][(pre+S)*272] fp64 copy of baseband_data (by capture)
