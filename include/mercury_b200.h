@@ -157,7 +157,10 @@ int mercury_b200_receive_baseband(mercury_b200_t *h, const double *baseband, int
  */
 typedef struct mercury_b200_receive_stats {
 	int32_t iterations_done, delay, delay_of_last_decoded_message, sync_trials;
-	int32_t message_decoded, crc, all_zeros, reserved;
+	int32_t message_decoded, crc, all_zeros;
+	int32_t mfsk_search_or_overflow; /* ROBUST (MFSK) configurations only.  IN: first symbol of the tone-preamble search, the reference's
+	                                    receive_stats.mfsk_search_raw - nUnder_processing_events (telecom_system.cc:684).  OUT:
+	                                    frame_overflow_symbols (:702-715), > 0 when the frame runs past the end of the capture. */
 	double freq_offset, freq_offset_of_last_decoded_message, SNR, signal_stregth_dbm, coarse_metric;
 } mercury_b200_receive_stats;
 

@@ -28,7 +28,7 @@ class RxStats(C.Structure):
 class ReceiveStats(C.Structure):
     """mercury_b200_receive_stats = st_receive_stats (telecom_system.h:63-82), fields of the OFDM branch."""
     _fields_ = [("iterations_done", C.c_int32), ("delay", C.c_int32), ("delay_of_last_decoded_message", C.c_int32), ("sync_trials", C.c_int32),
-                ("message_decoded", C.c_int32), ("crc", C.c_int32), ("all_zeros", C.c_int32), ("reserved", C.c_int32),
+                ("message_decoded", C.c_int32), ("crc", C.c_int32), ("all_zeros", C.c_int32), ("mfsk_search_or_overflow", C.c_int32),
                 ("freq_offset", C.c_double), ("freq_offset_of_last_decoded_message", C.c_double), ("SNR", C.c_double),
                 ("signal_stregth_dbm", C.c_double), ("coarse_metric", C.c_double)]
 

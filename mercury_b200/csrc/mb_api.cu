@@ -629,13 +629,13 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 1024 + 3) * 3 * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
-	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)MB_MAX_SYMB * MB_NOFDM * sizeof(float2)));
+	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)std::max(MB_MAX_SYMB, m.Nsymb) * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
 	MB_CUDA(h, cudaMalloc(&w.tail_stats, cap * sizeof(MbRxStats)));
 	MB_CUDA(h, cudaMalloc(&w.tail_payload, cap * 256));
 	MB_CUDA(h, cudaMalloc(&w.payload, cap * 256));
 	MB_CUDA(h, cudaMalloc(&w.stats, cap * sizeof(MbReceiveStats)));
-	if (want_dbg) MB_CUDA(h, cudaMalloc(&w.dbg_bb, cap * (size_t)(MB_MAX_SYMB + 4) * MB_NOFDM * sizeof(double2)));
+	if (want_dbg) MB_CUDA(h, cudaMalloc(&w.dbg_bb, cap * (size_t)(std::max(MB_MAX_SYMB, m.Nsymb) + 4) * MB_NOFDM * sizeof(double2)));
 	(void)bb_n;
 	w.want_dbg = want_dbg;
 	w.cap = cap;
@@ -644,6 +644,8 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 }
 
 // One chunk of captures already on the device: d_x [n][buf], d_stats [n] in/out, d_payload [n][frame_bytes].
+int fe_run_mfsk(mercury_b200_t *h, const MbFeArgs &a, MbReceiveStats *d_stats, cudaStream_t s);
+
 int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_payload, MbReceiveStats *d_stats, bool dbg, cudaStream_t s)
 {
 	const MbMode &m = cur_mode(h);
@@ -659,8 +661,9 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	a.frames = w.frames, a.dbg_bb = dbg ? w.dbg_bb : nullptr;
 	a.tail_stats = w.tail_stats, a.tail_payload = w.tail_payload, a.tail_payload_stride = m.frame_bytes;
 	a.payload_out = d_payload, a.counters = w.counters;
-	if ((a.buf - m.preamble_nSymb * MB_FE_SYM + 99) / 100 > kFeVals) return fail(h, MERCURY_B200_EINVAL, "capture too long for the correlation buffer");
 	MB_CUDA(h, cudaMemsetAsync(d_payload, 0, n * m.frame_bytes, s));
+	if (m.M == 200) return fe_run_mfsk(h, a, d_stats, s);
+	if ((a.buf - m.preamble_nSymb * MB_FE_SYM + 99) / 100 > kFeVals) return fail(h, MERCURY_B200_EINVAL, "capture too long for the correlation buffer");
 	MB_CUDA(h, mb_fe_begin(a, d_stats, s));
 	MB_CUDA(h, mb_fe_p2b_full(a, s));
 	h->launches += 4;
@@ -690,6 +693,49 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	}
 	MB_CUDA(h, mb_fe_finish(a, d_stats, s));
 	h->launches++;
+	MB_CUDA(h, cudaStreamSynchronize(s));
+	return MERCURY_B200_OK;
+}
+
+// The MFSK branch of receive_byte() (ROBUST configurations; telecom_system.cc:646-716, 928-943, 1020-1031, 1081-1198, 1343-1367): full-buffer
+// mix + time-sync FIR, tone-preamble sync on the symbol grid, frame-completeness check, one trial at that delay with the data filter and
+// no frequency correction, the MFSK tail.  One counter read-back.
+int fe_run_mfsk(mercury_b200_t *h, const MbFeArgs &a, MbReceiveStats *d_stats, cudaStream_t s)
+{
+	FeWork &w = h->fe;
+	const MbMode &m = cur_mode(h);
+	const int nsymb = a.buf / MB_FE_SYM, nblk = (a.buf + 1023) / 1024;
+	if (h->mfsk_cap_buffers < (size_t)a.n || h->mfsk_cap_energies < (size_t)a.n * nsymb * MB_NC) {
+		MB_CUDA(h, cudaDeviceSynchronize());
+		if (h->d_mfsk_out) cudaFree(h->d_mfsk_out);
+		if (h->d_mfsk_energies) cudaFree(h->d_mfsk_energies);
+		h->d_mfsk_out = nullptr, h->d_mfsk_energies = nullptr;
+		h->mfsk_cap_buffers = h->mfsk_cap_energies = 0;
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_out, (size_t)a.n * sizeof(MbMfskPatternResult)));
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_energies, (size_t)a.n * nsymb * MB_NC * sizeof(double)));
+		h->mfsk_cap_buffers = a.n, h->mfsk_cap_energies = (size_t)a.n * nsymb * MB_NC;
+	}
+	MB_CUDA(h, mb_fe_p2b_full(a, s));  // (also fills the coarse prefix sums, which this branch does not use)
+	// per-capture search start = the record's mfsk_search_or_overflow (int32 #7 of every 18-int32 record)
+	MB_CUDA(h, mb_launch_mfsk_patterns(a.bbi, 0, (size_t)a.n, a.buf, 0, reinterpret_cast<const int32_t *>(d_stats) + 7, (int)(sizeof(MbReceiveStats) / 4),
+					   h->mfsk_tones[h->config - 100], m.preamble_nSymb, h->d_mfsk_energies, h->d_mfsk_out, s));
+	MB_CUDA(h, cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), s));
+	MB_CUDA(h, mb_launch_mfsk_rx_decide(h->d_mfsk_out, a.energy_part, nblk, a.buf, a.pre, a.S, a.buffer_Nsymb, h->fe_const.fc, a.st, d_stats, a.n, w.counters, s));
+	MB_CUDA(h, cudaMemcpyAsync(w.h_counters, w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	MB_CUDA(h, cudaStreamSynchronize(s));
+	h->launches += 7;
+	h->fe_rounds++;
+	const int n_slots = w.h_counters[0];
+	if (n_slots > 0) {
+		MB_CUDA(h, mb_fe_extract_data(a, s));
+		h->launches++;
+		int rc = launch_demod(h, w.frames, (size_t)n_slots, w.llr, w.tail_stats, nullptr, 0, s);
+		if (rc) return rc;
+		rc = launch_ldpc(h, w.llr, (size_t)n_slots, w.tail_payload, w.tail_stats, s);
+		if (rc) return rc;
+		MB_CUDA(h, mb_launch_mfsk_rx_finish(a.st, w.tail_stats, w.tail_payload, m.frame_bytes, a.payload_out, d_stats, a.n, s));
+		h->launches++;
+	}
 	MB_CUDA(h, cudaStreamSynchronize(s));
 	return MERCURY_B200_OK;
 }
@@ -727,13 +773,13 @@ int mercury_b200_receive_byte_batch_device(mercury_b200_t *h, const void *d_x, i
 	if (n == 0) return MERCURY_B200_OK;
 	if (!d_x || !d_payload || !d_stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	const MbMode &m = cur_mode(h);
-	if (m.M == 200) return fail(h, MERCURY_B200_EINVAL, "receive_byte front-end: OFDM configurations only (the MFSK branch of receive_byte() is not built)");
 	const int buf = fe_capture_samples(m);
 	const size_t ss = fe_sample_bytes(fmt);
-	rc = fe_ensure(h, std::min(n, h->fe_chunk), buf, m, false, 0);
+	const size_t dchunk = m.M == 200 ? std::min<size_t>(h->fe_chunk, 128) : h->fe_chunk;  // ROBUST captures are 4-8x longer (11 MB of fp64 base-band each)
+	rc = fe_ensure(h, std::min(n, dchunk), buf, m, false, 0);
 	if (rc) return rc;
-	for (size_t done = 0; done < n; done += h->fe_chunk) {
-		const size_t c = std::min(h->fe_chunk, n - done);
+	for (size_t done = 0; done < n; done += dchunk) {
+		const size_t c = std::min(dchunk, n - done);
 		rc = fe_run(h, static_cast<const uint8_t *>(d_x) + done * buf * ss, fmt, c, static_cast<uint8_t *>(d_payload) + done * m.frame_bytes,
 			    static_cast<MbReceiveStats *>(d_stats) + done, false, static_cast<cudaStream_t>(stream));
 		if (rc) return rc;
@@ -749,7 +795,6 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 	if (n == 0) return MERCURY_B200_OK;
 	if (!x || !payload || !stats || fe_sample_bytes(fmt) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
 	const MbMode &m = cur_mode(h);
-	if (m.M == 200) return fail(h, MERCURY_B200_EINVAL, "receive_byte front-end: OFDM configurations only (the MFSK branch of receive_byte() is not built)");
 	const int buf = fe_capture_samples(m);
 	const size_t ss = fe_sample_bytes(fmt);
 	// chunks of host_chunk captures: the H2D copy of chunk i+1 (copy stream, second staging buffer) runs while the kernels of chunk i
@@ -757,6 +802,7 @@ int mercury_b200_receive_byte_batch(mercury_b200_t *h, const void *x, int fmt, s
 	// chunk schedule: a small first chunk (its copy is the only one nothing hides), then host_chunk captures (scaled up for the
 	// narrower sample formats so that a chunk stays around 100-200 MB)
 	size_t big = h->fe.host_chunk * (ss <= 2 ? 2 : 1);
+	if (m.M == 200) big = 64;  // ROBUST captures are 4-8x longer
 	big = std::min(std::min(n, h->fe_chunk), big);
 	const size_t first = std::min(big, std::max<size_t>(64, big / 4));
 	rc = fe_ensure(h, big, buf, m, baseband_dbg != nullptr, big * buf * ss);
@@ -1021,7 +1067,7 @@ int mercury_b200_mfsk_patterns_batch(mercury_b200_t *h, const void *bbi, int com
 	for (size_t done = 0; done < n_buffers; done += chunk) {
 		const size_t c = std::min(chunk, n_buffers - done);
 		MB_CUDA(h, cudaMemcpy(h->d_mfsk_in, static_cast<const uint8_t *>(bbi) + done * n_samples * es, c * n_samples * es, cudaMemcpyHostToDevice));
-		MB_CUDA(h, mb_launch_mfsk_patterns(h->d_mfsk_in, complex_format == MERCURY_B200_SAMPLES_F32, c, n_samples, search_start_symb,
+		MB_CUDA(h, mb_launch_mfsk_patterns(h->d_mfsk_in, complex_format == MERCURY_B200_SAMPLES_F32, c, n_samples, search_start_symb, nullptr, 0,
 						   h->mfsk_tones[h->config - 100], m.preamble_nSymb, h->d_mfsk_energies, h->d_mfsk_out, nullptr));
 		h->launches += 2;
 		MB_CUDA(h, cudaMemcpy(out + done, h->d_mfsk_out, c * sizeof(MbMfskPatternResult), cudaMemcpyDeviceToHost));

@@ -929,7 +929,7 @@ __global__ void k_fe_finish(const MbFeState *__restrict__ st_all, MbReceiveStats
 	const MbFeState &st = st_all[b];
 	MbReceiveStats r;
 	r.iterations_done = st.iterations_done, r.delay = st.delay, r.delay_of_last_decoded_message = st.last_delay, r.sync_trials = st.sync_trials;
-	r.message_decoded = st.message_decoded, r.crc = st.crc, r.all_zeros = st.all_zeros, r.reserved = 0;
+	r.message_decoded = st.message_decoded, r.crc = st.crc, r.all_zeros = st.all_zeros, r.mfsk_search_or_overflow = 0;
 	r.freq_offset = st.freq_offset, r.freq_offset_of_last_decoded_message = st.last_freq, r.SNR = st.SNR;
 	r.signal_stregth_dbm = st.signal_dbm, r.coarse_metric = st.coarse_metric;
 	out[b] = r;
@@ -1036,6 +1036,15 @@ static cudaError_t fe_extract_t(const MbFeArgs &a, cudaStream_t s)
 	return cudaGetLastError();
 }
 
+// the data kernel alone (the MFSK branch has no Moose step: the carrier stays at fc)
+template <typename T>
+static cudaError_t fe_extract_data_t(const MbFeArgs &a, cudaStream_t s)
+{
+	const int outs = (a.dbg_bb ? a.S + a.pre : a.S) * MB_NOFDM;
+	k_fe_extract_tiles<T><<<dim3((outs + 255) / 256, a.n), 256, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.frames, a.dbg_bb, a.pre, a.S);
+	return cudaGetLastError();
+}
+
 #define MB_FE_DISPATCH(fn, ...)                                      \
 	switch (a.x_format) {                                        \
 	case 0: return fn<double>(__VA_ARGS__);                      \
@@ -1048,6 +1057,7 @@ static cudaError_t fe_extract_t(const MbFeArgs &a, cudaStream_t s)
 cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_p2b_full_t, a, s); }
 cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s) { MB_FE_DISPATCH(fe_step_t, a, run_sc, s); }
 cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_extract_t, a, s); }
+cudaError_t mb_fe_extract_data(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_extract_data_t, a, s); }
 
 cudaError_t mb_fe_begin(const MbFeArgs &a, const MbReceiveStats *d_stats_in, cudaStream_t s)
 {

@@ -115,7 +115,7 @@ struct MbFeArgs {
 // Mirrors mercury_b200_receive_stats (include/mercury_b200.h); 72 bytes.
 struct MbReceiveStats {
 	int32_t iterations_done, delay, delay_of_last_decoded_message, sync_trials;
-	int32_t message_decoded, crc, all_zeros, reserved;
+	int32_t message_decoded, crc, all_zeros, mfsk_search_or_overflow;
 	double freq_offset, freq_offset_of_last_decoded_message, SNR, signal_stregth_dbm, coarse_metric;
 };
 
@@ -127,7 +127,8 @@ void mb_fe_host_carrier(const MbFeConst &k, double *cs, int n);
 cudaError_t mb_fe_init(const MbFeConst &k);
 cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s);
 cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s);  // [k_fe_window, k_fe_sc,] k_fe_decide
-cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s);
+cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s);       // k_fe_moose + k_fe_extract_tiles
+cudaError_t mb_fe_extract_data(const MbFeArgs &a, cudaStream_t s);  // k_fe_extract_tiles only
 
 // ---------------------------------------------------------------------------------------------------------------------
 // TX chain (mb_tx.cu): payload bytes -> pass-band frames, transmit_byte(SINGLE_MESSAGE).
@@ -189,5 +190,10 @@ struct MbMfskPatternResult {
 };
 
 cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStream_t s);
-cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const MbMfsk &t, int pre,
-				    double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s);
+// search start: one value for all buffers, or (d_search_start_each != NULL) one int32 per buffer every each_stride int32s
+cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const int32_t *d_search_start_each,
+				    int each_stride, const MbMfsk &t, int pre, double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s);
+cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int buffer_Nsymb, double fc,
+				     MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s);
+cudaError_t mb_launch_mfsk_rx_finish(const MbFeState *st, const MbRxStats *tail_stats, const uint8_t *tail_payload, int frame_bytes, uint8_t *payload_out,
+				     MbReceiveStats *stats, int n, cudaStream_t s);

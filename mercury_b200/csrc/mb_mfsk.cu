@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(256) k_mfsk_energies(const T2 *__restrict__ bb
 }
 
 // one CTA per buffer: time_sync_mfsk + detect_ack_pattern (ACK and BREAK) over the per-symbol carrier energies
-__global__ void __launch_bounds__(256) k_mfsk_patterns(const double *__restrict__ en_all, int nsymb, int n_samples, int search_start_symb, const MbMfsk t, int pre,
+__global__ void __launch_bounds__(256) k_mfsk_patterns(const double *__restrict__ en_all, int nsymb, int n_samples, int search_start_common,
+							 const int32_t *__restrict__ search_start_each, int each_stride, const MbMfsk t, int pre,
 							 MbMfskPatternResult *__restrict__ out)
 {
 	__shared__ double red_v[256];
 	__shared__ int red_i[256], red_m[256];
 	const int b = blockIdx.x, tid = threadIdx.x;
+	const int search_start_symb = search_start_each ? search_start_each[(size_t)b * each_stride] : search_start_common;
 	const double *en = en_all + (size_t)b * nsymb * MB_NC;
 	auto e_total = [&](int s) {
 		double tot = 0;
@@ -235,14 +237,89 @@ cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStrea
 	return cudaGetLastError();
 }
 
-cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const MbMfsk &t, int pre,
-				    double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s)
+cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const int32_t *d_search_start_each,
+				    int each_stride, const MbMfsk &t, int pre, double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s)
 {
 	const int nsymb = n_samples / MB_FE_SYM;
 	if (nsymb <= 0) return cudaErrorInvalidValue;
 	const dim3 grid(nsymb, (unsigned)n_buffers);
 	if (is_f32) k_mfsk_energies<float2><<<grid, 256, 0, s>>>(static_cast<const float2 *>(d_bbi), n_samples, nsymb, d_energies);
 	else k_mfsk_energies<double2><<<grid, 256, 0, s>>>(static_cast<const double2 *>(d_bbi), n_samples, nsymb, d_energies);
-	k_mfsk_patterns<<<(unsigned)n_buffers, 256, 0, s>>>(d_energies, nsymb, n_samples, search_start_symb, t, pre, d_out);
+	k_mfsk_patterns<<<(unsigned)n_buffers, 256, 0, s>>>(d_energies, nsymb, n_samples, search_start_symb, d_search_start_each, each_stride, t, pre, d_out);
+	return cudaGetLastError();
+}
+
+namespace {
+
+// ---- the MFSK branch of receive_byte() around the kernels above (telecom_system.cc:646-716, 928-943, 1020-1031, 1343-1367) ----
+// after the tone-preamble sync: frame-completeness check, bounds, clamp; hands the capture to k_fe_extract_tiles + the MFSK tail
+__global__ void k_mfsk_rx_decide(const MbMfskPatternResult *__restrict__ pat, const double *__restrict__ energy_part, int nblk, int buf, int pre, int S,
+				 int buffer_Nsymb, double fc, MbFeState *__restrict__ st_all, MbReceiveStats *__restrict__ stats, int n, int *__restrict__ counters)
+{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n) return;
+	MbFeState st;
+	memset(&st, 0, sizeof(st));
+	MbReceiveStats r = stats[b];
+	double e = 0;
+	for (int i = 0; i < nblk; i++) e += energy_part[(size_t)b * nblk + i];
+	r.signal_stregth_dbm = 10.0 * log10((e / buf) / 0.001);
+	r.iterations_done = 0, r.sync_trials = 0, r.message_decoded = 0, r.crc = 0, r.all_zeros = 0, r.SNR = 0, r.freq_offset = 0, r.coarse_metric = 0;
+	int delay = pat[b].time_sync_delay;
+	int pream = delay / MB_FE_SYM;
+	if (pream < 1) pream = 1;
+	r.mfsk_search_or_overflow = 0;
+	st.slot = -1;
+	const int frame_end = delay + (pre + S) * MB_FE_SYM;
+	if (frame_end > buf) {
+		r.mfsk_search_or_overflow = (frame_end - buf + MB_FE_SYM - 1) / MB_FE_SYM;  // frame_overflow_symbols (:702-715)
+	} else if (pream > pre && pream < buffer_Nsymb - (S + pre)) {
+		if (delay < 0) delay = 0;
+		const int max_delay = buf - (MB_NOFDM * (S + pre)) * 4;
+		if (delay > max_delay) delay = max_delay;
+		st.extract_pending = 1, st.cur_kind = 1, st.cur_f = fc;
+		st.slot = atomicAdd(&counters[0], 1);
+	}
+	st.delay = delay;
+	r.delay = delay;
+	st_all[b] = st;
+	stats[b] = r;
+}
+
+__global__ void k_mfsk_rx_finish(const MbFeState *__restrict__ st_all, const MbRxStats *__restrict__ tail_stats, const uint8_t *__restrict__ tail_payload,
+				 int frame_bytes, uint8_t *__restrict__ payload_out, MbReceiveStats *__restrict__ stats, int n)
+{
+	const int b = blockIdx.x;
+	if (b >= n) return;
+	const MbFeState &st = st_all[b];
+	if (st.slot < 0) return;
+	const MbRxStats ts = tail_stats[st.slot];
+	for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) payload_out[(size_t)b * frame_bytes + i] = tail_payload[(size_t)st.slot * frame_bytes + i];
+	if (threadIdx.x == 0) {
+		MbReceiveStats r = stats[b];
+		r.iterations_done = ts.iterations_done, r.crc = ts.crc, r.all_zeros = ts.all_zeros;
+		if (ts.message_decoded) {
+			r.SNR = 0.0, r.message_decoded = 1;  // :1362-1367
+			r.delay_of_last_decoded_message = st.delay;  // :1427 (the frequency-offset fields are not touched in MFSK modes, :1421)
+		} else {
+			r.SNR = -99.9, r.message_decoded = 0, r.sync_trials = 1;  // :1343-1359; the trial loop ends after one trial (:938-943)
+		}
+		stats[b] = r;
+	}
+}
+
+}  // namespace
+
+cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int buffer_Nsymb, double fc,
+				     MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s)
+{
+	k_mfsk_rx_decide<<<(n + 127) / 128, 128, 0, s>>>(pat, energy_part, nblk, buf, pre, S, buffer_Nsymb, fc, st, stats, n, counters);
+	return cudaGetLastError();
+}
+
+cudaError_t mb_launch_mfsk_rx_finish(const MbFeState *st, const MbRxStats *tail_stats, const uint8_t *tail_payload, int frame_bytes, uint8_t *payload_out,
+				     MbReceiveStats *stats, int n, cudaStream_t s)
+{
+	k_mfsk_rx_finish<<<n, 64, 0, s>>>(st, tail_stats, tail_payload, frame_bytes, payload_out, stats, n);
 	return cudaGetLastError();
 }

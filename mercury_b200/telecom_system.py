@@ -26,7 +26,7 @@ STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("crc", "<i4"), ("all_zeros"
 assert STATS_DTYPE.itemsize == C.sizeof(RxStats) == 32
 # mercury_b200_receive_stats (the whole receive_byte(), pass-band in): st_receive_stats of the OFDM branch
 RECEIVE_STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("delay", "<i4"), ("delay_of_last_decoded_message", "<i4"), ("sync_trials", "<i4"),
-                                ("message_decoded", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("reserved", "<i4"),
+                                ("message_decoded", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("mfsk_search_or_overflow", "<i4"),
                                 ("freq_offset", "<f8"), ("freq_offset_of_last_decoded_message", "<f8"), ("SNR", "<f8"),
                                 ("signal_stregth_dbm", "<f8"), ("coarse_metric", "<f8")])
 assert RECEIVE_STATS_DTYPE.itemsize == C.sizeof(ReceiveStats) == 72

@@ -1202,8 +1202,74 @@ static double moose(const mo_mode *m, const double complex *in, double carrier_w
  *              buffer samples, frame_bytes;  state[2] in/out: delay_of_last_decoded_message, freq_offset_of_last_decoded_message
  *   baseband_out (optional): the (pre+Nsymb)*272 post-synchronisation samples the last trial's tail consumed.
  */
+int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int search_start_symb);
+
+/* The MFSK branch of receive_byte() (mfsk_fixed_delay < 0, ctrl mode off): telecom_system.cc:646-716, 928-943, 1020-1031, 1081-1198,
+ * 1296-1367.  One trial: tone-preamble sync on the time-sync base-band (symbol grid), frame-completeness check, data-filter mix +
+ * decimation at that delay, no frequency correction, the MFSK tail.  state[2] in: first symbol of the preamble search
+ * (receive_stats.mfsk_search_raw - nUnder_processing_events); state[3] out: frame_overflow_symbols. */
+static void mo_receive_byte_mfsk(const mo_mode *m, const double *passband, int *out, double *stats, double *state, double complex *baseband_out)
+{
+	const mo_frontend *f = &m->fe;
+	int rate = f->interp, sym = m->Nofdm * rate, buf = m->Nofdm * f->buffer_Nsymb * rate, pre = m->preamble_nSymb, S = m->Nsymb;
+	int frame_dec = m->Nofdm * (S + pre);
+	double complex *bbi = malloc(sizeof(double complex) * buf), *scratch = malloc(sizeof(double complex) * buf);
+	double complex *bb = calloc(frame_dec, sizeof(double complex));
+	double tail_stats[8] = {0};
+	int payload[MO_N / 8];
+	mo_rx_out ro;
+	memset(&ro, 0, sizeof(ro));
+	ro.payload = payload, ro.stats = tail_stats;
+	int last_delay = (int)state[0], message_decoded = 0, sync_trials = 0, iterations = 0, crc = 0, all_zeros = 0, overflow = 0;
+	double SNR = 0;
+	p2b(m, passband, buf, bbi, f->fc, 0, scratch);
+	double ss = 0;
+	for (int i = 0; i < buf; i++) ss += pow(creal(bbi[i]), 2) + pow(cimag(bbi[i]), 2);
+	ss /= buf;
+	double signal_dbm = 10.0 * log10(ss / 0.001);
+	int search_start = (int)state[2];
+	if (search_start < 0) search_start = 0;
+	int delay = mo_time_sync_mfsk(m, bbi, buf, search_start); /* :686 */
+	int pream_symb_loc = delay / sym;
+	if (pream_symb_loc < 1) pream_symb_loc = 1;
+	int frame_end = delay + (pre + S) * sym; /* :702-715 */
+	if (frame_end > buf) {
+		overflow = (frame_end - buf + sym - 1) / sym;
+	} else {
+		int lower = pre, upper = f->buffer_Nsymb - (S + pre);
+		if (pream_symb_loc > lower && pream_symb_loc < upper) {
+			if (delay < 0) delay = 0;
+			int max_delay = buf - frame_dec * rate;
+			if (delay > max_delay) delay = max_delay;
+			p2b(m, passband, buf, bbi, f->fc, 1, scratch);
+			for (int i = 0, k = 0; i < frame_dec * rate; i += rate) bb[k++] = bbi[delay + i];
+			mo_rx_tail(m, bb + pre * m->Nofdm, &ro);
+			iterations = (int)tail_stats[0], crc = (int)tail_stats[1], all_zeros = (int)tail_stats[2];
+			for (int i = 0; i < m->frame_bytes; i++) out[i] = payload[i];
+			if (!(int)tail_stats[3]) {
+				SNR = -99.9;
+				sync_trials++;
+			} else {
+				SNR = 0.0;
+				message_decoded = 1;
+				last_delay = delay;
+			}
+		}
+	}
+	double v[12] = {iterations, crc, all_zeros, message_decoded, SNR, delay, sync_trials, 0, 0, signal_dbm, buf, m->frame_bytes};
+	memcpy(stats, v, sizeof(v));
+	state[0] = last_delay;
+	state[3] = overflow;
+	if (baseband_out) memcpy(baseband_out, bb, sizeof(double complex) * frame_dec);
+	free(bbi), free(scratch), free(bb);
+}
+
 void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats, double *state, double complex *baseband_out)
 {
+	if (m->M == 200) {
+		mo_receive_byte_mfsk(m, passband, out, stats, state, baseband_out);
+		return;
+	}
 	const mo_frontend *f = &m->fe;
 	int rate = f->interp, sym = m->Nofdm * rate, buf = m->Nofdm * f->buffer_Nsymb * rate;
 	int pre = m->preamble_nSymb, S = m->Nsymb;
@@ -1394,6 +1460,7 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 	stats[11] = m->frame_bytes;
 	state[0] = last_delay;
 	state[1] = last_freq;
+	state[3] = 0;
 	if (baseband_out) memcpy(baseband_out, bb, sizeof(double complex) * frame_dec);
 	free(bbi);
 	free(scratch);
@@ -1406,7 +1473,7 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags)
 {
 	int buf = m->Nofdm * m->fe.buffer_Nsymb * m->fe.interp, out[MO_N / 8];
-	double stats[12], state[2];
+	double stats[12], state[4] = {0};
 	struct timespec t0, t1;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	for (int c = 0; c < n_calls; c++) {

@@ -88,9 +88,50 @@ def test_pattern_detectors_against_oracle(ts, cfg):
         assert abs(float(res32["ack_metric"][i]) - o.detect_ack_pattern(w, False)[0]) <= 1e-9 * max(1.0, float(res32["ack_metric"][i]))
 
 
-def test_pass_band_entry_points_reject_robust_modes(ts):
+def test_transmit_rejects_robust_modes(ts):
     ts.load_configuration(100, 50)
     with pytest.raises(mb.MercuryB200Error):
-        ts.receive_byte_batch(np.zeros(ts.get_capture_samples() if ts.get_capture_samples() > 0 else 1088, np.float32))
-    with pytest.raises(mb.MercuryB200Error):
         ts.transmit_byte([1, 2, 3])
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_robust_receive_byte_against_reference(ts, cfg):
+    """The MFSK branch of the whole receive_byte(): pass-band captures holding the reference's own transmit_byte frame (clean, noisy,
+    very noisy, running past the end of the buffer, restricted search start) -- delay, verdict, payload, overflow count exact."""
+    if not ref.available():
+        pytest.skip("frames come from the reference's transmit_byte (oracle/_ref not on this box)")
+    r = ref.Ref(cfg, 50)
+    ts.load_configuration(cfg, 50)
+    n = r.capture_samples()
+    assert ts.get_capture_samples() == n
+    rng = np.random.default_rng(cfg)
+    caps, wants, states = [], [], mb.new_receive_stats(5)
+    for case, sigma in enumerate((1e-4, 0.05, 0.3, 0.01, 0.01)):
+        pl = rng.integers(0, 256, r.frame_bytes)
+        tx = r.transmit_byte(pl)
+        d = int(rng.integers(6, r.buffer_Nsymb - (r.Nsymb + 4) - 2)) * 1088 + int(rng.integers(0, 60))
+        if case == 3:
+            d = (r.buffer_Nsymb - (r.Nsymb + 4) + 3) * 1088
+        L = min(tx.size, n - d)
+        cap = np.zeros(n)
+        cap[d:d + L] += tx[:L]
+        cap = (cap + rng.normal(0, sigma, n)).astype(np.float32)
+        start = 3 if case == 4 else 0
+        states["mfsk_search_or_overflow"][case] = start
+        caps.append(cap)
+        wants.append((r.receive_byte2(cap.astype(np.float64), search_start_symb=start), pl))
+    payload, st, _ = ts.receive_byte_batch(np.stack(caps), states)
+    n_dec = 0
+    for i, (o, pl) in enumerate(wants):
+        assert int(st["delay"][i]) == o["delay"] and int(st["message_decoded"][i]) == o["decoded"], (cfg, i)
+        assert int(st["sync_trials"][i]) == o["sync_trials"] and int(st["iterations_done"][i]) == o["iterations"], (cfg, i)
+        assert int(st["crc"][i]) == o["crc"] and int(st["all_zeros"][i]) == o["all_zeros"]
+        assert int(st["mfsk_search_or_overflow"][i]) == o["frame_overflow_symbols"], (cfg, i)
+        assert int(st["delay_of_last_decoded_message"][i]) == o["last_delay"]
+        assert float(st["SNR"][i]) == pytest.approx(o["snr"], abs=1e-6)
+        assert abs(float(st["signal_stregth_dbm"][i]) - o["signal_dbm"]) <= 1e-9
+        assert np.array_equal(payload[i].astype(np.int32), o["payload"]), (cfg, i)
+        if o["decoded"]:
+            assert np.array_equal(payload[i], np.asarray(pl, np.uint8))
+            n_dec += 1
+    assert n_dec == 4 and int(st["mfsk_search_or_overflow"][3]) == 3

@@ -56,3 +56,35 @@ def test_mfsk_pattern_functions_bit_exact(cfg):
             assert matched >= 14 and m > 8 and r.detect_ack_pattern(buf, True)[0] < m / 2
         if kind == "frame":
             assert r.time_sync_mfsk(buf) == (pos // (r.Nofdm * 4)) * r.Nofdm * 4
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_mfsk_receive_byte_bit_exact(cfg):
+    """The MFSK branch of the whole receive_byte() (tone-preamble sync, frame-completeness check, one trial, no frequency correction)
+    on pass-band captures holding the reference's own transmit_byte frame."""
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    n = r.capture_samples()
+    rng = np.random.default_rng(cfg)
+    n_dec = 0
+    for case, sigma in enumerate((1e-4, 0.05, 0.3, 0.01, 0.01)):
+        pl = rng.integers(0, 256, r.frame_bytes)
+        tx = r.transmit_byte(pl)
+        d = int(rng.integers(6, r.buffer_Nsymb - (r.Nsymb + 4) - 2)) * 1088 + int(rng.integers(0, 60))
+        if case == 3:
+            d = (r.buffer_Nsymb - (r.Nsymb + 4) + 3) * 1088  # the frame runs past the end of the buffer -> frame_overflow_symbols
+        L = min(tx.size, n - d)
+        cap = np.zeros(n)
+        cap[d:d + L] += tx[:L]
+        cap = (cap + rng.normal(0, sigma, n)).astype(np.float32).astype(np.float64)
+        start = 3 if case == 4 else 0
+        a, b = r.receive_byte2(cap, search_start_symb=start), p.receive_byte2(cap, search_start_symb=start)
+        for k in ref.STAT12:
+            assert a[k] == b[k], (case, k, a[k], b[k])
+        assert a["frame_overflow_symbols"] == b["frame_overflow_symbols"] and a["last_delay"] == b["last_delay"]
+        assert np.array_equal(a["payload"], b["payload"])
+        if a["decoded"]:
+            assert np.array_equal(a["payload"], pl) and np.array_equal(a["baseband"], b["baseband"])
+            n_dec += 1
+        if case == 3:
+            assert a["frame_overflow_symbols"] == 3 and not a["decoded"]
+    assert n_dec == 4
