@@ -70,10 +70,10 @@ void fe_free(FeWork &w);
 namespace {
 // TX chain (mb_tx.cu): per-mode tables built lazily on the first transmit of the mode, plus the batch workspace.
 struct TxWork {
-	bool built[MB_NMODES] = {};
-	MbTxMode mode_host[MB_NMODES];
-	MbTxMode *mode_dev[MB_NMODES] = {};
-	uint8_t *tables[MB_NMODES] = {};
+	bool built[MB_NMODES + 3] = {};  // + ROBUST_0..2
+	MbTxMode mode_host[MB_NMODES + 3];
+	MbTxMode *mode_dev[MB_NMODES + 3] = {};
+	uint8_t *tables[MB_NMODES + 3] = {};
 	size_t cap = 0, cap_total = 0;
 	uint8_t *payload = nullptr, *dbg_cw = nullptr;
 	unsigned long long *start = nullptr;
@@ -859,7 +859,7 @@ namespace {
 
 void tx_free(TxWork &w)
 {
-	for (int i = 0; i < MB_NMODES; i++) {
+	for (int i = 0; i < MB_NMODES + 3; i++) {
 		if (w.mode_dev[i]) cudaFree(w.mode_dev[i]);
 		if (w.tables[i]) cudaFree(w.tables[i]);
 	}
@@ -871,11 +871,11 @@ void tx_free(TxWork &w)
 }
 
 int tx_total(const MbMode &m) { return (m.Nsymb + m.preamble_nSymb) * MB_FE_SYM; }
+int tx_slot(const mercury_b200_t *h) { return is_mfsk_config(h->config) ? MB_NMODES + h->config - 100 : h->config; }
 
 int tx_ensure_mode(mercury_b200_t *h)
 {
 	TxWork &w = h->tx;
-	if (is_mfsk_config(h->config)) return fail(h, MERCURY_B200_EINVAL, "transmit_byte: OFDM configurations only");
 	if (!w.init_done) {
 		if (!h->fe_ready) {
 			mb_fe_host_const(&h->fe_const);
@@ -887,10 +887,12 @@ int tx_ensure_mode(mercury_b200_t *h)
 		MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
 		w.init_done = true;
 	}
-	const int c = h->config;
+	const int c = tx_slot(h);
 	if (w.built[c]) return MERCURY_B200_OK;
 	std::vector<uint8_t> bytes;
-	const std::string e = mb_tx_build(h->blob, c, h->fe_const, &w.mode_host[c], &bytes);
+	const std::string e = is_mfsk_config(h->config)
+				      ? mb_tx_build_mfsk(h->blob, cur_mode(h), h->mfsk_tones[h->config - 100], h->fe_const, &w.mode_host[c], &bytes)
+				      : mb_tx_build(h->blob, c, h->fe_const, &w.mode_host[c], &bytes);
 	if (!e.empty()) return fail(h, MERCURY_B200_EINVAL, e);
 	MB_CUDA(h, cudaMalloc(&w.tables[c], bytes.size()));
 	MB_CUDA(h, cudaMemcpy(w.tables[c], bytes.data(), bytes.size(), cudaMemcpyHostToDevice));
@@ -928,9 +930,10 @@ int tx_ensure_work(mercury_b200_t *h, size_t n, int total, bool want_cw)
 int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long *d_start, size_t n, void *d_out, bool out_f32, uint8_t *d_cw, cudaStream_t s)
 {
 	TxWork &w = h->tx;
-	const int c = h->config;
+	const int c = tx_slot(h);
 	MbTxArgs a;
 	memset(&a, 0, sizeof(a));
+	a.tone = is_mfsk_config(h->config) ? &h->mfsk_tones[h->config - 100] : nullptr;
 	a.tm = w.mode_dev[c], a.tm_host = &w.mode_host[c], a.tables = w.tables[c];
 	a.payload = d_payload, a.start_sample = d_start, a.n = (int)n, a.out_f32 = out_f32;
 	a.bb = w.bb, a.pb = w.pb, a.p1 = w.p1, a.power_part = w.power_part, a.out = d_out, a.dbg_cw = d_cw;
@@ -980,7 +983,7 @@ int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_pay
 	if (rc) return rc;
 	const MbMode &m = cur_mode(h);
 	const int total = tx_total(m);
-	const size_t chunk = std::min<size_t>(n, 8192), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	const size_t chunk = std::min<size_t>(n, m.M == 200 ? 512 : 8192), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
 	rc = tx_ensure_work(h, chunk, total, false);
 	if (rc) return rc;
 	for (size_t done = 0; done < n; done += chunk) {
@@ -1005,7 +1008,7 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 	if (rc) return rc;
 	const MbMode &m = cur_mode(h);
 	const int total = tx_total(m);
-	const size_t chunk = std::min<size_t>(n, 2048), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	const size_t chunk = std::min<size_t>(n, m.M == 200 ? 256 : 2048), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
 	rc = tx_ensure_work(h, chunk, total, codeword_dbg != nullptr);
 	if (rc) return rc;
 	TxWork &w = h->tx;
@@ -1031,7 +1034,7 @@ int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, d
 	if (nBytes < 0 || nBytes > m.frame_bytes) return fail(h, MERCURY_B200_EINVAL, "message too long.. not sent.");  // telecom_system.cc:348-352
 	uint8_t pl[256] = {0};
 	for (int i = 0; i < nBytes; i++) pl[i] = (uint8_t)data[i];
-	uint64_t start = passband_start_sample ? *passband_start_sample : (uint64_t)MB_FE_SYM;
+	uint64_t start = passband_start_sample ? *passband_start_sample : (uint64_t)(m.M == 200 ? 0 : MB_FE_SYM);
 	rc = mercury_b200_transmit_byte_batch(h, pl, &start, 1, out, MERCURY_B200_SAMPLES_F64, nullptr);
 	if (rc) return rc;
 	if (passband_start_sample) *passband_start_sample = start + (uint64_t)tx_total(m);  // ofdm.cc:2313

@@ -163,9 +163,11 @@ struct MbTxArgs {
 	double *power_part;        // [n][ceil(total / 256)][2]
 	void *out;                 // [n][total] double or float
 	uint8_t *dbg_cw;           // optional [n][1600] codewords (parity tests)
+	const MbMfsk *tone;        // ROBUST (MFSK) modes: the tone plan (host pointer, passed to the kernel by value)
 };
 
 std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
+std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, const MbMfsk &t, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
 cudaError_t mb_tx_init();
 cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);
 

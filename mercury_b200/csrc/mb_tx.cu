@@ -134,6 +134,100 @@ __global__ void __launch_bounds__(256) k_tx_baseband(const MbTxMode *__restrict_
 	}
 }
 
+// ---- ROBUST (MFSK) modes: bits -> tones -> base-band symbols (telecom_system.cc:384-416,461-465,495-527; cl_mfsk::mod mfsk.cc:254-303,
+// generate_preamble :162-195).  Every symbol holds one tone per stream, so its IDFT is a sum of nStreams rotating phasors. ----
+__global__ void __launch_bounds__(256) k_tx_baseband_mfsk(const MbTxMode *__restrict__ tm_p, const uint8_t *__restrict__ tb, const MbMfsk t,
+							    const uint8_t *__restrict__ payload_all, double2 *__restrict__ bb_all, uint8_t *__restrict__ dbg_cw)
+{
+	__shared__ uint8_t cw[MB_N];
+	__shared__ uint8_t dpar[MB_N];
+	__shared__ uint8_t bytes[MB_N / 8 + 2];
+	__shared__ uint32_t wtot[8];
+	__shared__ double2 W[MB_NFFT];
+	__shared__ uint8_t tone[MB_N / 4][2];  // actual tone of (symbol, stream)
+	const MbTxMode &tm = *tm_p;
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const int fs = tm.frame_bytes, nR = tm.nReal, K = tm.K, P = tm.P;
+	const uint8_t *scr = tb + tm.off_scr;
+	const uint16_t *row_off = reinterpret_cast<const uint16_t *>(tb + tm.off_row_off), *row_var = reinterpret_cast<const uint16_t *>(tb + tm.off_row_var);
+	const uint16_t *bit_src = reinterpret_cast<const uint16_t *>(tb + tm.off_bit_src);
+	for (int i = tid; i < fs; i += 256) bytes[i] = payload_all[(size_t)b * fs + i];
+	{
+		double s, c;
+		sincospi(2.0 * tid / 256.0, &s, &c);
+		W[tid] = make_double2(c, s);
+	}
+	__syncthreads();
+	if (tid == 0) {
+		unsigned crc = 0xFFFF;
+		for (int j = 0; j < fs; j++) {
+			crc ^= bytes[j];
+			for (int i = 0; i < 8; i++) crc = (crc & 1) ? (crc >> 1) ^ 0xA001 : crc >> 1;
+		}
+		bytes[fs] = crc & 0xFF, bytes[fs + 1] = crc >> 8;
+	}
+	__syncthreads();
+	for (int i = tid; i < nR; i += 256) {
+		const int bit = i < (fs + 2) * 8 ? (bytes[i >> 3] >> (i & 7)) & 1 : 0;
+		cw[i] = (uint8_t)(bit ^ scr[i]);
+	}
+	__syncthreads();
+	for (int c = tid; c < P; c += 256) {
+		unsigned x = 0;
+		for (int e = row_off[c]; e < row_off[c + 1]; e++) x ^= cw[row_var[e]];
+		dpar[c] = (uint8_t)x;
+	}
+	__syncthreads();
+	{
+		const int per = (P + 255) / 256, c0 = tid * per, c1 = min(P, c0 + per);
+		unsigned loc = 0;
+		for (int c = c0; c < c1; c++) loc ^= dpar[c];
+		unsigned inc = loc;
+		const int lane = tid & 31, warp = tid >> 5;
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc ^= v;
+		}
+		if (lane == 31) wtot[warp] = inc;
+		__syncthreads();
+		unsigned run = inc ^ loc;
+		for (int w = 0; w < warp; w++) run ^= wtot[w];
+		for (int c = c0; c < c1; c++) {
+			run ^= dpar[c];
+			cw[K + c] = (uint8_t)run;
+		}
+	}
+	__syncthreads();
+	if (dbg_cw)
+		for (int i = tid; i < MB_N; i += 256) dbg_cw[(size_t)b * MB_N + i] = cw[i];
+	// cl_mfsk::mod: nBits interleaved bits (MSB first) -> Gray -> binary tone index, hopped by s * tone_hop_step
+	for (int q = tid; q < tm.S * t.nStreams; q += 256) {
+		const int s = q / t.nStreams, st = q % t.nStreams, off = s * tm.bps + st * t.nBits;
+		int g = 0;
+		for (int k = 0; k < t.nBits; k++) g |= cw[bit_src[off + k]] << (t.nBits - 1 - k);
+		int bin = g;
+		for (int sh = 1; sh < t.nBits; sh++) bin ^= (g >> sh);
+		if (bin >= t.M) bin = t.M - 1;
+		tone[s][st] = (uint8_t)((bin + s * t.tone_hop_step) % t.M);
+	}
+	__syncthreads();
+	double2 *bb = bb_all + (size_t)b * (tm.pre + tm.S) * MB_NOFDM;
+	for (int s = 0; s < tm.pre + tm.S; s++) {
+		double ar = 0, ai = 0;
+		for (int st = 0; st < t.nStreams; st++) {
+			const int tn = s < tm.pre ? t.preamble_tones[s % 4] : tone[s - tm.pre][st];
+			const int c = t.stream_offsets[st] + tn;
+			const int bin = c < MB_NC / 2 ? c + MB_NFFT - MB_NC / 2 : c - MB_NC / 2 + 1;
+			const double2 w = W[(bin * tid) & 255];
+			ar += w.x, ai += w.y;
+		}
+		const double sc = s < tm.pre ? tm.scale_pre : tm.scale_data;  // tone amplitude, power normalisation, output power, boosts
+		const double2 v = make_double2(ar * sc, ai * sc);
+		bb[s * MB_NOFDM + MB_NGI + tid] = v;
+		if (tid >= MB_NFFT - MB_NGI) bb[s * MB_NOFDM + tid - (MB_NFFT - MB_NGI)] = v;
+	}
+}
+
 // ---- baseband_to_passband: x4 linear interpolation inside each part (preamble / data), mix with the running carrier ----
 __global__ void __launch_bounds__(256) k_tx_mix(const MbTxMode *__restrict__ tm_p, const double2 *__restrict__ bb_all, const unsigned long long *__restrict__ start_all,
 						  double *__restrict__ pb_all, double *__restrict__ power_part, int nblk)
@@ -424,6 +518,67 @@ std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFe
 	return "";
 }
 
+// TX tables of a ROBUST (MFSK) mode: no pilots, constellation, preamble table or pre-equalisation; the interleaver map, the
+// scrambler, the check rows and the transmit FIRs remain.
+std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, const MbMfsk &t, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes)
+{
+	MbBlobHeader h;
+	memcpy(&h, blob.data(), sizeof(h));
+	const MbRate &r = h.rates[m.rate_idx];
+	const uint8_t *b = blob.data();
+	memset(tm, 0, sizeof(*tm));
+	tm->S = m.Nsymb, tm->pre = m.preamble_nSymb, tm->nData = m.nData, tm->nPilots = 0, tm->nBits = m.nBits, tm->nReal = m.nReal;
+	tm->nVirtual = m.nVirtual, tm->K = m.K, tm->P = m.P, tm->bps = m.bps, tm->M = m.M, tm->frame_bytes = m.frame_bytes;
+	tm->fc = fe.fc, tm->Ts = fe.Ts, tm->amp = fe.amp;
+	const double power_normalization = (double)(float)std::sqrt((double)(MB_NFFT * 4));
+	const double amp = std::sqrt((double)MB_NC / t.nStreams);                                        // mfsk.cc:166,262
+	const double mfsk_boost = std::sqrt((double)MB_NC / t.nStreams) * std::pow(10.0, -2.0 / 20.0);  // telecom_system.cc:511-515
+	tm->scale_data = amp / power_normalization * (std::sqrt(0.1) * mfsk_boost);
+	tm->scale_pre = amp / power_normalization * (std::sqrt(0.1) * std::sqrt(2) * mfsk_boost);
+	tm->papr_pre_lin = std::pow(10, 7 / 10.0), tm->papr_data_lin = std::pow(10, 10 / 10.0);
+	tm->start_after_init = 0;  // get_pre_equalization_channel is skipped for MFSK (telecom_system.cc:1954): the counter stays at 0
+	bytes->clear();
+	// interleaved bit j <- compacted codeword bit i with il_dst(i) = j (interleaver.cc:26-52); no virtual bits, so compacted index = codeword position
+	const int bs = m.nBits / 10, nb = m.nBits / bs;
+	std::vector<uint16_t> bit_src(m.nBits);
+	for (int i = 0; i < m.nBits; i++) bit_src[i < nb * bs ? (i % bs) * nb + i / bs : i] = (uint16_t)i;
+	tm->off_bit_src = put(*bytes, bit_src.data(), bit_src.size());
+	std::vector<uint8_t> scr(MB_N);
+	uint32_t st[35];
+	mb_srandom(st, 0);
+	for (int i = 0; i < MB_N; i++) scr[i] = (uint8_t)(mb_random(st) % 2);
+	tm->off_scr = put(*bytes, scr.data(), scr.size());
+	{
+		const uint16_t *var_of_cw = reinterpret_cast<const uint16_t *>(b + r.off_var_of_cw);
+		std::vector<uint16_t> cw_of_var(MB_N);
+		for (int i = 0; i < MB_N; i++) cw_of_var[var_of_cw[i]] = (uint16_t)i;
+		const uint8_t *cdeg = b + r.off_cdeg;
+		const uint32_t *cgbase = reinterpret_cast<const uint32_t *>(b + r.off_cgbase);
+		const uint16_t *ev = reinterpret_cast<const uint16_t *>(b + r.off_edge_var), *cos_ = reinterpret_cast<const uint16_t *>(b + r.off_check_of_sorted);
+		std::vector<std::vector<uint16_t>> rows(r.P);
+		for (int cs = 0; cs < r.P; cs++)
+			for (int k = 0; k < cdeg[cs]; k++) {
+				const uint16_t v = cw_of_var[ev[cgbase[cs >> 5] + 32 * k + (cs & 31)]];
+				const int c = cos_[cs];
+				if (v < r.K) rows[c].push_back(v);
+				else if (v != r.K + c && v != r.K + c - 1) return "check row is not {data, parity c-1, parity c}";
+			}
+		std::vector<uint16_t> off(r.P + 1, 0), var;
+		for (int c = 0; c < r.P; c++) {
+			for (uint16_t v : rows[c]) var.push_back(v);
+			off[c + 1] = (uint16_t)var.size();
+		}
+		tm->off_row_off = put(*bytes, off.data(), off.size());
+		tm->off_row_var = put(*bytes, var.data(), var.size());
+	}
+	std::vector<double> c1(kTxTaps), c2(kTxTaps);
+	fir_design_tx(true, false, fe.fc - fe.bandwidth / 2, 1000, fe.fs, c1.data());
+	fir_design_tx(false, true, fe.fc + fe.bandwidth / 2, 1000, fe.fs, c2.data());
+	tm->off_c1 = put(*bytes, c1.data(), c1.size());
+	tm->off_c2 = put(*bytes, c2.data(), c2.size());
+	return "";
+}
+
 size_t mb_tx_smem_bytes(const MbTxMode &tm) { return (size_t)((tm.pre + tm.S) * MB_NC + 256) * sizeof(double2) + MB_N + (size_t)tm.P + 16; }
 
 cudaError_t mb_tx_init()
@@ -435,7 +590,8 @@ cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s)
 {
 	const int total = (a.tm_host->pre + a.tm_host->S) * MB_FE_SYM;
 	const int nblk_mix = (total + 255) / 256;
-	k_tx_baseband<<<a.n, 256, mb_tx_smem_bytes(*a.tm_host), s>>>(a.tm, a.tables, a.payload, a.bb, a.dbg_cw);
+	if (a.tm_host->M == 200) k_tx_baseband_mfsk<<<a.n, 256, 0, s>>>(a.tm, a.tables, *a.tone, a.payload, a.bb, a.dbg_cw);
+	else k_tx_baseband<<<a.n, 256, mb_tx_smem_bytes(*a.tm_host), s>>>(a.tm, a.tables, a.payload, a.bb, a.dbg_cw);
 	k_tx_mix<<<dim3(nblk_mix, a.n), 256, 0, s>>>(a.tm, a.bb, a.start_sample, a.pb, a.power_part, nblk_mix);
 	const dim3 grid((total + kTxTile - 1) / kTxTile, a.n);
 	const double *c1 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c1), *c2 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c2);

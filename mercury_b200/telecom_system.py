@@ -189,7 +189,8 @@ class TelecomSystemB200:
         Returns (out float64[total_frame_size], counter after); passband_start_sample=None = a freshly initialised reference object."""
         d = np.asarray(list(data), np.int32)
         out = np.zeros(self.get_total_frame_size(), np.float64)
-        st = np.array([1088 if passband_start_sample is None else int(passband_start_sample)], np.uint64)
+        fresh = 0 if self.geometry["M"] == 200 else 1088  # where a freshly initialised reference object's counter stands (MFSK: no pre-equalisation pass)
+        st = np.array([fresh if passband_start_sample is None else int(passband_start_sample)], np.uint64)
         self._check(self._L.mercury_b200_transmit_byte(self._h, _vp(d), int(d.size), _vp(out), _vp(st)))
         return out, int(st[0])
 

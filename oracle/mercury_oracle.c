@@ -1569,6 +1569,16 @@ void mo_tx_init(mo_mode *m)
 	mo_tx *t = &m->tx;
 	mo_frontend *f = &m->fe;
 	int pre = m->preamble_nSymb;
+	if (m->M == 200) { /* MFSK: tone preamble (mfsk.cc:162-195), no pre-equalisation (telecom_system.cc:475-493) */
+		t->preamble_boost = sqrt(2);
+		t->output_power = 0.1;
+		t->preamble_papr = 7, t->data_papr = 10;
+		fir_design_tx(1, 0, f->fc - f->bandwidth / 2, 1000, f->fs, &t->ntaps1, t->c1);
+		fir_design_tx(0, 1, f->fc + f->bandwidth / 2, 1000, f->fs, &t->ntaps2, t->c2);
+		t->start_sample_after_init = 0; /* get_pre_equalization_channel is skipped (:1954): the counter stays where ofdm.init() left it */
+		t->ready = 1;
+		return;
+	}
 	/* the preamble is configured BEFORE the pilots (ofdm.cc:112-113): srandom(seed 1), two draws per carrier slot of the sequence */
 	mo_srandom(1);
 	double complex seq[4 * MO_NC];
@@ -1648,24 +1658,37 @@ int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, do
 	int total = (S + pre) * No * rate;
 	double complex framed[MO_MAX_CELLS], pdata[4 * MO_NC];
 	double complex *bbp = malloc(sizeof(double complex) * pre * No), *bbd = malloc(sizeof(double complex) * S * No);
-	double complex *scratch = malloc(sizeof(double complex) * S * No);
-	mo_tx_baseband(m, payload, nBytes, scratch, NULL, NULL, framed); /* bit chain + framer (:384-462) */
-	free(scratch);
-	for (int i = 0; i < pre * MO_NC; i++) pdata[i] = t->preamble[i]; /* :466-473 */
-	for (int i = 0; i < pre; i++)
-		for (int j = 0; j < MO_NC; j++) pdata[i * MO_NC + j] *= t->pre_eq[j]; /* :477-492 */
-	for (int i = 0; i < S; i++)
-		for (int j = 0; j < MO_NC; j++) framed[i * MO_NC + j] *= t->pre_eq[j];
-	for (int i = 0; i < pre; i++) symbol_mod(m, pdata + i * MO_NC, bbp + i * No); /* :495-505 */
-	for (int i = 0; i < S; i++) symbol_mod(m, framed + i * MO_NC, bbd + i * No);
+	double mfsk_boost = 1.0;
+	if (m->M == 200) { /* MFSK: tones, no pre-equalisation, drive-level boost (:411-416,461-465,507-515) */
+		const mo_mfsk *mf = &m->mfsk;
+		mo_tx_baseband(m, payload, nBytes, bbd, NULL, NULL, NULL); /* bit chain + cl_mfsk::mod + symbol_mod */
+		double amp = sqrt((double)MO_NC / mf->nStreams);
+		for (int s = 0; s < pre; s++) { /* cl_mfsk::generate_preamble: mfsk.cc:162-195 */
+			for (int k = 0; k < MO_NC; k++) pdata[k] = 0;
+			for (int st = 0; st < mf->nStreams; st++) pdata[mf->stream_offsets[st] + mf->preamble_tones[s % mf->preamble_nSymb]] = amp;
+			symbol_mod(m, pdata, bbp + s * No);
+		}
+		mfsk_boost = sqrt((double)MO_NC / mf->nStreams) * pow(10.0, -2.0 / 20.0);
+	} else {
+		double complex *scratch = malloc(sizeof(double complex) * S * No);
+		mo_tx_baseband(m, payload, nBytes, scratch, NULL, NULL, framed); /* bit chain + framer (:384-462) */
+		free(scratch);
+		for (int i = 0; i < pre * MO_NC; i++) pdata[i] = t->preamble[i]; /* :466-473 */
+		for (int i = 0; i < pre; i++)
+			for (int j = 0; j < MO_NC; j++) pdata[i * MO_NC + j] *= t->pre_eq[j]; /* :477-492 */
+		for (int i = 0; i < S; i++)
+			for (int j = 0; j < MO_NC; j++) framed[i * MO_NC + j] *= t->pre_eq[j];
+		for (int i = 0; i < pre; i++) symbol_mod(m, pdata + i * MO_NC, bbp + i * No); /* :495-505 */
+		for (int i = 0; i < S; i++) symbol_mod(m, framed + i * MO_NC, bbd + i * No);
+	}
 	float power_normalization = sqrt((double)(MO_NFFT * rate)); /* :388 */
 	for (int j = 0; j < No * pre; j++) {			     /* :517-527 */
 		bbp[j] /= power_normalization;
-		bbp[j] *= sqrt(t->output_power) * t->preamble_boost * 1.0;
+		bbp[j] *= sqrt(t->output_power) * t->preamble_boost * mfsk_boost;
 	}
 	for (int j = 0; j < No * S; j++) {
 		bbd[j] /= power_normalization;
-		bbd[j] *= sqrt(t->output_power) * 1.0;
+		bbd[j] *= sqrt(t->output_power) * mfsk_boost;
 	}
 	unsigned long start = (unsigned long)*start_sample_inout;
 	double *pb = malloc(sizeof(double) * total), *p1 = malloc(sizeof(double) * total);

@@ -88,10 +88,46 @@ def test_pattern_detectors_against_oracle(ts, cfg):
         assert abs(float(res32["ack_metric"][i]) - o.detect_ack_pattern(w, False)[0]) <= 1e-9 * max(1.0, float(res32["ack_metric"][i]))
 
 
-def test_transmit_rejects_robust_modes(ts):
-    ts.load_configuration(100, 50)
-    with pytest.raises(mb.MercuryB200Error):
-        ts.transmit_byte([1, 2, 3])
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_robust_transmit_byte_against_oracle(ts, cfg):
+    """transmit_byte(SINGLE_MESSAGE) in the ROBUST modes: tone preamble, cl_mfsk::mod, drive-level boost, no pre-equalisation."""
+    o, p = _oracle(cfg), port.Port(cfg, 50)
+    g = ts.load_configuration(cfg, 50)
+    assert ts.get_total_frame_size() == o.total_frame_size
+    rng = np.random.default_rng(300 + cfg)
+    pl = rng.integers(0, 256, (3, g["frame_bytes"])).astype(np.uint8)
+    starts = np.array([0, 777, 123456789], np.uint64)
+    out, cw = ts.transmit_byte_batch(pl, starts, want_codeword=True)
+    for i in range(3):
+        want, after = o.transmit_byte2(pl[i], int(starts[i]))
+        _, aux = p.tx_baseband(pl[i], want_aux=True)
+        assert np.array_equal(cw[i], aux["codeword"].astype(np.uint8)), (cfg, i)
+        assert np.abs(out[i] - want).max() <= 1e-9 * np.abs(want).max(), (cfg, i)
+    one, after = ts.transmit_byte([int(v) for v in pl[0]])  # default counter = a freshly initialised reference object (0 in MFSK modes)
+    assert after == o.total_frame_size and np.abs(one - out[0]).max() == 0
+
+
+@pytest.mark.parametrize("cfg,n", [(101, 48), (100, 24)])
+def test_robust_tx_channel_rx_round_trip_on_the_device(ts, cfg, n):
+    import torch
+    dev = torch.device("cuda", 0)
+    g = ts.load_configuration(cfg, 50)
+    fb, L, buf = g["frame_bytes"], ts.get_total_frame_size(), ts.get_capture_samples()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + cfg)
+    d_pl = torch.randint(0, 256, (n, fb), device=dev, dtype=torch.uint8, generator=gen)
+    d_tx = torch.empty((n, L), device=dev, dtype=torch.float32)
+    ts.transmit_byte_batch_device(d_pl, None, n, d_tx, mb.SAMPLES_F32, stream=torch.cuda.current_stream().cuda_stream)
+    symb = torch.randint(6, buf // 1088 - (g["Nsymb"] + 4) - 2, (n,), device=dev, generator=gen)
+    delays = symb * 1088 + torch.randint(0, 60, (n,), device=dev, generator=gen)
+    caps = torch.randn((n, buf), device=dev, dtype=torch.float32, generator=gen) * 0.05
+    caps[torch.arange(n, device=dev)[:, None], delays[:, None] + torch.arange(L, device=dev)[None, :]] += d_tx
+    d_st = torch.from_numpy(mb.new_receive_stats(n).view(np.uint8).reshape(n, -1)).to(dev)
+    d_out = torch.zeros((n, fb), device=dev, dtype=torch.uint8)
+    ts.receive_byte_batch_device(caps, mb.SAMPLES_F32, n, d_out, d_st, stream=torch.cuda.current_stream().cuda_stream)
+    st = d_st.cpu().numpy().view(mb.RECEIVE_STATS_DTYPE).reshape(-1)
+    assert int(st["message_decoded"].sum()) == n and torch.equal(d_out, d_pl)
+    assert np.array_equal(st["delay"], (symb * 1088).cpu().numpy())  # the tone-preamble sync works on the symbol grid
 
 
 @pytest.mark.parametrize("cfg", [100, 101, 102])

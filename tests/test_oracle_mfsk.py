@@ -88,3 +88,14 @@ def test_mfsk_receive_byte_bit_exact(cfg):
         if case == 3:
             assert a["frame_overflow_symbols"] == 3 and not a["decoded"]
     assert n_dec == 4
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_mfsk_transmit_byte_bit_exact(cfg):
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    rng = np.random.default_rng(7 + cfg)
+    pl = rng.integers(0, 256, r.frame_bytes)
+    assert np.array_equal(ref.Ref(cfg, 50).transmit_byte(pl), p.transmit_byte2(pl, 0)[0])  # a fresh reference object starts its carrier counter at 0
+    a, sa = r.transmit_byte2(pl, 4242)
+    b, sb = p.transmit_byte2(pl, 4242)
+    assert sa == sb and np.array_equal(a, b)
