@@ -202,6 +202,15 @@ int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, d
  * codeword_dbg (optional, host variant): n x 1600 LDPC codeword bits for parity tests. */
 int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n_frames, void *passband,
 				     int out_format, uint8_t *codeword_dbg);
+/* message_location (common_defines.h:197-201): SINGLE_MESSAGE = the filtered frame; NO_FILTER_MESSAGE = the clipped frame before the
+ * transmit FIRs, which is what the ARQ layer requests per frame (arq_common.cc:2224) before it filters the whole padded batch with
+ * ofdm.FIR_tx1.apply / ofdm.FIR_tx2.apply (arq_common.cc:2243-2246) = mercury_b200_fir_tx_apply.  The streaming FIRST / MIDDLE / FLUSH
+ * locations (TX_TEST's three-frame filter buffer) are not built. */
+#define MERCURY_B200_SINGLE_MESSAGE 3
+#define MERCURY_B200_NO_FILTER_MESSAGE 4
+int mercury_b200_transmit_byte_batch_ex(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n_frames, void *passband,
+					int out_format, int message_location, uint8_t *codeword_dbg);
+int mercury_b200_fir_tx_apply(mercury_b200_t *h, const double *in, size_t n_samples, double *out);
 int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n_frames, void *d_passband,
 					    int out_format, void *stream);
 

@@ -85,6 +85,8 @@ def lib():
         "mercury_b200_build_tx_tables_host": (i32, [C.c_char_p, i32, vp, vp, vp, vp]),
         "mercury_b200_transmit_byte": (i32, [vp, vp, i32, vp, vp]),
         "mercury_b200_transmit_byte_batch": (i32, [vp, vp, vp, sz, vp, i32, vp]),
+        "mercury_b200_transmit_byte_batch_ex": (i32, [vp, vp, vp, sz, vp, i32, i32, vp]),
+        "mercury_b200_fir_tx_apply": (i32, [vp, vp, sz, vp]),
         "mercury_b200_transmit_byte_batch_device": (i32, [vp, vp, vp, sz, vp, i32, vp]),
         "mercury_b200_mfsk_patterns_batch": (i32, [vp, vp, i32, sz, i32, i32, vp]),
         "mercury_b200_host_alloc": (vp, [sz]),

@@ -927,7 +927,8 @@ int tx_ensure_work(mercury_b200_t *h, size_t n, int total, bool want_cw)
 }
 
 // d_payload [n][frame_bytes], d_start [n] or NULL, d_out [n][total] (double, or float when out_f32), d_cw optional [n][1600]
-int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long *d_start, size_t n, void *d_out, bool out_f32, uint8_t *d_cw, cudaStream_t s)
+int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long *d_start, size_t n, void *d_out, bool out_f32, uint8_t *d_cw, cudaStream_t s,
+	   bool no_filter = false)
 {
 	TxWork &w = h->tx;
 	const int c = tx_slot(h);
@@ -935,7 +936,7 @@ int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long
 	memset(&a, 0, sizeof(a));
 	a.tone = is_mfsk_config(h->config) ? &h->mfsk_tones[h->config - 100] : nullptr;
 	a.tm = w.mode_dev[c], a.tm_host = &w.mode_host[c], a.tables = w.tables[c];
-	a.payload = d_payload, a.start_sample = d_start, a.n = (int)n, a.out_f32 = out_f32;
+	a.payload = d_payload, a.start_sample = d_start, a.n = (int)n, a.out_f32 = out_f32, a.no_filter = no_filter;
 	a.bb = w.bb, a.pb = w.pb, a.p1 = w.p1, a.power_part = w.power_part, a.out = d_out, a.dbg_cw = d_cw;
 	MB_CUDA(h, mb_tx_launch(a, s));
 	h->launches += 4;
@@ -996,9 +997,11 @@ int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_pay
 	return MERCURY_B200_OK;
 }
 
-int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n, void *passband, int out_format,
-				     uint8_t *codeword_dbg)
+int mercury_b200_transmit_byte_batch_ex(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n, void *passband, int out_format,
+					int message_location, uint8_t *codeword_dbg)
 {
+	if (message_location != MERCURY_B200_SINGLE_MESSAGE && message_location != MERCURY_B200_NO_FILTER_MESSAGE)
+		return fail(h, MERCURY_B200_EINVAL, "message_location must be SINGLE_MESSAGE (3) or NO_FILTER_MESSAGE (4)");
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
@@ -1016,12 +1019,40 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 		const size_t c = std::min(chunk, n - done);
 		MB_CUDA(h, cudaMemcpyAsync(w.payload, payload + done * m.frame_bytes, c * m.frame_bytes, cudaMemcpyHostToDevice, w.stream));
 		if (start_sample) MB_CUDA(h, cudaMemcpyAsync(w.start, start_sample + done, c * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream));
-		rc = tx_run(h, w.payload, start_sample ? w.start : nullptr, c, w.out, out_format == MERCURY_B200_SAMPLES_F32, codeword_dbg ? w.dbg_cw : nullptr, w.stream);
+		rc = tx_run(h, w.payload, start_sample ? w.start : nullptr, c, w.out, out_format == MERCURY_B200_SAMPLES_F32, codeword_dbg ? w.dbg_cw : nullptr, w.stream,
+			    message_location == MERCURY_B200_NO_FILTER_MESSAGE);
 		if (rc) return rc;
 		MB_CUDA(h, cudaMemcpyAsync(static_cast<uint8_t *>(passband) + done * total * ob, w.out, c * total * ob, cudaMemcpyDeviceToHost, w.stream));
 		if (codeword_dbg) MB_CUDA(h, cudaMemcpyAsync(codeword_dbg + done * MB_N, w.dbg_cw, c * MB_N, cudaMemcpyDeviceToHost, w.stream));
 		MB_CUDA(h, cudaStreamSynchronize(w.stream));
 	}
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n, void *passband, int out_format,
+				     uint8_t *codeword_dbg)
+{
+	return mercury_b200_transmit_byte_batch_ex(h, payload, start_sample, n, passband, out_format, MERCURY_B200_SINGLE_MESSAGE, codeword_dbg);
+}
+
+/* ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over one host buffer (the ARQ layer's batch filtering, arq_common.cc:2243-2246). */
+int mercury_b200_fir_tx_apply(mercury_b200_t *h, const double *in, size_t n, double *out)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (!in || !out || n == 0 || n > (size_t)1 << 30) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	rc = tx_ensure_mode(h);
+	if (rc) return rc;
+	TxWork &w = h->tx;
+	double *d = nullptr;
+	MB_CUDA(h, cudaMalloc(&d, 3 * n * sizeof(double)));
+	cudaError_t e = cudaMemcpyAsync(d, in, n * sizeof(double), cudaMemcpyHostToDevice, w.stream);
+	if (e == cudaSuccess) e = mb_tx_fir_apply(w.tables[tx_slot(h)], w.mode_host[tx_slot(h)], d, (int)n, d + n, d + 2 * n, w.stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, w.stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return cuda_fail(h, e, "fir_tx_apply");
+	h->launches += 2;
 	return MERCURY_B200_OK;
 }
 

@@ -157,7 +157,7 @@ struct MbTxArgs {
 	const uint8_t *tables;     // device: the mode's TX table buffer
 	const uint8_t *payload;    // [n][frame_bytes] zero-padded payloads
 	const unsigned long long *start_sample;  // [n] running carrier sample counter per frame, or NULL (= start_after_init)
-	int32_t n, out_f32;
+	int32_t n, out_f32, no_filter;  // no_filter: NO_FILTER_MESSAGE, stop after the PAPR clip
 	double2 *bb;               // [n][(pre + S) * 272] scaled base-band symbols
 	double *pb, *p1;           // [n][total] pass-band before / after FIR_tx1
 	double *power_part;        // [n][ceil(total / 256)][2]
@@ -170,6 +170,7 @@ std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFe
 std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, const MbMfsk &t, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
 cudaError_t mb_tx_init();
 cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);
+cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, const double *d_in, int n, double *d_tmp, double *d_out, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // MFSK row (mb_mfsk.cu): ROBUST_0..2 demodulator + tone-pattern detectors.

@@ -266,20 +266,19 @@ __global__ void __launch_bounds__(256) k_tx_mix(const MbTxMode *__restrict__ tm_
 
 // ---- one 97-tap real FIR pass (zero-phase, fir_filter.cc:189-210); pass 1 clips its input on the fly (peak_clip) ----
 template <bool CLIP, typename OUT>
-__global__ void __launch_bounds__(256) k_tx_fir(const MbTxMode *__restrict__ tm_p, const double *__restrict__ in_all, const double *__restrict__ coef_off_base,
-						  const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
+__global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_all, int total, int npre, double papr_pre_lin, double papr_data_lin,
+						  const double *__restrict__ coef_off_base, const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
 {
 	__shared__ double l[(kTxTile + kTxTaps - 1) * 5 / 4 + 2];
 	__shared__ double peak[2];
-	const MbTxMode &tm = *tm_p;
-	const int b = blockIdx.y, total = (tm.pre + tm.S) * MB_FE_SYM, npre = tm.pre * MB_FE_SYM, t0 = blockIdx.x * kTxTile;
+	const int b = blockIdx.y, t0 = blockIdx.x * kTxTile;
 	const double *in = in_all + (size_t)b * total;
 	if (CLIP) {
 		if (threadIdx.x < 2) {  // peak_allowed = sqrt(mean power of the part * 10^(papr/10))  (ofdm.cc:1570-1578)
 			double t = 0;
 			for (int k = 0; k < nblk_mix; k++) t += power_part[((size_t)b * nblk_mix + k) * 2 + threadIdx.x];
 			const int n = threadIdx.x == 0 ? npre : total - npre;
-			peak[threadIdx.x] = sqrt(t / n * (threadIdx.x == 0 ? tm.papr_pre_lin : tm.papr_data_lin));
+			peak[threadIdx.x] = sqrt(t / n * (threadIdx.x == 0 ? papr_pre_lin : papr_data_lin));
 		}
 		__syncthreads();
 	}
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(256) k_tx_fir(const MbTxMode *__restrict__ tm_
 	}
 	__syncthreads();
 	const int o = t0 + 4 * threadIdx.x;
-	if (o >= total) return;  // total is a multiple of 4
+	if (o >= total) return;
 	// output o + r, tap j uses in[o + r + 48 - j] = staged index 4 t + r + 96 - j; 4 outputs share a sliding window (see k_fe_p2b_full)
 	double acc[4] = {0, 0, 0, 0}, w[4];
 	const int base = 5 * threadIdx.x;
@@ -310,7 +309,30 @@ __global__ void __launch_bounds__(256) k_tx_fir(const MbTxMode *__restrict__ tm_
 	}
 	OUT *out = out_all + (size_t)b * total + o;
 #pragma unroll
-	for (int r = 0; r < 4; r++) out[r] = (OUT)acc[r];
+	for (int r = 0; r < 4; r++)
+		if (o + r < total) out[r] = (OUT)acc[r];
+}
+
+// NO_FILTER_MESSAGE (telecom_system.cc:537-544): the clipped pass-band frame, before the transmit FIRs
+template <typename OUT>
+__global__ void __launch_bounds__(256) k_tx_clip(const double *__restrict__ in_all, int total, int npre, double papr_pre_lin, double papr_data_lin,
+						   const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
+{
+	__shared__ double peak[2];
+	const int b = blockIdx.y;
+	if (threadIdx.x < 2) {
+		double t = 0;
+		for (int k = 0; k < nblk_mix; k++) t += power_part[((size_t)b * nblk_mix + k) * 2 + threadIdx.x];
+		const int n = threadIdx.x == 0 ? npre : total - npre;
+		peak[threadIdx.x] = sqrt(t / n * (threadIdx.x == 0 ? papr_pre_lin : papr_data_lin));
+	}
+	__syncthreads();
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= total) return;
+	const double pk = i < npre ? peak[0] : peak[1];
+	double v = in_all[(size_t)b * total + i];
+	v = v > pk ? pk : (v < -pk ? -pk : v);
+	out_all[(size_t)b * total + i] = (OUT)v;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -593,10 +615,29 @@ cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s)
 	if (a.tm_host->M == 200) k_tx_baseband_mfsk<<<a.n, 256, 0, s>>>(a.tm, a.tables, *a.tone, a.payload, a.bb, a.dbg_cw);
 	else k_tx_baseband<<<a.n, 256, mb_tx_smem_bytes(*a.tm_host), s>>>(a.tm, a.tables, a.payload, a.bb, a.dbg_cw);
 	k_tx_mix<<<dim3(nblk_mix, a.n), 256, 0, s>>>(a.tm, a.bb, a.start_sample, a.pb, a.power_part, nblk_mix);
+	const int npre = a.tm_host->pre * MB_FE_SYM;
+	const double pp = a.tm_host->papr_pre_lin, pd = a.tm_host->papr_data_lin;
+	if (a.no_filter) {
+		const dim3 g2(nblk_mix, a.n);
+		if (a.out_f32) k_tx_clip<float><<<g2, 256, 0, s>>>(a.pb, total, npre, pp, pd, a.power_part, nblk_mix, static_cast<float *>(a.out));
+		else k_tx_clip<double><<<g2, 256, 0, s>>>(a.pb, total, npre, pp, pd, a.power_part, nblk_mix, static_cast<double *>(a.out));
+		return cudaGetLastError();
+	}
 	const dim3 grid((total + kTxTile - 1) / kTxTile, a.n);
 	const double *c1 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c1), *c2 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c2);
-	k_tx_fir<true, double><<<grid, 256, 0, s>>>(a.tm, a.pb, c1, a.power_part, nblk_mix, a.p1);
-	if (a.out_f32) k_tx_fir<false, float><<<grid, 256, 0, s>>>(a.tm, a.p1, c2, nullptr, 0, static_cast<float *>(a.out));
-	else k_tx_fir<false, double><<<grid, 256, 0, s>>>(a.tm, a.p1, c2, nullptr, 0, static_cast<double *>(a.out));
+	k_tx_fir<true, double><<<grid, 256, 0, s>>>(a.pb, total, npre, pp, pd, c1, a.power_part, nblk_mix, a.p1);
+	if (a.out_f32) k_tx_fir<false, float><<<grid, 256, 0, s>>>(a.p1, total, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<float *>(a.out));
+	else k_tx_fir<false, double><<<grid, 256, 0, s>>>(a.p1, total, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<double *>(a.out));
+	return cudaGetLastError();
+}
+
+// ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over one device buffer of n doubles (the ARQ layer filters a whole padded batch of
+// NO_FILTER frames at once, arq_common.cc:2243-2246); tmp: n doubles of scratch.
+cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, const double *d_in, int n, double *d_tmp, double *d_out, cudaStream_t s)
+{
+	const dim3 grid((n + kTxTile - 1) / kTxTile, 1);
+	const double *c1 = reinterpret_cast<const double *>(tables + tm_host.off_c1), *c2 = reinterpret_cast<const double *>(tables + tm_host.off_c2);
+	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_in, n, 0, 0.0, 0.0, c1, nullptr, 0, d_tmp);
+	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0.0, 0.0, c2, nullptr, 0, d_out);
 	return cudaGetLastError();
 }

@@ -194,14 +194,23 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_transmit_byte(self._h, _vp(d), int(d.size), _vp(out), _vp(st)))
         return out, int(st[0])
 
-    def transmit_byte_batch(self, payload, start_sample=None, dtype=np.float64, want_codeword=False):
-        """payload [n, frame_bytes] uint8 -> pass-band frames [n, total_frame_size] (float64 or float32) [, codewords [n, 1600] u8]."""
+    def fir_tx_apply(self, x):
+        """ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over a host buffer of any length (the ARQ layer's batch filtering, arq_common.cc:2243-2246)."""
+        a = np.ascontiguousarray(x, np.float64)
+        out = np.zeros(a.size, np.float64)
+        self._check(self._L.mercury_b200_fir_tx_apply(self._h, _vp(a), a.size, _vp(out)))
+        return out
+
+    def transmit_byte_batch(self, payload, start_sample=None, dtype=np.float64, want_codeword=False, message_location=3):
+        """payload [n, frame_bytes] uint8 -> pass-band frames [n, total_frame_size] (float64 or float32) [, codewords [n, 1600] u8].
+        message_location: 3 = SINGLE_MESSAGE (filtered), 4 = NO_FILTER_MESSAGE (clipped, before the transmit FIRs)."""
         pl = np.ascontiguousarray(payload, np.uint8).reshape(-1, self.geometry["frame_bytes"])
         n = pl.shape[0]
         out = np.zeros((n, self.get_total_frame_size()), dtype)
         st = None if start_sample is None else np.ascontiguousarray(start_sample, np.uint64)
         cw = np.zeros((n, self.geometry["N"]), np.uint8) if want_codeword else None
-        self._check(self._L.mercury_b200_transmit_byte_batch(self._h, _vp(pl), _vp(st), n, _vp(out), _SAMPLE_FORMATS[np.dtype(dtype)], _vp(cw)))
+        self._check(self._L.mercury_b200_transmit_byte_batch_ex(self._h, _vp(pl), _vp(st), n, _vp(out), _SAMPLE_FORMATS[np.dtype(dtype)],
+                                                                int(message_location), _vp(cw)))
         return (out, cw) if want_codeword else out
 
     def transmit_byte_batch_device(self, d_payload, d_start_sample, n, d_passband, out_format, stream=0):

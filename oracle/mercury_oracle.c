@@ -1649,7 +1649,31 @@ void mo_tx_tables(mo_mode *m, double complex *preamble, int *preamble_type, doub
 
 /* transmit_byte + transmit_bit, SINGLE_MESSAGE: telecom_system.cc:342-553.  Returns total_frame_size; *start_sample is the running
  * carrier sample counter (ofdm.passband_start_sample), in and out. */
+static int transmit_byte_impl(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout, int no_filter);
+
 int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout)
+{
+	return transmit_byte_impl(m, payload, nBytes, out, start_sample_inout, 0);
+}
+
+/* message_location == NO_FILTER_MESSAGE (telecom_system.cc:537-544): the clipped pass-band frame before the transmit FIRs, what the
+ * ARQ layer asks for (arq_common.cc:2224). */
+int mo_transmit_byte_nofilter(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout)
+{
+	return transmit_byte_impl(m, payload, nBytes, out, start_sample_inout, 1);
+}
+
+/* ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over a buffer of any length (arq_common.cc:2243-2246). */
+void mo_fir_tx_apply(mo_mode *m, const double *in, int n, double *out)
+{
+	if (!m->tx.ready) mo_tx_init(m);
+	double *tmp = calloc(n, sizeof(double));
+	fir_apply_real(m->tx.c1, m->tx.ntaps1, in, tmp, n);
+	fir_apply_real(m->tx.c2, m->tx.ntaps2, tmp, out, n);
+	free(tmp);
+}
+
+static int transmit_byte_impl(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout, int no_filter)
 {
 	if (!m->tx.ready) mo_tx_init(m);
 	const mo_tx *t = &m->tx;
@@ -1696,8 +1720,12 @@ int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, do
 	b2p(m, bbd, No * S, pb + No * pre * rate, f->fc, &start);
 	peak_clip(pb, No * pre * rate, t->preamble_papr); /* :534-535 */
 	peak_clip(pb + No * pre * rate, No * S * rate, t->data_papr);
-	fir_apply_real(t->c1, t->ntaps1, pb, p1, total); /* :546-553 */
-	fir_apply_real(t->c2, t->ntaps2, p1, out, total);
+	if (no_filter) {
+		memcpy(out, pb, sizeof(double) * total);
+	} else {
+		fir_apply_real(t->c1, t->ntaps1, pb, p1, total); /* :546-553 */
+		fir_apply_real(t->c2, t->ntaps2, p1, out, total);
+	}
 	*start_sample_inout = (double)start;
 	free(bbp), free(bbd), free(pb), free(p1);
 	return total;

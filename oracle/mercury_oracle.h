@@ -114,6 +114,8 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 void mo_tx_init(mo_mode *m);
 void mo_tx_tables(mo_mode *m, double complex *preamble, int *preamble_type, double complex *pre_eq, int *ntaps, double *c1, double *c2, double *consts);
 int mo_transmit_byte(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout);
+int mo_transmit_byte_nofilter(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout);
+void mo_fir_tx_apply(mo_mode *m, const double *in, int n, double *out);
 /* MFSK pattern functions: bbi = n complex samples at the pass-band rate. */
 int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int search_start_symb);
 double mo_detect_ack_pattern(const mo_mode *m, const double complex *bbi, int n, int use_break_tones, int *matched_out);

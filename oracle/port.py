@@ -59,6 +59,9 @@ def lib():
         L.mo_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mo_transmit_byte.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mo_transmit_byte.restype = C.c_int
+        L.mo_transmit_byte_nofilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mo_transmit_byte_nofilter.restype = C.c_int
+        L.mo_fir_tx_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 

@@ -75,6 +75,9 @@ def lib():
         L.mref_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mref_transmit_byte2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_transmit_byte2.restype = C.c_int
+        L.mref_transmit_byte_nofilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mref_transmit_byte_nofilter.restype = C.c_int
+        L.mref_fir_tx_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -156,12 +159,22 @@ class FrontEndMixin:
                     output_power=k[0], preamble_boost=k[1], preamble_papr=k[2], data_papr=k[3], start_sample_after_init=int(k[4]),
                     total_frame_size=int(k[5]))
 
-    def transmit_byte2(self, payload, start_sample):
-        """transmit_byte(SINGLE_MESSAGE) from a chosen running carrier sample counter -> (passband[total_frame_size], counter after)."""
+    def fir_tx_apply(self, x):
+        """ofdm.FIR_tx1.apply then ofdm.FIR_tx2.apply over a buffer of any length (the ARQ layer's batch filtering, arq_common.cc:2243-2246)."""
+        a = np.ascontiguousarray(x, np.float64)
+        out = np.zeros(a.size, np.float64)
+        getattr(self._felib(), self._fe + "fir_tx_apply")(self.h, _p(a), a.size, _p(out))
+        return out
+
+    def transmit_byte2(self, payload, start_sample, no_filter=False):
+        """transmit_byte(SINGLE_MESSAGE | NO_FILTER_MESSAGE) from a chosen running carrier sample counter -> (passband[total_frame_size], counter after)."""
         pl = np.asarray(list(payload), np.int32)
         out = np.zeros(self.total_frame_size + 16, np.float64)
         st = np.array([float(start_sample)], np.float64)
-        name = "mref_transmit_byte2" if self._fe == "mref_" else "mo_transmit_byte"
+        if no_filter:
+            name = self._fe + "transmit_byte_nofilter"
+        else:
+            name = "mref_transmit_byte2" if self._fe == "mref_" else "mo_transmit_byte"
         n = getattr(self._felib(), name)(self.h, _p(pl), len(pl), _p(out), _p(st))
         return out[:n], int(st[0])
 

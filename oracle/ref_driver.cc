@@ -676,4 +676,28 @@ void mref_mfsk_tables(void *h, int *out /*[32]: M, nBits, nStreams, tone_hop_ste
 	for (int i = 0; i < 8; i++) out[k++] = ts.mfsk.break_tones[i];
 }
 
+/* The ARQ layer's TX path (arq_common.cc:2224-2247): transmit_byte(..., NO_FILTER_MESSAGE) per frame, then the two transmit FIRs over the
+ * whole padded batch buffer through the public ofdm.FIR_tx1 / FIR_tx2. */
+int mref_transmit_byte_nofilter(void *h, const int *payload, int nBytes, double *passband_out, double *start_sample_inout)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	int buf[N_MAX];
+	memset(buf, 0, sizeof(buf));
+	for (int i = 0; i < nBytes; i++) buf[i] = payload[i];
+	ts.ofdm.passband_start_sample = (long unsigned)*start_sample_inout;
+	ts.transmit_byte(buf, nBytes, passband_out, NO_FILTER_MESSAGE);
+	*start_sample_inout = (double)ts.ofdm.passband_start_sample;
+	return ts.data_container.total_frame_size;
+}
+
+void mref_fir_tx_apply(void *h, const double *in, int n, double *out)
+{
+	cl_telecom_system &ts = T(h);
+	double *tmp = new double[n]();
+	ts.ofdm.FIR_tx1.apply(const_cast<double *>(in), tmp, n);
+	ts.ofdm.FIR_tx2.apply(tmp, out, n);
+	delete[] tmp;
+}
+
 }  // extern "C"

@@ -91,3 +91,26 @@ def test_tx_channel_rx_round_trip_on_the_device(ts, cfg, n):
     assert dec.mean() >= (0.85 if cfg == 16 else 1.0), dec.mean()
     assert np.array_equal(d_out.cpu().numpy()[dec], d_pl.cpu().numpy()[dec])
     assert int(np.abs(st["delay"][dec] - delays.cpu().numpy()[dec]).max()) <= 64  # within the guard interval (16 samples x 4)
+
+
+@pytest.mark.parametrize("cfg", [8, 16, 101])
+def test_arq_batch_transmit_path(ts, cfg):
+    """What the ARQ layer does to send a batch (arq_common.cc:2224-2247): transmit_byte(..., NO_FILTER_MESSAGE) per frame with the carrier
+    counter running on, pad one frame on each side, FIR_tx1 + FIR_tx2 over the whole buffer."""
+    o = _oracle(cfg)
+    g = ts.load_configuration(cfg, 50)
+    L = ts.get_total_frame_size()
+    rng = np.random.default_rng(cfg)
+    pl = rng.integers(0, 256, (3, g["frame_bytes"])).astype(np.uint8)
+    starts = np.array([5000 + i * L for i in range(3)], np.uint64)
+    raw = ts.transmit_byte_batch(pl, starts, message_location=4)
+    want, counter = [], 5000
+    for i in range(3):
+        w, counter = o.transmit_byte2(pl[i], counter, no_filter=True)
+        want.append(w)
+        assert np.abs(raw[i] - w).max() <= 1e-9 * np.abs(w).max(), (cfg, i)
+    assert counter == 5000 + 3 * L
+    batch = np.concatenate([raw[0]] + list(raw) + [raw[2]])
+    got = ts.fir_tx_apply(batch)
+    ref_out = o.fir_tx_apply(np.concatenate([want[0]] + want + [want[2]]))
+    assert np.abs(got - ref_out).max() <= 1e-9 * np.abs(ref_out).max()
