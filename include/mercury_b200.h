@@ -232,6 +232,21 @@ typedef struct mercury_b200_mfsk_pattern_result {
 int mercury_b200_mfsk_patterns_batch(mercury_b200_t *h, const void *bbi /* n_buffers x n_samples x (re, im) */, int complex_format /* _F64 | _F32 */,
 				     size_t n_buffers, int n_samples, int search_start_symb, mercury_b200_mfsk_pattern_result *out);
 
+/*
+ * The ARQ-facing tone-pattern calls (telecom_system.h:122-130), valid in EVERY configuration: they use the reference's dedicated
+ * ack_mfsk plan (16-MFSK, one stream, telecom_system.cc:3003-3008).
+ *   mercury_b200_generate_pattern_passband           int generate_ack_pattern_passband(double* out) / generate_break_pattern_passband
+ *                                                    (telecom_system.cc:1589-1631,1657-1689): 16 x 1088 clipped pass-band samples, no FIRs;
+ *                                                    returns the sample count; *passband_start_sample = ofdm.passband_start_sample, advanced
+ *   mercury_b200_detect_patterns_from_passband_batch double detect_ack_pattern_from_passband(double* data, int size, int* matched) and
+ *                                                    detect_break_pattern_from_passband (telecom_system.cc:1633-1655,1691-1710): mix + FIR_rx_data
+ *                                                    over the whole buffer, then the matched tone detector, ACK and BREAK in one pass
+ *                                                    (time_sync_delay in the result is the 16-MFSK preamble search and has no reference caller)
+ */
+int mercury_b200_generate_pattern_passband(mercury_b200_t *h, int use_break_tones, double *out, uint64_t *passband_start_sample);
+int mercury_b200_detect_patterns_from_passband_batch(mercury_b200_t *h, const void *passband, int sample_format, size_t n_buffers, int n_samples,
+						     mercury_b200_mfsk_pattern_result *out);
+
 /* Pinned host memory and plain device memory helpers for callers that do not link the CUDA runtime. */
 void *mercury_b200_host_alloc(size_t bytes);
 void mercury_b200_host_free(void *p);

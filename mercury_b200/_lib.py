@@ -89,6 +89,8 @@ def lib():
         "mercury_b200_fir_tx_apply": (i32, [vp, vp, sz, vp]),
         "mercury_b200_transmit_byte_batch_device": (i32, [vp, vp, vp, sz, vp, i32, vp]),
         "mercury_b200_mfsk_patterns_batch": (i32, [vp, vp, i32, sz, i32, i32, vp]),
+        "mercury_b200_generate_pattern_passband": (i32, [vp, i32, vp, vp]),
+        "mercury_b200_detect_patterns_from_passband_batch": (i32, [vp, vp, i32, sz, i32, vp]),
         "mercury_b200_host_alloc": (vp, [sz]),
         "mercury_b200_host_free": (None, [vp]),
         "mercury_b200_device_alloc": (vp, [vp, sz]),

@@ -1109,6 +1109,86 @@ int mercury_b200_mfsk_patterns_batch(mercury_b200_t *h, const void *bbi, int com
 	return MERCURY_B200_OK;
 }
 
+/* The ARQ-facing tone-pattern calls (telecom_system.h:122-130): any configuration, dedicated 16-MFSK x 1 plan (telecom_system.cc:3003-3008). */
+}  // extern "C"
+
+namespace {
+MbMfsk ack_mfsk_plan()
+{  // cl_mfsk::init(16, 50, 1): mfsk.cc:49-160
+	MbMfsk t;
+	memset(&t, 0, sizeof(t));
+	static const int pre16[4] = {2, 10, 6, 14}, ack16[8] = {4, 7, 5, 12, 13, 1, 9, 15}, brk16[8] = {6, 14, 2, 3, 10, 8, 11, 15};
+	t.M = 16, t.nBits = 4, t.nStreams = 1, t.tone_hop_step = 7, t.stream_offsets[0] = (MB_NC - 16) / 2;
+	for (int i = 0; i < 4; i++) t.preamble_tones[i] = pre16[i];
+	for (int i = 0; i < 8; i++) t.ack_tones[i] = ack16[i], t.break_tones[i] = brk16[i];
+	return t;
+}
+}  // namespace
+
+extern "C" {
+
+int mercury_b200_generate_pattern_passband(mercury_b200_t *h, int use_break_tones, double *out, uint64_t *passband_start_sample)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (!out) return fail(h, MERCURY_B200_EINVAL, "null buffer");
+	rc = tx_ensure_mode(h);  // (front-end constants, TX stream)
+	if (rc) return rc;
+	const int total = 16 * MB_FE_SYM;
+	double *d = nullptr;
+	MB_CUDA(h, cudaMalloc(&d, (size_t)(16 * MB_NOFDM * 2 + 2 * total + 2 * ((total + 255) / 256)) * sizeof(double)));
+	double2 *d_bb = reinterpret_cast<double2 *>(d);
+	double *d_pb = d + 16 * MB_NOFDM * 2, *d_out = d_pb + total, *d_pp = d_out + total;
+	const uint64_t start = passband_start_sample ? *passband_start_sample : 0;
+	cudaError_t e = mb_tx_pattern(ack_mfsk_plan(), use_break_tones, h->fe_const.fc, h->fe_const.Ts, h->fe_const.amp, start, d_bb, d_pb, d_pp, d_out, h->tx.stream);
+	if (e == cudaSuccess) e = cudaMemcpy(out, d_out, total * sizeof(double), cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return cuda_fail(h, e, "generate_pattern_passband");
+	if (passband_start_sample) *passband_start_sample = start + total;
+	h->launches += 3;
+	return total;
+}
+
+int mercury_b200_detect_patterns_from_passband_batch(mercury_b200_t *h, const void *passband, int sample_format, size_t n_buffers, int n_samples,
+						     mercury_b200_mfsk_pattern_result *out)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n_buffers == 0) return MERCURY_B200_OK;
+	if (!passband || !out || n_samples < 16 * MB_FE_SYM || fe_sample_bytes(sample_format) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	const MbMode &m = cur_mode(h);
+	const size_t ss = fe_sample_bytes(sample_format);
+	const size_t chunk = std::min<size_t>(n_buffers, std::max<size_t>(1, (1u << 30) / ((size_t)n_samples * 16)));
+	rc = fe_ensure(h, chunk, n_samples, m, false, chunk * n_samples * ss);
+	if (rc) return rc;
+	FeWork &w = h->fe;
+	const int nsymb = n_samples / MB_FE_SYM;
+	if (h->mfsk_cap_buffers < chunk || h->mfsk_cap_energies < chunk * nsymb * MB_NC) {
+		MB_CUDA(h, cudaDeviceSynchronize());
+		if (h->d_mfsk_out) cudaFree(h->d_mfsk_out);
+		if (h->d_mfsk_energies) cudaFree(h->d_mfsk_energies);
+		h->d_mfsk_out = nullptr, h->d_mfsk_energies = nullptr;
+		h->mfsk_cap_buffers = h->mfsk_cap_energies = 0;
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_out, chunk * sizeof(MbMfskPatternResult)));
+		MB_CUDA(h, cudaMalloc(&h->d_mfsk_energies, chunk * nsymb * MB_NC * sizeof(double)));
+		h->mfsk_cap_buffers = chunk, h->mfsk_cap_energies = chunk * nsymb * MB_NC;
+	}
+	const MbMfsk plan = ack_mfsk_plan();
+	for (size_t done = 0; done < n_buffers; done += chunk) {
+		const size_t c = std::min(chunk, n_buffers - done);
+		MbFeArgs a;
+		memset(&a, 0, sizeof(a));
+		a.x = w.d_x[0], a.x_format = sample_format, a.n = (int)c, a.buf = n_samples, a.carrier = w.carrier, a.bbi = w.bbi, a.energy_part = w.energy_part;
+		MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], static_cast<const uint8_t *>(passband) + done * n_samples * ss, c * n_samples * ss, cudaMemcpyHostToDevice, w.stream));
+		MB_CUDA(h, mb_fe_p2b_data(a, w.stream));
+		MB_CUDA(h, mb_launch_mfsk_patterns(w.bbi, 0, c, n_samples, 0, nullptr, 0, plan, 4, h->d_mfsk_energies, h->d_mfsk_out, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(out + done, h->d_mfsk_out, c * sizeof(MbMfskPatternResult), cudaMemcpyDeviceToHost, w.stream));
+		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+		h->launches += 3;
+	}
+	return MERCURY_B200_OK;
+}
+
 void *mercury_b200_host_alloc(size_t bytes)
 {
 	void *p = nullptr;

@@ -95,7 +95,7 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 constexpr int kP2bTile = 1024;
 __device__ __forceinline__ int p2b_skew(int i) { return i + (i >> 2); }
 
-template <typename T>
+template <typename T, bool DATA_FILTER = false>
 __global__ void __launch_bounds__(256, 2) k_fe_p2b_full(const T *__restrict__ x_all, int buf, const double2 *__restrict__ carrier, double2 *__restrict__ bbi_all,
 						       double *__restrict__ energy_part, int nblk)
 {
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, 2) k_fe_p2b_full(const T *__restrict__ x_
 #pragma unroll
 		for (int j = 0; j < MB_FE_TAPS; j++) {
 			w[0] = l[base + (32 - j) + ((32 - j) >> 2)];
-			const double cj = fe_c.c_ts[j];
+			const double cj = DATA_FILTER ? fe_c.c_data[j] : fe_c.c_ts[j];
 #pragma unroll
 			for (int r = 0; r < 4; r++) {
 				ar[r] = dadd(ar[r], dmul(w[r].x, cj));
@@ -1045,6 +1045,15 @@ static cudaError_t fe_extract_data_t(const MbFeArgs &a, cudaStream_t s)
 	return cudaGetLastError();
 }
 
+// passband_to_baseband with FIR_rx_data over whole buffers (detect_ack_pattern_from_passband, telecom_system.cc:1637-1641)
+template <typename T>
+static cudaError_t fe_p2b_data_t(const MbFeArgs &a, cudaStream_t s)
+{
+	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
+	k_fe_p2b_full<T, true><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
+	return cudaGetLastError();
+}
+
 #define MB_FE_DISPATCH(fn, ...)                                      \
 	switch (a.x_format) {                                        \
 	case 0: return fn<double>(__VA_ARGS__);                      \
@@ -1058,6 +1067,7 @@ cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(f
 cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s) { MB_FE_DISPATCH(fe_step_t, a, run_sc, s); }
 cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_extract_t, a, s); }
 cudaError_t mb_fe_extract_data(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_extract_data_t, a, s); }
+cudaError_t mb_fe_p2b_data(const MbFeArgs &a, cudaStream_t s) { MB_FE_DISPATCH(fe_p2b_data_t, a, s); }
 
 cudaError_t mb_fe_begin(const MbFeArgs &a, const MbReceiveStats *d_stats_in, cudaStream_t s)
 {

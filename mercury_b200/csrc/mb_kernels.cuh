@@ -129,6 +129,7 @@ cudaError_t mb_fe_p2b_full(const MbFeArgs &a, cudaStream_t s);
 cudaError_t mb_fe_step(const MbFeArgs &a, bool run_sc, cudaStream_t s);  // [k_fe_window, k_fe_sc,] k_fe_decide
 cudaError_t mb_fe_extract(const MbFeArgs &a, cudaStream_t s);       // k_fe_moose + k_fe_extract_tiles
 cudaError_t mb_fe_extract_data(const MbFeArgs &a, cudaStream_t s);  // k_fe_extract_tiles only
+cudaError_t mb_fe_p2b_data(const MbFeArgs &a, cudaStream_t s);      // whole-buffer mix + FIR_rx_data (uses x, x_format, n, buf, carrier, bbi, energy_part)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // TX chain (mb_tx.cu): payload bytes -> pass-band frames, transmit_byte(SINGLE_MESSAGE).
@@ -170,6 +171,9 @@ std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFe
 std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, const MbMfsk &t, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
 cudaError_t mb_tx_init();
 cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);
+// generate_ack / generate_break_pattern_passband (telecom_system.cc:1589-1631,1657-1689): 16 hopped tones of the dedicated 16-MFSK plan
+cudaError_t mb_tx_pattern(const MbMfsk &plan, int use_break_tones, double fc, double Ts, double amp, unsigned long long start_sample, double2 *d_bb, double *d_pb,
+			  double *d_power_part, double *d_out, cudaStream_t s);
 cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, const double *d_in, int n, double *d_tmp, double *d_out, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------------------------------

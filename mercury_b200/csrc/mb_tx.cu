@@ -641,3 +641,47 @@ cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, cons
 	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0.0, 0.0, c2, nullptr, 0, d_out);
 	return cudaGetLastError();
 }
+
+namespace {
+// 16 symbols, one hopped tone each (cl_mfsk::generate_ack_pattern / generate_break_pattern, mfsk.cc:197-252), scaled like :1611-1617
+__global__ void __launch_bounds__(256) k_tx_pattern_baseband(const MbMfsk t, int use_break, double scale, double2 *__restrict__ bb)
+{
+	const int tid = threadIdx.x;
+	const int *tones = use_break ? t.break_tones : t.ack_tones;
+	for (int s = 0; s < 16; s++) {
+		const int c = t.stream_offsets[0] + (tones[s % 8] + s * t.tone_hop_step) % t.M;
+		const int bin = c < MB_NC / 2 ? c + MB_NFFT - MB_NC / 2 : c - MB_NC / 2 + 1;
+		double sn, cs;
+		sincospi(2.0 * ((bin * tid) & 255) / 256.0, &sn, &cs);
+		const double2 v = make_double2(cs * scale, sn * scale);
+		bb[s * MB_NOFDM + MB_NGI + tid] = v;
+		if (tid >= MB_NFFT - MB_NGI) bb[s * MB_NOFDM + tid - (MB_NFFT - MB_NGI)] = v;
+	}
+}
+}  // namespace
+
+cudaError_t mb_tx_pattern(const MbMfsk &plan, int use_break_tones, double fc, double Ts, double amp, unsigned long long start_sample, double2 *d_bb, double *d_pb,
+			  double *d_power_part, double *d_out, cudaStream_t s)
+{
+	// one "frame" without a preamble part: 16 symbols, clipped at the data PAPR (ofdm.peak_clip(out, samples, data_papr_cut), :1629)
+	MbTxMode tm;
+	memset(&tm, 0, sizeof(tm));
+	tm.S = 16, tm.pre = 0, tm.fc = fc, tm.Ts = Ts, tm.amp = amp, tm.start_after_init = start_sample;
+	tm.papr_pre_lin = tm.papr_data_lin = std::pow(10, 10 / 10.0);
+	MbTxMode *d_tm = nullptr;
+	cudaError_t e = cudaMalloc(&d_tm, sizeof(tm));
+	if (e != cudaSuccess) return e;
+	e = cudaMemcpyAsync(d_tm, &tm, sizeof(tm), cudaMemcpyHostToDevice, s);
+	const double power_normalization = (double)(float)std::sqrt((double)(MB_NFFT * 4));
+	const double tone_amp = std::sqrt((double)MB_NC / plan.nStreams), boost = std::sqrt((double)MB_NC / plan.nStreams) * std::pow(10.0, -2.0 / 20.0);
+	const int total = 16 * MB_FE_SYM, nblk = (total + 255) / 256;
+	if (e == cudaSuccess) {
+		k_tx_pattern_baseband<<<1, 256, 0, s>>>(plan, use_break_tones, tone_amp / power_normalization * (std::sqrt(0.1) * boost), d_bb);
+		k_tx_mix<<<dim3(nblk, 1), 256, 0, s>>>(d_tm, d_bb, nullptr, d_pb, d_power_part, nblk);
+		k_tx_clip<double><<<dim3(nblk, 1), 256, 0, s>>>(d_pb, total, 0, tm.papr_pre_lin, tm.papr_data_lin, d_power_part, nblk, d_out);
+		e = cudaGetLastError();
+	}
+	cudaError_t e2 = cudaStreamSynchronize(s);
+	cudaFree(d_tm);
+	return e != cudaSuccess ? e : e2;
+}

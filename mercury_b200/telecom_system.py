@@ -179,6 +179,26 @@ class TelecomSystemB200:
                                                              b.shape[1], int(search_start_symb), _vp(out)))
         return out
 
+    def generate_pattern_passband(self, use_break_tones=False, passband_start_sample=0):
+        """generate_ack_pattern_passband / generate_break_pattern_passband (telecom_system.cc:1589-1689) -> (samples float64[17408], counter after)."""
+        out = np.zeros(16 * 1088, np.float64)
+        st = np.array([int(passband_start_sample)], np.uint64)
+        n = self._L.mercury_b200_generate_pattern_passband(self._h, int(use_break_tones), _vp(out), _vp(st))
+        if n < 0:
+            self._check(n)
+        return out[:n], int(st[0])
+
+    def detect_patterns_from_passband_batch(self, passband):
+        """detect_ack_pattern_from_passband + detect_break_pattern_from_passband on [n_buffers, n_samples] pass-band buffers (any of the capture
+        sample formats) -> structured array (ack_metric, ack_matched, break_metric, break_matched)."""
+        x = np.ascontiguousarray(passband)
+        if x.dtype not in _SAMPLE_FORMATS:
+            raise TypeError("passband must be float64, float32, int16 or int32")
+        x = x.reshape(-1, x.shape[-1])
+        out = np.zeros(x.shape[0], MFSK_PATTERN_DTYPE)
+        self._check(self._L.mercury_b200_detect_patterns_from_passband_batch(self._h, _vp(x), _SAMPLE_FORMATS[x.dtype], x.shape[0], x.shape[1], _vp(out)))
+        return out
+
     # ---- TX chain (SURVEY.md 8f row 2) --------------------------------------------------------------------
     def get_total_frame_size(self):
         """Pass-band samples of one transmitted frame: (preamble_nSymb + Nsymb) * Nofdm * 4 (data_container.total_frame_size)."""

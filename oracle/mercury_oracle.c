@@ -1860,3 +1860,50 @@ void mo_mfsk_tables(const mo_mode *m, int *out)
 	for (int i = 0; i < 8; i++) out[k++] = f->ack_tones[i];
 	for (int i = 0; i < 8; i++) out[k++] = f->break_tones[i];
 }
+
+
+/* ================================================================================================
+ * The ARQ-facing tone-pattern calls (telecom_system.h:122-130): generate_ack/break_pattern_passband
+ * (telecom_system.cc:1589-1631,1657-1689) and detect_ack/break_pattern_from_passband (:1633-1655,
+ * 1691-1710).  Config independent: a dedicated cl_mfsk with M = 16, one stream (:3003-3008).
+ * ============================================================================================== */
+static void ack_mfsk_plan(mo_mfsk *f) { mfsk_init(f, 16, MO_NC, 1); }
+
+int mo_generate_pattern_passband(mo_mode *m, int use_break_tones, double *out, double *start_sample_inout)
+{
+	mo_mfsk f;
+	ack_mfsk_plan(&f);
+	const int *tones = use_break_tones ? f.break_tones : f.ack_tones;
+	int nsymb = 16, rate = m->fe.interp, n = nsymb * MO_NOFDM * rate;
+	double complex *bb = malloc(sizeof(double complex) * nsymb * MO_NOFDM);
+	double amp = sqrt((double)MO_NC / f.nStreams);
+	for (int s = 0; s < nsymb; s++) {
+		double complex pat[MO_NC];
+		for (int k = 0; k < MO_NC; k++) pat[k] = 0;
+		pat[f.stream_offsets[0] + (tones[s % 8] + s * f.tone_hop_step) % f.M] = amp;
+		symbol_mod(m, pat, bb + s * MO_NOFDM);
+	}
+	float power_normalization = sqrt((double)(MO_NFFT * rate));
+	double ack_boost = sqrt((double)MO_NC / f.nStreams) * pow(10.0, -2.0 / 20.0);
+	for (int j = 0; j < MO_NOFDM * nsymb; j++) {
+		bb[j] /= power_normalization;
+		bb[j] *= sqrt(0.1) * ack_boost;
+	}
+	unsigned long start = (unsigned long)*start_sample_inout;
+	b2p(m, bb, MO_NOFDM * nsymb, out, m->fe.fc, &start);
+	peak_clip(out, n, 10);
+	*start_sample_inout = (double)start;
+	free(bb);
+	return n;
+}
+
+double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int size, int use_break_tones, int *matched_out)
+{
+	mo_mode tmp = *m; /* shallow copy: only the tone plan differs (the detector reads m->mfsk, m->fe and the FFT tables) */
+	ack_mfsk_plan(&tmp.mfsk);
+	double complex *bbi = malloc(sizeof(double complex) * size), *scratch = malloc(sizeof(double complex) * size);
+	p2b(m, data, size, bbi, m->fe.fc, 1, scratch);
+	double v = mo_detect_ack_pattern(&tmp, bbi, size, use_break_tones, matched_out);
+	free(bbi), free(scratch);
+	return v;
+}

@@ -121,6 +121,8 @@ int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int se
 double mo_detect_ack_pattern(const mo_mode *m, const double complex *bbi, int n, int use_break_tones, int *matched_out);
 void mo_ack_pattern_baseband(const mo_mode *m, int use_break_tones, double complex *out /*[16 * 272]*/);
 void mo_mfsk_tables(const mo_mode *m, int *out /*[32]*/);
+int mo_generate_pattern_passband(mo_mode *m, int use_break_tones, double *out /*[16 * 272 * 4]*/, double *start_sample_inout);
+double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int size, int use_break_tones, int *matched_out);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

@@ -73,6 +73,10 @@ def lib():
         L.mref_detect_ack_pattern.restype = C.c_double
         L.mref_ack_pattern_baseband.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.mref_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
+        L.mref_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mref_generate_pattern_passband.restype = C.c_int
+        L.mref_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.mref_detect_pattern_from_passband.restype = C.c_double
         L.mref_transmit_byte2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_transmit_byte2.restype = C.c_int
         L.mref_transmit_byte_nofilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -199,6 +203,19 @@ class FrontEndMixin:
         getattr(self._felib(), self._fe + "mfsk_tables")(self.h, _p(t))
         return dict(M=int(t[0]), nBits=int(t[1]), nStreams=int(t[2]), tone_hop_step=int(t[3]), stream_offsets=t[4:8].copy(),
                     preamble_tones=t[8:12].copy(), ack_tones=t[12:20].copy(), break_tones=t[20:28].copy())
+
+    # ---- the ARQ-facing tone-pattern calls (any configuration; dedicated 16-MFSK plan) -------------------------------
+    def generate_pattern_passband(self, use_break_tones=False, start_sample=0):
+        out = np.zeros(16 * self.Nofdm * 4, np.float64)
+        st = np.array([float(start_sample)], np.float64)
+        n = getattr(self._felib(), self._fe + "generate_pattern_passband")(self.h, int(use_break_tones), _p(out), _p(st))
+        return out[:n], int(st[0])
+
+    def detect_pattern_from_passband(self, data, use_break_tones=False):
+        d = np.ascontiguousarray(data, np.float64)
+        m = np.zeros(1, np.int32)
+        v = getattr(self._felib(), self._fe + "detect_pattern_from_passband")(self.h, _p(d), d.size, int(use_break_tones), _p(m))
+        return float(v), int(m[0])
 
     def frontend_tables(self):
         nt = np.zeros(2, np.int32)

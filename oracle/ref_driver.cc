@@ -700,4 +700,26 @@ void mref_fir_tx_apply(void *h, const double *in, int n, double *out)
 	delete[] tmp;
 }
 
+/* The ARQ-facing tone-pattern calls (telecom_system.h:122-130, .cc:1589-1710): config-independent, dedicated ack_mfsk (M = 16, 1 stream). */
+int mref_generate_pattern_passband(void *h, int use_break_tones, double *out, double *start_sample_inout)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	ts.ofdm.passband_start_sample = (long unsigned)*start_sample_inout;
+	int n = use_break_tones ? ts.generate_break_pattern_passband(out) : ts.generate_ack_pattern_passband(out);
+	*start_sample_inout = (double)ts.ofdm.passband_start_sample;
+	return n;
+}
+
+double mref_detect_pattern_from_passband(void *h, const double *data, int size, int use_break_tones, int *matched)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	double *copy = new double[size];
+	memcpy(copy, data, sizeof(double) * size);
+	double m = use_break_tones ? ts.detect_break_pattern_from_passband(copy, size, matched) : ts.detect_ack_pattern_from_passband(copy, size, matched);
+	delete[] copy;
+	return m;
+}
+
 }  // extern "C"

@@ -171,3 +171,37 @@ def test_robust_receive_byte_against_reference(ts, cfg):
             assert np.array_equal(payload[i], np.asarray(pl, np.uint8))
             n_dec += 1
     assert n_dec == 4 and int(st["mfsk_search_or_overflow"][3]) == 3
+
+
+@pytest.mark.parametrize("cfg", [8, 16, 101])
+def test_arq_tone_pattern_calls_in_any_configuration(ts, cfg):
+    """generate_ack/break_pattern_passband and detect_ack/break_pattern_from_passband (telecom_system.h:122-130): the ARQ layer's
+    acknowledgement tones, config independent (dedicated 16-MFSK plan), here in an OFDM and a ROBUST configuration."""
+    o = _oracle(cfg)
+    ts.load_configuration(cfg, 50)
+    rng = np.random.default_rng(40 + cfg)
+    pats = {}
+    for brk in (False, True):
+        got, after = ts.generate_pattern_passband(brk, 4321)
+        want, wafter = o.generate_pattern_passband(brk, 4321)
+        assert after == wafter == 4321 + 16 * 1088 and got.size == want.size
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), (cfg, brk)
+        pats[brk] = want
+    n = 40 * 1088
+    bufs = []
+    for kind in ("ack", "break", "noise", "ack_weak"):
+        b = rng.normal(0, 0.05, n)
+        pos = int(rng.integers(2, 20)) * 1088 + int(rng.integers(0, 50))
+        if kind != "noise":
+            b[pos:pos + 16 * 1088] += pats[kind == "break"] * (0.15 if kind == "ack_weak" else 1.0)
+        bufs.append(b.astype(np.float32).astype(np.float64))
+    bufs = np.stack(bufs)
+    res = ts.detect_patterns_from_passband_batch(bufs)
+    for i in range(len(bufs)):
+        for brk, name in ((False, "ack"), (True, "break")):
+            m, matched = o.detect_pattern_from_passband(bufs[i], brk)
+            assert abs(float(res[name + "_metric"][i]) - m) <= 1e-9 * max(1.0, m), (cfg, i, name)
+            assert int(res[name + "_matched"][i]) == matched, (cfg, i, name)
+    assert res["ack_metric"][0] > 12 and res["break_metric"][1] > 12 and res["ack_metric"][2] < 6
+    res32 = ts.detect_patterns_from_passband_batch(bufs.astype(np.float32))  # float32 captures: the same values
+    assert res32.tobytes() == res.tobytes()

@@ -99,3 +99,19 @@ def test_mfsk_transmit_byte_bit_exact(cfg):
     a, sa = r.transmit_byte2(pl, 4242)
     b, sb = p.transmit_byte2(pl, 4242)
     assert sa == sb and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("cfg", [8, 101])
+def test_arq_tone_pattern_calls_bit_exact(cfg):
+    """generate_ack/break_pattern_passband + detect_ack/break_pattern_from_passband (telecom_system.h:122-130), any configuration."""
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    rng = np.random.default_rng(cfg)
+    for brk in (False, True):
+        a, sa = r.generate_pattern_passband(brk, 4321)
+        b, sb = p.generate_pattern_passband(brk, 4321)
+        assert sa == sb and np.array_equal(a, b)
+        buf = rng.normal(0, 0.05, 40 * 1088)
+        buf[7 * 1088 + 13:7 * 1088 + 13 + a.size] += a
+        for which in (False, True):
+            assert r.detect_pattern_from_passband(buf, which) == p.detect_pattern_from_passband(buf, which)
+        assert r.detect_pattern_from_passband(buf, brk)[1] == 16
