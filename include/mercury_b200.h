@@ -171,6 +171,15 @@ typedef struct mercury_b200_receive_stats {
 #define MERCURY_B200_SAMPLES_I32 3  /* int32 PCM, x / (double)INT_MAX (the reference's default capture format, audioio.c:744) */
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h);
+/* void set_mfsk_ctrl_mode(bool) / int get_active_nsymb() (telecom_system.cc:1572-1580): shortened control frames in ROBUST_0 (240 of 320 symbols)
+ * and ROBUST_1 (175 of 200): transmit_byte modulates only the active symbols (silence follows), receive_byte / the tail demodulate only those and
+ * erase the rest of the codeword.  Both return the active symbol count; load_configuration switches the mode off like the reference. */
+int mercury_b200_set_mfsk_ctrl_mode(mercury_b200_t *h, int enable);
+int mercury_b200_get_active_nsymb(const mercury_b200_t *h);
+/* char get_configuration(double SNR) (telecom_system.h:178, .cc:3036-3106): the gear-shift ladder; pure host function. */
+int mercury_b200_get_configuration(double SNR);
+/* double measure_signal_only(double* data) (telecom_system.h, .cc:1520-1541): signal strength in dBm of n captures, no search, no decode. */
+int mercury_b200_measure_signal_only_batch(mercury_b200_t *h, const void *passband, int sample_format, size_t n_captures, double *signal_dbm);
 /* Host-only (no device needed): the two receive FIR designs (33 taps each), {fs, fc, carrier amplitude, bandwidth, time_sync_trials_max,
  * use_last_good_time_sync, use_last_good_freq_offset, freq_offset_ignore_limit} and the first n_carrier (cos, sin) pairs of the carrier table. */
 int mercury_b200_build_frontend_tables_host(double *ts_coef, double *data_coef, double *consts, double *carrier, int n_carrier);

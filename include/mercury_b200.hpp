@@ -20,6 +20,8 @@
 //   st_receive_stats receive_bit(double*, int*) (.h:139) receive_bit(const std::complex<double>*, int* out)
 //   st_receive_stats receive_stats      (.h:114)        receive_stats (the fields the tail writes)
 //   data_container.{Nsymb,Nofdm,nBits,preamble_nSymb}   data_container.{...} (read-only copies), ldpc.{N,K,P}
+//   void transmit_byte(int*, int, double*, int) (.h:138) transmit_byte(...) SINGLE_MESSAGE / NO_FILTER_MESSAGE; fir_tx_apply(); ofdm.passband_start_sample
+//   set_mfsk_ctrl_mode / get_active_nsymb / get_configuration / measure_signal_only / generate_* / detect_*_pattern_*_passband  -- same names
 //   -                                                   receive_byte_batch(): many synchronised frames per call
 //
 // Error behaviour follows the reference: a frame that does not decode is RETURNED (message_decoded == NO, SNR == -99.9),
@@ -94,7 +96,7 @@ public:
 	// reference: out-of-range configurations are silently ignored (telecom_system.cc:2494-2497); so they are here
 	void load_configuration(int configuration)
 	{
-		if (configuration < 0 || configuration >= MERCURY_B200_NUM_CONFIGS) return;
+		if (!(configuration >= 100 && configuration <= 102) && (configuration < 0 || configuration >= MERCURY_B200_NUM_CONFIGS)) return;
 		if (mercury_b200_load_configuration(h_, configuration, default_configurations_telecom_system.ldpc_nIteration_max) != MERCURY_B200_OK) return;
 		mercury_b200_geometry g;
 		mercury_b200_get_geometry(h_, &g);
@@ -104,6 +106,7 @@ public:
 		ldpc.K = g.K, ldpc.P = g.P;
 		M = g.M;
 		nReal_ = g.nReal;
+		if (M == 200 && ofdm.passband_start_sample == 1088) ofdm.passband_start_sample = 0;  // MFSK: no pre-equalisation pass moved the counter
 	}
 	int get_frame_size_bytes() const { return mercury_b200_get_frame_size_bytes(h_); }
 	int get_frame_size_bits() const { return mercury_b200_get_frame_size_bits(h_); }
@@ -126,6 +129,41 @@ public:
 		receive_stats.signal_stregth_dbm = rs.signal_stregth_dbm, receive_stats.coarse_metric = rs.coarse_metric;
 		return receive_stats;
 	}
+
+	// ---- the rest of what the datalink layer calls on the object (source/datalink_layer/arq_*.cc) -------------------------------------
+	// void transmit_byte(int* data, int nBytes, double* out, int message_location) (telecom_system.h:138): SINGLE_MESSAGE (3) or
+	// NO_FILTER_MESSAGE (4, the ARQ layer's choice, arq_common.cc:2224); the running carrier counter lives in ofdm.passband_start_sample
+	struct {
+		uint64_t passband_start_sample = 1088;  // where a freshly initialised reference object stands in OFDM modes (0 in MFSK modes)
+	} ofdm;
+	void transmit_byte(int *data, int nBytes, double *out, int message_location = MERCURY_B200_SINGLE_MESSAGE)
+	{
+		std::vector<uint8_t> pl((size_t)get_frame_size_bytes(), 0);
+		for (int i = 0; i < nBytes && i < (int)pl.size(); i++) pl[(size_t)i] = (uint8_t)data[i];
+		const uint64_t start = ofdm.passband_start_sample;
+		const int rc = mercury_b200_transmit_byte_batch_ex(h_, pl.data(), &start, 1, out, MERCURY_B200_SAMPLES_F64, message_location, nullptr);
+		if (rc != MERCURY_B200_OK) throw std::runtime_error(std::string("mercury_b200_transmit_byte: ") + mercury_b200_last_error(h_));
+		ofdm.passband_start_sample = start + (uint64_t)mercury_b200_get_total_frame_size(h_);
+	}
+	// ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over a padded batch of NO_FILTER frames (arq_common.cc:2243-2246)
+	void fir_tx_apply(const double *in, double *out, int nItems)
+	{
+		if (mercury_b200_fir_tx_apply(h_, in, (size_t)nItems, out) != MERCURY_B200_OK) throw std::runtime_error(mercury_b200_last_error(h_));
+	}
+	void set_mfsk_ctrl_mode(bool enable) { mercury_b200_set_mfsk_ctrl_mode(h_, enable ? 1 : 0); }
+	int get_active_nsymb() const { return mercury_b200_get_active_nsymb(h_); }
+	char get_configuration(double SNR) const { return (char)mercury_b200_get_configuration(SNR); }
+	double measure_signal_only(double *data)
+	{
+		double dbm = 0;
+		if (mercury_b200_measure_signal_only_batch(h_, data, MERCURY_B200_SAMPLES_F64, 1, &dbm) != MERCURY_B200_OK) throw std::runtime_error(mercury_b200_last_error(h_));
+		receive_stats.signal_stregth_dbm = dbm;
+		return dbm;
+	}
+	int generate_ack_pattern_passband(double *out) { return pattern_tx(0, out); }
+	int generate_break_pattern_passband(double *out) { return pattern_tx(1, out); }
+	double detect_ack_pattern_from_passband(double *data, int size, int *out_matched = nullptr) { return pattern_rx(0, data, size, out_matched); }
+	double detect_break_pattern_from_passband(double *data, int size, int *out_matched = nullptr) { return pattern_rx(1, data, size, out_matched); }
 
 	// baseband_data: Nsymb * Nofdm samples, the frame's data symbols after time/frequency synchronisation (the reference
 	// indexes data_container.baseband_data at (preamble_nSymb + i) * Nofdm, telecom_system.cc:1137).  out: one int per byte.
@@ -171,6 +209,22 @@ public:
 	mercury_b200_t *handle() { return h_; }
 
 private:
+	int pattern_tx(int brk, double *out)
+	{
+		uint64_t c = ofdm.passband_start_sample;
+		const int n = mercury_b200_generate_pattern_passband(h_, brk, out, &c);
+		if (n < 0) throw std::runtime_error(mercury_b200_last_error(h_));
+		ofdm.passband_start_sample = c;
+		return n;
+	}
+	double pattern_rx(int brk, double *data, int size, int *out_matched)
+	{
+		mercury_b200_mfsk_pattern_result r;
+		if (mercury_b200_detect_patterns_from_passband_batch(h_, data, MERCURY_B200_SAMPLES_F64, 1, size, &r) != MERCURY_B200_OK)
+			throw std::runtime_error(mercury_b200_last_error(h_));
+		if (out_matched) *out_matched = brk ? r.break_matched : r.ack_matched;
+		return brk ? r.break_metric : r.ack_metric;
+	}
 	mercury_b200_t *h_ = nullptr;
 	int nReal_ = 0;
 };

@@ -77,6 +77,10 @@ def lib():
         "mercury_b200_set_debug_capture": (i32, [vp, vp, vp, vp]),
         "mercury_b200_receive_baseband": (i32, [vp, vp, vp, C.POINTER(RxStats)]),
         "mercury_b200_get_capture_samples": (i32, [vp]),
+        "mercury_b200_set_mfsk_ctrl_mode": (i32, [vp, i32]),
+        "mercury_b200_get_active_nsymb": (i32, [vp]),
+        "mercury_b200_get_configuration": (i32, [C.c_double]),
+        "mercury_b200_measure_signal_only_batch": (i32, [vp, vp, i32, sz, vp]),
         "mercury_b200_build_frontend_tables_host": (i32, [vp, vp, vp, vp, i32]),
         "mercury_b200_receive_byte": (i32, [vp, vp, vp, C.POINTER(ReceiveStats)]),
         "mercury_b200_receive_byte_batch": (i32, [vp, vp, i32, sz, vp, vp, vp]),

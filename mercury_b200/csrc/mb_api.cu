@@ -87,6 +87,7 @@ void tx_free(TxWork &w);
 }  // namespace
 
 struct mercury_b200 {
+	bool mfsk_ctrl = false;  // set_mfsk_ctrl_mode: shortened control frames in ROBUST_0 / ROBUST_1 (telecom_system.cc:1572-1585, 2966-2995)
 	MbMode mfsk_modes[3];  // ROBUST_0..2 (config 100..102): tables in the extension region behind the device blob
 	MbMfsk mfsk_tones[3];
 	double *d_mfsk_energies = nullptr;
@@ -119,6 +120,14 @@ namespace {
 
 inline bool is_mfsk_config(int c) { return c >= 100 && c <= 102; }
 inline const MbMode &cur_mode(const mercury_b200_t *h) { return is_mfsk_config(h->config) ? h->mfsk_modes[h->config - 100] : h->hdr.modes[h->config]; }
+// get_active_nsymb() (telecom_system.cc:1577-1580): ctrl_nBits = 1200 (ROBUST_0), 1400 (ROBUST_1), none otherwise (:2966-2990)
+inline int active_nsymb(const mercury_b200_t *h)
+{
+	const MbMode &m = cur_mode(h);
+	if (!h->mfsk_ctrl || m.M != 200) return m.Nsymb;
+	const int ctrl_bits = h->config == 100 ? 1200 : (h->config == 101 ? 1400 : 0);
+	return ctrl_bits > 0 ? ctrl_bits / m.bps : m.Nsymb;
+}
 
 int fail(mercury_b200_t *h, int code, const std::string &msg)
 {
@@ -173,7 +182,7 @@ int launch_demod(mercury_b200_t *h, const void *d_x, size_t n, void *d_llr, void
 		f.x = static_cast<const float2 *>(d_x);
 		f.sym_stride = gi_removed ? MB_NFFT : MB_NOFDM, f.sym_skip = gi_removed ? 0 : MB_NGI;
 		f.llr = static_cast<float *>(d_llr), f.llr_cw = static_cast<float *>(d_llr_cw), f.stats = static_cast<MbRxStats *>(d_stats);
-		f.blob = h->d_blob, f.mode = m, f.tone = h->mfsk_tones[h->config - 100];
+		f.blob = h->d_blob, f.mode = m, f.tone = h->mfsk_tones[h->config - 100], f.active_nsymb = active_nsymb(h);
 		cudaError_t e = mb_launch_mfsk_demod(f, n, s);
 		if (e != cudaSuccess) return cuda_fail(h, e, "mfsk demod kernel launch");
 		h->launches++;
@@ -374,6 +383,7 @@ int mercury_b200_load_configuration(mercury_b200_t *h, int config, int ldpc_iter
 	if (!is_mfsk_config(config) && (config < 0 || config >= MB_NMODES))
 		return fail(h, MERCURY_B200_EINVAL, "configuration must be 0..16 (CONFIG_0..CONFIG_16) or 100..102 (ROBUST_0..ROBUST_2)");
 	h->config = config;
+	h->mfsk_ctrl = false;  // telecom_system.cc:2989,3000
 	h->ldpc_iters = std::min(50, std::max(5, ldpc_iters));  // main.cc:303-311
 	return MERCURY_B200_OK;
 }
@@ -720,7 +730,7 @@ int fe_run_mfsk(mercury_b200_t *h, const MbFeArgs &a, MbReceiveStats *d_stats, c
 	MB_CUDA(h, mb_launch_mfsk_patterns(a.bbi, 0, (size_t)a.n, a.buf, 0, reinterpret_cast<const int32_t *>(d_stats) + 7, (int)(sizeof(MbReceiveStats) / 4),
 					   h->mfsk_tones[h->config - 100], m.preamble_nSymb, h->d_mfsk_energies, h->d_mfsk_out, s));
 	MB_CUDA(h, cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), s));
-	MB_CUDA(h, mb_launch_mfsk_rx_decide(h->d_mfsk_out, a.energy_part, nblk, a.buf, a.pre, a.S, a.buffer_Nsymb, h->fe_const.fc, a.st, d_stats, a.n, w.counters, s));
+	MB_CUDA(h, mb_launch_mfsk_rx_decide(h->d_mfsk_out, a.energy_part, nblk, a.buf, a.pre, a.S, active_nsymb(h), a.buffer_Nsymb, h->fe_const.fc, a.st, d_stats, a.n, w.counters, s));
 	MB_CUDA(h, cudaMemcpyAsync(w.h_counters, w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 	MB_CUDA(h, cudaStreamSynchronize(s));
 	h->launches += 7;
@@ -758,6 +768,69 @@ int mercury_b200_build_frontend_tables_host(double *ts_coef /*[33]*/, double *da
 	}
 	if (carrier && n_carrier > 0) mb_fe_host_carrier(k, carrier, n_carrier);
 	return MERCURY_B200_OK;
+}
+
+/* char cl_telecom_system::get_configuration(double SNR) (telecom_system.cc:3036-3106): the gear-shift ladder over the FER < 0.1 thresholds
+ * of include/common/common_defines.h:130-147; CONFIG_16 is never chosen (its threshold has no rung), like the reference. */
+int mercury_b200_get_configuration(double SNR)
+{
+	static const double rung[15] = {12.5, 9, 7.5, 6.5, 4, 3, 1.5, 0.5, -0.5, -1.5, -2.5, -3.5, -4.5, -6, -7.5};
+	for (int i = 0; i < 15; i++)
+		if (SNR > rung[i]) return 15 - i;
+	return 0;
+}
+
+/* double cl_telecom_system::measure_signal_only(double* data) (telecom_system.cc:1520-1541): mix + FIR_rx_time_sync over the capture, mean power
+ * in dBm -- no preamble search, no decoding.  n captures of capture_samples samples each (host). */
+int mercury_b200_measure_signal_only_batch(mercury_b200_t *h, const void *passband, int sample_format, size_t n, double *signal_dbm)
+{
+	int rc = check_ready(h);
+	if (rc) return rc;
+	if (n == 0) return MERCURY_B200_OK;
+	if (!passband || !signal_dbm || fe_sample_bytes(sample_format) == 0) return fail(h, MERCURY_B200_EINVAL, "bad argument");
+	const MbMode &m = cur_mode(h);
+	const int buf = fe_capture_samples(m);
+	const size_t ss = fe_sample_bytes(sample_format);
+	const size_t chunk = std::min<size_t>(n, m.M == 200 ? 64 : 512);
+	rc = fe_ensure(h, chunk, buf, m, false, chunk * buf * ss);
+	if (rc) return rc;
+	FeWork &w = h->fe;
+	const int nblk = (buf + 1023) / 1024;
+	std::vector<double> part(chunk * nblk);
+	for (size_t done = 0; done < n; done += chunk) {
+		const size_t c = std::min(chunk, n - done);
+		MbFeArgs a;
+		memset(&a, 0, sizeof(a));
+		a.x = w.d_x[0], a.x_format = sample_format, a.n = (int)c, a.buf = buf, a.carrier = w.carrier, a.bbi = w.bbi, a.energy_part = w.energy_part;
+		a.st = w.st, a.win = w.win, a.win_stride = kFeWin, a.pref_ts = w.pref_ts, a.tile_base = w.tile_base;
+		MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], static_cast<const uint8_t *>(passband) + done * buf * ss, c * buf * ss, cudaMemcpyHostToDevice, w.stream));
+		MB_CUDA(h, mb_fe_p2b_full(a, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(part.data(), w.energy_part, c * nblk * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
+		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+		h->launches += 3;
+		for (size_t i = 0; i < c; i++) {
+			double e = 0;
+			for (int k = 0; k < nblk; k++) e += part[i * nblk + k];
+			signal_dbm[done + i] = 10.0 * log10((e / buf) / 0.001);  // measure_signal_stregth, ofdm.cc:1523-1539
+		}
+	}
+	return MERCURY_B200_OK;
+}
+
+/* void set_mfsk_ctrl_mode(bool) + int get_active_nsymb() (telecom_system.h, .cc:1572-1580): shortened control frames in ROBUST_0 (240 of 320
+ * symbols) and ROBUST_1 (175 of 200); affects transmit_byte, receive_byte and the tail entry points.  Returns the active symbol count. */
+int mercury_b200_set_mfsk_ctrl_mode(mercury_b200_t *h, int enable)
+{
+	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
+	h->mfsk_ctrl = enable != 0;
+	h->mfsk_ctrl = active_nsymb(h) != cur_mode(h).Nsymb;  // only where a shorter control frame exists (:1574)
+	return active_nsymb(h);
+}
+
+int mercury_b200_get_active_nsymb(const mercury_b200_t *h)
+{
+	if (!h || h->blob.empty() || h->config < 0) return MERCURY_B200_ESTATE;
+	return active_nsymb(h);
 }
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h)
@@ -935,6 +1008,7 @@ int tx_run(mercury_b200_t *h, const uint8_t *d_payload, const unsigned long long
 	MbTxArgs a;
 	memset(&a, 0, sizeof(a));
 	a.tone = is_mfsk_config(h->config) ? &h->mfsk_tones[h->config - 100] : nullptr;
+	a.S_active = active_nsymb(h);
 	a.tm = w.mode_dev[c], a.tm_host = &w.mode_host[c], a.tables = w.tables[c];
 	a.payload = d_payload, a.start_sample = d_start, a.n = (int)n, a.out_f32 = out_f32, a.no_filter = no_filter;
 	a.bb = w.bb, a.pb = w.pb, a.p1 = w.p1, a.power_part = w.power_part, a.out = d_out, a.dbg_cw = d_cw;

@@ -159,6 +159,7 @@ struct MbTxArgs {
 	const uint8_t *payload;    // [n][frame_bytes] zero-padded payloads
 	const unsigned long long *start_sample;  // [n] running carrier sample counter per frame, or NULL (= start_after_init)
 	int32_t n, out_f32, no_filter;  // no_filter: NO_FILTER_MESSAGE, stop after the PAPR clip
+	int32_t S_active;          // data symbols actually modulated (MFSK control frames: < S; what follows is silence)
 	double2 *bb;               // [n][(pre + S) * 272] scaled base-band symbols
 	double *pb, *p1;           // [n][total] pass-band before / after FIR_tx1
 	double *power_part;        // [n][ceil(total / 256)][2]
@@ -188,6 +189,7 @@ struct MbMfskArgs {
 	const uint8_t *blob;   // device blob + MFSK extension
 	MbMode mode;
 	MbMfsk tone;
+	int32_t active_nsymb;  // get_active_nsymb(): < Nsymb for control frames (set_mfsk_ctrl_mode), the rest of the codeword is erased
 };
 
 // Mirrors mercury_b200_mfsk_pattern_result (include/mercury_b200.h); 32 bytes.
@@ -200,7 +202,7 @@ cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStrea
 // search start: one value for all buffers, or (d_search_start_each != NULL) one int32 per buffer every each_stride int32s
 cudaError_t mb_launch_mfsk_patterns(const void *d_bbi, int is_f32, size_t n_buffers, int n_samples, int search_start_symb, const int32_t *d_search_start_each,
 				    int each_stride, const MbMfsk &t, int pre, double *d_energies, MbMfskPatternResult *d_out, cudaStream_t s);
-cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int buffer_Nsymb, double fc,
-				     MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s);
+cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int S_active, int buffer_Nsymb,
+				     double fc, MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s);
 cudaError_t mb_launch_mfsk_rx_finish(const MbFeState *st, const MbRxStats *tail_stats, const uint8_t *tail_payload, int frame_bytes, uint8_t *payload_out,
 				     MbReceiveStats *stats, int n, cudaStream_t s);

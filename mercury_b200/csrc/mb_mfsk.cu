@@ -43,7 +43,15 @@ __global__ void __launch_bounds__(256) k_mfsk_demod(const MbMfskArgs a)
 	float2 *buf = scr[grp];
 	for (int s0 = 0; s0 < m.Nsymb; s0 += kSymPerRound) {
 		const int s = s0 + grp;
-		const bool active = s < m.Nsymb;
+		if (s0 >= a.active_nsymb) {  // control frame (set_mfsk_ctrl_mode): the punctured tail of the codeword is erased (telecom_system.cc:1188-1197)
+			if (s < m.Nsymb && q < m.bps) {
+				const int i = s * m.bps + q;
+				llr[dst[i]] = 0.f;
+				if (a.llr_cw) a.llr_cw[frame * MB_N + (i < nb * bs ? (i % nb) * bs + i / nb : i)] = 0.f;
+			}
+			continue;
+		}
+		const bool active = s < a.active_nsymb;
 		float2 v[16];
 		if (active) {
 			const float2 *xs = a.x + (frame * m.Nsymb + (size_t)s) * a.sym_stride + a.sym_skip + q;
@@ -86,6 +94,11 @@ __global__ void __launch_bounds__(256) k_mfsk_demod(const MbMfskArgs a)
 		float nv = nbins > 0 ? ns / nbins : 1e-30f;
 		if (nv < 1e-30f) nv = 1e-30f;
 		const float scale = 1.0f / (2.0f * nv);
+		if (!active && s < m.Nsymb && q < m.bps) {  // erased symbols inside the last active round
+			const int i = s * m.bps + q;
+			llr[dst[i]] = 0.f;
+			if (a.llr_cw) a.llr_cw[frame * MB_N + (i < nb * bs ? (i % nb) * bs + i / nb : i)] = 0.f;
+		}
 		if (active && q < m.bps) {  // one LLR per lane: stream st, bit k (mfsk.cc:341-387)
 			const int st = q / t.nBits, k = q % t.nBits, mask = 1 << (t.nBits - 1 - k);
 			const int hop = (s * t.tone_hop_step) % t.M;
@@ -254,7 +267,7 @@ namespace {
 // ---- the MFSK branch of receive_byte() around the kernels above (telecom_system.cc:646-716, 928-943, 1020-1031, 1343-1367) ----
 // after the tone-preamble sync: frame-completeness check, bounds, clamp; hands the capture to k_fe_extract_tiles + the MFSK tail
 __global__ void k_mfsk_rx_decide(const MbMfskPatternResult *__restrict__ pat, const double *__restrict__ energy_part, int nblk, int buf, int pre, int S,
-				 int buffer_Nsymb, double fc, MbFeState *__restrict__ st_all, MbReceiveStats *__restrict__ stats, int n, int *__restrict__ counters)
+				 int S_active, int buffer_Nsymb, double fc, MbFeState *__restrict__ st_all, MbReceiveStats *__restrict__ stats, int n, int *__restrict__ counters)
 {
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= n) return;
@@ -270,7 +283,7 @@ __global__ void k_mfsk_rx_decide(const MbMfskPatternResult *__restrict__ pat, co
 	if (pream < 1) pream = 1;
 	r.mfsk_search_or_overflow = 0;
 	st.slot = -1;
-	const int frame_end = delay + (pre + S) * MB_FE_SYM;
+	const int frame_end = delay + (pre + S_active) * MB_FE_SYM;  // get_active_nsymb(): control frames are shorter
 	if (frame_end > buf) {
 		r.mfsk_search_or_overflow = (frame_end - buf + MB_FE_SYM - 1) / MB_FE_SYM;  // frame_overflow_symbols (:702-715)
 	} else if (pream > pre && pream < buffer_Nsymb - (S + pre)) {
@@ -310,10 +323,10 @@ __global__ void k_mfsk_rx_finish(const MbFeState *__restrict__ st_all, const MbR
 
 }  // namespace
 
-cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int buffer_Nsymb, double fc,
-				     MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s)
+cudaError_t mb_launch_mfsk_rx_decide(const MbMfskPatternResult *pat, const double *energy_part, int nblk, int buf, int pre, int S, int S_active, int buffer_Nsymb,
+				     double fc, MbFeState *st, MbReceiveStats *stats, int n, int *counters, cudaStream_t s)
 {
-	k_mfsk_rx_decide<<<(n + 127) / 128, 128, 0, s>>>(pat, energy_part, nblk, buf, pre, S, buffer_Nsymb, fc, st, stats, n, counters);
+	k_mfsk_rx_decide<<<(n + 127) / 128, 128, 0, s>>>(pat, energy_part, nblk, buf, pre, S, S_active, buffer_Nsymb, fc, st, stats, n, counters);
 	return cudaGetLastError();
 }
 

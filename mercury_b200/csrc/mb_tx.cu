@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_tx_baseband(const MbTxMode *__restrict_
 
 // ---- ROBUST (MFSK) modes: bits -> tones -> base-band symbols (telecom_system.cc:384-416,461-465,495-527; cl_mfsk::mod mfsk.cc:254-303,
 // generate_preamble :162-195).  Every symbol holds one tone per stream, so its IDFT is a sum of nStreams rotating phasors. ----
-__global__ void __launch_bounds__(256) k_tx_baseband_mfsk(const MbTxMode *__restrict__ tm_p, const uint8_t *__restrict__ tb, const MbMfsk t,
+__global__ void __launch_bounds__(256) k_tx_baseband_mfsk(const MbTxMode *__restrict__ tm_p, const uint8_t *__restrict__ tb, const MbMfsk t, int S_active,
 							    const uint8_t *__restrict__ payload_all, double2 *__restrict__ bb_all, uint8_t *__restrict__ dbg_cw)
 {
 	__shared__ uint8_t cw[MB_N];
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(256) k_tx_baseband_mfsk(const MbTxMode *__rest
 			const double2 w = W[(bin * tid) & 255];
 			ar += w.x, ai += w.y;
 		}
-		const double sc = s < tm.pre ? tm.scale_pre : tm.scale_data;  // tone amplitude, power normalisation, output power, boosts
-		const double2 v = make_double2(ar * sc, ai * sc);
+		const double sc = s < tm.pre ? tm.scale_pre : (s < tm.pre + S_active ? tm.scale_data : 0.0);  // tone amplitude, power normalisation, output power, boosts;
+		const double2 v = make_double2(ar * sc, ai * sc);                                            // control frames: nothing after the active symbols
 		bb[s * MB_NOFDM + MB_NGI + tid] = v;
 		if (tid >= MB_NFFT - MB_NGI) bb[s * MB_NOFDM + tid - (MB_NFFT - MB_NGI)] = v;
 	}
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_tx_mix(const MbTxMode *__restrict__ tm_
 
 // ---- one 97-tap real FIR pass (zero-phase, fir_filter.cc:189-210); pass 1 clips its input on the fly (peak_clip) ----
 template <bool CLIP, typename OUT>
-__global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_all, int total, int npre, double papr_pre_lin, double papr_data_lin,
+__global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_all, int total, int npre, int ndata, double papr_pre_lin, double papr_data_lin,
 						  const double *__restrict__ coef_off_base, const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
 {
 	__shared__ double l[(kTxTile + kTxTaps - 1) * 5 / 4 + 2];
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_al
 		if (threadIdx.x < 2) {  // peak_allowed = sqrt(mean power of the part * 10^(papr/10))  (ofdm.cc:1570-1578)
 			double t = 0;
 			for (int k = 0; k < nblk_mix; k++) t += power_part[((size_t)b * nblk_mix + k) * 2 + threadIdx.x];
-			const int n = threadIdx.x == 0 ? npre : total - npre;
+			const int n = threadIdx.x == 0 ? npre : ndata;
 			peak[threadIdx.x] = sqrt(t / n * (threadIdx.x == 0 ? papr_pre_lin : papr_data_lin));
 		}
 		__syncthreads();
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_al
 
 // NO_FILTER_MESSAGE (telecom_system.cc:537-544): the clipped pass-band frame, before the transmit FIRs
 template <typename OUT>
-__global__ void __launch_bounds__(256) k_tx_clip(const double *__restrict__ in_all, int total, int npre, double papr_pre_lin, double papr_data_lin,
+__global__ void __launch_bounds__(256) k_tx_clip(const double *__restrict__ in_all, int total, int npre, int ndata, double papr_pre_lin, double papr_data_lin,
 						   const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
 {
 	__shared__ double peak[2];
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) k_tx_clip(const double *__restrict__ in_a
 	if (threadIdx.x < 2) {
 		double t = 0;
 		for (int k = 0; k < nblk_mix; k++) t += power_part[((size_t)b * nblk_mix + k) * 2 + threadIdx.x];
-		const int n = threadIdx.x == 0 ? npre : total - npre;
+		const int n = threadIdx.x == 0 ? npre : ndata;
 		peak[threadIdx.x] = sqrt(t / n * (threadIdx.x == 0 ? papr_pre_lin : papr_data_lin));
 	}
 	__syncthreads();
@@ -612,22 +612,24 @@ cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s)
 {
 	const int total = (a.tm_host->pre + a.tm_host->S) * MB_FE_SYM;
 	const int nblk_mix = (total + 255) / 256;
-	if (a.tm_host->M == 200) k_tx_baseband_mfsk<<<a.n, 256, 0, s>>>(a.tm, a.tables, *a.tone, a.payload, a.bb, a.dbg_cw);
+	const int S_active = (a.S_active > 0 && a.S_active < a.tm_host->S) ? a.S_active : a.tm_host->S;
+	const int ndata = S_active * MB_FE_SYM;
+	if (a.tm_host->M == 200) k_tx_baseband_mfsk<<<a.n, 256, 0, s>>>(a.tm, a.tables, *a.tone, S_active, a.payload, a.bb, a.dbg_cw);
 	else k_tx_baseband<<<a.n, 256, mb_tx_smem_bytes(*a.tm_host), s>>>(a.tm, a.tables, a.payload, a.bb, a.dbg_cw);
 	k_tx_mix<<<dim3(nblk_mix, a.n), 256, 0, s>>>(a.tm, a.bb, a.start_sample, a.pb, a.power_part, nblk_mix);
 	const int npre = a.tm_host->pre * MB_FE_SYM;
 	const double pp = a.tm_host->papr_pre_lin, pd = a.tm_host->papr_data_lin;
 	if (a.no_filter) {
 		const dim3 g2(nblk_mix, a.n);
-		if (a.out_f32) k_tx_clip<float><<<g2, 256, 0, s>>>(a.pb, total, npre, pp, pd, a.power_part, nblk_mix, static_cast<float *>(a.out));
-		else k_tx_clip<double><<<g2, 256, 0, s>>>(a.pb, total, npre, pp, pd, a.power_part, nblk_mix, static_cast<double *>(a.out));
+		if (a.out_f32) k_tx_clip<float><<<g2, 256, 0, s>>>(a.pb, total, npre, ndata, pp, pd, a.power_part, nblk_mix, static_cast<float *>(a.out));
+		else k_tx_clip<double><<<g2, 256, 0, s>>>(a.pb, total, npre, ndata, pp, pd, a.power_part, nblk_mix, static_cast<double *>(a.out));
 		return cudaGetLastError();
 	}
 	const dim3 grid((total + kTxTile - 1) / kTxTile, a.n);
 	const double *c1 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c1), *c2 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c2);
-	k_tx_fir<true, double><<<grid, 256, 0, s>>>(a.pb, total, npre, pp, pd, c1, a.power_part, nblk_mix, a.p1);
-	if (a.out_f32) k_tx_fir<false, float><<<grid, 256, 0, s>>>(a.p1, total, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<float *>(a.out));
-	else k_tx_fir<false, double><<<grid, 256, 0, s>>>(a.p1, total, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<double *>(a.out));
+	k_tx_fir<true, double><<<grid, 256, 0, s>>>(a.pb, total, npre, ndata, pp, pd, c1, a.power_part, nblk_mix, a.p1);
+	if (a.out_f32) k_tx_fir<false, float><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<float *>(a.out));
+	else k_tx_fir<false, double><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<double *>(a.out));
 	return cudaGetLastError();
 }
 
@@ -637,8 +639,8 @@ cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, cons
 {
 	const dim3 grid((n + kTxTile - 1) / kTxTile, 1);
 	const double *c1 = reinterpret_cast<const double *>(tables + tm_host.off_c1), *c2 = reinterpret_cast<const double *>(tables + tm_host.off_c2);
-	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_in, n, 0, 0.0, 0.0, c1, nullptr, 0, d_tmp);
-	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0.0, 0.0, c2, nullptr, 0, d_out);
+	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_in, n, 0, 0, 0.0, 0.0, c1, nullptr, 0, d_tmp);
+	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0, 0.0, 0.0, c2, nullptr, 0, d_out);
 	return cudaGetLastError();
 }
 
@@ -678,7 +680,7 @@ cudaError_t mb_tx_pattern(const MbMfsk &plan, int use_break_tones, double fc, do
 	if (e == cudaSuccess) {
 		k_tx_pattern_baseband<<<1, 256, 0, s>>>(plan, use_break_tones, tone_amp / power_normalization * (std::sqrt(0.1) * boost), d_bb);
 		k_tx_mix<<<dim3(nblk, 1), 256, 0, s>>>(d_tm, d_bb, nullptr, d_pb, d_power_part, nblk);
-		k_tx_clip<double><<<dim3(nblk, 1), 256, 0, s>>>(d_pb, total, 0, tm.papr_pre_lin, tm.papr_data_lin, d_power_part, nblk, d_out);
+		k_tx_clip<double><<<dim3(nblk, 1), 256, 0, s>>>(d_pb, total, 0, total, tm.papr_pre_lin, tm.papr_data_lin, d_power_part, nblk, d_out);
 		e = cudaGetLastError();
 	}
 	cudaError_t e2 = cudaStreamSynchronize(s);

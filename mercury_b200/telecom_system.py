@@ -127,6 +127,27 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_receive_baseband(self._h, _vp(bb), _vp(out), C.byref(st)))
         return out, {n: getattr(st, n) for n, _ in RxStats._fields_ if n != "reserved"}
 
+    def get_configuration(self, SNR):
+        """char cl_telecom_system::get_configuration(double SNR) (telecom_system.cc:3036-3106): the gear-shift ladder."""
+        return int(self._L.mercury_b200_get_configuration(float(SNR)))
+
+    def measure_signal_only(self, captures):
+        """double measure_signal_only(double* data) (telecom_system.cc:1520-1541) on [n, capture_samples] captures -> dBm per capture."""
+        x = np.ascontiguousarray(captures)
+        if x.dtype not in _SAMPLE_FORMATS:
+            raise TypeError("captures must be float64, float32, int16 or int32")
+        x = x.reshape(-1, self.get_capture_samples())
+        out = np.zeros(x.shape[0], np.float64)
+        self._check(self._L.mercury_b200_measure_signal_only_batch(self._h, _vp(x), _SAMPLE_FORMATS[x.dtype], x.shape[0], _vp(out)))
+        return out
+
+    def set_mfsk_ctrl_mode(self, enable):
+        """void set_mfsk_ctrl_mode(bool) (telecom_system.cc:1572-1575) -> get_active_nsymb()."""
+        return int(self._L.mercury_b200_set_mfsk_ctrl_mode(self._h, int(bool(enable))))
+
+    def get_active_nsymb(self):
+        return int(self._L.mercury_b200_get_active_nsymb(self._h))
+
     def get_capture_samples(self):
         """Pass-band samples receive_byte() is handed: Nofdm * buffer_Nsymb * 4 (data_container.cc:133-153)."""
         return self._L.mercury_b200_get_capture_samples(self._h)

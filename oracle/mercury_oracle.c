@@ -277,6 +277,17 @@ static void mfsk_init(mo_mfsk *f, int M, int Nc, int nStreams)
 	for (int i = 0; i < 8; i++) f->break_tones[i] = M == 32 ? brk32[i] : brk16[i];
 }
 
+/* get_active_nsymb / get_active_nbits: telecom_system.cc:1577-1585. */
+static int active_nsymb(const mo_mode *m) { return (m->ctrl_mode && m->ctrl_nsymb > 0) ? m->ctrl_nsymb : m->Nsymb; }
+static int active_nbits(const mo_mode *m) { return (m->ctrl_mode && m->ctrl_nBits > 0) ? m->ctrl_nBits : m->nBits; }
+
+/* set_mfsk_ctrl_mode: telecom_system.cc:1572-1575.  Returns the active symbol count. */
+int mo_set_mfsk_ctrl_mode(mo_mode *m, int enable)
+{
+	m->ctrl_mode = enable && m->M == 200 && m->ctrl_nBits > 0 && m->ctrl_nBits < m->nBits;
+	return active_nsymb(m);
+}
+
 /* ROBUST_0..2 (common_defines.h:63-65, telecom_system.cc:2625-2645,2694-2700,1812-1817): MFSK modes, Nsymb = N / (nBits * nStreams). */
 static int mo_mode_init_mfsk(mo_mode *m, int config, int ldpc_iters, const char *ldpc_blob_path)
 {
@@ -289,6 +300,9 @@ static int mo_mode_init_mfsk(mo_mode *m, int config, int ldpc_iters, const char 
 	mfsk_init(&m->mfsk, config == 100 ? 32 : 16, MO_NC, config == 100 ? 1 : 2);
 	m->bits_per_symbol = m->mfsk.nBits * m->mfsk.nStreams;
 	m->Nsymb = MO_N / m->bits_per_symbol;
+	m->ctrl_nBits = config == 100 ? 1200 : (config == 101 ? 1400 : 0); /* telecom_system.cc:2966-2990 */
+	m->ctrl_nsymb = m->ctrl_nBits / m->bits_per_symbol;
+	m->ctrl_mode = 0;
 	m->Nc = MO_NC, m->Nfft = MO_NFFT, m->Ngi = MO_NGI, m->Nofdm = MO_NOFDM;
 	m->boost = (double)1.33f;
 	m->ls_window = 21;
@@ -525,7 +539,7 @@ void mo_tx_baseband(const mo_mode *m, const int *payload, int nBytes, double com
 		const mo_mfsk *f = &m->mfsk;
 		double complex *fr = calloc((size_t)m->Nsymb * MO_NC, sizeof(double complex));
 		double amp = sqrt((double)MO_NC / f->nStreams);
-		for (int s = 0; s < m->Nsymb; s++)
+		for (int s = 0; s < active_nsymb(m); s++) /* ctrl mode: only the first ctrl_nBits interleaved bits are sent (:414-416) */
 			for (int st = 0; st < f->nStreams; st++) {
 				int off = s * m->bits_per_symbol + st * f->nBits, tone = 0;
 				for (int bb = 0; bb < f->nBits; bb++)
@@ -742,9 +756,11 @@ static void mo_rx_tail_mfsk(const mo_mode *m, const double complex *bb, mo_rx_ou
 	double complex *Y = malloc(sizeof(double complex) * cells);
 	float llr[MO_N], llr_cw[MO_N + 8];
 	int bits[MO_N], bytes[MO_N / 8 + 1];
-	for (int s = 0; s < S; s++) symbol_demod(m, bb + (size_t)s * m->Nofdm, Y + s * MO_NC);
+	for (int c = 0; c < cells; c++) Y[c] = 0;
+	for (int s = 0; s < active_nsymb(m); s++) symbol_demod(m, bb + (size_t)s * m->Nofdm, Y + s * MO_NC);
 	if (o->Y) memcpy(o->Y, Y, sizeof(double complex) * cells);
-	mfsk_demod(&m->mfsk, Y, m->nBits, llr);
+	mfsk_demod(&m->mfsk, Y, active_nbits(m), llr);
+	for (int i = active_nbits(m); i < m->nBits; i++) llr[i] = 0.0f; /* :1188-1197: punctured positions are erasures */
 	free(Y);
 	if (o->llr_demod) memcpy(o->llr_demod, llr, sizeof(float) * m->nBits);
 	int bs = m->bit_il_block, nb = m->nBits / bs;
@@ -1232,7 +1248,7 @@ static void mo_receive_byte_mfsk(const mo_mode *m, const double *passband, int *
 	int delay = mo_time_sync_mfsk(m, bbi, buf, search_start); /* :686 */
 	int pream_symb_loc = delay / sym;
 	if (pream_symb_loc < 1) pream_symb_loc = 1;
-	int frame_end = delay + (pre + S) * sym; /* :702-715 */
+	int frame_end = delay + (pre + active_nsymb(m)) * sym; /* :702-715 */
 	if (frame_end > buf) {
 		overflow = (frame_end - buf + sym - 1) / sym;
 	} else {
@@ -1715,11 +1731,12 @@ static int transmit_byte_impl(mo_mode *m, const int *payload, int nBytes, double
 		bbd[j] *= sqrt(t->output_power) * mfsk_boost;
 	}
 	unsigned long start = (unsigned long)*start_sample_inout;
-	double *pb = malloc(sizeof(double) * total), *p1 = malloc(sizeof(double) * total);
+	double *pb = calloc(total, sizeof(double)), *p1 = malloc(sizeof(double) * total);
+	int Sa = active_nsymb(m); /* ctrl frames: only the active symbols are modulated; what follows in the reference's buffer is stale, zero here */
 	b2p(m, bbp, No * pre, pb, f->fc, &start); /* :531-532 */
-	b2p(m, bbd, No * S, pb + No * pre * rate, f->fc, &start);
+	b2p(m, bbd, No * Sa, pb + No * pre * rate, f->fc, &start);
 	peak_clip(pb, No * pre * rate, t->preamble_papr); /* :534-535 */
-	peak_clip(pb + No * pre * rate, No * S * rate, t->data_papr);
+	peak_clip(pb + No * pre * rate, No * Sa * rate, t->data_papr);
 	if (no_filter) {
 		memcpy(out, pb, sizeof(double) * total);
 	} else {

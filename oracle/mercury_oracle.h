@@ -72,6 +72,7 @@ typedef struct mo_mode {
 	mo_frontend fe;
 	mo_tx tx;
 	mo_mfsk mfsk; /* ROBUST_0..2 (config 100..102, M == 200) only */
+	int ctrl_nBits, ctrl_nsymb, ctrl_mode; /* MFSK control frames (telecom_system.cc:1572-1585, 2966-2995) */
 } mo_mode;
 
 typedef struct mo_rx_out {
@@ -123,6 +124,7 @@ void mo_ack_pattern_baseband(const mo_mode *m, int use_break_tones, double compl
 void mo_mfsk_tables(const mo_mode *m, int *out /*[32]*/);
 int mo_generate_pattern_passband(mo_mode *m, int use_break_tones, double *out /*[16 * 272 * 4]*/, double *start_sample_inout);
 double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int size, int use_break_tones, int *matched_out);
+int mo_set_mfsk_ctrl_mode(mo_mode *m, int enable);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

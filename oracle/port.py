@@ -57,6 +57,8 @@ def lib():
         L.mo_detect_ack_pattern.restype = C.c_double
         L.mo_ack_pattern_baseband.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.mo_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
+        L.mo_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
+        L.mo_set_mfsk_ctrl_mode.restype = C.c_int
         L.mo_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mo_generate_pattern_passband.restype = C.c_int
         L.mo_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -73,6 +73,8 @@ def lib():
         L.mref_detect_ack_pattern.restype = C.c_double
         L.mref_ack_pattern_baseband.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.mref_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
+        L.mref_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
+        L.mref_set_mfsk_ctrl_mode.restype = C.c_int
         L.mref_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_generate_pattern_passband.restype = C.c_int
         L.mref_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -216,6 +218,10 @@ class FrontEndMixin:
         m = np.zeros(1, np.int32)
         v = getattr(self._felib(), self._fe + "detect_pattern_from_passband")(self.h, _p(d), d.size, int(use_break_tones), _p(m))
         return float(v), int(m[0])
+
+    def set_mfsk_ctrl_mode(self, enable):
+        """set_mfsk_ctrl_mode(bool) -> get_active_nsymb() (shortened control frames in ROBUST_0 / ROBUST_1)."""
+        return int(getattr(self._felib(), self._fe + "set_mfsk_ctrl_mode")(self.h, int(bool(enable))))
 
     def frontend_tables(self):
         nt = np.zeros(2, np.int32)

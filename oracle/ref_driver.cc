@@ -235,7 +235,8 @@ void mref_tx_baseband(void *h, const int *payload, int nBytes, double *out_cplx,
 	for (int i = 0; i < ts.ldpc.P; i++) dc.encoded_data[nReal + i] = dc.encoded_data[i + ts.ldpc.K];
 	interleaver(dc.encoded_data, dc.bit_interleaved_data, dc.nBits, ts.bit_interleaver_block_size);
 	if (ts.M == MOD_MFSK) {
-		ts.mfsk.mod(dc.bit_interleaved_data, dc.nBits, dc.ofdm_framed_data); /* telecom_system.cc:411-416: one-hot tones, no framer */
+		for (int i = 0; i < dc.Nsymb * dc.Nc; i++) dc.ofdm_framed_data[i] = 0;
+		ts.mfsk.mod(dc.bit_interleaved_data, ts.get_active_nbits(), dc.ofdm_framed_data); /* telecom_system.cc:411-416: one-hot tones, no framer */
 	} else {
 		ts.psk.mod(dc.bit_interleaved_data, dc.nBits, dc.modulated_data);
 		interleaver(dc.modulated_data, dc.ofdm_time_freq_interleaved_data, dc.nData, ts.time_freq_interleaver_block_size);
@@ -285,7 +286,8 @@ void mref_rx_tail(void *h, const double *baseband, mref_rx_out *o)
 	if (ts.M == MOD_MFSK) {
 		/* MFSK branch of the tail (telecom_system.cc:1142-1198): non-coherent energy detection, no AGC / channel estimate / gate */
 		if (o->Y) memcpy(o->Y, dc.ofdm_symbol_demodulated_data, sizeof(double) * 2 * cells);
-		ts.mfsk.demod(dc.ofdm_symbol_demodulated_data, dc.nBits, dc.demodulated_data);
+		ts.mfsk.demod(dc.ofdm_symbol_demodulated_data, ts.get_active_nbits(), dc.demodulated_data);
+		for (int i = ts.get_active_nbits(); i < dc.nBits; i++) dc.demodulated_data[i] = 0.0f; /* :1188-1197: punctured positions = erasures */
 		if (o->llr_demod) memcpy(o->llr_demod, dc.demodulated_data, sizeof(float) * dc.nBits);
 		deinterleaver(dc.demodulated_data, dc.deinterleaved_data, dc.nBits, ts.bit_interleaver_block_size);
 		for (int i = ts.ldpc.P - 1; i >= 0; i--) dc.deinterleaved_data[i + nReal + nVirtual] = dc.deinterleaved_data[i + nReal];
@@ -720,6 +722,14 @@ double mref_detect_pattern_from_passband(void *h, const double *data, int size, 
 	double m = use_break_tones ? ts.detect_break_pattern_from_passband(copy, size, matched) : ts.detect_ack_pattern_from_passband(copy, size, matched);
 	delete[] copy;
 	return m;
+}
+
+/* MFSK control frames (telecom_system.cc:1572-1585, 2966-2995): shortened frames in ROBUST_0 / ROBUST_1. Returns get_active_nsymb(). */
+int mref_set_mfsk_ctrl_mode(void *h, int enable)
+{
+	cl_telecom_system &ts = T(h);
+	ts.set_mfsk_ctrl_mode(enable != 0);
+	return ts.get_active_nsymb();
 }
 
 }  // extern "C"

@@ -60,6 +60,21 @@ int main(int argc, char **argv)
 				printf("\n");
 			}
 		}
+		{  // the TX-side and ARQ-facing members compile and run with the reference's signatures
+			std::vector<double> tx((size_t)mercury_b200_get_total_frame_size(telecom_system.handle()));
+			std::vector<int> msg((size_t)telecom_system.get_frame_size_bytes(), 7);
+			telecom_system.transmit_byte(msg.data(), (int)msg.size(), tx.data(), MERCURY_B200_NO_FILTER_MESSAGE);
+			std::vector<double> pat(16 * 1088), filtered(16 * 1088);
+			const int np = telecom_system.generate_ack_pattern_passband(pat.data());
+			telecom_system.fir_tx_apply(pat.data(), filtered.data(), np);
+			int matched = 0;
+			std::vector<double> rxbuf(40 * 1088, 0.0);
+			for (int i = 0; i < np; i++) rxbuf[5 * 1088 + i] = pat[(size_t)i];
+			const double metric = telecom_system.detect_ack_pattern_from_passband(rxbuf.data(), (int)rxbuf.size(), &matched);
+			printf("tx_side samples %zu pattern %d ack_metric %.3f matched %d break_metric %.3f config_for_5dB %d active_nsymb %d\n", tx.size(), np, metric, matched,
+			       telecom_system.detect_break_pattern_from_passband(rxbuf.data(), (int)rxbuf.size()), (int)telecom_system.get_configuration(5.0),
+			       telecom_system.get_active_nsymb());
+		}
 		telecom_system.load_configuration(99);  // ignored, like the reference (telecom_system.cc:2494-2497)
 		printf("after_bad_config frame_bytes %d\n", telecom_system.get_frame_size_bytes());
 	} catch (const std::exception &e) {

@@ -48,3 +48,14 @@ def test_host_side_table_build_and_errors():
     assert L.mercury_b200_get_frame_size_bytes(None) == -4 and L.mercury_b200_kernel_launches(None) == 0
     out = np.zeros(8, np.float32)
     assert L.mercury_b200_synth_frames(_lib.LDPC_TABLES.encode(), 99, 1, 0, 300.0, None, out.ctypes.data_as(C.c_void_p), None, 1) == -1
+
+
+def test_get_configuration_ladder_matches_the_reference_thresholds():
+    """get_configuration(SNR) (telecom_system.cc:3036-3106): host-only, checked against the ladder restated from the reference."""
+    from mercury_b200 import _lib
+    L = _lib.lib()
+    rungs = [(12.5, 15), (9, 14), (7.5, 13), (6.5, 12), (4, 11), (3, 10), (1.5, 9), (0.5, 8), (-0.5, 7), (-1.5, 6), (-2.5, 5), (-3.5, 4),
+             (-4.5, 3), (-6, 2), (-7.5, 1)]
+    for thr, cfg in rungs:
+        assert L.mercury_b200_get_configuration(thr + 1e-9) == cfg and L.mercury_b200_get_configuration(thr) == cfg - 1
+    assert L.mercury_b200_get_configuration(-50.0) == 0 and L.mercury_b200_get_configuration(99.0) == 15

@@ -63,6 +63,9 @@ def test_cpp_mirror_reproduces_the_reference_frame(exe, golden_dir, cfg):
     want = ((ref_bytes[:, None] >> np.arange(8)[None, :]) & 1).reshape(-1)
     assert np.array_equal(bits, want)  # receive_bit: LSB first, CRC bytes included (telecom_system.cc:636-644)
     assert int(lines["after_bad_config"].split()[1]) == fb
+    t = lines["tx_side"].split()  # transmit_byte(NO_FILTER), generate/detect pattern, fir_tx_apply, get_configuration, get_active_nsymb
+    assert int(t[1]) == (mb.MODES[cfg]["Nsymb"] + mb.MODES[cfg]["preamble_nSymb"]) * 1088 and int(t[3]) == 16 * 1088
+    assert float(t[5]) > 14 and int(t[7]) == 16 and float(t[9]) < 6 and int(t[11]) == 11 and int(t[13]) == mb.MODES[cfg]["Nsymb"]
 
 
 @pytest.mark.gpu

@@ -78,6 +78,10 @@ def test_receive_byte_scenarios(ts, cfg):
         for i in (0, 1):
             _compare(r.receive_byte2(conv[i], int(states["delay_of_last_decoded_message"][i]), float(states["freq_offset_of_last_decoded_message"][i])),
                      st_i[i], p_i[i], None, f"cfg{cfg}/{cases[i]}/{pcm.dtype}")
+    # measure_signal_only (telecom_system.cc:1520-1541): the same mix + time-sync FIR + mean power, nothing else
+    dbm = ts.measure_signal_only(caps)
+    for i in range(len(cases)):
+        assert abs(dbm[i] - oracle_out[i]["signal_dbm"]) <= 1e-9 or (np.isinf(dbm[i]) and np.isinf(oracle_out[i]["signal_dbm"])), cases[i]
     # ... and the single-capture call in the reference's own types
     for i in (0, len(cases) - 1):
         one = states[i:i + 1].copy()

@@ -205,3 +205,47 @@ def test_arq_tone_pattern_calls_in_any_configuration(ts, cfg):
     assert res["ack_metric"][0] > 12 and res["break_metric"][1] > 12 and res["ack_metric"][2] < 6
     res32 = ts.detect_patterns_from_passband_batch(bufs.astype(np.float32))  # float32 captures: the same values
     assert res32.tobytes() == res.tobytes()
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_mfsk_control_frames(ts, cfg):
+    """set_mfsk_ctrl_mode(true): shortened control frames (ROBUST_0 240 of 320 symbols, ROBUST_1 175 of 200, ROBUST_2 unchanged) through
+    transmit_byte, the tail and the whole receive_byte, against the oracle in the same mode."""
+    o, p = _oracle(cfg), port.Port(cfg, 50)
+    g = ts.load_configuration(cfg, 50)
+    na = ts.set_mfsk_ctrl_mode(True)
+    assert na == o.set_mfsk_ctrl_mode(True) == p.set_mfsk_ctrl_mode(True) == {100: 240, 101: 175, 102: 200}[cfg] == ts.get_active_nsymb()
+    rng = np.random.default_rng(70 + cfg)
+    pl = rng.integers(0, 256, g["frame_bytes"]).astype(np.uint8)
+    # tail: base-band frames whose symbols past the active ones are silence
+    x = o.tx_baseband(pl)
+    x[na * 272:] = 0
+    xs = np.stack([(x + sg * (rng.standard_normal(x.size) + 1j * rng.standard_normal(x.size))).astype(np.complex64) for sg in (0.0, 20.0, 45.0, 70.0)])
+    payload, st, llr = ts.demod_decode_batch(xs.reshape(4, g["Nsymb"], 272), want_llr=True)
+    for i in range(4):
+        r = o.rx_tail(xs[i].astype(np.complex128))
+        tol = 1e-4 * np.maximum(np.abs(r["llr_cw"]), np.median(np.abs(r["llr_cw"])) + 1e-3)
+        assert (np.abs(llr[i] - r["llr_cw"]) <= tol).all(), (cfg, i)
+        assert int(st["message_decoded"][i]) == r["decoded"] and int(st["iterations_done"][i]) == r["iterations"], (cfg, i)
+        if r["decoded"]:
+            assert np.array_equal(payload[i], pl)
+    # transmit: only the active symbols are modulated
+    tx = ts.transmit_byte_batch(pl[None, :], np.array([0], np.uint64))[0]
+    want, _ = o.transmit_byte2(pl, 0)
+    assert np.abs(tx - want).max() <= 1e-9 * np.abs(want).max()
+    L = (4 + na) * 1088
+    assert np.abs(tx[L + 200:]).max() <= 1e-12 if L + 200 < tx.size else True  # silence after the frame (past the FIR tails)
+    # the whole receive_byte on a capture holding that control frame
+    if ref.available():
+        n = o.capture_samples()
+        cap = np.zeros(n)
+        d = 30 * 1088 + 21
+        cap[d:d + L] += want[:L]
+        cap = (cap + rng.normal(0, 0.05, n)).astype(np.float32)
+        rr = o.receive_byte2(cap.astype(np.float64))
+        pay, rs, _ = ts.receive_byte_batch(cap)
+        assert int(rs["delay"][0]) == rr["delay"] and int(rs["message_decoded"][0]) == rr["decoded"] == 1
+        assert int(rs["iterations_done"][0]) == rr["iterations"] and np.array_equal(pay[0], pl)
+    # load_configuration switches the mode off, like the reference (telecom_system.cc:2989)
+    ts.load_configuration(cfg, 50)
+    assert ts.get_active_nsymb() == g["Nsymb"]

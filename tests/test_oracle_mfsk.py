@@ -115,3 +115,30 @@ def test_arq_tone_pattern_calls_bit_exact(cfg):
         for which in (False, True):
             assert r.detect_pattern_from_passband(buf, which) == p.detect_pattern_from_passband(buf, which)
         assert r.detect_pattern_from_passband(buf, brk)[1] == 16
+
+
+@pytest.mark.parametrize("cfg", [100, 101])
+def test_mfsk_control_frames_bit_exact(cfg):
+    """set_mfsk_ctrl_mode(true) (telecom_system.cc:1572-1585, 2966-2995): TX, tail and receive_byte with shortened control frames."""
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    na = r.set_mfsk_ctrl_mode(True)
+    assert na == p.set_mfsk_ctrl_mode(True) == {100: 240, 101: 175}[cfg]
+    rng = np.random.default_rng(cfg)
+    pl = rng.integers(0, 256, r.frame_bytes)
+    xr, xp = r.tx_baseband(pl), p.tx_baseband(pl)
+    assert np.array_equal(xr[:na * 272], xp[:na * 272]) and not xp[na * 272:].any()
+    for sg in (0.0, 20.0, 45.0):
+        x = xp + sg * (rng.standard_normal(xp.size) + 1j * rng.standard_normal(xp.size))
+        a, b = r.rx_tail(x), p.rx_tail(x)
+        assert a["iterations"] == b["iterations"] and a["decoded"] == b["decoded"]
+        for k in ("llr_cw", "bits", "payload"):
+            assert np.array_equal(a[k], b[k]), (sg, k)
+    a, sa = r.transmit_byte2(pl, 0)
+    b, sb = p.transmit_byte2(pl, 0)
+    assert sa == sb == (4 + na) * 1088 and np.array_equal(a, b)
+    n = r.capture_samples()
+    cap = np.zeros(n)
+    cap[20 * 1088 + 17:20 * 1088 + 17 + (4 + na) * 1088] += b[:(4 + na) * 1088]
+    cap = (cap + rng.normal(0, 0.05, n)).astype(np.float32).astype(np.float64)
+    ra, rb = r.receive_byte2(cap), p.receive_byte2(cap)
+    assert all(ra[k] == rb[k] for k in ref.STAT12) and np.array_equal(ra["payload"], rb["payload"]) and np.array_equal(ra["payload"], pl)
