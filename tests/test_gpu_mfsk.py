@@ -232,15 +232,17 @@ def test_mfsk_control_frames(ts, cfg):
     # transmit: only the active symbols are modulated
     tx = ts.transmit_byte_batch(pl[None, :], np.array([0], np.uint64))[0]
     want, _ = o.transmit_byte2(pl, 0)
-    assert np.abs(tx - want).max() <= 1e-9 * np.abs(want).max()
     L = (4 + na) * 1088
-    assert np.abs(tx[L + 200:]).max() <= 1e-12 if L + 200 < tx.size else True  # silence after the frame (past the FIR tails)
+    # the reference leaves whatever its TX buffer held before behind the active part (stale samples of earlier frames, which its
+    # FIRs also smear over the last 96 active samples); here silence follows.  Compare the part that is defined.
+    assert np.abs(tx[:L - 100] - want[:L - 100]).max() <= 1e-9 * np.abs(want).max()
+    assert L + 200 >= tx.size or np.abs(tx[L + 200:]).max() <= 1e-12
     # the whole receive_byte on a capture holding that control frame
     if ref.available():
         n = o.capture_samples()
         cap = np.zeros(n)
         d = 30 * 1088 + 21
-        cap[d:d + L] += want[:L]
+        cap[d:d + L - 100] += want[:L - 100]
         cap = (cap + rng.normal(0, 0.05, n)).astype(np.float32)
         rr = o.receive_byte2(cap.astype(np.float64))
         pay, rs, _ = ts.receive_byte_batch(cap)
