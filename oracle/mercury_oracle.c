@@ -1377,7 +1377,31 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 		skip_h_retry_point:
 			while (sync_trials <= f->trials_max) {
 				if (sync_trials == f->trials_max && f->use_last_time && last_delay != -1) delay = last_delay; /* :945-948 */
-				else /* :1017 (trial 1's coarse frequency search is off by default, gui_state.h:143) */
+				else if (sync_trials == 1 && f->coarse_freq_sync) { /* :949-1013: +-30 Hz search (g_gui_state.coarse_freq_sync_enabled) */
+					const double freq_search[3] = {-30.0, 0.0, 30.0};
+					double best_correlation = 0.0, best_offset = 0.0, zero_hz_correlation = 0.0;
+					int best_delay = delay;
+					for (int i = 0; i < 3; i++) {
+						p2b(m, passband, buf, bbi, f->fc + freq_search[i], 0, scratch);
+						double corr;
+						int d = time_sync(m, bbi, m->Nofdm * (2 * pre + S) * rate, rate, 0, step, 1, &corr, loc, vals);
+						if (fabs(freq_search[i]) < 0.1) zero_hz_correlation = corr;
+						if (corr > best_correlation) {
+							best_correlation = corr;
+							best_offset = freq_search[i];
+							best_delay = d;
+						}
+					}
+					if (fabs(best_offset) > 1.0 && best_correlation > 0.5 && best_correlation > zero_hz_correlation + 0.1) {
+						coarse_freq_offset = best_offset;
+						delay = best_delay;
+						pream_symb_loc = delay / sym;
+						if (pream_symb_loc < 1) pream_symb_loc = 1;
+					}
+					p2b(m, passband, buf, bbi, f->fc + coarse_freq_offset, 0, scratch);
+					delay = (pream_symb_loc - 1) * sym +
+						time_sync(m, bbi + (pream_symb_loc - 1) * sym, (pre + 4) * sym, rate, sync_trials, 1, f->trials_max, NULL, loc, vals);
+				} else /* :1017 */
 					delay = (pream_symb_loc - 1) * sym +
 						time_sync(m, bbi + (pream_symb_loc - 1) * sym, (pre + 4) * sym, rate, sync_trials, 1, f->trials_max, NULL, loc, vals);
 				if (delay < 0) delay = 0;
@@ -1924,3 +1948,7 @@ double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int
 	free(bbi), free(scratch);
 	return v;
 }
+
+
+/* g_gui_state.coarse_freq_sync_enabled (gui_state.h:143): the optional +-30 Hz search of trial 1. */
+void mo_set_coarse_freq_sync(mo_mode *m, int enable) { m->fe.coarse_freq_sync = enable != 0; }

@@ -28,7 +28,7 @@
 
 /* RX front-end constants (physical_config.cc:59,79-101) and the two receive FIR designs (fir_filter.cc:45-163). */
 typedef struct mo_frontend {
-	int interp, buffer_Nsymb, trials_max, use_last_time, use_last_freq, ntaps_ts, ntaps_data;
+	int interp, buffer_Nsymb, trials_max, use_last_time, use_last_freq, ntaps_ts, ntaps_data, coarse_freq_sync;
 	double fs, fc, amp, bandwidth, ignore_limit;
 	double c_ts[64], c_data[64];
 } mo_frontend;
@@ -125,6 +125,7 @@ void mo_mfsk_tables(const mo_mode *m, int *out /*[32]*/);
 int mo_generate_pattern_passband(mo_mode *m, int use_break_tones, double *out /*[16 * 272 * 4]*/, double *start_sample_inout);
 double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int size, int use_break_tones, int *matched_out);
 int mo_set_mfsk_ctrl_mode(mo_mode *m, int enable);
+void mo_set_coarse_freq_sync(mo_mode *m, int enable);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

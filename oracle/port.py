@@ -59,6 +59,7 @@ def lib():
         L.mo_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mo_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
         L.mo_set_mfsk_ctrl_mode.restype = C.c_int
+        L.mo_set_coarse_freq_sync.argtypes = [C.c_void_p, C.c_int]
         L.mo_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mo_generate_pattern_passband.restype = C.c_int
         L.mo_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -75,6 +75,7 @@ def lib():
         L.mref_mfsk_tables.argtypes = [C.c_void_p, C.c_void_p]
         L.mref_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
         L.mref_set_mfsk_ctrl_mode.restype = C.c_int
+        L.mref_set_coarse_freq_sync.argtypes = [C.c_int]
         L.mref_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_generate_pattern_passband.restype = C.c_int
         L.mref_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -218,6 +219,13 @@ class FrontEndMixin:
         m = np.zeros(1, np.int32)
         v = getattr(self._felib(), self._fe + "detect_pattern_from_passband")(self.h, _p(d), d.size, int(use_break_tones), _p(m))
         return float(v), int(m[0])
+
+    def set_coarse_freq_sync(self, enable):
+        """g_gui_state.coarse_freq_sync_enabled: the optional +-30 Hz search of trial 1 (GLOBAL in the reference, per mode object in the port)."""
+        if self._fe == "mref_":
+            self._felib().mref_set_coarse_freq_sync(int(bool(enable)))
+        else:
+            self._felib().mo_set_coarse_freq_sync(self.h, int(bool(enable)))
 
     def set_mfsk_ctrl_mode(self, enable):
         """set_mfsk_ctrl_mode(bool) -> get_active_nsymb() (shortened control frames in ROBUST_0 / ROBUST_1)."""

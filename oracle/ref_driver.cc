@@ -21,6 +21,7 @@
 #include <complex>
 
 #include "physical_layer/telecom_system.h"
+#include "gui/gui_state.h"
 
 namespace {
 
@@ -731,5 +732,9 @@ int mref_set_mfsk_ctrl_mode(void *h, int enable)
 	ts.set_mfsk_ctrl_mode(enable != 0);
 	return ts.get_active_nsymb();
 }
+
+/* The optional coarse frequency search of trial 1 (telecom_system.cc:949-1013) is switched by g_gui_state.coarse_freq_sync_enabled
+ * (gui_state.h:143, off by default; the GUI / ini file turn it on for HF radio use). */
+void mref_set_coarse_freq_sync(int enable) { g_gui_state.coarse_freq_sync_enabled.store(enable != 0); }
 
 }  // extern "C"

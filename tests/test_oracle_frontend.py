@@ -51,3 +51,27 @@ def test_port_against_frontend_fixture(path):
     assert np.array_equal(b["payload"], g["rx_payload"])
     assert b["last_delay"] == g["state_out"][0] and b["last_freq"] == g["state_out"][1]
     assert np.array_equal(b["baseband"], g["baseband"])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libmercury_ref.so not built")
+def test_optional_coarse_frequency_search_restated():
+    """g_gui_state.coarse_freq_sync_enabled (off by default): the +-30 Hz search of trial 1 (telecom_system.cc:949-1013) is restated in the
+    oracle and pinned here; the product does not build it.  A carrier offset large enough to need it (> 23 Hz, half a
+    carrier spacing) already fails the Schmidl-Cox gates before any trial runs -- the real part of the lag-1024 correlation turns negative --
+    so the branch is only reachable where Moose alone would have coped."""
+    r, p = ref.Ref(8, 50), port.Port(8, 50)
+    rng = np.random.default_rng(3)
+    n = r.capture_samples()
+    try:
+        for df in (28.0, 6.0, -12.0):
+            for en in (True, False):
+                r.set_coarse_freq_sync(en), p.set_coarse_freq_sync(en)
+                pl = rng.integers(0, 256, r.frame_bytes)
+                tx = r.transmit_byte(pl)
+                d = int(rng.integers(6000, 30000))
+                cap = np.zeros(n)
+                cap[d:d + tx.size] += tx
+                cap = (fc.freq_shift(cap, df) + rng.normal(0, 0.25 if df < 0 else 0.01, n)).astype(np.float32).astype(np.float64)
+                _same(r.receive_byte2(cap), p.receive_byte2(cap))
+    finally:
+        r.set_coarse_freq_sync(False)
