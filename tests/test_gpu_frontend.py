@@ -119,3 +119,38 @@ def test_receive_byte_many_links_against_port(ts):
         o = p.receive_byte2(caps[i])
         _compare(o, st[i], payload[i], None, f"link{i}")
     assert int(st["message_decoded"].sum()) >= n // 2
+
+
+def test_chunked_and_edge_arguments(ts, golden_dir, monkeypatch):
+    """Chunk boundaries (a handle whose device and host chunks are 5 and 3 captures), empty batches and bad arguments."""
+    g = np.load(os.path.join(golden_dir, "frontend_mode08_clean.npz"))
+    cap = g["capture"].astype(np.float32)
+    caps = np.stack([np.roll(cap, 53 * i) for i in range(13)])
+    ts.load_configuration(8, 50)
+    want_p, want_s, _ = ts.receive_byte_batch(caps)
+    monkeypatch.setenv("MERCURY_B200_FE_CHUNK", "5")
+    monkeypatch.setenv("MERCURY_B200_FE_HOST_CHUNK", "3")
+    t2 = mb.TelecomSystemB200(0)
+    try:
+        t2.load_configuration(8, 50)
+        p2, s2, _ = t2.receive_byte_batch(caps)
+        assert np.array_equal(p2, want_p) and s2.tobytes() == want_s.tobytes()
+        import torch
+        d = torch.from_numpy(caps).cuda()
+        d_st = torch.from_numpy(mb.new_receive_stats(13).view(np.uint8).reshape(13, -1)).cuda()
+        d_out = torch.zeros((13, want_p.shape[1]), dtype=torch.uint8, device="cuda")
+        t2.receive_byte_batch_device(d, mb.SAMPLES_F32, 13, d_out, d_st, stream=torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(d_out.cpu().numpy(), want_p)
+        assert d_st.cpu().numpy().view(mb.RECEIVE_STATS_DTYPE).reshape(-1).tobytes() == want_s.tobytes()
+        # empty batch: nothing to do, no error
+        e_p, e_s, _ = t2.receive_byte_batch(np.zeros((0, t2.get_capture_samples()), np.float32))
+        assert e_p.shape[0] == 0 and e_s.shape[0] == 0
+        with pytest.raises(TypeError):
+            t2.receive_byte_batch(np.zeros(t2.get_capture_samples(), np.int64))
+        with pytest.raises(ValueError):
+            t2.receive_byte_batch(np.zeros(1000, np.float32))
+        with pytest.raises(mb.MercuryB200Error):
+            t2.load_configuration(55, 50)
+    finally:
+        t2.close()
+    assert int(want_s["message_decoded"].sum()) == 13
