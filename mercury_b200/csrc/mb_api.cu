@@ -956,7 +956,7 @@ int tx_ensure_mode(mercury_b200_t *h)
 			if (e != cudaSuccess) return cuda_fail(h, e, "front-end constants");
 			h->fe_ready = true;
 		}
-		MB_CUDA(h, mb_tx_init());
+		MB_CUDA(h, mb_tx_init(h->fe_const));
 		MB_CUDA(h, cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
 		w.init_done = true;
 	}

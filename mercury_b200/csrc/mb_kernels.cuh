@@ -170,7 +170,7 @@ struct MbTxArgs {
 
 std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
 std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, const MbMfsk &t, const MbFeConst &fe, MbTxMode *tm, std::vector<uint8_t> *bytes);
-cudaError_t mb_tx_init();
+cudaError_t mb_tx_init(const MbFeConst &fe);
 cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s);
 // generate_ack / generate_break_pattern_passband (telecom_system.cc:1589-1631,1657-1689): 16 hopped tones of the dedicated 16-MFSK plan
 cudaError_t mb_tx_pattern(const MbMfsk &plan, int use_break_tones, double fc, double Ts, double amp, unsigned long long start_sample, double2 *d_bb, double *d_pb,

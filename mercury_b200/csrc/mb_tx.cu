@@ -28,6 +28,9 @@ constexpr int kTxTaps = 97;   // (int)(4 / (1000 / 24000)) = 96 -> odd 97 (fir_f
 constexpr int kTxHalf = 48;
 constexpr int kTxTile = 1024;
 
+// FIR_tx1 / FIR_tx2 (mode independent): in constant memory so that every tap's coefficient is an operand of the DFMA, not a load
+__constant__ double tx_c[2][kTxTaps + 1];
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // ---- bits -> framed grid -> IDFT + guard interval -> scaled base-band symbols (preamble first) ----
@@ -115,18 +118,22 @@ __global__ void __launch_bounds__(256) k_tx_baseband(const MbTxMode *__restrict_
 		Xd[cell] = cmul(cons[loc], pre_eq[cell % MB_NC]);
 	}
 	__syncthreads();
-	// symbol_mod: zero_padder (carriers c < 25 -> bins 231 + c, c >= 25 -> bins c - 24), unscaled IFFT, guard interval = last 16 samples
+	// symbol_mod: zero_padder (carriers c < 25 -> bins 231 + c, c >= 25 -> bins c - 24), unscaled IFFT, guard interval = last 16 samples.
+	// Thread n evaluates x[n] = w^231 * P_lo(w) + w * P_hi(w) with w = exp(2 pi i n / 256) by Horner's rule: two 24-step chains of complex
+	// FMAs on broadcast carrier reads, no twiddle table (the per-carrier gather W[(bin * n) & 255] was this kernel's bottleneck).
 	double2 *bb = bb_all + (size_t)b * (tm.pre + tm.S) * MB_NOFDM;
+	const double2 w = W[tid], w231 = W[(231 * tid) & 255];
 	for (int s = 0; s < tm.pre + tm.S; s++) {
 		const double2 *Xs = X + s * MB_NC;
-		double ar = 0, ai = 0;
-#pragma unroll 5
-		for (int c = 0; c < MB_NC; c++) {
-			const int bin = c < MB_NC / 2 ? c + MB_NFFT - MB_NC / 2 : c - MB_NC / 2 + 1;
-			const double2 w = W[(bin * tid) & 255], x = Xs[c];
-			ar += x.x * w.x - x.y * w.y;
-			ai += x.x * w.y + x.y * w.x;
+		double2 lo = Xs[MB_NC / 2 - 1], hi = Xs[MB_NC - 1];
+#pragma unroll 8
+		for (int c = MB_NC / 2 - 2; c >= 0; c--) {
+			const double2 a = Xs[c], h2 = Xs[MB_NC / 2 + c];
+			lo = make_double2(fma(lo.x, w.x, fma(-lo.y, w.y, a.x)), fma(lo.x, w.y, fma(lo.y, w.x, a.y)));
+			hi = make_double2(fma(hi.x, w.x, fma(-hi.y, w.y, h2.x)), fma(hi.x, w.y, fma(hi.y, w.x, h2.y)));
 		}
+		const double2 tl = cmul(lo, w231), th = cmul(hi, w);
+		const double ar = tl.x + th.x, ai = tl.y + th.y;
 		const double sc = s < tm.pre ? tm.scale_pre : tm.scale_data;  // / power_normalization * sqrt(output_power_Watt) [* preamble boost] (:517-527)
 		const double2 v = make_double2(ar * sc, ai * sc);
 		bb[s * MB_NOFDM + MB_NGI + tid] = v;
@@ -265,9 +272,9 @@ __global__ void __launch_bounds__(256) k_tx_mix(const MbTxMode *__restrict__ tm_
 }
 
 // ---- one 97-tap real FIR pass (zero-phase, fir_filter.cc:189-210); pass 1 clips its input on the fly (peak_clip) ----
-template <bool CLIP, typename OUT>
+template <bool CLIP, typename OUT, int WHICH>
 __global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_all, int total, int npre, int ndata, double papr_pre_lin, double papr_data_lin,
-						  const double *__restrict__ coef_off_base, const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
+						  const double *__restrict__ power_part, int nblk_mix, OUT *__restrict__ out_all)
 {
 	__shared__ double l[(kTxTile + kTxTaps - 1) * 5 / 4 + 2];
 	__shared__ double peak[2];
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(256) k_tx_fir(const double *__restrict__ in_al
 #pragma unroll
 	for (int j = 0; j < kTxTaps; j++) {
 		w[0] = l[base + (96 - j) + ((96 - j) >> 2)];
-		const double cj = coef_off_base[j];
+		const double cj = tx_c[WHICH][j];
 #pragma unroll
 		for (int r = 0; r < 4; r++) acc[r] += w[r] * cj;
 		w[3] = w[2], w[2] = w[1], w[1] = w[0];
@@ -603,8 +610,13 @@ std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, 
 
 size_t mb_tx_smem_bytes(const MbTxMode &tm) { return (size_t)((tm.pre + tm.S) * MB_NC + 256) * sizeof(double2) + MB_N + (size_t)tm.P + 16; }
 
-cudaError_t mb_tx_init()
+cudaError_t mb_tx_init(const MbFeConst &fe)
 {
+	double c[2][kTxTaps + 1] = {};
+	fir_design_tx(true, false, fe.fc - fe.bandwidth / 2, 1000, fe.fs, c[0]);   // FIR_tx1: HPF, Hamming (physical_config.cc:103-107)
+	fir_design_tx(false, true, fe.fc + fe.bandwidth / 2, 1000, fe.fs, c[1]);   // FIR_tx2: LPF, Blackman (:109-113)
+	cudaError_t e = cudaMemcpyToSymbol(tx_c, c, sizeof(c));
+	if (e != cudaSuccess) return e;
 	return cudaFuncSetAttribute(k_tx_baseband, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
@@ -626,10 +638,9 @@ cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s)
 		return cudaGetLastError();
 	}
 	const dim3 grid((total + kTxTile - 1) / kTxTile, a.n);
-	const double *c1 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c1), *c2 = reinterpret_cast<const double *>(a.tables + a.tm_host->off_c2);
-	k_tx_fir<true, double><<<grid, 256, 0, s>>>(a.pb, total, npre, ndata, pp, pd, c1, a.power_part, nblk_mix, a.p1);
-	if (a.out_f32) k_tx_fir<false, float><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<float *>(a.out));
-	else k_tx_fir<false, double><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, c2, nullptr, 0, static_cast<double *>(a.out));
+	k_tx_fir<true, double, 0><<<grid, 256, 0, s>>>(a.pb, total, npre, ndata, pp, pd, a.power_part, nblk_mix, a.p1);
+	if (a.out_f32) k_tx_fir<false, float, 1><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, nullptr, 0, static_cast<float *>(a.out));
+	else k_tx_fir<false, double, 1><<<grid, 256, 0, s>>>(a.p1, total, 0, 0, 0.0, 0.0, nullptr, 0, static_cast<double *>(a.out));
 	return cudaGetLastError();
 }
 
@@ -638,9 +649,9 @@ cudaError_t mb_tx_launch(const MbTxArgs &a, cudaStream_t s)
 cudaError_t mb_tx_fir_apply(const uint8_t *tables, const MbTxMode &tm_host, const double *d_in, int n, double *d_tmp, double *d_out, cudaStream_t s)
 {
 	const dim3 grid((n + kTxTile - 1) / kTxTile, 1);
-	const double *c1 = reinterpret_cast<const double *>(tables + tm_host.off_c1), *c2 = reinterpret_cast<const double *>(tables + tm_host.off_c2);
-	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_in, n, 0, 0, 0.0, 0.0, c1, nullptr, 0, d_tmp);
-	k_tx_fir<false, double><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0, 0.0, 0.0, c2, nullptr, 0, d_out);
+	(void)tables, (void)tm_host;
+	k_tx_fir<false, double, 0><<<grid, 256, 0, s>>>(d_in, n, 0, 0, 0.0, 0.0, nullptr, 0, d_tmp);
+	k_tx_fir<false, double, 1><<<grid, 256, 0, s>>>(d_tmp, n, 0, 0, 0.0, 0.0, nullptr, 0, d_out);
 	return cudaGetLastError();
 }
 
