@@ -361,7 +361,7 @@ def run_own(a):
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_frontend
-            receive_byte = bench_frontend.run(config=8, captures=512, steps=3, warmup=1, cpu_captures=8 if a.cpu_frames > 0 else 0, ts=ts)
+            receive_byte = bench_frontend.run(config=8, captures=2048, steps=3, warmup=1, cpu_captures=8 if a.cpu_frames > 0 else 0, ts=ts)
             ts.load_configuration(a.config, a.iters)
         except Exception as e:  # never let the extra leg take the headline line down
             receive_byte = {"error": repr(e)}
