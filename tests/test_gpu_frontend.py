@@ -43,7 +43,7 @@ def _compare(o, st, payload, bb, label):
         assert err <= 1e-9, (label, err)
 
 
-@pytest.mark.parametrize("cfg", [0, 8, 10, 13, 16])
+@pytest.mark.parametrize("cfg", list(range(17)))
 def test_receive_byte_scenarios(ts, cfg):
     if not ref.available():
         pytest.skip("scenario frames come from the reference's transmit_byte (oracle/_ref not on this box)")

@@ -26,7 +26,7 @@ def _oracle(cfg):
     return ref.Ref(cfg, 50) if ref.available() else port.Port(cfg, 50)
 
 
-@pytest.mark.parametrize("cfg", [0, 5, 8, 10, 13, 16])
+@pytest.mark.parametrize("cfg", list(range(17)))
 def test_transmit_byte_batch_against_oracle(ts, cfg):
     o, p = _oracle(cfg), port.Port(cfg, 50)
     g = ts.load_configuration(cfg, 50)

@@ -10,7 +10,7 @@ from mercury_b200 import _lib
 from oracle import port
 
 
-@pytest.mark.parametrize("cfg", [0, 8, 10, 13, 16])
+@pytest.mark.parametrize("cfg", [0, 3, 8, 10, 12, 13, 14, 16])
 def test_tx_tables_match_the_oracle(cfg):
     L = _lib.lib()
     p = port.Port(cfg, 50)
