@@ -214,12 +214,20 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 /* message_location (common_defines.h:197-201): SINGLE_MESSAGE = the filtered frame; NO_FILTER_MESSAGE = the clipped frame before the
  * transmit FIRs, which is what the ARQ layer requests per frame (arq_common.cc:2224) before it filters the whole padded batch with
  * ofdm.FIR_tx1.apply / ofdm.FIR_tx2.apply (arq_common.cc:2243-2246) = mercury_b200_fir_tx_apply.  The streaming FIRST / MIDDLE / FLUSH
- * locations (TX_TEST's three-frame filter buffer) are not built. */
+ * locations (TX_TEST's three-frame filter buffer) are single-stream: mercury_b200_transmit_byte_loc below. */
 #define MERCURY_B200_SINGLE_MESSAGE 3
 #define MERCURY_B200_NO_FILTER_MESSAGE 4
 int mercury_b200_transmit_byte_batch_ex(mercury_b200_t *h, const uint8_t *payload, const uint64_t *start_sample, size_t n_frames, void *passband,
 					int out_format, int message_location, uint8_t *codeword_dbg);
 int mercury_b200_fir_tx_apply(mercury_b200_t *h, const double *in, size_t n_samples, double *out);
+/* One frame with any message_location, the reference's own types: FIRST_MESSAGE 0 / MIDDLE_MESSAGE 1 / FLUSH_MESSAGE 2 stream through a
+ * three-frame filter buffer kept on the device (telecom_system.cc:559-594; TX_TEST, :2033-2038) and return the PREVIOUS frame filtered with both
+ * neighbours as context; 3 and 4 as above.  One stream per handle. */
+#define MERCURY_B200_FIRST_MESSAGE 0
+#define MERCURY_B200_MIDDLE_MESSAGE 1
+#define MERCURY_B200_FLUSH_MESSAGE 2
+int mercury_b200_transmit_byte_loc(mercury_b200_t *h, const int *data, int nBytes, double *out, uint64_t *passband_start_sample, int message_location);
+int mercury_b200_reset_tx_stream(mercury_b200_t *h);
 int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_payload, const void *d_start_sample, size_t n_frames, void *d_passband,
 					    int out_format, void *stream);
 

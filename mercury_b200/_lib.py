@@ -91,6 +91,8 @@ def lib():
         "mercury_b200_transmit_byte_batch": (i32, [vp, vp, vp, sz, vp, i32, vp]),
         "mercury_b200_transmit_byte_batch_ex": (i32, [vp, vp, vp, sz, vp, i32, i32, vp]),
         "mercury_b200_fir_tx_apply": (i32, [vp, vp, sz, vp]),
+        "mercury_b200_transmit_byte_loc": (i32, [vp, vp, i32, vp, vp, i32]),
+        "mercury_b200_reset_tx_stream": (i32, [vp]),
         "mercury_b200_transmit_byte_batch_device": (i32, [vp, vp, vp, sz, vp, i32, vp]),
         "mercury_b200_mfsk_patterns_batch": (i32, [vp, vp, i32, sz, i32, i32, vp]),
         "mercury_b200_generate_pattern_passband": (i32, [vp, i32, vp, vp]),

@@ -25,6 +25,8 @@ static_assert(MB_HANDOFF_STRIDE == MERCURY_B200_HANDOFF_FLOATS, "hand-off stride
 static_assert(sizeof(MbMfskPatternResult) == sizeof(mercury_b200_mfsk_pattern_result) && sizeof(MbMfskPatternResult) == 32, "pattern result layout");
 static_assert(sizeof(MbReceiveStats) == sizeof(mercury_b200_receive_stats) && sizeof(MbReceiveStats) == 72, "receive stats record layout");
 
+extern "C" int mercury_b200_reset_tx_stream(mercury_b200_t *h);
+
 namespace {
 constexpr int kSlots = 3;
 
@@ -80,6 +82,8 @@ struct TxWork {
 	double2 *bb = nullptr;
 	double *pb = nullptr, *p1 = nullptr, *power_part = nullptr;
 	void *out = nullptr;
+	double *stream_buf = nullptr;  // passband_data_tx_buffer: three frames of the streaming message locations, + 4 frames of scratch
+	int stream_total = 0, stream_slot = -1;
 	cudaStream_t stream = nullptr;
 	bool init_done = false;
 };
@@ -382,6 +386,7 @@ int mercury_b200_load_configuration(mercury_b200_t *h, int config, int ldpc_iter
 	// telecom_system.cc:2494-2497: out-of-range configurations are ignored by the reference; here they are an error
 	if (!is_mfsk_config(config) && (config < 0 || config >= MB_NMODES))
 		return fail(h, MERCURY_B200_EINVAL, "configuration must be 0..16 (CONFIG_0..CONFIG_16) or 100..102 (ROBUST_0..ROBUST_2)");
+	if (h->config != config) mercury_b200_reset_tx_stream(h);
 	h->config = config;
 	h->mfsk_ctrl = false;  // telecom_system.cc:2989,3000
 	h->ldpc_iters = std::min(50, std::max(5, ldpc_iters));  // main.cc:303-311
@@ -936,7 +941,7 @@ void tx_free(TxWork &w)
 		if (w.mode_dev[i]) cudaFree(w.mode_dev[i]);
 		if (w.tables[i]) cudaFree(w.tables[i]);
 	}
-	void *ptrs[] = {w.payload, w.dbg_cw, w.start, w.bb, w.pb, w.p1, w.power_part, w.out};
+	void *ptrs[] = {w.payload, w.dbg_cw, w.start, w.bb, w.pb, w.p1, w.power_part, w.out, w.stream_buf};
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	if (w.stream) cudaStreamDestroy(w.stream);
@@ -1107,6 +1112,70 @@ int mercury_b200_transmit_byte_batch(mercury_b200_t *h, const uint8_t *payload, 
 				     uint8_t *codeword_dbg)
 {
 	return mercury_b200_transmit_byte_batch_ex(h, payload, start_sample, n, passband, out_format, MERCURY_B200_SINGLE_MESSAGE, codeword_dbg);
+}
+
+/* transmit_byte with the streaming message locations FIRST_MESSAGE (0) / MIDDLE_MESSAGE (1) / FLUSH_MESSAGE (2) (telecom_system.cc:559-594, the
+ * TX_TEST path :2033-2038): a three-frame buffer of clipped frames lives on the device between calls, both FIRs run over the two frames centred
+ * on the middle one, which is what comes out (one frame of latency).  SINGLE (3) and NO_FILTER (4) are accepted too.  One stream per handle;
+ * mercury_b200_load_configuration and mercury_b200_reset_tx_stream clear the buffer. */
+int mercury_b200_transmit_byte_loc(mercury_b200_t *h, const int *data, int nBytes, double *out, uint64_t *passband_start_sample, int message_location)
+{
+	if (!h || !data || !out) return MERCURY_B200_EINVAL;
+	int rc = check_ready(h);
+	if (rc) return rc;
+	const MbMode &m = cur_mode(h);
+	if (nBytes < 0 || nBytes > m.frame_bytes) return fail(h, MERCURY_B200_EINVAL, "message too long.. not sent.");
+	if (message_location < 0 || message_location > 4) return fail(h, MERCURY_B200_EINVAL, "unknown message_location");
+	uint8_t pl[256] = {0};
+	for (int i = 0; i < nBytes; i++) pl[i] = (uint8_t)data[i];
+	uint64_t start = passband_start_sample ? *passband_start_sample : (uint64_t)(m.M == 200 ? 0 : MB_FE_SYM);
+	const int T = tx_total(m);
+	if (message_location >= 3) {
+		rc = mercury_b200_transmit_byte_batch_ex(h, pl, &start, 1, out, MERCURY_B200_SAMPLES_F64, message_location, nullptr);
+	} else {
+		rc = tx_ensure_mode(h);
+		if (rc) return rc;
+		rc = tx_ensure_work(h, 1, T, false);
+		if (rc) return rc;
+		TxWork &w = h->tx;
+		if (!w.stream_buf || w.stream_total != T || w.stream_slot != tx_slot(h)) {
+			if (w.stream_buf) cudaFree(w.stream_buf);
+			w.stream_buf = nullptr;
+			MB_CUDA(h, cudaMalloc(&w.stream_buf, (size_t)7 * T * sizeof(double)));
+			MB_CUDA(h, cudaMemsetAsync(w.stream_buf, 0, (size_t)7 * T * sizeof(double), w.stream));
+			w.stream_total = T, w.stream_slot = tx_slot(h);
+		}
+		double *buf = w.stream_buf, *f1 = buf + 3 * (size_t)T, *f2 = f1 + 2 * (size_t)T;
+		MB_CUDA(h, cudaMemcpyAsync(w.payload, pl, m.frame_bytes, cudaMemcpyHostToDevice, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(w.start, &start, sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream));
+		rc = tx_run(h, w.payload, w.start, 1, buf + 2 * (size_t)T, false, nullptr, w.stream, /*no_filter=*/true);  // the clipped frame -> third slot
+		if (rc) return rc;
+		if (message_location == 0)  // FIRST_MESSAGE: the frame also fills the middle slot (:559-566)
+			MB_CUDA(h, cudaMemcpyAsync(buf + T, buf + 2 * (size_t)T, (size_t)T * sizeof(double), cudaMemcpyDeviceToDevice, w.stream));
+		MB_CUDA(h, mb_tx_fir_apply(w.tables[tx_slot(h)], w.mode_host[tx_slot(h)], buf + T / 2, 2 * T, f1, f2, w.stream));
+		h->launches += 2;
+		MB_CUDA(h, cudaMemcpyAsync(out, f2 + T / 2, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
+		// shift_left(buffer, 3T, T): slot 0 <- slot 1, slot 1 <- slot 2 (slot 2 keeps its content, like the reference)
+		MB_CUDA(h, cudaMemcpyAsync(buf, buf + T, (size_t)T * sizeof(double), cudaMemcpyDeviceToDevice, w.stream));
+		MB_CUDA(h, cudaMemcpyAsync(buf + T, buf + 2 * (size_t)T, (size_t)T * sizeof(double), cudaMemcpyDeviceToDevice, w.stream));
+		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+	}
+	if (rc) return rc;
+	if (passband_start_sample) *passband_start_sample = start + (uint64_t)(active_nsymb(h) + m.preamble_nSymb) * MB_FE_SYM;
+	return MERCURY_B200_OK;
+}
+
+int mercury_b200_reset_tx_stream(mercury_b200_t *h)
+{
+	if (!h) return MERCURY_B200_EINVAL;
+	TxWork &w = h->tx;
+	if (w.stream_buf) {
+		cudaSetDevice(h->device);
+		cudaFree(w.stream_buf);
+		w.stream_buf = nullptr;
+	}
+	w.stream_total = 0, w.stream_slot = -1;
+	return MERCURY_B200_OK;
 }
 
 /* ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over one host buffer (the ARQ layer's batch filtering, arq_common.cc:2243-2246). */

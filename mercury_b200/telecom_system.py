@@ -235,6 +235,18 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_transmit_byte(self._h, _vp(d), int(d.size), _vp(out), _vp(st)))
         return out, int(st[0])
 
+    def transmit_byte_loc(self, data, passband_start_sample, message_location):
+        """transmit_byte(data, nBytes, out, message_location) with FIRST 0 / MIDDLE 1 / FLUSH 2 (streaming, one frame of latency) / SINGLE 3 /
+        NO_FILTER 4 -> (out float64[total_frame_size], counter after)."""
+        d = np.asarray(list(data), np.int32)
+        out = np.zeros(self.get_total_frame_size(), np.float64)
+        st = np.array([int(passband_start_sample)], np.uint64)
+        self._check(self._L.mercury_b200_transmit_byte_loc(self._h, _vp(d), int(d.size), _vp(out), _vp(st), int(message_location)))
+        return out, int(st[0])
+
+    def reset_tx_stream(self):
+        self._check(self._L.mercury_b200_reset_tx_stream(self._h))
+
     def fir_tx_apply(self, x):
         """ofdm.FIR_tx1.apply + ofdm.FIR_tx2.apply over a host buffer of any length (the ARQ layer's batch filtering, arq_common.cc:2243-2246)."""
         a = np.ascontiguousarray(x, np.float64)

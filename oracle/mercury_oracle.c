@@ -366,7 +366,9 @@ void mo_mode_free(mo_mode *m)
 	free(m->V);
 	free(m->Vpos);
 	free(m->vdeg);
+	free(m->tx_stream);
 	m->C = m->V = m->Vpos = m->vdeg = NULL;
+	m->tx_stream = NULL;
 }
 
 mo_mode *mo_mode_new(int config, int ldpc_iters, const char *ldpc_blob_path)
@@ -1952,3 +1954,35 @@ double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int
 
 /* g_gui_state.coarse_freq_sync_enabled (gui_state.h:143): the optional +-30 Hz search of trial 1. */
 void mo_set_coarse_freq_sync(mo_mode *m, int enable) { m->fe.coarse_freq_sync = enable != 0; }
+
+
+/* transmit_bit's streaming locations FIRST_MESSAGE / MIDDLE_MESSAGE / FLUSH_MESSAGE (telecom_system.cc:559-594): a three-frame buffer of
+ * clipped frames, both FIRs over the two frames centred on the middle one, which is what comes out (one frame of latency). */
+void mo_reset_tx_stream(mo_mode *m)
+{
+	int total = (m->Nsymb + m->preamble_nSymb) * m->Nofdm * m->fe.interp;
+	free(m->tx_stream);
+	m->tx_stream = calloc(3 * (size_t)total, sizeof(double));
+}
+
+int mo_transmit_byte_loc(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout, int message_location)
+{
+	if (message_location == 3) return transmit_byte_impl(m, payload, nBytes, out, start_sample_inout, 0);
+	if (message_location == 4) return transmit_byte_impl(m, payload, nBytes, out, start_sample_inout, 1);
+	if (!m->tx.ready) mo_tx_init(m);
+	int T = (m->Nsymb + m->preamble_nSymb) * m->Nofdm * m->fe.interp;
+	if (!m->tx_stream) mo_reset_tx_stream(m);
+	double *frame = malloc(sizeof(double) * T), *f1 = calloc(2 * (size_t)T, sizeof(double)), *f2 = calloc(2 * (size_t)T, sizeof(double));
+	transmit_byte_impl(m, payload, nBytes, frame, start_sample_inout, 1);
+	double *buf = m->tx_stream;
+	if (message_location == 0)
+		for (int i = 0; i < T; i++) buf[T + i] = frame[i], buf[2 * T + i] = frame[i];
+	else
+		for (int i = 0; i < T; i++) buf[2 * T + i] = frame[i];
+	fir_apply_real(m->tx.c1, m->tx.ntaps1, buf + T / 2, f1, 2 * T);
+	fir_apply_real(m->tx.c2, m->tx.ntaps2, f1, f2, 2 * T);
+	for (int i = 0; i < T; i++) out[i] = f2[T / 2 + i];
+	for (int j = 0; j < 2 * T; j++) buf[j] = buf[j + T]; /* shift_left(buffer, 3T, T): misc.cc:24-32 */
+	free(frame), free(f1), free(f2);
+	return T;
+}

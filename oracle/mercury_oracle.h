@@ -73,6 +73,7 @@ typedef struct mo_mode {
 	mo_tx tx;
 	mo_mfsk mfsk; /* ROBUST_0..2 (config 100..102, M == 200) only */
 	int ctrl_nBits, ctrl_nsymb, ctrl_mode; /* MFSK control frames (telecom_system.cc:1572-1585, 2966-2995) */
+	double *tx_stream;		       /* passband_data_tx_buffer: three frames, streaming message locations */
 } mo_mode;
 
 typedef struct mo_rx_out {
@@ -126,6 +127,8 @@ int mo_generate_pattern_passband(mo_mode *m, int use_break_tones, double *out /*
 double mo_detect_pattern_from_passband(const mo_mode *m, const double *data, int size, int use_break_tones, int *matched_out);
 int mo_set_mfsk_ctrl_mode(mo_mode *m, int enable);
 void mo_set_coarse_freq_sync(mo_mode *m, int enable);
+void mo_reset_tx_stream(mo_mode *m);
+int mo_transmit_byte_loc(mo_mode *m, const int *payload, int nBytes, double *out, double *start_sample_inout, int message_location);
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags);
 
 #endif

@@ -60,6 +60,9 @@ def lib():
         L.mo_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
         L.mo_set_mfsk_ctrl_mode.restype = C.c_int
         L.mo_set_coarse_freq_sync.argtypes = [C.c_void_p, C.c_int]
+        L.mo_transmit_byte_loc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.mo_transmit_byte_loc.restype = C.c_int
+        L.mo_reset_tx_stream.argtypes = [C.c_void_p]
         L.mo_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mo_generate_pattern_passband.restype = C.c_int
         L.mo_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

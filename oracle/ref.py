@@ -76,6 +76,9 @@ def lib():
         L.mref_set_mfsk_ctrl_mode.argtypes = [C.c_void_p, C.c_int]
         L.mref_set_mfsk_ctrl_mode.restype = C.c_int
         L.mref_set_coarse_freq_sync.argtypes = [C.c_int]
+        L.mref_transmit_byte_loc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.mref_transmit_byte_loc.restype = C.c_int
+        L.mref_reset_tx_stream.argtypes = [C.c_void_p]
         L.mref_generate_pattern_passband.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_generate_pattern_passband.restype = C.c_int
         L.mref_detect_pattern_from_passband.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -219,6 +222,17 @@ class FrontEndMixin:
         m = np.zeros(1, np.int32)
         v = getattr(self._felib(), self._fe + "detect_pattern_from_passband")(self.h, _p(d), d.size, int(use_break_tones), _p(m))
         return float(v), int(m[0])
+
+    def reset_tx_stream(self):
+        getattr(self._felib(), self._fe + "reset_tx_stream")(self.h)
+
+    def transmit_byte_loc(self, payload, start_sample, message_location):
+        """transmit_byte with message_location FIRST 0 / MIDDLE 1 / FLUSH 2 / SINGLE 3 / NO_FILTER 4 -> (passband, counter after)."""
+        pl = np.asarray(list(payload), np.int32)
+        out = np.zeros(self.total_frame_size + 16, np.float64)
+        st = np.array([float(start_sample)], np.float64)
+        n = getattr(self._felib(), self._fe + "transmit_byte_loc")(self.h, _p(pl), len(pl), _p(out), _p(st), int(message_location))
+        return out[:n], int(st[0])
 
     def set_coarse_freq_sync(self, enable):
         """g_gui_state.coarse_freq_sync_enabled: the optional +-30 Hz search of trial 1 (GLOBAL in the reference, per mode object in the port)."""

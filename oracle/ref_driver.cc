@@ -737,4 +737,26 @@ int mref_set_mfsk_ctrl_mode(void *h, int enable)
  * (gui_state.h:143, off by default; the GUI / ini file turn it on for HF radio use). */
 void mref_set_coarse_freq_sync(int enable) { g_gui_state.coarse_freq_sync_enabled.store(enable != 0); }
 
+/* transmit_byte with any message_location (FIRST 0, MIDDLE 1, FLUSH 2, SINGLE 3, NO_FILTER 4): the streaming locations keep the reference's
+ * own three-frame filter buffer between calls (telecom_system.cc:559-594). */
+int mref_transmit_byte_loc(void *h, const int *payload, int nBytes, double *passband_out, double *start_sample_inout, int message_location)
+{
+	QuietStdout q;
+	cl_telecom_system &ts = T(h);
+	int buf[N_MAX];
+	memset(buf, 0, sizeof(buf));
+	for (int i = 0; i < nBytes; i++) buf[i] = payload[i];
+	ts.ofdm.passband_start_sample = (long unsigned)*start_sample_inout;
+	ts.transmit_byte(buf, nBytes, passband_out, message_location);
+	*start_sample_inout = (double)ts.ofdm.passband_start_sample;
+	return ts.data_container.total_frame_size;
+}
+
+/* zero the reference's streaming filter buffer (it is allocated uninitialised) so that a sequence starts from a defined state */
+void mref_reset_tx_stream(void *h)
+{
+	cl_telecom_system &ts = T(h);
+	for (int i = 0; i < 3 * ts.data_container.total_frame_size; i++) ts.data_container.passband_data_tx_buffer[i] = 0;
+}
+
 }  // extern "C"

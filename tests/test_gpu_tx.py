@@ -147,3 +147,18 @@ def test_every_configuration_round_trips_on_the_device(ts, cfg):
     # (mode 14, 8PSK 14/16 behind a 2-symbol preamble, is the extreme: the unmodified reference decodes 15 of 40 such captures of its own frames)
     assert dec.mean() >= {14: 0.3}.get(cfg, 0.85 if cfg in (12, 13, 15, 16) else 1.0), (cfg, dec.mean())
     assert np.array_equal(d_out.cpu().numpy()[dec], d_pl.cpu().numpy()[dec])
+
+
+@pytest.mark.parametrize("cfg", [8, 16])
+def test_streaming_message_locations(ts, cfg):
+    """FIRST / MIDDLE / MIDDLE / FLUSH (TX_TEST, telecom_system.cc:2033-2038,559-594): the three-frame filter buffer lives on the device."""
+    o = _oracle(cfg)
+    g = ts.load_configuration(cfg, 50)
+    o.reset_tx_stream(), ts.reset_tx_stream()
+    rng = np.random.default_rng(cfg)
+    sr = sg = 1088
+    for loc in (0, 1, 1, 2):
+        pl = rng.integers(0, 256, g["frame_bytes"])
+        want, sr = o.transmit_byte_loc(pl, sr, loc)
+        got, sg = ts.transmit_byte_loc(pl, sg, loc)
+        assert sg == sr and np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), (cfg, loc)

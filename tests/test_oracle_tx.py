@@ -35,3 +35,17 @@ def test_port_against_tx_fixture(golden_dir):
     t = p.tx_tables()
     assert np.array_equal(t["pre_eq"], g["pre_eq"]) and np.array_equal(t["preamble"], g["preamble"])
     assert np.array_equal(t["tx1"], g["tx1"]) and np.array_equal(t["tx2"], g["tx2"])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libmercury_ref.so not built")
+@pytest.mark.parametrize("cfg", [8, 16])
+def test_streaming_message_locations_bit_exact(cfg):
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    r.reset_tx_stream(), p.reset_tx_stream()
+    rng = np.random.default_rng(cfg)
+    sr = sp = 1088
+    for loc in (0, 1, 1, 2):
+        pl = rng.integers(0, 256, r.frame_bytes)
+        a, sr = r.transmit_byte_loc(pl, sr, loc)
+        b, sp = p.transmit_byte_loc(pl, sp, loc)
+        assert sr == sp and np.array_equal(a, b), (cfg, loc)
