@@ -730,7 +730,11 @@ int fe_run_mfsk(mercury_b200_t *h, const MbFeArgs &a, MbReceiveStats *d_stats, c
 		MB_CUDA(h, cudaMalloc(&h->d_mfsk_energies, (size_t)a.n * nsymb * MB_NC * sizeof(double)));
 		h->mfsk_cap_buffers = a.n, h->mfsk_cap_energies = (size_t)a.n * nsymb * MB_NC;
 	}
-	MB_CUDA(h, mb_fe_p2b_full(a, s));  // (also fills the coarse prefix sums, which this branch does not use)
+	{
+		MbFeArgs a2 = a;
+		a2.pref_ts = nullptr;  // the Schmidl-Cox prefix sums are not needed in this branch
+		MB_CUDA(h, mb_fe_p2b_full(a2, s));
+	}
 	// per-capture search start = the record's mfsk_search_or_overflow (int32 #7 of every 18-int32 record)
 	MB_CUDA(h, mb_launch_mfsk_patterns(a.bbi, 0, (size_t)a.n, a.buf, 0, reinterpret_cast<const int32_t *>(d_stats) + 7, (int)(sizeof(MbReceiveStats) / 4),
 					   h->mfsk_tones[h->config - 100], m.preamble_nSymb, h->d_mfsk_energies, h->d_mfsk_out, s));
@@ -738,7 +742,7 @@ int fe_run_mfsk(mercury_b200_t *h, const MbFeArgs &a, MbReceiveStats *d_stats, c
 	MB_CUDA(h, mb_launch_mfsk_rx_decide(h->d_mfsk_out, a.energy_part, nblk, a.buf, a.pre, a.S, active_nsymb(h), a.buffer_Nsymb, h->fe_const.fc, a.st, d_stats, a.n, w.counters, s));
 	MB_CUDA(h, cudaMemcpyAsync(w.h_counters, w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 	MB_CUDA(h, cudaStreamSynchronize(s));
-	h->launches += 7;
+	h->launches += 4;
 	h->fe_rounds++;
 	const int n_slots = w.h_counters[0];
 	if (n_slots > 0) {
@@ -807,12 +811,11 @@ int mercury_b200_measure_signal_only_batch(mercury_b200_t *h, const void *passba
 		MbFeArgs a;
 		memset(&a, 0, sizeof(a));
 		a.x = w.d_x[0], a.x_format = sample_format, a.n = (int)c, a.buf = buf, a.carrier = w.carrier, a.bbi = w.bbi, a.energy_part = w.energy_part;
-		a.st = w.st, a.win = w.win, a.win_stride = kFeWin, a.pref_ts = w.pref_ts, a.tile_base = w.tile_base;
 		MB_CUDA(h, cudaMemcpyAsync(w.d_x[0], static_cast<const uint8_t *>(passband) + done * buf * ss, c * buf * ss, cudaMemcpyHostToDevice, w.stream));
-		MB_CUDA(h, mb_fe_p2b_full(a, w.stream));
+		MB_CUDA(h, mb_fe_p2b_full(a, w.stream));  // pref_ts == NULL: base-band + energy partials only
 		MB_CUDA(h, cudaMemcpyAsync(part.data(), w.energy_part, c * nblk * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
 		MB_CUDA(h, cudaStreamSynchronize(w.stream));
-		h->launches += 3;
+		h->launches += 1;
 		for (size_t i = 0; i < c; i++) {
 			double e = 0;
 			for (int k = 0; k < nblk; k++) e += part[i * nblk + k];

@@ -1003,6 +1003,7 @@ static cudaError_t fe_p2b_full_t(const MbFeArgs &a, cudaStream_t s)
 {
 	const int nblk = (a.buf + kP2bTile - 1) / kP2bTile;
 	k_fe_p2b_full<T><<<dim3(nblk, a.n), 256, 0, s>>>(static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.energy_part, nblk);
+	if (!a.pref_ts) return cudaGetLastError();  // callers that only want the base-band and its energy (measure_signal_only, the MFSK branch)
 	const int ntile = (a.buf / 4 + kTileEntries - 1) / kTileEntries;
 	k_fe_prefix4_tiles<<<dim3(ntile, a.n), kTileEntries, 0, s>>>(a.bbi, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.tile_base, ntile);
 	k_fe_prefix4_base<<<(a.n * 32 + 127) / 128, 128, 0, s>>>(a.tile_base, ntile, a.buf, a.pref_ts, (size_t)a.buf / 4 + 1, a.n);
