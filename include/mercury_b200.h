@@ -160,9 +160,15 @@ typedef struct mercury_b200_receive_stats {
 	int32_t message_decoded, crc, all_zeros;
 	int32_t mfsk_search_or_overflow; /* ROBUST (MFSK) configurations only.  IN: first symbol of the tone-preamble search, the reference's
 	                                    receive_stats.mfsk_search_raw - nUnder_processing_events (telecom_system.cc:684).  OUT:
-	                                    frame_overflow_symbols (:702-715), > 0 when the frame runs past the end of the capture. */
+	                                    frame_overflow_symbols (:702-715), > 0 when the frame runs past the end of the capture.
+	                                    IN, alternatively, MERCURY_B200_MFSK_FIXED_DELAY(d): the reference's one-shot member mfsk_fixed_delay = d
+	                                    (telecom_system.h:110, .cc:663-673; set by the ARQ layer's overflow recapture, arq_common.cc:2830-2833):
+	                                    no search, delay = d samples, signal_stregth_dbm = 0.  Consumed like the reference's: OUT never carries it. */
 	double freq_offset, freq_offset_of_last_decoded_message, SNR, signal_stregth_dbm, coarse_metric;
 } mercury_b200_receive_stats;
+
+#define MERCURY_B200_MFSK_FIXED_DELAY_FLAG 0x40000000
+#define MERCURY_B200_MFSK_FIXED_DELAY(d) ((int32_t)(MERCURY_B200_MFSK_FIXED_DELAY_FLAG | ((d) < 0 ? 0 : (d))))
 
 #define MERCURY_B200_SAMPLES_F64 0  /* double, the reference's own type */
 #define MERCURY_B200_SAMPLES_F32 1  /* float: half the bytes; every float is exactly representable as the double the reference would see */

@@ -58,6 +58,8 @@ struct st_receive_stats {
 	double SNR = -99.9;
 	int crc = 0;
 	int all_zeros = NO;
+	int mfsk_search_raw = 0;         // MFSK anti-re-decode: first symbol of the tone-preamble search before the nUnder adjustment (telecom_system.h:79, .cc:684)
+	int frame_overflow_symbols = 0;  // > 0: the MFSK frame runs past the end of the capture by this many symbols (telecom_system.h:80, .cc:702-715)
 	float variance = 0.f;      // pilot noise variance behind the LLRs (:1291)
 	float mean_H = 0.f;        // mean |H| over pilots after AGC (:1225-1244)
 };
@@ -70,12 +72,15 @@ public:
 	struct {
 		int Nsymb = 0, Nofdm = MERCURY_B200_NOFDM, Nc = 0, nBits = 0, nData = 0, preamble_nSymb = 0;
 		int buffer_Nsymb = 0, interpolation_rate = 4;  // capture = Nofdm * buffer_Nsymb * interpolation_rate samples (data_container.cc:133-153)
+		int nUnder_processing_events = 0;              // written by the caller's audio side; receive_byte subtracts it from mfsk_search_raw (.cc:684)
 	} data_container;
 	struct {
 		int N = MERCURY_B200_N, K = 0, P = 0;
 	} ldpc;
 	st_receive_stats receive_stats;
 	int M = 0;
+	int mfsk_fixed_delay = -1;  // >= 0: the next receive_byte() skips the tone-preamble search and uses this delay, once (telecom_system.h:110, .cc:663-673;
+	                            // the ARQ layer's overflow recapture sets it, arq_common.cc:2830-2833)
 
 	explicit cl_telecom_system(int device = 0, const std::string &ldpc_table_path = "")
 	{
@@ -116,9 +121,12 @@ public:
 	// object's receive_stats the same way.
 	st_receive_stats receive_byte(double *data, int *out)
 	{
-		mercury_b200_receive_stats rs;
+		mercury_b200_receive_stats rs = mercury_b200_receive_stats();
 		rs.delay_of_last_decoded_message = receive_stats.delay_of_last_decoded_message;
 		rs.freq_offset_of_last_decoded_message = receive_stats.freq_offset_of_last_decoded_message;
+		rs.mfsk_search_or_overflow = mfsk_fixed_delay >= 0 ? MERCURY_B200_MFSK_FIXED_DELAY(mfsk_fixed_delay)
+		                                                   : receive_stats.mfsk_search_raw - data_container.nUnder_processing_events;
+		mfsk_fixed_delay = -1;  // consumed (.cc:669)
 		const int rc = mercury_b200_receive_byte(h_, data, out, &rs);
 		if (rc != MERCURY_B200_OK) throw std::runtime_error(std::string("mercury_b200_receive_byte: ") + mercury_b200_last_error(h_));
 		receive_stats.iterations_done = rs.iterations_done, receive_stats.delay = rs.delay, receive_stats.sync_trials = rs.sync_trials;
@@ -127,6 +135,7 @@ public:
 		receive_stats.message_decoded = rs.message_decoded ? YES : NO, receive_stats.SNR = rs.SNR;
 		receive_stats.crc = rs.crc, receive_stats.all_zeros = rs.all_zeros;
 		receive_stats.signal_stregth_dbm = rs.signal_stregth_dbm, receive_stats.coarse_metric = rs.coarse_metric;
+		receive_stats.frame_overflow_symbols = rs.mfsk_search_or_overflow;  // 0 in OFDM configurations (.cc:654)
 		return receive_stats;
 	}
 

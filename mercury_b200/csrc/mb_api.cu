@@ -24,6 +24,7 @@ static_assert(sizeof(MbRxStats) == 32, "stats record size");
 static_assert(MB_HANDOFF_STRIDE == MERCURY_B200_HANDOFF_FLOATS, "hand-off stride");
 static_assert(sizeof(MbMfskPatternResult) == sizeof(mercury_b200_mfsk_pattern_result) && sizeof(MbMfskPatternResult) == 32, "pattern result layout");
 static_assert(sizeof(MbReceiveStats) == sizeof(mercury_b200_receive_stats) && sizeof(MbReceiveStats) == 72, "receive stats record layout");
+static_assert(MB_MFSK_FIXED_DELAY_FLAG == MERCURY_B200_MFSK_FIXED_DELAY_FLAG, "mfsk_fixed_delay encoding");
 
 extern "C" int mercury_b200_reset_tx_stream(mercury_b200_t *h);
 

@@ -113,6 +113,7 @@ struct MbFeArgs {
 };
 
 // Mirrors mercury_b200_receive_stats (include/mercury_b200.h); 72 bytes.
+constexpr int32_t MB_MFSK_FIXED_DELAY_FLAG = 0x40000000;  // == MERCURY_B200_MFSK_FIXED_DELAY_FLAG (static_assert in mb_api.cu)
 struct MbReceiveStats {
 	int32_t iterations_done, delay, delay_of_last_decoded_message, sync_trials;
 	int32_t message_decoded, crc, all_zeros, mfsk_search_or_overflow;

@@ -279,6 +279,11 @@ __global__ void k_mfsk_rx_decide(const MbMfskPatternResult *__restrict__ pat, co
 	r.signal_stregth_dbm = 10.0 * log10((e / buf) / 0.001);
 	r.iterations_done = 0, r.sync_trials = 0, r.message_decoded = 0, r.crc = 0, r.all_zeros = 0, r.SNR = 0, r.freq_offset = 0, r.coarse_metric = 0;
 	int delay = pat[b].time_sync_delay;
+	if (r.mfsk_search_or_overflow >= MB_MFSK_FIXED_DELAY_FLAG) {
+		// mfsk_fixed_delay >= 0 (:663-673): the caller knows where the preamble is (overflow recapture); the search result is not used
+		delay = r.mfsk_search_or_overflow - MB_MFSK_FIXED_DELAY_FLAG;
+		r.signal_stregth_dbm = 0;
+	}
 	int pream = delay / MB_FE_SYM;
 	if (pream < 1) pream = 1;
 	r.mfsk_search_or_overflow = 0;

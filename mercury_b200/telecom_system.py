@@ -33,6 +33,13 @@ assert RECEIVE_STATS_DTYPE.itemsize == C.sizeof(ReceiveStats) == 72
 MFSK_PATTERN_DTYPE = np.dtype([("time_sync_delay", "<i4"), ("ack_matched", "<i4"), ("break_matched", "<i4"), ("reserved", "<i4"),
                                ("ack_metric", "<f8"), ("break_metric", "<f8")])
 SAMPLES_F64, SAMPLES_F32, SAMPLES_I16, SAMPLES_I32 = 0, 1, 2, 3
+MFSK_FIXED_DELAY_FLAG = 0x40000000  # MERCURY_B200_MFSK_FIXED_DELAY_FLAG
+
+
+def mfsk_fixed_delay(d):
+    """MERCURY_B200_MFSK_FIXED_DELAY(d): the IN value of a record's mfsk_search_or_overflow that stands for the reference's one-shot member
+    mfsk_fixed_delay = d (telecom_system.h:110, .cc:663-673; set by the ARQ layer's overflow recapture, arq_common.cc:2830-2833)."""
+    return MFSK_FIXED_DELAY_FLAG | max(int(d), 0)
 _SAMPLE_FORMATS = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2, np.dtype(np.int32): 3}
 
 

@@ -1222,10 +1222,11 @@ static double moose(const mo_mode *m, const double complex *in, double carrier_w
  */
 int mo_time_sync_mfsk(const mo_mode *m, const double complex *bbi, int n, int search_start_symb);
 
-/* The MFSK branch of receive_byte() (mfsk_fixed_delay < 0, ctrl mode off): telecom_system.cc:646-716, 928-943, 1020-1031, 1081-1198,
+/* The MFSK branch of receive_byte() (ctrl mode off): telecom_system.cc:646-716, 928-943, 1020-1031, 1081-1198,
  * 1296-1367.  One trial: tone-preamble sync on the time-sync base-band (symbol grid), frame-completeness check, data-filter mix +
  * decimation at that delay, no frequency correction, the MFSK tail.  state[2] in: first symbol of the preamble search
- * (receive_stats.mfsk_search_raw - nUnder_processing_events); state[3] out: frame_overflow_symbols. */
+ * (receive_stats.mfsk_search_raw - nUnder_processing_events); state[3] out: frame_overflow_symbols; state[4] in/out: mfsk_fixed_delay
+ * (>= 0 bypasses the search once, -1 afterwards; only this branch honours it: the reference sets it in MFSK configurations only). */
 static void mo_receive_byte_mfsk(const mo_mode *m, const double *passband, int *out, double *stats, double *state, double complex *baseband_out)
 {
 	const mo_frontend *f = &m->fe;
@@ -1240,14 +1241,22 @@ static void mo_receive_byte_mfsk(const mo_mode *m, const double *passband, int *
 	ro.payload = payload, ro.stats = tail_stats;
 	int last_delay = (int)state[0], message_decoded = 0, sync_trials = 0, iterations = 0, crc = 0, all_zeros = 0, overflow = 0;
 	double SNR = 0;
-	p2b(m, passband, buf, bbi, f->fc, 0, scratch);
-	double ss = 0;
-	for (int i = 0; i < buf; i++) ss += pow(creal(bbi[i]), 2) + pow(cimag(bbi[i]), 2);
-	ss /= buf;
-	double signal_dbm = 10.0 * log10(ss / 0.001);
-	int search_start = (int)state[2];
-	if (search_start < 0) search_start = 0;
-	int delay = mo_time_sync_mfsk(m, bbi, buf, search_start); /* :686 */
+	double signal_dbm;
+	int delay, fixed_delay = (int)state[4];
+	if (fixed_delay >= 0) { /* :663-673: known delay (the ARQ layer's overflow recapture, arq_common.cc:2830-2833) -- no mix, no search, used once */
+		delay = fixed_delay;
+		state[4] = -1;
+		signal_dbm = 0;
+	} else {
+		p2b(m, passband, buf, bbi, f->fc, 0, scratch);
+		double ss = 0;
+		for (int i = 0; i < buf; i++) ss += pow(creal(bbi[i]), 2) + pow(cimag(bbi[i]), 2);
+		ss /= buf;
+		signal_dbm = 10.0 * log10(ss / 0.001);
+		int search_start = (int)state[2];
+		if (search_start < 0) search_start = 0;
+		delay = mo_time_sync_mfsk(m, bbi, buf, search_start); /* :686 */
+	}
 	int pream_symb_loc = delay / sym;
 	if (pream_symb_loc < 1) pream_symb_loc = 1;
 	int frame_end = delay + (pre + active_nsymb(m)) * sym; /* :702-715 */
@@ -1515,12 +1524,13 @@ void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double 
 double mo_receive_byte_timed(const mo_mode *m, const double *passband, int n_calls, int *decoded_flags)
 {
 	int buf = m->Nofdm * m->fe.buffer_Nsymb * m->fe.interp, out[MO_N / 8];
-	double stats[12], state[4] = {0};
+	double stats[12], state[5] = {0};
 	struct timespec t0, t1;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	for (int c = 0; c < n_calls; c++) {
 		state[0] = -1;
 		state[1] = 0;
+		state[4] = -1;
 		mo_receive_byte(m, passband + (size_t)c * buf, out, stats, state, NULL);
 		if (decoded_flags) decoded_flags[c] = (int)stats[3];
 	}

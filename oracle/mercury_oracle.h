@@ -110,7 +110,7 @@ void mo_ldpc_encode(const mo_mode *m, const int *data, int *encoded);
 /* RX front-end: the whole receive_byte(), pass-band capture in, payload out. */
 void mo_frontend_init(mo_mode *m);
 void mo_frontend_tables(const mo_mode *m, int *ntaps /*[2]*/, double *ts_coef, double *data_coef, double *consts /*[8]*/);
-void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats /*[12]*/, double *state /*[4]*/,
+void mo_receive_byte(const mo_mode *m, const double *passband, int *out, double *stats /*[12]*/, double *state /*[5]*/,
 		     double complex *baseband_out);
 /* TX chain to pass-band: transmit_byte(SINGLE_MESSAGE). */
 void mo_tx_init(mo_mode *m);

@@ -132,19 +132,19 @@ class FrontEndMixin:
     def capture_samples(self):
         return self.Nofdm * self.buffer_Nsymb * self.interp_rate
 
-    def receive_byte2(self, passband, last_delay=-1, last_freq=0.0, search_start_symb=0):
+    def receive_byte2(self, passband, last_delay=-1, last_freq=0.0, search_start_symb=0, mfsk_fixed_delay=-1):
         L = self._felib()
         n = self.capture_samples()
         pb = np.ascontiguousarray(passband, np.float64)
         assert pb.size == n, (pb.size, n)
         out = np.zeros(self.frame_bytes, np.int32)
         st = np.zeros(12, np.float64)
-        state = np.array([last_delay, last_freq, search_start_symb, 0], np.float64)
+        state = np.array([last_delay, last_freq, search_start_symb, 0, mfsk_fixed_delay], np.float64)
         bb = np.zeros((self.Nsymb + self.preamble_nSymb) * self.Nofdm, np.complex128)
         getattr(L, self._fe + "receive_byte2" if self._fe == "mref_" else self._fe + "receive_byte")(
             self.h, _p(pb), _p(out), _p(st), _p(state), _p(bb))
         r = {k: (float(st[i]) if k in ("snr", "freq_offset", "coarse_metric", "signal_dbm") else int(st[i])) for i, k in enumerate(STAT12)}
-        r.update(payload=out, baseband=bb, last_delay=int(state[0]), last_freq=float(state[1]), frame_overflow_symbols=int(state[3]))
+        r.update(payload=out, baseband=bb, last_delay=int(state[0]), last_freq=float(state[1]), frame_overflow_symbols=int(state[3]), mfsk_fixed_delay_after=int(state[4]))
         return r
 
     def receive_byte_timed(self, captures):

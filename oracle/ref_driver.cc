@@ -491,7 +491,7 @@ void mref_receive_byte(void *h, const double *passband, int *out, double *stats 
  * stats[12]: iterations, crc, all_zeros, decoded, SNR, delay, sync_trials, freq_offset, coarse_metric,
  * signal_stregth_dbm, buffer samples, frame_bytes.
  */
-void mref_receive_byte2(void *h, const double *passband, int *out, double *stats /*[12]*/, double *state /*[4]*/, double *baseband_out)
+void mref_receive_byte2(void *h, const double *passband, int *out, double *stats /*[12]*/, double *state /*[5]*/, double *baseband_out)
 {
 	QuietStdout q;
 	cl_telecom_system &ts = T(h);
@@ -504,6 +504,7 @@ void mref_receive_byte2(void *h, const double *passband, int *out, double *stats
 	ts.receive_stats.delay_of_last_decoded_message = (int)state[0];
 	ts.receive_stats.freq_offset_of_last_decoded_message = state[1];
 	ts.receive_stats.mfsk_search_raw = (int)state[2]; /* MFSK: first symbol of the preamble search (telecom_system.cc:684-686) */
+	ts.mfsk_fixed_delay = (int)state[4]; /* >= 0: the ARQ layer's overflow recapture bypasses the search once (arq_common.cc:2830-2833, telecom_system.cc:663-673) */
 	dc.nUnder_processing_events = 0;
 	ts.receive_stats.freq_offset = 0;
 	ts.receive_stats.coarse_metric = 0;
@@ -529,6 +530,7 @@ void mref_receive_byte2(void *h, const double *passband, int *out, double *stats
 	state[0] = rs.delay_of_last_decoded_message;
 	state[1] = rs.freq_offset_of_last_decoded_message;
 	state[3] = rs.frame_overflow_symbols;
+	state[4] = ts.mfsk_fixed_delay; /* consumed: -1 after the call (:669) */
 	if (baseband_out) memcpy(baseband_out, dc.baseband_data, sizeof(double) * 2 * (dc.Nsymb + dc.preamble_nSymb) * dc.Nofdm);
 }
 

@@ -173,6 +173,54 @@ def test_robust_receive_byte_against_reference(ts, cfg):
     assert n_dec == 4 and int(st["mfsk_search_or_overflow"][3]) == 3
 
 
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_robust_fixed_delay_overflow_recapture(ts, cfg):
+    """mfsk_fixed_delay (telecom_system.h:110, .cc:663-673) = MERCURY_B200_MFSK_FIXED_DELAY(d) in the record: the ARQ layer's overflow recapture
+    (arq_common.cc:2815-2841).  Call 1 reports frame_overflow_symbols; the caller shifts the buffer by overflow + 4 symbols and calls again with
+    the known delay.  One batch mixes searching and fixed-delay captures; every field equals the unmodified reference's."""
+    if not ref.available():
+        pytest.skip("frames come from the reference's transmit_byte (oracle/_ref not on this box)")
+    r = ref.Ref(cfg, 50)
+    ts.load_configuration(cfg, 50)
+    n, sym = r.capture_samples(), 1088
+    rng = np.random.default_rng(300 + cfg)
+    pl = rng.integers(0, 256, r.frame_bytes)
+    tx = r.transmit_byte(pl)
+    d = (r.buffer_Nsymb - (r.Nsymb + 4) + 3) * sym
+    stream = np.zeros(n + 16 * sym)
+    stream[d:d + tx.size] += tx
+    stream = (stream + rng.normal(0, 0.01, stream.size)).astype(np.float32)
+    payload, st, _ = ts.receive_byte_batch(stream[None, :n])
+    o = r.receive_byte2(stream[:n].astype(np.float64))
+    assert int(st["mfsk_search_or_overflow"][0]) == o["frame_overflow_symbols"] == 3 and int(st["delay"][0]) == o["delay"] == d
+    shift = 3 + 4
+    fixed = max(d - shift * sym, 0)
+    cap2 = stream[shift * sym:shift * sym + n]
+    cases = [fixed, fixed + 3, fixed + 5 * sym, 2 * sym, 0, n - 10 * sym, -1]  # -1: the same capture with the ordinary search
+    states = mb.new_receive_stats(len(cases))
+    for i, fd in enumerate(cases):
+        states["mfsk_search_or_overflow"][i] = mb.mfsk_fixed_delay(fd) if fd >= 0 else 0
+    payload, st, _ = ts.receive_byte_batch(np.stack([cap2] * len(cases)), states)
+    n_dec = 0
+    for i, fd in enumerate(cases):
+        o = r.receive_byte2(cap2.astype(np.float64), mfsk_fixed_delay=fd)
+        assert int(st["delay"][i]) == o["delay"] and int(st["message_decoded"][i]) == o["decoded"], (cfg, fd)
+        assert int(st["sync_trials"][i]) == o["sync_trials"] and int(st["iterations_done"][i]) == o["iterations"], (cfg, fd)
+        assert int(st["crc"][i]) == o["crc"] and int(st["all_zeros"][i]) == o["all_zeros"]
+        assert int(st["mfsk_search_or_overflow"][i]) == o["frame_overflow_symbols"], (cfg, fd)  # the fixed delay is consumed, never echoed
+        assert int(st["delay_of_last_decoded_message"][i]) == o["last_delay"]
+        assert float(st["SNR"][i]) == pytest.approx(o["snr"], abs=1e-6)
+        if fd >= 0:
+            assert float(st["signal_stregth_dbm"][i]) == o["signal_dbm"] == 0.0
+        else:
+            assert abs(float(st["signal_stregth_dbm"][i]) - o["signal_dbm"]) <= 1e-9
+        assert np.array_equal(payload[i].astype(np.int32), o["payload"]), (cfg, fd)
+        if o["decoded"]:
+            assert np.array_equal(payload[i], np.asarray(pl, np.uint8))
+            n_dec += 1
+    assert n_dec == 3  # the exact delay, three samples late (inside the guard interval), and the ordinary search
+
+
 @pytest.mark.parametrize("cfg", [8, 16, 101])
 def test_arq_tone_pattern_calls_in_any_configuration(ts, cfg):
     """generate_ack/break_pattern_passband and detect_ack/break_pattern_from_passband (telecom_system.h:122-130): the ARQ layer's

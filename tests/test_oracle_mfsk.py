@@ -142,3 +142,33 @@ def test_mfsk_control_frames_bit_exact(cfg):
     cap = (cap + rng.normal(0, 0.05, n)).astype(np.float32).astype(np.float64)
     ra, rb = r.receive_byte2(cap), p.receive_byte2(cap)
     assert all(ra[k] == rb[k] for k in ref.STAT12) and np.array_equal(ra["payload"], rb["payload"]) and np.array_equal(ra["payload"], pl)
+
+
+@pytest.mark.parametrize("cfg", [100, 101, 102])
+def test_mfsk_fixed_delay_overflow_recapture_bit_exact(cfg):
+    """mfsk_fixed_delay (telecom_system.h:110, .cc:663-673): the ARQ layer's overflow recapture (arq_common.cc:2815-2841) -- a frame that runs
+    past the end of the capture reports frame_overflow_symbols, the caller shifts the buffer by overflow + 4 symbols and calls receive_byte again
+    with the known delay: no mix for the search, no search, signal strength 0, the value is consumed by the call."""
+    r, p = ref.Ref(cfg, 50), port.Port(cfg, 50)
+    n, sym = r.capture_samples(), 1088
+    rng = np.random.default_rng(300 + cfg)
+    pl = rng.integers(0, 256, r.frame_bytes)
+    tx = r.transmit_byte(pl)
+    d = (r.buffer_Nsymb - (r.Nsymb + 4) + 3) * sym  # three symbols of the frame are still to come
+    stream = np.zeros(n + 16 * sym)
+    stream[d:d + tx.size] += tx
+    stream = (stream + rng.normal(0, 0.01, stream.size)).astype(np.float32).astype(np.float64)
+    a, b = r.receive_byte2(stream[:n]), p.receive_byte2(stream[:n])
+    assert a["frame_overflow_symbols"] == b["frame_overflow_symbols"] == 3 and a["delay"] == b["delay"] == d and not a["decoded"]
+    shift = a["frame_overflow_symbols"] + 4
+    fixed = max(a["delay"] - shift * sym, 0)
+    cap2 = stream[shift * sym:shift * sym + n]
+    for fd, want_dec in ((fixed, 1), (fixed + 3, 1), (fixed + 5 * sym, 0), (2 * sym, 0), (0, 0), (n - 10 * sym, 0)):
+        a, b = r.receive_byte2(cap2, mfsk_fixed_delay=fd), p.receive_byte2(cap2, mfsk_fixed_delay=fd)
+        for k in ref.STAT12:
+            assert a[k] == b[k], (fd, k, a[k], b[k])
+        assert a["frame_overflow_symbols"] == b["frame_overflow_symbols"] and a["last_delay"] == b["last_delay"]
+        assert a["mfsk_fixed_delay_after"] == b["mfsk_fixed_delay_after"] == -1 and a["signal_dbm"] == 0.0
+        assert np.array_equal(a["payload"], b["payload"]) and a["decoded"] == want_dec, (fd, a["decoded"])
+        if a["decoded"]:
+            assert np.array_equal(a["payload"], pl) and np.array_equal(a["baseband"], b["baseband"])
