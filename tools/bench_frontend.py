@@ -124,6 +124,21 @@ def run(config=8, captures=1024, steps=5, warmup=2, noise=0.02, fmt="f32", cpu_c
                  "identical_to_device_run": bool(np.array_equal(p2, pay)), "pcie_gbs": hx.nbytes / dt / 1e9}
         del h_x
 
+    single = None
+    if e2e:
+        # the reference's own call shape, one link: receive_byte(double* data, int* out) on one pageable double capture per call
+        k = min(64, n)
+        h64 = caps64[:k].cpu().numpy()
+        lat, ok = [], 0
+        for i in range(-3, k):
+            t0 = time.perf_counter()
+            out1, st1 = ts.receive_byte(h64[max(i, 0)])
+            if i >= 0:
+                lat.append(time.perf_counter() - t0)
+                ok += int(st1["message_decoded"][0] == dec[i] and (not dec[i] or np.array_equal(out1.astype(np.uint8), pay[i])))
+        single = {"median_us": float(np.median(lat) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6), "calls": k, "identical_to_batch": ok,
+                  "api": "mercury_b200_receive_byte (one capture of doubles in, ints out: H2D + front-end + tail + D2H per call)"}
+
     cpu = None
     if cpu_captures > 0:
         from oracle import port, ref
@@ -142,7 +157,7 @@ def run(config=8, captures=1024, steps=5, warmup=2, noise=0.02, fmt="f32", cpu_c
             "config": {"workload": f"mode {config}, {n} captures of {buf} pass-band samples ({fmt}), one reference-TX frame per capture at a random "
                                    f"delay, white noise sigma {noise}", "l2_policy": f"captures {d_x.element_size() * n * buf / 1e9:.2f} GB + "
                                    f"{16 * n * buf / 1e9:.2f} GB of fp64 base-band >> 126 MB L2"},
-            "gpu_launches": int(launches), "e2e": e2e_d, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "e2e": e2e_d, "single_call": single, "cpu_baseline": cpu,
             "integrity": {"decoded": int(dec.sum()), "captures": n, "payload_mismatches_among_decoded": mism,
                           "delay_error_max": int(np.abs(st["delay"][dec] - delays[dec]).max()) if dec.any() else None,
                           "sync_trials_hist": np.bincount(st["sync_trials"], minlength=4).tolist()}}
