@@ -93,9 +93,69 @@ struct Blob {
 
 struct RateTables {
 	int rate_num = 0, N = 0, K = 0, P = 0, n_edges = 0;
-	std::vector<std::vector<int>> crow;  // check -> variables, reference order (ascending)
-	std::vector<std::vector<int>> vrow;  // variable -> checks, reference V-row order
+	std::vector<std::vector<int>> crow;  // check -> variables, reference order (ascending) unless ldpc_layout.bin re-orders it
+	std::vector<std::vector<int>> vrow;  // variable -> checks, reference V-row order unless ldpc_layout.bin re-orders it
+	std::vector<int> corder, vorder;     // optional ('MLAY' section): checks / variables in decoder order (degree descending)
 };
+
+// Optional layout file mercury_b200/data/ldpc_layout.bin ('MLAY', written by tools/ldpc_layout_opt.cpp): for every rate the order of the nodes inside their
+// warp groups and the order of every node's edges, chosen offline so that the decoder's shared-memory gathers hit distinct banks.
+// It only PERMUTES what the reference tables define: every row must be a permutation of the reference row and the node orders
+// permutations that keep the degrees descending, else the section is rejected as a whole.
+bool apply_layout_section(FILE *f, std::vector<RateTables> &rates, std::string &err)
+{
+	uint8_t hdr[12];
+	const size_t got = fread(hdr, 1, 12, f);
+	if (got == 0) return true;  // empty file: reference order
+	uint32_t ver, n;
+	memcpy(&ver, hdr + 4, 4), memcpy(&n, hdr + 8, 4);
+	if (got != 12 || memcmp(hdr, "MLAY", 4) != 0 || ver != 1 || n != rates.size()) {
+		err = "bad LDPC layout section";
+		return false;
+	}
+	for (RateTables &t : rates) {
+		uint16_t h[4];
+		uint32_t ne;
+		if (fread(h, 2, 4, f) != 4 || fread(&ne, 4, 1, f) != 1 || h[0] != t.rate_num || h[1] != t.N || h[2] != t.P || (int)ne != t.n_edges) {
+			err = "LDPC layout section does not match the tables";
+			return false;
+		}
+		std::vector<uint16_t> vo(t.N), co(t.P), ce(ne), ve(ne);
+		if (fread(vo.data(), 2, t.N, f) != (size_t)t.N || fread(co.data(), 2, t.P, f) != (size_t)t.P || fread(ce.data(), 2, ne, f) != ne ||
+		    fread(ve.data(), 2, ne, f) != ne) {
+			err = "LDPC layout section truncated";
+			return false;
+		}
+		auto order_ok = [&](const std::vector<uint16_t> &o, const std::vector<std::vector<int>> &rows) {
+			std::vector<char> seen(rows.size(), 0);
+			for (size_t i = 0; i < o.size(); i++) {
+				if (o[i] >= rows.size() || seen[o[i]]) return false;
+				seen[o[i]] = 1;
+				if (i > 0 && rows[o[i]].size() > rows[o[i - 1]].size()) return false;
+			}
+			return true;
+		};
+		auto rows_ok = [&](const std::vector<uint16_t> &flat, std::vector<std::vector<int>> &rows) {
+			size_t e = 0;
+			std::vector<std::vector<int>> neu(rows.size());
+			for (size_t r = 0; r < rows.size(); r++) {
+				neu[r].assign(flat.begin() + (long)e, flat.begin() + (long)(e + rows[r].size()));
+				e += rows[r].size();
+				std::vector<int> a = neu[r], b = rows[r];
+				std::sort(a.begin(), a.end()), std::sort(b.begin(), b.end());
+				if (a != b) return false;
+			}
+			rows.swap(neu);
+			return true;
+		};
+		if (!order_ok(vo, t.vrow) || !order_ok(co, t.crow) || !rows_ok(ce, t.crow) || !rows_ok(ve, t.vrow)) {
+			err = "LDPC layout section is not a permutation of the reference tables";
+			return false;
+		}
+		t.vorder.assign(vo.begin(), vo.end()), t.corder.assign(co.begin(), co.end());
+	}
+	return true;
+}
 
 bool load_ldpc_file(const char *path, std::vector<RateTables> &rates, std::string &err)
 {
@@ -132,12 +192,21 @@ bool load_ldpc_file(const char *path, std::vector<RateTables> &rates, std::strin
 			for (int j = 0; j < vdeg[v]; j++) t.vrow[v].push_back(vc[e++]);
 		rates.push_back(std::move(t));
 	}
-	fclose(f);
 	if (rates.size() != MB_NRATES) {
+		fclose(f);
 		err = "LDPC table file truncated";
 		return false;
 	}
-	return true;
+	fclose(f);
+	// optional layout file next to the tables: <dir>/ldpc_layout.bin
+	std::string lp(path);
+	const size_t slash = lp.find_last_of('/');
+	lp = (slash == std::string::npos ? std::string() : lp.substr(0, slash + 1)) + "ldpc_layout.bin";
+	FILE *lf = fopen(lp.c_str(), "rb");
+	if (!lf) return true;  // none: reference order
+	const bool ok = apply_layout_section(lf, rates, err);
+	fclose(lf);
+	return ok;
 }
 
 std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<uint16_t> &var_of_cw)
@@ -148,12 +217,14 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	std::vector<int> csorted(P);
 	std::iota(csorted.begin(), csorted.end(), 0);
 	std::stable_sort(csorted.begin(), csorted.end(), [&](int a, int b) { return t.crow[a].size() > t.crow[b].size(); });
+	if (!t.corder.empty()) csorted = t.corder;  // layout section: same degree order, bank-friendly positions inside the warp groups
 	std::vector<int> cpos(P);
 	for (int i = 0; i < P; i++) cpos[csorted[i]] = i;
 	// variables renumbered by degree, descending (stable)
 	std::vector<int> vsorted(N);
 	std::iota(vsorted.begin(), vsorted.end(), 0);
 	std::stable_sort(vsorted.begin(), vsorted.end(), [&](int a, int b) { return t.vrow[a].size() > t.vrow[b].size(); });
+	if (!t.vorder.empty()) vsorted = t.vorder;
 	var_of_cw.assign(N, 0);
 	for (int i = 0; i < N; i++) var_of_cw[vsorted[i]] = (uint16_t)i;
 
