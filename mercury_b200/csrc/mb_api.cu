@@ -47,6 +47,7 @@ struct FeWork {
 	int buf = 0;
 	void *d_x[2] = {nullptr, nullptr};  // staged pass-band samples of the host entry point, double buffered
 	size_t x_bytes = 0;
+	size_t out_slot_bytes = 0;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
 	size_t host_chunk = 384;  // captures per H2D chunk of the host entry point (copy of chunk i+1 overlaps the kernels of chunk i)
@@ -82,7 +83,10 @@ struct TxWork {
 	unsigned long long *start = nullptr;
 	double2 *bb = nullptr;
 	double *pb = nullptr, *p1 = nullptr, *power_part = nullptr;
-	void *out = nullptr;
+	void *out = nullptr;  // two output slots of cap * cap_total doubles: the D2H copy of one chunk overlaps the kernels of the next (host batch path)
+	size_t out_slot_bytes = 0;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 	double *stream_buf = nullptr;  // passband_data_tx_buffer: three frames of the streaming message locations, + 4 frames of scratch
 	int stream_total = 0, stream_slot = -1;
 	cudaStream_t stream = nullptr;
@@ -949,6 +953,11 @@ void tx_free(TxWork &w)
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	if (w.stream) cudaStreamDestroy(w.stream);
+	if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+	for (int i = 0; i < 2; i++) {
+		if (w.ev_done[i]) cudaEventDestroy(w.ev_done[i]);
+		if (w.ev_copied[i]) cudaEventDestroy(w.ev_copied[i]);
+	}
 	w = TxWork();
 }
 
@@ -989,7 +998,7 @@ int tx_ensure_work(mercury_b200_t *h, size_t n, int total, bool want_cw)
 	TxWork &w = h->tx;
 	if (w.cap >= n && w.cap_total >= (size_t)total && (!want_cw || w.dbg_cw)) return MERCURY_B200_OK;
 	MB_CUDA(h, cudaDeviceSynchronize());
-	void **ptrs[] = {(void **)&w.payload, (void **)&w.dbg_cw, (void **)&w.start, (void **)&w.bb, (void **)&w.pb, (void **)&w.p1, (void **)&w.power_part, &w.out};
+	void **ptrs[] = {(void **)&w.payload, (void **)&w.dbg_cw, (void **)&w.start, (void **)&w.bb, (void **)&w.pb, (void **)&w.p1, (void **)&w.power_part};
 	for (void **p : ptrs) {
 		if (*p) cudaFree(*p);
 		*p = nullptr;
@@ -1002,9 +1011,29 @@ int tx_ensure_work(mercury_b200_t *h, size_t n, int total, bool want_cw)
 	MB_CUDA(h, cudaMalloc(&w.pb, cap * tot * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.p1, cap * tot * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.power_part, cap * ((tot + 255) / 256) * 2 * sizeof(double)));
-	MB_CUDA(h, cudaMalloc(&w.out, cap * tot * sizeof(double)));
 	if (want_cw) MB_CUDA(h, cudaMalloc(&w.dbg_cw, cap * MB_N));
 	w.cap = cap, w.cap_total = tot;
+	return MERCURY_B200_OK;
+}
+
+// the host batch path's two output slots (the device entry points write straight into the caller's buffer)
+int tx_ensure_out(mercury_b200_t *h, size_t n, int total)
+{
+	TxWork &w = h->tx;
+	const size_t need = n * (size_t)total * sizeof(double);
+	if (w.out_slot_bytes >= need && w.copy_stream) return MERCURY_B200_OK;
+	MB_CUDA(h, cudaDeviceSynchronize());
+	if (w.out) cudaFree(w.out);
+	w.out = nullptr, w.out_slot_bytes = 0;
+	MB_CUDA(h, cudaMalloc(&w.out, 2 * need));
+	w.out_slot_bytes = need;
+	if (!w.copy_stream) {
+		MB_CUDA(h, cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++) {
+			MB_CUDA(h, cudaEventCreateWithFlags(&w.ev_done[i], cudaEventDisableTiming));
+			MB_CUDA(h, cudaEventCreateWithFlags(&w.ev_copied[i], cudaEventDisableTiming));
+		}
+	}
 	return MERCURY_B200_OK;
 }
 
@@ -1094,21 +1123,35 @@ int mercury_b200_transmit_byte_batch_ex(mercury_b200_t *h, const uint8_t *payloa
 	if (rc) return rc;
 	const MbMode &m = cur_mode(h);
 	const int total = tx_total(m);
-	const size_t chunk = std::min<size_t>(n, m.M == 200 ? 256 : 2048), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
+	// chunks of 512 frames (15-60 MB of samples each): the output is ~400x the input, so the call is bound by the D2H copy; two output slots
+	// let the copy of chunk i (copy stream) run under the kernels of chunk i + 1.  With pageable host memory the copy still serialises on the
+	// host side; with pinned memory (mercury_b200_host_alloc) the link stays busy.
+	const size_t chunk = std::min<size_t>(n, m.M == 200 ? 256 : 512), ob = out_format == MERCURY_B200_SAMPLES_F32 ? 4 : 8;
 	rc = tx_ensure_work(h, chunk, total, codeword_dbg != nullptr);
 	if (rc) return rc;
+	rc = tx_ensure_out(h, chunk, total);
+	if (rc) return rc;
 	TxWork &w = h->tx;
-	for (size_t done = 0; done < n; done += chunk) {
+	const size_t slot_bytes = w.out_slot_bytes;
+	size_t i = 0;
+	for (size_t done = 0; done < n; done += chunk, i++) {
 		const size_t c = std::min(chunk, n - done);
+		const int slot = (int)(i & 1);
+		uint8_t *d_out = static_cast<uint8_t *>(w.out) + (size_t)slot * slot_bytes;
+		if (i >= 2) MB_CUDA(h, cudaStreamWaitEvent(w.stream, w.ev_copied[slot], 0));  // the copy of chunk i - 2 has left this slot
 		MB_CUDA(h, cudaMemcpyAsync(w.payload, payload + done * m.frame_bytes, c * m.frame_bytes, cudaMemcpyHostToDevice, w.stream));
 		if (start_sample) MB_CUDA(h, cudaMemcpyAsync(w.start, start_sample + done, c * sizeof(uint64_t), cudaMemcpyHostToDevice, w.stream));
-		rc = tx_run(h, w.payload, start_sample ? w.start : nullptr, c, w.out, out_format == MERCURY_B200_SAMPLES_F32, codeword_dbg ? w.dbg_cw : nullptr, w.stream,
+		rc = tx_run(h, w.payload, start_sample ? w.start : nullptr, c, d_out, out_format == MERCURY_B200_SAMPLES_F32, codeword_dbg ? w.dbg_cw : nullptr, w.stream,
 			    message_location == MERCURY_B200_NO_FILTER_MESSAGE);
 		if (rc) return rc;
-		MB_CUDA(h, cudaMemcpyAsync(static_cast<uint8_t *>(passband) + done * total * ob, w.out, c * total * ob, cudaMemcpyDeviceToHost, w.stream));
 		if (codeword_dbg) MB_CUDA(h, cudaMemcpyAsync(codeword_dbg + done * MB_N, w.dbg_cw, c * MB_N, cudaMemcpyDeviceToHost, w.stream));
-		MB_CUDA(h, cudaStreamSynchronize(w.stream));
+		MB_CUDA(h, cudaEventRecord(w.ev_done[slot], w.stream));
+		MB_CUDA(h, cudaStreamWaitEvent(w.copy_stream, w.ev_done[slot], 0));
+		MB_CUDA(h, cudaMemcpyAsync(static_cast<uint8_t *>(passband) + done * total * ob, d_out, c * total * ob, cudaMemcpyDeviceToHost, w.copy_stream));
+		MB_CUDA(h, cudaEventRecord(w.ev_copied[slot], w.copy_stream));
 	}
+	MB_CUDA(h, cudaStreamSynchronize(w.stream));
+	MB_CUDA(h, cudaStreamSynchronize(w.copy_stream));
 	return MERCURY_B200_OK;
 }
 

@@ -261,12 +261,16 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_fir_tx_apply(self._h, _vp(a), a.size, _vp(out)))
         return out
 
-    def transmit_byte_batch(self, payload, start_sample=None, dtype=np.float64, want_codeword=False, message_location=3):
+    def transmit_byte_batch(self, payload, start_sample=None, dtype=np.float64, want_codeword=False, message_location=3, out=None):
         """payload [n, frame_bytes] uint8 -> pass-band frames [n, total_frame_size] (float64 or float32) [, codewords [n, 1600] u8].
-        message_location: 3 = SINGLE_MESSAGE (filtered), 4 = NO_FILTER_MESSAGE (clipped, before the transmit FIRs)."""
+        message_location: 3 = SINGLE_MESSAGE (filtered), 4 = NO_FILTER_MESSAGE (clipped, before the transmit FIRs).
+        out: optional preallocated [n, total_frame_size] array of `dtype` (pinned memory lets the D2H copy overlap the kernels)."""
         pl = np.ascontiguousarray(payload, np.uint8).reshape(-1, self.geometry["frame_bytes"])
         n = pl.shape[0]
-        out = np.zeros((n, self.get_total_frame_size()), dtype)
+        if out is None:
+            out = np.zeros((n, self.get_total_frame_size()), dtype)
+        elif out.dtype != np.dtype(dtype) or out.shape != (n, self.get_total_frame_size()) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous [n, total_frame_size] array of dtype")
         st = None if start_sample is None else np.ascontiguousarray(start_sample, np.uint64)
         cw = np.zeros((n, self.geometry["N"]), np.uint8) if want_codeword else None
         self._check(self._L.mercury_b200_transmit_byte_batch_ex(self._h, _vp(pl), _vp(st), n, _vp(out), _SAMPLE_FORMATS[np.dtype(dtype)],
