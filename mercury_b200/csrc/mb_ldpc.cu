@@ -100,6 +100,45 @@ __device__ __forceinline__ float lds_f(unsigned sbase, unsigned off)
 	return v;
 }
 
+// Sum-product check node of one lane (one check of a warp group padded to degree d): reads the d posteriors and messages, writes the d new
+// messages, returns the XOR of the hard decisions (sign bit in bit 0).
+// Leave-one-out sums without cancellation: the largest term is kept apart (big) and rest = sum of all the others, by a running (min, max)
+// pair -- no index tracking: the edge that owns the largest term is recognised by value in the second loop (ties are harmless: each tied
+// edge's leave-one-out sum is the same `rest`).  s = +inf (q == 0) needs no clamp: it parks in `big`, every other edge then sees
+// inf -> message 0, and two of them make rest = inf -> all messages 0.
+// D > 0: the group degree is a compile-time constant (the common degrees are instantiated): both loops unroll completely, every
+// shared-memory access is [register + immediate] and there is no loop counter -- about a sixth of the generic loop's instructions
+// were counters, compares, branches and address arithmetic (ncu source page, profiles/r1n).  Same operations in the same order.
+template <int D>
+__device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt)
+{
+	const int d = D > 0 ? D : d_rt;
+	unsigned hard = 0, par = 0;
+	float big = 0.f, rest = 0.f;
+#pragma unroll(D > 0 ? D : 4)
+	for (int k = 0; k < d; k++) {
+		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
+		const float q = lam - Re[k * 32];
+		hard ^= __float_as_uint(lam);  // sign bit only is used
+		par ^= __float_as_uint(q);
+		float s = phi_fwd(fabsf(q));
+		s = s < kTanhOne2 ? 0.f : s;
+		rest += fminf(s, big);
+		big = fmaxf(s, big);
+		Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
+	}
+	const unsigned pneg = par & 0x80000000u;
+#pragma unroll(D > 0 ? D : 4)
+	for (int k = 0; k < d; k++) {
+		const unsigned tb = __float_as_uint(Re[k * 32]);
+		const float sk = __uint_as_float(tb & 0x7fffffffu);
+		const float so = sk == big ? rest : (rest - sk) + big;
+		const float mag = sel_gt0(so, phi_bwd(so), kClampR);  // all-saturated product -> 2 atanh(0.9999999)
+		Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
+	}
+	return lam_sign_fix(hard);
+}
+
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
 {
@@ -179,32 +218,14 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 				Re[0] = fabsf(q1) > kSatQ ? copysignf(kClampR, q1) : q1;
 				Re[32] = fabsf(q0) > kSatQ ? copysignf(kClampR, q0) : q0;
 			} else if (ALGO == 0) {
-				// Leave-one-out sums without cancellation: the largest term is kept apart (big) and rest = sum of all the others, by a
-				// running (min, max) pair -- no index tracking: the edge that owns the largest term is recognised by value in the second
-				// loop (ties are harmless: each tied edge's leave-one-out sum is the same `rest`).  s = +inf (q == 0) needs no clamp:
-				// it parks in `big`, every other edge then sees inf -> message 0, and two of them make rest = inf -> all messages 0.
-				float big = 0.f, rest = 0.f;
-#pragma unroll 4
-				for (int k = 0; k < d; k++) {
-					const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
-					const float q = lam - Re[k * 32];
-					hard ^= __float_as_uint(lam);  // sign bit only is used
-					par ^= __float_as_uint(q);
-					float s = phi_fwd(fabsf(q));
-					s = s < kTanhOne2 ? 0.f : s;
-					rest += fminf(s, big);
-					big = fmaxf(s, big);
-					Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
-				}
-				hard = (lam_sign_fix(hard));
-				const unsigned pneg = par & 0x80000000u;
-#pragma unroll 4
-				for (int k = 0; k < d; k++) {
-					const unsigned tb = __float_as_uint(Re[k * 32]);
-					const float sk = __uint_as_float(tb & 0x7fffffffu);
-					const float so = sk == big ? rest : (rest - sk) + big;
-					const float mag = sel_gt0(so, phi_bwd(so), kClampR);  // all-saturated product -> 2 atanh(0.9999999)
-					Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
+				switch (d) {
+				case 3: hard = spa_check_node<3>(sbase, ve, Re, d); break;
+				case 4: hard = spa_check_node<4>(sbase, ve, Re, d); break;
+				case 5: hard = spa_check_node<5>(sbase, ve, Re, d); break;
+				case 6: hard = spa_check_node<6>(sbase, ve, Re, d); break;
+				case 7: hard = spa_check_node<7>(sbase, ve, Re, d); break;
+				case 8: hard = spa_check_node<8>(sbase, ve, Re, d); break;
+				default: hard = spa_check_node<0>(sbase, ve, Re, d); break;
 				}
 			} else {
 				const int c = (int)((desc >> 24) - 1u) * 32 + lane;
