@@ -109,13 +109,22 @@ __device__ __forceinline__ float lds_f(unsigned sbase, unsigned off)
 // D > 0: the group degree is a compile-time constant (the common degrees are instantiated): both loops unroll completely, every
 // shared-memory access is [register + immediate] and there is no loop counter -- about a sixth of the generic loop's instructions
 // were counters, compares, branches and address arithmetic (ncu source page, profiles/r1n).  Same operations in the same order.
+// Which group degrees get their own instantiation is an instruction-cache trade (B200, mode 8 = rate 6/16, ms per 65,536 frames; generic loop
+// only: 5.06): {3..8} 4.67, {4..8} 4.47, {5..8} 4.51, {3..6} 4.39, {5..7} 4.41, {4..6} 4.48, {4..7} 4.32, {3..10} 4.98 -- every body is ~45
+// instructions per edge and the eight warps of a CTA sit in different bodies at once.  Unrolling the generic loop by 4 / 2 / 1 next to {4..7}:
+// 4.32 / 4.32 / 4.39.  Keeping the parked magnitudes in registers instead of the message slots (degree <= 4 / 6 / 8): 4.69 / 4.74 / 4.73
+// against 4.66 without, so they stay parked.
+// So the kernel is instantiated per degree SET and the launch picks the set that covers the rate's check degrees (SURVEY.md 8a graph table):
+// rates 1..4/16 (degrees 2-5 carry 85-100 % of the edges) {3..5}, rates 5,6/16 {4..7}, rate 8/16 {6..9}; rate 14/16 (degrees 23-46) runs
+// the generic loop whichever set is loaded.
+constexpr int kGenUnroll = 4;
 template <int D>
 __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt)
 {
 	const int d = D > 0 ? D : d_rt;
 	unsigned hard = 0, par = 0;
 	float big = 0.f, rest = 0.f;
-#pragma unroll(D > 0 ? D : 4)
+#pragma unroll(D > 0 ? D : kGenUnroll)
 	for (int k = 0; k < d; k++) {
 		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
 		const float q = lam - Re[k * 32];
@@ -128,7 +137,7 @@ __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_
 		Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
 	}
 	const unsigned pneg = par & 0x80000000u;
-#pragma unroll(D > 0 ? D : 4)
+#pragma unroll(D > 0 ? D : kGenUnroll)
 	for (int k = 0; k < d; k++) {
 		const unsigned tb = __float_as_uint(Re[k * 32]);
 		const float sk = __uint_as_float(tb & 0x7fffffffu);
@@ -139,7 +148,7 @@ __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_
 	return lam_sign_fix(hard);
 }
 
-template <int ALGO>
+template <int ALGO, int FMIN, int FMAX>
 __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,12 +228,18 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 				Re[32] = fabsf(q0) > kSatQ ? copysignf(kClampR, q0) : q0;
 			} else if (ALGO == 0) {
 				switch (d) {
-				case 3: hard = spa_check_node<3>(sbase, ve, Re, d); break;
-				case 4: hard = spa_check_node<4>(sbase, ve, Re, d); break;
-				case 5: hard = spa_check_node<5>(sbase, ve, Re, d); break;
-				case 6: hard = spa_check_node<6>(sbase, ve, Re, d); break;
-				case 7: hard = spa_check_node<7>(sbase, ve, Re, d); break;
-				case 8: hard = spa_check_node<8>(sbase, ve, Re, d); break;
+#define MB_FIX_CASE(D_) \
+	case D_:            /* a degree outside the instantiated set falls through to the generic loop */ \
+		if (D_ >= FMIN && D_ <= FMAX && d == D_) { hard = spa_check_node<(D_ >= FMIN && D_ <= FMAX) ? D_ : 0>(sbase, ve, Re, d); break; }
+				MB_FIX_CASE(3)
+				MB_FIX_CASE(4)
+				MB_FIX_CASE(5)
+				MB_FIX_CASE(6)
+				MB_FIX_CASE(7)
+				MB_FIX_CASE(8)
+				MB_FIX_CASE(9)
+				MB_FIX_CASE(10)
+#undef MB_FIX_CASE
 				default: hard = spa_check_node<0>(sbase, ve, Re, d); break;
 				}
 			} else {
@@ -447,20 +462,27 @@ size_t mb_ldpc_smem_bytes(int c_slots)
 	return (size_t)kOffR + (size_t)((c_slots + 4) & ~3) * sizeof(float) + 2 * MB_LDPC_WARPS * MB_SCHED_LEN * sizeof(uint32_t) + 256;
 }
 
+namespace {
+typedef void (*LdpcKernel)(const MbLdpcArgs);
+// [0] min-sum, [1..3] sum-product with the degree sets {3..5}, {4..7}, {6..9}
+const LdpcKernel kKernels[4] = {mb_ldpc_kernel<1, 0, 0>, mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 4, 7>, mb_ldpc_kernel<0, 6, 9>};
+}  // namespace
+
 cudaError_t mb_ldpc_init()
 {
-	cudaError_t e = cudaFuncSetAttribute(mb_ldpc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(mb_ldpc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+	for (LdpcKernel k : kKernels) {
+		cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
 }
 
 cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream)
 {
 	if (n_frames == 0) return cudaSuccess;
 	const size_t smem = mb_ldpc_smem_bytes(a.rate.c_slots);
-	if (algo == 0)
-		mb_ldpc_kernel<0><<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
-	else
-		mb_ldpc_kernel<1><<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
+	const int r = a.rate.rate_num;
+	const LdpcKernel k = kKernels[algo != 0 ? 0 : (r <= 4 ? 1 : (r <= 6 ? 2 : 3))];
+	k<<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
 	return cudaGetLastError();
 }
