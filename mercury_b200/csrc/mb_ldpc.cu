@@ -109,22 +109,26 @@ __device__ __forceinline__ float lds_f(unsigned sbase, unsigned off)
 // D > 0: the group degree is a compile-time constant (the common degrees are instantiated): both loops unroll completely, every
 // shared-memory access is [register + immediate] and there is no loop counter -- about a sixth of the generic loop's instructions
 // were counters, compares, branches and address arithmetic (ncu source page, profiles/r1n).  Same operations in the same order.
-// Which group degrees get their own instantiation is an instruction-cache trade (B200, mode 8 = rate 6/16, ms per 65,536 frames; generic loop
-// only: 5.06): {3..8} 4.67, {4..8} 4.47, {5..8} 4.51, {3..6} 4.39, {5..7} 4.41, {4..6} 4.48, {4..7} 4.32, {3..10} 4.98 -- every body is ~45
-// instructions per edge and the eight warps of a CTA sit in different bodies at once.  Unrolling the generic loop by 4 / 2 / 1 next to {4..7}:
-// 4.32 / 4.32 / 4.39.  Keeping the parked magnitudes in registers instead of the message slots (degree <= 4 / 6 / 8): 4.69 / 4.74 / 4.73
-// against 4.66 without, so they stay parked.
-// So the kernel is instantiated per degree SET and the launch picks the set that covers the rate's check degrees (SURVEY.md 8a graph table):
-// rates 1..4/16 (degrees 2-5 carry 85-100 % of the edges) {3..5}, rates 5,6/16 {4..7}, rate 8/16 {6..9}; rate 14/16 (degrees 23-46) runs
-// the generic loop whichever set is loaded.
+// Which group degrees get their own body was measured on the GPU (B200, ms per 65,536 frames; generic loop only: mode 8 5.06):
+//   mode 8 (rate 6/16): {3..8} 4.67, {4..8} 4.47, {5..8} 4.51, {3..6} 4.39, {5..7} 4.41, {4..6} 4.48, {4..7} 4.32, {3..7} 4.24, {3..10} 4.98
+//   mode 9 (rate 8/16): {3..7} 4.31, {5..7} 4.29, {6..7} 4.38, {7} 4.54, {6..9} 4.31, {5..9} 4.22
+// More bodies are not better: a body is ~45 instructions per edge, the eight warps of a CTA sit in different bodies at once (instruction
+// cache), and degrees that are multiples of 4 lose little in the generic loop anyway (it is unrolled by 4: 4 / 2 / 1 next to {4..7} gave
+// 4.32 / 4.32 / 4.39).  Chunked unrolling of the larger fixed degrees (8 -> 2 x 4) did not change that in mode 8 ({3..8} 4.37-4.40), nor did keeping
+// the parked magnitudes in registers instead of the message slots (degree <= 4 / 6 / 8: 4.69 / 4.74 / 4.73 against 4.66).
+// So the kernel is instantiated per degree SET and the launch picks the set by rate (check degrees: SURVEY.md 8a graph table): rates
+// 1..4/16 {3..5}, rates 5,6/16 {3..7}, rate 8/16 {5..9}; rate 14/16 (degrees 23-46) runs the generic loop whichever set is loaded.
 constexpr int kGenUnroll = 4;
+// unroll factor of a body: complete up to 7 edges, beyond that in equal chunks (8 -> 2 x 4, 9 -> 3 x 3): the trip count is still a constant
+// (no remainder loop) and the body stays small.  Rate 8/16 (mode 9, 65,536 frames): {5..9} chunked 4.22 ms, {5..9} complete 4.62, {6..9} 4.31.
+__host__ __device__ constexpr int fix_unroll(int D) { return D <= 0 ? kGenUnroll : (D <= 7 ? D : (D % 2 == 0 ? D / 2 : (D % 3 == 0 ? D / 3 : D))); }
 template <int D>
 __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt)
 {
 	const int d = D > 0 ? D : d_rt;
 	unsigned hard = 0, par = 0;
 	float big = 0.f, rest = 0.f;
-#pragma unroll(D > 0 ? D : kGenUnroll)
+#pragma unroll(fix_unroll(D))
 	for (int k = 0; k < d; k++) {
 		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
 		const float q = lam - Re[k * 32];
@@ -137,7 +141,7 @@ __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_
 		Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
 	}
 	const unsigned pneg = par & 0x80000000u;
-#pragma unroll(D > 0 ? D : kGenUnroll)
+#pragma unroll(fix_unroll(D))
 	for (int k = 0; k < d; k++) {
 		const unsigned tb = __float_as_uint(Re[k * 32]);
 		const float sk = __uint_as_float(tb & 0x7fffffffu);
@@ -464,8 +468,8 @@ size_t mb_ldpc_smem_bytes(int c_slots)
 
 namespace {
 typedef void (*LdpcKernel)(const MbLdpcArgs);
-// [0] min-sum, [1..3] sum-product with the degree sets {3..5}, {4..7}, {6..9}
-const LdpcKernel kKernels[4] = {mb_ldpc_kernel<1, 0, 0>, mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 4, 7>, mb_ldpc_kernel<0, 6, 9>};
+// [0] min-sum, [1..3] sum-product with the degree sets {3..5}, {3..7}, {5..9}
+const LdpcKernel kKernels[4] = {mb_ldpc_kernel<1, 0, 0>, mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 3, 7>, mb_ldpc_kernel<0, 5, 9>};
 }  // namespace
 
 cudaError_t mb_ldpc_init()
