@@ -152,6 +152,40 @@ __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_
 	return lam_sign_fix(hard);
 }
 
+// Normalised min-sum check node of one lane, same contract as spa_check_node (alpha 1 for true degree <= 2 where min-sum is exact, 0.85 for
+// 3, 0.75 above); D > 0: fixed group degree, loops unrolled, the sign bits and the arg-min compare against constants.
+template <int D>
+__device__ __forceinline__ unsigned minsum_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt, int dc)
+{
+	const int d = D > 0 ? D : d_rt;
+	unsigned hard = 0, par = 0;
+	float m1 = 3.0e38f, m2 = 3.0e38f;
+	int arg = -1;
+	unsigned long long signs = 0ull;
+#pragma unroll(fix_unroll(D))
+	for (int k = 0; k < d; k++) {
+		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
+		const float q = lam - Re[k * 32];
+		hard ^= __float_as_uint(lam);
+		par ^= __float_as_uint(q);
+		signs |= (unsigned long long)(__float_as_uint(q) >> 31) << k;
+		const float aq = fabsf(q);
+		const bool lt1 = aq < m1;
+		m2 = lt1 ? m1 : fminf(m2, aq);
+		arg = lt1 ? k : arg;
+		m1 = lt1 ? aq : m1;
+	}
+	const float alpha = dc <= 2 ? 1.0f : (dc == 3 ? 0.85f : 0.75f);
+	const unsigned pneg = par >> 31;
+#pragma unroll(fix_unroll(D))
+	for (int k = 0; k < d; k++) {
+		const float mag = fminf(alpha * (k == arg ? m2 : m1), kClampR);
+		const unsigned neg = pneg ^ (unsigned)((signs >> k) & 1ull);
+		Re[k * 32] = neg ? -mag : mag;
+	}
+	return lam_sign_fix(hard);
+}
+
 template <int ALGO, int FMIN, int FMAX>
 __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
 {
@@ -249,28 +283,20 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			} else {
 				const int c = (int)((desc >> 24) - 1u) * 32 + lane;
 				const int dc = c < rt.P ? (int)(a.blob + rt.off_cdeg)[c] : 0;  // the true degree picks the normalisation
-				float m1 = 3.0e38f, m2 = 3.0e38f;
-				int arg = -1;
-				unsigned long long signs = 0ull;
-				for (int k = 0; k < d; k++) {
-					const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
-					const float q = lam - Re[k * 32];
-					hard ^= __float_as_uint(lam);
-					par ^= __float_as_uint(q);
-					signs |= (unsigned long long)(__float_as_uint(q) >> 31) << k;
-					const float aq = fabsf(q);
-					const bool lt1 = aq < m1;
-					m2 = lt1 ? m1 : fminf(m2, aq);
-					arg = lt1 ? k : arg;
-					m1 = lt1 ? aq : m1;
-				}
-				hard = (lam_sign_fix(hard));
-				const float alpha = dc <= 2 ? 1.0f : (dc == 3 ? 0.85f : 0.75f);
-				const unsigned pneg = par >> 31;
-				for (int k = 0; k < d; k++) {
-					const float mag = fminf(alpha * (k == arg ? m2 : m1), kClampR);
-					const unsigned neg = pneg ^ (unsigned)((signs >> k) & 1ull);
-					Re[k * 32] = neg ? -mag : mag;
+				switch (d) {
+#define MB_FIX_CASE(D_) \
+	case D_:            /* a degree outside the instantiated set falls through to the generic loop */ \
+		if (D_ >= FMIN && D_ <= FMAX && d == D_) { hard = minsum_check_node<(D_ >= FMIN && D_ <= FMAX) ? D_ : 0>(sbase, ve, Re, d, dc); break; }
+				MB_FIX_CASE(3)
+				MB_FIX_CASE(4)
+				MB_FIX_CASE(5)
+				MB_FIX_CASE(6)
+				MB_FIX_CASE(7)
+				MB_FIX_CASE(8)
+				MB_FIX_CASE(9)
+				MB_FIX_CASE(10)
+#undef MB_FIX_CASE
+				default: hard = minsum_check_node<0>(sbase, ve, Re, d, dc); break;
 				}
 			}
 			unsat |= hard;
@@ -468,8 +494,9 @@ size_t mb_ldpc_smem_bytes(int c_slots)
 
 namespace {
 typedef void (*LdpcKernel)(const MbLdpcArgs);
-// [0] min-sum, [1..3] sum-product with the degree sets {3..5}, {3..7}, {5..9}
-const LdpcKernel kKernels[4] = {mb_ldpc_kernel<1, 0, 0>, mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 3, 7>, mb_ldpc_kernel<0, 5, 9>};
+// [algo][set]: sum-product / min-sum, each with the degree sets {3..5}, {3..7}, {5..9}
+const LdpcKernel kKernels[6] = {mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 3, 7>, mb_ldpc_kernel<0, 5, 9>,
+				mb_ldpc_kernel<1, 3, 5>, mb_ldpc_kernel<1, 3, 7>, mb_ldpc_kernel<1, 5, 9>};
 }  // namespace
 
 cudaError_t mb_ldpc_init()
@@ -486,7 +513,7 @@ cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaS
 	if (n_frames == 0) return cudaSuccess;
 	const size_t smem = mb_ldpc_smem_bytes(a.rate.c_slots);
 	const int r = a.rate.rate_num;
-	const LdpcKernel k = kKernels[algo != 0 ? 0 : (r <= 4 ? 1 : (r <= 6 ? 2 : 3))];
+	const LdpcKernel k = kKernels[(algo != 0 ? 3 : 0) + (r <= 4 ? 0 : (r <= 6 ? 1 : 2))];
 	k<<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
 	return cudaGetLastError();
 }
