@@ -152,6 +152,48 @@ __device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_
 	return lam_sign_fix(hard);
 }
 
+// Variable node of the head (degree > 2, groups padded to an even degree): channel LLR + the incoming messages in the table's order.
+// D > 0: fixed group degree, every index load and gather at an immediate offset.
+template <int D>
+__device__ __forceinline__ float var_node_sum(unsigned sbase, const uint16_t *__restrict__ se, float acc, int d_rt)
+{
+	if (D > 0) {
+		unsigned idx[D > 0 ? D : 1];
+#pragma unroll
+		for (int k = 0; k < D; k++) idx[k] = se[k * 32];
+#pragma unroll
+		for (int k = 0; k < D; k++) acc += lds_f(sbase, kOffR + idx[k]);
+		return acc;
+	}
+	int k = 0;
+#pragma unroll 1
+	for (; k + 4 <= d_rt; k += 4) {
+		const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
+		se += 128;
+		acc += lds_f(sbase, kOffR + i0);
+		acc += lds_f(sbase, kOffR + i1);
+		acc += lds_f(sbase, kOffR + i2);
+		acc += lds_f(sbase, kOffR + i3);
+	}
+	if (k < d_rt) {
+		const unsigned i0 = se[0], i1 = se[32];
+		acc += lds_f(sbase, kOffR + i0);
+		acc += lds_f(sbase, kOffR + i1);
+	}
+	return acc;
+}
+
+// XOR of the hard decisions of one check (syndrome-only test)
+template <int D>
+__device__ __forceinline__ unsigned check_parity(unsigned sbase, const uint16_t *__restrict__ ve, int d_rt)
+{
+	const int d = D > 0 ? D : d_rt;
+	unsigned hard = 0;
+#pragma unroll(D > 0 ? D : 4)
+	for (int k = 0; k < d; k++) hard ^= __float_as_uint(lds_f(sbase, kOffLam + ve[k * 32]));
+	return hard >> 31;
+}
+
 // Normalised min-sum check node of one lane, same contract as spa_check_node (alpha 1 for true degree <= 2 where min-sum is exact, 0.85 for
 // 3, 0.75 above); D > 0: fixed group degree, loops unrolled, the sign bits and the arg-min compare against constants.
 template <int D>
@@ -321,20 +363,12 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			const int v = (int)((desc >> 24) - 1u) * 32 + lane;
 			const uint16_t *__restrict__ se = g_vedge + ((desc & 0xFFFFu) + lane);
 			float acc = s_lch[v];
-			int k = 0;
-#pragma unroll 1
-			for (; k + 4 <= d; k += 4) {
-				const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
-				se += 128;
-				acc += lds_f(sbase, kOffR + i0);
-				acc += lds_f(sbase, kOffR + i1);
-				acc += lds_f(sbase, kOffR + i2);
-				acc += lds_f(sbase, kOffR + i3);
-			}
-			if (k < d) {
-				const unsigned i0 = se[0], i1 = se[32];
-				acc += lds_f(sbase, kOffR + i0);
-				acc += lds_f(sbase, kOffR + i1);
+			switch (d) {  // variable degrees are 3..9 in all eight codes (padded: 4, 6, 8, 10)
+			case 4: acc = var_node_sum<4>(sbase, se, acc, d); break;
+			case 6: acc = var_node_sum<6>(sbase, se, acc, d); break;
+			case 8: acc = var_node_sum<8>(sbase, se, acc, d); break;
+			case 10: acc = var_node_sum<10>(sbase, se, acc, d); break;
+			default: acc = var_node_sum<0>(sbase, se, acc, d); break;
 			}
 			s_lam[v] = acc;
 		}
@@ -353,10 +387,17 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
 				const int d = (int)((desc >> 16) & 0xFFu);
 				const uint16_t *__restrict__ ve = g_edge_var + (desc & 0xFFFFu) + lane;
-				unsigned hard = 0;
-#pragma unroll 4
-				for (int k = 0; k < d; k++) hard ^= __float_as_uint(lds_f(sbase, kOffLam + ve[k * 32]));
-				bad |= hard >> 31;
+				switch (d) {
+				case 2: bad |= check_parity<2>(sbase, ve, d); break;
+				case 3: bad |= check_parity<3>(sbase, ve, d); break;
+				case 4: bad |= check_parity<4>(sbase, ve, d); break;
+				case 5: bad |= check_parity<5>(sbase, ve, d); break;
+				case 6: bad |= check_parity<6>(sbase, ve, d); break;
+				case 7: bad |= check_parity<7>(sbase, ve, d); break;
+				case 8: bad |= check_parity<8>(sbase, ve, d); break;
+				case 9: bad |= check_parity<9>(sbase, ve, d); break;
+				default: bad |= check_parity<0>(sbase, ve, d); break;
+				}
 			}
 			if (__syncthreads_or((int)bad) == 0) {
 				iterations = pass + 1;  // exactly what the next check pass would have reported
