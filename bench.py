@@ -315,8 +315,8 @@ def run_own(a):
             "edges": m["edges"], "mean_iterations": float(its_run.mean()), "frames_per_s": B / t_ldpc_s,
             "hbm_gbs": B * (1600 * 4 + fb + 32 + 32) / t_ldpc_s / 1e9, "share_of_step": t_ldpc_s / (t_demod_s + t_ldpc_s),
             # neither HBM nor tensor bound: the decoder's state lives in shared memory for all iterations.  What bounds it is instruction
-            # issue (ncu: smsp__issue_active 85 %, XU pipe 60 % busy from 6 MUFU per edge and iteration), see DESIGN.md section 4 (K_ldpc)
-            "bound": "instruction issue", "evidence": "profiles/r1p_ncu_full.txt (ncu --set full of this kernel)"}
+            # issue (ncu: smsp__issue_active 84 %, XU pipe 61 % busy from 6 MUFU per edge and iteration), see DESIGN.md section 4 (K_ldpc)
+            "bound": "instruction issue", "evidence": "profiles/r1q_ncu_full.txt (ncu --set full of this kernel)"}
 
     # ---- e2e: host buffers through the C-ABI batch call (pinned memory; H2D + kernels + D2H timed) --------------
     e2e = None
