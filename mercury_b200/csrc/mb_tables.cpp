@@ -304,8 +304,10 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 			vtail[(size_t)(i - tail)] = o[0] | (o[1] << 16);
 		}
 		out.off_vtail = bl.put(vtail);
-		// longest-processing-time-first assignment of groups to warps; weight = padded degree of the group (+1 for its fixed cost)
-		auto schedule = [&](int n_groups, auto weight, auto base, uint32_t &off) -> bool {
+		// longest-processing-time-first assignment of groups to warps; weight = padded degree of the group (what the kernel loops over),
+		// cost = what balances the warps: warp instructions of the group in the kernel that will run it (mb_ldpc.cu, ncu source page:
+		// ~45 per edge in a fully unrolled body, ~52 in the generic loop, a degree-2 check is a pass-through; ~3 per edge on the variable side)
+		auto schedule = [&](int n_groups, auto weight, auto cost, auto base, uint32_t &off) -> bool {
 			std::vector<int> order(n_groups);
 			std::iota(order.begin(), order.end(), 0);
 			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
@@ -317,14 +319,18 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 					if (load[i] < load[w]) w = i;
 				if (cnt[w] >= MB_SCHED_LEN - 1 || base(g) > 0xFFFFu || weight(g) > 255) return false;
 				sched[w * MB_SCHED_LEN + cnt[w]++] = base(g) | ((uint32_t)weight(g) << 16) | ((uint32_t)(g + 1) << 24);
-				load[w] += weight(g) + 1;
+				load[w] += cost(weight(g));
 			}
 			off = bl.put(sched);
 			return true;
 		};
-		if (!schedule((P + 31) / 32, [&](int g) { return (int)t.crow[csorted[g * 32]].size(); }, [&](int g) { return cgbase[g]; }, out.off_csched))
+		int fix_lo, fix_hi;
+		mb_ldpc_degree_set(t.rate_num, &fix_lo, &fix_hi);
+		auto check_cost = [&](int d) { return d <= 2 ? 30 : (d >= fix_lo && d <= fix_hi ? 45 * d + 20 : 52 * d + 40); };
+		auto var_cost = [&](int d) { return 3 * d + 8; };
+		if (!schedule((P + 31) / 32, [&](int g) { return (int)t.crow[csorted[g * 32]].size(); }, check_cost, [&](int g) { return cgbase[g]; }, out.off_csched))
 			return "check schedule overflow";
-		if (!schedule(tail / 32, [&](int g) { return (int)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1); }, [&](int g) { return vgbase[g]; },
+		if (!schedule(tail / 32, [&](int g) { return (int)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1); }, var_cost, [&](int g) { return vgbase[g]; },
 			      out.off_vsched))
 			return "variable schedule overflow";
 	}

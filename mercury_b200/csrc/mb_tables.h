@@ -127,6 +127,16 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size);
 void mb_srandom(uint32_t state[35], unsigned seed);
 int mb_random(uint32_t state[35]);
 int mb_rate_index(int rate_num);
+// Which check-group degrees the decoder kernel launched for this rate runs as fully unrolled bodies (mb_ldpc.cu: one kernel instantiation per
+// degree set, measured on the GPU); the table builder balances the static warp schedule with the same knowledge.  Returns 0 / 1 / 2.
+inline int mb_ldpc_degree_set(int rate_num, int *lo, int *hi)
+{
+	const int set = rate_num <= 4 ? 0 : (rate_num <= 6 ? 1 : 2);
+	static const int kLo[3] = {3, 3, 5}, kHi[3] = {5, 7, 9};
+	if (lo) *lo = kLo[set];
+	if (hi) *hi = kHi[set];
+	return set;
+}
 
 // Tone plan of a ROBUST (MFSK) mode: cl_mfsk (include/physical_layer/mfsk.h, mfsk.cc:49-160).
 struct MbMfsk {

@@ -65,14 +65,17 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
     for i, w in enumerate(r["vtail"].astype(int)):
         offs = [int(r["vedge"][be.vslot(r, k, t0 + i)]) * 4 for k in range(int(r["vdeg"][t0 + i]))] + [4 * r["c_slots"]] * 2
         assert (w & 0xFFFF, w >> 16) == (offs[0], offs[1])
-    for sched, n_groups, weight, base in ((r["csched"], (r["P"] + 31) // 32, lambda g: int(r["cdeg"][32 * g]), r["cgbase"]),
-                                          (r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"])):
+    lo, hi = {1: (3, 5), 2: (3, 5), 3: (3, 5), 4: (3, 5), 5: (3, 7), 6: (3, 7), 8: (5, 9), 14: (5, 9)}[r["rate_num"]]  # mb_ldpc_degree_set
+    check_cost = lambda d: 30 if d <= 2 else (45 * d + 20 if lo <= d <= hi else 52 * d + 40)
+    var_cost = lambda d: 3 * d + 8
+    for sched, n_groups, weight, base, cost in ((r["csched"], (r["P"] + 31) // 32, lambda g: int(r["cdeg"][32 * g]), r["cgbase"], check_cost),
+                                                (r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"], var_cost)):
         ent = [int(e) for row in sched for e in row if e != 0]
         assert sorted((e >> 24) - 1 for e in ent) == list(range(n_groups))     # every group exactly once
         assert all(e & 0xFFFF == int(base[(e >> 24) - 1]) and (e >> 16) & 0xFF == weight((e >> 24) - 1) for e in ent)
         assert all(row[-1] == 0 for row in sched)                              # terminated
-        loads = [sum(((int(e) >> 16) & 0xFF) + 1 for e in row if e != 0) for row in sched]
-        assert max(loads) - min(loads) <= max(weight(g) for g in range(n_groups)) + 1  # LPT balance
+        loads = [sum(cost((int(e) >> 16) & 0xFF) for e in row if e != 0) for row in sched]
+        assert max(loads) - min(loads) <= max(cost(weight(g)) for g in range(n_groups))  # LPT balance, in the builder's cost model
     for vi in range(1600):
         v = int(cw_of_var[vi])
         ref_row = [int(c) for c in lt["V"][v] if c != -1]
