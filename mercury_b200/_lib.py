@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmercury_b200.so")
+SO_PATH = os.environ.get("MERCURY_B200_SO") or os.path.join(_HERE, "libmercury_b200.so")  # the override is for kernel tuning builds only
 LDPC_TABLES = os.path.join(_HERE, "data", "ldpc_tables.bin")
 HEADER = os.path.normpath(os.path.join(_HERE, "..", "include", "mercury_b200.h"))
 

@@ -123,6 +123,8 @@ struct mercury_b200 {
 	float2 *dbg_Y = nullptr, *dbg_H = nullptr, *dbg_Z = nullptr;
 	float *h_stage = nullptr;  // pinned staging for receive_baseband
 	size_t h_stage_bytes = 0;
+	// work queues of the persistent decoder kernel: two device words per stream (launches on one stream serialise; the kernel re-arms them)
+	std::vector<std::pair<cudaStream_t, unsigned *>> ldpc_queues;
 };
 
 namespace {
@@ -233,6 +235,14 @@ int launch_ldpc(mercury_b200_t *h, const void *d_llr, size_t n, void *d_payload,
 	a.max_iters = h->ldpc_iters;
 	a.check_gate = 1;
 	a.cheap_test_threads = h->cheap_test_threads;
+	for (const auto &q : h->ldpc_queues)
+		if (q.first == s) a.queue = q.second;
+	if (!a.queue) {
+		MB_CUDA(h, cudaMalloc(&a.queue, 256 + mb_ldpc_max_ctas() * 2 * MB_N * sizeof(float)));  // queue words + per-CTA channel-LLR scratch
+		MB_CUDA(h, cudaMemset(a.queue, 0, 256));
+		h->ldpc_queues.emplace_back(s, a.queue);
+	}
+	a.lch_scratch = reinterpret_cast<float *>(reinterpret_cast<char *>(a.queue) + 256);
 	cudaError_t e = mb_launch_ldpc(a, n, h->decoder, s);
 	if (e != cudaSuccess) return cuda_fail(h, e, "ldpc kernel launch");
 	h->launches++;
@@ -327,6 +337,7 @@ void mercury_b200_destroy(mercury_b200_t *h)
 		if (s.stream) cudaStreamDestroy(s.stream);
 	}
 	if (h->d_scratch_llr) cudaFree(h->d_scratch_llr);
+	for (const auto &q : h->ldpc_queues) cudaFree(q.second);
 	if (h->d_blob) cudaFree(h->d_blob);
 	if (h->d_mfsk_energies) cudaFree(h->d_mfsk_energies);
 	if (h->d_mfsk_out) cudaFree(h->d_mfsk_out);

@@ -39,6 +39,9 @@ struct MbLdpcArgs {
 	int32_t max_iters;
 	int32_t check_gate;    // 1: honour the mean|H| < 0.3 gate recorded by the demod kernel
 	int32_t cheap_test_threads;  // run the syndrome-only test after an iteration that started with <= this many unhappy threads
+	unsigned *queue;       // [2] device words, zero between launches: next frame of the batch, CTAs finished (the kernel re-arms them)
+	float *lch_scratch;    // [mb_ldpc_max_ctas()][2 * 1600] per-CTA channel-LLR scratch (same stream as the queue)
+	unsigned long long n_frames;  // filled by mb_launch_ldpc (the kernel is persistent: resident CTAs pull frames from the queue)
 };
 
 size_t mb_ldpc_smem_bytes(int c_slots);
@@ -48,6 +51,8 @@ cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaS
 cudaError_t mb_demod_init();  // opt-in shared memory attributes, occupancy of every instantiation
 int mb_demod_ctas_per_sm(int Nsymb, int M, int estimator, int phase_only);  // resident CTAs per SM (0 = no such instantiation)
 cudaError_t mb_ldpc_init();
+size_t mb_ldpc_max_ctas();  // largest grid mb_launch_ldpc uses on this device (sizes lch_scratch)
+int mb_ldpc_ctas_per_sm(int algo, int rate_idx, int rate_num, int c_slots);  // resident decoder CTAs (frame pairs) per SM
 
 // ---------------------------------------------------------------------------------------------------------------------
 // RX front-end (mb_frontend.cu): pass-band capture buffers -> synchronised base-band frames for the tail.

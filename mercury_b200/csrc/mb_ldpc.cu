@@ -8,76 +8,355 @@
 //   all-zeros test + CRC16 self check + decision telecom_system.cc:1319-1349, SNR report :1368-1375
 //
 // How (B200-first):
-//   * One CTA per frame. The whole decoder state of a frame lives in shared memory for all iterations:
-//     posterior[1600] + channel LLR[1600] + one float per Tanner-graph edge (26-39 KB per frame, so 5 frames
-//     are resident per SM); HBM is touched once for the 6.4 KB of LLRs in and <=175 bytes + 32 bytes out.
-//   * Only posterior and check->variable messages are stored: the variable->check message of the reference
-//     (its Q array) is recomputed as posterior - R, which is exactly the reference's Q update.
-//   * The Tanner graph is laid out on the host as a warp-blocked ELL on BOTH sides: checks (variables) sorted by
-//     descending degree, cut into groups of 32, each group padded to its largest degree.  A warp owns a group, so
-//     thread-per-check (thread-per-variable) loops walk the per-edge array with a constant +32-word stride, 32
-//     consecutive words per step (conflict free, <12 % padding, uniform trip count inside a warp).  Index tables
-//     are read through the read-only path and stay in L1 (shared by all CTAs of the SM).
-//   * The syndrome of iteration i is evaluated inside the check pass of iteration i+1 (it gathers the same
-//     posteriors anyway) and combined with a single __syncthreads_or: one barrier per half-iteration.
-//   * SPA mode evaluates the check node in the log-magnitude domain, s = -log2 tanh(|q|/2), R = phi(sum of the
-//     other s) (phi is its own inverse).  This keeps fp32 accurate where the product of tanh saturates, and
-//     reproduces the reference's double-precision clamp rule: a factor whose tanh rounds to 1.0 in double
-//     (s < 2^-54 nats) contributes 0, and an all-saturated product gives 2 atanh(0.9999999).
-//     The leave-one-out sum never cancels: the largest term is kept apart (rest = sum of all others), so the edge
-//     that owns it reads `rest` and every other edge reads (rest - self) + largest.  No fp64, no conversions: the
-//     kernel is bound by instruction issue and by the XU pipe (3 MUFU per phi), not by memory.
-//   * MINSUM mode (north_star): normalised min-sum (alpha 1 for degree<=2 where min-sum is exact, 0.85 for 3,
-//     0.75 above), same schedule / exit / clamp.
+//   * TWO frames per thread.  A CTA (8 warps) decodes a PAIR of frames in lock step; every per-edge quantity is a float2
+//     (x = frame in slot A, y = frame in slot B) interleaved in shared memory, so each index load, address computation,
+//     shared-memory access (LDS.64 / STS.64), loop counter and branch is shared by the two frames, and the arithmetic runs on the
+//     packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one issue slot for both frames).  The kernel is bound by instruction issue and by
+//     the XU (MUFU) pipe, not by memory, so this -- with the check-node arithmetic below -- is what sets its speed.
+//   * The two slots are independent decodes: each has its own iteration counter, early exit and verdict.  When a slot finishes
+//     (converged, or ran out of iterations) its epilogue runs and the slot is REFILLED with the next frame of the batch from a
+//     global queue (one atomic per frame), while the other slot carries on: no frame waits for its neighbour, and a batch with a
+//     few non-converging frames (50 iterations against ~5) does not leave SMs idle behind them.  Grid = resident CTAs only.
+//   * The whole decoder state of a pair lives in shared memory for all iterations: posterior[1600] + channel LLR[1600] + one
+//     message per Tanner-graph edge slot, x2 frames (58-86 KB per pair, 3 pairs resident per SM up to rate 8/16).  HBM is touched
+//     once per frame: 6.4 KB of LLRs in, <= 175 + 32 bytes out.
+//   * Only posterior and check->variable messages are stored: the variable->check message of the reference (its Q array) is
+//     recomputed as posterior - R, which is exactly the reference's Q update.
+//   * The Tanner graph is a warp-blocked ELL on BOTH sides (csrc/mb_tables.cpp): checks (variables) sorted by degree, cut into
+//     groups of 32 (one warp), padded to the group's largest degree with edges to a +inf posterior (the neutral element of every
+//     reduction of the check node), static degree-balanced warp schedules.  Index tables hold BYTE offsets into the interleaved
+//     shared arrays and are read through L1.
+//   * The syndrome of iteration i is evaluated inside the check pass of iteration i+1 (it gathers the same posteriors anyway).
+//   * Sum-product check node in the "e-domain", all state in base-2 units (LLR * log2 e, so ex2 / lg2 need no scaling):
+//         e_k = 2^-|q_k|                                (1 MUFU; tanh(|q|/2) = (1 - e)/(1 + e))
+//         (P, M) <- (P + e M, M + e P)  from (1, 0)      (the tanh addition rule: M/P = tanh(sum atanh e_k); all terms positive)
+//         |R_k| = log2(P_k / M_k)  over the OTHER edges  (2 MUFU: rcp, lg2)
+//     which is 2 atanh(prod_{j != k} tanh(|q_j|/2)) exactly, at 3 MUFU per edge and iteration instead of the 6 of the log-domain
+//     form (phi forward + phi backward), with no cancellation anywhere: small degrees combine prefix and suffix pairs in
+//     registers (fully unrolled bodies per degree), larger degrees keep the largest term apart and divide the others out
+//     ((P - e M, M - e P), recombined with the largest term, which dominates whatever the subtraction lost).
+//     It reproduces the reference's DOUBLE-precision clamp rule (ldpc_decoder_SPA.cc:147-155): a factor whose tanh rounds to 1.0
+//     in double (e < 2^-55) contributes e = 0, and an all-saturated product (M == 0) yields 2 atanh(0.9999999).
+//     tools/ldpc_numerics.py: on frames at the decoding threshold this arithmetic agrees with the double-precision reference on
+//     converged / not converged and on the iteration count as the former log-domain form did (100 % of the frames sampled).
+//   * MINSUM mode (north_star): normalised min-sum (alpha 1 for degree<=2 where min-sum is exact, 0.85 for 3, 0.75 above), same
+//     schedule / exit / clamp, same pair structure.
+#include <algorithm>
+#include <cstdlib>
+
 #include "mb_kernels.cuh"
 
 namespace {
 
 constexpr int kThreads = 32 * MB_LDPC_WARPS;
-constexpr float kLn2 = 0.69314718055994531f;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kClampR = 16.811242831518264f;               // 2*atanh(0.9999999), ldpc_decoder_SPA.cc:147-155
-constexpr float kTanhOne2 = 5.5511151231257827e-17f * kLog2e; // s (base-2 units) below which tanh(|q|/2) == 1.0 in double
-constexpr float kSatQ = 38.123095f;                          // |q| above which tanh(|q|/2) == 1.0 in double (the same boundary as kTanhOne2)
-constexpr float kTiny2 = 0.015625f * kLog2e;                 // below this S, 1 - 2^-S would cancel: use log2(2/(S ln2))
+constexpr float kClampR2 = 16.811242831518264f * kLog2e;  // 2 atanh(0.9999999) (ldpc_decoder_SPA.cc:147-155) in base-2 units
+constexpr float kSatQ2 = 55.0f;                           // |q| (base-2 units) above which tanh(|q|/2) == 1.0 in double: e = 2^-|q| < 2^-55
 
-// Forward map, x = |q| (nats) -> s = -log2 tanh(x/2) = log2((1+e)/(1-e)), e = exp(-x).
-//   e < 0.1 : odd series (2/ln2) e (1 + e^2/3 + e^4/5), rel. error < 2e-7  (the logarithm's argument would round to 1)
-//   else    : log2((1+e)/(1-e)); x == 0 gives +inf ("this edge carries no information"), which the check node handles as such.
-__device__ __forceinline__ float phi_fwd(float x)
+typedef float2 f2;
+
+// shared-memory layout (bytes from the start of the dynamic segment); constant offsets keep every hot access [reg + imm].
+// Every array is float2: .x = slot A, .y = slot B.
+constexpr int kOffLam = 0;                         // f2[1601] posterior; [1600] = +inf, the variable every padding slot points at
+// The channel LLRs are NOT in shared memory: they are read once per iteration and variable, in order, so they live in a per-CTA global
+// scratch (L2 resident, 12.8 KB per pair, written at refill) and are streamed past L1.  That keeps three pairs per SM inside 196 KB of
+// shared memory and leaves the L1 60 KB instead of 28 KB: the index tables (22-28 KB per rate, gathered by every warp in every pass)
+// stay L1 resident (ncu: 72 % -> L1 hit rate, long-scoreboard stalls on the index loads).
+#ifndef MB_LDPC_LCH_SMEM
+#define MB_LDPC_LCH_SMEM 0
+#endif
+constexpr int kOffLch = (MB_N + 2) * 8;            // f2[1600] channel LLR (only with MB_LDPC_LCH_SMEM)
+constexpr int kOffR = kOffLch + (MB_LDPC_LCH_SMEM ? MB_N * 8 : 0);  // f2[c_slots + 1] check -> variable message per check-side slot; [c_slots] == 0 always
+constexpr int kMiscBytes = 512;                    // packed bytes of the epilogue [256] + vote counters + queue hand-off
+
+__host__ __device__ constexpr int r_bytes(int c_slots) { return ((c_slots + 2) & ~1) * 8; }
+
+// 32-bit shared-window addressing (one add per access, base kept in a register)
+__device__ __forceinline__ f2 lds2(unsigned addr)
 {
-	const float e = exp2f(-x * kLog2e);  // ex2.approx.ftz under -ftz=true
-	const float e2 = e * e;
-	const float t = fmaf(e2, 0.2f, 1.0f / 3.0f);
-	const float e_s = e * (2.0f * kLog2e);
-	const float series = fmaf(e_s, e2 * t, e_s);
-	const float lg = __log2f(__fdividef(1.0f + e, 1.0f - e));
-	return e < 0.1f ? series : lg;
+	f2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	return v;
 }
+__device__ __forceinline__ void sts2(unsigned addr, f2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
 
-// Backward map, S (base-2 units) -> R = phi(S) in nats = ln((1+e)/(1-e)), e = 2^-S.
-//   S < kTiny2 : ln(2 / (S ln2))   (1 - e would cancel; error < 2e-5 absolute on a value > 4.8)
-//   else       : ln2 * log2((1+e)/(1-e)); for large S the result is tiny and only its absolute error (1e-7) matters.
-__device__ __forceinline__ float phi_bwd(float S)
+__device__ __forceinline__ float ldg_stream(const float *p)
 {
-	const float e = exp2f(-S);
-	const bool tiny = S < kTiny2;
-	const float num = tiny ? 2.0f * kLog2e : 1.0f + e;
-	const float den = tiny ? S : 1.0f - e;
-	return kLn2 * __log2f(__fdividef(num, den));
+	float v;
+	asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	return v;
 }
-
-// x > 0 ? a : b as an opaque select: phi_bwd is evaluated unconditionally (its inf/NaN at x <= 0 is discarded), which is cheaper
-// than the divergent branch the compiler would otherwise wrap around the three MUFU operations
-__device__ __forceinline__ float sel_gt0(float x, float a, float b)
+__device__ __forceinline__ unsigned fbits(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ float ex2_negabs(float x)
 {
 	float r;
-	asm("{\n\t.reg .pred p;\n\tsetp.gt.ftz.f32 p, %1, 0f00000000;\n\tselp.f32 %0, %2, %3, p;\n\t}" : "=f"(r) : "f"(x), "f"(a), "f"(b));
+	asm("{\n\t.reg .f32 t;\n\tabs.f32 t, %1;\n\tneg.f32 t, t;\n\tex2.approx.ftz.f32 %0, t;\n\t}" : "=f"(r) : "f"(x));  // -|x| folds into the MUFU operand
 	return r;
 }
+__device__ __forceinline__ float rcp_fast(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float lg2_fast(float x)
+{
+	float r;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+// (a & 0x7fffffff) | (s & 0x80000000): one LOP3
+__device__ __forceinline__ float copysign_bits(float mag, unsigned s) { return __uint_as_float((fbits(mag) & 0x7fffffffu) | (s & 0x80000000u)); }
 
-// parity of the hard decisions accumulated as XOR of raw sign bits -> 0/1
-__device__ __forceinline__ unsigned lam_sign_fix(unsigned x) { return x >> 31; }
+// e = 2^-|q| for both frames, flushed to 0 below 2^-55 (the factor's tanh is 1.0 in double): scaling by 2^-71 under FTZ drops
+// exactly those values and is exact for the others (two packed multiplies instead of two compare + select pairs).
+__device__ __forceinline__ f2 edge_e(f2 q)
+{
+	const f2 e = make_float2(ex2_negabs(q.x), ex2_negabs(q.y));
+	f2 t;
+	asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmul.rn.ftz.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+	    : "=f"(t.x), "=f"(t.y)
+	    : "f"(e.x), "f"(e.y), "f"(4.235164736e-22f /* 2^-71 */));
+	return __fmul2_rn(t, make_float2(2.361183241e21f, 2.361183241e21f) /* 2^71 */);
+}
+
+// (P, M) pairs of the tanh addition rule, packed over the two frames
+struct Gen {
+	f2 P, M;
+};
+__device__ __forceinline__ Gen comb_ss(f2 a, f2 b) { return Gen{__ffma2_rn(a, b, make_float2(1.f, 1.f)), __fadd2_rn(a, b)}; }
+__device__ __forceinline__ Gen comb_gs(Gen g, f2 e) { return Gen{__ffma2_rn(e, g.M, g.P), __ffma2_rn(e, g.P, g.M)}; }
+__device__ __forceinline__ Gen comb_gg(Gen a, Gen b)
+{
+	return Gen{__ffma2_rn(a.M, b.M, __fmul2_rn(a.P, b.P)), __ffma2_rn(a.M, b.P, __fmul2_rn(a.P, b.M))};
+}
+
+// |R| = log2(P / M) of the other edges, M == 0 (every other factor saturated) -> the reference's clamp; sign = product of the other
+// edges' signs = parity of all of them ^ this edge's own.  GUARD: the divide-out form can leave rounding noise of either sign where the
+// true ratio is 1 (message 0); a ratio below 1 / NaN is read as 1.
+template <bool GUARD>
+__device__ __forceinline__ void emit(unsigned addr, Gen o, unsigned sa, unsigned sb)
+{
+	f2 ratio = __fmul2_rn(o.P, make_float2(rcp_fast(o.M.x), rcp_fast(o.M.y)));
+	if (GUARD) ratio = make_float2(fmaxf(ratio.x, 1.0f), fmaxf(ratio.y, 1.0f));
+	float lx = lg2_fast(ratio.x), ly = lg2_fast(ratio.y);
+	lx = lx < 3.0e38f ? lx : kClampR2;
+	ly = ly < 3.0e38f ? ly : kClampR2;
+	sts2(addr, make_float2(copysign_bits(lx, sa), copysign_bits(ly, sb)));
+}
+
+// Shuffle helpers for checks split over S = 2, 4, 8 lanes (lanes of one check are 32 / S apart: xor masks 32 / S, .., 16).
+__device__ __forceinline__ Gen shfl_gen(Gen g, int mask)
+{
+	Gen r;
+	r.P.x = __shfl_xor_sync(0xffffffffu, g.P.x, mask), r.P.y = __shfl_xor_sync(0xffffffffu, g.P.y, mask);
+	r.M.x = __shfl_xor_sync(0xffffffffu, g.M.x, mask), r.M.y = __shfl_xor_sync(0xffffffffu, g.M.y, mask);
+	return r;
+}
+// (+) of the totals T of all OTHER lanes of this lane's check (xor butterfly: the partner's total, then the other pair's, then the other quad's)
+__device__ __forceinline__ Gen lanes_outside(Gen T, int log2s)
+{
+	int mask = 32 >> log2s;
+	Gen out = shfl_gen(T, mask);
+	if (log2s > 1) {
+		Gen U = comb_gg(T, out);
+		mask <<= 1;
+		const Gen U2 = shfl_gen(U, mask);
+		out = comb_gg(out, U2);
+		if (log2s > 2) {
+			U = comb_gg(U, U2);
+			out = comb_gg(out, shfl_gen(U, mask << 1));
+		}
+	}
+	return out;
+}
+__device__ __forceinline__ unsigned lanes_xor(unsigned x, int log2s)
+{
+	for (int mask = 32 >> log2s; mask < 32; mask <<= 1) x ^= __shfl_xor_sync(0xffffffffu, x, mask);
+	return x;
+}
+
+// Sum-product check node of one lane for a PAIR of frames, D edges (compile time, 3..MB_LDPC_DMAX + 1): reads the posteriors and
+// messages, writes the new messages, XORs the hard decisions into hard_a / hard_b (sign bit).  Leave-one-out by prefix and suffix
+// (P, M) pairs held in registers; the first combinations are specialised ((1, 0) and (1, e) need no multiplies).
+// log2s > 0 (warp uniform): the check is spread over 2^log2s lanes (mb_tables.h: mb_ldpc_split), D - 1 real edges in this lane.  The
+// lanes exchange their totals, sign parities and hard-decision parities by shuffles, and the (+) of the OTHER lanes' totals enters this
+// lane's leave-one-out as one more edge, e = M / P (a (P, M) pair and the single term (1, M / P) are the same up to a factor that
+// cancels in every ratio).  So split and unsplit checks run the SAME body: the decoder's hot code has to stay inside the 32 KB
+// instruction cache (ncu: with separate bodies the warps stalled on instruction fetch as often as on the barriers).
+template <int D>
+__device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int log2s, unsigned &hard_a, unsigned &hard_b)
+{
+	f2 q[D], e[D];
+	unsigned pa = 0, pb = 0, ha = 0, hb = 0;
+	const bool split = D >= 5 && log2s != 0;  // split tasks hold 4..MB_LDPC_DMAX edges per lane
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		if (k == D - 1 && split) break;
+		const unsigned off = ve[k * 32];
+		const f2 lam = lds2(sbase + kOffLam + off);
+		const f2 r = lds2(raddr + k * 256);
+		q[k] = __ffma2_rn(r, make_float2(-1.f, -1.f), lam);
+		ha ^= fbits(lam.x);
+		hb ^= fbits(lam.y);
+		pa ^= fbits(q[k].x);
+		pb ^= fbits(q[k].y);
+		e[k] = edge_e(q[k]);
+	}
+	if (split) {
+		// sign parities and hard-decision parities of the whole check: one word per frame through the butterfly (bit 31: q, bit 30: posterior)
+		pa = lanes_xor((pa & 0x80000000u) | ((ha >> 1) & 0x40000000u), log2s);
+		pb = lanes_xor((pb & 0x80000000u) | ((hb >> 1) & 0x40000000u), log2s);
+		ha = pa << 1, hb = pb << 1;
+		Gen tot = comb_ss(e[0], e[1]);
+#pragma unroll
+		for (int k = 2; k < D - 1; k++) tot = comb_gs(tot, e[k]);
+		const Gen out = lanes_outside(tot, log2s);
+		e[D - 1] = __fmul2_rn(out.M, make_float2(rcp_fast(out.P.x), rcp_fast(out.P.y)));  // P >= 1
+		q[D - 1] = make_float2(0.f, 0.f);
+	}
+	hard_a ^= ha, hard_b ^= hb;
+	Gen pre[D];  // pre[k] = e_0 (+) .. (+) e_{k-1}, k >= 2
+	pre[2] = comb_ss(e[0], e[1]);
+#pragma unroll
+	for (int k = 3; k < D; k++) pre[k] = comb_gs(pre[k - 1], e[k - 1]);
+	if (!split) emit<false>(raddr + (D - 1) * 256, pre[D - 1], fbits(q[D - 1].x) ^ pa, fbits(q[D - 1].y) ^ pb);
+	if (D >= 4)
+		emit<false>(raddr + (D - 2) * 256, comb_gs(pre[D >= 4 ? D - 2 : 2], e[D - 1]), fbits(q[D - 2].x) ^ pa, fbits(q[D - 2].y) ^ pb);
+	else
+		emit<false>(raddr + 256, comb_ss(e[0], e[2]), fbits(q[1].x) ^ pa, fbits(q[1].y) ^ pb);
+	Gen suf = comb_ss(e[D - 2], e[D - 1]);
+#pragma unroll
+	for (int k = D - 3; k >= 0; k--) {
+		const Gen o = k >= 2 ? comb_gg(pre[k >= 2 ? k : 2], suf) : (k == 1 ? comb_gs(suf, e[0]) : suf);
+		emit<false>(raddr + k * 256, o, fbits(q[k].x) ^ pa, fbits(q[k].y) ^ pb);
+		if (k > 0) suf = comb_gs(suf, e[k]);
+	}
+}
+
+// Degree-2 check (two thirds of the checks of the low-rate codes): R_a = 2 atanh(tanh(q_b / 2)) is q_b itself until tanh rounds to 1.0
+// in double, where the reference's clamp gives 2 atanh(0.9999999) (ldpc_decoder_SPA.cc:147-155).  A padding edge (q = +inf) saturates
+// to the clamp: exactly the reference's empty product of a degree-1 check.
+__device__ __forceinline__ float sat_q(float q) { return fabsf(q) > kSatQ2 ? copysign_bits(kClampR2, fbits(q)) : q; }
+__device__ __forceinline__ void spa_check_pair_2(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, unsigned &hard_a, unsigned &hard_b)
+{
+	const f2 l0 = lds2(sbase + kOffLam + ve[0]), l1 = lds2(sbase + kOffLam + ve[32]);
+	const f2 q0 = __ffma2_rn(lds2(raddr), make_float2(-1.f, -1.f), l0), q1 = __ffma2_rn(lds2(raddr + 256), make_float2(-1.f, -1.f), l1);
+	hard_a ^= fbits(l0.x) ^ fbits(l1.x);
+	hard_b ^= fbits(l0.y) ^ fbits(l1.y);
+	sts2(raddr, make_float2(sat_q(q1.x), sat_q(q1.y)));
+	sts2(raddr + 256, make_float2(sat_q(q0.x), sat_q(q0.y)));
+}
+
+// Normalised min-sum check node of one lane for a pair of frames (alpha 1 for true degree <= 2 where min-sum is exact, 0.85 for 3,
+// 0.75 above), d edges per lane (warp uniform, <= MB_LDPC_DMAX); a check split over 2^log2s lanes merges the lanes' two smallest
+// magnitudes and sign parities by shuffles.
+struct MinSum {
+	float m1 = 3.0e38f, m2 = 3.0e38f;
+	int arg = -1;
+	unsigned signs = 0u;
+	unsigned par = 0;
+	__device__ __forceinline__ void take(float q, int k)
+	{
+		par ^= fbits(q);
+		signs |= (fbits(q) >> 31) << k;
+		const float aq = fabsf(q);
+		const bool lt1 = aq < m1;
+		m2 = lt1 ? m1 : fminf(m2, aq);
+		arg = lt1 ? k : arg;
+		m1 = lt1 ? aq : m1;
+	}
+	// the smallest magnitude over the OTHER lanes of the check (-> o1), and the sign parity over ALL its lanes
+	__device__ __forceinline__ void exchange(int log2s, float &o1)
+	{
+		o1 = 3.0e38f;
+		float u1 = m1;
+		for (int mask = 32 >> log2s; mask < 32; mask <<= 1) {
+			const float t1 = __shfl_xor_sync(0xffffffffu, u1, mask);
+			o1 = fminf(o1, t1), u1 = fminf(u1, t1);
+			par ^= __shfl_xor_sync(0xffffffffu, par, mask);
+		}
+	}
+	__device__ __forceinline__ float give(int k, float alpha, float o1) const
+	{
+		const float mag = fminf(alpha * fminf(k == arg ? m2 : m1, o1), kClampR2);
+		return ((par >> 31) ^ ((signs >> k) & 1u)) ? -mag : mag;
+	}
+};
+__device__ __forceinline__ void minsum_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int d, int log2s, int dc, unsigned &hard_a,
+						  unsigned &hard_b)
+{
+	MinSum a, b;
+	unsigned ha = 0, hb = 0;
+#pragma unroll 4
+	for (int k = 0; k < d; k++) {
+		const f2 lam = lds2(sbase + kOffLam + ve[k * 32]);
+		const f2 q = __ffma2_rn(lds2(raddr + k * 256), make_float2(-1.f, -1.f), lam);
+		ha ^= fbits(lam.x);
+		hb ^= fbits(lam.y);
+		a.take(q.x, k);
+		b.take(q.y, k);
+	}
+	float oa = 3.0e38f, ob = 3.0e38f;
+	if (log2s > 0) {
+		a.exchange(log2s, oa);
+		b.exchange(log2s, ob);
+		ha = lanes_xor(ha, log2s), hb = lanes_xor(hb, log2s);
+	}
+	hard_a ^= ha, hard_b ^= hb;
+	const float alpha = dc <= 2 ? 1.0f : (dc == 3 ? 0.85f : 0.75f);
+#pragma unroll 4
+	for (int k = 0; k < d; k++) sts2(raddr + k * 256, make_float2(a.give(k, alpha, oa), b.give(k, alpha, ob)));
+}
+
+// Variable node of the head (degree > 2, groups padded to an even degree): channel LLR + the incoming messages in the table's order.
+// D > 0: fixed group degree, every index load and gather at an immediate offset.
+template <int D>
+__device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__restrict__ se, f2 acc, int d_rt)
+{
+	if (D > 0) {
+		unsigned idx[D > 0 ? D : 1];
+#pragma unroll
+		for (int k = 0; k < D; k++) idx[k] = se[k * 32];
+#pragma unroll
+		for (int k = 0; k < D; k++) acc = __fadd2_rn(acc, lds2(sbase + kOffR + idx[k]));
+		return acc;
+	}
+	int k = 0;
+#pragma unroll 1
+	for (; k + 4 <= d_rt; k += 4) {
+		const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
+		se += 128;
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i0));
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i1));
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i2));
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i3));
+	}
+	if (k < d_rt) {
+		const unsigned i0 = se[0], i1 = se[32];
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i0));
+		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i1));
+	}
+	return acc;
+}
+
+// XOR of the hard decisions of one check (syndrome-only test), both frames; D edges per lane, the check spread over 2^log2s lanes
+template <int D>
+__device__ __forceinline__ void check_parity(unsigned sbase, const uint16_t *__restrict__ ve, int log2s, unsigned &bad_a, unsigned &bad_b)
+{
+	unsigned idx[D], ha = 0, hb = 0;
+#pragma unroll
+	for (int k = 0; k < D; k++) idx[k] = ve[k * 32];
+#pragma unroll
+	for (int k = 0; k < D; k++) {
+		const f2 lam = lds2(sbase + kOffLam + idx[k]);
+		ha ^= fbits(lam.x);
+		hb ^= fbits(lam.y);
+	}
+	if (log2s > 0) ha = lanes_xor(ha, log2s), hb = lanes_xor(hb, log2s);
+	bad_a |= ha >> 31;
+	bad_b |= hb >> 31;
+}
 
 __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 {
@@ -87,328 +366,38 @@ __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 	return crc;
 }
 
-// shared-memory layout (bytes from the start of the dynamic segment); constant offsets keep every hot access [reg + imm]
-constexpr int kOffLam = 0;                        // float[1601] posterior; [1600] = +inf, the variable every padding slot points at
-constexpr int kOffLch = (MB_N + 4) * 4;           // float[1600] channel LLR
-constexpr int kOffR = kOffLch + MB_N * 4;         // float[c_slots + 1] check -> variable message per check-side slot; [c_slots] == 0 always
+struct Smem {
+	unsigned char *raw;
+	unsigned sbase;
+	unsigned char *bytes;   // [256] packed bytes of the frame being finished; [255] = its verdict
+	unsigned *cnt;          // [2][MB_LDPC_WARPS] per-warp vote counts (check pass, syndrome test): A | B << 16
+	volatile int *next;     // [2] queue hand-off: tickets of the next two refills, alternating (no barrier between reading one and fetching the next)
+	int *turn;              // which of the two holds the next refill's ticket (register copy per thread, uniform)
+	const uint32_t *csched; // [MB_LDPC_WARPS][MB_SCHED_LEN] check tasks per warp (shared-memory copy)
+	__device__ __forceinline__ float &lam(int v, int X) const { return reinterpret_cast<float *>(raw + kOffLam)[2 * v + X]; }
+	float *lch_g;           // this CTA's channel-LLR scratch in global memory, f2[1600] (x = slot A, y = slot B)
+	__device__ __forceinline__ void set_lch(int v, int X, float w) const
+	{
+		if (MB_LDPC_LCH_SMEM) reinterpret_cast<float *>(raw + kOffLch)[2 * v + X] = w;
+		else lch_g[2 * v + X] = w;
+	}
+	__device__ __forceinline__ f2 get_lch(int v) const
+	{
+		if (MB_LDPC_LCH_SMEM) return lds2(sbase + kOffLch + v * 8);
+		f2 r;
+		asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(lch_g + 2 * v));
+		return r;
+	}
+	__device__ __forceinline__ float &R(int i, int X) const { return reinterpret_cast<float *>(raw + kOffR)[2 * i + X]; }
+};
 
-// 32-bit shared-window addressing for the gathers of the hot loops (one add per access, base kept in a register)
-__device__ __forceinline__ float lds_f(unsigned sbase, unsigned off)
+// ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record (+ the ZF modes' SNR report) of slot X ------------
+// Called by the whole CTA (uniform); the other slot's interleaved state is not touched.
+__device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int X, size_t frame, int iterations)
 {
-	float v;
-	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sbase + off));
-	return v;
-}
-
-// Sum-product check node of one lane (one check of a warp group padded to degree d): reads the d posteriors and messages, writes the d new
-// messages, returns the XOR of the hard decisions (sign bit in bit 0).
-// Leave-one-out sums without cancellation: the largest term is kept apart (big) and rest = sum of all the others, by a running (min, max)
-// pair -- no index tracking: the edge that owns the largest term is recognised by value in the second loop (ties are harmless: each tied
-// edge's leave-one-out sum is the same `rest`).  s = +inf (q == 0) needs no clamp: it parks in `big`, every other edge then sees
-// inf -> message 0, and two of them make rest = inf -> all messages 0.
-// D > 0: the group degree is a compile-time constant (the common degrees are instantiated): both loops unroll completely, every
-// shared-memory access is [register + immediate] and there is no loop counter -- about a sixth of the generic loop's instructions
-// were counters, compares, branches and address arithmetic (ncu source page, profiles/r1n).  Same operations in the same order.
-// Which group degrees get their own body was measured on the GPU (B200, ms per 65,536 frames; generic loop only: mode 8 5.06):
-//   mode 8 (rate 6/16): {3..8} 4.67, {4..8} 4.47, {5..8} 4.51, {3..6} 4.39, {5..7} 4.41, {4..6} 4.48, {4..7} 4.32, {3..7} 4.24, {3..10} 4.98
-//   mode 9 (rate 8/16): {3..7} 4.31, {5..7} 4.29, {6..7} 4.38, {7} 4.54, {6..9} 4.31, {5..9} 4.22
-// More bodies are not better: a body is ~45 instructions per edge, the eight warps of a CTA sit in different bodies at once (instruction
-// cache), and degrees that are multiples of 4 lose little in the generic loop anyway (it is unrolled by 4: 4 / 2 / 1 next to {4..7} gave
-// 4.32 / 4.32 / 4.39).  Chunked unrolling of the larger fixed degrees (8 -> 2 x 4) did not change that in mode 8 ({3..8} 4.37-4.40), nor did keeping
-// the parked magnitudes in registers instead of the message slots (degree <= 4 / 6 / 8: 4.69 / 4.74 / 4.73 against 4.66).
-// So the kernel is instantiated per degree SET and the launch picks the set by rate (check degrees: SURVEY.md 8a graph table): rates
-// 1..4/16 {3..5}, rates 5,6/16 {3..7}, rate 8/16 {5..9}; rate 14/16 (degrees 23-46) runs the generic loop whichever set is loaded.
-constexpr int kGenUnroll = 4;
-// unroll factor of a body: complete up to 7 edges, beyond that in equal chunks (8 -> 2 x 4, 9 -> 3 x 3): the trip count is still a constant
-// (no remainder loop) and the body stays small.  Rate 8/16 (mode 9, 65,536 frames): {5..9} chunked 4.22 ms, {5..9} complete 4.62, {6..9} 4.31.
-__host__ __device__ constexpr int fix_unroll(int D) { return D <= 0 ? kGenUnroll : (D <= 7 ? D : (D % 2 == 0 ? D / 2 : (D % 3 == 0 ? D / 3 : D))); }
-template <int D>
-__device__ __forceinline__ unsigned spa_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt)
-{
-	const int d = D > 0 ? D : d_rt;
-	unsigned hard = 0, par = 0;
-	float big = 0.f, rest = 0.f;
-#pragma unroll(fix_unroll(D))
-	for (int k = 0; k < d; k++) {
-		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
-		const float q = lam - Re[k * 32];
-		hard ^= __float_as_uint(lam);  // sign bit only is used
-		par ^= __float_as_uint(q);
-		float s = phi_fwd(fabsf(q));
-		s = s < kTanhOne2 ? 0.f : s;
-		rest += fminf(s, big);
-		big = fmaxf(s, big);
-		Re[k * 32] = __uint_as_float(__float_as_uint(s) | (__float_as_uint(q) & 0x80000000u));  // signed magnitude parked in the slot
-	}
-	const unsigned pneg = par & 0x80000000u;
-#pragma unroll(fix_unroll(D))
-	for (int k = 0; k < d; k++) {
-		const unsigned tb = __float_as_uint(Re[k * 32]);
-		const float sk = __uint_as_float(tb & 0x7fffffffu);
-		const float so = sk == big ? rest : (rest - sk) + big;
-		const float mag = sel_gt0(so, phi_bwd(so), kClampR);  // all-saturated product -> 2 atanh(0.9999999)
-		Re[k * 32] = __uint_as_float(__float_as_uint(mag) | ((tb ^ pneg) & 0x80000000u));
-	}
-	return lam_sign_fix(hard);
-}
-
-// Variable node of the head (degree > 2, groups padded to an even degree): channel LLR + the incoming messages in the table's order.
-// D > 0: fixed group degree, every index load and gather at an immediate offset.
-template <int D>
-__device__ __forceinline__ float var_node_sum(unsigned sbase, const uint16_t *__restrict__ se, float acc, int d_rt)
-{
-	if (D > 0) {
-		unsigned idx[D > 0 ? D : 1];
-#pragma unroll
-		for (int k = 0; k < D; k++) idx[k] = se[k * 32];
-#pragma unroll
-		for (int k = 0; k < D; k++) acc += lds_f(sbase, kOffR + idx[k]);
-		return acc;
-	}
-	int k = 0;
-#pragma unroll 1
-	for (; k + 4 <= d_rt; k += 4) {
-		const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
-		se += 128;
-		acc += lds_f(sbase, kOffR + i0);
-		acc += lds_f(sbase, kOffR + i1);
-		acc += lds_f(sbase, kOffR + i2);
-		acc += lds_f(sbase, kOffR + i3);
-	}
-	if (k < d_rt) {
-		const unsigned i0 = se[0], i1 = se[32];
-		acc += lds_f(sbase, kOffR + i0);
-		acc += lds_f(sbase, kOffR + i1);
-	}
-	return acc;
-}
-
-// XOR of the hard decisions of one check (syndrome-only test)
-template <int D>
-__device__ __forceinline__ unsigned check_parity(unsigned sbase, const uint16_t *__restrict__ ve, int d_rt)
-{
-	const int d = D > 0 ? D : d_rt;
-	unsigned hard = 0;
-#pragma unroll(D > 0 ? D : 4)
-	for (int k = 0; k < d; k++) hard ^= __float_as_uint(lds_f(sbase, kOffLam + ve[k * 32]));
-	return hard >> 31;
-}
-
-// Normalised min-sum check node of one lane, same contract as spa_check_node (alpha 1 for true degree <= 2 where min-sum is exact, 0.85 for
-// 3, 0.75 above); D > 0: fixed group degree, loops unrolled, the sign bits and the arg-min compare against constants.
-template <int D>
-__device__ __forceinline__ unsigned minsum_check_node(unsigned sbase, const uint16_t *__restrict__ ve, float *__restrict__ Re, int d_rt, int dc)
-{
-	const int d = D > 0 ? D : d_rt;
-	unsigned hard = 0, par = 0;
-	float m1 = 3.0e38f, m2 = 3.0e38f;
-	int arg = -1;
-	unsigned long long signs = 0ull;
-#pragma unroll(fix_unroll(D))
-	for (int k = 0; k < d; k++) {
-		const float lam = lds_f(sbase, kOffLam + ve[k * 32]);
-		const float q = lam - Re[k * 32];
-		hard ^= __float_as_uint(lam);
-		par ^= __float_as_uint(q);
-		signs |= (unsigned long long)(__float_as_uint(q) >> 31) << k;
-		const float aq = fabsf(q);
-		const bool lt1 = aq < m1;
-		m2 = lt1 ? m1 : fminf(m2, aq);
-		arg = lt1 ? k : arg;
-		m1 = lt1 ? aq : m1;
-	}
-	const float alpha = dc <= 2 ? 1.0f : (dc == 3 ? 0.85f : 0.75f);
-	const unsigned pneg = par >> 31;
-#pragma unroll(fix_unroll(D))
-	for (int k = 0; k < d; k++) {
-		const float mag = fminf(alpha * (k == arg ? m2 : m1), kClampR);
-		const unsigned neg = pneg ^ (unsigned)((signs >> k) & 1ull);
-		Re[k * 32] = neg ? -mag : mag;
-	}
-	return lam_sign_fix(hard);
-}
-
-template <int ALGO, int FMIN, int FMAX>
-__global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	constexpr bool kSmallBodies = FMAX <= 7;  // per-degree bodies of the variable nodes and of the syndrome test as well
 	const MbMode &m = a.mode;
 	const MbRate &rt = a.rate;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int CS = rt.c_slots;
-	float *s_lam = reinterpret_cast<float *>(smem_raw + kOffLam);
-	float *s_lch = reinterpret_cast<float *>(smem_raw + kOffLch);
-	float *s_R = reinterpret_cast<float *>(smem_raw + kOffR);
-	uint32_t *s_csched = reinterpret_cast<uint32_t *>(smem_raw + kOffR + ((CS + 4) & ~3) * 4);  // [8][16] check-group descriptors per warp
-	uint32_t *s_vsched = s_csched + MB_LDPC_WARPS * MB_SCHED_LEN;                              // [8][16] variable-group descriptors per warp
-	unsigned char *s_bytes = reinterpret_cast<unsigned char *>(s_vsched + MB_LDPC_WARPS * MB_SCHED_LEN);
-
-	const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
-
-	const size_t frame = blockIdx.x;
-	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);  // byte offsets into s_lam
-	const uint16_t *__restrict__ g_vedge = reinterpret_cast<const uint16_t *>(a.blob + rt.off_vedgeb);        // byte offsets into s_R
-	const uint32_t *__restrict__ g_vtail = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vtail);          // two byte offsets per degree-<=2 variable
-
-	MbRxStats st = a.stats[frame];
-	if (a.check_gate && !(st.mean_H >= 0.3f)) {
-		// telecom_system.cc:1268-1280: a channel estimate this weak means a false sync; the reference skips the decode
-		for (int i = tid; i < m.frame_bytes; i += kThreads) a.payload[frame * (size_t)m.frame_bytes + i] = 0;
-		if (tid == 0) {
-			st.iterations_done = -1;
-			st.crc = 0;
-			st.all_zeros = 0;
-			st.message_decoded = 0;
-			st.SNR = -99.9f;
-			a.stats[frame] = st;
-		}
-		return;
-	}
-
-	{
-		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores
-		const float *__restrict__ src = a.llr + frame * (size_t)MB_HANDOFF_STRIDE;
-		for (int i = tid; i < MB_N; i += kThreads) {
-			const float v = __ldcs(src + i);
-			const unsigned p = MB_HANDOFF_INV((unsigned)i);
-			s_lam[p] = v;
-			s_lch[p] = v;
-		}
-		for (int i = tid; i <= CS; i += kThreads) s_R[i] = 0.f;
-		if (tid < MB_LDPC_WARPS * MB_SCHED_LEN) {
-			s_csched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_csched)[tid];
-			s_vsched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vsched)[tid];
-		}
-		if (tid == 0) s_lam[MB_N] = __int_as_float(0x7f800000);  // +inf: a padding edge contributes s = 0, sign +, hard bit 0
-	}
-	__syncthreads();
-
-	const int vtail0 = rt.vtail_start;
-	int iterations = 0;
-	for (int pass = 0;; pass++) {
-		// ---- check pass: syndrome of the current posterior + new check->variable messages ----------------
-		// A warp owns a group of 32 checks padded to one degree; padding slots point at the +inf variable, so the loops are
-		// warp-uniform (no per-thread degree, no divergence) and a padding edge is the neutral element of every reduction.
-		unsigned unsat = 0;
-		const uint32_t *sched = s_csched + warp * MB_SCHED_LEN;
-		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check groups (static, degree-balanced schedule)
-			const int d = (int)((desc >> 16) & 0xFFu);
-			const int e0 = (int)(desc & 0xFFFFu) + lane;
-			float *__restrict__ Re = s_R + e0;
-			const uint16_t *__restrict__ ve = g_edge_var + e0;
-			unsigned hard = 0, par = 0;
-			if (ALGO == 0 && d == 2) {
-				// Degree-2 check (two thirds of the checks of the low-rate codes): R_a = 2 atanh(tanh(q_b / 2)) is q_b itself until tanh
-				// rounds to 1.0 in double (|q| > 37.43), where the reference's clamp gives 2 atanh(0.9999999) (ldpc_decoder_SPA.cc:147-155).
-				// A padding edge (q = +inf) saturates to the clamp: exactly the reference's empty product of a degree-1 check.
-				const float l0 = lds_f(sbase, kOffLam + ve[0]), l1 = lds_f(sbase, kOffLam + ve[32]);
-				const float q0 = l0 - Re[0], q1 = l1 - Re[32];
-				hard = lam_sign_fix(__float_as_uint(l0) ^ __float_as_uint(l1));
-				Re[0] = fabsf(q1) > kSatQ ? copysignf(kClampR, q1) : q1;
-				Re[32] = fabsf(q0) > kSatQ ? copysignf(kClampR, q0) : q0;
-			} else if (ALGO == 0) {
-				switch (d) {
-#define MB_FIX_CASE(D_) \
-	case D_:            /* a degree outside the instantiated set falls through to the generic loop */ \
-		if (D_ >= FMIN && D_ <= FMAX && d == D_) { hard = spa_check_node<(D_ >= FMIN && D_ <= FMAX) ? D_ : 0>(sbase, ve, Re, d); break; }
-				MB_FIX_CASE(3)
-				MB_FIX_CASE(4)
-				MB_FIX_CASE(5)
-				MB_FIX_CASE(6)
-				MB_FIX_CASE(7)
-				MB_FIX_CASE(8)
-				MB_FIX_CASE(9)
-				MB_FIX_CASE(10)
-#undef MB_FIX_CASE
-				default: hard = spa_check_node<0>(sbase, ve, Re, d); break;
-				}
-			} else {
-				const int c = (int)((desc >> 24) - 1u) * 32 + lane;
-				const int dc = c < rt.P ? (int)(a.blob + rt.off_cdeg)[c] : 0;  // the true degree picks the normalisation
-				switch (d) {
-#define MB_FIX_CASE(D_) \
-	case D_:            /* a degree outside the instantiated set falls through to the generic loop */ \
-		if (D_ >= FMIN && D_ <= FMAX && d == D_) { hard = minsum_check_node<(D_ >= FMIN && D_ <= FMAX) ? D_ : 0>(sbase, ve, Re, d, dc); break; }
-				MB_FIX_CASE(3)
-				MB_FIX_CASE(4)
-				MB_FIX_CASE(5)
-				MB_FIX_CASE(6)
-				MB_FIX_CASE(7)
-				MB_FIX_CASE(8)
-				MB_FIX_CASE(9)
-				MB_FIX_CASE(10)
-#undef MB_FIX_CASE
-				default: hard = minsum_check_node<0>(sbase, ve, Re, d, dc); break;
-				}
-			}
-			unsat |= hard;
-		}
-		// number of threads that saw an unsatisfied check: 0 = converged; a small count = "probably one iteration to go"
-		const int n_unsat = __syncthreads_count((int)unsat);
-		if (n_unsat == 0) {
-			iterations = pass;  // converged after `pass` iterations (0 = clean on arrival, ldpc_decoder_SPA.cc:62-77)
-			break;
-		}
-		if (pass == a.max_iters) {
-			iterations = a.max_iters + 1;  // ldpc_decoder_SPA.cc:127,217: loop ran out
-			break;
-		}
-		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order) ----------
-		// Variables are numbered by descending degree.  The head (degree > 2) is walked in warp groups padded to one even
-		// degree (padding reads the always-zero slot); the long tail of degree-<=2 variables (the accumulator chain of the IRA
-		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.
-		sched = s_vsched + warp * MB_SCHED_LEN;
-		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
-			const int d = (int)((desc >> 16) & 0xFFu);
-			const int v = (int)((desc >> 24) - 1u) * 32 + lane;
-			const uint16_t *__restrict__ se = g_vedge + ((desc & 0xFFFFu) + lane);
-			float acc = s_lch[v];
-			// (the {5..9} kernel of rate 8/16 is at its instruction-cache budget with the check bodies alone: mode 9 4.22 ms without these, 4.41 with)
-			switch (kSmallBodies ? d : 0) {  // variable degrees are 3..9 in all eight codes (padded: 4, 6, 8, 10)
-			case 4: acc = var_node_sum<4>(sbase, se, acc, d); break;
-			case 6: acc = var_node_sum<6>(sbase, se, acc, d); break;
-			case 8: acc = var_node_sum<8>(sbase, se, acc, d); break;
-			case 10: acc = var_node_sum<10>(sbase, se, acc, d); break;
-			default: acc = var_node_sum<0>(sbase, se, acc, d); break;
-			}
-			s_lam[v] = acc;
-		}
-		for (int v = vtail0 + tid; v < MB_N; v += kThreads) {
-			const uint32_t w = __ldg(g_vtail + (v - vtail0));
-			float acc = s_lch[v];
-			acc += lds_f(sbase, kOffR + (w & 0xFFFFu));
-			acc += lds_f(sbase, kOffR + (w >> 16));
-			s_lam[v] = acc;
-		}
-		__syncthreads();
-		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
-		if (n_unsat <= a.cheap_test_threads) {
-			unsigned bad = 0;
-			sched = s_csched + warp * MB_SCHED_LEN;
-			for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
-				const int d = (int)((desc >> 16) & 0xFFu);
-				const uint16_t *__restrict__ ve = g_edge_var + (desc & 0xFFFFu) + lane;
-				switch (kSmallBodies ? d : 0) {
-				case 2: bad |= check_parity<2>(sbase, ve, d); break;
-				case 3: bad |= check_parity<3>(sbase, ve, d); break;
-				case 4: bad |= check_parity<4>(sbase, ve, d); break;
-				case 5: bad |= check_parity<5>(sbase, ve, d); break;
-				case 6: bad |= check_parity<6>(sbase, ve, d); break;
-				case 7: bad |= check_parity<7>(sbase, ve, d); break;
-				case 8: bad |= check_parity<8>(sbase, ve, d); break;
-				case 9: bad |= check_parity<9>(sbase, ve, d); break;
-				default: bad |= check_parity<0>(sbase, ve, d); break;
-				}
-			}
-			if (__syncthreads_or((int)bad) == 0) {
-				iterations = pass + 1;  // exactly what the next check pass would have reported
-				break;
-			}
-		}
-	}
-
-	// ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record --------------------------
 	const uint16_t *__restrict__ g_bit_var = reinterpret_cast<const uint16_t *>(a.blob + m.off_bit_var);
 	const uint8_t *__restrict__ g_scr = a.blob + m.off_scr;
 	unsigned byte = 0;
@@ -416,19 +405,20 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 #pragma unroll
 		for (int b = 0; b < 8; b++) {
 			const int i = tid * 8 + b;
-			const unsigned bit = (__float_as_uint(s_lam[g_bit_var[i]]) >> 31) ^ (unsigned)g_scr[i];  // hard decision = sign bit (LLR < 0)
+			const unsigned bit = (fbits(s.lam(g_bit_var[i], X)) >> 31) ^ (unsigned)g_scr[i];  // hard decision = sign bit (LLR < 0)
 			byte |= bit << b;
 		}
-		s_bytes[tid] = (unsigned char)byte;
+		s.bytes[tid] = (unsigned char)byte;
 		if (tid < m.frame_bytes) a.payload[frame * (size_t)m.frame_bytes + tid] = (uint8_t)byte;
 	}
 	const int nonzero = __syncthreads_or((int)byte);
+	MbRxStats st;
 	if (tid < 32) {
 		const uint16_t *__restrict__ g_mat = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcmat);
 		uint16_t part = 0;
 		const int b0 = tid * m.crc_chunk;
 		for (int i = 0; i < m.crc_chunk; i++)
-			if (b0 + i < m.crc_bytes) part = crc_step_byte(part, s_bytes[b0 + i]);
+			if (b0 + i < m.crc_bytes) part = crc_step_byte(part, s.bytes[b0 + i]);
 		unsigned adv = 0;
 #pragma unroll
 		for (int b = 0; b < 16; b++)
@@ -436,6 +426,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) adv ^= __shfl_xor_sync(0xffffffffu, adv, o);
 		if (tid == 0) {
+			st = a.stats[frame];
 			const int all_zeros = nonzero ? 0 : 1;
 			const int crc = all_zeros ? 0 : (int)((adv ^ m.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
 			const int decoded = (!all_zeros && crc == 0) ? 1 : 0;               // telecom_system.cc:1343-1349
@@ -445,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			st.message_decoded = decoded;
 			st.SNR = decoded ? st.SNR : -99.9f;
 			if (m.estimator == 1 || !decoded) a.stats[frame] = st;
-			s_bytes[255] = (unsigned char)decoded;
+			s.bytes[255] = (unsigned char)decoded;
 		}
 	}
 	if (m.estimator == 1) return;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
@@ -454,36 +445,43 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 	// Re-encode the hard decisions (scrambled info bits, virtual copies, IRA parity), re-map them onto the constellation through
 	// the same composed interleaver records the demodulator scatters by, and measure the mean squared distance of the equalised
 	// data symbols (kept by the demodulator behind the LLRs of the hand-off record) to the re-encoded ones (ofdm.cc:1622-1635).
+	// Scratch: this slot's messages are dead: [0, P) data parity per check, [P, P + 1600) re-encoded bit per internal variable.
 	__syncthreads();
-	if (!s_bytes[255]) return;
-	uint32_t *s_bit = reinterpret_cast<uint32_t *>(smem_raw + kOffLch);          // [1600] re-encoded bit per internal variable (the channel LLRs are dead)
-	unsigned char *s_d = reinterpret_cast<unsigned char *>(smem_raw + kOffR);    // [P] data parity of every check, reference check order (the messages are dead)
+	if (!s.bytes[255]) return;
+	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);
 	const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + rt.off_var_of_cw);
 	const int K = m.K, P = rt.P, nReal = m.nReal, nVirtual = m.nVirtual;
-	for (int v = tid; v < MB_N; v += kThreads) s_bit[v] = 0u;  // parity variables stay 0 while the data parities are formed
+	auto bit_at = [&](int v) -> unsigned & { return reinterpret_cast<unsigned &>(s.R(P + v, X)); };  // P + 1600 <= edges <= c_slots in all eight codes
+	auto dpar_at = [&](int c) -> unsigned & { return reinterpret_cast<unsigned &>(s.R(c, X)); };
+	for (int v = tid; v < MB_N; v += kThreads) bit_at(v) = 0u;  // parity variables stay 0 while the data parities are formed
 	__syncthreads();
 	for (int i = tid; i < nReal; i += kThreads) {  // hd_decoded_data_bit, scrambled back = the decoder's hard decisions (:1378)
-		const unsigned b = __float_as_uint(s_lam[g_voc[i]]) >> 31;
-		s_bit[g_voc[i]] = b;
-		if (i < nVirtual) s_bit[g_voc[nReal + i]] = b;  // virtual bits are copies of the first ones (:1380-1383)
+		const unsigned b = fbits(s.lam(g_voc[i], X)) >> 31;
+		bit_at(g_voc[i]) = b;
+		if (i < nVirtual) bit_at(g_voc[nReal + i]) = b;  // virtual bits are copies of the first ones (:1380-1383)
 	}
 	__syncthreads();
 	{  // cl_ldpc::encode (ldpc.cc:111-132): every check row is {data bits, parity i-1, parity i}, so parity = running XOR of the data parities
-		const uint8_t *__restrict__ g_cdeg = a.blob + rt.off_cdeg;
-		const uint32_t *__restrict__ g_cgbase = reinterpret_cast<const uint32_t *>(a.blob + rt.off_cgbase);
 		const uint16_t *__restrict__ g_cos = reinterpret_cast<const uint16_t *>(a.blob + rt.off_check_of_sorted);
-		for (int c = tid; c < P; c += kThreads) {
-			const uint16_t *__restrict__ ve = g_edge_var + g_cgbase[c >> 5] + (c & 31);
+		const uint32_t *sched = s.csched + warp * MB_SCHED_LEN;
+		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check tasks, in the check pass's layout
+			const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc), per = 32 >> l2;
+			const uint16_t *__restrict__ ve = g_edge_var + MB_CDESC_BASE(desc) + lane;
 			unsigned x = 0;
-			for (int k = 0; k < (int)g_cdeg[c]; k++) x ^= s_bit[ve[k * 32] >> 2];
-			s_d[g_cos[c]] = (unsigned char)x;
+			for (int k = 0; k < dp; k++) {
+				const int v = (int)(ve[k * 32] >> 3);
+				if (v < MB_N) x ^= bit_at(v);  // padding edges name variable N
+			}
+			x = lanes_xor(x, l2);
+			const int c = (int)MB_CDESC_GROUP(desc) * 32 + (int)MB_CDESC_TASK(desc) * per + (lane & (per - 1));
+			if (lane < per && c < P) dpar_at(g_cos[c]) = x;
 		}
 	}
 	__syncthreads();
 	if (warp == 0) {
 		const int chunk = (P + 31) >> 5;
 		unsigned x = 0;
-		for (int i = lane * chunk; i < min(P, (lane + 1) * chunk); i++) x ^= s_d[i];
+		for (int i = lane * chunk; i < min(P, (lane + 1) * chunk); i++) x ^= dpar_at(i);
 		unsigned carry = x;  // inclusive XOR scan of the chunk parities over the lanes
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -492,8 +490,8 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 		}
 		unsigned run = carry ^ x;  // parity of everything before this lane's chunk
 		for (int i = lane * chunk; i < min(P, (lane + 1) * chunk); i++) {
-			run ^= s_d[i];
-			s_bit[g_voc[K + i]] = run;
+			run ^= dpar_at(i);
+			bit_at(g_voc[K + i]) = run;
 		}
 	}
 	__syncthreads();
@@ -508,14 +506,14 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 			for (int e = 0; e < bps; e++) {  // interleaver o psk.mod o interleaver (:1389-1391): bits MSB first
 				const uint32_t w = g_drec[d * rw + 1 + (e >> 1)];
 				const uint32_t off = (e & 1) ? (w >> 16) : (w & 0xFFFFu);
-				loc = (loc << 1) | s_bit[MB_HANDOFF_INV(off >> 2)];
+				loc = (loc << 1) | bit_at(MB_HANDOFF_INV(off >> 2));
 			}
 			const float2 c = g_cons[loc], z = zf[d];
 			acc += (c.x - z.x) * (c.x - z.x) + (c.y - z.y) * (c.y - z.y);
 		}
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-		float *s_acc = reinterpret_cast<float *>(smem_raw + kOffLam);  // the posteriors are dead now
+		float *s_acc = reinterpret_cast<float *>(s.bytes);  // the packed bytes are dead now
 		__syncthreads();
 		if (lane == 0) s_acc[warp] = acc;
 		__syncthreads();
@@ -528,34 +526,353 @@ __global__ void __launch_bounds__(kThreads, 5) mb_ldpc_kernel(const MbLdpcArgs a
 	}
 }
 
+// ---- next frame of the batch into slot X (uniform).  Returns its index, or -1 when the queue is empty (the slot then holds an
+// all-satisfied dummy and is ignored).  Frames the demodulator gated out (mean|H| < 0.3) get their record here and are skipped.
+// The queue is read one grab ahead (thread 0 holds the ticket of the NEXT refill in shared memory, so the atomic's latency is never
+// waited for), and every grab prefetches into L2 the LLRs of the frame that will be handed out one "wave" of resident slots later
+// (frames are handed out in order), so a refill reads L2, not DRAM, while the pair's other slot waits.
+__device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int X)
+{
+	const MbMode &m = a.mode;
+	const int tid = threadIdx.x, CS = a.rate.c_slots;
+	int frame;
+	for (;;) {
+		// The ticket was published before a barrier every thread has passed (the end of the previous refill / the kernel prologue); the
+		// other word takes the ticket of the refill after this one, fetched by a thread of warp 1 (warp 0 may still be in the epilogue's
+		// CRC) and published by the barrier at the end of this refill.  No barrier here: the loads below overlap the epilogue's tail.
+		const int turn = *s.turn;
+		const unsigned f = (unsigned)s.next[turn];
+		*s.turn = turn ^ 1;
+		if (tid == 32) s.next[turn ^ 1] = (int)atomicAdd(a.queue, 1u);
+		if ((unsigned long long)f >= a.n_frames) {
+			frame = -1;
+			break;
+		}
+		frame = (int)f;
+		{
+			const unsigned long long ahead = (unsigned long long)f + 2ull * gridDim.x;
+			if (ahead < a.n_frames && tid < (MB_N * 4 + 127) / 128)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.llr + ahead * MB_HANDOFF_STRIDE) + tid * 128));
+		}
+		if (a.check_gate && !(a.stats[f].mean_H >= 0.3f)) {
+			// telecom_system.cc:1268-1280: a channel estimate this weak means a false sync; the reference skips the decode
+			for (int i = tid; i < m.frame_bytes; i += kThreads) a.payload[f * (size_t)m.frame_bytes + i] = 0;
+			if (tid == 0) {
+				MbRxStats st = a.stats[f];
+				st.iterations_done = -1;
+				st.crc = 0;
+				st.all_zeros = 0;
+				st.message_decoded = 0;
+				st.SNR = -99.9f;
+				a.stats[f] = st;
+			}
+			__syncthreads();  // the next ticket is visible
+			continue;
+		}
+		break;
+	}
+	if (frame >= 0) {
+		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores.
+		// Base-2 units from here on; "+ 0" turns an LLR of -0 into +0 (hard decision 0 like the reference's `< 0` test).
+		const float *__restrict__ src = a.llr + (size_t)frame * MB_HANDOFF_STRIDE;
+		constexpr int kPer = (MB_N + kThreads - 1) / kThreads;
+		float v[kPer];
+#pragma unroll
+		for (int j = 0; j < kPer; j++) {
+			const int i = tid + j * kThreads;
+			v[j] = i < MB_N ? ldg_stream(src + i) : 0.f;  // all loads in flight together; no L1 allocation (the index tables live there)
+		}
+#pragma unroll
+		for (int j = 0; j < kPer; j++) {
+			const int i = tid + j * kThreads;
+			if (i < MB_N) {
+				const float w = fmaf(v[j], kLog2e, 0.0f);
+				const unsigned p = MB_HANDOFF_INV((unsigned)i);
+				s.lam((int)p, X) = w;
+				s.set_lch((int)p, X, w);
+			}
+		}
+	} else {
+		for (int i = tid; i < MB_N; i += kThreads) s.lam(i, X) = 1.0f, s.set_lch(i, X, 1.0f);
+	}
+	for (int i = tid; i <= CS; i += kThreads) s.R(i, X) = 0.f;
+	__syncthreads();
+	return frame;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const MbRate &rt = a.rate;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int CS = rt.c_slots;
+	Smem s;
+	s.raw = smem_raw;
+	s.sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+	uint32_t *s_csched = reinterpret_cast<uint32_t *>(smem_raw + kOffR + r_bytes(CS));  // [8][16] check-group descriptors per warp
+	uint32_t *s_vsched = s_csched + MB_LDPC_WARPS * MB_SCHED_LEN;                       // [8][16] variable-group descriptors per warp
+	s.bytes = reinterpret_cast<unsigned char *>(s_vsched + MB_LDPC_WARPS * MB_SCHED_LEN);
+	s.cnt = reinterpret_cast<unsigned *>(s.bytes + 256);
+	s.next = reinterpret_cast<volatile int *>(s.cnt + 2 * MB_LDPC_WARPS);
+	s.csched = s_csched;
+	s.lch_g = a.lch_scratch + (size_t)blockIdx.x * (2 * MB_N);
+	const unsigned sbase = s.sbase;
+
+	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);  // byte offsets into the posteriors
+	const uint16_t *__restrict__ g_vedge = reinterpret_cast<const uint16_t *>(a.blob + rt.off_vedgeb);        // byte offsets into the messages
+	const uint32_t *__restrict__ g_vtail = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vtail);          // two byte offsets per degree-<=2 variable
+
+	if (tid < MB_LDPC_WARPS * MB_SCHED_LEN) {
+		s_csched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_csched)[tid];
+		s_vsched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vsched)[tid];
+	}
+	if (tid == 0) {
+		s.lam(MB_N, 0) = __int_as_float(0x7f800000);  // +inf: a padding edge contributes e = 0, sign +, hard bit 0
+		s.lam(MB_N, 1) = __int_as_float(0x7f800000);
+	}
+	int turn_reg = 0;
+	s.turn = &turn_reg;
+	if (tid == 32) s.next[0] = (int)atomicAdd(a.queue, 1u);
+	__syncthreads();
+	int frame[2];
+	int pass[2] = {0, 0};  // check passes this slot's frame has been through = iterations completed
+	frame[0] = refill_slot(a, s, 0);
+	frame[1] = refill_slot(a, s, 1);
+
+	const int vtail0 = rt.vtail_start;
+	while (frame[0] >= 0 || frame[1] >= 0) {
+		// ---- check pass: syndrome of the current posteriors + new check->variable messages, both slots ----------------
+		// A warp owns a group of 32 checks padded to one degree; padding slots point at the +inf variable, so the loops are
+		// warp-uniform (no per-thread degree, no divergence) and a padding edge is the neutral element of every reduction.
+		unsigned hard_a = 0, hard_b = 0;
+		const uint32_t *sched = s_csched + warp * MB_SCHED_LEN;
+		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check tasks (static, cost-balanced schedule)
+			const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc);
+			const unsigned e0 = MB_CDESC_BASE(desc) + (unsigned)lane;
+			const unsigned raddr = sbase + kOffR + e0 * 8u;
+			const uint16_t *__restrict__ ve = g_edge_var + e0;
+			unsigned ha = 0, hb = 0;
+			if (ALGO == 0) {
+#define MB_FIX_CASE(D_) \
+	case D_:         \
+		spa_check_pair<D_>(sbase, ve, raddr, l2, ha, hb); \
+		break;
+				switch (dp + (l2 != 0 ? 1 : 0)) {  // a split task runs the body of one more edge: the other lanes' total (see spa_check_pair)
+				case 2: spa_check_pair_2(sbase, ve, raddr, ha, hb); break;
+				MB_FIX_CASE(3)
+				MB_FIX_CASE(4)
+				MB_FIX_CASE(5)
+				MB_FIX_CASE(6)
+				MB_FIX_CASE(7)
+				MB_FIX_CASE(8)
+				default: break;
+				}
+#undef MB_FIX_CASE
+				static_assert(MB_LDPC_DMAX == 7, "check-node bodies are instantiated for 3..MB_LDPC_DMAX + 1 edges");
+			} else {
+				const int per = 32 >> l2;
+				const int c = (int)MB_CDESC_GROUP(desc) * 32 + (int)MB_CDESC_TASK(desc) * per + (lane & (per - 1));
+				const int dc = c < rt.P ? (int)(a.blob + rt.off_cdeg)[c] : 0;  // the true degree picks the normalisation
+				minsum_check_pair(sbase, ve, raddr, dp, l2, dc, ha, hb);
+			}
+			hard_a |= ha & 0x80000000u;
+			hard_b |= hb & 0x80000000u;
+		}
+		// The channel LLRs of this thread's tail variables for the variable pass below: issued before the barrier, so that their L2 latency
+		// is spent waiting for the other warps (they are read-only; a slot refilled in between re-reads them).
+		constexpr int kTailRegs = 6;  // the tail is at most 1600 - 128 variables (rate 1/16)
+		f2 lt[kTailRegs];
+#pragma unroll
+		for (int i = 0; i < kTailRegs; i++) {
+			const int v = vtail0 + tid + i * kThreads;
+			lt[i] = v < MB_N ? s.get_lch(v) : make_float2(0.f, 0.f);
+		}
+		// threads that saw an unsatisfied check, per slot: 0 = converged; a small count = "probably one iteration to go"
+		{
+			const unsigned ba = __ballot_sync(0xffffffffu, hard_a != 0u), bb = __ballot_sync(0xffffffffu, hard_b != 0u);
+			if (lane == 0) s.cnt[warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
+		}
+		__syncthreads();
+		unsigned tot = 0;
+#pragma unroll
+		for (int w = 0; w < MB_LDPC_WARPS; w++) tot += s.cnt[w];
+		int n_unsat[2] = {(int)(tot & 0xFFFFu), (int)(tot >> 16)};
+		bool fresh[2] = {false, false};
+#pragma unroll
+		for (int X = 0; X < 2; X++) {
+			if (frame[X] < 0) continue;
+			int iterations = -1;
+			if (n_unsat[X] == 0)
+				iterations = pass[X];  // converged after pass[X] iterations (0 = clean on arrival, ldpc_decoder_SPA.cc:62-77)
+			else if (pass[X] == a.max_iters)
+				iterations = a.max_iters + 1;  // ldpc_decoder_SPA.cc:127,217: loop ran out
+			if (iterations >= 0) {
+				finish_slot(a, s, X, (size_t)frame[X], iterations);
+				frame[X] = refill_slot(a, s, X);
+				pass[X] = 0;
+				fresh[X] = true;
+			} else {
+				pass[X]++;
+			}
+		}
+		if (frame[0] < 0 && frame[1] < 0) break;
+		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order), both slots ----------
+		// Variables are numbered by descending degree.  The head (degree > 2) is walked in warp groups padded to one even
+		// degree (padding reads the always-zero slot); the long tail of degree-<=2 variables (the accumulator chain of the IRA
+		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.  A slot refilled above has
+		// all-zero messages: its posterior is rewritten with the channel LLR, and the next check pass is its pass 0.
+		if (fresh[0] || fresh[1]) {
+#pragma unroll
+			for (int i = 0; i < kTailRegs; i++) {
+				const int v = vtail0 + tid + i * kThreads;
+				lt[i] = v < MB_N ? s.get_lch(v) : make_float2(0.f, 0.f);
+			}
+		}
+		sched = s_vsched + warp * MB_SCHED_LEN;
+		uint32_t desc = *sched;
+		f2 lh = desc != 0u ? s.get_lch((int)((desc >> 24) - 1u) * 32 + lane) : make_float2(0.f, 0.f);  // first head group: in flight during the tail
+#pragma unroll
+		for (int i = 0; i < kTailRegs; i++) {
+			const int v = vtail0 + tid + i * kThreads;
+			if (v < MB_N) {
+				const uint32_t w = __ldg(g_vtail + (v - vtail0));
+				f2 acc = __fadd2_rn(lt[i], lds2(sbase + kOffR + (w & 0xFFFFu)));
+				acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w >> 16)));
+				sts2(sbase + kOffLam + v * 8, acc);
+			}
+		}
+		for (int v = vtail0 + tid + kTailRegs * kThreads; v < MB_N; v += kThreads) {  // (not reached with the eight codes of the reference)
+			const uint32_t w = __ldg(g_vtail + (v - vtail0));
+			f2 acc = s.get_lch(v);
+			acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w & 0xFFFFu)));
+			acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w >> 16)));
+			sts2(sbase + kOffLam + v * 8, acc);
+		}
+		while (desc != 0u) {
+			const int d = (int)((desc >> 16) & 0xFFu);
+			const int v = (int)((desc >> 24) - 1u) * 32 + lane;
+			const uint16_t *__restrict__ se = g_vedge + ((desc & 0xFFFFu) + lane);
+			const uint32_t nd = *++sched;
+			f2 acc = lh;
+			if (nd != 0u) lh = s.get_lch((int)((nd >> 24) - 1u) * 32 + lane);  // the next group's, one ahead
+			switch (d) {  // variable degrees are 3..9 in all eight codes (padded: 4, 6, 8, 10)
+			case 4: acc = var_node_sum<4>(sbase, se, acc, d); break;
+			case 6: acc = var_node_sum<6>(sbase, se, acc, d); break;
+			case 8: acc = var_node_sum<8>(sbase, se, acc, d); break;
+			default: acc = var_node_sum<0>(sbase, se, acc, d); break;
+			}
+			sts2(sbase + kOffLam + v * 8, acc);
+			desc = nd;
+		}
+		__syncthreads();
+		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
+		const bool try_a = frame[0] >= 0 && !fresh[0] && n_unsat[0] <= a.cheap_test_threads;
+		const bool try_b = frame[1] >= 0 && !fresh[1] && n_unsat[1] <= a.cheap_test_threads;
+		if (try_a || try_b) {
+			unsigned bad_a = 0, bad_b = 0;
+			sched = s_csched + warp * MB_SCHED_LEN;
+			for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
+				const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc);
+				const uint16_t *__restrict__ ve = g_edge_var + MB_CDESC_BASE(desc) + lane;
+				switch (dp) {
+				case 2: check_parity<2>(sbase, ve, l2, bad_a, bad_b); break;
+				case 3: check_parity<3>(sbase, ve, l2, bad_a, bad_b); break;
+				case 4: check_parity<4>(sbase, ve, l2, bad_a, bad_b); break;
+				case 5: check_parity<5>(sbase, ve, l2, bad_a, bad_b); break;
+				case 6: check_parity<6>(sbase, ve, l2, bad_a, bad_b); break;
+				case 7: check_parity<7>(sbase, ve, l2, bad_a, bad_b); break;
+				default: break;
+				}
+			}
+			const unsigned ba = __ballot_sync(0xffffffffu, bad_a != 0u), bb = __ballot_sync(0xffffffffu, bad_b != 0u);
+			if (lane == 0) s.cnt[MB_LDPC_WARPS + warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
+			__syncthreads();
+			unsigned t2 = 0;
+#pragma unroll
+			for (int w = 0; w < MB_LDPC_WARPS; w++) t2 += s.cnt[MB_LDPC_WARPS + w];
+			const bool done_a = try_a && (t2 & 0xFFFFu) == 0u, done_b = try_b && (t2 >> 16) == 0u;
+			if (done_a) {  // exactly what the next check pass would have reported
+				finish_slot(a, s, 0, (size_t)frame[0], pass[0]);
+				frame[0] = refill_slot(a, s, 0);
+				pass[0] = 0;
+			}
+			if (done_b) {
+				finish_slot(a, s, 1, (size_t)frame[1], pass[1]);
+				frame[1] = refill_slot(a, s, 1);
+				pass[1] = 0;
+			}
+		}
+	}
+	// the last CTA out re-arms the queue for the next launch on this stream
+	__syncthreads();
+	if (tid == 0) {
+		__threadfence();
+		if (atomicAdd(a.queue + 1, 1u) == gridDim.x - 1) {
+			a.queue[0] = 0u;
+			a.queue[1] = 0u;
+			__threadfence();
+		}
+	}
+}
+
 }  // namespace
 
 size_t mb_ldpc_smem_bytes(int c_slots)
 {
-	return (size_t)kOffR + (size_t)((c_slots + 4) & ~3) * sizeof(float) + 2 * MB_LDPC_WARPS * MB_SCHED_LEN * sizeof(uint32_t) + 256;
+	return (size_t)kOffR + (size_t)r_bytes(c_slots) + 2 * MB_LDPC_WARPS * MB_SCHED_LEN * sizeof(uint32_t) + kMiscBytes;
 }
 
 namespace {
 typedef void (*LdpcKernel)(const MbLdpcArgs);
-// [algo][set]: sum-product / min-sum, each with the degree sets {3..5}, {3..7}, {5..9}
-const LdpcKernel kKernels[6] = {mb_ldpc_kernel<0, 3, 5>, mb_ldpc_kernel<0, 3, 7>, mb_ldpc_kernel<0, 5, 9>,
-				mb_ldpc_kernel<1, 3, 5>, mb_ldpc_kernel<1, 3, 7>, mb_ldpc_kernel<1, 5, 9>};
+const LdpcKernel kKernels[2] = {mb_ldpc_kernel<0>, mb_ldpc_kernel<1>};  // sum-product / min-sum
+int g_ctas_per_sm[2][MB_NRATES] = {};
+int g_sms = 0;
 }  // namespace
 
 cudaError_t mb_ldpc_init()
 {
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+	if (e != cudaSuccess) return e;
 	for (LdpcKernel k : kKernels) {
-		cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+		e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+		if (e != cudaSuccess) return e;
+		int carve = MB_LDPC_LCH_SMEM ? (int)cudaSharedmemCarveoutMaxShared : 77;  // 196 KB of the 256 KB array: three pairs of up to 64 KB + 60 KB of L1
+		if (const char *v = getenv("MERCURY_B200_LDPC_CARVEOUT")) carve = atoi(v);  // tuning: percent of the unified L1/shared array given to shared memory
+		e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
 		if (e != cudaSuccess) return e;
 	}
 	return cudaSuccess;
 }
 
+size_t mb_ldpc_max_ctas() { return (size_t)g_sms * 4; }
+
+int mb_ldpc_ctas_per_sm(int algo, int rate_idx, int rate_num, int c_slots)
+{
+	const int ki = algo != 0 ? 1 : 0;
+	(void)rate_num;
+	if (g_ctas_per_sm[ki][rate_idx] == 0) {
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernels[ki], kThreads, mb_ldpc_smem_bytes(c_slots)) != cudaSuccess || n < 1) n = 1;
+		g_ctas_per_sm[ki][rate_idx] = n;
+	}
+	return g_ctas_per_sm[ki][rate_idx];
+}
+
 cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaStream_t stream)
 {
 	if (n_frames == 0) return cudaSuccess;
+	if (!a.queue || !a.lch_scratch || n_frames > 0x7fff0000ull) return cudaErrorInvalidValue;  // frame tickets are 31-bit
 	const size_t smem = mb_ldpc_smem_bytes(a.rate.c_slots);
-	const LdpcKernel k = kKernels[(algo != 0 ? 3 : 0) + mb_ldpc_degree_set(a.rate.rate_num, nullptr, nullptr)];
-	k<<<(unsigned)n_frames, kThreads, smem, stream>>>(a);
+	const LdpcKernel k = kKernels[algo != 0 ? 1 : 0];
+	const int rate_idx = mb_rate_index(a.rate.rate_num);
+	const size_t resident = (size_t)g_sms * (size_t)mb_ldpc_ctas_per_sm(algo, rate_idx < 0 ? 0 : rate_idx, a.rate.rate_num, a.rate.c_slots);
+	MbLdpcArgs b = a;
+	b.n_frames = n_frames;
+	const size_t grid = std::min(std::min(resident, mb_ldpc_max_ctas()), (n_frames + 1) / 2);
+	k<<<(unsigned)grid, kThreads, smem, stream>>>(b);
 	return cudaGetLastError();
 }

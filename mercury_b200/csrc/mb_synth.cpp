@@ -146,7 +146,7 @@ std::string mb_synth_frames(const std::vector<uint8_t> &blob, int config, size_t
 		const uint16_t *cos_ = (const uint16_t *)(b + T.r.off_check_of_sorted);
 		T.check_rows.resize(T.r.P);
 		for (int cs = 0; cs < T.r.P; cs++)
-			for (int k = 0; k < cdeg[cs]; k++) T.check_rows[cos_[cs]].push_back(T.cw_of_var[ev[cgbase[cs >> 5] + 32 * k + (cs & 31)]]);
+			for (int k = 0; k < cdeg[cs]; k++) T.check_rows[cos_[cs]].push_back(T.cw_of_var[ev[mb_ldpc_cslot(cgbase, cdeg[cs & ~31], cs, k)]]);
 	}
 	T.tw.resize(128);
 	for (int k = 0; k < 128; k++) T.tw[k] = std::polar(1.0, 2.0 * M_PI * k / 256.0);

@@ -233,16 +233,18 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	// warp-blocked ELL: groups of 32 sorted checks / variables, each padded to the degree of its first member
 	std::vector<uint32_t> cgbase(MB_MAX_GROUPS, 0), vgbase(MB_MAX_GROUPS, 0);
 	uint32_t c_slots = 0, v_slots = 0;
-	for (int g = 0; g * 32 < P; g++) {
+	for (int g = 0; g * 32 < P; g++) {  // S tasks of Dp steps each (mb_ldpc_split): 32 * S * Dp >= 32 * d slots
+		int S, Dp;
+		mb_ldpc_split((int)t.crow[csorted[g * 32]].size(), &S, &Dp);
 		cgbase[g] = c_slots;
-		c_slots += 32u * (uint32_t)t.crow[csorted[g * 32]].size();
+		c_slots += 32u * (uint32_t)(S * Dp);
 	}
 	for (int g = 0; g * 32 < N; g++) {  // variable groups are padded to an EVEN degree: the kernel's loop takes two edges per trip
 		vgbase[g] = v_slots;
 		v_slots += 32u * (uint32_t)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1);
 	}
 	if (c_slots >= 0xFFFFu || v_slots >= 0xFFFFu) return "LDPC slot count exceeds 16-bit slot ids";
-	auto cslot = [&](int k, int cs) { return cgbase[cs >> 5] + 32u * (uint32_t)k + (uint32_t)(cs & 31); };
+	auto cslot = [&](int k, int cs) { return mb_ldpc_cslot(cgbase.data(), (int)t.crow[csorted[cs & ~31]].size(), cs, k); };
 	auto vslot = [&](int k, int vs) { return vgbase[vs >> 5] + 32u * (uint32_t)k + (uint32_t)(vs & 31); };
 
 	std::vector<uint8_t> cdeg(P), vdeg(N);
@@ -287,9 +289,9 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 	out.off_vedge = bl.put(vedge);
 	{
 		std::vector<uint16_t> evb(c_slots, 0), veb(v_slots, 0);
-		for (uint32_t i = 0; i < c_slots; i++) evb[i] = (uint16_t)((edge_var[i] == 0xFFFF ? (uint32_t)N : (uint32_t)edge_var[i]) * 4);
-		for (uint32_t i = 0; i < v_slots; i++) veb[i] = (uint16_t)(vedge[i] * 4);
-		if (c_slots * 4 > 0xFFFFu) return "LDPC slot byte offsets exceed 16 bits";
+		for (uint32_t i = 0; i < c_slots; i++) evb[i] = (uint16_t)((edge_var[i] == 0xFFFF ? (uint32_t)N : (uint32_t)edge_var[i]) * 8);
+		for (uint32_t i = 0; i < v_slots; i++) veb[i] = (uint16_t)(vedge[i] * 8);
+		if (c_slots * 8 > 0xFFFFu) return "LDPC slot byte offsets exceed 16 bits";
 		out.off_edge_varb = bl.put(evb);
 		out.off_vedgeb = bl.put(veb);
 		// tail of degree-<=2 variables (sorted by descending degree, so it is a suffix), from a multiple of 32
@@ -299,40 +301,49 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 		out.vtail_start = tail;
 		std::vector<uint32_t> vtail((size_t)(N - tail), 0);
 		for (int i = tail; i < N; i++) {
-			uint32_t o[2] = {c_slots * 4u, c_slots * 4u};
-			for (size_t k = 0; k < t.vrow[vsorted[i]].size(); k++) o[k] = (uint32_t)vedge[vslot((int)k, i)] * 4u;
+			uint32_t o[2] = {c_slots * 8u, c_slots * 8u};
+			for (size_t k = 0; k < t.vrow[vsorted[i]].size(); k++) o[k] = (uint32_t)vedge[vslot((int)k, i)] * 8u;
 			vtail[(size_t)(i - tail)] = o[0] | (o[1] << 16);
 		}
 		out.off_vtail = bl.put(vtail);
-		// longest-processing-time-first assignment of groups to warps; weight = padded degree of the group (what the kernel loops over),
-		// cost = what balances the warps: warp instructions of the group in the kernel that will run it (mb_ldpc.cu, ncu source page:
-		// ~45 per edge in a fully unrolled body, ~52 in the generic loop, a degree-2 check is a pass-through; ~3 per edge on the variable side)
-		auto schedule = [&](int n_groups, auto weight, auto cost, auto base, uint32_t &off) -> bool {
-			std::vector<int> order(n_groups);
-			std::iota(order.begin(), order.end(), 0);
-			std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+		// longest-processing-time-first assignment of tasks to warps; cost = what balances the warps: warp instructions of the task in
+		// the kernel (mb_ldpc.cu: ~25 per edge of a pair of frames in an unrolled body, ~12 more per edge and ~40 per task when the
+		// check is split over lanes, a degree-2 check is a pass-through; ~3 per edge on the variable side)
+		auto lpt = [&](std::vector<std::pair<int, uint32_t>> items, uint32_t &off) -> bool {  // (cost, descriptor)
+			std::stable_sort(items.begin(), items.end(), [](const std::pair<int, uint32_t> &a, const std::pair<int, uint32_t> &b) { return a.first > b.first; });
 			std::vector<uint32_t> sched(MB_LDPC_WARPS * MB_SCHED_LEN, 0u);
 			int load[MB_LDPC_WARPS] = {0}, cnt[MB_LDPC_WARPS] = {0};
-			for (int g : order) {
+			for (const auto &it : items) {
 				int w = 0;
 				for (int i = 1; i < MB_LDPC_WARPS; i++)
 					if (load[i] < load[w]) w = i;
-				if (cnt[w] >= MB_SCHED_LEN - 1 || base(g) > 0xFFFFu || weight(g) > 255) return false;
-				sched[w * MB_SCHED_LEN + cnt[w]++] = base(g) | ((uint32_t)weight(g) << 16) | ((uint32_t)(g + 1) << 24);
-				load[w] += cost(weight(g));
+				if (cnt[w] >= MB_SCHED_LEN - 1) return false;
+				sched[w * MB_SCHED_LEN + cnt[w]++] = it.second;
+				load[w] += it.first;
 			}
 			off = bl.put(sched);
 			return true;
 		};
-		int fix_lo, fix_hi;
-		mb_ldpc_degree_set(t.rate_num, &fix_lo, &fix_hi);
-		auto check_cost = [&](int d) { return d <= 2 ? 30 : (d >= fix_lo && d <= fix_hi ? 45 * d + 20 : 52 * d + 40); };
-		auto var_cost = [&](int d) { return 3 * d + 8; };
-		if (!schedule((P + 31) / 32, [&](int g) { return (int)t.crow[csorted[g * 32]].size(); }, check_cost, [&](int g) { return cgbase[g]; }, out.off_csched))
-			return "check schedule overflow";
-		if (!schedule(tail / 32, [&](int g) { return (int)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1); }, var_cost, [&](int g) { return vgbase[g]; },
-			      out.off_vsched))
-			return "variable schedule overflow";
+		std::vector<std::pair<int, uint32_t>> ctasks, vtasks;
+		for (int g = 0; g * 32 < P; g++) {
+			int S, Dp, l2 = 0;
+			mb_ldpc_split((int)t.crow[csorted[g * 32]].size(), &S, &Dp);
+			while ((1 << l2) < S) l2++;
+			for (int tk = 0; tk < S; tk++) {
+				if (g * 32 + tk * (32 / S) >= P) break;  // no check left for this task (last group)
+				const uint32_t base = cgbase[g] + (uint32_t)(tk * Dp * 32);
+				if (base > 0xFFFFu || Dp > 15 || g + 1 > 127) return "check schedule overflow";
+				const int cost = Dp <= 2 && S == 1 ? 26 : (S == 1 ? 25 * Dp + 15 : 37 * Dp + 55);
+				ctasks.emplace_back(cost, base | ((uint32_t)Dp << 16) | ((uint32_t)l2 << 20) | ((uint32_t)tk << 22) | ((uint32_t)(g + 1) << 25));
+			}
+		}
+		for (int g = 0; g < tail / 32; g++) {
+			const int d = (int)((t.vrow[vsorted[g * 32]].size() + 1) & ~(size_t)1);
+			if (vgbase[g] > 0xFFFFu || d > 255) return "variable schedule overflow";
+			vtasks.emplace_back(3 * d + 8, vgbase[g] | ((uint32_t)d << 16) | ((uint32_t)(g + 1) << 24));
+		}
+		if (!lpt(ctasks, out.off_csched)) return "check schedule overflow";
+		if (!lpt(vtasks, out.off_vsched)) return "variable schedule overflow";
 	}
 	out.off_var_of_cw = bl.put(var_of_cw);
 	out.off_check_of_sorted = bl.put(check_of_sorted);
@@ -646,8 +657,42 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		if (t.c_slots < t.n_edges || t.c_slots > 12288 || t.v_slots < t.n_edges || t.v_slots > 12288) return "table blob: bad slot counts";
 		if (!in(t.off_cdeg, t.P) || !in(t.off_cgbase, 4 * MB_MAX_GROUPS) || !in(t.off_edge_var, 2 * (size_t)t.c_slots) ||
 		    !in(t.off_vdeg, t.N) || !in(t.off_vgbase, 4 * MB_MAX_GROUPS) || !in(t.off_vgdeg, MB_MAX_GROUPS) || !in(t.off_vedge, 2 * (size_t)t.v_slots) ||
-		    !in(t.off_var_of_cw, 2 * (size_t)t.N))
+		    !in(t.off_var_of_cw, 2 * (size_t)t.N) || !in(t.off_check_of_sorted, 2 * (size_t)t.P) || !in(t.off_edge_varb, 2 * (size_t)t.c_slots) ||
+		    !in(t.off_vedgeb, 2 * (size_t)t.v_slots) || !in(t.off_csched, 4 * MB_LDPC_WARPS * MB_SCHED_LEN) || !in(t.off_vsched, 4 * MB_LDPC_WARPS * MB_SCHED_LEN) ||
+		    t.vtail_start < 0 || t.vtail_start > t.N || (t.vtail_start & 31) != 0 || !in(t.off_vtail, 4 * (size_t)(t.N - t.vtail_start)))
 			return "table blob: rate table out of range";
+		// contents the decoder kernel uses as shared-memory byte offsets / loop bounds without further checks
+		if ((size_t)t.c_slots * 8 > 0xFFFFu) return "table blob: slot count exceeds the 16-bit byte offsets";
+		{
+			const uint16_t *evb = reinterpret_cast<const uint16_t *>(blob + t.off_edge_varb), *veb = reinterpret_cast<const uint16_t *>(blob + t.off_vedgeb);
+			for (int i = 0; i < t.c_slots; i++)
+				if (evb[i] > 8 * MB_N || (evb[i] & 7)) return "table blob: posterior offset out of range";
+			for (int i = 0; i < t.v_slots; i++)
+				if (veb[i] > 8 * t.c_slots || (veb[i] & 7)) return "table blob: message offset out of range";
+			const uint32_t *vt = reinterpret_cast<const uint32_t *>(blob + t.off_vtail);
+			for (int i = 0; i < t.N - t.vtail_start; i++)
+				if ((vt[i] & 0xFFFFu) > 8u * (uint32_t)t.c_slots || (vt[i] >> 16) > 8u * (uint32_t)t.c_slots || (vt[i] & 0x00070007u)) return "table blob: tail offset out of range";
+			const uint32_t *cs = reinterpret_cast<const uint32_t *>(blob + t.off_csched), *vs = reinterpret_cast<const uint32_t *>(blob + t.off_vsched);
+			for (int w = 0; w < MB_LDPC_WARPS; w++) {
+				if (cs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1] != 0u || vs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1] != 0u) return "table blob: schedule not terminated";
+				for (int i = 0; i < MB_SCHED_LEN; i++) {
+					const uint32_t c = cs[w * MB_SCHED_LEN + i], v = vs[w * MB_SCHED_LEN + i];
+					if (c != 0u && ((c >> 25) == 0u || MB_CDESC_BASE(c) + 32u * MB_CDESC_DP(c) > (uint32_t)t.c_slots || MB_CDESC_DP(c) < 2u || MB_CDESC_DP(c) > MB_LDPC_DMAX ||
+							MB_CDESC_TASK(c) >= (1u << MB_CDESC_LOG2S(c)) || MB_CDESC_GROUP(c) * 32u >= (uint32_t)t.P))
+						return "table blob: check schedule out of range";
+					if (v != 0u && ((v >> 24) == 0u || (v & 0xFFFFu) + 32u * ((v >> 16) & 0xFFu) > (uint32_t)t.v_slots || ((v >> 24) - 1u) * 32u + 32u > (uint32_t)t.N))
+						return "table blob: variable schedule out of range";
+				}
+			}
+			const uint8_t *cdeg = blob + t.off_cdeg;
+			const uint32_t *cgb = reinterpret_cast<const uint32_t *>(blob + t.off_cgbase);
+			const uint16_t *cos = reinterpret_cast<const uint16_t *>(blob + t.off_check_of_sorted), *voc = reinterpret_cast<const uint16_t *>(blob + t.off_var_of_cw);
+			for (int c = 0; c < t.P; c++)
+				if (cdeg[c] > MB_MAX_CDEG || cdeg[c] > cdeg[c & ~31] || mb_ldpc_cslot(cgb, cdeg[c & ~31], c | 31, cdeg[c & ~31] - 1) >= (uint32_t)t.c_slots || cos[c] >= t.P)
+					return "table blob: check table out of range";
+			for (int v = 0; v < t.N; v++)
+				if (voc[v] >= t.N) return "table blob: variable map out of range";
+		}
 	}
 	for (int c = 0; c < MB_NMODES; c++) {
 		const MbMode &m = h.modes[c];

@@ -29,13 +29,18 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 12u
+#define MB_BLOB_VERSION 13u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
 #define MB_MAX_GROUPS 64  // warp-sized groups of checks / variables (<= 50 used)
-#define MB_LDPC_WARPS 8   // warps per decoder CTA (the group schedules below are built for this many)
-#define MB_SCHED_LEN 16   // groups per warp in a schedule, 0xFF terminated
+#ifndef MB_LDPC_WARPS
+#define MB_LDPC_WARPS 8   // warps per decoder CTA (the task schedules below are built for this many)
+#endif
+#ifndef MB_LDPC_MIN_CTAS
+#define MB_LDPC_MIN_CTAS 3  // resident decoder CTAs per SM the kernel's register budget is set for
+#endif
+#define MB_SCHED_LEN 16   // tasks per warp in a schedule, 0 terminated
 #define MB_ZF_STRIDE 27   // compact pilot row: 4 zeros | <= 17 pilots (columns s%3 + 3j at [4 + j]) | zeros
 #define MB_LS_COLS 18     // distinct clipped 21-column windows per row: start index (c + 4 - s%3) / 3 = 0..17
 // LLR hand-off layout between the two kernels: internal variable v sits at MB_HANDOFF(v): every 32-float row is rotated by
@@ -50,9 +55,10 @@ struct MbRate {
 	int32_t max_cdeg, max_vdeg;
 	int32_t c_slots, v_slots;  // padded slot counts of the two warp-blocked ELL layouts below
 	int32_t reserved;
-	// Check side. Checks are sorted by degree (descending) and cut into groups of 32 (one warp); group g is padded to
-	// the degree of its first (= largest) check: slot(k, c') = cgbase[c' >> 5] + 32 k + (c' & 31).  A warp that owns a
-	// group therefore walks its edges with a constant +32 stride and touches 32 consecutive words per step.
+	// Check side. Checks are sorted by degree (descending) and cut into groups of 32; group g is padded to the degree of its
+	// first (= largest) check and laid out as S warp tasks (mb_ldpc_split / mb_ldpc_cslot below; S = 1: one lane per check,
+	// slot(k, c') = cgbase[c' >> 5] + 32 k + (c' & 31)).  A warp that owns a task walks its edges with a constant +32 stride and
+	// touches 32 consecutive words per step.
 	uint32_t off_cdeg;      // u8 [P]             degree of sorted check c'
 	uint32_t off_cgbase;    // u32[MB_MAX_GROUPS] first slot of each group of 32 checks
 	uint32_t off_edge_var;  // u16[c_slots]       internal variable index of each check-side slot (0xFFFF = padding)
@@ -66,10 +72,10 @@ struct MbRate {
 	// The decoder kernel's own tables: BYTE offsets into its shared-memory arrays (no index scaling per edge), padding that is
 	// the neutral element of every reduction (so the loops need no per-thread degree), and static schedules that balance the
 	// padded degrees of the groups over the CTA's warps (longest-processing-time first), so no warp idles at the barriers.
-	uint32_t off_edge_varb; // u16[c_slots]  4 * internal variable index of each check-side slot (padding: 4 * N, the +inf variable)
-	uint32_t off_vedgeb;    // u16[v_slots]  4 * check-side slot id held by each variable-side slot (padding: 4 * c_slots, an always-zero message)
-	uint32_t off_csched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check groups of each warp: first slot | padded degree << 16 | (group + 1) << 24; 0 ends
-	uint32_t off_vsched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] variable groups (degree > 2 part) of each warp, same packing
+	uint32_t off_edge_varb; // u16[c_slots]  8 * internal variable index of each check-side slot (padding: 8 * N, the +inf variable): byte offset of the float2 (frame pair)
+	uint32_t off_vedgeb;    // u16[v_slots]  8 * check-side slot id held by each variable-side slot (padding: 8 * c_slots, an always-zero message)
+	uint32_t off_csched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check tasks of each warp (MB_CDESC_*); 0 ends
+	uint32_t off_vsched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] variable groups (degree > 2 part) of each warp: first slot | padded degree << 16 | (group + 1) << 24
 	uint32_t off_vtail;     // u32[N - vtail_start] variables vtail_start.. (degree <= 2): byte offsets of their two messages, low | high << 16
 	int32_t vtail_start;    // multiple of 32
 };
@@ -127,16 +133,34 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size);
 void mb_srandom(uint32_t state[35], unsigned seed);
 int mb_random(uint32_t state[35]);
 int mb_rate_index(int rate_num);
-// Which check-group degrees the decoder kernel launched for this rate runs as fully unrolled bodies (mb_ldpc.cu: one kernel instantiation per
-// degree set, measured on the GPU); the table builder balances the static warp schedule with the same knowledge.  Returns 0 / 1 / 2.
-inline int mb_ldpc_degree_set(int rate_num, int *lo, int *hi)
+// Check-side layout of the decoder (mb_ldpc.cu).  A group of 32 sorted checks whose largest degree d exceeds MB_LDPC_DMAX is SPLIT over
+// S = 2, 4 or 8 lanes per check (the smallest S with ceil(d / S) <= MB_LDPC_DMAX): the group becomes S warp tasks of 32 / S checks, each lane
+// holds Dp = ceil(d / S) edges of its check in registers and the lanes of a check combine their partial results by warp shuffles.
+// So every lane of every task runs one of the fully unrolled bodies (3..MB_LDPC_DMAX edges), whatever the check degree (up to 46), and the
+// tasks are small enough to balance over the warps.  Groups up to MB_LDPC_DMAX are one task, one lane per check (S = 1, Dp = d).
+//   task t of group g: checks g * 32 + t * (32 / S) + cl, cl < 32 / S; lane l = j * (32 / S) + cl holds edge positions p = j * Dp + k, k < Dp
+//   slot(p, c') = cgbase[g] + (t * Dp + k) * 32 + l
+#define MB_LDPC_DMAX 7
+inline void mb_ldpc_split(int d, int *S, int *Dp)
 {
-	const int set = rate_num <= 4 ? 0 : (rate_num <= 6 ? 1 : 2);
-	static const int kLo[3] = {3, 3, 5}, kHi[3] = {5, 7, 9};
-	if (lo) *lo = kLo[set];
-	if (hi) *hi = kHi[set];
-	return set;
+	int s = 1;
+	while ((d + s - 1) / s > MB_LDPC_DMAX) s *= 2;
+	*S = s, *Dp = (d + s - 1) / s;
 }
+// slot of edge position p of sorted check cs; d_first = degree of the first (largest) check of its group
+inline uint32_t mb_ldpc_cslot(const uint32_t *cgbase, int d_first, int cs, int p)
+{
+	int S, Dp;
+	mb_ldpc_split(d_first, &S, &Dp);
+	const int per = 32 / S, ci = cs & 31, t = ci / per, cl = ci % per, j = p / Dp, k = p % Dp;
+	return cgbase[cs >> 5] + (uint32_t)((t * Dp + k) * 32 + j * per + cl);
+}
+// check-schedule descriptor: first slot of the task | Dp << 16 | log2(S) << 20 | t << 22 | (group + 1) << 25
+#define MB_CDESC_BASE(x) ((x) & 0xFFFFu)
+#define MB_CDESC_DP(x) (((x) >> 16) & 0xFu)
+#define MB_CDESC_LOG2S(x) (((x) >> 20) & 0x3u)
+#define MB_CDESC_TASK(x) (((x) >> 22) & 0x7u)
+#define MB_CDESC_GROUP(x) (((x) >> 25) - 1u)
 
 // Tone plan of a ROBUST (MFSK) mode: cl_mfsk (include/physical_layer/mfsk.h, mfsk.cc:49-160).
 struct MbMfsk {

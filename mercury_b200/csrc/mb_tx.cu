@@ -442,7 +442,7 @@ std::string mb_tx_build(const std::vector<uint8_t> &blob, int config, const MbFe
 		std::vector<std::vector<uint16_t>> rows(r.P);
 		for (int cs = 0; cs < r.P; cs++)
 			for (int k = 0; k < cdeg[cs]; k++) {
-				const uint16_t v = cw_of_var[ev[cgbase[cs >> 5] + 32 * k + (cs & 31)]];
+				const uint16_t v = cw_of_var[ev[mb_ldpc_cslot(cgbase, cdeg[cs & ~31], cs, k)]];
 				const int c = cos_[cs];
 				if (v < r.K) rows[c].push_back(v);
 				else if (v != r.K + c && v != r.K + c - 1) return "check row is not {data, parity c-1, parity c}: the prefix-XOR encoder does not apply";
@@ -587,7 +587,7 @@ std::string mb_tx_build_mfsk(const std::vector<uint8_t> &blob, const MbMode &m, 
 		std::vector<std::vector<uint16_t>> rows(r.P);
 		for (int cs = 0; cs < r.P; cs++)
 			for (int k = 0; k < cdeg[cs]; k++) {
-				const uint16_t v = cw_of_var[ev[cgbase[cs >> 5] + 32 * k + (cs & 31)]];
+				const uint16_t v = cw_of_var[ev[mb_ldpc_cslot(cgbase, cdeg[cs & ~31], cs, k)]];
 				const int c = cos_[cs];
 				if (v < r.K) rows[c].push_back(v);
 				else if (v != r.K + c && v != r.K + c - 1) return "check row is not {data, parity c-1, parity c}";

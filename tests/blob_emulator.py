@@ -74,9 +74,23 @@ def handoff(v):
     return (v & ~31) | ((v + (v >> 5)) & 31)
 
 
+LDPC_DMAX = 7  # MB_LDPC_DMAX (mb_tables.h)
+
+
+def ldpc_split(d):
+    """mb_ldpc_split (mb_tables.h): lanes per check S and edges per lane Dp of a group of 32 sorted checks whose largest degree is d"""
+    s = 1
+    while (d + s - 1) // s > LDPC_DMAX:
+        s *= 2
+    return s, (d + s - 1) // s
+
+
 def cslot(r, k, cs):
-    """check-side slot of edge k of sorted check cs (warp-blocked ELL, see mb_tables.h)"""
-    return int(r["cgbase"][cs >> 5]) + 32 * k + (cs & 31)
+    """check-side slot of edge position k of sorted check cs (mb_ldpc_cslot, mb_tables.h: warp-blocked ELL, large checks split over S lanes)"""
+    S, Dp = ldpc_split(int(r["cdeg"][cs & ~31]))
+    per, ci = 32 // S, cs & 31
+    t, cl, j, kk = ci // per, ci % per, k // Dp, k % Dp
+    return int(r["cgbase"][cs >> 5]) + (t * Dp + kk) * 32 + j * per + cl
 
 
 def vslot(r, k, vs):

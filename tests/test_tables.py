@@ -55,21 +55,30 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
     assert len(slot_of) == r["n_edges"] == len(set(slot_of.values())) and max(slot_of.values()) < r["c_slots"]
     assert (r["edge_var"] != 0xFFFF).sum() == r["n_edges"] == (r["vedge"] != r["c_slots"]).sum()
     assert all(int(r["vgdeg"][g]) == (int(r["vdeg"][32 * g]) + 1) // 2 * 2 for g in range(50))
-    assert r["c_slots"] <= 1.15 * r["n_edges"] and r["v_slots"] <= 1.25 * r["n_edges"]  # padding stays small
+    assert r["c_slots"] <= 1.23 * r["n_edges"] and r["v_slots"] <= 1.25 * r["n_edges"]  # padding stays small
     # the decoder kernel's byte-offset copies, neutral padding, degree-<=2 tail and static warp schedules
     real = r["edge_var"] != 0xFFFF
-    assert np.array_equal(r["edge_varb"][real], r["edge_var"][real] * 4) and (r["edge_varb"][~real] == 4 * 1600).all()
-    assert np.array_equal(r["vedgeb"].astype(int), r["vedge"].astype(int) * 4)
+    assert np.array_equal(r["edge_varb"][real], r["edge_var"][real] * 8) and (r["edge_varb"][~real] == 8 * 1600).all()
+    assert np.array_equal(r["vedgeb"].astype(int), r["vedge"].astype(int) * 8)
     t0 = r["vtail_start"]
     assert t0 % 32 == 0 and (r["vdeg"][t0:] <= 2).all() and (t0 < 32 or r["vdeg"][t0 - 32] > 2)
     for i, w in enumerate(r["vtail"].astype(int)):
-        offs = [int(r["vedge"][be.vslot(r, k, t0 + i)]) * 4 for k in range(int(r["vdeg"][t0 + i]))] + [4 * r["c_slots"]] * 2
+        offs = [int(r["vedge"][be.vslot(r, k, t0 + i)]) * 8 for k in range(int(r["vdeg"][t0 + i]))] + [8 * r["c_slots"]] * 2
         assert (w & 0xFFFF, w >> 16) == (offs[0], offs[1])
-    lo, hi = {1: (3, 5), 2: (3, 5), 3: (3, 5), 4: (3, 5), 5: (3, 7), 6: (3, 7), 8: (5, 9), 14: (5, 9)}[r["rate_num"]]  # mb_ldpc_degree_set
-    check_cost = lambda d: 30 if d <= 2 else (45 * d + 20 if lo <= d <= hi else 52 * d + 40)
+    # check tasks (MB_CDESC_*: base | Dp << 16 | log2 S << 20 | task << 22 | (group + 1) << 25): every task of every group exactly once
+    ent = [int(e) for row in r["csched"] for e in row if e != 0]
+    want = []
+    for g in range((r["P"] + 31) // 32):
+        S, Dp = be.ldpc_split(int(r["cdeg"][32 * g]))
+        for t in range(S):
+            if g * 32 + t * (32 // S) < r["P"]:
+                want.append((int(r["cgbase"][g]) + t * Dp * 32) | Dp << 16 | (S.bit_length() - 1) << 20 | t << 22 | (g + 1) << 25)
+    assert sorted(ent) == sorted(want) and all(2 <= (e >> 16) & 0xF <= be.LDPC_DMAX for e in ent)
+    ccost = lambda e: 26 if (e >> 16) & 0xF <= 2 else (25 * ((e >> 16) & 0xF) + 15 if (e >> 20) & 3 == 0 else 37 * ((e >> 16) & 0xF) + 55)
+    loads = [sum(ccost(int(e)) for e in row if e != 0) for row in r["csched"]]
+    assert all(row[-1] == 0 for row in r["csched"]) and max(loads) - min(loads) <= max(ccost(e) for e in ent)  # LPT balance, in the builder's cost model
     var_cost = lambda d: 3 * d + 8
-    for sched, n_groups, weight, base, cost in ((r["csched"], (r["P"] + 31) // 32, lambda g: int(r["cdeg"][32 * g]), r["cgbase"], check_cost),
-                                                (r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"], var_cost)):
+    for sched, n_groups, weight, base, cost in ((r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"], var_cost),):
         ent = [int(e) for row in sched for e in row if e != 0]
         assert sorted((e >> 24) - 1 for e in ent) == list(range(n_groups))     # every group exactly once
         assert all(e & 0xFFFF == int(base[(e >> 24) - 1]) and (e >> 16) & 0xFF == weight((e >> 24) - 1) for e in ent)
@@ -119,20 +128,23 @@ def test_decoder_schedule_and_crc_tables(blob, cfg, golden_dir):
 
 
 def _gather_wavefronts(r):
-    """Shared-memory wavefronts per warp gather of the decoder, from the blob: lane i of a check (variable) group reads posterior[edge_var]
-    (message[vedge]) at step k; distinct words in one bank serialise, the same word is a broadcast.  -> (check side, variable side)."""
-    out = []
-    for tab, gbase, gdeg, n_nodes in ((r["edge_var"].astype(int), r["cgbase"], lambda g: int(r["cdeg"][32 * g]), r["P"]),
-                                      (r["vedge"].astype(int), r["vgbase"], lambda g: int(r["vgdeg"][g]), r["N"])):
-        tot = steps = 0
-        for g in range((n_nodes + 31) // 32):
-            for k in range(gdeg(g)):
-                words = set(int(w) for w in tab[int(gbase[g]) + 32 * k:int(gbase[g]) + 32 * k + 32])
-                words = {1600 if w == 0xFFFF else w for w in words}
-                tot += max(np.bincount([w % 32 for w in words], minlength=32))
-                steps += 1
-        out.append(tot / steps)
-    return out
+    """Shared-memory wavefronts per warp gather of the decoder, from the blob: lane i of a check task (variable group) reads the float2
+    (pair of frames) posterior[edge_var] (message[vedge]) at step k.  A 64-bit access is served half-warp by half-warp over 16 eight-byte
+    banks: distinct words in one bank serialise, the same word is a broadcast; the minimum is 2.  -> (check side, variable side)."""
+    def rows_cost(tab, starts):
+        tot = 0
+        for st in starts:
+            row = [1600 if int(w) == 0xFFFF else int(w) for w in tab[st:st + 32]]
+            for half in (row[:16], row[16:]):
+                if half:
+                    tot += max(np.bincount([w % 16 for w in set(half)], minlength=16))
+        return tot / len(starts)
+    csteps = []
+    for g in range((r["P"] + 31) // 32):
+        S, Dp = be.ldpc_split(int(r["cdeg"][32 * g]))
+        csteps += [int(r["cgbase"][g]) + 32 * i for i in range(S * Dp)]
+    vsteps = [int(r["vgbase"][g]) + 32 * k for g in range((r["N"] + 31) // 32) for k in range(int(r["vgdeg"][g]))]
+    return [rows_cost(r["edge_var"].astype(int), csteps), rows_cost(r["vedge"].astype(int), vsteps)]
 
 
 def test_layout_file_only_permutes_and_lowers_bank_conflicts(tmp_path):
@@ -147,7 +159,7 @@ def test_layout_file_only_permutes_and_lowers_bank_conflicts(tmp_path):
     tuned = be.Blob(mb.build_tables_host())
     for idx in (0, 5, 7):
         (c0, v0), (c1, v1) = _gather_wavefronts(plain.rate(idx)), _gather_wavefronts(tuned.rate(idx))
-        assert c1 < 0.6 * c0 and v1 < 0.75 * v0 and c1 < 1.3 and v1 < 2.1, (idx, c0, v0, c1, v1)
+        assert c1 < 0.6 * c0 and v1 < 0.75 * v0 and c1 < 2.6 and v1 < 3.9, (idx, c0, v0, c1, v1)
         assert plain.rate(idx)["c_slots"] == tuned.rate(idx)["c_slots"] and plain.rate(idx)["v_slots"] == tuned.rate(idx)["v_slots"]
     lay = bytearray(open(os.path.join(os.path.dirname(_lib.LDPC_TABLES), "ldpc_layout.bin"), "rb").read())
     lay[12 + 12 + 2 * 1600 + 2 * 1500 + 10] ^= 1   # an edge of a check of the first rate now names another variable

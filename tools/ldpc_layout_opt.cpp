@@ -1,18 +1,22 @@
 // tools/ldpc_layout_opt.cpp -- offline optimiser of the decoder's shared-memory layout: mercury_b200/data/ldpc_tables.bin -> ldpc_layout.bin ('MLAY').
 //
-//   g++ -O2 -std=c++17 tools/ldpc_layout_opt.cpp -o /tmp/ldpc_layout_opt && /tmp/ldpc_layout_opt mercury_b200/data/ldpc_tables.bin mercury_b200/data/ldpc_layout.bin [moves]
+//   g++ -O2 -std=c++17 -Imercury_b200/csrc tools/ldpc_layout_opt.cpp -o /tmp/ldpc_layout_opt && /tmp/ldpc_layout_opt mercury_b200/data/ldpc_tables.bin mercury_b200/data/ldpc_layout.bin [moves]
 //
-// mb_ldpc_kernel keeps posterior[1600] and one message per Tanner-graph edge in shared memory.  A warp owns 32 checks (variables)
-// and at step k every lane gathers through its k-th edge: lane i of a check group reads posterior[variable(i, k)], lane i of a
-// variable group reads message[slot of edge (i, k)].  The bank of a posterior is the variable's position inside ITS group of 32, the
-// bank of a message is the check's position inside ITS group of 32, so a random graph costs ~3 shared-memory wavefronts per gather.
-// Two things are free without touching the kernel or the graph: the ORDER of a node's edges, and the order of the nodes INSIDE a
-// group of 32 (membership of the groups -- nodes sorted by degree -- stays as it is, so the two sides decouple: check-side gathers
-// depend on the checks' edge orders and the variables' in-group positions, variable-side gathers on the variables' edge orders and
-// the checks' in-group positions).  This tool minimises sum over (group, step) of the largest bank multiplicity by hill climbing with
-// plateau moves (fixed seed) and writes the layout file: new node orders and edge orders.  The decoder's arithmetic is unchanged
-// up to the order in which fp32 sums run; mb_tables.cpp validates the file (permutations of the reference rows) and uses the
-// reference order without it.  The tables file itself (what tools/extract_ldpc_tables.py derives from the reference) is not touched.
+// mb_ldpc_kernel keeps posterior[1600] and one message per Tanner-graph edge in shared memory, both as float2 (a PAIR of frames), so a
+// gather is a 64-bit access: the hardware serves it half-warp by half-warp over 16 eight-byte banks, and inside a half-warp two lanes
+// conflict when they name different words of the same bank.  A warp owns a check task (mb_tables.h: mb_ldpc_split -- a group of 32 sorted
+// checks is S tasks of 32 / S checks, S lanes per check, lane l = j * (32 / S) + cl holding edge positions j * Dp + k) or a group of 32
+// variables, and at step k every lane gathers through its k-th edge: a check-task lane reads posterior[variable], a variable-group lane
+// reads message[slot of the edge].  The bank of a posterior is the variable's position in ITS group of 32 modulo 16; the bank of a
+// message is the lane of its slot modulo 16, i.e. (j * (32 / S) + cl) & 15 of the check that owns it.
+// Two things are free without touching the kernel or the graph: the ORDER of a node's edges, and the order of equal-degree nodes INSIDE a
+// group of 32 -- here restricted to swaps that keep a node in its half-warp (variables, unsplit checks) or in its task (split checks),
+// so that the two sides decouple: check-side gathers depend on the checks' edge orders and the variables' in-half positions,
+// variable-side gathers on the variables' edge orders and the checks' in-task positions (given the final check-side edge orders).
+// This tool minimises the sum over (task / group, step) of the wavefronts by hill climbing with plateau moves (fixed seed) and writes the
+// layout file: new node orders and edge orders.  The decoder's arithmetic is unchanged up to the order in which fp32 sums run;
+// mb_tables.cpp validates the file (permutations of the reference rows) and uses the reference order without it.  The tables file itself
+// (what tools/extract_ldpc_tables.py derives from the reference) is not touched.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -21,6 +25,8 @@
 #include <numeric>
 #include <string>
 #include <vector>
+
+#include "mb_tables.h"
 
 struct Rate {
 	uint16_t h[6];  // rate_num, N, K, P, Cwidth, Vwidth
@@ -35,114 +41,213 @@ static inline uint32_t rnd()
 	return (uint32_t)(rng_state >> 32);
 }
 
-// One side of the problem.  `rows[n]` = targets of gathering node n (order is optimised); `groups` = the gathering nodes in warp
-// groups of 32 (fixed); `tgroup[t]`, `tlane[t]` = group and in-group position of target t (lane is optimised by swaps inside a group).
-struct Side {
-	std::vector<std::vector<int>> *rows;
-	std::vector<std::vector<int>> groups;
-	std::vector<int> node_group, tgroup, tlane, tdeg;  // tdeg: the target's own degree -- only equal-degree targets trade places (groups stay sorted)
-	std::vector<std::vector<int>> tmembers;           // targets of each target group
-	std::vector<std::vector<int>> cost;               // [group][step]
-	bool broadcast = true;  // two lanes naming the same target read the same word (a posterior: yes; messages of one check: no, same bank, different words)
+struct Graph {
+	int N, P;
+	std::vector<std::vector<int>> crow, vrow;
+	std::vector<int> cat, vat;    // node at sorted position i
+	std::vector<int> cpos, vpos;  // sorted position of node
+	std::vector<int> gS, gDp;     // per check group: lanes per check, edges per lane
+	int S(int c) const { return gS[cpos[c] >> 5]; }
+	int Dp(int c) const { return gDp[cpos[c] >> 5]; }
+	int per(int c) const { return 32 / S(c); }
+	int task(int c) const { return (cpos[c] & 31) / per(c); }
+	int cl(int c) const { return (cpos[c] & 31) % per(c); }
+};
 
-	// objective of the search: 64 * (largest bank load) + sum of squared bank loads -- the first term is what the hardware pays (wavefronts),
-	// the second gives the climb a slope across the plateaus where the maximum does not change yet
-	int step_cost(int g, int k, bool wavefronts_only = false) const
+// wavefronts of one 64-bit gather: per half-warp the largest number of distinct words in one 8-byte bank
+struct SetCost {
+	int cnt[2][16] = {{0}}, m[2] = {0, 0};
+	int seen[2][32], ns[2] = {0, 0};
+	void add(int half, int bank, int word)  // word < 0: never equal to another lane's
 	{
-		int cnt[32] = {0}, m = 1;
-		int seen[32], ns = 0;
-		bool had_pad = false;
-		for (int n : groups[g]) {
-			const std::vector<int> &r = (*rows)[n];
-			if (k >= (int)r.size()) {  // padding: every padded lane reads the one neutral word, which sits in the bank of position 0
-				if (!had_pad) had_pad = true, m = std::max(m, ++cnt[0]);
-				continue;
-			}
-			const int t = r[k];
-			bool dup = false;  // the same word read twice is a broadcast, not a conflict
-			for (int i = 0; broadcast && i < ns; i++) dup |= seen[i] == t;
-			if (dup) continue;
-			if (broadcast) seen[ns++] = t;
-			m = std::max(m, ++cnt[tlane[t]]);
+		if (word >= 0) {
+			for (int i = 0; i < ns[half]; i++)
+				if (seen[half][i] == word) return;  // the same word read twice is a broadcast, not a conflict
+			seen[half][ns[half]++] = word;
 		}
-		if (wavefronts_only) return m;
+		m[half] = std::max(m[half], ++cnt[half][bank]);
+	}
+	int wavefronts() const { return m[0] + m[1]; }
+	int objective() const  // 64 * wavefronts (what the hardware pays) + squared bank loads (a slope across the plateaus)
+	{
 		int sq = 0;
-		for (int b = 0; b < 32; b++) sq += cnt[b] * cnt[b];
-		return 64 * m + sq;
+		for (int h = 0; h < 2; h++)
+			for (int b = 0; b < 16; b++) sq += cnt[h][b] * cnt[h][b];
+		return 64 * wavefronts() + sq;
+	}
+};
+
+// ---- check side: set (g, t, k) --------------------------------------------------------------------------------------------------------
+struct CheckSide {
+	Graph &G;
+	std::vector<int> setbase;  // first set id of each check group
+	std::vector<int> cost;
+	explicit CheckSide(Graph &g) : G(g)
+	{
+		int n = 0;
+		for (size_t g2 = 0; g2 < G.gS.size(); g2++) setbase.push_back(n), n += G.gS[g2] * G.gDp[g2];
+		cost.assign(n, 0);
+		for (int i = 0; i < n; i++) cost[i] = eval(i).objective();
+	}
+	int set_of(int c, int p) const { return setbase[G.cpos[c] >> 5] + G.task(c) * G.Dp(c) + p % G.Dp(c); }
+	SetCost eval(int sid) const
+	{
+		int g = (int)(std::upper_bound(setbase.begin(), setbase.end(), sid) - setbase.begin()) - 1;
+		const int S = G.gS[g], Dp = G.gDp[g], per = 32 / S, t = (sid - setbase[g]) / Dp, k = (sid - setbase[g]) % Dp;
+		SetCost sc;
+		for (int cl = 0; cl < per; cl++) {
+			const int pos = g * 32 + t * per + cl;
+			for (int j = 0; j < S; j++) {
+				const int half = (j * per + cl) / 16, p = j * Dp + k;
+				if (pos >= G.P || p >= (int)G.crow[G.cat[pos]].size()) sc.add(half, 0, 1 << 20);  // padding: the one neutral word, bank of position 0
+				else {
+					const int v = G.crow[G.cat[pos]][p];
+					sc.add(half, G.vpos[v] & 15, v);
+				}
+			}
+		}
+		return sc;
 	}
 	long wavefronts() const
 	{
 		long s = 0;
-		for (size_t g = 0; g < cost.size(); g++)
-			for (size_t k = 0; k < cost[g].size(); k++) s += step_cost((int)g, (int)k, true);
+		for (size_t i = 0; i < cost.size(); i++) s += eval((int)i).wavefronts();
 		return s;
-	}
-	long total() const
-	{
-		long s = 0;
-		for (auto &g : cost)
-			for (int c : g) s += c;
-		return s;
-	}
-	void init()
-	{
-		cost.assign(groups.size(), {});
-		for (size_t g = 0; g < groups.size(); g++) {
-			size_t d = 0;
-			for (int n : groups[g]) d = std::max(d, (*rows)[n].size());
-			cost[g].resize(d);
-			for (size_t k = 0; k < d; k++) cost[g][k] = step_cost((int)g, (int)k);
-		}
 	}
 	void run(long moves)
 	{
 		std::vector<int> nodes;
-		for (size_t n = 0; n < rows->size(); n++)
-			if ((*rows)[n].size() >= 2) nodes.push_back((int)n);
-		std::vector<int> tg;
-		for (size_t g = 0; g < tmembers.size(); g++)
-			if (tmembers[g].size() >= 2) tg.push_back((int)g);
-		// which (group, step) pairs a target appears in: positions change with edge swaps, so look them up through the rows
-		std::vector<std::vector<int>> users(tgroup.size());  // target -> gathering nodes
-		for (size_t n = 0; n < rows->size(); n++)
-			for (int t : (*rows)[n]) users[t].push_back((int)n);
+		for (int c = 0; c < G.P; c++)
+			if (G.crow[c].size() >= 2) nodes.push_back(c);
 		for (long it = 0; it < moves; it++) {
-			if (rnd() & 1) {  // swap two edges of one node
-				const int n = nodes[rnd() % nodes.size()];
-				std::vector<int> &r = (*rows)[n];
+			if (rnd() & 1) {  // swap two edges of one check
+				const int c = nodes[rnd() % nodes.size()];
+				std::vector<int> &r = G.crow[c];
 				const int i = rnd() % r.size();
 				int j = rnd() % (r.size() - 1);
 				if (j >= i) j++;
-				const int g = node_group[n];
-				const int old = cost[g][i] + cost[g][j];
+				const int si = set_of(c, i), sj = set_of(c, j);
+				const int old = cost[si] + (sj != si ? cost[sj] : 0);
 				std::swap(r[i], r[j]);
-				const int ci = step_cost(g, i), cj = step_cost(g, j);
-				if (ci + cj <= old) cost[g][i] = ci, cost[g][j] = cj;
-				else std::swap(r[i], r[j]);
-			} else {  // swap the in-group positions of two targets of one target group
-				const std::vector<int> &mem = tmembers[tg[rnd() % tg.size()]];
-				const int a = mem[rnd() % mem.size()];
-				int bi = rnd() % (mem.size() - 1);
-				const int b = mem[bi] == a ? mem[mem.size() - 1] : mem[bi];
-				if (a == b || tdeg[a] != tdeg[b]) continue;
-				std::pair<int, int> aff[128];
-				int na = 0;
-				for (int t : {a, b})
-					for (int n : users[t]) {
-						const std::vector<int> &r = (*rows)[n];
-						const int k = (int)(std::find(r.begin(), r.end(), t) - r.begin());
-						const std::pair<int, int> p(node_group[n], k);
+				const int ci = eval(si).objective(), cj = sj != si ? eval(sj).objective() : 0;
+				if (ci + cj <= old) {
+					cost[si] = ci;
+					if (sj != si) cost[sj] = cj;
+				} else
+					std::swap(r[i], r[j]);
+			} else {  // swap two variables of equal degree inside one half of one variable group
+				const int a = rnd() % G.N;
+				const int base = G.vpos[a] & ~15;
+				const int pb = base + (int)(rnd() % 16);
+				if (pb >= G.N) continue;
+				const int b = G.vat[pb];
+				if (a == b || G.vrow[a].size() != G.vrow[b].size()) continue;
+				int aff[64], na = 0;
+				for (int v : {a, b})
+					for (int c : G.vrow[v]) {
+						const std::vector<int> &r = G.crow[c];
+						const int sid = set_of(c, (int)(std::find(r.begin(), r.end(), v) - r.begin()));
 						bool dup = false;
-						for (int q = 0; q < na; q++) dup |= aff[q] == p;
-						if (!dup && na < 128) aff[na++] = p;
+						for (int q = 0; q < na; q++) dup |= aff[q] == sid;
+						if (!dup && na < 64) aff[na++] = sid;
+					}
+				int old = 0, neu = 0, nc[64];
+				for (int q = 0; q < na; q++) old += cost[aff[q]];
+				std::swap(G.vpos[a], G.vpos[b]), G.vat[G.vpos[a]] = a, G.vat[G.vpos[b]] = b;
+				for (int q = 0; q < na; q++) neu += nc[q] = eval(aff[q]).objective();
+				if (neu <= old)
+					for (int q = 0; q < na; q++) cost[aff[q]] = nc[q];
+				else
+					std::swap(G.vpos[a], G.vpos[b]), G.vat[G.vpos[a]] = a, G.vat[G.vpos[b]] = b;
+			}
+		}
+	}
+};
+
+// ---- variable side: set (vg, k) -------------------------------------------------------------------------------------------------------
+struct VarSide {
+	Graph &G;
+	std::vector<int> setbase, vgdeg;
+	std::vector<int> cost;
+	std::vector<std::vector<int>> ejl;  // per variable, per edge: j * per of its slot (fixed: the check-side edge orders are final)
+	explicit VarSide(Graph &g) : G(g)
+	{
+		int n = 0;
+		for (int vg = 0; vg * 32 < G.N; vg++) {
+			const int d = (int)((G.vrow[G.vat[vg * 32]].size() + 1) & ~(size_t)1);
+			setbase.push_back(n), vgdeg.push_back(d), n += d;
+		}
+		ejl.resize(G.N);
+		for (int v = 0; v < G.N; v++)
+			for (int c : G.vrow[v]) {
+				const std::vector<int> &r = G.crow[c];
+				const int p = (int)(std::find(r.begin(), r.end(), v) - r.begin());
+				ejl[v].push_back(p / G.Dp(c) * G.per(c));
+			}
+		cost.assign(n, 0);
+		for (int i = 0; i < n; i++) cost[i] = eval(i).objective();
+	}
+	int set_of(int v, int k) const { return setbase[G.vpos[v] >> 5] + k; }
+	SetCost eval(int sid) const
+	{
+		const int vg = (int)(std::upper_bound(setbase.begin(), setbase.end(), sid) - setbase.begin()) - 1, k = sid - setbase[vg];
+		SetCost sc;
+		for (int i = 0; i < 32 && vg * 32 + i < G.N; i++) {
+			const int v = G.vat[vg * 32 + i];
+			if (k >= (int)G.vrow[v].size()) sc.add(i / 16, 0, 1 << 20);  // padding: the always-zero message behind the last slot
+			else sc.add(i / 16, (ejl[v][k] + G.cl(G.vrow[v][k])) & 15, -1);
+		}
+		return sc;
+	}
+	long wavefronts() const
+	{
+		long s = 0;
+		for (size_t i = 0; i < cost.size(); i++) s += eval((int)i).wavefronts();
+		return s;
+	}
+	void run(long moves)
+	{
+		std::vector<int> nodes;
+		for (int v = 0; v < G.N; v++)
+			if (G.vrow[v].size() >= 2) nodes.push_back(v);
+		for (long it = 0; it < moves; it++) {
+			if (rnd() & 1) {  // swap two edges of one variable
+				const int v = nodes[rnd() % nodes.size()];
+				std::vector<int> &r = G.vrow[v];
+				const int i = rnd() % r.size();
+				int j = rnd() % (r.size() - 1);
+				if (j >= i) j++;
+				const int si = set_of(v, i), sj = set_of(v, j);
+				const int old = cost[si] + cost[sj];
+				std::swap(r[i], r[j]), std::swap(ejl[v][i], ejl[v][j]);
+				const int ci = eval(si).objective(), cj = eval(sj).objective();
+				if (ci + cj <= old) cost[si] = ci, cost[sj] = cj;
+				else std::swap(r[i], r[j]), std::swap(ejl[v][i], ejl[v][j]);
+			} else {  // swap two checks of equal degree inside one task (split groups) or one half (unsplit groups)
+				const int a = rnd() % G.P;
+				const int span = std::min(16, G.per(a));
+				const int base = G.cpos[a] - (G.cpos[a] & 31) % span;  // per is 16, 8 or 4 for split groups: tasks are aligned to their size
+				const int pb = base + (int)(rnd() % span);
+				if (pb >= G.P) continue;
+				const int b = G.cat[pb];
+				if (a == b || G.crow[a].size() != G.crow[b].size()) continue;
+				int aff[128], na = 0;
+				for (int c : {a, b})
+					for (int v : G.crow[c]) {
+						const std::vector<int> &r = G.vrow[v];
+						const int sid = set_of(v, (int)(std::find(r.begin(), r.end(), c) - r.begin()));
+						bool dup = false;
+						for (int q = 0; q < na; q++) dup |= aff[q] == sid;
+						if (!dup && na < 128) aff[na++] = sid;
 					}
 				int old = 0, neu = 0, nc[128];
-				for (int q = 0; q < na; q++) old += cost[aff[q].first][aff[q].second];
-				std::swap(tlane[a], tlane[b]);
-				for (int q = 0; q < na; q++) neu += nc[q] = step_cost(aff[q].first, aff[q].second);
+				for (int q = 0; q < na; q++) old += cost[aff[q]];
+				std::swap(G.cpos[a], G.cpos[b]), G.cat[G.cpos[a]] = a, G.cat[G.cpos[b]] = b;
+				for (int q = 0; q < na; q++) neu += nc[q] = eval(aff[q]).objective();
 				if (neu <= old)
-					for (int q = 0; q < na; q++) cost[aff[q].first][aff[q].second] = nc[q];
-				else std::swap(tlane[a], tlane[b]);
+					for (int q = 0; q < na; q++) cost[aff[q]] = nc[q];
+				else
+					std::swap(G.cpos[a], G.cpos[b]), G.cat[G.cpos[a]] = a, G.cat[G.cpos[b]] = b;
 			}
 		}
 	}
@@ -193,55 +298,39 @@ int main(int argc, char **argv)
 	lay.insert(lay.end(), {'M', 'L', 'A', 'Y'});
 	put32(1), put32(nr);
 	for (Rate &r : rates) {
-		const int N = r.h[1], P = r.h[3];
-		std::vector<int> csorted(P), vsorted(N);
-		std::iota(csorted.begin(), csorted.end(), 0);
-		std::stable_sort(csorted.begin(), csorted.end(), [&](int a, int b) { return r.crow[a].size() > r.crow[b].size(); });
-		std::iota(vsorted.begin(), vsorted.end(), 0);
-		std::stable_sort(vsorted.begin(), vsorted.end(), [&](int a, int b) { return r.vrow[a].size() > r.vrow[b].size(); });
-		auto make_side = [&](std::vector<std::vector<int>> &rows, const std::vector<int> &gsorted, const std::vector<int> &tsorted,
-				     const std::vector<std::vector<int>> &trows) {
-			Side s;
-			s.rows = &rows;
-			s.node_group.assign(gsorted.size(), 0);
-			for (size_t i = 0; i < gsorted.size(); i++) {
-				if (i % 32 == 0) s.groups.emplace_back();
-				s.groups.back().push_back(gsorted[i]);
-				s.node_group[gsorted[i]] = (int)(i / 32);
-			}
-			s.tgroup.assign(tsorted.size(), 0), s.tlane.assign(tsorted.size(), 0), s.tdeg.assign(tsorted.size(), 0);
-			for (size_t t = 0; t < tsorted.size(); t++) s.tdeg[t] = (int)trows[t].size();
-			s.tmembers.assign((tsorted.size() + 31) / 32, {});
-			for (size_t i = 0; i < tsorted.size(); i++) {
-				s.tgroup[tsorted[i]] = (int)(i / 32), s.tlane[tsorted[i]] = (int)(i % 32);
-				s.tmembers[i / 32].push_back(tsorted[i]);
-			}
-			s.init();
-			return s;
-		};
-		Side cs = make_side(r.crow, csorted, vsorted, r.vrow);  // check-side gathers of posteriors
-		Side vs = make_side(r.vrow, vsorted, csorted, r.crow);  // variable-side gathers of messages
-		vs.broadcast = false;
-		vs.init();
-		const long c0 = cs.wavefronts(), v0 = vs.wavefronts();
-		size_t csteps = 0, vsteps = 0;
-		for (auto &g : cs.cost) csteps += g.size();
-		for (auto &g : vs.cost) vsteps += g.size();
-		cs.run(moves), vs.run(moves);
-		printf("rate %2d/16: check-side gathers %ld -> %ld wavefronts over %zu steps (%.2f -> %.2f), variable-side %ld -> %ld over %zu (%.2f -> %.2f)\n", r.h[0], c0,
-		       cs.wavefronts(), csteps, (double)c0 / csteps, (double)cs.wavefronts() / csteps, v0, vs.wavefronts(), vsteps, (double)v0 / vsteps,
-		       (double)vs.wavefronts() / vsteps);
-		// new node orders: group membership kept, in-group position = optimised lane
-		std::vector<int> vnew(N), cnew(P);
-		for (int v = 0; v < N; v++) vnew[cs.tgroup[v] * 32 + cs.tlane[v]] = v;
-		for (int c = 0; c < P; c++) cnew[vs.tgroup[c] * 32 + vs.tlane[c]] = c;
-		put16(r.h[0]), put16((uint16_t)N), put16((uint16_t)P), put16(0), put32(r.ne);
-		for (int v : vnew) put16((uint16_t)v);
-		for (int c : cnew) put16((uint16_t)c);
-		for (int c = 0; c < P; c++)
-			for (int v : r.crow[c]) put16((uint16_t)v);
-		for (int v = 0; v < N; v++)
-			for (int c : r.vrow[v]) put16((uint16_t)c);
+		Graph G;
+		G.N = r.h[1], G.P = r.h[3];
+		G.crow = r.crow, G.vrow = r.vrow;
+		G.cat.resize(G.P), G.vat.resize(G.N), G.cpos.resize(G.P), G.vpos.resize(G.N);
+		std::iota(G.cat.begin(), G.cat.end(), 0);
+		std::stable_sort(G.cat.begin(), G.cat.end(), [&](int a, int b) { return G.crow[a].size() > G.crow[b].size(); });
+		std::iota(G.vat.begin(), G.vat.end(), 0);
+		std::stable_sort(G.vat.begin(), G.vat.end(), [&](int a, int b) { return G.vrow[a].size() > G.vrow[b].size(); });
+		for (int i = 0; i < G.P; i++) G.cpos[G.cat[i]] = i;
+		for (int i = 0; i < G.N; i++) G.vpos[G.vat[i]] = i;
+		for (int g = 0; g * 32 < G.P; g++) {
+			int S, Dp;
+			mb_ldpc_split((int)G.crow[G.cat[g * 32]].size(), &S, &Dp);
+			G.gS.push_back(S), G.gDp.push_back(Dp);
+		}
+		CheckSide cs(G);
+		const long c0 = cs.wavefronts();
+		cs.run(moves);
+		const long c1 = cs.wavefronts();
+		VarSide vs(G);  // after the check side: the lanes of the slots depend on the final check-side edge orders
+		const long v0 = vs.wavefronts();
+		vs.run(moves);
+		const long v1 = vs.wavefronts();
+		printf("rate %2d/16: check-side gathers %ld -> %ld wavefronts over %zu steps (%.2f -> %.2f), variable-side %ld -> %ld over %zu (%.2f -> %.2f); minimum 2\n",
+		       r.h[0], c0, c1, cs.cost.size(), (double)c0 / cs.cost.size(), (double)c1 / cs.cost.size(), v0, v1, vs.cost.size(), (double)v0 / vs.cost.size(),
+		       (double)v1 / vs.cost.size());
+		put16(r.h[0]), put16((uint16_t)G.N), put16((uint16_t)G.P), put16(0), put32(r.ne);
+		for (int v : G.vat) put16((uint16_t)v);
+		for (int c : G.cat) put16((uint16_t)c);
+		for (int c = 0; c < G.P; c++)
+			for (int v : G.crow[c]) put16((uint16_t)v);
+		for (int v = 0; v < G.N; v++)
+			for (int c : G.vrow[v]) put16((uint16_t)c);
 	}
 	f = fopen(argv[2], "wb");
 	if (!f) return perror(argv[2]), 1;
