@@ -114,7 +114,7 @@ struct mercury_b200 {
 	MbBlobHeader hdr;
 	uint8_t *d_blob = nullptr;
 	int config = -1, ldpc_iters = 50, decoder = MERCURY_B200_DECODER_SPA;
-	int cheap_test_threads = 16;  // tuning knob of the decoder's early syndrome test (MERCURY_B200_CHEAP_TEST in the environment)
+	int cheap_test_threads = -1;  // tuning knob of the decoder's early syndrome test (MERCURY_B200_CHEAP_TEST in the environment); -1: by rate
 	std::string err;
 	uint64_t launches = 0;
 	Slot slots[kSlots];
@@ -234,7 +234,8 @@ int launch_ldpc(mercury_b200_t *h, const void *d_llr, size_t n, void *d_payload,
 	a.rate = h->hdr.rates[m.rate_idx];
 	a.max_iters = h->ldpc_iters;
 	a.check_gate = 1;
-	a.cheap_test_threads = h->cheap_test_threads;
+	// measured on B200 (two frames per CTA share the instruction stream, so the test only buys an earlier refill): it pays from rate 8/16 up (+5 %), costs 1-13 % below
+	a.cheap_test_threads = h->cheap_test_threads >= 0 ? h->cheap_test_threads : (a.rate.rate_num >= 8 ? 16 : 0);
 	for (const auto &q : h->ldpc_queues)
 		if (q.first == s) a.queue = q.second;
 	if (!a.queue) {

@@ -185,7 +185,7 @@ __device__ __forceinline__ unsigned lanes_xor(unsigned x, int log2s)
 // cancels in every ratio).  So split and unsplit checks run the SAME body: the decoder's hot code has to stay inside the 32 KB
 // instruction cache (ncu: with separate bodies the warps stalled on instruction fetch as often as on the barriers).
 template <int D>
-__device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int log2s, unsigned &hard_a, unsigned &hard_b)
+__device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int log2s, f2 nm, unsigned &hard_a, unsigned &hard_b)
 {
 	f2 q[D], e[D];
 	unsigned pa = 0, pb = 0, ha = 0, hb = 0;
@@ -196,7 +196,7 @@ __device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *_
 		const unsigned off = ve[k * 32];
 		const f2 lam = lds2(sbase + kOffLam + off);
 		const f2 r = lds2(raddr + k * 256);
-		q[k] = __ffma2_rn(r, make_float2(-1.f, -1.f), lam);
+		q[k] = __ffma2_rn(r, nm, lam);  // nm = -1, or 0 for a slot whose messages are not written yet (just refilled)
 		ha ^= fbits(lam.x);
 		hb ^= fbits(lam.y);
 		pa ^= fbits(q[k].x);
@@ -238,10 +238,10 @@ __device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *_
 // in double, where the reference's clamp gives 2 atanh(0.9999999) (ldpc_decoder_SPA.cc:147-155).  A padding edge (q = +inf) saturates
 // to the clamp: exactly the reference's empty product of a degree-1 check.
 __device__ __forceinline__ float sat_q(float q) { return fabsf(q) > kSatQ2 ? copysign_bits(kClampR2, fbits(q)) : q; }
-__device__ __forceinline__ void spa_check_pair_2(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, unsigned &hard_a, unsigned &hard_b)
+__device__ __forceinline__ void spa_check_pair_2(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, f2 nm, unsigned &hard_a, unsigned &hard_b)
 {
 	const f2 l0 = lds2(sbase + kOffLam + ve[0]), l1 = lds2(sbase + kOffLam + ve[32]);
-	const f2 q0 = __ffma2_rn(lds2(raddr), make_float2(-1.f, -1.f), l0), q1 = __ffma2_rn(lds2(raddr + 256), make_float2(-1.f, -1.f), l1);
+	const f2 q0 = __ffma2_rn(lds2(raddr), nm, l0), q1 = __ffma2_rn(lds2(raddr + 256), nm, l1);
 	hard_a ^= fbits(l0.x) ^ fbits(l1.x);
 	hard_b ^= fbits(l0.y) ^ fbits(l1.y);
 	sts2(raddr, make_float2(sat_q(q1.x), sat_q(q1.y)));
@@ -283,15 +283,15 @@ struct MinSum {
 		return ((par >> 31) ^ ((signs >> k) & 1u)) ? -mag : mag;
 	}
 };
-__device__ __forceinline__ void minsum_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int d, int log2s, int dc, unsigned &hard_a,
-						  unsigned &hard_b)
+__device__ __forceinline__ void minsum_check_pair(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, int d, int log2s, int dc, f2 nm,
+						  unsigned &hard_a, unsigned &hard_b)
 {
 	MinSum a, b;
 	unsigned ha = 0, hb = 0;
 #pragma unroll 4
 	for (int k = 0; k < d; k++) {
 		const f2 lam = lds2(sbase + kOffLam + ve[k * 32]);
-		const f2 q = __ffma2_rn(lds2(raddr + k * 256), make_float2(-1.f, -1.f), lam);
+		const f2 q = __ffma2_rn(lds2(raddr + k * 256), nm, lam);
 		ha ^= fbits(lam.x);
 		hb ^= fbits(lam.y);
 		a.take(q.x, k);
@@ -312,14 +312,14 @@ __device__ __forceinline__ void minsum_check_pair(unsigned sbase, const uint16_t
 // Variable node of the head (degree > 2, groups padded to an even degree): channel LLR + the incoming messages in the table's order.
 // D > 0: fixed group degree, every index load and gather at an immediate offset.
 template <int D>
-__device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__restrict__ se, f2 acc, int d_rt)
+__device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__restrict__ se, f2 acc, int d_rt, f2 vm)
 {
 	if (D > 0) {
 		unsigned idx[D > 0 ? D : 1];
 #pragma unroll
 		for (int k = 0; k < D; k++) idx[k] = se[k * 32];
 #pragma unroll
-		for (int k = 0; k < D; k++) acc = __fadd2_rn(acc, lds2(sbase + kOffR + idx[k]));
+		for (int k = 0; k < D; k++) acc = __ffma2_rn(lds2(sbase + kOffR + idx[k]), vm, acc);  // vm = 1, or 0 for a just-refilled slot
 		return acc;
 	}
 	int k = 0;
@@ -327,15 +327,15 @@ __device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__res
 	for (; k + 4 <= d_rt; k += 4) {
 		const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
 		se += 128;
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i0));
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i1));
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i2));
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i3));
+		acc = __ffma2_rn(lds2(sbase + kOffR + i0), vm, acc);
+		acc = __ffma2_rn(lds2(sbase + kOffR + i1), vm, acc);
+		acc = __ffma2_rn(lds2(sbase + kOffR + i2), vm, acc);
+		acc = __ffma2_rn(lds2(sbase + kOffR + i3), vm, acc);
 	}
 	if (k < d_rt) {
 		const unsigned i0 = se[0], i1 = se[32];
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i0));
-		acc = __fadd2_rn(acc, lds2(sbase + kOffR + i1));
+		acc = __ffma2_rn(lds2(sbase + kOffR + i0), vm, acc);
+		acc = __ffma2_rn(lds2(sbase + kOffR + i1), vm, acc);
 	}
 	return acc;
 }
@@ -534,7 +534,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int X)
 {
 	const MbMode &m = a.mode;
-	const int tid = threadIdx.x, CS = a.rate.c_slots;
+	const int tid = threadIdx.x;
 	int frame;
 	for (;;) {
 		// The ticket was published before a barrier every thread has passed (the end of the previous refill / the kernel prologue); the
@@ -595,7 +595,7 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 	} else {
 		for (int i = tid; i < MB_N; i += kThreads) s.lam(i, X) = 1.0f, s.set_lch(i, X, 1.0f);
 	}
-	for (int i = tid; i <= CS; i += kThreads) s.R(i, X) = 0.f;
+	// the slot's old messages stay where they are: until its first check pass has rewritten them they are multiplied by 0 (the kernel's nm / vm)
 	__syncthreads();
 	return frame;
 }
@@ -631,12 +631,14 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 		s.lam(MB_N, 0) = __int_as_float(0x7f800000);  // +inf: a padding edge contributes e = 0, sign +, hard bit 0
 		s.lam(MB_N, 1) = __int_as_float(0x7f800000);
 	}
+	for (int i = tid; i < 2 * (CS + 1); i += kThreads) reinterpret_cast<float *>(smem_raw + kOffR)[i] = 0.f;  // once: 0 x (stale finite message) is 0, 0 x (garbage NaN) is not
 	int turn_reg = 0;
 	s.turn = &turn_reg;
 	if (tid == 32) s.next[0] = (int)atomicAdd(a.queue, 1u);
 	__syncthreads();
 	int frame[2];
 	int pass[2] = {0, 0};  // check passes this slot's frame has been through = iterations completed
+	bool virgin[2] = {true, true};  // refilled, messages not yet rewritten by a check pass
 	frame[0] = refill_slot(a, s, 0);
 	frame[1] = refill_slot(a, s, 1);
 
@@ -646,48 +648,54 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 		// A warp owns a group of 32 checks padded to one degree; padding slots point at the +inf variable, so the loops are
 		// warp-uniform (no per-thread degree, no divergence) and a padding edge is the neutral element of every reduction.
 		unsigned hard_a = 0, hard_b = 0;
+		const f2 nm = make_float2(virgin[0] ? 0.f : -1.f, virgin[1] ? 0.f : -1.f);
+		virgin[0] = virgin[1] = false;
+		// This warp's check tasks (static, cost-balanced schedule), sorted by body: one loop per body, no per-task dispatch.
 		const uint32_t *sched = s_csched + warp * MB_SCHED_LEN;
-		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check tasks (static, cost-balanced schedule)
-			const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc);
-			const unsigned e0 = MB_CDESC_BASE(desc) + (unsigned)lane;
-			const unsigned raddr = sbase + kOffR + e0 * 8u;
-			const uint16_t *__restrict__ ve = g_edge_var + e0;
-			unsigned ha = 0, hb = 0;
-			if (ALGO == 0) {
-#define MB_FIX_CASE(D_) \
-	case D_:         \
-		spa_check_pair<D_>(sbase, ve, raddr, l2, ha, hb); \
-		break;
-				switch (dp + (l2 != 0 ? 1 : 0)) {  // a split task runs the body of one more edge: the other lanes' total (see spa_check_pair)
-				case 2: spa_check_pair_2(sbase, ve, raddr, ha, hb); break;
-				MB_FIX_CASE(3)
-				MB_FIX_CASE(4)
-				MB_FIX_CASE(5)
-				MB_FIX_CASE(6)
-				MB_FIX_CASE(7)
-				MB_FIX_CASE(8)
-				default: break;
-				}
-#undef MB_FIX_CASE
-				static_assert(MB_LDPC_DMAX == 7, "check-node bodies are instantiated for 3..MB_LDPC_DMAX + 1 edges");
-			} else {
-				const int per = 32 >> l2;
+		const uint32_t counts = sched[MB_SCHED_LEN - 1];
+#define MB_TASK_PROLOGUE                                                          \
+	const uint32_t desc = *sched++;                                           \
+	const int l2 = (int)MB_CDESC_LOG2S(desc);                                 \
+	const unsigned e0 = MB_CDESC_BASE(desc) + (unsigned)lane;                 \
+	const unsigned raddr = sbase + kOffR + e0 * 8u;                           \
+	const uint16_t *__restrict__ ve = g_edge_var + e0;                        \
+	unsigned ha = 0, hb = 0;
+#define MB_TASK_EPILOGUE                \
+	hard_a |= ha & 0x80000000u;     \
+	hard_b |= hb & 0x80000000u;
+		if (ALGO == 0) {
+			for (int n = (int)(counts & 15u); n > 0; n--) {
+				MB_TASK_PROLOGUE
+				(void)l2;
+				spa_check_pair_2(sbase, ve, raddr, nm, ha, hb);
+				MB_TASK_EPILOGUE
+			}
+#define MB_BODY_LOOP(B_)                                                                    \
+	for (int n = (int)((counts >> (4 * (B_ - 2))) & 15u); n > 0; n--) {                 \
+		MB_TASK_PROLOGUE                                                            \
+		spa_check_pair<B_>(sbase, ve, raddr, l2, nm, ha, hb);                       \
+		MB_TASK_EPILOGUE                                                            \
+	}
+			MB_BODY_LOOP(3)
+			MB_BODY_LOOP(4)
+			MB_BODY_LOOP(5)
+			MB_BODY_LOOP(6)
+			MB_BODY_LOOP(7)
+			MB_BODY_LOOP(8)
+#undef MB_BODY_LOOP
+			static_assert(MB_LDPC_DMAX == 7, "check-node bodies are instantiated for 3..MB_LDPC_DMAX + 1 edges");
+		} else {
+			for (uint32_t d0 = *sched; d0 != 0u; d0 = *sched) {
+				MB_TASK_PROLOGUE
+				const int dp = (int)MB_CDESC_DP(desc), per = 32 >> l2;
 				const int c = (int)MB_CDESC_GROUP(desc) * 32 + (int)MB_CDESC_TASK(desc) * per + (lane & (per - 1));
 				const int dc = c < rt.P ? (int)(a.blob + rt.off_cdeg)[c] : 0;  // the true degree picks the normalisation
-				minsum_check_pair(sbase, ve, raddr, dp, l2, dc, ha, hb);
+				minsum_check_pair(sbase, ve, raddr, dp, l2, dc, nm, ha, hb);
+				MB_TASK_EPILOGUE
 			}
-			hard_a |= ha & 0x80000000u;
-			hard_b |= hb & 0x80000000u;
 		}
-		// The channel LLRs of this thread's tail variables for the variable pass below: issued before the barrier, so that their L2 latency
-		// is spent waiting for the other warps (they are read-only; a slot refilled in between re-reads them).
-		constexpr int kTailRegs = 6;  // the tail is at most 1600 - 128 variables (rate 1/16)
-		f2 lt[kTailRegs];
-#pragma unroll
-		for (int i = 0; i < kTailRegs; i++) {
-			const int v = vtail0 + tid + i * kThreads;
-			lt[i] = v < MB_N ? s.get_lch(v) : make_float2(0.f, 0.f);
-		}
+#undef MB_TASK_PROLOGUE
+#undef MB_TASK_EPILOGUE
 		// threads that saw an unsatisfied check, per slot: 0 = converged; a small count = "probably one iteration to go"
 		{
 			const unsigned ba = __ballot_sync(0xffffffffu, hard_a != 0u), bb = __ballot_sync(0xffffffffu, hard_b != 0u);
@@ -712,6 +720,7 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 				frame[X] = refill_slot(a, s, X);
 				pass[X] = 0;
 				fresh[X] = true;
+				virgin[X] = true;
 			} else {
 				pass[X]++;
 			}
@@ -722,12 +731,15 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 		// degree (padding reads the always-zero slot); the long tail of degree-<=2 variables (the accumulator chain of the IRA
 		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.  A slot refilled above has
 		// all-zero messages: its posterior is rewritten with the channel LLR, and the next check pass is its pass 0.
-		if (fresh[0] || fresh[1]) {
+		// A slot refilled above keeps its old messages (x 0 here): its posterior is rewritten with the channel LLR, the next check pass is
+		// its pass 0.  The channel LLRs come from the L2 (global scratch): all of a thread's loads are issued before the first is used.
+		const f2 vm = make_float2(virgin[0] ? 0.f : 1.f, virgin[1] ? 0.f : 1.f);
+		constexpr int kTailRegs = 6;  // the tail is at most 1600 - 128 variables (rate 1/16)
+		f2 lt[kTailRegs];
 #pragma unroll
-			for (int i = 0; i < kTailRegs; i++) {
-				const int v = vtail0 + tid + i * kThreads;
-				lt[i] = v < MB_N ? s.get_lch(v) : make_float2(0.f, 0.f);
-			}
+		for (int i = 0; i < kTailRegs; i++) {
+			const int v = vtail0 + tid + i * kThreads;
+			lt[i] = v < MB_N ? s.get_lch(v) : make_float2(0.f, 0.f);
 		}
 		sched = s_vsched + warp * MB_SCHED_LEN;
 		uint32_t desc = *sched;
@@ -737,16 +749,16 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 			const int v = vtail0 + tid + i * kThreads;
 			if (v < MB_N) {
 				const uint32_t w = __ldg(g_vtail + (v - vtail0));
-				f2 acc = __fadd2_rn(lt[i], lds2(sbase + kOffR + (w & 0xFFFFu)));
-				acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w >> 16)));
+				f2 acc = __ffma2_rn(lds2(sbase + kOffR + (w & 0xFFFFu)), vm, lt[i]);
+				acc = __ffma2_rn(lds2(sbase + kOffR + (w >> 16)), vm, acc);
 				sts2(sbase + kOffLam + v * 8, acc);
 			}
 		}
 		for (int v = vtail0 + tid + kTailRegs * kThreads; v < MB_N; v += kThreads) {  // (not reached with the eight codes of the reference)
 			const uint32_t w = __ldg(g_vtail + (v - vtail0));
 			f2 acc = s.get_lch(v);
-			acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w & 0xFFFFu)));
-			acc = __fadd2_rn(acc, lds2(sbase + kOffR + (w >> 16)));
+			acc = __ffma2_rn(lds2(sbase + kOffR + (w & 0xFFFFu)), vm, acc);
+			acc = __ffma2_rn(lds2(sbase + kOffR + (w >> 16)), vm, acc);
 			sts2(sbase + kOffLam + v * 8, acc);
 		}
 		while (desc != 0u) {
@@ -757,10 +769,10 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 			f2 acc = lh;
 			if (nd != 0u) lh = s.get_lch((int)((nd >> 24) - 1u) * 32 + lane);  // the next group's, one ahead
 			switch (d) {  // variable degrees are 3..9 in all eight codes (padded: 4, 6, 8, 10)
-			case 4: acc = var_node_sum<4>(sbase, se, acc, d); break;
-			case 6: acc = var_node_sum<6>(sbase, se, acc, d); break;
-			case 8: acc = var_node_sum<8>(sbase, se, acc, d); break;
-			default: acc = var_node_sum<0>(sbase, se, acc, d); break;
+			case 4: acc = var_node_sum<4>(sbase, se, acc, d, vm); break;
+			case 6: acc = var_node_sum<6>(sbase, se, acc, d, vm); break;
+			case 8: acc = var_node_sum<8>(sbase, se, acc, d, vm); break;
+			default: acc = var_node_sum<0>(sbase, se, acc, d, vm); break;
 			}
 			sts2(sbase + kOffLam + v * 8, acc);
 			desc = nd;
@@ -772,19 +784,23 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 		if (try_a || try_b) {
 			unsigned bad_a = 0, bad_b = 0;
 			sched = s_csched + warp * MB_SCHED_LEN;
-			for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {
-				const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc);
-				const uint16_t *__restrict__ ve = g_edge_var + MB_CDESC_BASE(desc) + lane;
-				switch (dp) {
-				case 2: check_parity<2>(sbase, ve, l2, bad_a, bad_b); break;
-				case 3: check_parity<3>(sbase, ve, l2, bad_a, bad_b); break;
-				case 4: check_parity<4>(sbase, ve, l2, bad_a, bad_b); break;
-				case 5: check_parity<5>(sbase, ve, l2, bad_a, bad_b); break;
-				case 6: check_parity<6>(sbase, ve, l2, bad_a, bad_b); break;
-				case 7: check_parity<7>(sbase, ve, l2, bad_a, bad_b); break;
-				default: break;
-				}
-			}
+			const uint32_t pcounts = sched[MB_SCHED_LEN - 1];
+#define MB_PARITY_LOOP(B_)                                                                                   \
+	for (int n = (int)((pcounts >> (4 * (B_ - 2))) & 15u); n > 0; n--) {                                 \
+		const uint32_t desc = *sched++;                                                              \
+		const int l2 = (int)MB_CDESC_LOG2S(desc);                                                    \
+		const uint16_t *__restrict__ ve = g_edge_var + MB_CDESC_BASE(desc) + lane;                   \
+		if (B_ <= MB_LDPC_DMAX && (B_ == 2 || l2 == 0)) check_parity<(B_ <= MB_LDPC_DMAX ? B_ : 2)>(sbase, ve, l2, bad_a, bad_b); \
+		else check_parity<B_ - 1>(sbase, ve, l2, bad_a, bad_b);  /* a split task holds one edge less than its body */ \
+	}
+			MB_PARITY_LOOP(2)
+			MB_PARITY_LOOP(3)
+			MB_PARITY_LOOP(4)
+			MB_PARITY_LOOP(5)
+			MB_PARITY_LOOP(6)
+			MB_PARITY_LOOP(7)
+			MB_PARITY_LOOP(8)
+#undef MB_PARITY_LOOP
 			const unsigned ba = __ballot_sync(0xffffffffu, bad_a != 0u), bb = __ballot_sync(0xffffffffu, bad_b != 0u);
 			if (lane == 0) s.cnt[MB_LDPC_WARPS + warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
 			__syncthreads();
@@ -796,11 +812,13 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 				finish_slot(a, s, 0, (size_t)frame[0], pass[0]);
 				frame[0] = refill_slot(a, s, 0);
 				pass[0] = 0;
+				virgin[0] = true;
 			}
 			if (done_b) {
 				finish_slot(a, s, 1, (size_t)frame[1], pass[1]);
 				frame[1] = refill_slot(a, s, 1);
 				pass[1] = 0;
+				virgin[1] = true;
 			}
 		}
 	}

@@ -309,7 +309,9 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 		// longest-processing-time-first assignment of tasks to warps; cost = what balances the warps: warp instructions of the task in
 		// the kernel (mb_ldpc.cu: ~25 per edge of a pair of frames in an unrolled body, ~12 more per edge and ~40 per task when the
 		// check is split over lanes, a degree-2 check is a pass-through; ~3 per edge on the variable side)
-		auto lpt = [&](std::vector<std::pair<int, uint32_t>> items, uint32_t &off) -> bool {  // (cost, descriptor)
+		// check_side: each warp's tasks are then sorted by body (edges per lane + 1 for a split task), and the last word of the warp's row
+		// holds the number of tasks per body, 4 bits each from body 2: the kernel runs one loop per body instead of a switch per task.
+		auto lpt = [&](std::vector<std::pair<int, uint32_t>> items, uint32_t &off, bool check_side) -> bool {  // (cost, descriptor)
 			std::stable_sort(items.begin(), items.end(), [](const std::pair<int, uint32_t> &a, const std::pair<int, uint32_t> &b) { return a.first > b.first; });
 			std::vector<uint32_t> sched(MB_LDPC_WARPS * MB_SCHED_LEN, 0u);
 			int load[MB_LDPC_WARPS] = {0}, cnt[MB_LDPC_WARPS] = {0};
@@ -317,10 +319,22 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 				int w = 0;
 				for (int i = 1; i < MB_LDPC_WARPS; i++)
 					if (load[i] < load[w]) w = i;
-				if (cnt[w] >= MB_SCHED_LEN - 1) return false;
+				if (cnt[w] >= MB_SCHED_LEN - 2) return false;
 				sched[w * MB_SCHED_LEN + cnt[w]++] = it.second;
 				load[w] += it.first;
 			}
+			if (check_side)
+				for (int w = 0; w < MB_LDPC_WARPS; w++) {
+					uint32_t *row = sched.data() + w * MB_SCHED_LEN;
+					std::stable_sort(row, row + cnt[w], [](uint32_t a, uint32_t b) { return MB_CDESC_BODY(a) < MB_CDESC_BODY(b); });
+					uint32_t counts = 0;
+					for (int i = 0; i < cnt[w]; i++) {
+						const uint32_t body = MB_CDESC_BODY(row[i]);
+						if (body < 2 || body > MB_LDPC_DMAX + 1 || ((counts >> (4 * (body - 2))) & 15u) == 15u) return false;
+						counts += 1u << (4 * (body - 2));
+					}
+					row[MB_SCHED_LEN - 1] = counts;
+				}
 			off = bl.put(sched);
 			return true;
 		};
@@ -342,8 +356,8 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 			if (vgbase[g] > 0xFFFFu || d > 255) return "variable schedule overflow";
 			vtasks.emplace_back(3 * d + 8, vgbase[g] | ((uint32_t)d << 16) | ((uint32_t)(g + 1) << 24));
 		}
-		if (!lpt(ctasks, out.off_csched)) return "check schedule overflow";
-		if (!lpt(vtasks, out.off_vsched)) return "variable schedule overflow";
+		if (!lpt(ctasks, out.off_csched, true)) return "check schedule overflow";
+		if (!lpt(vtasks, out.off_vsched, false)) return "variable schedule overflow";
 	}
 	out.off_var_of_cw = bl.put(var_of_cw);
 	out.off_check_of_sorted = bl.put(check_of_sorted);
@@ -674,9 +688,17 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 				if ((vt[i] & 0xFFFFu) > 8u * (uint32_t)t.c_slots || (vt[i] >> 16) > 8u * (uint32_t)t.c_slots || (vt[i] & 0x00070007u)) return "table blob: tail offset out of range";
 			const uint32_t *cs = reinterpret_cast<const uint32_t *>(blob + t.off_csched), *vs = reinterpret_cast<const uint32_t *>(blob + t.off_vsched);
 			for (int w = 0; w < MB_LDPC_WARPS; w++) {
-				if (cs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1] != 0u || vs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1] != 0u) return "table blob: schedule not terminated";
+				if (cs[w * MB_SCHED_LEN + MB_SCHED_LEN - 2] != 0u || vs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1] != 0u) return "table blob: schedule not terminated";
+				{  // the per-body counts must describe the row: sorted by body, as many tasks as counted
+					uint32_t counts = cs[w * MB_SCHED_LEN + MB_SCHED_LEN - 1], at = 0;
+					if (counts >> (4 * MB_LDPC_DMAX)) return "table blob: check schedule counts out of range";
+					for (uint32_t body = 2; body <= MB_LDPC_DMAX + 1; body++)
+						for (uint32_t n = (counts >> (4 * (body - 2))) & 15u; n > 0; n--, at++)
+							if (at >= MB_SCHED_LEN - 2 || cs[w * MB_SCHED_LEN + at] == 0u || MB_CDESC_BODY(cs[w * MB_SCHED_LEN + at]) != body) return "table blob: check schedule counts do not match";
+					if (cs[w * MB_SCHED_LEN + at] != 0u) return "table blob: check schedule counts do not match";
+				}
 				for (int i = 0; i < MB_SCHED_LEN; i++) {
-					const uint32_t c = cs[w * MB_SCHED_LEN + i], v = vs[w * MB_SCHED_LEN + i];
+					const uint32_t c = i == MB_SCHED_LEN - 1 ? 0u : cs[w * MB_SCHED_LEN + i], v = vs[w * MB_SCHED_LEN + i];
 					if (c != 0u && ((c >> 25) == 0u || MB_CDESC_BASE(c) + 32u * MB_CDESC_DP(c) > (uint32_t)t.c_slots || MB_CDESC_DP(c) < 2u || MB_CDESC_DP(c) > MB_LDPC_DMAX ||
 							MB_CDESC_TASK(c) >= (1u << MB_CDESC_LOG2S(c)) || MB_CDESC_GROUP(c) * 32u >= (uint32_t)t.P))
 						return "table blob: check schedule out of range";

@@ -29,7 +29,7 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 13u
+#define MB_BLOB_VERSION 14u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
@@ -74,7 +74,7 @@ struct MbRate {
 	// padded degrees of the groups over the CTA's warps (longest-processing-time first), so no warp idles at the barriers.
 	uint32_t off_edge_varb; // u16[c_slots]  8 * internal variable index of each check-side slot (padding: 8 * N, the +inf variable): byte offset of the float2 (frame pair)
 	uint32_t off_vedgeb;    // u16[v_slots]  8 * check-side slot id held by each variable-side slot (padding: 8 * c_slots, an always-zero message)
-	uint32_t off_csched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check tasks of each warp (MB_CDESC_*); 0 ends
+	uint32_t off_csched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check tasks of each warp (MB_CDESC_*), sorted by body, 0 ends; last word: tasks per body, 4 bits each from body 2
 	uint32_t off_vsched;    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] variable groups (degree > 2 part) of each warp: first slot | padded degree << 16 | (group + 1) << 24
 	uint32_t off_vtail;     // u32[N - vtail_start] variables vtail_start.. (degree <= 2): byte offsets of their two messages, low | high << 16
 	int32_t vtail_start;    // multiple of 32
@@ -161,6 +161,7 @@ inline uint32_t mb_ldpc_cslot(const uint32_t *cgbase, int d_first, int cs, int p
 #define MB_CDESC_LOG2S(x) (((x) >> 20) & 0x3u)
 #define MB_CDESC_TASK(x) (((x) >> 22) & 0x7u)
 #define MB_CDESC_GROUP(x) (((x) >> 25) - 1u)
+#define MB_CDESC_BODY(x) (MB_CDESC_DP(x) + (MB_CDESC_LOG2S(x) != 0u ? 1u : 0u))  // which unrolled body runs the task (mb_ldpc.cu)
 
 // Tone plan of a ROBUST (MFSK) mode: cl_mfsk (include/physical_layer/mfsk.h, mfsk.cc:49-160).
 struct MbMfsk {

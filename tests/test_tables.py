@@ -66,7 +66,7 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
         offs = [int(r["vedge"][be.vslot(r, k, t0 + i)]) * 8 for k in range(int(r["vdeg"][t0 + i]))] + [8 * r["c_slots"]] * 2
         assert (w & 0xFFFF, w >> 16) == (offs[0], offs[1])
     # check tasks (MB_CDESC_*: base | Dp << 16 | log2 S << 20 | task << 22 | (group + 1) << 25): every task of every group exactly once
-    ent = [int(e) for row in r["csched"] for e in row if e != 0]
+    ent = [int(e) for row in r["csched"] for e in row[:-1] if e != 0]
     want = []
     for g in range((r["P"] + 31) // 32):
         S, Dp = be.ldpc_split(int(r["cdeg"][32 * g]))
@@ -74,9 +74,14 @@ def test_jds_graph_is_the_reference_graph(blob, rate_idx):
             if g * 32 + t * (32 // S) < r["P"]:
                 want.append((int(r["cgbase"][g]) + t * Dp * 32) | Dp << 16 | (S.bit_length() - 1) << 20 | t << 22 | (g + 1) << 25)
     assert sorted(ent) == sorted(want) and all(2 <= (e >> 16) & 0xF <= be.LDPC_DMAX for e in ent)
+    body = lambda e: ((e >> 16) & 0xF) + (1 if (e >> 20) & 3 else 0)   # MB_CDESC_BODY: a split task runs the body of one more edge
+    for row in r["csched"]:   # sorted by body, 0-terminated, last word = tasks per body (4 bits each from body 2)
+        tasks = [int(e) for e in row[:-1] if e != 0]
+        assert [body(e) for e in tasks] == sorted(body(e) for e in tasks) and int(row[len(tasks)]) == 0 and len(tasks) <= 14
+        assert int(row[-1]) == sum(1 << (4 * (body(e) - 2)) for e in tasks)
     ccost = lambda e: 26 if (e >> 16) & 0xF <= 2 else (25 * ((e >> 16) & 0xF) + 15 if (e >> 20) & 3 == 0 else 37 * ((e >> 16) & 0xF) + 55)
-    loads = [sum(ccost(int(e)) for e in row if e != 0) for row in r["csched"]]
-    assert all(row[-1] == 0 for row in r["csched"]) and max(loads) - min(loads) <= max(ccost(e) for e in ent)  # LPT balance, in the builder's cost model
+    loads = [sum(ccost(int(e)) for e in row[:-1] if e != 0) for row in r["csched"]]
+    assert max(loads) - min(loads) <= max(ccost(e) for e in ent)  # LPT balance, in the builder's cost model
     var_cost = lambda d: 3 * d + 8
     for sched, n_groups, weight, base, cost in ((r["vsched"], t0 // 32, lambda g: int(r["vgdeg"][g]), r["vgbase"], var_cost),):
         ent = [int(e) for row in sched for e in row if e != 0]

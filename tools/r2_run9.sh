@@ -1,0 +1,24 @@
+mkdir -p gpurun_out
+T=${1:-r2i}
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --no-e2e --cpu-frames 0 --steps 5 $BARGS > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
+}
+for cfg in 8 9 5; do
+BARGS="--config $cfg"
+run m${cfg}_ct0 MERCURY_B200_CHEAP_TEST=0
+run m${cfg}_ct8 MERCURY_B200_CHEAP_TEST=8
+run m${cfg}_ct16 MERCURY_B200_CHEAP_TEST=16
+run m${cfg}_ct32 MERCURY_B200_CHEAP_TEST=32
+done
+MERCURY_B200_CHEAP_TEST=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mb_ldpc -s 1 -c 1 -o gpurun_out/${T}_prof_ct0 \
+    python bench.py --batch 16384 --steps 1 --warmup 1 --no-e2e --cpu-frames 0 > gpurun_out/${T}_prof.log 2>&1
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("gpurun_out/${T}_bench_*.json")):
+    try:
+        d = json.load(open(f)); r, l = d["roofline"], d["ldpc"]
+        print(f, f"value {d['value']:.4g} | demod {r['kernel_ms']:.3f} ms | ldpc {l['kernel_ms']:.3f} ms it {l['mean_iterations']:.2f} | mism {d['integrity']['payload_mismatches_among_decoded']} fer {d['integrity']['fer']}")
+    except Exception as e:
+        print(f, "failed", e)
+PY
