@@ -5,10 +5,11 @@
   python bench.py --impl reference [--gpus N --steps K --warmup W] the reference's own CPU implementation of the path
   torchrun ... bench.py --gpus N ...                               one rank per GPU, frames sharded, no data-path collective
 
-A step = one pass of the hot path over one batch of synthetic frames.  Workload at every N: BASELINE config #2,
-mode 8 (CONFIG_8 = QPSK, LDPC 6/16), -I 50, 65,536 frames per GPU (weak scaling), Es/N0 = threshold + 2 dB = 2.5 dB,
-every frame with its own payload-tile and its own noise realisation.  Inputs (3.4 GB per GPU) are far larger than
-the 126 MB L2, so no flush is needed between timed steps.
+A step = one pass of the hot path over one batch of synthetic frames.  Workload: mode 8 (CONFIG_8 = QPSK, LDPC 6/16), -I 50,
+Es/N0 = threshold + 2 dB = 2.5 dB, every frame with its own payload-tile and its own noise realisation.  N = 1: BASELINE config #2,
+65,536 frames.  N > 1: the per-GPU shard of BASELINE config #5 (1,048,576 frames over 8 GPUs = 131,072 frames per GPU, contiguous
+frame ranges, weak scaling: the N = 8 line IS config #5).  Inputs (3.4 / 6.8 GB per GPU) are far larger than the 126 MB L2, so no
+flush is needed between timed steps.
 
   value : frames/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e   : the same through the host-buffer C-ABI call (pinned host memory; H2D + kernels + D2H inside the timed region)
@@ -41,20 +42,39 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--config", type=int, default=8)
-    ap.add_argument("--batch", type=int, default=65536, help="frames per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU (default: 65,536 = config #2 at N = 1; 131,072 = the config #5 shard at N > 1)")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--esn0", type=float, default=None, help="Es/N0 in dB (default: mode threshold + 2 dB)")
     ap.add_argument("--decoder", default="spa", choices=["spa", "minsum"])
     ap.add_argument("--unique", type=int, default=4096, help="distinct clean frames synthesised on the host")
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extra", action="store_true", help="skip the one-line summaries of the other BASELINE configurations (modes 9 and 16)")
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 65536 if int(os.environ.get("WORLD_SIZE", "1")) == 1 and a.gpus == 1 else 131072
+    return a
 
 
-def workload_name(m, a, esn0):
+def workload_name(m, a, esn0, world):
     mod = {2: "BPSK", 4: "QPSK", 8: "8PSK", 16: "16QAM", 32: "32QAM"}[m["M"]]
-    return (f"mode {m['config']} ({mod}, LDPC {m['rate_num']}/16, Nsymb {m['Nsymb']}), -I {a.iters}, "
+    tag = ""
+    if m["config"] == 8 and a.iters == 50:
+        if world == 1 and a.batch == 65536:
+            tag = "BASELINE config #2: "
+        elif a.batch == 131072:
+            tag = f"BASELINE config #5 shard ({world} of 8 GPUs x 131,072 frames{', = 1,048,576 frames' if world == 8 else ''}): "
+    return (f"{tag}mode {m['config']} ({mod}, LDPC {m['rate_num']}/16, Nsymb {m['Nsymb']}), -I {a.iters}, "
             f"batch {a.batch} frames/GPU, AWGN Es/N0 {esn0:g} dB")
+
+
+def config_dict(m, a, esn0, world):
+    """The `config` object of the JSON line -- built by ONE function for both arms, so that they name the same workload key by key."""
+    B, S, U = a.batch, m["Nsymb"], min(a.unique, a.batch)
+    return {"workload": workload_name(m, a, esn0, world), "frames_total": world * B, "decoder": a.decoder,
+            "l2_policy": f"inputs {B * S * 272 * 8 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
+            "input": f"{U} distinct host-synthesised frames tiled to {B}, independent AWGN per frame (torch.randn on device)",
+            "parallelism": f"frame shards x{world}, tables broadcast once ({'NCCL' if world > 1 else 'local'}), no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -121,11 +141,21 @@ def _cpu_oracle(cfg, iters):
     return port.Port(cfg, iters), "port"
 
 
-def _cpu_worker(args):
-    cfg, iters, x = args
-    o, _ = _cpu_oracle(cfg, iters)
-    secs, pay, dec, its = o.rx_tail_timed(x.astype(np.complex128))
-    return secs, int(dec.sum()), x.shape[0]
+_W = {}  # per-worker state of the reference arm: the reference object (built ONCE, in the pool initializer) and the frames
+
+
+def _cpu_worker_init(cfg, iters):
+    _W["o"], _ = _cpu_oracle(cfg, iters)   # load_configuration() and all table set-up happen here, outside every timed region
+
+
+def _cpu_worker(job):
+    lo, hi = job
+    x = _W_FRAMES[lo:hi]                   # inherited through fork: nothing is pickled per step
+    secs, pay, dec, its = _W["o"].rx_tail_timed(x)
+    return secs, int(dec.sum()), hi - lo
+
+
+_W_FRAMES = None
 
 
 def cpu_baseline_sample(cfg, iters, x_sample, pl_sample):
@@ -140,38 +170,47 @@ def cpu_baseline_sample(cfg, iters, x_sample, pl_sample):
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores (rank 0 only).  One forked worker per core
+    (the reference is not thread-safe), each building its reference object ONCE; a step = every worker decoding its share of a
+    bounded sample of the own arm's workload (same generator, mode, -I, Es/N0); only decoding is inside the timed region."""
+    global _W_FRAMES
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
 
     import mercury_b200 as mb
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
     m = mb.MODES[a.config]
     esn0 = a.esn0 if a.esn0 is not None else m["thresh_db"] + 2.0
     cores = os.cpu_count() or 1
-    per_core = 128 if m["Nsymb"] >= 24 else 256  # bounded sample: a few seconds of CPU work per step
+    per_core = 128 if m["Nsymb"] >= 24 else 256  # bounded sample: about half a second of CPU work per core and step
     n = cores * per_core
     x, pl = mb.synth_frames(a.config, n, seed=1234, esn0_db=esn0)
+    _W_FRAMES = x.astype(np.complex128)
     _, kind = _cpu_oracle(a.config, a.iters)
     ctx = mp.get_context("fork")
-    times = []
-    with ctx.Pool(cores) as pool:
-        jobs = [(a.config, a.iters, x[i * per_core:(i + 1) * per_core]) for i in range(cores)]
+    times, busy = [], []
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(a.config, a.iters)) as pool:
+        jobs = [(i * per_core, (i + 1) * per_core) for i in range(cores)]
+        pool.map(_cpu_worker, jobs)  # every worker has run its initializer before the first timed step
         for step in range(a.warmup + a.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, jobs)
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
             if step >= a.warmup:
                 times.append(dt)
+                busy.append(max(r[0] for r in res))
     total = float(np.sum(times))
     value = n * len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(m, a, esn0), "sample_frames_per_step": n},
+        "data": "synthetic", "config": config_dict(m, a, esn0, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{n} frames per step ({per_core} per core, one forked worker per core), same generator and Es/N0 as the GPU arm"},
+                         "sample": f"{n} frames per step ({per_core} per core, one forked worker per core with its reference object built once "
+                                   f"before the timed steps), same generator and Es/N0 as the GPU arm; wall clock of the step "
+                                   f"{1e3 * total / len(times):.0f} ms, slowest worker's own decode time {1e3 * float(np.mean(busy)):.0f} ms"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,6 +243,46 @@ def synth_batch_on_device(config, B, esn0_db, dev, seed, unique=4096):
     del d_clean
     pl_all = np.tile(pl_u, ((B + U - 1) // U, 1))[:B]
     return d_x, pl_all
+
+
+def side_config(ts, mb, torch, dev, cfg, iters, B, esn0, stream):
+    """One BASELINE configuration besides the headline, device-resident: frames/s, stage times, integrity.  -> dict"""
+    m = mb.MODES[cfg]
+    geom = ts.load_configuration(cfg, iters)
+    esn0 = m["thresh_db"] + 2.0 if esn0 is None else esn0
+    d_x, pl = synth_batch_on_device(cfg, B, esn0, dev, seed=0x5EED + cfg, unique=2048)
+    fb = geom["frame_bytes"]
+    d_pay = torch.zeros((B, fb), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros((B, 32), dtype=torch.uint8, device=dev)
+    d_llr = torch.empty((B, mb.HANDOFF_FLOATS), dtype=torch.float32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    td = tl = 0.0
+    reps = 3
+    for i in range(reps + 1):
+        ev[0].record()
+        ts.demod_batch_device(d_x, B, d_llr, d_st, None, stream=stream)
+        ev[1].record()
+        ts.ldpc_decode_batch_device(d_llr, B, d_pay, d_st, stream=stream)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if i > 0:
+            td += ev[0].elapsed_time(ev[1]) / reps
+            tl += ev[1].elapsed_time(ev[2]) / reps
+    st = d_st.cpu().numpy().view(mb.STATS_DTYPE).reshape(-1)
+    pay = d_pay.cpu().numpy()
+    dec = st["message_decoded"] == 1
+    its = np.clip(st["iterations_done"], 0, iters).astype(np.float64)
+    peak = 6545.9
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    return {"workload": f"mode {cfg}, LDPC {m['rate_num']}/16, -I {iters}, batch {B}, AWGN Es/N0 {esn0:g} dB", "frames_per_s": B / ((td + tl) * 1e-3),
+            "demod_ms": td, "demod_gbs": m["demod_bytes"] * B / (td * 1e-3) / 1e9, "demod_frac_of_hbm_peak": m["demod_bytes"] * B / (td * 1e-3) / 1e9 / peak,
+            "ldpc_ms": tl, "ldpc_edge_updates_per_s": float(its.sum()) * m["edges"] / (tl * 1e-3), "mean_iterations": float(its.mean()),
+            "fer": float(1.0 - dec.mean()), "payload_mismatches_among_decoded": int((pay[dec] != pl[dec]).any(axis=1).sum()),
+            "note": "frames the reference also rejects count in fer (mode 16 at 18 dB: the reference's ZF noise variance makes its decoder a hard-decision "
+                    "pass-through, SURVEY.md 7); parity with the reference on these configurations: profiles/r2_baseline_configs.log"}
 
 
 def run_own(a):
@@ -270,12 +349,16 @@ def run_own(a):
     ms_total = float(ms.item())
     value = world * B * a.steps / (ms_total * 1e-3)
 
-    # ---- integrity of what was just timed ----------------------------------------------------------------------
+    # ---- integrity of what was just timed: EVERY rank checks its shard against the payloads it synthesised, totals over ranks -------
     st = d_st.cpu().numpy().view(mb.STATS_DTYPE).reshape(-1)
     pay = d_pay.cpu().numpy()
     dec = st["message_decoded"] == 1
     mism = int((pay[dec] != pl_all[dec]).any(axis=1).sum())
     its_run = np.clip(st["iterations_done"], 0, a.iters).astype(np.float64)
+    integ = torch.tensor([float(dec.sum()), float(B), float(mism), float(its_run.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(integ, op=dist.ReduceOp.SUM)
+    tot_dec, tot_frames, tot_mism, tot_its = (float(v) for v in integ.tolist())
 
     # ---- per-kernel timing (same stream, same inputs): roofline of the demod stage, edge rate of the decoder ----
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -311,38 +394,98 @@ def run_own(a):
                 "traffic": traffic, "algorithmic_bytes_per_frame": m["demod_bytes"], "peak_source": peak_src,
                 "kernel_ms": 1e3 * t_demod_s, "share_of_step": t_demod_s / (t_demod_s + t_ldpc_s)}
     edge_updates = float(its_run.sum()) * m["edges"]
+    sm_mhz = clocks.summary()["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    winst = None
+    try:
+        winst = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"ldpc_mode{a.config}_{a.decoder}_warp_inst_per_frame")
+    except Exception:
+        pass
+    issue_peak = n_sm * 4 * sm_mhz * 1e6                 # warp instructions / s: one per SM sub-partition and clock
+    xu_peak = n_sm * 16 * sm_mhz * 1e6                   # MUFU lane-operations / s: 16 XU lanes per SM
     ldpc = {"kernel": "mb_ldpc_kernel", "decoder": a.decoder, "edge_updates_per_s": edge_updates / t_ldpc_s, "kernel_ms": 1e3 * t_ldpc_s,
             "edges": m["edges"], "mean_iterations": float(its_run.mean()), "frames_per_s": B / t_ldpc_s,
             "hbm_gbs": B * (1600 * 4 + fb + 32 + 32) / t_ldpc_s / 1e9, "share_of_step": t_ldpc_s / (t_demod_s + t_ldpc_s),
-            # neither HBM nor tensor bound: the decoder's state lives in shared memory for all iterations.  What bounds it is instruction
-            # issue (ncu: smsp__issue_active 84 %, XU pipe 61 % busy from 6 MUFU per edge and iteration), see DESIGN.md section 4 (K_ldpc)
-            "bound": "instruction issue", "evidence": "profiles/r1q_ncu_full.txt (ncu --set full of this kernel)"}
+            # neither HBM nor tensor bound: the decoder's state lives in shared memory for all iterations.  What bounds it is instruction issue
+            # and the latency of its dependent MUFU / shared-memory chains, so it is reported against the issue-slot and XU-pipe rooflines
+            # (K_ldpc): warp instructions per frame come from the committed ncu capture of this kernel on this workload.
+            "bound": "instruction issue",
+            "roofline": {"bound": "issue", "unit": "warp-inst/s", "peak": issue_peak,
+                         "achieved": None if winst is None else winst * B / t_ldpc_s,
+                         "frac": None if winst is None else winst * B / t_ldpc_s / issue_peak,
+                         "warp_inst_per_frame": winst, "sm_mhz": sm_mhz, "sms": n_sm,
+                         "thread_inst_per_edge_update": None if winst is None else winst * 32 * B / edge_updates,
+                         "xu": {"unit": "MUFU lane-op/s", "peak": xu_peak, "mufu_per_edge_update": 3 if a.decoder == "spa" else 0,
+                                "achieved_at_least": (3 if a.decoder == "spa" else 0) * edge_updates / t_ldpc_s,
+                                "frac_at_least": (3 if a.decoder == "spa" else 0) * edge_updates / t_ldpc_s / xu_peak}},
+            "evidence": "profiles/r2_ncu_full.txt (ncu --set full of this kernel), profiles/ncu_traffic.json"}
 
     # ---- e2e: host buffers through the C-ABI batch call (pinned memory; H2D + kernels + D2H timed) --------------
+    # The call is bound by the H2D copy of the samples, so it is measured with the 4-byte sample format the ABI offers for exactly that
+    # reason (complex int16, mercury_b200_demod_decode_batch_fmt) -- the headline -- and with complex64; next to them the box's own
+    # ceiling: the same bytes copied pinned-host -> device by all ranks at once, nothing else running.
     e2e = None
     if not a.no_e2e:
-        h_x = torch.empty((B, S, 272), dtype=torch.complex64, pin_memory=True)
-        h_x.copy_(d_x)
-        h_pay = torch.zeros((B, fb), dtype=torch.uint8, pin_memory=True)
-        h_st = torch.zeros((B, 32), dtype=torch.uint8, pin_memory=True)
-        hx, hp, hs = h_x.numpy(), h_pay.numpy(), h_st.numpy().view(mb.STATS_DTYPE).reshape(-1)
-        for _ in range(min(2, a.warmup)):
-            ts.demod_decode_batch(hx, out=(hp, hs))
-        barrier()
-        clocks.start()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            ts.demod_decode_batch(hx, out=(hp, hs))  # returns after its streams are synchronised
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        clocks.stop()
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e_mism = int((hp[hs["message_decoded"] == 1] != pl_all[hs["message_decoded"] == 1]).any(axis=1).sum())
-        e2e = {"value": world * B * a.steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(B * S * 256 * 8),  # the guard interval is skipped by the strided H2D copy
-               "d2h_bytes_per_step": int(B * (fb + 32)), "payload_mismatches": e2e_mism,
-               "api": "mercury_b200_demod_decode_batch (pinned host buffers, 3-slot chunk pipeline, GI-free strided H2D)"}
-        del h_x
+        Be = min(B, 65536)  # frames of the batch that go through the host path (keeps pinned host memory per rank at 3.4 GB)
+        peak_abs = float(d_x[:Be].abs().max().item())
+        scale = peak_abs / 32000.0
+        h_q = torch.empty((Be, S, 272, 2), dtype=torch.int16, pin_memory=True)
+        h_q.copy_(torch.round(torch.view_as_real(d_x[:Be]) / scale).to(torch.int16))
+        h_x = torch.empty((Be, S, 272), dtype=torch.complex64, pin_memory=True)
+        h_x.copy_(d_x[:Be])
+        h_pay = torch.zeros((Be, fb), dtype=torch.uint8, pin_memory=True)
+        h_st = torch.zeros((Be, 32), dtype=torch.uint8, pin_memory=True)
+        hq, hx, hp, hs = h_q.numpy(), h_x.numpy(), h_pay.numpy(), h_st.numpy().view(mb.STATS_DTYPE).reshape(-1)
+
+        def timed_host(buf, **kw):
+            for _ in range(min(2, a.warmup)):
+                ts.demod_decode_batch(buf, out=(hp, hs), **kw)
+            barrier()
+            clocks.start()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                ts.demod_decode_batch(buf, out=(hp, hs), **kw)  # returns after its streams are synchronised
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            clocks.stop()
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            ok = hs["message_decoded"] == 1
+            bad = torch.tensor([float((hp[ok] != pl_all[:Be][ok]).any(axis=1).sum()), float(ok.sum())], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+            return world * Be * a.steps / float(dt.item()), int(bad[0].item()), int(bad[1].item())
+
+        v16, mism16, dec16 = timed_host(hq, scale=scale)
+        v64, mism64, dec64 = timed_host(hx)
+        # concurrent H2D ceiling: the int16 batch's useful bytes (guard interval skipped), all ranks together, best of 3
+        n16 = Be * S * 256 * 2
+        d_tmp = torch.empty(n16, dtype=torch.int16, device=dev)
+        src = h_q.view(-1)[:n16]  # contiguous pinned memory: one DMA, no staging
+        best = None
+        for _ in range(3):
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            d_tmp.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        h2d16 = int(Be * S * 256 * 4)
+        ceil_gbs = h2d16 / (best * 1e-3) / 1e9
+        e2e = {"value": v16, "unit": UNIT, "h2d_bytes_per_step": h2d16,  # the guard interval is skipped by the strided H2D copy
+               "d2h_bytes_per_step": int(Be * (fb + 32)), "frames_per_step_per_gpu": int(Be), "payload_mismatches": mism16, "frames_decoded": dec16,
+               "sample_format": f"complex int16 (MERCURY_B200_BASEBAND_CI16, scale {scale:.3e}: full scale = 1.024 x the batch's peak)",
+               "api": "mercury_b200_demod_decode_batch_fmt (pinned host buffers, 3-slot chunk pipeline, GI-free strided H2D)",
+               "complex64": {"value": v64, "h2d_bytes_per_step": int(Be * S * 256 * 8), "payload_mismatches": mism64, "frames_decoded": dec64,
+                             "api": "mercury_b200_demod_decode_batch"},
+               "h2d_ceiling": {"gbs_per_gpu": ceil_gbs, "gbs_all_gpus": ceil_gbs * world, "frames_per_s": world * Be / (best * 1e-3),
+                               "frac_of_ceiling": v16 / (world * Be / (best * 1e-3)),
+                               "how": "the same number of bytes, one contiguous pinned-host -> device copy per rank, all ranks at once, nothing else running (best of 3)"}}
+        del h_x, h_q, d_tmp
 
     # ---- the drop-in call itself: one synchronised frame per call, like the reference's receive_byte() ----
     single = None
@@ -358,6 +501,11 @@ def run_own(a):
         single = {"median_us": float(np.median(lat) * 1e6), "p99_us": float(np.percentile(lat, 99) * 1e6),
                   "api": "mercury_b200_receive_baseband (double samples in, int bytes out, H2D + 2 kernels + D2H per call)"}
 
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_frames > 0:
+        n = min(a.cpu_frames, B)
+        cpu = cpu_baseline_sample(a.config, a.iters, d_x[:n].cpu().numpy(), pl_all[:n])
+
     # ---- next row: the WHOLE receive_byte(), pass-band captures in, front-end + tail on the GPU --------------
     receive_byte = None
     if rank == 0 and world == 1 and not a.no_e2e:
@@ -369,24 +517,34 @@ def run_own(a):
         except Exception as e:  # never let the extra leg take the headline line down
             receive_byte = {"error": repr(e)}
 
-    cpu = None
-    if rank == 0 and world == 1 and a.cpu_frames > 0:
-        n = min(a.cpu_frames, B)
-        cpu = cpu_baseline_sample(a.config, a.iters, d_x[:n].cpu().numpy(), pl_all[:n])
+    # ---- the other BASELINE configurations, one line each (device-resident, same kernels; parity on them: tools/run_baseline_configs.py) ----
+    other = None
+    if rank == 0 and world == 1 and not a.no_extra and a.config == 8:
+        other = {}
+        for name, cfg, iters2, B2, esn0_2 in (("config2_mode9_rate_8_16", 9, 50, 65536, None), ("config3_mode16", 16, 20, 262144, 18.0)):
+            try:
+                del d_x
+            except NameError:
+                pass
+            torch.cuda.empty_cache()
+            try:
+                other[name] = side_config(ts, mb, torch, dev, cfg, iters2, B2, esn0_2, stream)
+            except Exception as e:  # never let an extra leg take the headline line down
+                other[name] = {"error": repr(e)}
+        ts.load_configuration(a.config, a.iters)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(m, a, esn0), "frames_total": world * B, "decoder": a.decoder,
-                       "l2_policy": f"inputs {B * S * 272 * 8 / 1e9:.2f} GB per GPU >> 126 MB L2 (no flush needed)",
-                       "input": f"{U} distinct host-synthesised frames tiled to {B}, independent AWGN per frame (torch.randn on device)",
-                       "parallelism": f"frame shards x{world}, tables broadcast once ({'NCCL' if world > 1 else 'local'}), no data-path collective"},
+            "config": config_dict(m, a, esn0, world),
             "roofline": roofline, "ldpc": ldpc, "cpu_baseline": cpu, "e2e": e2e, "single_frame_call": single, "receive_byte": receive_byte, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "integrity": {"frames_decoded": int(dec.sum()), "frames": int(B), "payload_mismatches_among_decoded": mism,
-                          "fer": float(1.0 - dec.mean())},
+            "integrity": {"frames_decoded": int(tot_dec), "frames": int(tot_frames), "payload_mismatches_among_decoded": int(tot_mism),
+                          "fer": float(1.0 - tot_dec / tot_frames), "ranks_checked": world,
+                          "note": "every rank compares its shard with the payloads it synthesised; totals over all ranks"},
+            "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

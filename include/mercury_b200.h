@@ -126,6 +126,23 @@ int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *baseband, si
 				    mercury_b200_rx_stats *stats, float *llr_cw);
 int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_payload,
 					   void *d_stats, void *d_llr_cw, void *stream);
+/*
+ * The same two calls for narrower base-band samples.  A host batch is bound by the PCIe link (H2D of the samples), so the
+ * bytes per sample are the throughput of the call: 4-byte complex samples double it against complex64.
+ *   MERCURY_B200_BASEBAND_C64   interleaved (re, im) float32 -- what the calls above take
+ *   MERCURY_B200_BASEBAND_CI16  interleaved (re, im) int16; sample = integer x scale (what a fixed-point front-end / ADC delivers)
+ *   MERCURY_B200_BASEBAND_CF16  interleaved (re, im) IEEE binary16 (scale ignored)
+ * The kernel widens the samples to float32 in its load; everything after that is the arithmetic of the complex64 call, i.e. the
+ * result is that of the reference on the same quantised values (parity tests feed the reference exactly those, as doubles).
+ * OFDM configurations only (the ROBUST / MFSK tail takes complex64).
+ */
+#define MERCURY_B200_BASEBAND_C64 0
+#define MERCURY_B200_BASEBAND_CI16 1
+#define MERCURY_B200_BASEBAND_CF16 2
+int mercury_b200_demod_decode_batch_fmt(mercury_b200_t *h, const void *baseband, int sample_format, float scale, size_t n_frames,
+					uint8_t *payload, mercury_b200_rx_stats *stats, float *llr_cw);
+int mercury_b200_demod_decode_batch_device_fmt(mercury_b200_t *h, const void *d_baseband, int sample_format, float scale, size_t n_frames,
+					       void *d_payload, void *d_stats, void *d_llr_cw, void *stream);
 /* The two stages separately (device buffers). d_llr is the stage hand-off: n_frames x MERCURY_B200_HANDOFF_FLOATS float32
  * (LLRs in the decoder's internal layout, then -- ZF modes only -- the equalised data symbols the decoder's SNR report needs). */
 int mercury_b200_demod_batch_device(mercury_b200_t *h, const void *d_baseband, size_t n_frames, void *d_llr, void *d_stats,
@@ -242,7 +259,7 @@ int mercury_b200_transmit_byte_batch_device(mercury_b200_t *h, const void *d_pay
  * common_defines.h:63-65: 32-MFSK x1 / 16-MFSK x2, LDPC 1/16, 1/16, 4/16): the batch and single-frame TAIL entry points above then run the
  * MFSK branch of the tail (telecom_system.cc:1132-1198: symbol_demod + cl_mfsk::demod, mfsk.cc:305-390) in front of the same decoder, on
  * Nsymb = 320 / 200 / 200 synchronised symbols per frame; SNR reads 0 for a decoded frame like the reference's.  The pass-band entry
- * points (receive_byte / transmit_byte) remain OFDM-only.
+ * points (receive_byte / transmit_byte and their batch forms) run the MFSK branches of the reference in these configurations as well.
  * The tone-pattern detectors work on base-band buffers at the pass-band rate (baseband_data_interpolated), n_samples complex samples each:
  *   time_sync_delay            int cl_ofdm::time_sync_mfsk(...)            ofdm.cc:1969-2065 (preamble tones of the loaded configuration)
  *   ack_metric / ack_matched   double cl_ofdm::detect_ack_pattern(...)     ofdm.cc:2067-2186 with mfsk.ack_tones   (mfsk.cc:113-136)

@@ -72,6 +72,8 @@ def lib():
         "mercury_b200_get_frame_size_bits": (i32, [vp]),
         "mercury_b200_demod_decode_batch": (i32, [vp, vp, sz, vp, vp, vp]),
         "mercury_b200_demod_decode_batch_device": (i32, [vp, vp, sz, vp, vp, vp, vp]),
+        "mercury_b200_demod_decode_batch_fmt": (i32, [vp, vp, i32, C.c_float, sz, vp, vp, vp]),
+        "mercury_b200_demod_decode_batch_device_fmt": (i32, [vp, vp, i32, C.c_float, sz, vp, vp, vp, vp]),
         "mercury_b200_demod_batch_device": (i32, [vp, vp, sz, vp, vp, vp, vp]),
         "mercury_b200_ldpc_decode_batch_device": (i32, [vp, vp, sz, vp, vp, vp]),
         "mercury_b200_set_debug_capture": (i32, [vp, vp, vp, vp]),

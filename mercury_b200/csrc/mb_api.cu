@@ -184,9 +184,11 @@ int check_ready(mercury_b200_t *h)
 }
 
 int launch_demod(mercury_b200_t *h, const void *d_x, size_t n, void *d_llr, void *d_stats, void *d_llr_cw, size_t dbg_frame_off, cudaStream_t s,
-		 bool gi_removed = false)
+		 bool gi_removed = false, int fmt = MERCURY_B200_BASEBAND_C64, float scale = 1.0f)
 {
 	const MbMode &m = cur_mode(h);
+	if (fmt < MERCURY_B200_BASEBAND_C64 || fmt > MERCURY_B200_BASEBAND_CF16) return fail(h, MERCURY_B200_EINVAL, "unknown base-band sample format");
+	if (m.M == 200 && fmt != MERCURY_B200_BASEBAND_C64) return fail(h, MERCURY_B200_EINVAL, "the ROBUST (MFSK) tail takes complex64 samples");
 	if (m.M == 200) {  // ROBUST modes: FFT + non-coherent tone detection instead of the coherent OFDM demodulator
 		MbMfskArgs f;
 		memset(&f, 0, sizeof(f));
@@ -204,6 +206,8 @@ int launch_demod(mercury_b200_t *h, const void *d_x, size_t n, void *d_llr, void
 	a.x = static_cast<const float2 *>(d_x);
 	a.sym_stride = gi_removed ? MB_NFFT : MB_NOFDM;
 	a.sym_skip = gi_removed ? 0 : MB_NGI;
+	a.x_format = fmt;
+	a.x_scale = scale;
 	a.llr = static_cast<float *>(d_llr);
 	a.llr_cw = static_cast<float *>(d_llr_cw);
 	a.stats = static_cast<MbRxStats *>(d_stats);
@@ -475,6 +479,12 @@ int mercury_b200_ldpc_decode_batch_device(mercury_b200_t *h, const void *d_llr, 
 int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_x, size_t n, void *d_payload, void *d_stats, void *d_llr_cw,
 					   void *stream)
 {
+	return mercury_b200_demod_decode_batch_device_fmt(h, d_x, MERCURY_B200_BASEBAND_C64, 1.0f, n, d_payload, d_stats, d_llr_cw, stream);
+}
+
+int mercury_b200_demod_decode_batch_device_fmt(mercury_b200_t *h, const void *d_x, int fmt, float scale, size_t n, void *d_payload, void *d_stats,
+					       void *d_llr_cw, void *stream)
+{
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
@@ -488,23 +498,31 @@ int mercury_b200_demod_decode_batch_device(mercury_b200_t *h, const void *d_x, s
 		h->scratch_frames = n;
 	}
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	rc = launch_demod(h, d_x, n, h->d_scratch_llr, d_stats, d_llr_cw, 0, s);
+	rc = launch_demod(h, d_x, n, h->d_scratch_llr, d_stats, d_llr_cw, 0, s, false, fmt, scale);
 	if (rc) return rc;
 	return launch_ldpc(h, h->d_scratch_llr, n, d_payload, d_stats, s);
 }
 
 int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *x, size_t n, uint8_t *payload, mercury_b200_rx_stats *stats, float *llr_cw)
 {
+	return mercury_b200_demod_decode_batch_fmt(h, x, MERCURY_B200_BASEBAND_C64, 1.0f, n, payload, stats, llr_cw);
+}
+
+int mercury_b200_demod_decode_batch_fmt(mercury_b200_t *h, const void *x, int fmt, float scale, size_t n, uint8_t *payload, mercury_b200_rx_stats *stats,
+					float *llr_cw)
+{
 	int rc = check_ready(h);
 	if (rc) return rc;
 	if (n == 0) return MERCURY_B200_OK;
 	if (!x || !payload || !stats) return fail(h, MERCURY_B200_EINVAL, "null host buffer");
+	if (fmt < MERCURY_B200_BASEBAND_C64 || fmt > MERCURY_B200_BASEBAND_CF16) return fail(h, MERCURY_B200_EINVAL, "unknown base-band sample format");
 	const MbMode &m = cur_mode(h);
-	const size_t frame_x = (size_t)m.Nsymb * MB_NOFDM * sizeof(float2);
+	const size_t esz = fmt == MERCURY_B200_BASEBAND_C64 ? sizeof(float2) : 4;  // bytes per complex sample
+	const size_t frame_x = (size_t)m.Nsymb * MB_NOFDM * esz;
 	// The guard interval never crosses PCIe: a strided (2-D) copy moves the 2,048 useful bytes of every 2,176-byte symbol, so the
 	// device copy of a chunk is [frames][Nsymb][256] and the demodulator is told that the GI is already gone (-5.9 % of the bytes
 	// of the link that bounds this path).
-	const size_t sym_in = MB_NOFDM * sizeof(float2), sym_dev = MB_NFFT * sizeof(float2), gi = MB_NGI * sizeof(float2);
+	const size_t sym_in = MB_NOFDM * esz, sym_dev = MB_NFFT * esz, gi = MB_NGI * esz;
 	// chunks of ~64 MB of samples: large enough to fill the GPU (>= 8 CTAs per SM), small enough to pipeline
 	size_t chunk = std::max<size_t>(1184, (64u << 20) / frame_x);
 	chunk = std::min(chunk, n);
@@ -520,7 +538,7 @@ int mercury_b200_demod_decode_batch(mercury_b200_t *h, const float *x, size_t n,
 		MB_CUDA(h, cudaEventSynchronize(s.done));
 		MB_CUDA(h, cudaMemcpy2DAsync(s.d_x, sym_dev, reinterpret_cast<const uint8_t *>(x) + done * frame_x + gi, sym_in, sym_dev, c * (size_t)m.Nsymb,
 					     cudaMemcpyHostToDevice, s.stream));
-		rc = launch_demod(h, s.d_x, c, s.d_llr, s.d_stats, llr_cw ? s.d_llr_cw : nullptr, done, s.stream, /*gi_removed=*/true);
+		rc = launch_demod(h, s.d_x, c, s.d_llr, s.d_stats, llr_cw ? s.d_llr_cw : nullptr, done, s.stream, /*gi_removed=*/true, fmt, scale);
 		if (rc) return rc;
 		rc = launch_ldpc(h, s.d_llr, c, s.d_payload, s.d_stats, s.stream);
 		if (rc) return rc;

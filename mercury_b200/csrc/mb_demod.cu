@@ -1,4 +1,4 @@
-// mb_demod.cu -- K_demod: fused OFDM demodulator for sm_100a; persistent CTAs fed by the bulk-copy (TMA) engine.
+// mb_demod.cu -- K_demod: fused OFDM demodulator for sm_100a; one CTA per frame, streaming 8-byte loads in, one bulk (TMA engine) store out.
 //
 //   FFT-256 per symbol  ->  AGC  ->  LS / ZF channel estimate  ->  column interpolation  ->  (phase-only)
 //   equalise  ->  pilot noise variance  ->  deframe + T/F de-interleave  ->  max-log soft de-map  ->
@@ -32,6 +32,8 @@
 //   (A persistent variant fed by a cp.async.bulk ring was measured first: 74 KB of shared memory per CTA left 2 CTAs per
 //    SM and 29 % of the HBM roofline, profiles/r1e_ncu_full_demod_tma_persistent.txt; occupancy wins on this kernel.)
 #include "mb_fft.cuh"
+#include <cuda_fp16.h>
+
 #include "mb_kernels.cuh"
 
 namespace {
@@ -133,7 +135,7 @@ struct Geo {
 	static_assert(OFF_L % 16 == 0 && OFF_Y % 16 == 0 && OFF_ZF % 16 == 0 && OFF_PM % 16 == 0, "alignment");
 };
 
-template <int S, int M, bool LS, bool PHASE>
+template <int S, int M, bool LS, bool PHASE, bool NARROW>
 __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const MbDemodArgs a)
 {
 	using G = Geo<S>;
@@ -185,19 +187,38 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		// is this kernel's busiest unit, the FMA pipe is not.  The table's 1/256 (ofdm.cc:439-442) moves to the 4 outputs.
 		const float2 w1 = cscale(__ldg(reinterpret_cast<const float2 *>(a.blob + a.off_twiddle) + 16 + t), 256.0f);
 		const size_t stride = (size_t)a.sym_stride;
-		const float2 *__restrict__ xs = a.x + (frame * S + (size_t)(active ? grp : 0)) * stride + a.sym_skip + t;
+		// sample formats of the input (MbDemodArgs::x_format): complex64, or (NARROW instantiations) 4-byte samples -- complex int16
+		// (x a.x_scale) / complex fp16 -- that halve the bytes a host batch moves over PCIe; converted here, in the load, to the float2
+		// the rest of the kernel works on
+		const int fmt = NARROW ? a.x_format : 0;
+		constexpr unsigned esz = NARROW ? 4u : 8u;
+		const char *__restrict__ xs = reinterpret_cast<const char *>(a.x) + ((frame * S + (size_t)(active ? grp : 0)) * stride + a.sym_skip + t) * esz;
 		if (NCH > 1 && active) {  // later rounds: one 128-byte line per thread into L2 while round 0 is in flight
-			const char *line = reinterpret_cast<const char *>(a.x + (frame * S + (size_t)grp) * stride + a.sym_skip) + t * 128;
+			const char *line = reinterpret_cast<const char *>(a.x) + ((frame * S + (size_t)grp) * stride + a.sym_skip) * esz + t * 128;
 #pragma unroll
 			for (int ch = 1; ch < NCH; ch++)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(line + (size_t)ch * SC * stride * 8));
+				if (!NARROW || t < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(line + (size_t)ch * SC * stride * esz));
 		}
 #pragma unroll 1
-		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * stride) {
+		for (int ch = 0; ch < NCH; ch++, xs += (size_t)SC * stride * esz) {
 			float2 v[16];
 			if (active) {
+				if (!NARROW) {
 #pragma unroll
-				for (int n1 = 0; n1 < 16; n1++) v[n1] = ld_stream(xs + 16 * n1);  // x[16 n1 + t], GI skipped
+					for (int n1 = 0; n1 < 16; n1++) v[n1] = ld_stream(reinterpret_cast<const float2 *>(xs) + 16 * n1);  // x[16 n1 + t], GI skipped
+				} else {
+					uint32_t w[16];
+#pragma unroll
+					for (int n1 = 0; n1 < 16; n1++) w[n1] = ld_stream_b32(reinterpret_cast<const uint32_t *>(xs) + 16 * n1);
+					if (fmt == 1) {
+						const float sc = a.x_scale;
+#pragma unroll
+						for (int n1 = 0; n1 < 16; n1++) v[n1] = make_float2((float)(short)(w[n1] & 0xFFFFu) * sc, (float)(short)(w[n1] >> 16) * sc);
+					} else {
+#pragma unroll
+						for (int n1 = 0; n1 < 16; n1++) v[n1] = __half22float2(*reinterpret_cast<const __half2 *>(&w[n1]));
+					}
+				}
 				float2 A[16];
 				fft16(v, A);
 				buf[t * 17] = A[0];
@@ -440,12 +461,14 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 // launch plumbing: one instantiation per (Nsymb, M, estimator, phase-only) combination of the 17 modes
 // ------------------------------------------------------------------------------------------------------------------
 struct Variant {
-	int S, M, ls, phase;
+	int S, M, ls, phase, narrow;
 	const void *fn;
 	int threads, smem, ctas_per_sm;
 };
 
-#define MB_VARIANT(S, M, LS, PH) {S, M, LS, PH, (const void *)mb_demod_kernel<S, M, LS, PH>, Geo<S>::T, Geo<S>::SMEM, 0}
+#define MB_VARIANT(S, M, LS, PH)                                                                                   \
+	{S, M, LS, PH, 0, (const void *)mb_demod_kernel<S, M, LS, PH, false>, Geo<S>::T, Geo<S>::SMEM, 0},         \
+	{S, M, LS, PH, 1, (const void *)mb_demod_kernel<S, M, LS, PH, true>, Geo<S>::T, Geo<S>::SMEM, 0}
 Variant g_variants[] = {
 	MB_VARIANT(48, 2, true, true),    // CONFIG_0..6   BPSK
 	MB_VARIANT(24, 4, true, true),    // CONFIG_7..9,12 QPSK
@@ -456,10 +479,10 @@ Variant g_variants[] = {
 };
 int g_num_sms = 0;
 
-Variant *find_variant(const MbMode &m)
+Variant *find_variant(const MbMode &m, int narrow = 0)
 {
 	for (Variant &v : g_variants)
-		if (v.S == m.Nsymb && v.M == m.M && v.ls == (m.estimator == 1) && v.phase == (m.phase_only != 0)) return &v;
+		if (v.S == m.Nsymb && v.M == m.M && v.ls == (m.estimator == 1) && v.phase == (m.phase_only != 0) && v.narrow == narrow) return &v;
 	return nullptr;
 }
 
@@ -493,7 +516,7 @@ int mb_demod_ctas_per_sm(int Nsymb, int M, int estimator, int phase_only)
 cudaError_t mb_launch_demod(const MbDemodArgs &a, size_t n_frames, cudaStream_t stream)
 {
 	if (n_frames == 0) return cudaSuccess;
-	const Variant *v = find_variant(a.mode);
+	const Variant *v = find_variant(a.mode, a.x_format != 0 ? 1 : 0);
 	if (!v || g_num_sms <= 0) return cudaErrorInvalidDeviceFunction;
 	// bulk copies need 16-byte aligned global addresses; frames are multiples of 16 bytes, so only the bases matter
 	if ((reinterpret_cast<uintptr_t>(a.x) & 15u) || (reinterpret_cast<uintptr_t>(a.llr) & 15u)) return cudaErrorMisalignedAddress;

@@ -3,6 +3,7 @@
 // translation unit compiled WITHOUT -ftz (see the Makefile: under FTZ ptxas no longer folds negations into the packed operands).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace mbfft {
 
@@ -29,6 +30,12 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p)
 {
 	float2 r;
 	asm("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_b32(const uint32_t *p)
+{
+	uint32_t r;
+	asm("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
 	return r;
 }
 __device__ __forceinline__ float cnorm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }

@@ -18,6 +18,8 @@ struct MbDemodArgs {
 	const float2 *x;       // [B][Nsymb][sym_stride] complex64 baseband, preamble stripped; the 256 useful samples start at sym_skip
 	int32_t sym_stride;    // 272 = symbols as delivered (guard interval present, skipped: sym_skip 16); 256 = guard interval already removed
 	int32_t sym_skip;
+	int32_t x_format;      // 0: complex64; 1: complex int16 (re, im; value = int x x_scale); 2: complex fp16 -- MERCURY_B200_BASEBAND_*
+	float x_scale;
 	float *llr;            // [B][1600] LLRs in the hand-off layout (internal variable order, 32-float rows rotated: MB_HANDOFF)
 	float *llr_cw;         // optional [B][1600] LLRs in codeword order (parity output)
 	MbRxStats *stats;      // [B]

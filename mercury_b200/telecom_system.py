@@ -19,6 +19,7 @@ from ._lib import Geometry, ReceiveStats, RxStats
 
 YES, NO = 1, 0
 DECODER_SPA, DECODER_MINSUM = 0, 1
+BASEBAND_C64, BASEBAND_CI16, BASEBAND_CF16 = 0, 1, 2  # MERCURY_B200_BASEBAND_*: base-band sample formats of the batch calls
 HANDOFF_FLOATS = 2400  # MERCURY_B200_HANDOFF_FLOATS: float32 per frame of the stage hand-off buffer between the two kernels
 
 STATS_DTYPE = np.dtype([("iterations_done", "<i4"), ("crc", "<i4"), ("all_zeros", "<i4"), ("message_decoded", "<i4"),
@@ -282,14 +283,16 @@ class TelecomSystemB200:
                                                                     int(out_format), C.c_void_p(stream)))
 
     # ---- batched entry points ----------------------------------------------------------------------------
-    def demod_decode_batch(self, baseband, want_llr=False, out=None):
-        """Host buffers: baseband [B, Nsymb, 272] complex64 (or float32 [..., 2]). Returns (payload[B,frame_bytes] u8, stats[B], llr_cw|None)."""
+    def demod_decode_batch(self, baseband, want_llr=False, out=None, scale=1.0):
+        """Host buffers: baseband [B, Nsymb, 272] complex64 (or float32 [..., 2]), or the 4-byte formats int16 [..., 2] (sample = integer x
+        scale) / float16 [..., 2].  Returns (payload[B,frame_bytes] u8, stats[B], llr_cw|None)."""
         g = self.geometry
         bb = np.ascontiguousarray(baseband)
         if bb.dtype == np.complex64:
             bb = bb.view(np.float32)
-        if bb.dtype != np.float32:
-            raise TypeError("baseband must be complex64 / float32")
+        fmt = {np.dtype(np.float32): BASEBAND_C64, np.dtype(np.int16): BASEBAND_CI16, np.dtype(np.float16): BASEBAND_CF16}.get(bb.dtype)
+        if fmt is None:
+            raise TypeError("baseband must be complex64 / float32, int16 or float16 (re, im interleaved)")
         per = g["Nsymb"] * g["Nofdm"] * 2
         if bb.size % per:
             raise ValueError("baseband size is not a whole number of frames")
@@ -300,12 +303,12 @@ class TelecomSystemB200:
         else:
             payload, stats = out
         llr = np.zeros((n, g["N"]), np.float32) if want_llr else None
-        self._check(self._L.mercury_b200_demod_decode_batch(self._h, _vp(bb), n, _vp(payload), _vp(stats), _vp(llr)))
+        self._check(self._L.mercury_b200_demod_decode_batch_fmt(self._h, _vp(bb), fmt, float(scale), n, _vp(payload), _vp(stats), _vp(llr)))
         return payload, stats, llr
 
-    def demod_decode_batch_device(self, d_baseband, n_frames, d_payload, d_stats, d_llr_cw=None, stream=0):
-        self._check(self._L.mercury_b200_demod_decode_batch_device(self._h, _vp(d_baseband), int(n_frames), _vp(d_payload),
-                                                                   _vp(d_stats), _vp(d_llr_cw), C.c_void_p(stream)))
+    def demod_decode_batch_device(self, d_baseband, n_frames, d_payload, d_stats, d_llr_cw=None, stream=0, sample_format=0, scale=1.0):
+        self._check(self._L.mercury_b200_demod_decode_batch_device_fmt(self._h, _vp(d_baseband), int(sample_format), float(scale), int(n_frames),
+                                                                       _vp(d_payload), _vp(d_stats), _vp(d_llr_cw), C.c_void_p(stream)))
 
     def demod_batch_device(self, d_baseband, n_frames, d_llr, d_stats, d_llr_cw=None, stream=0):
         self._check(self._L.mercury_b200_demod_batch_device(self._h, _vp(d_baseband), int(n_frames), _vp(d_llr), _vp(d_stats),
