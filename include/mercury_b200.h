@@ -101,6 +101,15 @@ int mercury_b200_load_tables(mercury_b200_t *h, const char *ldpc_table_path);
 /* Table blob exchange for multi-GPU start-up: rank 0 exports, broadcasts (NCCL), the others import. */
 int mercury_b200_export_tables(const mercury_b200_t *h, void *buf, size_t *size /* in: capacity, out: bytes */);
 int mercury_b200_import_tables(mercury_b200_t *h, const void *buf, size_t size);
+/*
+ * The same exchange as ONE call from C / C++ host code (north_star: "partitioned across GPUs only as independent frame shards via NCCL
+ * broadcast of the codeword tables"): every rank of `nccl_comm` (an ncclComm_t the host program created, one rank per
+ * handle / GPU -- several handles of one process with ncclCommInitAll, or one per process) calls this once; the root's handle must have
+ * its tables loaded (mercury_b200_load_tables), the others receive the blob over NCCL (NVLink / NVSwitch between the GPUs of a node),
+ * validate and import it.  `stream` is a cudaStream_t of the handle's device (NULL: the default stream).  After it, ranks process disjoint
+ * frame ranges with no further collective.  libnccl.so.2 is loaded on first use (dlopen): the library has no link-time NCCL dependency.
+ */
+int mercury_b200_broadcast_tables(mercury_b200_t *h, void *nccl_comm, int root, void *stream);
 /* Host-only table construction (no device needed): same blob as export_tables(). buf may be NULL to query size. */
 int mercury_b200_build_tables_host(const char *ldpc_table_path, void *buf, size_t *size);
 

@@ -70,6 +70,7 @@ def lib():
         "mercury_b200_get_geometry": (i32, [vp, C.POINTER(Geometry)]),
         "mercury_b200_get_frame_size_bytes": (i32, [vp]),
         "mercury_b200_get_frame_size_bits": (i32, [vp]),
+        "mercury_b200_broadcast_tables": (i32, [vp, vp, i32, vp]),
         "mercury_b200_demod_decode_batch": (i32, [vp, vp, sz, vp, vp, vp]),
         "mercury_b200_demod_decode_batch_device": (i32, [vp, vp, sz, vp, vp, vp, vp]),
         "mercury_b200_demod_decode_batch_fmt": (i32, [vp, vp, i32, C.c_float, sz, vp, vp, vp]),

@@ -4,6 +4,7 @@
 // Mirrors the reference's cl_telecom_system surface for the RX tail (see the header for file:line anchors).
 // There is deliberately no CPU implementation behind any compute entry point.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -398,6 +399,53 @@ int mercury_b200_import_tables(mercury_b200_t *h, const void *buf, size_t size)
 	h->blob.assign(static_cast<const uint8_t *>(buf), static_cast<const uint8_t *>(buf) + size);
 	MB_CUDA(h, cudaSetDevice(h->device));
 	return upload_blob(h);
+}
+
+// NCCL through dlopen: ncclBroadcast(sendbuff, recvbuff, count, ncclChar = 0, root, comm, stream), ncclCommUserRank(comm, int *)
+int mercury_b200_broadcast_tables(mercury_b200_t *h, void *comm, int root, void *stream)
+{
+	if (!h || !comm) return MERCURY_B200_EINVAL;
+	typedef int (*bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+	typedef int (*rank_fn)(void *, int *);
+	static bcast_fn p_bcast = nullptr;
+	static rank_fn p_rank = nullptr;
+	if (!p_bcast) {
+		void *so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!so) return fail(h, MERCURY_B200_EIO, std::string("libnccl.so.2 not found: ") + dlerror());
+		p_rank = reinterpret_cast<rank_fn>(dlsym(so, "ncclCommUserRank"));
+		p_bcast = reinterpret_cast<bcast_fn>(dlsym(so, "ncclBroadcast"));
+		if (!p_bcast || !p_rank) return fail(h, MERCURY_B200_EIO, "ncclBroadcast / ncclCommUserRank not found in libnccl");
+	}
+	MB_CUDA(h, cudaSetDevice(h->device));
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	int rank = -1;
+	if (p_rank(comm, &rank) != 0) return fail(h, MERCURY_B200_ECUDA, "ncclCommUserRank failed");
+	if (rank == root && h->blob.empty()) return fail(h, MERCURY_B200_ESTATE, "the root's tables are not loaded (mercury_b200_load_tables)");
+	unsigned long long *d_n = nullptr;
+	uint8_t *d_buf = nullptr;
+	unsigned long long n = rank == root ? (unsigned long long)h->blob.size() : 0ull;
+	MB_CUDA(h, cudaMalloc(&d_n, sizeof(n)));
+	MB_CUDA(h, cudaMemcpyAsync(d_n, &n, sizeof(n), cudaMemcpyHostToDevice, s));
+	if (p_bcast(d_n, d_n, sizeof(n), /*ncclChar*/ 0, root, comm, s) != 0) return fail(h, MERCURY_B200_ECUDA, "ncclBroadcast (size) failed");
+	MB_CUDA(h, cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, s));
+	MB_CUDA(h, cudaStreamSynchronize(s));
+	cudaFree(d_n);
+	if (n < sizeof(MbBlobHeader) || n > (64ull << 20)) return fail(h, MERCURY_B200_EINVAL, "broadcast table blob has an implausible size");
+	MB_CUDA(h, cudaMalloc(&d_buf, n));
+	if (rank == root) MB_CUDA(h, cudaMemcpyAsync(d_buf, h->blob.data(), n, cudaMemcpyHostToDevice, s));
+	if (p_bcast(d_buf, d_buf, n, 0, root, comm, s) != 0) return fail(h, MERCURY_B200_ECUDA, "ncclBroadcast (blob) failed");
+	int rc = MERCURY_B200_OK;
+	if (rank != root) {
+		std::vector<uint8_t> host(n);
+		MB_CUDA(h, cudaMemcpyAsync(host.data(), d_buf, n, cudaMemcpyDeviceToHost, s));
+		MB_CUDA(h, cudaStreamSynchronize(s));
+		rc = mercury_b200_import_tables(h, host.data(), host.size());  // validates the blob before anything dereferences it
+	} else {
+		MB_CUDA(h, cudaStreamSynchronize(s));
+	}
+	cudaFree(d_buf);
+	return rc;
 }
 
 int mercury_b200_load_configuration(mercury_b200_t *h, int config, int ldpc_iters)

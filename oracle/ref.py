@@ -34,18 +34,23 @@ class _RxOut(C.Structure):
     ]
 
 
-_lib = None
+_libs = {}
+# the same reference with receive_byte() re-pointed at libmercury_b200.so (oracle/dropin/make_patched.py, `make -C oracle dropin`)
+SO_DROPIN_TAIL = os.path.join(_HERE, "_ref", "libmercury_ref_tail.so")
+SO_DROPIN_WHOLE = os.path.join(_HERE, "_ref", "libmercury_ref_whole.so")
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            raise RuntimeError("oracle/_ref/libmercury_ref.so not built (make -C oracle ref; needs /root/reference)")
-        L = C.CDLL(_SO)
+def lib(so=None):
+    so = so or _SO
+    if so not in _libs:
+        if not os.path.exists(so):
+            raise RuntimeError(f"{so} not built (make -C oracle ref / dropin; needs /root/reference)")
+        L = C.CDLL(so)
         L.mref_create.restype = C.c_void_p
         L.mref_create.argtypes = [C.c_int, C.c_int]
         L.mref_destroy.argtypes = [C.c_void_p]
+        if hasattr(L, "mref_load_configuration"):
+            L.mref_load_configuration.argtypes = [C.c_void_p, C.c_int]
         L.mref_geometry.argtypes = [C.c_void_p, C.c_void_p]
         L.mref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.mref_ldpc_tables.argtypes = [C.c_int] + [C.c_void_p] * 5
@@ -88,8 +93,8 @@ def lib():
         L.mref_transmit_byte_nofilter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.mref_transmit_byte_nofilter.restype = C.c_int
         L.mref_fir_tx_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-        _lib = L
-    return _lib
+        _libs[so] = L
+    return _libs[so]
 
 
 def _p(a):
@@ -260,15 +265,26 @@ class Ref(FrontEndMixin):
 
     _fe = "mref_"
 
-    @staticmethod
-    def _felib():
-        return lib()
+    def _felib(self):
+        return self._L
 
-    def __init__(self, config, ldpc_iters=50):
-        self.h = lib().mref_create(config, ldpc_iters)
+    def __init__(self, config, ldpc_iters=50, so=None):
+        self._L = lib(so)
+        self.h = self._L.mref_create(config, ldpc_iters)
         self.config = config
         g = np.zeros(64, np.int32)
-        lib().mref_geometry(self.h, _p(g))
+        self._L.mref_geometry(self.h, _p(g))
+        self.geom = {k: int(g[i]) for i, k in enumerate(GEOM_FIELDS)}
+        self.__dict__.update(self.geom)
+        self.nReal = self.nBits - self.P
+        self.nVirtual = self.N - self.nBits
+
+    def load_configuration(self, config):
+        """cl_telecom_system::load_configuration(int) on this object (telecom_system.cc:2487); refreshes the geometry attributes."""
+        self._L.mref_load_configuration(self.h, config)
+        self.config = config
+        g = np.zeros(64, np.int32)
+        self._L.mref_geometry(self.h, _p(g))
         self.geom = {k: int(g[i]) for i, k in enumerate(GEOM_FIELDS)}
         self.__dict__.update(self.geom)
         self.nReal = self.nBits - self.P
@@ -276,7 +292,7 @@ class Ref(FrontEndMixin):
 
     def close(self):
         if self.h:
-            lib().mref_destroy(self.h)
+            self._L.mref_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -291,7 +307,7 @@ class Ref(FrontEndMixin):
         sc = np.zeros(self.N, np.int32)
         co = np.zeros(2 * self.M, np.float64)
         boost = np.zeros(1, np.float64)
-        lib().mref_tables(self.h, _p(ct), _p(ps), _p(sc), _p(co), _p(boost))
+        self._L.mref_tables(self.h, _p(ct), _p(ps), _p(sc), _p(co), _p(boost))
         return dict(carrier_type=ct.reshape(self.Nsymb, self.Nc), pilot_seq=ps, scrambler=sc,
                     constellation=co.view(np.complex128), pilot_boost=float(boost[0]))
 
@@ -301,7 +317,7 @@ class Ref(FrontEndMixin):
         info = np.zeros(self.nReal, np.int32)
         cw = np.zeros(self.N, np.int32)
         framed = np.zeros(self.Nsymb * self.Nc, np.complex128)
-        lib().mref_tx_baseband(self.h, _p(pl), len(pl), _p(out), _p(info), _p(cw), _p(framed))
+        self._L.mref_tx_baseband(self.h, _p(pl), len(pl), _p(out), _p(info), _p(cw), _p(framed))
         if want_aux:
             return out, dict(info_bits=info, codeword=cw, framed=framed.reshape(self.Nsymb, self.Nc))
         return out
@@ -317,7 +333,7 @@ class Ref(FrontEndMixin):
             payload=np.zeros(self.frame_bytes, np.int32), stats=np.zeros(8, np.float64),
         )
         o = _RxOut(*[_p(r[k]) for k in ("Y", "H", "Z", "llr_demod", "llr_cw", "bits", "bytes", "payload", "stats")])
-        lib().mref_rx_tail(self.h, _p(bb), C.byref(o))
+        self._L.mref_rx_tail(self.h, _p(bb), C.byref(o))
         st = r.pop("stats")
         r.update(iterations=int(st[0]), crc=int(st[1]), all_zeros=int(st[2]), decoded=int(st[3]), snr=float(st[4]),
                  variance=np.float32(st[5]), mean_H=float(st[7]))
@@ -331,19 +347,19 @@ class Ref(FrontEndMixin):
         pay = np.zeros((n, self.frame_bytes), np.int32)
         dec = np.zeros(n, np.int32)
         its = np.zeros(n, np.int32)
-        secs = lib().mref_rx_tail_timed(self.h, _p(bb), n, _p(pay), _p(dec), _p(its))
+        secs = self._L.mref_rx_tail_timed(self.h, _p(bb), n, _p(pay), _p(dec), _p(its))
         return secs, pay, dec, its
 
     def ldpc_decode(self, llr_cw):
         l = np.ascontiguousarray(llr_cw, np.float32)
         bits = np.zeros(self.K, np.int32)
-        it = lib().mref_ldpc_decode(self.h, _p(l), _p(bits))
+        it = self._L.mref_ldpc_decode(self.h, _p(l), _p(bits))
         return it, bits
 
     def transmit_byte(self, payload):
         pl = np.asarray(list(payload), np.int32)
         out = np.zeros(self.total_frame_size + 16, np.float64)
-        n = lib().mref_transmit_byte(self.h, _p(pl), len(pl), _p(out))
+        n = self._L.mref_transmit_byte(self.h, _p(pl), len(pl), _p(out))
         return out[:n]
 
     def receive_byte(self, passband):
@@ -353,6 +369,6 @@ class Ref(FrontEndMixin):
         out = np.zeros(self.frame_bytes, np.int32)
         st = np.zeros(8, np.float64)
         bb = np.zeros((self.Nsymb + self.preamble_nSymb) * self.Nofdm, np.complex128)
-        lib().mref_receive_byte(self.h, _p(pb), _p(out), _p(st), _p(bb))
+        self._L.mref_receive_byte(self.h, _p(pb), _p(out), _p(st), _p(bb))
         return dict(payload=out, iterations=int(st[0]), crc=int(st[1]), all_zeros=int(st[2]), decoded=int(st[3]),
                     snr=float(st[4]), delay=int(st[5]), sync_trials=int(st[6]), freq_offset=float(st[7]), baseband=bb)

@@ -76,6 +76,15 @@ void *mref_create(int config, int ldpc_iters)
 	return r;
 }
 
+/* cl_telecom_system::load_configuration(int) on the SAME object, as the ARQ layer does between data and ack configurations (arq_commander.cc:431,574,661) */
+void mref_load_configuration(void *h, int config)
+{
+	QuietStdout q;
+	Ref *r = static_cast<Ref *>(h);
+	r->config = config;
+	r->ts->load_configuration(config);
+}
+
 void mref_destroy(void *h)
 {
 	QuietStdout q;

@@ -6,9 +6,13 @@
   #4  LDPC rate sweep 1..14/16 at fixed symbol count (BPSK geometry CONFIG_0..6 + mode 12 for 14/16), 131,072 frames
   all 17 modes at threshold + 2 dB, 32,768 frames (frames/s of both stages, FER, payload integrity)
 
+  threshold region: modes 0, 8, 13 at the Es/N0 where 10-50 % of the frames fail (both outcomes, near-threshold iteration counts)
+
 Per line: device-resident frames/s (CUDA events), per-kernel times, demod GB/s on the algorithmic bytes of SURVEY.md 8d,
-decoder edge-updates/s, FER, payload mismatches among decoded frames, and -- on a bounded sample -- agreement with the
-reference CPU path (oracle/_ref if present, else the C port).  Not a bench line; bench.py keeps the driver's contract.
+decoder edge-updates/s, FER, payload mismatches among decoded frames, and agreement with the reference CPU path (oracle/_ref if present,
+else the C port) on >= 8,192 frames per configuration (the first 4,096 + 4,096 random frames of the batch), decoded by the
+reference on all host cores (one forked worker per core, each with its own reference object): decoded flag, payload, iteration count,
+with every disagreeing frame listed.  Not a bench line; bench.py keeps the driver's contract.
 """
 import argparse
 import json
@@ -21,6 +25,51 @@ ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import mercury_b200 as mb  # noqa: E402
+
+
+_W = {}
+_X = None
+
+
+def _ref_init(cfg, iters):
+    from oracle import port, ref
+    _W["o"] = ref.Ref(cfg, iters) if ref.available() else port.Port(cfg, iters)
+
+
+def _ref_job(job):
+    lo, hi = job
+    _, pay, dec, its = _W["o"].rx_tail_timed(_X[lo:hi])
+    return lo, pay, dec, its
+
+
+def reference_compare(cfg, iters, xs, pay_gpu, st_gpu, idx):
+    """Decode xs (complex64 [n, S, 272], frames idx of the batch) with the reference on all cores and compare with the GPU's results."""
+    global _X
+    import multiprocessing as mp
+    from oracle import ref
+    n = xs.shape[0]
+    _X = xs.astype(np.complex128)
+    cores = os.cpu_count() or 1
+    step = max(16, (n + 8 * cores - 1) // (8 * cores))
+    jobs = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+    pay = np.zeros((n, pay_gpu.shape[1]), np.uint8)
+    dec, its = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    with mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(cfg, iters)) as pool:
+        for lo, p, d, i in pool.imap_unordered(_ref_job, jobs):
+            pay[lo:lo + len(d)] = p[:, :pay_gpu.shape[1]].astype(np.uint8)
+            dec[lo:lo + len(d)], its[lo:lo + len(d)] = d, i
+    _X = None
+    g_dec, g_its = st_gpu["message_decoded"][idx], st_gpu["iterations_done"][idx]
+    both = (dec == 1) & (g_dec == 1)
+    bad_dec = np.flatnonzero(dec != g_dec)
+    bad_its = np.flatnonzero(its != g_its)
+    bad_pay = np.flatnonzero(both & (pay != pay_gpu[idx]).any(axis=1))
+    return {"kind": "reference" if ref.available() else "port", "frames": int(n), "cores": cores, "reference_decoded": int((dec == 1).sum()),
+            "decoded_flag_agrees": int(n - bad_dec.size), "payload_bit_exact_where_reference_decodes": int(((dec == 1) & (g_dec == 1)).sum() - bad_pay.size),
+            "iteration_count_agrees": int(n - bad_its.size), "reference_fer": float(1 - (dec == 1).mean()),
+            "reference_mean_iterations": float(np.minimum(its, iters).mean()),
+            "disagreements": [{"frame": int(idx[f]), "ref_decoded": int(dec[f]), "gpu_decoded": int(g_dec[f]), "ref_iterations": int(its[f]),
+                               "gpu_iterations": int(g_its[f])} for f in sorted(set(bad_dec.tolist()) | set(bad_its.tolist()) | set(bad_pay.tolist()))[:64]]}
 
 
 def run_one(ts, cfg, B, iters, esn0, steps, sample, decoder="spa"):
@@ -63,19 +112,13 @@ def run_one(ts, cfg, B, iters, esn0, steps, sample, decoder="spa"):
         "payload_mismatches_among_decoded": int((pay[dec] != pl[dec]).any(axis=1).sum()),
     }
     if sample:
-        o = ref.Ref(cfg, iters) if ref.available() else port.Port(cfg, iters)
-        xs = d_x[:sample].cpu().numpy()
-        agree_dec = agree_pay = agree_it = ref_dec = 0
-        for f in range(sample):
-            r = o.rx_tail(xs[f].reshape(-1).astype(np.complex128))
-            agree_dec += int(r["decoded"] == st["message_decoded"][f])
-            agree_it += int(r["iterations"] == st["iterations_done"][f])
-            if r["decoded"]:
-                ref_dec += 1
-                agree_pay += int(np.array_equal(r["payload"].astype(np.uint8), pay[f]))
-        out["reference_sample"] = {"kind": "reference" if ref.available() else "port", "frames": sample, "reference_decoded": ref_dec,
-                                   "decoded_flag_agrees": agree_dec, "payload_bit_exact_where_reference_decodes": agree_pay,
-                                   "iteration_count_agrees": agree_it, "reference_fer": 1 - ref_dec / sample}
+        sample = min(sample, B)
+        head = min(sample // 2, B)
+        rng = np.random.default_rng(4242 + cfg)
+        rest = rng.choice(np.arange(head, B), size=sample - head, replace=False) if B > head else np.zeros(0, np.int64)
+        idx = np.concatenate([np.arange(head), np.sort(rest)]).astype(np.int64)
+        xs = d_x[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        out["reference_sample"] = reference_compare(cfg, iters, xs, pay, st, idx)
     del d_x, d_llr
     torch.cuda.empty_cache()
     return out
@@ -83,22 +126,26 @@ def run_one(ts, cfg, B, iters, esn0, steps, sample, decoder="spa"):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_baseline_configs.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_baseline_configs.json"))
     ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
     ts = mb.TelecomSystemB200(0)
     q = 8 if a.quick else 1
-    res = {"config2": [], "config3": [], "config4": [], "all_modes": []}
+    n_ref = 8192 // q
+    res = {"config2": [], "config3": [], "config4": [], "threshold_region": [], "all_modes": []}
     for cfg in (8, 9):
-        res["config2"].append(run_one(ts, cfg, 65536 // q, 50, mb.THRESH_DB[cfg] + 2.0, 5, 256))
+        res["config2"].append(run_one(ts, cfg, 65536 // q, 50, mb.THRESH_DB[cfg] + 2.0, 5, n_ref))
         res["config2"].append(run_one(ts, cfg, 65536 // q, 50, mb.THRESH_DB[cfg] + 2.0, 5, 0, decoder="minsum"))
     for esn0 in (18.0, 20.0, 22.0, 25.0, 30.0):
-        res["config3"].append(run_one(ts, 16, 262144 // q, 20, esn0, 3, 128))
+        res["config3"].append(run_one(ts, 16, 262144 // q, 20, esn0, 3, n_ref if esn0 in (18.0, 22.0) else n_ref // 4))
     for cfg in (0, 1, 2, 3, 4, 5, 6, 12):
-        res["config4"].append(run_one(ts, cfg, 131072 // q, 50, mb.THRESH_DB[cfg] + 2.0, 3, 64))
+        res["config4"].append(run_one(ts, cfg, 131072 // q, 50, mb.THRESH_DB[cfg] + 2.0, 3, n_ref))
+    # where 10-50 % of the frames fail: the fp32 decoder against the double-precision reference on both outcomes
+    for cfg, off in ((0, 0.1), (0, 0.4), (8, 0.0), (8, 0.3), (13, -0.2), (13, 0.1)):
+        res["threshold_region"].append(run_one(ts, cfg, 16384 // q, 50, mb.THRESH_DB[cfg] + off, 3, n_ref))
     for cfg in range(17):
         esn0 = mb.THRESH_DB[cfg] + (2.0 if cfg < 15 else 14.0)
-        res["all_modes"].append(run_one(ts, cfg, 32768 // q, 20 if cfg == 16 else 50, esn0, 3, 32))
+        res["all_modes"].append(run_one(ts, cfg, 32768 // q, 20 if cfg == 16 else 50, esn0, 3, 256 // q))
     json.dump(res, open(a.out, "w"), indent=1)
     for k, v in res.items():
         print(k)
@@ -107,7 +154,9 @@ def main():
             print(f"  mode {r['config']:2d} {r['decoder']:6s} B={r['frames']:6d} EsN0={r['esn0_db']:5.1f} {r['frames_per_s'] / 1e6:6.2f} Mf/s "
                   f"demod {r['demod_gbs_algorithmic']:6.0f} GB/s ldpc {r['ldpc_edge_updates_per_s'] / 1e9:6.1f} Ge/s it {r['mean_iterations']:5.2f} "
                   f"FER {r['fer']:.4f} mism {r['payload_mismatches_among_decoded']} "
-                  f"ref[{rs.get('frames', 0)}]: dec= {rs.get('decoded_flag_agrees', '-')} pay= {rs.get('payload_bit_exact_where_reference_decodes', '-')}/{rs.get('reference_decoded', '-')} it= {rs.get('iteration_count_agrees', '-')}")
+                  f"ref[{rs.get('frames', 0)}]: dec= {rs.get('decoded_flag_agrees', '-')} pay= {rs.get('payload_bit_exact_where_reference_decodes', '-')}/{rs.get('reference_decoded', '-')} it= {rs.get('iteration_count_agrees', '-')} ref-FER {rs.get('reference_fer', float('nan')):.3f}")
+            for d in rs.get("disagreements", [])[:8]:
+                print("      disagreement:", d)
 
 
 if __name__ == "__main__":
