@@ -46,6 +46,7 @@ namespace {
 struct FeWork {
 	size_t cap = 0;
 	int buf = 0;
+	int symb = 0;  // symbols per frame the per-capture frame / debug buffers were sized for
 	void *d_x[2] = {nullptr, nullptr};  // staged pass-band samples of the host entry point, double buffered
 	size_t x_bytes = 0;
 	size_t out_slot_bytes = 0;
@@ -706,7 +707,8 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 		w.x_bytes = stage_bytes;
 	}
 	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
-	if (w.cap >= n && w.buf >= buf && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
+	const int symb = std::max(MB_MAX_SYMB, m.Nsymb);  // ROBUST_0 frames are 320 symbols: a workspace sized in an OFDM mode must not be reused for them
+	if (w.cap >= n && w.buf >= buf && w.symb >= symb && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
 	MB_CUDA(h, cudaDeviceSynchronize());
 	void **ptrs[] = {(void **)&w.st, (void **)&w.bbi, (void **)&w.win, (void **)&w.dbg_bb, (void **)&w.energy_part, (void **)&w.vals, (void **)&w.frames,
 			 (void **)&w.pref_ts, (void **)&w.pref_win, (void **)&w.flags, (void **)&w.tile_base,
@@ -715,9 +717,9 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 		if (*p) cudaFree(*p);
 		*p = nullptr;
 	}
-	w.cap = 0;
-	const int bufmax = std::max(buf, w.buf);
+	const int bufmax = std::max(buf, w.buf), symbmax = std::max(symb, w.symb);
 	const size_t cap = std::max(n, w.cap);
+	w.cap = 0;
 	MB_CUDA(h, cudaMalloc(&w.st, cap * sizeof(MbFeState)));
 	MB_CUDA(h, cudaMalloc(&w.bbi, cap * bufmax * sizeof(double2)));
 	MB_CUDA(h, cudaMalloc(&w.win, cap * kFeWin * sizeof(double2)));
@@ -727,17 +729,18 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 1024 + 3) * 3 * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
-	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)std::max(MB_MAX_SYMB, m.Nsymb) * MB_NOFDM * sizeof(float2)));
+	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)symbmax * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
 	MB_CUDA(h, cudaMalloc(&w.tail_stats, cap * sizeof(MbRxStats)));
 	MB_CUDA(h, cudaMalloc(&w.tail_payload, cap * 256));
 	MB_CUDA(h, cudaMalloc(&w.payload, cap * 256));
 	MB_CUDA(h, cudaMalloc(&w.stats, cap * sizeof(MbReceiveStats)));
-	if (want_dbg) MB_CUDA(h, cudaMalloc(&w.dbg_bb, cap * (size_t)(std::max(MB_MAX_SYMB, m.Nsymb) + 4) * MB_NOFDM * sizeof(double2)));
+	if (want_dbg) MB_CUDA(h, cudaMalloc(&w.dbg_bb, cap * (size_t)(symbmax + 4) * MB_NOFDM * sizeof(double2)));
 	(void)bb_n;
 	w.want_dbg = want_dbg;
 	w.cap = cap;
 	w.buf = bufmax;
+	w.symb = symbmax;
 	return MERCURY_B200_OK;
 }
 
@@ -1336,7 +1339,9 @@ int mercury_b200_transmit_byte(mercury_b200_t *h, const int *data, int nBytes, d
 	uint64_t start = passband_start_sample ? *passband_start_sample : (uint64_t)(m.M == 200 ? 0 : MB_FE_SYM);
 	rc = mercury_b200_transmit_byte_batch(h, pl, &start, 1, out, MERCURY_B200_SAMPLES_F64, nullptr);
 	if (rc) return rc;
-	if (passband_start_sample) *passband_start_sample = start + (uint64_t)tx_total(m);  // ofdm.cc:2313
+	// the carrier counter advances by what baseband_to_passband was given: (preamble + ACTIVE symbols) * Nofdm * 4 -- fewer than the frame
+	// in ROBUST control-frame mode (telecom_system.cc:531-532, ofdm.cc:2313), like mercury_b200_transmit_byte_loc
+	if (passband_start_sample) *passband_start_sample = start + (uint64_t)(active_nsymb(h) + m.preamble_nSymb) * MB_FE_SYM;
 	return MERCURY_B200_OK;
 }
 

@@ -64,6 +64,8 @@ struct mercury_b200_batcher {
 	Buffer buf[2];
 	int cur = 0;  // buffer currently accepting frames
 	bool stop = false;
+	size_t in_flight = 0;            // callers currently inside submit() (destroy waits for them before it frees anything)
+	std::condition_variable idle;    // destroy: in_flight dropped to 0
 	std::thread worker;
 	uint64_t n_batches = 0, n_frames = 0, n_full = 0;
 };
@@ -238,6 +240,15 @@ int mercury_b200_batcher_create_with_backend(size_t frame_floats, size_t frame_b
 static int submit(mercury_b200_batcher_t *b, const void *in, uint8_t *payload, void *stats)
 {
 	std::unique_lock<std::mutex> lk(b->mu);
+	if (b->stop) return MERCURY_B200_ESTATE;
+	b->in_flight++;
+	struct Leave {  // every exit below runs with the lock held
+		mercury_b200_batcher *b;
+		~Leave()
+		{
+			if (--b->in_flight == 0) b->idle.notify_all();
+		}
+	} leave{b};
 	Buffer *B;
 	for (;;) {  // a buffer that accepts frames: not closed, not full, previous results all read out
 		if (b->stop) return MERCURY_B200_ESTATE;
@@ -304,6 +315,12 @@ void mercury_b200_batcher_destroy(mercury_b200_batcher_t *b)
 	b->work.notify_all();
 	b->space.notify_all();
 	if (b->worker.joinable()) b->worker.join();
+	{
+		// The worker leaves as soon as the buffer it looks at is empty; callers of the other buffer may still be copying their results
+		// out, or be on their way out of submit().  Nothing is freed before the last of them has left (they hold the mutex when they do).
+		std::unique_lock<std::mutex> lk(b->mu);
+		b->idle.wait(lk, [&] { return b->in_flight == 0; });
+	}
 	free_buffers(b);
 	delete b;
 }

@@ -105,6 +105,57 @@ __device__ __forceinline__ void demap_scatter(const float2 z, const float inv_va
 	}
 }
 
+// 16QAM (psk.cc:117-140): the constellation is a product set -- index bits 3,2 pick the in-phase level, bits 1,0 the quadrature level --
+// so the minimum of |z - c|^2 over the points with bit k = b splits into a minimum over the 2 levels of that bit's axis plus the minimum
+// over the other axis, and the latter is common to both hypotheses: it cancels in Dmin1 - Dmin0.  8 squared differences and 8 minima
+// per symbol instead of 16 distances and 64 minima; equal to the reference's float distances up to their own rounding (~1e-7 D / sigma^2,
+// three orders inside the LLR tolerance).  lv[0..3] = in-phase level of index bits 3,2 = a, lv[4..7] = quadrature level of bits 1,0 = b.
+__device__ __forceinline__ void demap_scatter_qam16(const float2 z, const float inv_var, const float (&lv)[8], const uint32_t (&dw)[3], unsigned char *s_L)
+{
+	float dI[4], dQ[4];
+#pragma unroll
+	for (int a = 0; a < 4; a++) {
+		const float x = z.x - lv[a], y = z.y - lv[4 + a];
+		dI[a] = x * x, dQ[a] = y * y;
+	}
+	const float llr[4] = {inv_var * (fminf(dI[2], dI[3]) - fminf(dI[0], dI[1])),   // index bit 3, emitted first (MSB first)
+			      inv_var * (fminf(dI[1], dI[3]) - fminf(dI[0], dI[2])),   // bit 2
+			      inv_var * (fminf(dQ[2], dQ[3]) - fminf(dQ[0], dQ[1])),   // bit 1
+			      inv_var * (fminf(dQ[1], dQ[3]) - fminf(dQ[0], dQ[2]))};  // bit 0
+#pragma unroll
+	for (int e = 0; e < 4; e++) {
+		const uint32_t off = (e & 1) ? (dw[e >> 1] >> 16) : (dw[e >> 1] & 0xFFFFu);
+		*reinterpret_cast<float *>(s_L + off) = llr[e];
+	}
+}
+
+// 32QAM (psk.cc:142-190): the cross constellation -- levels {+-1, +-3, +-5} u on both axes without the four corners -- is a union of
+// rectangles: per half plane (index bit 4 = sign of the in-phase level), bits 3,2 = 00 is the cap (in-phase 3 u or 1 u by bit 0, quadrature
+// +-5 u by bit 1), 01 / 10 / 11 the columns 5 u / 1 u / 3 u with quadrature 3, 1, -3, -1 u by bits 1,0.  The minimum of |z - c|^2 over a
+// rectangle is the sum of the two per-axis minima, so every Dmin is the smaller of at most two such sums: 12 squared differences and ~45
+// minima / sums per symbol instead of 32 distances and 160 minima (checked against the brute force over the table in tests/test_tables.py).
+__device__ __forceinline__ void demap_scatter_qam32(const float2 z, const float inv_var, const float u, const uint32_t (&dw)[3], unsigned char *s_L)
+{
+	auto sq = [](float a) { return a * a; };
+	const float X5m = sq(z.x + 5.f * u), X3m = sq(z.x + 3.f * u), X1m = sq(z.x + u), X1p = sq(z.x - u), X3p = sq(z.x - 3.f * u), X5p = sq(z.x - 5.f * u);
+	const float Y5m = sq(z.y + 5.f * u), Y3m = sq(z.y + 3.f * u), Y1m = sq(z.y + u), Y1p = sq(z.y - u), Y3p = sq(z.y - 3.f * u), Y5p = sq(z.y - 5.f * u);
+	const float Am = fminf(X3m, X1m), Ap = fminf(X3p, X1p), Bm = fminf(Am, X5m), Bp = fminf(Ap, X5p);
+	const float A = fminf(Am, Ap), B = fminf(Bm, Bp), C = fminf(fminf(X5m, X3m), fminf(X5p, X3p));
+	const float X3 = fminf(X3m, X3p), X1 = fminf(X1m, X1p), X5 = fminf(X5m, X5p);
+	const float Yb1_0 = fminf(Y3p, Y1p), Yb1_1 = fminf(Y3m, Y1m), Yb0_0 = fminf(Y3p, Y3m), Yb0_1 = fminf(Y1p, Y1m);
+	const float Yc = fminf(Yb1_0, Yb1_1), Ycap = fminf(Y5p, Y5m), AYcap = A + Ycap;
+	const float llr[5] = {inv_var * (fminf(Ap + Ycap, Bp + Yc) - fminf(Am + Ycap, Bm + Yc)),        // index bit 4, emitted first (MSB first)
+			      inv_var * ((A + Yc) - fminf(AYcap, X5 + Yc)),                                 // bit 3
+			      inv_var * ((C + Yc) - fminf(AYcap, X1 + Yc)),                                 // bit 2
+			      inv_var * (fminf(A + Y5m, B + Yb1_1) - fminf(A + Y5p, B + Yb1_0)),             // bit 1
+			      inv_var * (fminf(X1 + Ycap, B + Yb0_1) - fminf(X3 + Ycap, B + Yb0_0))};        // bit 0
+#pragma unroll
+	for (int e = 0; e < 5; e++) {
+		const uint32_t off = (e & 1) ? (dw[e >> 1] >> 16) : (dw[e >> 1] & 0xFFFFu);
+		*reinterpret_cast<float *>(s_L + off) = llr[e];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // compile-time geometry of one instantiation
 // ------------------------------------------------------------------------------------------------------------------
@@ -114,7 +165,7 @@ struct Geo {
 	static constexpr int NCH = S / SC;                                                // rounds per frame
 	static constexpr int T = (SC * 16 + 31) / 32 * 32;                                // threads per CTA
 	static constexpr int NW = T / 32;
-	static constexpr int MINB = T <= 128 ? 6 : 5;      // resident CTAs per SM the register file is budgeted for (64 / 80 registers)
+	static constexpr int MINB = T <= 160 ? 6 : 5;      // resident CTAs per SM the register file is budgeted for (64 / 80 registers)
 	static constexpr int CELLS = S * MB_NC;
 	static constexpr int NPIL = (S * MB_NC + 2) / 3;   // pilots: cells with s%3 == c%3
 	static constexpr int NDATA = CELLS - NPIL;
@@ -378,6 +429,10 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 	float2 c_reg[M <= 4 ? M : 1];  // BPSK / QPSK: the constellation lives in registers for the whole loop
 #pragma unroll
 	for (int j = 0; j < (M <= 4 ? M : 1); j++) c_reg[j] = s_cons[j];
+	const float unit32 = M == 32 ? s_cons[9].y : 0.f;  // 32QAM: index 9 is (-1, +1) u
+	float lv16[8];  // 16QAM: the 4 + 4 axis levels (index = a * 4 + b: in-phase from c[4 a], quadrature from c[b])
+#pragma unroll
+	for (int j = 0; j < 4; j++) lv16[j] = M == 16 ? s_cons[4 * j].x : 0.f, lv16[4 + j] = M == 16 ? s_cons[j].y : 0.f;
 #pragma unroll 1
 	for (int d = tid; d < G::NDATA; d += T) {
 		const uint32_t w0 = dr[0], dw[3] = {dr[1], dr[2], dr[3]};
@@ -420,6 +475,10 @@ __global__ void __launch_bounds__(Geo<S>::T, Geo<S>::MINB) mb_demod_kernel(const
 		if (!LS) zf_out[d] = z;  // ZF modes: the decoder's SNR report re-encodes the frame and needs the equalised data symbols (:1376-1400)
 		if (M <= 4)
 			demap_scatter<M, BPS>(z, inv_var, c_reg, dw, s_Lb);
+		else if (M == 16)
+			demap_scatter_qam16(z, inv_var, lv16, dw, s_Lb);
+		else if (M == 32)
+			demap_scatter_qam32(z, inv_var, unit32, dw, s_Lb);
 		else
 			demap_scatter<M, BPS>(z, inv_var, s_cons, dw, s_Lb);
 	}

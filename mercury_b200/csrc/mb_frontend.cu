@@ -363,6 +363,9 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 		vals_all[(size_t)b * vals_stride + k] = v;
 		flags_all[(size_t)b * vals_stride + k] = amb ? 1 : 0;
 	}
+	// the maximum that anchors pass B's band runs over the positions the selection can return (k * step >= location_to_return): with the
+	// global maximum at an excluded position the survivors could otherwise fall outside the band and be compared by their approximations
+	if (k < st.sc_npos && k * st.sc_step < st.sc_from) v = -3.0;
 	for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 	if ((threadIdx.x & 31) == 0 && v > -3.0) atomicMax(&st.sc_max_key, metric_key(v));
 }
@@ -539,9 +542,10 @@ __device__ double energy_cur_sum(const DecideCtx &c, const double2 *bbi, const T
 	return block_sum(e, red);
 }
 
-__device__ __forceinline__ void request_sc(MbFeState &st, int src, int start, int size, int step, int pre)
+__device__ __forceinline__ void request_sc(MbFeState &st, int src, int start, int size, int step, int pre, int from = 0)
 {
 	st.sc_pending = 1;
+	st.sc_from = from;  // positions below it cannot be returned: they stay out of the approximate maximum that defines pass B's band
 	st.sc_src = src, st.sc_start = start, st.sc_size = size, st.sc_step = step;
 	const int span = size - pre * MB_FE_SYM;
 	st.sc_npos = span > 0 ? (span + step - 1) / step : 0;
@@ -657,7 +661,8 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 					st.delay = st.last_delay;
 					st.phase = MB_FE_POSTDELAY;
 				} else {
-					request_sc(st, st.cur_kind, (st.pream_symb_loc - 1) * sym, (pre + 4) * sym, 1, pre);
+					request_sc(st, st.cur_kind, (st.pream_symb_loc - 1) * sym, (pre + 4) * sym, 1, pre,
+						   st.sync_trials >= fe_c.trials_max ? fe_c.trials_max - 1 : st.sync_trials);  // = `want` of MB_FE_FINE_WAIT
 					st.phase = MB_FE_FINE_WAIT;
 				}
 			}

@@ -92,6 +92,8 @@ struct MbFeState {
 	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for
 	int32_t slot;        // tail slot of the running trial
 	int32_t extract_pending;  // k_fe_moose has chosen the carrier, k_fe_extract_tiles still has to write the frame
+	int32_t sc_from;     // the pending run's location_to_return: only positions >= it can be selected (ofdm.cc:1821-1823, 1946-1958)
+	int32_t sc_pad;
 	unsigned long long sc_max_key;  // approximate maximum of the pending run (pass A of the two-pass Schmidl-Cox), order-preserving key
 };
 

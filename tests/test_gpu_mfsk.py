@@ -285,6 +285,15 @@ def test_mfsk_control_frames(ts, cfg):
     # FIRs also smear over the last 96 active samples); here silence follows.  Compare the part that is defined.
     assert np.abs(tx[:L - 100] - want[:L - 100]).max() <= 1e-9 * np.abs(want).max()
     assert L + 200 >= tx.size or np.abs(tx[L + 200:]).max() <= 1e-12
+    # the running carrier counter advances by (preamble + ACTIVE symbols) * 1088 (telecom_system.cc:531-532, ofdm.cc:2313): three frames in a
+    # row through the single-frame entry point, counter and samples against the oracle's, which is called the same way
+    cnt_gpu = cnt_ref = 12345
+    for k in range(3):
+        plk = rng.integers(0, 256, g["frame_bytes"]).astype(np.uint8)
+        got, cnt_gpu = ts.transmit_byte([int(v) for v in plk], cnt_gpu)
+        exp, cnt_ref = o.transmit_byte2(plk, cnt_ref)
+        assert cnt_gpu == cnt_ref == 12345 + (k + 1) * (4 + na) * 1088, (cfg, k, cnt_gpu, cnt_ref)
+        assert np.abs(got[:L - 100] - exp[:L - 100]).max() <= 1e-9 * np.abs(exp).max(), (cfg, k)
     # the whole receive_byte on a capture holding that control frame
     if ref.available():
         n = o.capture_samples()

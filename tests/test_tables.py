@@ -171,3 +171,41 @@ def test_layout_file_only_permutes_and_lowers_bank_conflicts(tmp_path):
     open(os.path.join(d, "ldpc_layout.bin"), "wb").write(bytes(lay))
     with pytest.raises(mb.MercuryB200Error):
         mb.build_tables_host(os.path.join(d, "ldpc_tables.bin"))
+
+
+def test_qam_demap_decompositions_equal_the_brute_force(blob):
+    """mb_demod.cu demap_scatter_qam16 / demap_scatter_qam32: the max-log LLR numerators (Dmin1 - Dmin0, psk.cc:278-326) from per-axis minima
+    over the rectangles the 16QAM / 32QAM index mapping is made of, against the minimum over all constellation points of the table."""
+    rng = np.random.default_rng(5)
+    z = (rng.standard_normal(40000) + 1j * rng.standard_normal(40000)) * 0.9
+    mn = np.minimum
+
+    def brute(c, nbits):
+        D = np.abs(z[:, None] - c[None, :].astype(np.complex128)) ** 2
+        out = np.zeros((z.size, nbits))
+        for k in range(nbits):
+            one = ((np.arange(c.size) >> k) & 1) == 1
+            out[:, k] = D[:, one].min(1) - D[:, ~one].min(1)
+        return out
+
+    c = blob.mode(13)["cons"].astype(np.complex128)          # 16QAM: index = a * 4 + b, in-phase level from c[4 a], quadrature from c[b]
+    dI = [(z.real - c[4 * a].real) ** 2 for a in range(4)]
+    dQ = [(z.imag - c[b].imag) ** 2 for b in range(4)]
+    fast = np.stack([mn(dQ[1], dQ[3]) - mn(dQ[0], dQ[2]), mn(dQ[2], dQ[3]) - mn(dQ[0], dQ[1]),
+                     mn(dI[1], dI[3]) - mn(dI[0], dI[2]), mn(dI[2], dI[3]) - mn(dI[0], dI[1])], axis=1)
+    assert np.abs(fast - brute(c, 4)).max() < 1e-12
+
+    c = blob.mode(16)["cons"].astype(np.complex128)          # 32QAM: index 9 is (-1, +1) u
+    u = c[9].imag
+    assert u > 0 and c[9].real == -u
+    X = {l: (z.real - l * u) ** 2 for l in (-5, -3, -1, 1, 3, 5)}
+    Y = {l: (z.imag - l * u) ** 2 for l in (-5, -3, -1, 1, 3, 5)}
+    Am, Ap = mn(X[-3], X[-1]), mn(X[3], X[1])
+    Bm, Bp = mn(Am, X[-5]), mn(Ap, X[5])
+    A, B, C = mn(Am, Ap), mn(Bm, Bp), mn(mn(X[-5], X[-3]), mn(X[5], X[3]))
+    X3, X1, X5 = mn(X[-3], X[3]), mn(X[-1], X[1]), mn(X[-5], X[5])
+    Yb1_0, Yb1_1, Yb0_0, Yb0_1 = mn(Y[3], Y[1]), mn(Y[-3], Y[-1]), mn(Y[3], Y[-3]), mn(Y[1], Y[-1])
+    Yc, Ycap = mn(Yb1_0, Yb1_1), mn(Y[5], Y[-5])
+    fast = np.stack([mn(X1 + Ycap, B + Yb0_1) - mn(X3 + Ycap, B + Yb0_0), mn(A + Y[-5], B + Yb1_1) - mn(A + Y[5], B + Yb1_0),
+                     (C + Yc) - mn(A + Ycap, X1 + Yc), (A + Yc) - mn(A + Ycap, X5 + Yc), mn(Ap + Ycap, Bp + Yc) - mn(Am + Ycap, Bm + Yc)], axis=1)
+    assert np.abs(fast - brute(c, 5)).max() < 1e-6   # the table's levels are float32 roundings of 3 u and 5 u, the kernel multiplies u
