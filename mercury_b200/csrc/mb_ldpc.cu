@@ -726,11 +726,13 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 			}
 		}
 		if (frame[0] < 0 && frame[1] < 0) break;
+		// both slots just refilled (the usual case where frames arrive clean: 0 iterations each): their posteriors are the channel LLRs
+		// already, there is nothing for a variable pass to do
+		if (virgin[0] && virgin[1]) continue;
 		// ---- variable pass: posterior = channel + sum of incoming messages (reference V-row order), both slots ----------
 		// Variables are numbered by descending degree.  The head (degree > 2) is walked in warp groups padded to one even
 		// degree (padding reads the always-zero slot); the long tail of degree-<=2 variables (the accumulator chain of the IRA
-		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.  A slot refilled above has
-		// all-zero messages: its posterior is rewritten with the channel LLR, and the next check pass is its pass 0.
+		// code, ~60 % of all variables) is a flat loop with both message offsets packed in one word.
 		// A slot refilled above keeps its old messages (x 0 here): its posterior is rewritten with the channel LLR, the next check pass is
 		// its pass 0.  The channel LLRs come from the L2 (global scratch): all of a thread's loads are issued before the first is used.
 		const f2 vm = make_float2(virgin[0] ? 0.f : 1.f, virgin[1] ? 0.f : 1.f);

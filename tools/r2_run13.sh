@@ -1,19 +1,17 @@
 mkdir -p gpurun_out
-T=${1:-r2m}
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5 > gpurun_out/${T}_pytest.log
+T=${1:-r2n}
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/${T}_pytest.log
 run() { name=$1; shift; env "$@" timeout 300 python bench.py --no-e2e --no-extra --cpu-frames 0 --steps 5 $BARGS > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err; }
 for cfg in 8 0 9 12 13; do BARGS="--config $cfg"; run m${cfg} X=1; done
 BARGS="--config 16 --iters 20 --esn0 30"; run m16_30dB X=1
 BARGS="--config 16 --iters 20 --esn0 18"; run m16_18dB X=1
 BARGS="--config 15 --esn0 26.5"; run m15 X=1
-timeout 600 python tools/run_baseline_configs.py --only threshold_region --out gpurun_out/${T}_threshold.json > gpurun_out/${T}_threshold.log 2> gpurun_out/${T}_threshold.err
 for cfg in 8 13 15 16; do
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mb_demod -s 1 -c 1 -o gpurun_out/${T}_prof_demod_m$cfg \
     python bench.py --config $cfg --batch 16384 --steps 1 --warmup 1 --no-e2e --no-extra --cpu-frames 0 > gpurun_out/${T}_prof_demod_m$cfg.log 2>&1
 done
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mb_ldpc -s 1 -c 1 -o gpurun_out/${T}_prof_ldpc \
     python bench.py --batch 16384 --steps 1 --warmup 1 --no-e2e --no-extra --cpu-frames 0 > gpurun_out/${T}_prof_ldpc.log 2>&1
-cat gpurun_out/${T}_pytest.log | tail -3; cat gpurun_out/${T}_threshold.log | cut -c1-300; tail -3 gpurun_out/${T}_threshold.err
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("gpurun_out/${T}_bench_*.json")):
