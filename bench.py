@@ -245,6 +245,30 @@ def synth_batch_on_device(config, B, esn0_db, dev, seed, unique=4096):
     return d_x, pl_all
 
 
+def pin_to_gpu_numa_node(torch, dev):
+    """Bind this rank's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated, so that
+    they are first-touched on the near node (the H2D copies of all ranks at once are what bounds e2e at N > 1).  Returns what was done."""
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"pci": bdf, "numa_node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return {"pci": bdf, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, ids)
+        return {"pci": bdf, "numa_node": node, "bound": True, "cpus": cpus}
+    except Exception as e:  # flat VMs expose no topology: nothing to do
+        return {"bound": False, "why": repr(e)[:80]}
+
+
 def side_config(ts, mb, torch, dev, cfg, iters, B, esn0, stream):
     """One BASELINE configuration besides the headline, device-resident: frames/s, stage times, integrity.  -> dict"""
     m = mb.MODES[cfg]
@@ -392,6 +416,8 @@ def run_own(a):
         pass
     roofline = {"kernel": "mb_demod_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_frame": m["demod_bytes"], "peak_source": peak_src,
+                # the same fraction on the bytes the kernel really moves (ncu dram__bytes; the guard interval is never fetched)
+                "frac_of_dram_bytes": None if traffic is None else traffic / t_demod_s / 1e9 / peak,
                 "kernel_ms": 1e3 * t_demod_s, "share_of_step": t_demod_s / (t_demod_s + t_ldpc_s)}
     edge_updates = float(its_run.sum()) * m["edges"]
     sm_mhz = clocks.summary()["sm_mhz"] or float(peaks.get("sm_max_mhz", 1965.0))
@@ -427,6 +453,7 @@ def run_own(a):
     e2e = None
     if not a.no_e2e:
         Be = min(B, 65536)  # frames of the batch that go through the host path (keeps pinned host memory per rank at 3.4 GB)
+        numa = pin_to_gpu_numa_node(torch, dev)
         peak_abs = float(d_x[:Be].abs().max().item())
         scale = peak_abs / 32000.0
         h_q = torch.empty((Be, S, 272, 2), dtype=torch.int16, pin_memory=True)
@@ -482,6 +509,7 @@ def run_own(a):
                "api": "mercury_b200_demod_decode_batch_fmt (pinned host buffers, 3-slot chunk pipeline, GI-free strided H2D)",
                "complex64": {"value": v64, "h2d_bytes_per_step": int(Be * S * 256 * 8), "payload_mismatches": mism64, "frames_decoded": dec64,
                              "api": "mercury_b200_demod_decode_batch"},
+               "numa": numa,
                "h2d_ceiling": {"gbs_per_gpu": ceil_gbs, "gbs_all_gpus": ceil_gbs * world, "frames_per_s": world * Be / (best * 1e-3),
                                "frac_of_ceiling": v16 / (world * Be / (best * 1e-3)),
                                "how": "the same number of bytes, one contiguous pinned-host -> device copy per rank, all ranks at once, nothing else running (best of 3)"}}

@@ -746,38 +746,38 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 		sched = s_vsched + warp * MB_SCHED_LEN;
 		uint32_t desc = *sched;
 		f2 lh = desc != 0u ? s.get_lch((int)((desc >> 24) - 1u) * 32 + lane) : make_float2(0.f, 0.f);  // first head group: in flight during the tail
-#pragma unroll
-		for (int i = 0; i < kTailRegs; i++) {
-			const int v = vtail0 + tid + i * kThreads;
-			if (v < MB_N) {
-				const uint32_t w = __ldg(g_vtail + (v - vtail0));
-				f2 acc = __ffma2_rn(lds2(sbase + kOffR + (w & 0xFFFFu)), vm, lt[i]);
-				acc = __ffma2_rn(lds2(sbase + kOffR + (w >> 16)), vm, acc);
-				sts2(sbase + kOffLam + v * 8, acc);
-			}
-		}
-		for (int v = vtail0 + tid + kTailRegs * kThreads; v < MB_N; v += kThreads) {  // (not reached with the eight codes of the reference)
-			const uint32_t w = __ldg(g_vtail + (v - vtail0));
-			f2 acc = s.get_lch(v);
-			acc = __ffma2_rn(lds2(sbase + kOffR + (w & 0xFFFFu)), vm, acc);
-			acc = __ffma2_rn(lds2(sbase + kOffR + (w >> 16)), vm, acc);
-			sts2(sbase + kOffLam + v * 8, acc);
-		}
+		// The channel LLRs arrive from the L2 (~300 cycles): every sum below adds its messages first and the channel value LAST, and the
+		// head groups (channel value fetched one group ahead) run before the tail, whose values were requested first.
 		while (desc != 0u) {
 			const int d = (int)((desc >> 16) & 0xFFu);
 			const int v = (int)((desc >> 24) - 1u) * 32 + lane;
 			const uint16_t *__restrict__ se = g_vedge + ((desc & 0xFFFFu) + lane);
 			const uint32_t nd = *++sched;
-			f2 acc = lh;
+			const f2 lcur = lh;
 			if (nd != 0u) lh = s.get_lch((int)((nd >> 24) - 1u) * 32 + lane);  // the next group's, one ahead
+			f2 acc = make_float2(0.f, 0.f);
 			switch (d) {  // variable degrees are 3..9 in all eight codes (padded: 4, 6, 8, 10)
 			case 4: acc = var_node_sum<4>(sbase, se, acc, d, vm); break;
 			case 6: acc = var_node_sum<6>(sbase, se, acc, d, vm); break;
 			case 8: acc = var_node_sum<8>(sbase, se, acc, d, vm); break;
 			default: acc = var_node_sum<0>(sbase, se, acc, d, vm); break;
 			}
-			sts2(sbase + kOffLam + v * 8, acc);
+			sts2(sbase + kOffLam + v * 8, __fadd2_rn(acc, lcur));
 			desc = nd;
+		}
+#pragma unroll
+		for (int i = 0; i < kTailRegs; i++) {
+			const int v = vtail0 + tid + i * kThreads;
+			if (v < MB_N) {
+				const uint32_t w = __ldg(g_vtail + (v - vtail0));
+				const f2 r0 = lds2(sbase + kOffR + (w & 0xFFFFu)), r1 = lds2(sbase + kOffR + (w >> 16));
+				sts2(sbase + kOffLam + v * 8, __ffma2_rn(__fadd2_rn(r0, r1), vm, lt[i]));
+			}
+		}
+		for (int v = vtail0 + tid + kTailRegs * kThreads; v < MB_N; v += kThreads) {  // (not reached with the eight codes of the reference)
+			const uint32_t w = __ldg(g_vtail + (v - vtail0));
+			const f2 r0 = lds2(sbase + kOffR + (w & 0xFFFFu)), r1 = lds2(sbase + kOffR + (w >> 16));
+			sts2(sbase + kOffLam + v * 8, __ffma2_rn(__fadd2_rn(r0, r1), vm, s.get_lch(v)));
 		}
 		__syncthreads();
 		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
