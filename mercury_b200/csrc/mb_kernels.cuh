@@ -44,6 +44,10 @@ struct MbLdpcArgs {
 	unsigned *queue;       // [2] device words, zero between launches: next frame of the batch, CTAs finished (the kernel re-arms them)
 	float *lch_scratch;    // [mb_ldpc_max_ctas()][2 * 1600] per-CTA channel-LLR scratch (same stream as the queue)
 	unsigned long long n_frames;  // filled by mb_launch_ldpc (the kernel is persistent: resident CTAs pull frames from the queue)
+	// filled by mb_launch_ldpc: blob + rate.off_edge_varb / off_vedgeb / off_vtail (the kernel re-derives a pointer per task otherwise)
+	const uint16_t *edge_var;
+	const uint16_t *vedge;
+	const uint32_t *vtail;
 };
 
 size_t mb_ldpc_smem_bytes(int c_slots);

@@ -71,13 +71,20 @@ constexpr int kMiscBytes = 512;                    // packed bytes of the epilog
 
 __host__ __device__ constexpr int r_bytes(int c_slots) { return ((c_slots + 2) & ~1) * 8; }
 
-// 32-bit shared-window addressing (one add per access, base kept in a register)
-__device__ __forceinline__ f2 lds2(unsigned addr)
+// The decoder's shared memory is ONE dynamic window (no static __shared__ in this file) whose shared-space address is a constant of
+// the toolchain: kSmemBase (the first KB of the window is the system's).  Every gather is therefore [index register + immediate]
+// -- no address add per access (ncu r2p: 4.6 % of the decoder's instructions were those adds).  The kernel traps at entry if the
+// constant is ever not what the compiler produced.
+constexpr unsigned kSmemBase = 0x400;
+extern __shared__ __align__(16) unsigned char mb_smem[];
+template <int IMM>
+__device__ __forceinline__ f2 lds2i(unsigned reg)
 {
 	f2 v;
-	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(reg), "n"(IMM));
 	return v;
 }
+__device__ __forceinline__ f2 lds2(unsigned addr) { return lds2i<0>(addr); }
 __device__ __forceinline__ void sts2(unsigned addr, f2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
 
 __device__ __forceinline__ float ldg_stream(const float *p)
@@ -132,17 +139,16 @@ __device__ __forceinline__ Gen comb_gg(Gen a, Gen b)
 }
 
 // |R| = log2(P / M) of the other edges, M == 0 (every other factor saturated) -> the reference's clamp; sign = product of the other
-// edges' signs = parity of all of them ^ this edge's own.  GUARD: the divide-out form can leave rounding noise of either sign where the
-// true ratio is 1 (message 0); a ratio below 1 / NaN is read as 1.
-template <bool GUARD>
-__device__ __forceinline__ void emit(unsigned addr, Gen o, unsigned sa, unsigned sb)
+// edges' signs = parity of all of them ^ this edge's own.  The sign goes on as one packed multiply by (+-1, +-1): sgn_k = (q_k & sign
+// bit) ^ one, where `one` is 1.0f carrying the parity of the whole check in its sign bit (one LOP3 per frame, not xor + copysign).
+__device__ __forceinline__ void emit(unsigned addr, Gen o, float qa, float qb, unsigned one_a, unsigned one_b)
 {
-	f2 ratio = __fmul2_rn(o.P, make_float2(rcp_fast(o.M.x), rcp_fast(o.M.y)));
-	if (GUARD) ratio = make_float2(fmaxf(ratio.x, 1.0f), fmaxf(ratio.y, 1.0f));
+	const f2 ratio = __fmul2_rn(o.P, make_float2(rcp_fast(o.M.x), rcp_fast(o.M.y)));
 	float lx = lg2_fast(ratio.x), ly = lg2_fast(ratio.y);
 	lx = lx < 3.0e38f ? lx : kClampR2;
 	ly = ly < 3.0e38f ? ly : kClampR2;
-	sts2(addr, make_float2(copysign_bits(lx, sa), copysign_bits(ly, sb)));
+	const f2 sgn = make_float2(__uint_as_float((fbits(qa) & 0x80000000u) ^ one_a), __uint_as_float((fbits(qb) & 0x80000000u) ^ one_b));
+	sts2(addr, __fmul2_rn(make_float2(lx, ly), sgn));
 }
 
 // Shuffle helpers for checks split over S = 2, 4, 8 lanes (lanes of one check are 32 / S apart: xor masks 32 / S, .., 16).
@@ -194,7 +200,7 @@ __device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *_
 	for (int k = 0; k < D; k++) {
 		if (k == D - 1 && split) break;
 		const unsigned off = ve[k * 32];
-		const f2 lam = lds2(sbase + kOffLam + off);
+		const f2 lam = lds2i<kSmemBase + kOffLam>(off);
 		const f2 r = lds2(raddr + k * 256);
 		q[k] = __ffma2_rn(r, nm, lam);  // nm = -1, or 0 for a slot whose messages are not written yet (just refilled)
 		ha ^= fbits(lam.x);
@@ -216,20 +222,21 @@ __device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *_
 		q[D - 1] = make_float2(0.f, 0.f);
 	}
 	hard_a ^= ha, hard_b ^= hb;
+	const unsigned one_a = (pa & 0x80000000u) | 0x3f800000u, one_b = (pb & 0x80000000u) | 0x3f800000u;
 	Gen pre[D];  // pre[k] = e_0 (+) .. (+) e_{k-1}, k >= 2
 	pre[2] = comb_ss(e[0], e[1]);
 #pragma unroll
 	for (int k = 3; k < D; k++) pre[k] = comb_gs(pre[k - 1], e[k - 1]);
-	if (!split) emit<false>(raddr + (D - 1) * 256, pre[D - 1], fbits(q[D - 1].x) ^ pa, fbits(q[D - 1].y) ^ pb);
+	if (!split) emit(raddr + (D - 1) * 256, pre[D - 1], q[D - 1].x, q[D - 1].y, one_a, one_b);
 	if (D >= 4)
-		emit<false>(raddr + (D - 2) * 256, comb_gs(pre[D >= 4 ? D - 2 : 2], e[D - 1]), fbits(q[D - 2].x) ^ pa, fbits(q[D - 2].y) ^ pb);
+		emit(raddr + (D - 2) * 256, comb_gs(pre[D >= 4 ? D - 2 : 2], e[D - 1]), q[D - 2].x, q[D - 2].y, one_a, one_b);
 	else
-		emit<false>(raddr + 256, comb_ss(e[0], e[2]), fbits(q[1].x) ^ pa, fbits(q[1].y) ^ pb);
+		emit(raddr + 256, comb_ss(e[0], e[2]), q[1].x, q[1].y, one_a, one_b);
 	Gen suf = comb_ss(e[D - 2], e[D - 1]);
 #pragma unroll
 	for (int k = D - 3; k >= 0; k--) {
 		const Gen o = k >= 2 ? comb_gg(pre[k >= 2 ? k : 2], suf) : (k == 1 ? comb_gs(suf, e[0]) : suf);
-		emit<false>(raddr + k * 256, o, fbits(q[k].x) ^ pa, fbits(q[k].y) ^ pb);
+		emit(raddr + k * 256, o, q[k].x, q[k].y, one_a, one_b);
 		if (k > 0) suf = comb_gs(suf, e[k]);
 	}
 }
@@ -240,7 +247,7 @@ __device__ __forceinline__ void spa_check_pair(unsigned sbase, const uint16_t *_
 __device__ __forceinline__ float sat_q(float q) { return fabsf(q) > kSatQ2 ? copysign_bits(kClampR2, fbits(q)) : q; }
 __device__ __forceinline__ void spa_check_pair_2(unsigned sbase, const uint16_t *__restrict__ ve, unsigned raddr, f2 nm, unsigned &hard_a, unsigned &hard_b)
 {
-	const f2 l0 = lds2(sbase + kOffLam + ve[0]), l1 = lds2(sbase + kOffLam + ve[32]);
+	const f2 l0 = lds2i<kSmemBase + kOffLam>(ve[0]), l1 = lds2i<kSmemBase + kOffLam>(ve[32]);
 	const f2 q0 = __ffma2_rn(lds2(raddr), nm, l0), q1 = __ffma2_rn(lds2(raddr + 256), nm, l1);
 	hard_a ^= fbits(l0.x) ^ fbits(l1.x);
 	hard_b ^= fbits(l0.y) ^ fbits(l1.y);
@@ -290,7 +297,7 @@ __device__ __forceinline__ void minsum_check_pair(unsigned sbase, const uint16_t
 	unsigned ha = 0, hb = 0;
 #pragma unroll 4
 	for (int k = 0; k < d; k++) {
-		const f2 lam = lds2(sbase + kOffLam + ve[k * 32]);
+		const f2 lam = lds2i<kSmemBase + kOffLam>(ve[k * 32]);
 		const f2 q = __ffma2_rn(lds2(raddr + k * 256), nm, lam);
 		ha ^= fbits(lam.x);
 		hb ^= fbits(lam.y);
@@ -319,7 +326,7 @@ __device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__res
 #pragma unroll
 		for (int k = 0; k < D; k++) idx[k] = se[k * 32];
 #pragma unroll
-		for (int k = 0; k < D; k++) acc = __ffma2_rn(lds2(sbase + kOffR + idx[k]), vm, acc);  // vm = 1, or 0 for a just-refilled slot
+		for (int k = 0; k < D; k++) acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(idx[k]), vm, acc);  // vm = 1, or 0 for a just-refilled slot
 		return acc;
 	}
 	int k = 0;
@@ -327,15 +334,15 @@ __device__ __forceinline__ f2 var_node_sum(unsigned sbase, const uint16_t *__res
 	for (; k + 4 <= d_rt; k += 4) {
 		const unsigned i0 = se[0], i1 = se[32], i2 = se[64], i3 = se[96];
 		se += 128;
-		acc = __ffma2_rn(lds2(sbase + kOffR + i0), vm, acc);
-		acc = __ffma2_rn(lds2(sbase + kOffR + i1), vm, acc);
-		acc = __ffma2_rn(lds2(sbase + kOffR + i2), vm, acc);
-		acc = __ffma2_rn(lds2(sbase + kOffR + i3), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i0), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i1), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i2), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i3), vm, acc);
 	}
 	if (k < d_rt) {
 		const unsigned i0 = se[0], i1 = se[32];
-		acc = __ffma2_rn(lds2(sbase + kOffR + i0), vm, acc);
-		acc = __ffma2_rn(lds2(sbase + kOffR + i1), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i0), vm, acc);
+		acc = __ffma2_rn(lds2i<kSmemBase + kOffR>(i1), vm, acc);
 	}
 	return acc;
 }
@@ -349,7 +356,7 @@ __device__ __forceinline__ void check_parity(unsigned sbase, const uint16_t *__r
 	for (int k = 0; k < D; k++) idx[k] = ve[k * 32];
 #pragma unroll
 	for (int k = 0; k < D; k++) {
-		const f2 lam = lds2(sbase + kOffLam + idx[k]);
+		const f2 lam = lds2i<kSmemBase + kOffLam>(idx[k]);
 		ha ^= fbits(lam.x);
 		hb ^= fbits(lam.y);
 	}
@@ -368,7 +375,7 @@ __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 
 struct Smem {
 	unsigned char *raw;
-	unsigned sbase;
+	static constexpr unsigned sbase = kSmemBase;
 	unsigned char *bytes;   // [256] packed bytes of the frame being finished; [255] = its verdict
 	unsigned *cnt;          // [2][MB_LDPC_WARPS] per-warp vote counts (check pass, syndrome test): A | B << 16
 	volatile int *next;     // [2] queue hand-off: tickets of the next two refills, alternating (no barrier between reading one and fetching the next)
@@ -448,7 +455,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 	// Scratch: this slot's messages are dead: [0, P) data parity per check, [P, P + 1600) re-encoded bit per internal variable.
 	__syncthreads();
 	if (!s.bytes[255]) return;
-	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);
+	const uint16_t *__restrict__ g_edge_var = a.edge_var;
 	const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + rt.off_var_of_cw);
 	const int K = m.K, P = rt.P, nReal = m.nReal, nVirtual = m.nVirtual;
 	auto bit_at = [&](int v) -> unsigned & { return reinterpret_cast<unsigned &>(s.R(P + v, X)); };  // P + 1600 <= edges <= c_slots in all eight codes
@@ -600,16 +607,21 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 	return frame;
 }
 
+#ifdef MB_LDPC_MAXNREG
+#define MB_LDPC_BOUNDS __maxnreg__(MB_LDPC_MAXNREG)
+#else
+#define MB_LDPC_BOUNDS __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS)
+#endif
 template <int ALGO>
-__global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
+__global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	unsigned char *const smem_raw = mb_smem;
+	if ((unsigned)__cvta_generic_to_shared(smem_raw) != kSmemBase) __trap();  // the immediates of lds2i assume it
 	const MbRate &rt = a.rate;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int CS = rt.c_slots;
 	Smem s;
 	s.raw = smem_raw;
-	s.sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
 	uint32_t *s_csched = reinterpret_cast<uint32_t *>(smem_raw + kOffR + r_bytes(CS));  // [8][16] check-group descriptors per warp
 	uint32_t *s_vsched = s_csched + MB_LDPC_WARPS * MB_SCHED_LEN;                       // [8][16] variable-group descriptors per warp
 	s.bytes = reinterpret_cast<unsigned char *>(s_vsched + MB_LDPC_WARPS * MB_SCHED_LEN);
@@ -617,11 +629,11 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 	s.next = reinterpret_cast<volatile int *>(s.cnt + 2 * MB_LDPC_WARPS);
 	s.csched = s_csched;
 	s.lch_g = a.lch_scratch + (size_t)blockIdx.x * (2 * MB_N);
-	const unsigned sbase = s.sbase;
+	constexpr unsigned sbase = Smem::sbase;
 
-	const uint16_t *__restrict__ g_edge_var = reinterpret_cast<const uint16_t *>(a.blob + rt.off_edge_varb);  // byte offsets into the posteriors
-	const uint16_t *__restrict__ g_vedge = reinterpret_cast<const uint16_t *>(a.blob + rt.off_vedgeb);        // byte offsets into the messages
-	const uint32_t *__restrict__ g_vtail = reinterpret_cast<const uint32_t *>(a.blob + rt.off_vtail);          // two byte offsets per degree-<=2 variable
+	const uint16_t *__restrict__ g_edge_var = a.edge_var;  // byte offsets into the posteriors
+	const uint16_t *__restrict__ g_vedge = a.vedge;        // byte offsets into the messages
+	const uint32_t *__restrict__ g_vtail = a.vtail;        // two byte offsets per degree-<=2 variable
 
 	if (tid < MB_LDPC_WARPS * MB_SCHED_LEN) {
 		s_csched[tid] = reinterpret_cast<const uint32_t *>(a.blob + rt.off_csched)[tid];
@@ -770,13 +782,13 @@ __global__ void __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS) mb_ldpc_kernel(con
 			const int v = vtail0 + tid + i * kThreads;
 			if (v < MB_N) {
 				const uint32_t w = __ldg(g_vtail + (v - vtail0));
-				const f2 r0 = lds2(sbase + kOffR + (w & 0xFFFFu)), r1 = lds2(sbase + kOffR + (w >> 16));
+				const f2 r0 = lds2i<kSmemBase + kOffR>(w & 0xFFFFu), r1 = lds2i<kSmemBase + kOffR>(w >> 16);
 				sts2(sbase + kOffLam + v * 8, __ffma2_rn(__fadd2_rn(r0, r1), vm, lt[i]));
 			}
 		}
 		for (int v = vtail0 + tid + kTailRegs * kThreads; v < MB_N; v += kThreads) {  // (not reached with the eight codes of the reference)
 			const uint32_t w = __ldg(g_vtail + (v - vtail0));
-			const f2 r0 = lds2(sbase + kOffR + (w & 0xFFFFu)), r1 = lds2(sbase + kOffR + (w >> 16));
+			const f2 r0 = lds2i<kSmemBase + kOffR>(w & 0xFFFFu), r1 = lds2i<kSmemBase + kOffR>(w >> 16);
 			sts2(sbase + kOffLam + v * 8, __ffma2_rn(__fadd2_rn(r0, r1), vm, s.get_lch(v)));
 		}
 		__syncthreads();
@@ -892,6 +904,9 @@ cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaS
 	const size_t resident = (size_t)g_sms * (size_t)mb_ldpc_ctas_per_sm(algo, rate_idx < 0 ? 0 : rate_idx, a.rate.rate_num, a.rate.c_slots);
 	MbLdpcArgs b = a;
 	b.n_frames = n_frames;
+	b.edge_var = reinterpret_cast<const uint16_t *>(a.blob + a.rate.off_edge_varb);
+	b.vedge = reinterpret_cast<const uint16_t *>(a.blob + a.rate.off_vedgeb);
+	b.vtail = reinterpret_cast<const uint32_t *>(a.blob + a.rate.off_vtail);
 	const size_t grid = std::min(std::min(resident, mb_ldpc_max_ctas()), (n_frames + 1) / 2);
 	k<<<(unsigned)grid, kThreads, smem, stream>>>(b);
 	return cudaGetLastError();

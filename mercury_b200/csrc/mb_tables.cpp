@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -338,6 +339,8 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 			off = bl.put(sched);
 			return true;
 		};
+		int kc[5] = {26, 25, 15, 37, 55};
+		if (const char *e = getenv("MERCURY_B200_LDPC_COST")) sscanf(e, "%d,%d,%d,%d,%d", &kc[0], &kc[1], &kc[2], &kc[3], &kc[4]);  // tuning only
 		std::vector<std::pair<int, uint32_t>> ctasks, vtasks;
 		for (int g = 0; g * 32 < P; g++) {
 			int S, Dp, l2 = 0;
@@ -347,7 +350,7 @@ std::string build_rate(Blob &bl, const RateTables &t, MbRate &out, std::vector<u
 				if (g * 32 + tk * (32 / S) >= P) break;  // no check left for this task (last group)
 				const uint32_t base = cgbase[g] + (uint32_t)(tk * Dp * 32);
 				if (base > 0xFFFFu || Dp > 15 || g + 1 > 127) return "check schedule overflow";
-				const int cost = Dp <= 2 && S == 1 ? 26 : (S == 1 ? 25 * Dp + 15 : 37 * Dp + 55);
+				const int cost = Dp <= 2 && S == 1 ? kc[0] : (S == 1 ? kc[1] * Dp + kc[2] : kc[3] * Dp + kc[4]);
 				ctasks.emplace_back(cost, base | ((uint32_t)Dp << 16) | ((uint32_t)l2 << 20) | ((uint32_t)tk << 22) | ((uint32_t)(g + 1) << 25));
 			}
 		}
