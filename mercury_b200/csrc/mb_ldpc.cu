@@ -419,7 +419,6 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 		if (tid < m.frame_bytes) a.payload[frame * (size_t)m.frame_bytes + tid] = (uint8_t)byte;
 	}
 	const int nonzero = __syncthreads_or((int)byte);
-	MbRxStats st;
 	if (tid < 32) {
 		const uint16_t *__restrict__ g_mat = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcmat);
 		uint16_t part = 0;
@@ -433,16 +432,13 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) adv ^= __shfl_xor_sync(0xffffffffu, adv, o);
 		if (tid == 0) {
-			st = a.stats[frame];
+			// only the fields the decoder owns are written (no read-modify-write: the record's load would sit on this warp's path to the refill)
 			const int all_zeros = nonzero ? 0 : 1;
 			const int crc = all_zeros ? 0 : (int)((adv ^ m.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
 			const int decoded = (!all_zeros && crc == 0) ? 1 : 0;               // telecom_system.cc:1343-1349
-			st.iterations_done = iterations;
-			st.crc = crc;
-			st.all_zeros = all_zeros;
-			st.message_decoded = decoded;
-			st.SNR = decoded ? st.SNR : -99.9f;
-			if (m.estimator == 1 || !decoded) a.stats[frame] = st;
+			MbRxStats *rec = a.stats + frame;
+			*reinterpret_cast<int4 *>(rec) = make_int4(iterations, crc, all_zeros, decoded);  // iterations_done, crc, all_zeros, message_decoded
+			if (!decoded) rec->SNR = -99.9f;
 			s.bytes[255] = (unsigned char)decoded;
 		}
 	}
@@ -527,8 +523,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 		if (tid == 0) {
 			float tot = 0.f;
 			for (int w = 0; w < kThreads / 32; w++) tot += s_acc[w];
-			st.SNR = -10.0f * log10f(tot / (float)m.nData);  // measure_SNR, ofdm.cc:1622-1635
-			a.stats[frame] = st;
+			a.stats[frame].SNR = -10.0f * log10f(tot / (float)m.nData);  // measure_SNR, ofdm.cc:1622-1635
 		}
 	}
 }
@@ -542,53 +537,52 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 {
 	const MbMode &m = a.mode;
 	const int tid = threadIdx.x;
+	constexpr int kPer = (MB_N + kThreads - 1) / kThreads;
 	int frame;
 	for (;;) {
 		// The ticket was published before a barrier every thread has passed (the end of the previous refill / the kernel prologue); the
 		// other word takes the ticket of the refill after this one, fetched by a thread of warp 1 (warp 0 may still be in the epilogue's
 		// CRC) and published by the barrier at the end of this refill.  No barrier here: the loads below overlap the epilogue's tail.
+		// Everything this refill reads from global memory -- the next ticket, the demodulator's gate value, the LLRs -- is requested
+		// BEFORE anything is waited for: one L2 round trip on the path to the barrier, not three.
 		const int turn = *s.turn;
 		const unsigned f = (unsigned)s.next[turn];
 		*s.turn = turn ^ 1;
-		if (tid == 32) s.next[turn ^ 1] = (int)atomicAdd(a.queue, 1u);
+		unsigned nxt = 0u;
+		if (tid == 32) nxt = atomicAdd(a.queue, 1u);
 		if ((unsigned long long)f >= a.n_frames) {
+			if (tid == 32) s.next[turn ^ 1] = (int)nxt;
 			frame = -1;
 			break;
 		}
-		frame = (int)f;
 		{
 			const unsigned long long ahead = (unsigned long long)f + 2ull * gridDim.x;
 			if (ahead < a.n_frames && tid < (MB_N * 4 + 127) / 128)
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.llr + ahead * MB_HANDOFF_STRIDE) + tid * 128));
 		}
-		if (a.check_gate && !(a.stats[f].mean_H >= 0.3f)) {
-			// telecom_system.cc:1268-1280: a channel estimate this weak means a false sync; the reference skips the decode
-			for (int i = tid; i < m.frame_bytes; i += kThreads) a.payload[f * (size_t)m.frame_bytes + i] = 0;
-			if (tid == 0) {
-				MbRxStats st = a.stats[f];
-				st.iterations_done = -1;
-				st.crc = 0;
-				st.all_zeros = 0;
-				st.message_decoded = 0;
-				st.SNR = -99.9f;
-				a.stats[f] = st;
-			}
-			__syncthreads();  // the next ticket is visible
-			continue;
-		}
-		break;
-	}
-	if (frame >= 0) {
 		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores.
-		// Base-2 units from here on; "+ 0" turns an LLR of -0 into +0 (hard decision 0 like the reference's `< 0` test).
-		const float *__restrict__ src = a.llr + (size_t)frame * MB_HANDOFF_STRIDE;
-		constexpr int kPer = (MB_N + kThreads - 1) / kThreads;
+		const float *__restrict__ src = a.llr + (size_t)f * MB_HANDOFF_STRIDE;
 		float v[kPer];
 #pragma unroll
 		for (int j = 0; j < kPer; j++) {
 			const int i = tid + j * kThreads;
 			v[j] = i < MB_N ? ldg_stream(src + i) : 0.f;  // all loads in flight together; no L1 allocation (the index tables live there)
 		}
+		const float mean_H = a.check_gate ? ldg_stream(&a.stats[f].mean_H) : 1.0f;
+		if (tid == 32) s.next[turn ^ 1] = (int)nxt;
+		if (!(mean_H >= 0.3f)) {
+			// telecom_system.cc:1268-1280: a channel estimate this weak means a false sync; the reference skips the decode
+			for (int i = tid; i < m.frame_bytes; i += kThreads) a.payload[f * (size_t)m.frame_bytes + i] = 0;
+			if (tid == 0) {
+				MbRxStats *rec = a.stats + f;
+				*reinterpret_cast<int4 *>(rec) = make_int4(-1, 0, 0, 0);  // iterations_done, crc, all_zeros, message_decoded
+				rec->SNR = -99.9f;
+			}
+			__syncthreads();  // the next ticket is visible
+			continue;
+		}
+		frame = (int)f;
+		// Base-2 units from here on; "+ 0" turns an LLR of -0 into +0 (hard decision 0 like the reference's `< 0` test).
 #pragma unroll
 		for (int j = 0; j < kPer; j++) {
 			const int i = tid + j * kThreads;
@@ -599,9 +593,10 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 				s.set_lch((int)p, X, w);
 			}
 		}
-	} else {
-		for (int i = tid; i < MB_N; i += kThreads) s.lam(i, X) = 1.0f, s.set_lch(i, X, 1.0f);
+		break;
 	}
+	if (frame < 0)
+		for (int i = tid; i < MB_N; i += kThreads) s.lam(i, X) = 1.0f, s.set_lch(i, X, 1.0f);
 	// the slot's old messages stay where they are: until its first check pass has rewritten them they are multiplied by 0 (the kernel's nm / vm)
 	__syncthreads();
 	return frame;

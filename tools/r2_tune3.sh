@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 T=${1:-r2w}
 VARS=${2:-"x8 x6 x6r x5 x5r x4"}
 MODES=${3:-"8 0 9"}
-MERCURY_B200_SO=$PWD/tuning/libmb_x8.so timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/${T}_pytest_x8.log 2>&1; tail -3 gpurun_out/${T}_pytest_x8.log
+MERCURY_B200_SO=$PWD/tuning/libmb_${PV:-x8}.so timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
 run() { name=$1; shift; env "$@" timeout 300 python bench.py --no-e2e --no-extra --cpu-frames 0 --steps 5 $BARGS > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err; }
 for cfg in $MODES; do BARGS="--config $cfg"
 for v in $VARS; do run m${cfg}_$v MERCURY_B200_SO=$PWD/tuning/libmb_$v.so; done
