@@ -57,7 +57,12 @@ typedef float2 f2;
 
 // shared-memory layout (bytes from the start of the dynamic segment); constant offsets keep every hot access [reg + imm].
 // Every array is float2: .x = slot A, .y = slot B.
-constexpr int kOffLam = 0;                         // f2[1601] posterior; [1600] = +inf, the variable every padding slot points at
+constexpr int kOffBytes = 0;                       // u8[256] packed bytes of the frame being finished; [255] = its verdict
+constexpr int kOffCnt = 256;                       // u32[2][MB_LDPC_WARPS] per-warp vote counts (check pass, syndrome test): A | B << 16
+constexpr int kOffNext = 384;                      // int[2] queue hand-off: tickets of the next two refills, alternating
+constexpr int kOffCsched = 512;                    // u32[MB_LDPC_WARPS][MB_SCHED_LEN] check tasks per warp
+constexpr int kOffVsched = kOffCsched + MB_LDPC_WARPS * MB_SCHED_LEN * 4;  // ... variable groups per warp
+constexpr int kOffLam = kOffVsched + MB_LDPC_WARPS * MB_SCHED_LEN * 4;     // f2[1601] posterior; [1600] = +inf, the variable every padding slot points at
 // The channel LLRs are NOT in shared memory: they are read once per iteration and variable, in order, so they live in a per-CTA global
 // scratch (L2 resident, 12.8 KB per pair, written at refill) and are streamed past L1.  That keeps three pairs per SM inside 196 KB of
 // shared memory and leaves the L1 60 KB instead of 28 KB: the index tables (22-28 KB per rate, gathered by every warp in every pass)
@@ -65,9 +70,9 @@ constexpr int kOffLam = 0;                         // f2[1601] posterior; [1600]
 #ifndef MB_LDPC_LCH_SMEM
 #define MB_LDPC_LCH_SMEM 0
 #endif
-constexpr int kOffLch = (MB_N + 2) * 8;            // f2[1600] channel LLR (only with MB_LDPC_LCH_SMEM)
+constexpr int kOffLch = kOffLam + (MB_N + 2) * 8;  // f2[1600] channel LLR (only with MB_LDPC_LCH_SMEM)
 constexpr int kOffR = kOffLch + (MB_LDPC_LCH_SMEM ? MB_N * 8 : 0);  // f2[c_slots + 1] check -> variable message per check-side slot; [c_slots] == 0 always
-constexpr int kMiscBytes = 512;                    // packed bytes of the epilogue [256] + vote counters + queue hand-off
+static_assert(2 * MB_LDPC_WARPS * 4 <= kOffNext - kOffCnt && kOffLam % 16 == 0, "decoder shared-memory layout");
 
 __host__ __device__ constexpr int r_bytes(int c_slots) { return ((c_slots + 2) & ~1) * 8; }
 
@@ -373,19 +378,21 @@ __device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
 	return crc;
 }
 
+// Shared-memory views: every address is mb_smem + a compile-time constant (the noinline epilogue / refill used to chase these pointers
+// through a struct in local memory, one dependent load per store).  Passed BY VALUE: the only datum is the scratch pointer.
 struct Smem {
-	unsigned char *raw;
 	static constexpr unsigned sbase = kSmemBase;
-	unsigned char *bytes;   // [256] packed bytes of the frame being finished; [255] = its verdict
-	unsigned *cnt;          // [2][MB_LDPC_WARPS] per-warp vote counts (check pass, syndrome test): A | B << 16
-	volatile int *next;     // [2] queue hand-off: tickets of the next two refills, alternating (no barrier between reading one and fetching the next)
-	int *turn;              // which of the two holds the next refill's ticket (register copy per thread, uniform)
-	const uint32_t *csched; // [MB_LDPC_WARPS][MB_SCHED_LEN] check tasks per warp (shared-memory copy)
-	__device__ __forceinline__ float &lam(int v, int X) const { return reinterpret_cast<float *>(raw + kOffLam)[2 * v + X]; }
 	float *lch_g;           // this CTA's channel-LLR scratch in global memory, f2[1600] (x = slot A, y = slot B)
+	__device__ __forceinline__ static unsigned char *bytes() { return mb_smem + kOffBytes; }
+	__device__ __forceinline__ static unsigned *cnt() { return reinterpret_cast<unsigned *>(mb_smem + kOffCnt); }
+	__device__ __forceinline__ static volatile int *next() { return reinterpret_cast<volatile int *>(mb_smem + kOffNext); }
+	__device__ __forceinline__ static uint32_t *csched() { return reinterpret_cast<uint32_t *>(mb_smem + kOffCsched); }
+	__device__ __forceinline__ static uint32_t *vsched() { return reinterpret_cast<uint32_t *>(mb_smem + kOffVsched); }
+	__device__ __forceinline__ static float &lam(int v, int X) { return reinterpret_cast<float *>(mb_smem + kOffLam)[2 * v + X]; }
+	__device__ __forceinline__ static float &R(int i, int X) { return reinterpret_cast<float *>(mb_smem + kOffR)[2 * i + X]; }
 	__device__ __forceinline__ void set_lch(int v, int X, float w) const
 	{
-		if (MB_LDPC_LCH_SMEM) reinterpret_cast<float *>(raw + kOffLch)[2 * v + X] = w;
+		if (MB_LDPC_LCH_SMEM) reinterpret_cast<float *>(mb_smem + kOffLch)[2 * v + X] = w;
 		else lch_g[2 * v + X] = w;
 	}
 	__device__ __forceinline__ f2 get_lch(int v) const
@@ -395,12 +402,51 @@ struct Smem {
 		asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(lch_g + 2 * v));
 		return r;
 	}
-	__device__ __forceinline__ float &R(int i, int X) const { return reinterpret_cast<float *>(raw + kOffR)[2 * i + X]; }
 };
+// The fields of the launch arguments the epilogue / refill need right away, by value (registers): through the reference they are
+// generic loads from the parameter block, each one a dependent round trip before the first useful request leaves.
+struct Hot {
+	const float *llr;
+	MbRxStats *stats;
+	unsigned *queue;
+	unsigned long long n_frames;
+	int check_gate;
+};
+
+// ---- CRC16 of the packed bytes + the frame's record: warp 0 (32 chunk CRCs advanced to the end by the mode's matrices) ---------------
+__device__ __forceinline__ void crc_and_record(const MbLdpcArgs &a, const Smem s, const Hot h, size_t frame, int iterations, int nonzero)
+{
+	const MbMode &m = a.mode;
+	const int tid = threadIdx.x;
+	const uint16_t *__restrict__ g_mat = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcmat);
+	uint16_t part = 0;
+	const int b0 = tid * m.crc_chunk;
+	for (int i = 0; i < m.crc_chunk; i++)
+		if (b0 + i < m.crc_bytes) part = crc_step_byte(part, s.bytes()[b0 + i]);
+	unsigned adv = 0;
+#pragma unroll
+	for (int b = 0; b < 16; b++)
+		if ((part >> b) & 1) adv ^= g_mat[tid * 16 + b];
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) adv ^= __shfl_xor_sync(0xffffffffu, adv, o);
+	if (tid == 0) {
+		// only the fields the decoder owns are written (no read-modify-write: the record's load would sit on this warp's path to the refill)
+		const int all_zeros = nonzero ? 0 : 1;
+		const int crc = all_zeros ? 0 : (int)((adv ^ m.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
+		const int decoded = (!all_zeros && crc == 0) ? 1 : 0;               // telecom_system.cc:1343-1349
+		MbRxStats *rec = h.stats + frame;
+		*reinterpret_cast<int4 *>(rec) = make_int4(iterations, crc, all_zeros, decoded);  // iterations_done, crc, all_zeros, message_decoded
+		if (!decoded) rec->SNR = -99.9f;
+		s.bytes()[255] = (unsigned char)decoded;
+	}
+}
 
 // ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record (+ the ZF modes' SNR report) of slot X ------------
 // Called by the whole CTA (uniform); the other slot's interleaved state is not touched.
-__device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int X, size_t frame, int iterations)
+// LS modes: returns the "any payload bit set" flag (0 / 1) with the CRC and the record still TO DO -- refill_slot() runs them on warp 0
+// after it has requested the next frame's data, so the warp every refill waits for no longer arrives a CRC late.  ZF modes: returns -1,
+// everything done here.
+__device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, size_t frame, int iterations)
 {
 	const MbMode &m = a.mode;
 	const MbRate &rt = a.rate;
@@ -415,34 +461,16 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 			const unsigned bit = (fbits(s.lam(g_bit_var[i], X)) >> 31) ^ (unsigned)g_scr[i];  // hard decision = sign bit (LLR < 0)
 			byte |= bit << b;
 		}
-		s.bytes[tid] = (unsigned char)byte;
+		s.bytes()[tid] = (unsigned char)byte;
 		if (tid < m.frame_bytes) a.payload[frame * (size_t)m.frame_bytes + tid] = (uint8_t)byte;
 	}
 	const int nonzero = __syncthreads_or((int)byte);
-	if (tid < 32) {
-		const uint16_t *__restrict__ g_mat = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcmat);
-		uint16_t part = 0;
-		const int b0 = tid * m.crc_chunk;
-		for (int i = 0; i < m.crc_chunk; i++)
-			if (b0 + i < m.crc_bytes) part = crc_step_byte(part, s.bytes[b0 + i]);
-		unsigned adv = 0;
-#pragma unroll
-		for (int b = 0; b < 16; b++)
-			if ((part >> b) & 1) adv ^= g_mat[tid * 16 + b];
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) adv ^= __shfl_xor_sync(0xffffffffu, adv, o);
-		if (tid == 0) {
-			// only the fields the decoder owns are written (no read-modify-write: the record's load would sit on this warp's path to the refill)
-			const int all_zeros = nonzero ? 0 : 1;
-			const int crc = all_zeros ? 0 : (int)((adv ^ m.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
-			const int decoded = (!all_zeros && crc == 0) ? 1 : 0;               // telecom_system.cc:1343-1349
-			MbRxStats *rec = a.stats + frame;
-			*reinterpret_cast<int4 *>(rec) = make_int4(iterations, crc, all_zeros, decoded);  // iterations_done, crc, all_zeros, message_decoded
-			if (!decoded) rec->SNR = -99.9f;
-			s.bytes[255] = (unsigned char)decoded;
-		}
-	}
-	if (m.estimator == 1) return;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
+#ifndef MB_LDPC_DEFER_CRC
+#define MB_LDPC_DEFER_CRC 1
+#endif
+	if (MB_LDPC_DEFER_CRC && m.estimator == 1) return nonzero ? 1 : 0;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
+	if (tid < 32) crc_and_record(a, s, h, frame, iterations, nonzero);
+	if (m.estimator == 1) return -1;
 
 	// ---- ZF modes: SNR report of a decoded frame (telecom_system.cc:1376-1400) -----------------------------------------
 	// Re-encode the hard decisions (scrambled info bits, virtual copies, IRA parity), re-map them onto the constellation through
@@ -450,7 +478,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 	// data symbols (kept by the demodulator behind the LLRs of the hand-off record) to the re-encoded ones (ofdm.cc:1622-1635).
 	// Scratch: this slot's messages are dead: [0, P) data parity per check, [P, P + 1600) re-encoded bit per internal variable.
 	__syncthreads();
-	if (!s.bytes[255]) return;
+	if (!s.bytes()[255]) return -1;
 	const uint16_t *__restrict__ g_edge_var = a.edge_var;
 	const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + rt.off_var_of_cw);
 	const int K = m.K, P = rt.P, nReal = m.nReal, nVirtual = m.nVirtual;
@@ -466,7 +494,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 	__syncthreads();
 	{  // cl_ldpc::encode (ldpc.cc:111-132): every check row is {data bits, parity i-1, parity i}, so parity = running XOR of the data parities
 		const uint16_t *__restrict__ g_cos = reinterpret_cast<const uint16_t *>(a.blob + rt.off_check_of_sorted);
-		const uint32_t *sched = s.csched + warp * MB_SCHED_LEN;
+		const uint32_t *sched = s.csched() + warp * MB_SCHED_LEN;
 		for (uint32_t desc = *sched; desc != 0u; desc = *++sched) {  // this warp's check tasks, in the check pass's layout
 			const int dp = (int)MB_CDESC_DP(desc), l2 = (int)MB_CDESC_LOG2S(desc), per = 32 >> l2;
 			const uint16_t *__restrict__ ve = g_edge_var + MB_CDESC_BASE(desc) + lane;
@@ -516,7 +544,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 		}
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-		float *s_acc = reinterpret_cast<float *>(s.bytes);  // the packed bytes are dead now
+		float *s_acc = reinterpret_cast<float *>(s.bytes());  // the packed bytes are dead now
 		__syncthreads();
 		if (lane == 0) s_acc[warp] = acc;
 		__syncthreads();
@@ -526,6 +554,7 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 			a.stats[frame].SNR = -10.0f * log10f(tot / (float)m.nData);  // measure_SNR, ofdm.cc:1622-1635
 		}
 	}
+	return -1;
 }
 
 // ---- next frame of the batch into slot X (uniform).  Returns its index, or -1 when the queue is empty (the slot then holds an
@@ -533,7 +562,9 @@ __device__ __noinline__ void finish_slot(const MbLdpcArgs &a, const Smem &s, int
 // The queue is read one grab ahead (thread 0 holds the ticket of the NEXT refill in shared memory, so the atomic's latency is never
 // waited for), and every grab prefetches into L2 the LLRs of the frame that will be handed out one "wave" of resident slots later
 // (frames are handed out in order), so a refill reads L2, not DRAM, while the pair's other slot waits.
-__device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int X)
+// `turn`: which of the two ticket words holds this refill's ticket (uniform; the caller keeps it).  Returns {frame, next turn}.
+__device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, int turn, long long done_frame = -1, int done_iterations = 0,
+					  int done_nonzero = 0)
 {
 	const MbMode &m = a.mode;
 	const int tid = threadIdx.x;
@@ -545,36 +576,38 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 		// CRC) and published by the barrier at the end of this refill.  No barrier here: the loads below overlap the epilogue's tail.
 		// Everything this refill reads from global memory -- the next ticket, the demodulator's gate value, the LLRs -- is requested
 		// BEFORE anything is waited for: one L2 round trip on the path to the barrier, not three.
-		const int turn = *s.turn;
-		const unsigned f = (unsigned)s.next[turn];
-		*s.turn = turn ^ 1;
+		const unsigned f = (unsigned)s.next()[turn];
+		turn ^= 1;
 		unsigned nxt = 0u;
-		if (tid == 32) nxt = atomicAdd(a.queue, 1u);
-		if ((unsigned long long)f >= a.n_frames) {
-			if (tid == 32) s.next[turn ^ 1] = (int)nxt;
+		if (tid == 32) nxt = atomicAdd(h.queue, 1u);
+		if ((unsigned long long)f >= h.n_frames) {
+			if (done_frame >= 0 && tid < 32) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);
+			if (tid == 32) s.next()[turn] = (int)nxt;
 			frame = -1;
 			break;
 		}
 		{
 			const unsigned long long ahead = (unsigned long long)f + 2ull * gridDim.x;
-			if (ahead < a.n_frames && tid < (MB_N * 4 + 127) / 128)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.llr + ahead * MB_HANDOFF_STRIDE) + tid * 128));
+			if (ahead < h.n_frames && tid < (MB_N * 4 + 127) / 128)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(h.llr + ahead * MB_HANDOFF_STRIDE) + tid * 128));
 		}
 		// hand-off layout: every 32-float row arrives rotated by its row index (MB_HANDOFF); coalesced loads, conflict-free stores.
-		const float *__restrict__ src = a.llr + (size_t)f * MB_HANDOFF_STRIDE;
+		const float *__restrict__ src = h.llr + (size_t)f * MB_HANDOFF_STRIDE;
 		float v[kPer];
 #pragma unroll
 		for (int j = 0; j < kPer; j++) {
 			const int i = tid + j * kThreads;
 			v[j] = i < MB_N ? ldg_stream(src + i) : 0.f;  // all loads in flight together; no L1 allocation (the index tables live there)
 		}
-		const float mean_H = a.check_gate ? ldg_stream(&a.stats[f].mean_H) : 1.0f;
-		if (tid == 32) s.next[turn ^ 1] = (int)nxt;
+		const float mean_H = h.check_gate ? ldg_stream(&h.stats[f].mean_H) : 1.0f;
+		if (done_frame >= 0 && tid < 32) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);  // while the loads travel
+		done_frame = -1;
+		if (tid == 32) s.next()[turn] = (int)nxt;
 		if (!(mean_H >= 0.3f)) {
 			// telecom_system.cc:1268-1280: a channel estimate this weak means a false sync; the reference skips the decode
 			for (int i = tid; i < m.frame_bytes; i += kThreads) a.payload[f * (size_t)m.frame_bytes + i] = 0;
 			if (tid == 0) {
-				MbRxStats *rec = a.stats + f;
+				MbRxStats *rec = h.stats + f;
 				*reinterpret_cast<int4 *>(rec) = make_int4(-1, 0, 0, 0);  // iterations_done, crc, all_zeros, message_decoded
 				rec->SNR = -99.9f;
 			}
@@ -599,7 +632,14 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 		for (int i = tid; i < MB_N; i += kThreads) s.lam(i, X) = 1.0f, s.set_lch(i, X, 1.0f);
 	// the slot's old messages stay where they are: until its first check pass has rewritten them they are multiplied by 0 (the kernel's nm / vm)
 	__syncthreads();
-	return frame;
+	return make_int2(frame, turn);
+}
+
+// a finished frame leaves slot X, the next one of the queue enters; returns {the new frame's index (-1: queue empty), next turn}
+__device__ __forceinline__ int2 retire_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, int turn, int frame, int iterations)
+{
+	const int todo = finish_slot(a, s, h, X, (size_t)frame, iterations);  // >= 0: CRC + record left to refill_slot()
+	return refill_slot(a, s, h, X, turn, todo >= 0 ? (long long)frame : -1ll, iterations, todo);
 }
 
 #ifdef MB_LDPC_MAXNREG
@@ -610,20 +650,15 @@ __device__ __noinline__ int refill_slot(const MbLdpcArgs &a, const Smem &s, int 
 template <int ALGO>
 __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
 {
-	unsigned char *const smem_raw = mb_smem;
-	if ((unsigned)__cvta_generic_to_shared(smem_raw) != kSmemBase) __trap();  // the immediates of lds2i assume it
+	if ((unsigned)__cvta_generic_to_shared(mb_smem) != kSmemBase) __trap();  // the immediates of lds2i assume it
 	const MbRate &rt = a.rate;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int CS = rt.c_slots;
 	Smem s;
-	s.raw = smem_raw;
-	uint32_t *s_csched = reinterpret_cast<uint32_t *>(smem_raw + kOffR + r_bytes(CS));  // [8][16] check-group descriptors per warp
-	uint32_t *s_vsched = s_csched + MB_LDPC_WARPS * MB_SCHED_LEN;                       // [8][16] variable-group descriptors per warp
-	s.bytes = reinterpret_cast<unsigned char *>(s_vsched + MB_LDPC_WARPS * MB_SCHED_LEN);
-	s.cnt = reinterpret_cast<unsigned *>(s.bytes + 256);
-	s.next = reinterpret_cast<volatile int *>(s.cnt + 2 * MB_LDPC_WARPS);
-	s.csched = s_csched;
+	uint32_t *const s_csched = Smem::csched();  // [warps][16] check-task descriptors per warp
+	uint32_t *const s_vsched = Smem::vsched();  // [warps][16] variable-group descriptors per warp
 	s.lch_g = a.lch_scratch + (size_t)blockIdx.x * (2 * MB_N);
+	const Hot hot = {a.llr, a.stats, a.queue, a.n_frames, a.check_gate};
 	constexpr unsigned sbase = Smem::sbase;
 
 	const uint16_t *__restrict__ g_edge_var = a.edge_var;  // byte offsets into the posteriors
@@ -638,16 +673,19 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 		s.lam(MB_N, 0) = __int_as_float(0x7f800000);  // +inf: a padding edge contributes e = 0, sign +, hard bit 0
 		s.lam(MB_N, 1) = __int_as_float(0x7f800000);
 	}
-	for (int i = tid; i < 2 * (CS + 1); i += kThreads) reinterpret_cast<float *>(smem_raw + kOffR)[i] = 0.f;  // once: 0 x (stale finite message) is 0, 0 x (garbage NaN) is not
-	int turn_reg = 0;
-	s.turn = &turn_reg;
-	if (tid == 32) s.next[0] = (int)atomicAdd(a.queue, 1u);
+	for (int i = tid; i < 2 * (CS + 1); i += kThreads) reinterpret_cast<float *>(mb_smem + kOffR)[i] = 0.f;  // once: 0 x (stale finite message) is 0, 0 x (garbage NaN) is not
+	int turn = 0;  // which ticket word the next refill reads (uniform)
+	if (tid == 32) s.next()[0] = (int)atomicAdd(a.queue, 1u);
 	__syncthreads();
 	int frame[2];
 	int pass[2] = {0, 0};  // check passes this slot's frame has been through = iterations completed
 	bool virgin[2] = {true, true};  // refilled, messages not yet rewritten by a check pass
-	frame[0] = refill_slot(a, s, 0);
-	frame[1] = refill_slot(a, s, 1);
+	{
+		int2 r = refill_slot(a, s, hot, 0, turn);
+		frame[0] = r.x;
+		r = refill_slot(a, s, hot, 1, r.y);
+		frame[1] = r.x, turn = r.y;
+	}
 
 	const int vtail0 = rt.vtail_start;
 	while (frame[0] >= 0 || frame[1] >= 0) {
@@ -706,12 +744,12 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 		// threads that saw an unsatisfied check, per slot: 0 = converged; a small count = "probably one iteration to go"
 		{
 			const unsigned ba = __ballot_sync(0xffffffffu, hard_a != 0u), bb = __ballot_sync(0xffffffffu, hard_b != 0u);
-			if (lane == 0) s.cnt[warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
+			if (lane == 0) s.cnt()[warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
 		}
 		__syncthreads();
 		unsigned tot = 0;
 #pragma unroll
-		for (int w = 0; w < MB_LDPC_WARPS; w++) tot += s.cnt[w];
+		for (int w = 0; w < MB_LDPC_WARPS; w++) tot += s.cnt()[w];
 		int n_unsat[2] = {(int)(tot & 0xFFFFu), (int)(tot >> 16)};
 		bool fresh[2] = {false, false};
 #pragma unroll
@@ -723,8 +761,8 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 			else if (pass[X] == a.max_iters)
 				iterations = a.max_iters + 1;  // ldpc_decoder_SPA.cc:127,217: loop ran out
 			if (iterations >= 0) {
-				finish_slot(a, s, X, (size_t)frame[X], iterations);
-				frame[X] = refill_slot(a, s, X);
+				const int2 r = retire_slot(a, s, hot, X, turn, frame[X], iterations);
+				frame[X] = r.x, turn = r.y;
 				pass[X] = 0;
 				fresh[X] = true;
 				virgin[X] = true;
@@ -811,21 +849,21 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 			MB_PARITY_LOOP(8)
 #undef MB_PARITY_LOOP
 			const unsigned ba = __ballot_sync(0xffffffffu, bad_a != 0u), bb = __ballot_sync(0xffffffffu, bad_b != 0u);
-			if (lane == 0) s.cnt[MB_LDPC_WARPS + warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
+			if (lane == 0) s.cnt()[MB_LDPC_WARPS + warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
 			__syncthreads();
 			unsigned t2 = 0;
 #pragma unroll
-			for (int w = 0; w < MB_LDPC_WARPS; w++) t2 += s.cnt[MB_LDPC_WARPS + w];
+			for (int w = 0; w < MB_LDPC_WARPS; w++) t2 += s.cnt()[MB_LDPC_WARPS + w];
 			const bool done_a = try_a && (t2 & 0xFFFFu) == 0u, done_b = try_b && (t2 >> 16) == 0u;
 			if (done_a) {  // exactly what the next check pass would have reported
-				finish_slot(a, s, 0, (size_t)frame[0], pass[0]);
-				frame[0] = refill_slot(a, s, 0);
+				const int2 r = retire_slot(a, s, hot, 0, turn, frame[0], pass[0]);
+				frame[0] = r.x, turn = r.y;
 				pass[0] = 0;
 				virgin[0] = true;
 			}
 			if (done_b) {
-				finish_slot(a, s, 1, (size_t)frame[1], pass[1]);
-				frame[1] = refill_slot(a, s, 1);
+				const int2 r = retire_slot(a, s, hot, 1, turn, frame[1], pass[1]);
+				frame[1] = r.x, turn = r.y;
 				pass[1] = 0;
 				virgin[1] = true;
 			}
@@ -847,7 +885,7 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 
 size_t mb_ldpc_smem_bytes(int c_slots)
 {
-	return (size_t)kOffR + (size_t)r_bytes(c_slots) + 2 * MB_LDPC_WARPS * MB_SCHED_LEN * sizeof(uint32_t) + kMiscBytes;
+	return (size_t)kOffR + (size_t)r_bytes(c_slots);
 }
 
 namespace {
