@@ -370,14 +370,6 @@ __device__ __forceinline__ void check_parity(unsigned sbase, const uint16_t *__r
 	bad_b |= hb >> 31;
 }
 
-__device__ __forceinline__ uint16_t crc_step_byte(uint16_t crc, unsigned byte)
-{
-	crc ^= (uint16_t)byte;
-#pragma unroll
-	for (int i = 0; i < 8; i++) crc = (crc & 1) ? (uint16_t)((crc >> 1) ^ 0xA001) : (uint16_t)(crc >> 1);
-	return crc;
-}
-
 // Shared-memory views: every address is mb_smem + a compile-time constant (the noinline epilogue / refill used to chase these pointers
 // through a struct in local memory, one dependent load per store).  Passed BY VALUE: the only datum is the scratch pointer.
 struct Smem {
@@ -413,32 +405,23 @@ struct Hot {
 	int check_gate;
 };
 
-// ---- CRC16 of the packed bytes + the frame's record: warp 0 (32 chunk CRCs advanced to the end by the mode's matrices) ---------------
+// ---- the frame's record: thread 0 folds the per-warp CRC words the epilogue left in shared memory (the CRC is linear: XOR over the
+// message's set bits of a per-bit table, MbMode::off_crcbit) --------------------------------------------------------------------------
 __device__ __forceinline__ void crc_and_record(const MbLdpcArgs &a, const Smem s, const Hot h, size_t frame, int iterations, int nonzero)
 {
-	const MbMode &m = a.mode;
-	const int tid = threadIdx.x;
-	const uint16_t *__restrict__ g_mat = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcmat);
-	uint16_t part = 0;
-	const int b0 = tid * m.crc_chunk;
-	for (int i = 0; i < m.crc_chunk; i++)
-		if (b0 + i < m.crc_bytes) part = crc_step_byte(part, s.bytes()[b0 + i]);
+	if (threadIdx.x != 0) return;
+	const unsigned *crcw = reinterpret_cast<const unsigned *>(s.bytes());
 	unsigned adv = 0;
 #pragma unroll
-	for (int b = 0; b < 16; b++)
-		if ((part >> b) & 1) adv ^= g_mat[tid * 16 + b];
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) adv ^= __shfl_xor_sync(0xffffffffu, adv, o);
-	if (tid == 0) {
-		// only the fields the decoder owns are written (no read-modify-write: the record's load would sit on this warp's path to the refill)
-		const int all_zeros = nonzero ? 0 : 1;
-		const int crc = all_zeros ? 0 : (int)((adv ^ m.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
-		const int decoded = (!all_zeros && crc == 0) ? 1 : 0;               // telecom_system.cc:1343-1349
-		MbRxStats *rec = h.stats + frame;
-		*reinterpret_cast<int4 *>(rec) = make_int4(iterations, crc, all_zeros, decoded);  // iterations_done, crc, all_zeros, message_decoded
-		if (!decoded) rec->SNR = -99.9f;
-		s.bytes()[255] = (unsigned char)decoded;
-	}
+	for (int w = 0; w < MB_LDPC_WARPS; w++) adv ^= crcw[w];
+	// only the fields the decoder owns are written (no read-modify-write: the record's load would sit on this warp's path to the refill)
+	const int all_zeros = nonzero ? 0 : 1;
+	const int crc = all_zeros ? 0 : (int)((adv ^ a.mode.crc_init) & 0xFFFFu);  // telecom_system.cc:1337-1341
+	const int decoded = (!all_zeros && crc == 0) ? 1 : 0;                    // telecom_system.cc:1343-1349
+	MbRxStats *rec = h.stats + frame;
+	*reinterpret_cast<int4 *>(rec) = make_int4(iterations, crc, all_zeros, decoded);  // iterations_done, crc, all_zeros, message_decoded
+	if (!decoded) rec->SNR = -99.9f;
+	s.bytes()[255] = (unsigned char)decoded;
 }
 
 // ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record (+ the ZF modes' SNR report) of slot X ------------
@@ -453,23 +436,30 @@ __device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint16_t *__restrict__ g_bit_var = reinterpret_cast<const uint16_t *>(a.blob + m.off_bit_var);
 	const uint8_t *__restrict__ g_scr = a.blob + m.off_scr;
-	unsigned byte = 0;
+	const uint16_t *__restrict__ g_crcbit = reinterpret_cast<const uint16_t *>(a.blob + m.off_crcbit);
+	unsigned byte = 0, crcw = 0;
 	if (tid < m.crc_bytes) {
+		unsigned tb[8];
+#pragma unroll
+		for (int b = 0; b < 8; b++) tb[b] = g_crcbit[tid * 8 + b];  // requested with the bit tables, not after the decisions
 #pragma unroll
 		for (int b = 0; b < 8; b++) {
 			const int i = tid * 8 + b;
 			const unsigned bit = (fbits(s.lam(g_bit_var[i], X)) >> 31) ^ (unsigned)g_scr[i];  // hard decision = sign bit (LLR < 0)
 			byte |= bit << b;
+			crcw ^= (0u - bit) & tb[b];
 		}
-		s.bytes()[tid] = (unsigned char)byte;
 		if (tid < m.frame_bytes) a.payload[frame * (size_t)m.frame_bytes + tid] = (uint8_t)byte;
 	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) crcw ^= __shfl_xor_sync(0xffffffffu, crcw, o);
+	if (lane == 0) reinterpret_cast<unsigned *>(s.bytes())[warp] = crcw;
 	const int nonzero = __syncthreads_or((int)byte);
 #ifndef MB_LDPC_DEFER_CRC
 #define MB_LDPC_DEFER_CRC 1
 #endif
 	if (MB_LDPC_DEFER_CRC && m.estimator == 1) return nonzero ? 1 : 0;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
-	if (tid < 32) crc_and_record(a, s, h, frame, iterations, nonzero);
+	crc_and_record(a, s, h, frame, iterations, nonzero);
 	if (m.estimator == 1) return -1;
 
 	// ---- ZF modes: SNR report of a decoded frame (telecom_system.cc:1376-1400) -----------------------------------------
@@ -581,7 +571,7 @@ __device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, cons
 		unsigned nxt = 0u;
 		if (tid == 32) nxt = atomicAdd(h.queue, 1u);
 		if ((unsigned long long)f >= h.n_frames) {
-			if (done_frame >= 0 && tid < 32) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);
+			if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);
 			if (tid == 32) s.next()[turn] = (int)nxt;
 			frame = -1;
 			break;
@@ -600,7 +590,7 @@ __device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, cons
 			v[j] = i < MB_N ? ldg_stream(src + i) : 0.f;  // all loads in flight together; no L1 allocation (the index tables live there)
 		}
 		const float mean_H = h.check_gate ? ldg_stream(&h.stats[f].mean_H) : 1.0f;
-		if (done_frame >= 0 && tid < 32) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);  // while the loads travel
+		if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);  // while the loads travel
 		done_frame = -1;
 		if (tid == 32) s.next()[turn] = (int)nxt;
 		if (!(mean_H >= 0.3f)) {

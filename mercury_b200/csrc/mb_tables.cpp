@@ -404,6 +404,20 @@ uint16_t crc_zero_byte(uint16_t s)  // advance the reflected CRC-16/MODBUS regis
 	for (int i = 0; i < 8; i++) s = (s & 1) ? (uint16_t)((s >> 1) ^ 0xA001) : (uint16_t)(s >> 1);
 	return s;
 }
+// The CRC is linear over GF(2): with preset 0 it is the XOR, over the set bits of the message, of the register a message with only
+// that bit set leaves after all n_bytes bytes.  The decoder's epilogue XORs these per thread (one byte each) and reduces over the CTA.
+std::vector<uint16_t> crc_bit_table(int n_bytes)
+{
+	std::vector<uint16_t> t(8 * (size_t)n_bytes, 0);
+	for (int j = 0; j < n_bytes; j++)
+		for (int b = 0; b < 8; b++) {
+			uint16_t s = (uint16_t)(1u << b);  // register 0 ^ the byte, then its eight shifts = crc_zero_byte of it
+			s = crc_zero_byte(s);
+			for (int k = j + 1; k < n_bytes; k++) s = crc_zero_byte(s);
+			t[8 * (size_t)j + b] = s;
+		}
+	return t;
+}
 
 std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<uint16_t> &var_of_cw, MbMode &m)
 {
@@ -509,19 +523,9 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 		for (int i = 0; i < MB_N; i++) scr[i] = (uint8_t)(mb_random(st) % 2);
 		for (int i = 0; i < 8 * m.crc_bytes; i++) bit_var[i] = var_of_cw[i];
 	}
-	// warp-parallel CRC: lane l owns bytes [l*chunk, (l+1)*chunk); its partial CRC (preset 0) is advanced over the
-	// bytes that follow by a 16x16 GF(2) matrix; the 0xFFFF preset contributes a constant.
-	m.crc_chunk = (m.crc_bytes + 31) / 32;
-	std::vector<uint16_t> crcmat(32 * 16, 0);
-	for (int l = 0; l < 32; l++) {
-		int end = std::min(m.crc_bytes, (l + 1) * m.crc_chunk);
-		int follow = std::max(0, m.crc_bytes - end);
-		for (int b = 0; b < 16; b++) {
-			uint16_t s = (uint16_t)(1u << b);
-			for (int i = 0; i < follow; i++) s = crc_zero_byte(s);
-			crcmat[l * 16 + b] = s;
-		}
-	}
+	// CTA-parallel CRC (crc_bit_table above); the 0xFFFF preset contributes a constant.
+	m.crc_reserved = 0;
+	std::vector<uint16_t> crcbit = crc_bit_table(m.crc_bytes);
 	{
 		uint16_t s = 0xFFFF;
 		for (int i = 0; i < m.crc_bytes; i++) s = crc_zero_byte(s);
@@ -612,7 +616,7 @@ std::string build_mode(Blob &bl, int cfg, const MbRate &rate, const std::vector<
 	m.off_const = bl.put(cons);
 	m.off_bit_var = bl.put(bit_var);
 	m.off_scr = bl.put(scr);
-	m.off_crcmat = bl.put(crcmat);
+	m.off_crcbit = bl.put(crcbit);
 	return "";
 }
 
@@ -727,7 +731,7 @@ std::string mb_validate_blob(const uint8_t *blob, size_t size)
 		if (!in(m.off_pinv, 4 * cells) || !in(m.off_pval, 4 * cells) || !in(m.off_invn, 4 * cells) ||
 		    !in(m.off_pilot_cell, 2 * (size_t)m.nPilots) || !in(m.off_sym_cell, 2 * (size_t)m.nData) ||
 		    !in(m.off_llr_dst, 2 * (size_t)m.nBits) || !in(m.off_llr_dst2, 2 * (size_t)m.nBits) || !in(m.off_const, 8 * (size_t)m.M) ||
-		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcmat, 2 * 32 * 16) ||
+		    !in(m.off_bit_var, 16 * (size_t)m.crc_bytes) || !in(m.off_scr, MB_N) || !in(m.off_crcbit, 16 * (size_t)m.crc_bytes) ||
 		    !in(m.off_zf_src, 4 * (size_t)m.Nsymb * MB_ZF_STRIDE) || !in(m.off_pilot_rec, 16 * (size_t)m.nPilots) ||
 		    !in(m.off_pilot_f, 8 * (size_t)m.nPilots) || (m.data_rec_words != 2 && m.data_rec_words != 4) ||
 		    !in(m.off_data_rec, 4 * (size_t)m.data_rec_words * m.nData) || !in(m.off_virt, 4 * (size_t)m.nVirtual) ||
@@ -788,17 +792,8 @@ std::string mb_build_mfsk_ext(const std::vector<uint8_t> &blob, uint32_t base, M
 		mb_srandom(st, 0);
 		for (int q = 0; q < MB_N; q++) scr[q] = (uint8_t)(mb_random(st) % 2);
 		m.off_scr = base + bl.put(scr);
-		m.crc_chunk = (m.crc_bytes + 31) / 32;
-		std::vector<uint16_t> crcmat(32 * 16, 0);
-		for (int l = 0; l < 32; l++) {
-			const int end = std::min(m.crc_bytes, (l + 1) * m.crc_chunk), follow = std::max(0, m.crc_bytes - end);
-			for (int b = 0; b < 16; b++) {
-				uint16_t sreg = (uint16_t)(1u << b);
-				for (int k = 0; k < follow; k++) sreg = crc_zero_byte(sreg);
-				crcmat[l * 16 + b] = sreg;
-			}
-		}
-		m.off_crcmat = base + bl.put(crcmat);
+		m.crc_reserved = 0;
+		m.off_crcbit = base + bl.put(crc_bit_table(m.crc_bytes));
 		uint16_t sreg = 0xFFFF;
 		for (int k = 0; k < m.crc_bytes; k++) sreg = crc_zero_byte(sreg);
 		m.crc_init = sreg;

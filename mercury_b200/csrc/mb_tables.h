@@ -29,7 +29,7 @@
 #define MB_MAX_CELLS (MB_MAX_SYMB * MB_NC)
 #define MB_LS_HALF 10        // LS window 21x21 (20 -> odd 21, telecom_system.cc:2799-2809)
 #define MB_BLOB_MAGIC 0x42324d42u /* "BM2B" */
-#define MB_BLOB_VERSION 14u
+#define MB_BLOB_VERSION 15u
 #define MB_NO_DST 0xFFFFu
 #define MB_MAX_CDEG 48
 #define MB_MAX_VDEG 16
@@ -85,7 +85,7 @@ struct MbMode {
 	int32_t Nsymb, nData, nPilots, nBits, nReal, nVirtual, K, P;
 	int32_t frame_bytes, estimator /*0 ZF, 1 LS*/, phase_only, preamble_nSymb;
 	int32_t crc_bytes;      // nReal/8: bytes covered by the CRC self check
-	int32_t crc_chunk;      // bytes per lane in the warp-parallel CRC
+	int32_t crc_reserved;   // (was: bytes per lane of the chunked CRC)
 	uint32_t crc_init;      // contribution of the 0xFFFF preset after crc_bytes bytes
 	float boost;
 	uint32_t off_pinv;       // f32[cells]  1/p at pilot cells, 0 at data cells
@@ -98,7 +98,7 @@ struct MbMode {
 	uint32_t off_const;      // f32[2*M]    constellation (re,im), unit mean power
 	uint32_t off_bit_var;    // u16[8*crc_bytes] internal variable of info bit i
 	uint32_t off_scr;        // u8 [N]      scrambler bit i (bit_energy_dispersal sequence)
-	uint32_t off_crcmat;     // u16[32*16]  per-lane "advance CRC by the bytes that follow my chunk" matrices
+	uint32_t off_crcbit;     // u16[8*crc_bytes] CRC register (preset 0) after all crc_bytes bytes of a message with only bit i set: the CRC is their XOR over the set bits
 	// ---- descriptors of the persistent demodulator kernel (mb_demod.cu): all lattice / window / interleaver arithmetic is
 	// resolved here, offsets are BYTE offsets into the kernel's shared-memory arrays so that no scaling is left per frame.
 	uint32_t off_zf_src;     // u32[Nsymb*27] compact pilot-row slot -> (cell*8) | valid << 30 | (pilot negative) << 31

@@ -12,10 +12,10 @@ RATE_DT = np.dtype([(n, "<i4") for n in ("rate_num", "N", "K", "P", "n_edges", "
                                          "off_csched", "off_vsched", "off_vtail")] + [("vtail_start", "<i4")])
 MODE_DT = np.dtype([(n, "<i4") for n in ("config", "M", "bps", "rate_idx", "rate_num", "Nsymb", "nData", "nPilots", "nBits",
                                          "nReal", "nVirtual", "K", "P", "frame_bytes", "estimator", "phase_only",
-                                         "preamble_nSymb", "crc_bytes", "crc_chunk")] +
+                                         "preamble_nSymb", "crc_bytes", "crc_reserved")] +
                    [("crc_init", "<u4"), ("boost", "<f4")] +
                    [(n, "<u4") for n in ("off_pinv", "off_pval", "off_invn", "off_pilot_cell", "off_sym_cell", "off_llr_dst",
-                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcmat", "off_zf_src", "off_pilot_rec",
+                                         "off_llr_dst2", "off_const", "off_bit_var", "off_scr", "off_crcbit", "off_zf_src", "off_pilot_rec",
                                          "off_pilot_f", "off_data_rec", "off_virt")] +
                    [("data_rec_words", "<i4"), ("pinv_mag", "<f4"), ("off_pilot_neg", "<u4")])
 HDR_DT = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u4"), ("reserved", "<u4"), ("off_twiddle", "<u4"),
@@ -42,7 +42,7 @@ class Blob:
                  llr_dst2=self.arr(m["off_llr_dst2"], "<u2", m["nBits"]),
                  cons=self.arr(m["off_const"], "<f4", 2 * m["M"]).view(np.complex64),
                  bit_var=self.arr(m["off_bit_var"], "<u2", 8 * m["crc_bytes"]), scr=self.arr(m["off_scr"], "u1", MB_N),
-                 crcmat=self.arr(m["off_crcmat"], "<u2", 512).reshape(32, 16),
+                 crcbit=self.arr(m["off_crcbit"], "<u2", 8 * int(m["crc_bytes"])),
                  zf_src=self.arr(m["off_zf_src"], "<u4", int(m["Nsymb"]) * ZF_STRIDE),
                  pilot_rec=self.arr(m["off_pilot_rec"], "<u4", 4 * int(m["nPilots"])).reshape(-1, 4),
                  pilot_f=self.arr(m["off_pilot_f"], "<f4", 2 * int(m["nPilots"])).reshape(-1, 2),
@@ -249,7 +249,7 @@ def ldpc_decode(blob, cfg, llr_internal, max_iters):
 
 
 def finish(blob, cfg, posterior):
-    """hard decision -> de-scramble -> pack -> warp-parallel CRC exactly as mb_ldpc.cu. -> (bytes[crc_bytes], crc, all_zeros)."""
+    """hard decision -> de-scramble -> pack -> table-driven CRC exactly as mb_ldpc.cu. -> (bytes[crc_bytes], crc, all_zeros)."""
     m = blob.mode(cfg)
     nb = m["crc_bytes"]
     bits = (posterior[m["bit_var"].astype(int)] < 0).astype(np.uint8) ^ m["scr"][: 8 * nb]
@@ -257,17 +257,8 @@ def finish(blob, cfg, posterior):
     for b in range(8):
         by |= (bits[b::8] << b).astype(np.uint8)
     adv = 0
-    for lane in range(32):
-        part = 0
-        for i in range(m["crc_chunk"]):
-            j = lane * m["crc_chunk"] + i
-            if j < nb:
-                part ^= int(by[j])
-                for _ in range(8):
-                    part = ((part >> 1) ^ 0xA001) if part & 1 else part >> 1
-        for b in range(16):
-            if (part >> b) & 1:
-                adv ^= int(m["crcmat"][lane, b])
+    for i in np.nonzero(bits)[0]:  # the CRC is linear: XOR of the per-bit table over the set bits
+        adv ^= int(m["crcbit"][i])
     all_zeros = int(not by.any())
     crc = 0 if all_zeros else (adv ^ m["crc_init"]) & 0xFFFF
     return by, crc, all_zeros
