@@ -424,15 +424,11 @@ __device__ __forceinline__ void crc_and_record(const MbLdpcArgs &a, const Smem s
 	s.bytes()[255] = (unsigned char)decoded;
 }
 
-// ---- hard decision -> de-scramble -> pack LSB first -> all-zeros / CRC16 -> record (+ the ZF modes' SNR report) of slot X ------------
-// Called by the whole CTA (uniform); the other slot's interleaved state is not touched.
-// LS modes: returns the "any payload bit set" flag (0 / 1) with the CRC and the record still TO DO -- refill_slot() runs them on warp 0
-// after it has requested the next frame's data, so the warp every refill waits for no longer arrives a CRC late.  ZF modes: returns -1,
-// everything done here.
-__device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, size_t frame, int iterations)
+// ---- hard decision -> de-scramble -> pack LSB first -> payload bytes + per-warp CRC words of slot X; returns "any bit set" ------------
+// Called by the whole CTA (uniform, one barrier inside); the other slot's interleaved state is not touched.
+__device__ __forceinline__ int hard_decisions(const MbLdpcArgs &a, const Smem s, int X, size_t frame)
 {
 	const MbMode &m = a.mode;
-	const MbRate &rt = a.rate;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint16_t *__restrict__ g_bit_var = reinterpret_cast<const uint16_t *>(a.blob + m.off_bit_var);
 	const uint8_t *__restrict__ g_scr = a.blob + m.off_scr;
@@ -454,13 +450,18 @@ __device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) crcw ^= __shfl_xor_sync(0xffffffffu, crcw, o);
 	if (lane == 0) reinterpret_cast<unsigned *>(s.bytes())[warp] = crcw;
-	const int nonzero = __syncthreads_or((int)byte);
-#ifndef MB_LDPC_DEFER_CRC
-#define MB_LDPC_DEFER_CRC 1
-#endif
-	if (MB_LDPC_DEFER_CRC && m.estimator == 1) return nonzero ? 1 : 0;  // LS modes: the demodulator's pilot variance is the SNR report (:1368-1375)
-	crc_and_record(a, s, h, frame, iterations, nonzero);
-	if (m.estimator == 1) return -1;
+	return __syncthreads_or((int)byte);
+}
+
+// ---- epilogue of the ZF modes: the above, the record, and the SNR report of a decoded frame -------------------------------------------
+// (LS modes: the demodulator's pilot variance is the SNR report, telecom_system.cc:1368-1375; their epilogue runs INSIDE refill_slot(),
+// between the requests for the next frame's data and their use.)
+__device__ __noinline__ void finish_slot_zf(const MbLdpcArgs &a, const Smem s, const Hot h, int X, size_t frame, int iterations)
+{
+	const MbMode &m = a.mode;
+	const MbRate &rt = a.rate;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	crc_and_record(a, s, h, frame, iterations, hard_decisions(a, s, X, frame));
 
 	// ---- ZF modes: SNR report of a decoded frame (telecom_system.cc:1376-1400) -----------------------------------------
 	// Re-encode the hard decisions (scrambled info bits, virtual copies, IRA parity), re-map them onto the constellation through
@@ -468,7 +469,7 @@ __device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const
 	// data symbols (kept by the demodulator behind the LLRs of the hand-off record) to the re-encoded ones (ofdm.cc:1622-1635).
 	// Scratch: this slot's messages are dead: [0, P) data parity per check, [P, P + 1600) re-encoded bit per internal variable.
 	__syncthreads();
-	if (!s.bytes()[255]) return -1;
+	if (!s.bytes()[255]) return;
 	const uint16_t *__restrict__ g_edge_var = a.edge_var;
 	const uint16_t *__restrict__ g_voc = reinterpret_cast<const uint16_t *>(a.blob + rt.off_var_of_cw);
 	const int K = m.K, P = rt.P, nReal = m.nReal, nVirtual = m.nVirtual;
@@ -544,7 +545,6 @@ __device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const
 			a.stats[frame].SNR = -10.0f * log10f(tot / (float)m.nData);  // measure_SNR, ofdm.cc:1622-1635
 		}
 	}
-	return -1;
 }
 
 // ---- next frame of the batch into slot X (uniform).  Returns its index, or -1 when the queue is empty (the slot then holds an
@@ -553,8 +553,8 @@ __device__ __noinline__ int finish_slot(const MbLdpcArgs &a, const Smem s, const
 // waited for), and every grab prefetches into L2 the LLRs of the frame that will be handed out one "wave" of resident slots later
 // (frames are handed out in order), so a refill reads L2, not DRAM, while the pair's other slot waits.
 // `turn`: which of the two ticket words holds this refill's ticket (uniform; the caller keeps it).  Returns {frame, next turn}.
-__device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, int turn, long long done_frame = -1, int done_iterations = 0,
-					  int done_nonzero = 0)
+// done_frame >= 0 (LS modes): the frame leaving the slot; its epilogue (hard decisions, CRC, record) runs here while the requests travel.
+__device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, int turn, long long done_frame = -1, int done_iterations = 0)
 {
 	const MbMode &m = a.mode;
 	const int tid = threadIdx.x;
@@ -571,7 +571,7 @@ __device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, cons
 		unsigned nxt = 0u;
 		if (tid == 32) nxt = atomicAdd(h.queue, 1u);
 		if ((unsigned long long)f >= h.n_frames) {
-			if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);
+			if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, hard_decisions(a, s, X, (size_t)done_frame));
 			if (tid == 32) s.next()[turn] = (int)nxt;
 			frame = -1;
 			break;
@@ -590,7 +590,7 @@ __device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, cons
 			v[j] = i < MB_N ? ldg_stream(src + i) : 0.f;  // all loads in flight together; no L1 allocation (the index tables live there)
 		}
 		const float mean_H = h.check_gate ? ldg_stream(&h.stats[f].mean_H) : 1.0f;
-		if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, done_nonzero);  // while the loads travel
+		if (done_frame >= 0) crc_and_record(a, s, h, (size_t)done_frame, done_iterations, hard_decisions(a, s, X, (size_t)done_frame));  // while the loads travel
 		done_frame = -1;
 		if (tid == 32) s.next()[turn] = (int)nxt;
 		if (!(mean_H >= 0.3f)) {
@@ -628,10 +628,19 @@ __device__ __noinline__ int2 refill_slot(const MbLdpcArgs &a, const Smem s, cons
 // a finished frame leaves slot X, the next one of the queue enters; returns {the new frame's index (-1: queue empty), next turn}
 __device__ __forceinline__ int2 retire_slot(const MbLdpcArgs &a, const Smem s, const Hot h, int X, int turn, int frame, int iterations)
 {
-	const int todo = finish_slot(a, s, h, X, (size_t)frame, iterations);  // >= 0: CRC + record left to refill_slot()
-	return refill_slot(a, s, h, X, turn, todo >= 0 ? (long long)frame : -1ll, iterations, todo);
+	if (a.mode.estimator == 1) return refill_slot(a, s, h, X, turn, (long long)frame, iterations);
+	finish_slot_zf(a, s, h, X, (size_t)frame, iterations);
+	return refill_slot(a, s, h, X, turn);
 }
 
+// Development aid (-DMB_LDPC_TIMING): cycles per phase and warp, printed by the first CTAs (never in the shipped build).
+#ifdef MB_LDPC_TIMING
+#define MB_T_DECL unsigned t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = (unsigned)clock();
+#define MB_T(i) { const unsigned t_now = (unsigned)clock(); t_ph[i] += t_now - t_last; t_last = t_now; }
+#else
+#define MB_T_DECL
+#define MB_T(i)
+#endif
 #ifdef MB_LDPC_MAXNREG
 #define MB_LDPC_BOUNDS __maxnreg__(MB_LDPC_MAXNREG)
 #else
@@ -678,7 +687,9 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 	}
 
 	const int vtail0 = rt.vtail_start;
+	MB_T_DECL
 	while (frame[0] >= 0 || frame[1] >= 0) {
+		MB_T(7)
 		// ---- check pass: syndrome of the current posteriors + new check->variable messages, both slots ----------------
 		// A warp owns a group of 32 checks padded to one degree; padding slots point at the +inf variable, so the loops are
 		// warp-uniform (no per-thread degree, no divergence) and a padding edge is the neutral element of every reduction.
@@ -736,7 +747,9 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 			const unsigned ba = __ballot_sync(0xffffffffu, hard_a != 0u), bb = __ballot_sync(0xffffffffu, hard_b != 0u);
 			if (lane == 0) s.cnt()[warp] = (unsigned)__popc(ba) | ((unsigned)__popc(bb) << 16);
 		}
+		MB_T(0)
 		__syncthreads();
+		MB_T(1)
 		unsigned tot = 0;
 #pragma unroll
 		for (int w = 0; w < MB_LDPC_WARPS; w++) tot += s.cnt()[w];
@@ -751,8 +764,10 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 			else if (pass[X] == a.max_iters)
 				iterations = a.max_iters + 1;  // ldpc_decoder_SPA.cc:127,217: loop ran out
 			if (iterations >= 0) {
+				MB_T(2)
 				const int2 r = retire_slot(a, s, hot, X, turn, frame[X], iterations);
 				frame[X] = r.x, turn = r.y;
+				MB_T(3)
 				pass[X] = 0;
 				fresh[X] = true;
 				virgin[X] = true;
@@ -760,6 +775,7 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 				pass[X]++;
 			}
 		}
+		MB_T(2)
 		if (frame[0] < 0 && frame[1] < 0) break;
 		// both slots just refilled (the usual case where frames arrive clean: 0 iterations each): their posteriors are the channel LLRs
 		// already, there is nothing for a variable pass to do
@@ -814,7 +830,9 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 			const f2 r0 = lds2i<kSmemBase + kOffR>(w & 0xFFFFu), r1 = lds2i<kSmemBase + kOffR>(w >> 16);
 			sts2(sbase + kOffLam + v * 8, __ffma2_rn(__fadd2_rn(r0, r1), vm, s.get_lch(v)));
 		}
+		MB_T(4)
 		__syncthreads();
+		MB_T(5)
 		// ---- cheap syndrome-only test when convergence is likely: saves the (expensive) message update of a final pass ----
 		const bool try_a = frame[0] >= 0 && !fresh[0] && n_unsat[0] <= a.cheap_test_threads;
 		const bool try_b = frame[1] >= 0 && !fresh[1] && n_unsat[1] <= a.cheap_test_threads;
@@ -858,7 +876,13 @@ __global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs
 				virgin[1] = true;
 			}
 		}
+		MB_T(6)
 	}
+#ifdef MB_LDPC_TIMING
+	if (lane == 0 && (blockIdx.x % 111) == 5)
+		printf("T cta %d warp %d check %u barA %u decide %u retire %u var %u barB %u cheap %u loop %u\n", (int)blockIdx.x, warp, t_ph[0], t_ph[1],
+		       t_ph[2], t_ph[3], t_ph[4], t_ph[5], t_ph[6], t_ph[7]);
+#endif
 	// the last CTA out re-arms the queue for the next launch on this stream
 	__syncthreads();
 	if (tid == 0) {
