@@ -387,6 +387,7 @@ def run_own(a):
     # ---- per-kernel timing (same stream, same inputs): roofline of the demod stage, edge rate of the decoder ----
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     t_demod = t_ldpc = 0.0
+    per_step = []
     clocks.start()
     for _ in range(a.steps):
         ev[0].record()
@@ -397,6 +398,7 @@ def run_own(a):
         torch.cuda.synchronize()
         t_demod += ev[0].elapsed_time(ev[1])
         t_ldpc += ev[1].elapsed_time(ev[2])
+        per_step.append((round(ev[0].elapsed_time(ev[1]), 4), round(ev[1].elapsed_time(ev[2]), 4)))
     clocks.stop()
     t_demod_s, t_ldpc_s = 1e-3 * t_demod / a.steps, 1e-3 * t_ldpc / a.steps
     peaks = {}
@@ -430,7 +432,7 @@ def run_own(a):
     issue_peak = n_sm * 4 * sm_mhz * 1e6                 # warp instructions / s: one per SM sub-partition and clock
     xu_peak = n_sm * 16 * sm_mhz * 1e6                   # MUFU lane-operations / s: 16 XU lanes per SM
     ldpc = {"kernel": "mb_ldpc_kernel", "decoder": a.decoder, "edge_updates_per_s": edge_updates / t_ldpc_s, "kernel_ms": 1e3 * t_ldpc_s,
-            "edges": m["edges"], "mean_iterations": float(its_run.mean()), "frames_per_s": B / t_ldpc_s,
+            "kernel_ms_per_step": [t[1] for t in per_step], "edges": m["edges"], "mean_iterations": float(its_run.mean()), "frames_per_s": B / t_ldpc_s,
             "hbm_gbs": B * (1600 * 4 + fb + 32 + 32) / t_ldpc_s / 1e9, "share_of_step": t_ldpc_s / (t_demod_s + t_ldpc_s),
             # neither HBM nor tensor bound: the decoder's state lives in shared memory for all iterations.  What bounds it is instruction issue
             # and the latency of its dependent MUFU / shared-memory chains, so it is reported against the issue-slot and XU-pipe rooflines
