@@ -1,25 +1,14 @@
 mkdir -p gpurun_out
-T=${1:-r2h}
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -30 > gpurun_out/${T}_pytest.log
-run() { # name, env...
-  name=$1; shift
-  env "$@" timeout 300 python bench.py --no-e2e --cpu-frames 0 --steps 5 $BARGS > gpurun_out/${T}_bench_$name.json 2> gpurun_out/${T}_bench_$name.err
-}
-for cfg in 8 0 3 9 13; do
-BARGS="--config $cfg"
-run m${cfg} X=1
-done
-BARGS="--config 16 --iters 20"
-run m16 X=1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:mb_ldpc -s 1 -c 1 -o gpurun_out/${T}_prof \
-    python bench.py --batch 16384 --steps 1 --warmup 1 --no-e2e --cpu-frames 0 > gpurun_out/${T}_prof.log 2>&1
-cat gpurun_out/${T}_pytest.log | tail -15
+T=${1:-r3q}
+N=${2:-8}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/${T}_bench_${N}gpu.json 2> gpurun_out/${T}_bench_${N}gpu.err
+g++ -std=c++14 -O2 -I include -I /usr/local/cuda/include tests/cpp/multi_gpu_host.cpp -o /tmp/multi_gpu_host -L mercury_b200 -lmercury_b200 -L/usr/local/cuda/lib64 -lcudart -lnccl -pthread -Wl,-rpath,$PWD/mercury_b200
+timeout 600 /tmp/multi_gpu_host mercury_b200/data/ldpc_tables.bin $N 65536 2 8 i16 > gpurun_out/${T}_cpp_host_${N}gpu_i16.json 2> gpurun_out/${T}_cpp_host_${N}gpu.err
+tail -3 gpurun_out/${T}_bench_${N}gpu.err; cat gpurun_out/${T}_cpp_host_${N}gpu_*.json; tail -2 gpurun_out/${T}_cpp_host_${N}gpu.err
 python - <<PY
-import json,glob
-for f in sorted(glob.glob("gpurun_out/${T}_bench_*.json")):
-    try:
-        d = json.load(open(f)); r, l = d["roofline"], d["ldpc"]
-        print(f, f"value {d['value']:.4g} | demod {r['kernel_ms']:.3f} ms | ldpc {l['kernel_ms']:.3f} ms it {l['mean_iterations']:.2f} | mism {d['integrity']['payload_mismatches_among_decoded']} fer {d['integrity']['fer']}")
-    except Exception as e:
-        print(f, "failed", e)
+import json
+d=json.loads(open("gpurun_out/${T}_bench_${N}gpu.json").read().strip().splitlines()[-1])
+print("value", d["value"], "n_gpus", d["n_gpus"], d["config"]["workload"], "ms/step", d["ms_per_step"])
+print("integrity", d["integrity"])
+e=d["e2e"]; print("e2e", e["value"], "c64", e["complex64"]["value"], "ceiling", e["h2d_ceiling"])
 PY
