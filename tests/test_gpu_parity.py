@@ -208,6 +208,39 @@ def test_large_batch_properties_mode8(ts):
     assert np.array_equal(p2, payload[perm]) and np.array_equal(s2, stats[perm])  # frames are independent; results deterministic
 
 
+@pytest.mark.parametrize("cfg", [8, 16])
+def test_gated_frames_inside_a_busy_queue(ts, cfg):
+    """Frames the demodulator gates out (mean|H| < 0.3, telecom_system.cc:1268-1280) in the middle of a batch larger than the decoder's
+    resident slots: they are skipped by the refill of a slot whose previous frame has just been finished (epilogue and refill share one
+    function in the LS modes; the ZF modes run their epilogue first), several in a row included, and every frame around them is decoded as if they were not there."""
+    geom = ts.load_configuration(cfg, 50)
+    S = geom["Nsymb"]
+    n = 3000
+    x, pl = mb.synth_frames(cfg, n, seed=21, esn0_db=THRESH[8] + 2.0 if cfg == 8 else 32.0)  # (ZF modes decode by hard decision: SURVEY.md 7)
+    x = np.ascontiguousarray(x)
+    rng = np.random.default_rng(5)
+    noise_at = np.zeros(n, bool)
+    noise_at[::5] = True
+    noise_at[1001:1009] = True          # a run of gated frames: the refill loops over them
+    noise_at[-3:] = True                # and the queue ends on gated frames
+    k = int(noise_at.sum())
+    x[noise_at] = (0.05 * (rng.standard_normal((k, S, 272)) + 1j * rng.standard_normal((k, S, 272)))).astype(np.complex64)
+    p, s, _ = ts.demod_decode_batch(x)
+    gated = s["mean_H"] < 0.3
+    if cfg == 8:  # LS estimate of noise: weak.  (ZF: H = Y / p under the AGC never is -- there the noise frames run all iterations and fail.)
+        assert gated[noise_at].all()
+    assert not gated[~noise_at].any()
+    assert (s["iterations_done"][gated] == -1).all() and (s["message_decoded"][gated] == 0).all() and not p[gated].any()
+    assert (s["crc"][gated] == 0).all() and (s["all_zeros"][gated] == 0).all() and np.allclose(s["SNR"][gated], -99.9)
+    good = ~noise_at
+    assert (s["message_decoded"][good] == 1).mean() > 0.99
+    dec = good & (s["message_decoded"] == 1)
+    assert np.array_equal(p[dec], pl[dec])
+    sub = np.r_[995:1015, n - 8:n]      # the same frames in a batch of their own: identical records
+    p2, s2, _ = ts.demod_decode_batch(x[sub])
+    assert np.array_equal(p2, p[sub]) and np.array_equal(s2, s[sub])
+
+
 def test_edge_cases(ts):
     geom = ts.load_configuration(8, 50)
     S, fb = geom["Nsymb"], geom["frame_bytes"]
