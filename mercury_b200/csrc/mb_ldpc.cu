@@ -42,6 +42,7 @@
 //   * MINSUM mode (north_star): normalised min-sum (alpha 1 for degree<=2 where min-sum is exact, 0.85 for 3, 0.75 above), same
 //     schedule / exit / clamp, same pair structure.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "mb_kernels.cuh"
@@ -909,11 +910,26 @@ int g_ctas_per_sm[2][MB_NRATES] = {};
 int g_sms = 0;
 }  // namespace
 
+// the shared-space address of the dynamic window in a kernel of this file (no static __shared__): what kSmemBase has to be
+__global__ void mb_ldpc_smem_base_probe(unsigned *out) { *out = (unsigned)__cvta_generic_to_shared(mb_smem); }
+
 cudaError_t mb_ldpc_init()
 {
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) return e;
+	{  // fail HERE, with a reason, rather than by the decoder's entry trap, if a toolchain / driver ever moves the window
+		unsigned *d = nullptr, hbase = 0;
+		if ((e = cudaMalloc(&d, sizeof(unsigned))) != cudaSuccess) return e;
+		mb_ldpc_smem_base_probe<<<1, 1, 1024>>>(d);
+		e = cudaMemcpy(&hbase, d, sizeof(unsigned), cudaMemcpyDeviceToHost);
+		cudaFree(d);
+		if (e != cudaSuccess) return e;
+		if (hbase != kSmemBase) {
+			fprintf(stderr, "mercury_b200: the dynamic shared-memory window starts at 0x%x, the decoder was built for 0x%x (mb_ldpc.cu kSmemBase)\n", hbase, kSmemBase);
+			return cudaErrorInvalidDeviceFunction;
+		}
+	}
 	e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
 	if (e != cudaSuccess) return e;
 	for (LdpcKernel k : kKernels) {
