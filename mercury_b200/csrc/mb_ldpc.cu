@@ -11,15 +11,16 @@
 //   * TWO frames per thread.  A CTA (8 warps) decodes a PAIR of frames in lock step; every per-edge quantity is a float2
 //     (x = frame in slot A, y = frame in slot B) interleaved in shared memory, so each index load, address computation,
 //     shared-memory access (LDS.64 / STS.64), loop counter and branch is shared by the two frames, and the arithmetic runs on the
-//     packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one issue slot for both frames).  The kernel is bound by instruction issue and by
-//     the XU (MUFU) pipe, not by memory, so this -- with the check-node arithmetic below -- is what sets its speed.
+//     packed fp32 pipe (FADD2 / FMUL2 / FFMA2: one issue slot for both frames).  The kernel is bound by instruction count and
+//     latency (issue slots 61 % busy, XU 54 %), not by memory, so this -- with the check-node arithmetic below -- is what sets its speed.
 //   * The two slots are independent decodes: each has its own iteration counter, early exit and verdict.  When a slot finishes
 //     (converged, or ran out of iterations) its epilogue runs and the slot is REFILLED with the next frame of the batch from a
 //     global queue (one atomic per frame), while the other slot carries on: no frame waits for its neighbour, and a batch with a
 //     few non-converging frames (50 iterations against ~5) does not leave SMs idle behind them.  Grid = resident CTAs only.
-//   * The whole decoder state of a pair lives in shared memory for all iterations: posterior[1600] + channel LLR[1600] + one
-//     message per Tanner-graph edge slot, x2 frames (58-86 KB per pair, 3 pairs resident per SM up to rate 8/16).  HBM is touched
-//     once per frame: 6.4 KB of LLRs in, <= 175 + 32 bytes out.
+//     The hand-over requests the next frame's data first and runs the old frame's epilogue while it travels (refill_slot()).
+//   * The decoder state of a pair lives in shared memory for all iterations: posterior[1601] + one message per Tanner-graph edge
+//     slot, x2 frames (59-77 KB per pair, 3 pairs resident per SM up to rate 8/16); the channel LLRs, read once per iteration and
+//     variable, in a per-CTA global scratch that stays in the L2.  HBM is touched once per frame: 6.4 KB of LLRs in, <= 175 + 32 bytes out.
 //   * Only posterior and check->variable messages are stored: the variable->check message of the reference (its Q array) is
 //     recomputed as posterior - R, which is exactly the reference's Q update.
 //   * The Tanner graph is a warp-blocked ELL on BOTH sides (csrc/mb_tables.cpp): checks (variables) sorted by degree, cut into
@@ -32,9 +33,9 @@
 //         (P, M) <- (P + e M, M + e P)  from (1, 0)      (the tanh addition rule: M/P = tanh(sum atanh e_k); all terms positive)
 //         |R_k| = log2(P_k / M_k)  over the OTHER edges  (2 MUFU: rcp, lg2)
 //     which is 2 atanh(prod_{j != k} tanh(|q_j|/2)) exactly, at 3 MUFU per edge and iteration instead of the 6 of the log-domain
-//     form (phi forward + phi backward), with no cancellation anywhere: small degrees combine prefix and suffix pairs in
-//     registers (fully unrolled bodies per degree), larger degrees keep the largest term apart and divide the others out
-//     ((P - e M, M - e P), recombined with the largest term, which dominates whatever the subtraction lost).
+//     form (phi forward + phi backward), with no cancellation anywhere: leave-one-out = prefix (+) suffix pairs in registers,
+//     one fully unrolled body per edge count (3..8); checks above 7 edges are split over 2 / 4 / 8 lanes that exchange their (P, M)
+//     totals by shuffles, the other lanes' total entering as one more edge e = M / P -- so split and unsplit checks run the same bodies.
 //     It reproduces the reference's DOUBLE-precision clamp rule (ldpc_decoder_SPA.cc:147-155): a factor whose tanh rounds to 1.0
 //     in double (e < 2^-55) contributes e = 0, and an all-saturated product (M == 0) yields 2 atanh(0.9999999).
 //     tools/ldpc_numerics.py: on frames at the decoding threshold this arithmetic agrees with the double-precision reference on
