@@ -9,9 +9,9 @@ g++ -std=c++14 -O2 -I include -I /usr/local/cuda/include tests/cpp/multi_gpu_hos
 tail -3 gpurun_out/${T}_bench_${N}gpu.err; cat gpurun_out/${T}_cpp_host_${N}gpu_*.json; tail -2 gpurun_out/${T}_cpp_host_${N}gpu.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/${T}_bench_${N}gpu.json"))
+d=json.loads(open("gpurun_out/${T}_bench_${N}gpu.json").read().strip().splitlines()[-1])
 print("value", d["value"], "n_gpus", d["n_gpus"], d["config"]["workload"])
 print("integrity", d["integrity"])
 e=d["e2e"]; print("e2e", e["value"], "c64", e["complex64"]["value"], "ceiling", e["h2d_ceiling"])
-r=json.load(open("gpurun_out/${T}_bench_ref_${N}gpu.json")); print("ref", r["value"], r["config"]==d["config"])
+r=json.loads(open("gpurun_out/${T}_bench_ref_${N}gpu.json").read().strip().splitlines()[-1]); print("ref", r["value"], r["config"]==d["config"])
 PY
