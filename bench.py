@@ -325,8 +325,19 @@ def run_own(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-        blob = broadcast_tables(mb.build_tables_host() if rank == 0 else None, src=0, device=dev)  # NCCL broadcast of the tables
+        # NCCL announces itself ("NCCL version ...") on file descriptor 1 when its first communicator comes up: stdout carries ONE JSON
+        # line, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        fd1 = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            blob = broadcast_tables(mb.build_tables_host() if rank == 0 else None, src=0, device=dev)  # NCCL broadcast of the tables
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(fd1, 1)
+            os.close(fd1)
         ts = mb.TelecomSystemB200(local, tables_blob=blob)
     else:
         ts = mb.TelecomSystemB200(local)
