@@ -203,6 +203,12 @@ typedef struct mercury_b200_receive_stats {
 #define MERCURY_B200_SAMPLES_I32 3  /* int32 PCM, x / (double)INT_MAX (the reference's default capture format, audioio.c:744) */
 
 int mercury_b200_get_capture_samples(const mercury_b200_t *h);
+/* g_gui_state.coarse_freq_sync_enabled (include/common/gui_state.h:143; read by receive_byte() at telecom_system.cc:949): the optional coarse
+ * frequency search of trial 1 -- when trial 0 fails, Schmidl-Cox over the head of the buffer with the time-sync filter at fc - 30, fc and
+ * fc + 30 Hz (:949-983), the winning carrier kept for the rest of the call if it beats 0 Hz by 0.1 (:985-993). Off by default, like the
+ * reference's flag. Affects mercury_b200_receive_byte* in the OFDM configurations. */
+int mercury_b200_set_coarse_freq_sync(mercury_b200_t *h, int enable);
+
 /* void set_mfsk_ctrl_mode(bool) / int get_active_nsymb() (telecom_system.cc:1572-1580): shortened control frames in ROBUST_0 (240 of 320 symbols)
  * and ROBUST_1 (175 of 200): transmit_byte modulates only the active symbols (silence follows), receive_byte / the tail demodulate only those and
  * erase the rest of the codeword.  Both return the active symbol count; load_configuration switches the mode off like the reference. */

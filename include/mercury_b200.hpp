@@ -160,6 +160,8 @@ public:
 		if (mercury_b200_fir_tx_apply(h_, in, (size_t)nItems, out) != MERCURY_B200_OK) throw std::runtime_error(mercury_b200_last_error(h_));
 	}
 	void set_mfsk_ctrl_mode(bool enable) { mercury_b200_set_mfsk_ctrl_mode(h_, enable ? 1 : 0); }
+	// g_gui_state.coarse_freq_sync_enabled (a global of the reference's GUI state, read by receive_byte(): telecom_system.cc:949)
+	void set_coarse_freq_sync(bool enable) { mercury_b200_set_coarse_freq_sync(h_, enable ? 1 : 0); }
 	int get_active_nsymb() const { return mercury_b200_get_active_nsymb(h_); }
 	char get_configuration(double SNR) const { return (char)mercury_b200_get_configuration(SNR); }
 	double measure_signal_only(double *data)

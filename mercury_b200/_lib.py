@@ -81,6 +81,7 @@ def lib():
         "mercury_b200_receive_baseband": (i32, [vp, vp, vp, C.POINTER(RxStats)]),
         "mercury_b200_get_capture_samples": (i32, [vp]),
         "mercury_b200_set_mfsk_ctrl_mode": (i32, [vp, i32]),
+        "mercury_b200_set_coarse_freq_sync": (i32, [vp, i32]),
         "mercury_b200_get_active_nsymb": (i32, [vp]),
         "mercury_b200_get_configuration": (i32, [C.c_double]),
         "mercury_b200_measure_signal_only_batch": (i32, [vp, vp, i32, sz, vp]),

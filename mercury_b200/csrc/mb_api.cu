@@ -47,6 +47,7 @@ struct FeWork {
 	size_t cap = 0;
 	int buf = 0;
 	int symb = 0;  // symbols per frame the per-capture frame / debug buffers were sized for
+	int win_n = 0; // samples per capture of the on-demand window and its prefix sums (kFeWin; (2 pre + S) symbols with the coarse frequency search)
 	void *d_x[2] = {nullptr, nullptr};  // staged pass-band samples of the host entry point, double buffered
 	size_t x_bytes = 0;
 	size_t out_slot_bytes = 0;
@@ -98,6 +99,7 @@ void tx_free(TxWork &w);
 }  // namespace
 
 struct mercury_b200 {
+	bool coarse_freq_sync = false;  // g_gui_state.coarse_freq_sync_enabled (gui_state.h:143): the optional +-30 Hz search of trial 1 (telecom_system.cc:949-1013)
 	bool mfsk_ctrl = false;  // set_mfsk_ctrl_mode: shortened control frames in ROBUST_0 / ROBUST_1 (telecom_system.cc:1572-1585, 2966-2995)
 	MbMode mfsk_modes[3];  // ROBUST_0..2 (config 100..102): tables in the extension region behind the device blob
 	MbMfsk mfsk_tones[3];
@@ -708,7 +710,8 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	}
 	const size_t bb_n = (size_t)(m.Nsymb + m.preamble_nSymb) * MB_NOFDM;
 	const int symb = std::max(MB_MAX_SYMB, m.Nsymb);  // ROBUST_0 frames are 320 symbols: a workspace sized in an OFDM mode must not be reused for them
-	if (w.cap >= n && w.buf >= buf && w.symb >= symb && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
+	const int win_need = h->coarse_freq_sync && m.M != 200 ? std::max(kFeWin, (2 * m.preamble_nSymb + m.Nsymb) * MB_FE_SYM) : kFeWin;  // :970-973 searches the head of the buffer
+	if (w.cap >= n && w.buf >= buf && w.symb >= symb && w.win_n >= win_need && (!want_dbg || w.want_dbg)) return MERCURY_B200_OK;
 	MB_CUDA(h, cudaDeviceSynchronize());
 	void **ptrs[] = {(void **)&w.st, (void **)&w.bbi, (void **)&w.win, (void **)&w.dbg_bb, (void **)&w.energy_part, (void **)&w.vals, (void **)&w.frames,
 			 (void **)&w.pref_ts, (void **)&w.pref_win, (void **)&w.flags, (void **)&w.tile_base,
@@ -717,18 +720,18 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 		if (*p) cudaFree(*p);
 		*p = nullptr;
 	}
-	const int bufmax = std::max(buf, w.buf), symbmax = std::max(symb, w.symb);
+	const int bufmax = std::max(buf, w.buf), symbmax = std::max(symb, w.symb), winmax = std::max(win_need, w.win_n);
 	const size_t cap = std::max(n, w.cap);
 	w.cap = 0;
 	MB_CUDA(h, cudaMalloc(&w.st, cap * sizeof(MbFeState)));
 	MB_CUDA(h, cudaMalloc(&w.bbi, cap * bufmax * sizeof(double2)));
-	MB_CUDA(h, cudaMalloc(&w.win, cap * kFeWin * sizeof(double2)));
+	MB_CUDA(h, cudaMalloc(&w.win, cap * (size_t)winmax * sizeof(double2)));
 	MB_CUDA(h, cudaMalloc(&w.energy_part, cap * ((bufmax + 255) / 256) * sizeof(double)));  // >= one partial per 1024-sample tile
 	MB_CUDA(h, cudaMalloc(&w.vals, cap * kFeVals * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.flags, cap * kFeVals));
 	MB_CUDA(h, cudaMalloc(&w.pref_ts, cap * 3 * ((size_t)bufmax / 4 + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.tile_base, cap * ((size_t)bufmax / 1024 + 3) * 3 * sizeof(double)));
-	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)kFeWin + 1) * sizeof(double)));
+	MB_CUDA(h, cudaMalloc(&w.pref_win, cap * 3 * ((size_t)winmax + 1) * sizeof(double)));
 	MB_CUDA(h, cudaMalloc(&w.frames, cap * (size_t)symbmax * MB_NOFDM * sizeof(float2)));
 	MB_CUDA(h, cudaMalloc(&w.llr, cap * MB_HANDOFF_STRIDE * sizeof(float)));
 	MB_CUDA(h, cudaMalloc(&w.tail_stats, cap * sizeof(MbRxStats)));
@@ -741,6 +744,7 @@ int fe_ensure(mercury_b200_t *h, size_t n, int buf, const MbMode &m, bool want_d
 	w.cap = cap;
 	w.buf = bufmax;
 	w.symb = symbmax;
+	w.win_n = winmax;
 	return MERCURY_B200_OK;
 }
 
@@ -757,7 +761,8 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	a.buffer_Nsymb = mb_fe_buffer_nsymb(m.Nsymb, m.preamble_nSymb);
 	a.buf = MB_NOFDM * a.buffer_Nsymb * 4, a.pre = m.preamble_nSymb, a.S = m.Nsymb, a.frame_bytes = m.frame_bytes;
 	a.carrier = w.carrier, a.st = w.st, a.bbi = w.bbi, a.energy_part = w.energy_part;
-	a.win = w.win, a.win_stride = kFeWin, a.vals = w.vals, a.vals_stride = kFeVals;
+	a.win = w.win, a.win_stride = w.win_n, a.vals = w.vals, a.vals_stride = kFeVals;
+	a.coarse_freq_sync = h->coarse_freq_sync && m.M != 200 ? 1 : 0;
 	a.flags = w.flags, a.pref_ts = w.pref_ts, a.pref_win = w.pref_win, a.tile_base = w.tile_base;
 	a.frames = w.frames, a.dbg_bb = dbg ? w.dbg_bb : nullptr;
 	a.tail_stats = w.tail_stats, a.tail_payload = w.tail_payload, a.tail_payload_stride = m.frame_bytes;
@@ -771,7 +776,7 @@ int fe_run(mercury_b200_t *h, const void *d_x, int fmt, size_t n, uint8_t *d_pay
 	bool run_sc = true;
 	// every round each capture either finishes or passes one of: coarse run, <= 2 recovery runs, 3 fine runs + 3 tails, SKIP-H
 	// recovery and 3 more trials -- 32 rounds is far above the longest path through receive_byte()
-	for (int round = 0; round < 32; round++) {
+	for (int round = 0; round < (a.coarse_freq_sync ? 48 : 32); round++) {  // (+ 4 rounds per pass through trial 1 with the coarse frequency search)
 		MB_CUDA(h, cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), s));
 		MB_CUDA(h, mb_fe_step(a, run_sc, s));
 		h->launches += run_sc ? 5 : 1;
@@ -908,6 +913,16 @@ int mercury_b200_measure_signal_only_batch(mercury_b200_t *h, const void *passba
 			signal_dbm[done + i] = 10.0 * log10((e / buf) / 0.001);  // measure_signal_stregth, ofdm.cc:1523-1539
 		}
 	}
+	return MERCURY_B200_OK;
+}
+
+/* g_gui_state.coarse_freq_sync_enabled (gui_state.h:143, read at telecom_system.cc:949): when trial 0 of receive_byte() fails, search fc - 30,
+ * fc, fc + 30 Hz with the time-sync filter before trial 1 and keep the winning carrier for the rest of the call. Off by default, like the
+ * reference's. */
+int mercury_b200_set_coarse_freq_sync(mercury_b200_t *h, int enable)
+{
+	if (!h) return MERCURY_B200_EINVAL;
+	h->coarse_freq_sync = enable != 0;
 	return MERCURY_B200_OK;
 }
 

@@ -143,11 +143,13 @@ __global__ void __launch_bounds__(256) k_fe_window(const T *__restrict__ x_all, 
 {
 	const int b = blockIdx.y;
 	const MbFeState &st = st_all[b];
-	if (!st.sc_pending || st.sc_src != 1) return;
+	if (!st.sc_pending || st.sc_src == 0) return;
 	const T *x = x_all + (size_t)b * buf;
-	const bool table = st.cur_f == fe_c.fc;
+	const double f = st.sc_src == 1 ? st.cur_f : st.win_f;           // 2: the time-sync filter at a carrier of the coarse frequency search
+	const double *coef = st.sc_src == 1 ? fe_c.c_data : fe_c.c_ts;
+	const bool table = f == fe_c.fc;
 	for (int i = blockIdx.x * 256 + threadIdx.x; i < st.sc_size; i += gridDim.x * 256)
-		win_all[(size_t)b * win_stride + i] = fir_on_demand(x, st.sc_start + i, buf, carrier, table, st.cur_f, fe_c.c_data);
+		win_all[(size_t)b * win_stride + i] = fir_on_demand(x, st.sc_start + i, buf, carrier, table, f, coef);
 }
 
 // ---- Schmidl-Cox metric (ofdm.cc:1891-1940) in two passes -------------------------------------------------------------
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kPrefThreads) k_fe_prefix(const MbFeState *__r
 	int len = buf;
 	if (RES == 1) {
 		const MbFeState &st = st_all[b];
-		if (!st.sc_pending || st.sc_step != 1) return;
+		if (!st.sc_pending || (st.sc_step != 1 && st.sc_src == 0)) return;  // fine runs, and every run over a window
 		len = st.sc_size;
 		w = st.sc_src == 0 ? w + st.sc_start : win_all + (size_t)b * win_stride;
 	}
@@ -335,8 +337,8 @@ __global__ void __launch_bounds__(kScThreads) k_fe_sc_approx(MbFeState *__restri
 		// coarse runs (step 100) read the tiled RES-4 prefix of the whole time-sync base-band (local + tile base), fine runs (step 1) the
 		// RES-1 prefix of their window
 		double cc = 0, na = 0, nb = 0;
-		if (st.sc_step == 1) {
-			const double *CE = pref_win + (size_t)b * 3 * pstride_win + k, *C1 = CE + pstride_win, *C2 = C1 + pstride_win;
+		if (st.sc_step == 1 || st.sc_src != 0) {
+			const double *CE = pref_win + (size_t)b * 3 * pstride_win + (size_t)k * st.sc_step, *C1 = CE + pstride_win, *C2 = C1 + pstride_win;
 			for (int l = 0; l < pre; l++) {
 				const int o = l * MB_FE_SYM;
 				cc += (C1[o + 64] - C1[o]) + (C2[o + 576] - C2[o + 64]);
@@ -536,7 +538,7 @@ __device__ double energy_cur_sum(const DecideCtx &c, const double2 *bbi, const T
 	const bool table = c.st.cur_f == fe_c.fc;
 	for (int i = threadIdx.x; i < n; i += blockDim.x) {
 		if (pos + i >= c.buf) break;
-		const double2 v = c.st.cur_kind == 0 ? bbi[pos + i] : fir_on_demand(x, pos + i, c.buf, carrier, table, c.st.cur_f, fe_c.c_data);
+		const double2 v = c.st.cur_kind == 0 ? bbi[pos + i] : fir_on_demand(x, pos + i, c.buf, carrier, table, c.st.cur_f, c.st.cur_kind == 1 ? fe_c.c_data : fe_c.c_ts);
 		e += v.x * v.x + v.y * v.y;
 	}
 	return block_sum(e, red);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 								const double2 *__restrict__ bbi_all, const double *__restrict__ vals_all, int vals_stride,
 								const double *__restrict__ energy_part, int nblk, const MbRxStats *__restrict__ tail_stats,
 								const uint8_t *__restrict__ tail_payload, int tail_payload_stride, uint8_t *__restrict__ payload_out,
-								int frame_bytes, int pre, int S, int buffer_Nsymb, int *__restrict__ counters)
+								int frame_bytes, int pre, int S, int buffer_Nsymb, int coarse_freq_sync, int *__restrict__ counters)
 {
 	__shared__ DecideCtx c;
 	__shared__ double red[8];
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 				if (phase == MB_FE_REC_BOUNDS) st.phase = MB_FE_GATE;
 				else if (phase == MB_FE_REC_SILENCE) st.phase = ok ? MB_FE_TRIAL : MB_FE_DONE, st.skip_h_count = 0, st.skip_h_recovery_attempted = 0;
 				else {
-					if (ok) st.sync_trials = 0, st.skip_h_count = 0, st.phase = MB_FE_TRIAL;
+					if (ok) st.sync_trials = 0, st.skip_h_count = 0, st.coarse_off = 0.0, st.phase = MB_FE_TRIAL;  // (:1493: coarse_freq_offset = 0)
 					else st.phase = MB_FE_DONE;
 				}
 			}
@@ -660,6 +662,13 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 				else if (st.sync_trials == fe_c.trials_max && fe_c.use_last_time && st.last_delay != -1) {
 					st.delay = st.last_delay;
 					st.phase = MB_FE_POSTDELAY;
+				} else if (st.sync_trials == 1 && coarse_freq_sync) {
+					// trial 0 failed: Schmidl-Cox over the head of the buffer with the time-sync filter at fc - 30, fc, fc + 30 Hz (:949-983);
+					// the windows are computed on demand (k_fe_window, source 2), the time-sync base-band at fc stays as it is
+					st.cfs_i = 0, st.cfs_best = 0.0, st.cfs_best_off = 0.0, st.cfs_zero = 0.0, st.cfs_best_delay = st.delay;
+					st.win_f = fe_c.fc + -30.0;
+					request_sc(st, 2, 0, MB_NOFDM * (2 * pre + S) * 4, 100, pre);
+					st.phase = MB_FE_CFS_WAIT;
 				} else {
 					request_sc(st, st.cur_kind, (st.pream_symb_loc - 1) * sym, (pre + 4) * sym, 1, pre,
 						   st.sync_trials >= fe_c.trials_max ? fe_c.trials_max - 1 : st.sync_trials);  // = `want` of MB_FE_FINE_WAIT
@@ -667,7 +676,35 @@ __global__ void __launch_bounds__(kDecideThreads) k_fe_decide(MbFeState *__restr
 				}
 			}
 			__syncthreads();
-			if (st.phase == MB_FE_FINE_WAIT) wait = true;
+			if (st.phase == MB_FE_FINE_WAIT || st.phase == MB_FE_CFS_WAIT) wait = true;
+			break;
+		}
+		case MB_FE_CFS_WAIT: {  // one of the three runs has finished (:966-983); after the last: decision (:985-993) and the fine sync (:995-1013)
+			sc_result(c, vals, 0, &loc, &corr, red_v, red_k);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				st.sc_pending = 0;
+				const double off = st.cfs_i == 0 ? -30.0 : (st.cfs_i == 1 ? 0.0 : 30.0);
+				if (fabs(off) < 0.1) st.cfs_zero = corr;
+				if (corr > st.cfs_best) st.cfs_best = corr, st.cfs_best_off = off, st.cfs_best_delay = loc;
+				st.cfs_i++;
+				if (st.cfs_i < 3) {
+					st.win_f = fe_c.fc + (st.cfs_i == 1 ? 0.0 : 30.0);
+					request_sc(st, 2, 0, MB_NOFDM * (2 * pre + S) * 4, 100, pre);
+				} else {
+					if (fabs(st.cfs_best_off) > 1.0 && st.cfs_best > 0.5 && st.cfs_best > st.cfs_zero + 0.1) {
+						st.coarse_off = st.cfs_best_off;
+						st.delay = st.cfs_best_delay;
+						st.pream_symb_loc = st.delay / sym < 1 ? 1 : st.delay / sym;
+					}
+					// baseband_data_interpolated = the time-sync filter at the (possibly corrected) carrier; fine sync on it
+					st.cur_kind = 2, st.cur_f = fe_c.fc + st.coarse_off, st.win_f = st.cur_f;
+					request_sc(st, 2, (st.pream_symb_loc - 1) * sym, (pre + 4) * sym, 1, pre,
+						   st.sync_trials >= fe_c.trials_max ? fe_c.trials_max - 1 : st.sync_trials);
+					st.phase = MB_FE_FINE_WAIT;
+				}
+			}
+			wait = true;
 			break;
 		}
 		case MB_FE_FINE_WAIT: {
@@ -791,6 +828,7 @@ __global__ void __launch_bounds__(256) k_fe_moose(MbFeState *__restrict__ st_all
 	const int np2 = pre / 2 == 0 ? 1 : pre / 2;  // ofdm.cc:548-555
 	const bool use_last = st.sync_trials == fe_c.trials_max && fe_c.use_last_freq && st.last_freq != 0;  // :1108-1111
 	double fm = st.last_freq;
+	const double fbase = fe_c.fc + st.coarse_off;  // effective_fc (:1076): fc unless the coarse frequency search moved it
 	if (!use_last) {
 		if (tid < 128) {
 			double sn, cs;
@@ -802,7 +840,7 @@ __global__ void __launch_bounds__(256) k_fe_moose(MbFeState *__restrict__ st_all
 			double ar = 0, ai = 0;
 #pragma unroll
 			for (int j = 0; j < MB_FE_TAPS; j++) {
-				const double2 l = mixed_sample(x, o + MB_FE_TAPS / 2 - j, buf, carrier, true, 0.0);
+				const double2 l = mixed_sample(x, o + MB_FE_TAPS / 2 - j, buf, carrier, fbase == fe_c.fc, fbase);
 				ar = dadd(ar, dmul(l.x, fe_c.c_data[j]));
 				ai = dadd(ai, dmul(l.y, fe_c.c_data[j]));
 			}
@@ -853,7 +891,7 @@ __global__ void __launch_bounds__(256) k_fe_moose(MbFeState *__restrict__ st_all
 	if (tid == 0) {
 		const bool corrected = fabs(fm) > fe_c.ignore_limit;  // :1126
 		st.freq_offset_measured = fm;
-		st.cur_kind = 1, st.cur_f = corrected ? fe_c.fc + fm : fe_c.fc;
+		st.cur_kind = 1, st.cur_f = corrected ? fbase + fm : fbase;
 		st.extract_pending = 1;
 		st.phase = MB_FE_TAIL_WAIT;
 	}
@@ -1029,7 +1067,7 @@ static cudaError_t fe_step_t(const MbFeArgs &a, bool run_sc, cudaStream_t s)
 	}
 	k_fe_decide<T><<<a.n, kDecideThreads, 0, s>>>(a.st, static_cast<const T *>(a.x), a.buf, a.carrier, a.bbi, a.vals, a.vals_stride, a.energy_part, nblk,
 							a.tail_stats, a.tail_payload, a.tail_payload_stride, a.payload_out, a.frame_bytes, a.pre, a.S,
-							a.buffer_Nsymb, a.counters);
+							a.buffer_Nsymb, a.coarse_freq_sync, a.counters);
 	return cudaGetLastError();
 }
 

@@ -78,6 +78,7 @@ enum MbFePhase {
 	MB_FE_TAIL_WAIT,        // waiting for the tail's verdict
 	MB_FE_TRIALS_END,       // SKIP-H recovery check                           (:1436-1504)
 	MB_FE_REC_SKIPH,
+	MB_FE_CFS_WAIT,         // waiting for one of the three coarse-frequency runs of trial 1 (:949-1013, optional)
 	MB_FE_DONE
 };
 
@@ -92,18 +93,24 @@ struct MbFeState {
 	double last_freq, SNR, freq_offset, coarse_metric, signal_dbm, cur_f, freq_offset_measured;
 	int32_t last_delay, delay, sync_trials, message_decoded, iterations_done, crc, all_zeros;
 	int32_t phase, pream_symb_loc, skip_h_count, skip_h_recovery_attempted;
-	int32_t cur_kind;    // what baseband_data_interpolated holds: 0 = time-sync filter at fc (materialised), 1 = data filter at cur_f (on demand)
-	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for
+	int32_t cur_kind;    // what baseband_data_interpolated holds: 0 = time-sync filter at fc (materialised), 1 = data filter at cur_f (on demand), 2 = time-sync filter at cur_f (on demand: after the coarse frequency search)
+	int32_t sc_pending, sc_src, sc_start, sc_size, sc_step, sc_npos;  // the Schmidl-Cox run this capture waits for (sc_src: 0 the time-sync base-band, 1 a window of the data-filter base-band at cur_f, 2 a window of the time-sync filter at win_f)
 	int32_t slot;        // tail slot of the running trial
 	int32_t extract_pending;  // k_fe_moose has chosen the carrier, k_fe_extract_tiles still has to write the frame
 	int32_t sc_from;     // the pending run's location_to_return: only positions >= it can be selected (ofdm.cc:1821-1823, 1946-1958)
 	int32_t sc_pad;
 	unsigned long long sc_max_key;  // approximate maximum of the pending run (pass A of the two-pass Schmidl-Cox), order-preserving key
+	// the optional coarse frequency search of trial 1 (telecom_system.cc:949-1013; g_gui_state.coarse_freq_sync_enabled)
+	double coarse_off;   // coarse_freq_offset: 0 or +-30 Hz once the search has applied one; effective carrier = fc + coarse_off
+	double win_f;        // carrier of the time-sync-filter window a pending run of source 2 is computed at
+	double cfs_best, cfs_zero, cfs_best_off;  // best_correlation, zero_hz_correlation, best_offset
+	int32_t cfs_i, cfs_best_delay;            // which of {-30, 0, +30} Hz is running; best_delay
 };
 
 struct MbFeArgs {
 	const void *x;       // [n][buf] pass-band samples
 	int32_t x_format /* MERCURY_B200_SAMPLES_*: 0 f64, 1 f32, 2 i16, 3 i32 */, n, buf, pre, S, buffer_Nsymb, frame_bytes;
+	int32_t coarse_freq_sync;  // g_gui_state.coarse_freq_sync_enabled: the +-30 Hz search before trial 1 (win / pref_win then hold (2 pre + S) symbols)
 	const double2 *carrier;  // [>= buf] (cos, sin)(2 pi fc i Ts), host libm
 	MbFeState *st;       // [n]
 	double2 *bbi;        // [n][buf]  time-sync base-band

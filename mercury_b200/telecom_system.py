@@ -149,6 +149,11 @@ class TelecomSystemB200:
         self._check(self._L.mercury_b200_measure_signal_only_batch(self._h, _vp(x), _SAMPLE_FORMATS[x.dtype], x.shape[0], _vp(out)))
         return out
 
+    def set_coarse_freq_sync(self, enable):
+        """g_gui_state.coarse_freq_sync_enabled (gui_state.h:143): the optional +-30 Hz search before trial 1 of receive_byte()
+        (telecom_system.cc:949-1013).  Off by default."""
+        self._check(self._L.mercury_b200_set_coarse_freq_sync(self._h, int(bool(enable))))
+
     def set_mfsk_ctrl_mode(self, enable):
         """void set_mfsk_ctrl_mode(bool) (telecom_system.cc:1572-1575) -> get_active_nsymb()."""
         return int(self._L.mercury_b200_set_mfsk_ctrl_mode(self._h, int(bool(enable))))

@@ -35,7 +35,7 @@ PRELUDE = r'''
 #include "mercury_b200.h"
 #include <map>
 namespace {
-struct B200Link { mercury_b200_t *h = nullptr; int config = -999, iters = -1, ctrl = -1; };
+struct B200Link { mercury_b200_t *h = nullptr; int config = -999, iters = -1, ctrl = -1, cfs = -1; };
 mercury_b200_t *b200_of(cl_telecom_system *ts)
 {
 	static std::map<cl_telecom_system *, B200Link> links;
@@ -51,6 +51,10 @@ mercury_b200_t *b200_of(cl_telecom_system *ts)
 			exit(1);
 		}
 		l.config = ts->current_configuration, l.iters = ts->ldpc.nIteration_max, l.ctrl = -1;
+	}
+	if (l.cfs != (int)g_gui_state.coarse_freq_sync_enabled.load()) {  // the GUI's switch for the +-30 Hz search of trial 1 (:949)
+		l.cfs = (int)g_gui_state.coarse_freq_sync_enabled.load();
+		mercury_b200_set_coarse_freq_sync(l.h, l.cfs);
 	}
 	if (l.ctrl != (int)ts->mfsk_ctrl_mode) {
 		mercury_b200_set_mfsk_ctrl_mode(l.h, ts->mfsk_ctrl_mode ? 1 : 0);

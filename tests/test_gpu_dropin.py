@@ -102,3 +102,31 @@ def test_patched_reference_robust_modes(cfg, variant):
         want = plain.receive_byte2(cap, search_start_symb=start)
         got = patched.receive_byte2(cap, search_start_symb=start)
         _check((cfg, variant, case), want, got, exact_sync=(variant == "tail"))
+
+
+def test_patched_reference_forwards_the_coarse_frequency_search_switch():
+    """g_gui_state.coarse_freq_sync_enabled is a global of the reference's GUI state; the whole-body variant hands it to the library
+    (mercury_b200_set_coarse_freq_sync) on every call.  Captures whose outcome the search changes (carrier offset 11-13 Hz: trial 1 fails
+    as well, trial 2 decodes) must come out of the patched object as they come out of the plain one, switch on and off."""
+    _need(ref.SO_DROPIN_WHOLE)
+    plain, patched = ref.Ref(8, 50), ref.Ref(8, 50, so=ref.SO_DROPIN_WHOLE)
+    n = plain.capture_samples()
+    rng = np.random.default_rng(77)
+    caps = []
+    for df in (12.1, -11.4, 13.6, 3.0):
+        tx = plain.transmit_byte(rng.integers(0, 256, plain.frame_bytes))
+        d = int(rng.integers(6000, 30000))
+        cap = np.zeros(n)
+        cap[d:d + tx.size] += tx
+        caps.append((fc.freq_shift(cap, df) + rng.normal(0, 0.1, n)).astype(np.float32).astype(np.float64))
+    try:
+        trials = {}
+        for enable in (True, False):
+            plain.set_coarse_freq_sync(enable), patched.set_coarse_freq_sync(enable)
+            for i, cap in enumerate(caps):
+                want, got = plain.receive_byte2(cap), patched.receive_byte2(cap)
+                _check((8, "whole", f"cfs{int(enable)}", i), want, got, exact_sync=False)
+                trials[(enable, i)] = want["sync_trials"]
+        assert any(trials[(True, i)] != trials[(False, i)] for i in range(len(caps)))
+    finally:
+        plain.set_coarse_freq_sync(False), patched.set_coarse_freq_sync(False)

@@ -90,6 +90,49 @@ def test_receive_byte_scenarios(ts, cfg):
         _compare(oracle_out[i], one[0], out, None, f"cfg{cfg}/{cases[i]}/single")
 
 
+@pytest.mark.parametrize("cfg", [8, 13])
+def test_receive_byte_with_coarse_frequency_search(ts, cfg):
+    """g_gui_state.coarse_freq_sync_enabled (off by default): when trial 0 fails, receive_byte() runs Schmidl-Cox with the time-sync filter at
+    fc - 30, fc and fc + 30 Hz before trial 1 and fine-syncs on the time-sync base-band (telecom_system.cc:949-1013).  Captures with a
+    carrier offset of 10-14 Hz are where that changes the outcome (trial 1 then fails too, trial 2 decodes); offsets that would need the
+    +-30 Hz correction fail the Schmidl-Cox gate before any trial runs.  Every field against the reference with the flag on, then off again."""
+    if not ref.available():
+        pytest.skip("scenario frames come from the reference's transmit_byte (oracle/_ref not on this box)")
+    r = ref.Ref(cfg, 50)
+    ts.load_configuration(cfg, 50)
+    n = r.capture_samples()
+    rng = np.random.default_rng(40 + cfg)
+    caps = []
+    for df, sigma in ((12.1, 0.1), (-11.4, 0.1), (11.0, 0.1), (-10.7, 0.01), (13.6, 0.1), (-11.1, 0.1), (8.6, 0.1), (28.0, 0.01), (-12.0, 0.25), (0.0, 0.02)):
+        tx = r.transmit_byte(rng.integers(0, 256, r.frame_bytes))
+        d = int(rng.integers(6000, 30000))
+        cap = np.zeros(n)
+        cap[d:d + tx.size] += tx
+        caps.append((fc.freq_shift(cap, df) + rng.normal(0, sigma, n)).astype(np.float32).astype(np.float64))
+    for i, case in enumerate(("noise_heavy", "two_frames", "weak_frame", "tone_then_frame")):
+        caps.append(fc.make_capture(r, case, 900 + 10 * cfg + i)[0])
+    caps = np.stack(caps)
+    states = mb.new_receive_stats(len(caps))
+    states["delay_of_last_decoded_message"][:] = -1
+    try:
+        changed = 0
+        for enable in (True, False):
+            r.set_coarse_freq_sync(enable)
+            ts.set_coarse_freq_sync(enable)
+            want = [r.receive_byte2(c) for c in caps]
+            payload, st, bb = ts.receive_byte_batch(caps, states.copy(), want_baseband=True)
+            for i in range(len(caps)):
+                _compare(want[i], st[i], payload[i], bb[i], f"cfg{cfg}/cfs{int(enable)}/{i}")
+            if enable:
+                with_search = [w["sync_trials"] for w in want]
+            else:
+                changed = sum(a != b["sync_trials"] for a, b in zip(with_search, want))
+        assert changed >= 2  # the search was on the path of some captures
+    finally:
+        r.set_coarse_freq_sync(False)
+        ts.set_coarse_freq_sync(False)
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "frontend_*.npz"))))
 def test_receive_byte_reference_fixture(ts, path):
     g = np.load(path)

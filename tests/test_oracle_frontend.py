@@ -56,7 +56,7 @@ def test_port_against_frontend_fixture(path):
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libmercury_ref.so not built")
 def test_optional_coarse_frequency_search_restated():
     """g_gui_state.coarse_freq_sync_enabled (off by default): the +-30 Hz search of trial 1 (telecom_system.cc:949-1013) is restated in the
-    oracle and pinned here; the product does not build it.  A carrier offset large enough to need it (> 23 Hz, half a
+    oracle and pinned here (the product's version: tests/test_gpu_frontend.py).  A carrier offset large enough to need it (> 23 Hz, half a
     carrier spacing) already fails the Schmidl-Cox gates before any trial runs -- the real part of the lag-1024 correlation turns negative --
     so the branch is only reachable where Moose alone would have coped."""
     r, p = ref.Ref(8, 50), port.Port(8, 50)
