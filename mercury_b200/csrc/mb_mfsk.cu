@@ -19,10 +19,14 @@ __device__ __forceinline__ int carrier_bin(int c) { return c < MB_NC / 2 ? c + M
 
 // 16 threads per symbol (the OFDM demodulator's FFT-256: two radix-4x4 16-point DFTs in registers around a padded shared-memory
 // transpose, twiddles by running product, second DFT pruned to the 4 outputs per thread that reach the 50 active carriers);
-// a 256-thread CTA handles 16 symbols per round.
-constexpr int kSymPerRound = 16;
+// a 128-thread CTA handles 8 symbols per round (measured on B200, ms per 8,192 ROBUST_0 / ROBUST_2 frames: 16 per round 1.58 / 0.87,
+// 8 per round 1.46 / 0.76, 4 per round 1.49 / 0.77 -- like the OFDM demodulator, smaller CTAs overlap loads and arithmetic at a finer grain).
+#ifndef MB_MFSK_SYM_PER_ROUND
+#define MB_MFSK_SYM_PER_ROUND 8
+#endif
+constexpr int kSymPerRound = MB_MFSK_SYM_PER_ROUND;
 
-__global__ void __launch_bounds__(256) k_mfsk_demod(const MbMfskArgs a)
+__global__ void __launch_bounds__(16 * kSymPerRound) k_mfsk_demod(const MbMfskArgs a)
 {
 	__shared__ float2 scr[kSymPerRound][16 * 17];
 	__shared__ float E[kSymPerRound][MB_NC + 2];
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(256) k_mfsk_patterns(const double *__restrict_
 
 cudaError_t mb_launch_mfsk_demod(const MbMfskArgs &a, size_t n_frames, cudaStream_t s)
 {
-	k_mfsk_demod<<<(unsigned)n_frames, 256, 0, s>>>(a);
+	k_mfsk_demod<<<(unsigned)n_frames, 16 * kSymPerRound, 0, s>>>(a);
 	return cudaGetLastError();
 }
 
