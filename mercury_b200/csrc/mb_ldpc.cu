@@ -643,13 +643,11 @@ __device__ __forceinline__ int2 retire_slot(const MbLdpcArgs &a, const Smem s, c
 #define MB_T_DECL
 #define MB_T(i)
 #endif
-#ifdef MB_LDPC_MAXNREG
-#define MB_LDPC_BOUNDS __maxnreg__(MB_LDPC_MAXNREG)
-#else
-#define MB_LDPC_BOUNDS __launch_bounds__(kThreads, MB_LDPC_MIN_CTAS)
-#endif
-template <int ALGO>
-__global__ void MB_LDPC_BOUNDS mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
+// MINCTAS: resident pairs per SM the registers are budgeted for -- MB_LDPC_MIN_CTAS (3: 80 registers) wherever shared memory lets three
+// pairs in, 2 (up to 128 registers) for rate 14/16, whose 77 KB per pair leave room for two anyway (18.9 against 19.4 ms per 65,536
+// mode-16 frames at 20 iterations).
+template <int ALGO, int MINCTAS>
+__global__ void __launch_bounds__(kThreads, MINCTAS) mb_ldpc_kernel(const __grid_constant__ MbLdpcArgs a)
 {
 	if ((unsigned)__cvta_generic_to_shared(mb_smem) != kSmemBase) __trap();  // the immediates of lds2i assume it
 	const MbRate &rt = a.rate;
@@ -906,8 +904,10 @@ size_t mb_ldpc_smem_bytes(int c_slots)
 
 namespace {
 typedef void (*LdpcKernel)(const MbLdpcArgs);
-const LdpcKernel kKernels[2] = {mb_ldpc_kernel<0>, mb_ldpc_kernel<1>};  // sum-product / min-sum
+const LdpcKernel kKernels[2][2] = {{mb_ldpc_kernel<0, MB_LDPC_MIN_CTAS>, mb_ldpc_kernel<0, 2>},   // sum-product: three pairs per SM / two
+				   {mb_ldpc_kernel<1, MB_LDPC_MIN_CTAS>, mb_ldpc_kernel<1, 2>}};  // min-sum
 int g_ctas_per_sm[2][MB_NRATES] = {};
+int g_variant[2][MB_NRATES] = {};  // which of the two register budgets a rate runs with
 int g_sms = 0;
 }  // namespace
 
@@ -933,7 +933,7 @@ cudaError_t mb_ldpc_init()
 	}
 	e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
 	if (e != cudaSuccess) return e;
-	for (LdpcKernel k : kKernels) {
+	for (LdpcKernel k : {kKernels[0][0], kKernels[0][1], kKernels[1][0], kKernels[1][1]}) {
 		e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 		if (e != cudaSuccess) return e;
 		int carve = MB_LDPC_LCH_SMEM ? (int)cudaSharedmemCarveoutMaxShared : 77;  // 196 KB of the 256 KB array: three pairs of up to 64 KB + 60 KB of L1
@@ -951,9 +951,14 @@ int mb_ldpc_ctas_per_sm(int algo, int rate_idx, int rate_num, int c_slots)
 	const int ki = algo != 0 ? 1 : 0;
 	(void)rate_num;
 	if (g_ctas_per_sm[ki][rate_idx] == 0) {
-		int n = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernels[ki], kThreads, mb_ldpc_smem_bytes(c_slots)) != cudaSuccess || n < 1) n = 1;
+		int n = 0, v = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernels[ki][0], kThreads, mb_ldpc_smem_bytes(c_slots)) != cudaSuccess || n < 1) n = 1;
+		if (n <= 2 && MB_LDPC_MIN_CTAS > 2) {  // shared memory admits two pairs: take the kernel whose registers are budgeted for two
+			int n2 = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2, kKernels[ki][1], kThreads, mb_ldpc_smem_bytes(c_slots)) == cudaSuccess && n2 >= n) v = 1, n = n2;
+		}
 		g_ctas_per_sm[ki][rate_idx] = n;
+		g_variant[ki][rate_idx] = v;
 	}
 	return g_ctas_per_sm[ki][rate_idx];
 }
@@ -963,9 +968,9 @@ cudaError_t mb_launch_ldpc(const MbLdpcArgs &a, size_t n_frames, int algo, cudaS
 	if (n_frames == 0) return cudaSuccess;
 	if (!a.queue || !a.lch_scratch || n_frames > 0x7fff0000ull) return cudaErrorInvalidValue;  // frame tickets are 31-bit
 	const size_t smem = mb_ldpc_smem_bytes(a.rate.c_slots);
-	const LdpcKernel k = kKernels[algo != 0 ? 1 : 0];
-	const int rate_idx = mb_rate_index(a.rate.rate_num);
-	const size_t resident = (size_t)g_sms * (size_t)mb_ldpc_ctas_per_sm(algo, rate_idx < 0 ? 0 : rate_idx, a.rate.rate_num, a.rate.c_slots);
+	const int rate_idx = std::max(0, mb_rate_index(a.rate.rate_num));
+	const size_t resident = (size_t)g_sms * (size_t)mb_ldpc_ctas_per_sm(algo, rate_idx, a.rate.rate_num, a.rate.c_slots);
+	const LdpcKernel k = kKernels[algo != 0 ? 1 : 0][g_variant[algo != 0 ? 1 : 0][rate_idx]];
 	MbLdpcArgs b = a;
 	b.n_frames = n_frames;
 	b.edge_var = reinterpret_cast<const uint16_t *>(a.blob + a.rate.off_edge_varb);
