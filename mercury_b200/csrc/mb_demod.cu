@@ -162,7 +162,7 @@ __device__ __forceinline__ void demap_scatter_qam32(const float2 z, const float 
 template <int S>
 struct Geo {
 	// Symbols transformed per round = threads per CTA / 16.  Measured on B200 (tools/r2_tune10.sh, ms per 65,536 frames): a 24-symbol frame
-	// in 4 rounds of 6 (96 threads, 7 CTAs per SM at 92 registers) 0.864 against 0.927 in 2 rounds of 12 and 0.886 / 0.967 / 1.10 in rounds
+	// in 4 rounds of 6 (96 threads, 6 CTAs per SM at 94 registers) 0.864 against 0.927 in 2 rounds of 12 and 0.886 / 0.967 / 1.10 in rounds
 	// of 8 / 4 / 3; a 12-symbol frame in 2 rounds of 6 at 80 registers 0.461 against 0.527 in one round (0.47 / 0.51 in rounds of 4 / 3);
 	// 48-symbol frames stay at 12 (6: 1.84, 8: 1.79 against 1.72), 16-symbol frames at 8 (4: 0.65, 16: 0.73 against 0.63), 9-symbol
 	// frames at 9 (3: 0.42 against 0.43, 1: 0.61).  Small CTAs overlap one frame's loads with another's arithmetic at a finer grain.
@@ -170,7 +170,7 @@ struct Geo {
 	static constexpr int NCH = S / SC;                                                // rounds per frame
 	static constexpr int T = (SC * 16 + 31) / 32 * 32;                                // threads per CTA
 	static constexpr int NW = T / 32;
-	// resident CTAs per SM the register file is budgeted for (96 threads: 92 registers for the 24-symbol frames, 80 for the 12-symbol ones)
+	// resident CTAs per SM the register file is budgeted for (96 threads: 94 registers for the 24-symbol frames, 80 for the 12-symbol ones)
 	static constexpr int MINB = T <= 96 ? (S == 12 ? 7 : 6) : (T <= 160 ? 6 : (T <= 192 ? 5 : 3));
 	static constexpr int CELLS = S * MB_NC;
 	static constexpr int NPIL = (S * MB_NC + 2) / 3;   // pilots: cells with s%3 == c%3
