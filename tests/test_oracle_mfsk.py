@@ -135,7 +135,12 @@ def test_mfsk_control_frames_bit_exact(cfg):
             assert np.array_equal(a[k], b[k]), (sg, k)
     a, sa = r.transmit_byte2(pl, 0)
     b, sb = p.transmit_byte2(pl, 0)
-    assert sa == sb == (4 + na) * 1088 and np.array_equal(a, b)
+    # The reference leaves whatever its TX buffers held before behind the active part of a control frame (seen: denormal residue of earlier
+    # objects, a different one from run to run) and its FIRs smear that over the last 96 active samples; the restatement has silence there.
+    # Bit-exact on the part that is defined.
+    L = (4 + na) * 1088
+    assert sa == sb == L and np.array_equal(a[:L - 100], b[:L - 100]) and not b[L + 200:].any()
+    assert np.abs(a[L - 100:L] - b[L - 100:L]).max() <= 1e-9 * np.abs(b).max()
     n = r.capture_samples()
     cap = np.zeros(n)
     cap[20 * 1088 + 17:20 * 1088 + 17 + (4 + na) * 1088] += b[:(4 + na) * 1088]
